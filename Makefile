@@ -1,0 +1,27 @@
+# Builds libswrt.so (sm_100a only) and the CPU oracle's C restatement.
+NVCC      ?= nvcc
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
+CSRC      := swraytracing_b200/csrc
+OBJ       := build
+LIB       := swraytracing_b200/libswrt.so
+ORACLE    := oracle/build/liboracle.so
+
+all: $(LIB) $(ORACLE)
+
+$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/swrt_internal.h include/swrt.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)/spectral_kernels.o $(OBJ)/lagrange_kernels.o $(OBJ)/misc_kernels.o $(OBJ)/swrt_api.o
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+
+$(ORACLE): oracle/swrt_oracle.c
+	@mkdir -p oracle/build
+	$(CC) -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -o $@ $< -lm
+
+clean:
+	rm -rf $(OBJ) $(LIB) oracle/build
+
+.PHONY: all clean

@@ -1,0 +1,147 @@
+/* swrt.h -- C ABI of libswrt.so: B200-native engine for SWRaytracing's packet hot path.
+ *
+ * The reference (ndefilippis/SWRaytracing) is MATLAB and has no FFI; its callers are MATLAB
+ * scripts that invoke a handful of functions by name.  Each entry point below replaces one of
+ * those function-level interfaces (cited as file:line relative to the reference tree); the MEX
+ * gateway (matlab/swrt_mex.c) and the Python ctypes mirror (swraytracing_b200/engine.py) bind
+ * exactly these symbols.  See INTEGRATION.md for the reference-side stubs.
+ *
+ * Conventions
+ *   - all arrays are caller-owned HOST pointers unless the name says _dev; fp64; MATLAB
+ *     column-major; complex data as separate real/imag arrays (Octave's MEX API is
+ *     non-interleaved);
+ *   - every function returns 0 on success, <0 on error; swrt_last_error() gives the message;
+ *     nothing throws or longjmps; no caller pointer is kept after return;
+ *   - one host thread drives a handle; a handle owns one CUDA device and the device-resident
+ *     SoA packet state (x,y,k,l,a) plus the flow-coefficient stacks;
+ *   - there is NO CPU fallback: without a CUDA device every call fails with SWRT_ERR_CUDA.
+ */
+#ifndef SWRT_H
+#define SWRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWRT_VERSION 100
+
+/* error codes */
+#define SWRT_OK            0
+#define SWRT_ERR_ARG      -1   /* bad argument (null pointer, size mismatch, bad enum) */
+#define SWRT_ERR_STATE    -2   /* call order (no flow set, no packets set, wrong mode) */
+#define SWRT_ERR_CUDA     -3   /* CUDA runtime / no device */
+#define SWRT_ERR_ALLOC    -4   /* out of device or host memory */
+#define SWRT_ERR_NCCL     -5
+
+/* field-evaluation mode */
+#define SWRT_MODE_SPECTRAL  0  /* exact Fourier-series sum (dense DMMA contraction)            */
+#define SWRT_MODE_LAGRANGE6 1  /* the reference's 6x6 Lagrange stencil, interpolate.m:12-49     */
+
+/* integrator */
+#define SWRT_SCHEME_LEAPFROG   0  /* ode_symplectic.m:13-21,33-37                               */
+#define SWRT_SCHEME_RK4_PACKET 1  /* ray_trace_sw/step_packet.m:37-78                           */
+#define SWRT_SCHEME_RK4_XKA    2  /* ray_trace_sw/step_packet_xka.m:38-91 (+ cg_sw.m:15-31)     */
+
+/* histogram kind */
+#define SWRT_HIST_INTRINSIC 0  /* omega = sqrt(f^2 + gH K^2), analysis/load_data.m:33           */
+#define SWRT_HIST_ABSOLUTE  1  /* Omega = omega + U.k, symplectic_full_fourier.m:41,55          */
+
+typedef struct swrt_handle swrt_handle;
+
+typedef struct swrt_params {
+    int32_t nx;        /* grid size (even); spectral arrays are (nx-1) x (nx/2), g2k.m:5-9      */
+    int32_t mode;      /* SWRT_MODE_*                                                           */
+    int32_t device;    /* CUDA device ordinal                                                   */
+    int32_t reserved;
+    double  L;         /* domain side; dx = L/nx (qgsw_raytrace.m:13-14)                        */
+    double  f;         /* Coriolis parameter                                                    */
+    double  gH;        /* Cg^2 = C0^2 (ode_symplectic.m:10-11)                                  */
+    double  bump;      /* Lagrange "bump": 1e-13 (interpolate.m:13) or 1e-10 (interpolate_par)  */
+} swrt_params;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+int  swrt_version(void);
+int  swrt_device_count(void);
+int  swrt_create(const swrt_params* p, swrt_handle** h);
+int  swrt_destroy(swrt_handle* h);
+/* message of the last failure on this handle (h may be NULL: last failure of swrt_create) */
+const char* swrt_last_error(const swrt_handle* h);
+
+/* ---- background flow (slots 0 and 1 = the two time frames of interpolate_U.m:5-17) --------- */
+/* psi-hat in g2k layout; builds u,v,ux,uy,vx,vy = SpectralScheme.m:18-25 / grid_U.m:3-9 with
+ * wavenumbers kappa*kx, kappa*ky (kappa = 2*pi/L) and adds u_mean to u (grid_U.m:11).          */
+int swrt_set_flow_spectral(swrt_handle* h, int slot, const double* psik_re, const double* psik_im,
+                           int nkx, int nky, double u_mean);
+/* caller-supplied coefficient planes in the order u,v,ux,uy,vx,vy[,H]; nplanes = 6 or 7.
+ * Plane 7 holds the coefficients of H = 1 + eta_g (raytrace_sw.m:44-45), mean included.        */
+int swrt_set_flow_planes_spectral(swrt_handle* h, int slot, const double* const* planes_re,
+                                  const double* const* planes_im, int nplanes, int nkx, int nky);
+/* gridded planes nx x nx (column-major, x fastest) = grid_U.m:11-17 output / SpectralScheme
+ * fields; H may be NULL.  In SPECTRAL mode the grids are transformed with g2k on the device.   */
+int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* v,
+                       const double* ux, const double* uy, const double* vx, const double* vy,
+                       const double* H, int nx);
+
+/* ---- packets ------------------------------------------------------------------------------ */
+int swrt_set_packets(swrt_handle* h, int64_t n, const double* x, const double* y,
+                     const double* k, const double* l, const double* a /* may be NULL -> 1 */);
+int swrt_get_packets(swrt_handle* h, double* x, double* y, double* k, double* l,
+                     double* a /* may be NULL */);
+int64_t swrt_num_packets(const swrt_handle* h);
+/* device-resident SoA buffers (for callers that already live on the GPU, e.g. torch) */
+int swrt_packets_alloc_dev(swrt_handle* h, int64_t n);
+int swrt_packets_dev(swrt_handle* h, double** x, double** y, double** k, double** l, double** a);
+
+/* ---- evaluation --------------------------------------------------------------------------- */
+/* U,V,Ux,Uy,Vx,Vy at the current packet positions, flow = (1-alpha)*slot0 + alpha*slot1
+ * (interpolate_U.m:19-23; SpectralScheme.U / grad_U, SpectralScheme.m:45-68).  Any output
+ * pointer may be NULL.  If slot 1 is unset alpha must be 0.                                    */
+int swrt_eval(swrt_handle* h, double alpha, double* U, double* V, double* Ux, double* Uy,
+              double* Vx, double* Vy);
+/* the same at caller-given positions (n host doubles each); does not touch the packet state.  */
+int swrt_eval_at(swrt_handle* h, double alpha, int64_t n, const double* x, const double* y,
+                 double* U, double* V, double* Ux, double* Uy, double* Vx, double* Vy, double* H);
+/* odefun of qgsw_raytrace.m:259-265: dx/dt = U + Cg k/omega, dk/dt = -(grad U)^T k             */
+int swrt_rhs(swrt_handle* h, double alpha, double* dxdt, double* dydt, double* dkdt, double* dldt);
+/* standalone FI = interpolate(x,y,F,dx,dy) (interpolate.m:1-50): one nx x ny grid, n points.   */
+int swrt_interpolate(int device, const double* x, const double* y, int64_t n, const double* F,
+                     int nx, int ny, double dx, double dy, double bump, double* FI);
+
+/* ---- stepping ----------------------------------------------------------------------------- */
+/* nsteps fused steps of the chosen scheme; step j evaluates the flow at alpha0 + j*dalpha.    */
+int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha);
+
+/* ---- diagnostics -------------------------------------------------------------------------- */
+/* histcounts(omega, edges) (analysis/load_data.m:39-47): counts[nedges-1], bin i = [e_i,e_i+1),
+ * last bin closed; accumulate != 0 adds to counts instead of overwriting.                      */
+int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges, int nedges,
+                    uint64_t* counts, int accumulate);
+/* out[0]=sum omega, out[1]=sum Omega (omega+U.k), out[2]=max omega, out[3]=min omega,
+ * out[4]=number of non-finite packets, out[5]=sum a, out[6]=n, out[7]=sum omega*a              */
+int swrt_diag(swrt_handle* h, double alpha, double out[8]);
+/* per-packet intrinsic and absolute frequency (symplectic_full_fourier.m:41,54-56)             */
+int swrt_omega(swrt_handle* h, double alpha, double* omega, double* Omega_abs);
+
+/* ---- spectral <-> grid kit on the device (setup, not hot path) ----------------------------- */
+/* fk = g2k(fg) (g2k.m:5-9) and fg = k2g(fk) (k2g.m:5-6, fulspec.m:10-19), column-major.         */
+int swrt_g2k(int device, const double* fg, int nx, double* fk_re, double* fk_im);
+int swrt_k2g(int device, const double* fk_re, const double* fk_im, int nx, double* fg);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+/* number of kernel launches issued by this handle since creation / since the last reset        */
+int64_t swrt_launch_count(swrt_handle* h, int reset);
+/* milliseconds spent in the dominant kernel of the most recent swrt_step / swrt_eval call,
+ * measured with CUDA events on the handle's stream; nlaunch receives how many launches         */
+double  swrt_last_kernel_ms(swrt_handle* h, int* nlaunch);
+/* executed real fp64 flops (spectral) or gathered bytes (Lagrange) per packet per evaluation   */
+double  swrt_work_per_eval(const swrt_handle* h, int nplanes);
+int     swrt_synchronize(swrt_handle* h);
+/* tuning knob: 1 or 2 m-tiles per warp in the spectral kernel (0 = automatic)                  */
+int     swrt_set_tuning(swrt_handle* h, int mtiles, int reserved);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWRT_H */

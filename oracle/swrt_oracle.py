@@ -1,0 +1,678 @@
+"""CPU oracle for the SWRaytracing packet hot path -- TEST INFRASTRUCTURE ONLY.
+
+This module is a numpy restatement of the reference's MATLAB algorithm for the one hot path
+this repository accelerates (evaluate U, V, grad U at every wave packet + integrator step).
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it; the product (``swraytracing_b200``) never does.
+
+Parity status: **parity unpinned** at the MATLAB-builtin boundaries.  The reference
+(/root/reference, ~9k lines of MATLAB) ships no tests, no golden vectors and no stored outputs,
+and neither MATLAB nor GNU Octave exists in this image, so the reference cannot be executed
+here.  The oracle is pinned instead by the known-answer tests derived from the reference's own
+scripts (``tests/test_oracle_kat.py``): grid-node identity of
+``interpolate``, the closed-form Childress-Soward flow of ``ray_trace_sw/raytrace.m:31-37``,
+the zero-flow analytic trajectory, the direct trig-sum pattern of
+``scratch/fourier_interpolate_test.m:92-136``, the ``g2k(k2g(.))`` round trip, and the
+Omega-drift bound of ``symplectic_full_fourier.m:54-57``.
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+Array layout follows MATLAB: ``F[ix, iy]`` with x the first index; in memory the oracle keeps
+numpy C-order arrays and converts explicitly where the C ABI wants column-major.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+# --------------------------------------------------------------------------------------------
+# MATLAB numeric primitives
+# --------------------------------------------------------------------------------------------
+
+def matlab_mod(a, m):
+    """MATLAB ``mod(a,m)`` for m>0: ``a - floor(a/m)*m`` in [0,m]; ``mod(-tiny,m)`` rounds to m.
+    numpy's ``np.mod`` on floats (fmod + sign fix-up) produces the same doubles."""
+    return np.mod(a, m)
+
+
+def matlab_linspace(a, b, n):
+    """MATLAB ``linspace(a,b,n)``: ``a + (0:n-1)*(b-a)/(n-1)`` with the end point forced to b
+    (used by analysis/load_data.m:39)."""
+    a = float(a); b = float(b)
+    out = a + np.arange(n, dtype=np.float64) * (b - a) / (n - 1)
+    out[-1] = b
+    return out
+
+
+def matlab_rand_stream(seed):
+    """``rng(seed)`` = mt19937ar; ``rand`` yields the same 53-bit doubles as numpy's legacy
+    RandomState (qgsw_raytrace.m:23, symplectic_full_fourier.m:11)."""
+    return np.random.RandomState(seed)
+
+
+def histcounts(w, edges):
+    """``histcounts(w, edges)`` (analysis/load_data.m:47): bin i counts edges[i] <= w < edges[i+1],
+    the last bin also includes w == edges[-1]; out-of-range and NaN values are dropped."""
+    w = np.asarray(w, dtype=np.float64).ravel()
+    edges = np.asarray(edges, dtype=np.float64)
+    nb = len(edges) - 1
+    counts = np.zeros(nb, dtype=np.uint64)
+    ok = ~np.isnan(w) & (w >= edges[0]) & (w <= edges[-1])
+    w = w[ok]
+    idx = np.searchsorted(edges, w, side="right") - 1   # edges[idx] <= w < edges[idx+1]
+    idx[w == edges[-1]] = nb - 1
+    idx = idx[(idx >= 0) & (idx < nb)]
+    np.add.at(counts, idx, 1)
+    return counts
+
+
+# --------------------------------------------------------------------------------------------
+# Spectral <-> grid kit
+# --------------------------------------------------------------------------------------------
+
+def wavenumbers(nx):
+    """``[kx_,ky_] = ndgrid(-kmax:kmax, 0:kmax)`` (SpectralScheme.m:12-13, qgsw_raytrace.m:18-20)."""
+    kmax = nx // 2 - 1
+    kx = np.arange(-kmax, kmax + 1, dtype=np.float64)[:, None]
+    ky = np.arange(0, kmax + 1, dtype=np.float64)[None, :]
+    kx_, ky_ = np.broadcast_arrays(kx, ky)
+    return kx_.copy(), ky_.copy()
+
+
+def g2k(fg):
+    """qg_flow_ray_trace/g2k.m:5-9: ``fftshift(fft2(fg))/nx^2`` restricted to rows 2:end
+    (kx=-kmax..kmax) and columns kmax+2:end (ky=0..kmax)."""
+    nx = fg.shape[0]
+    kmax = nx // 2 - 1
+    fkt = np.fft.fftshift(np.fft.fft2(fg)) / nx**2
+    return fkt[1:, kmax + 1:].copy()
+
+
+def fulspec(fk):
+    """qg_flow_ray_trace/fulspec.m:10-19: fill the lower half plane by conjugate symmetry,
+    zero the Nyquist row/column, and conjugate-symmetrise the ky=0 column from its kx>0 half."""
+    nkx, nky = fk.shape
+    nx = nkx + 1
+    kmax = nky - 1
+    fkf = np.zeros((nx, nx), dtype=np.complex128)
+    fup = fk.astype(np.complex128).copy()
+    # fup(kmax:-1:1,1) = conj(fup(kmax+2:nkx,1))
+    fup[kmax - 1::-1, 0] = np.conj(fup[kmax + 1:nkx, 0])
+    # fdn = conj(fup(nkx:-1:1, nky:-1:2))
+    fdn = np.conj(fup[::-1, nky - 1:0:-1])
+    fkf[1:nx, nky:nx] = fup
+    fkf[1:nx, 1:nky] = fdn
+    return fkf
+
+
+def k2g(fk):
+    """qg_flow_ray_trace/k2g.m:5-6: ``nx^2*ifft2(ifftshift(fulspec(fk)))``.  MATLAB's ifft2 returns
+    a real matrix for exactly conjugate-symmetric input except for Im F(0,0); numpy leaves ~1e-17
+    imaginary residue, so the real part is taken."""
+    nx = fk.shape[0] + 1
+    return (nx**2 * np.fft.ifft2(np.fft.ifftshift(fulspec(fk)))).real
+
+
+def symmetrise_ky0(fk):
+    """The ky=0 treatment of fulspec.m:16 applied to a half-plane array: F(-kx,0) := conj F(kx,0),
+    and Im F(0,0) dropped (it cannot contribute to the real field k2g returns)."""
+    fk = np.array(fk, dtype=np.complex128)
+    nkx = fk.shape[0]
+    kmax = (nkx - 1) // 2
+    fk[kmax - 1::-1, 0] = np.conj(fk[kmax + 1:nkx, 0])
+    fk[kmax, 0] = fk[kmax, 0].real
+    return fk
+
+
+def velocity_planes_k(psik, kx_, ky_):
+    """Spectral velocity and gradient planes from psi-hat:
+    SpectralScheme.m:18-25 (= grid_U.m:3-9): u=-i ky psi, v=i kx psi, ux=i kx u, uy=i ky u, ..."""
+    uk = -1j * ky_ * psik
+    vk = 1j * kx_ * psik
+    return [uk, vk, 1j * kx_ * uk, 1j * ky_ * uk, 1j * kx_ * vk, 1j * ky_ * vk]
+
+
+def grid_U(qk, K_d2, K2, kx_, ky_, shear_strength=0.0):
+    """qg_flow_ray_trace/grid_U.m:2-17: psi=-q/(K_d2+K2); six k2g's; mean shear added to u.
+    Returns dict with keys u,v,ux,uy,vx,vy (the reference's struct field names)."""
+    psik = -qk / (K_d2 + K2)
+    uk, vk, ukx, uky, vkx, vky = velocity_planes_k(psik, kx_, ky_)
+    return {"u": k2g(uk) + shear_strength, "v": k2g(vk), "ux": k2g(ukx), "uy": k2g(uky),
+            "vx": k2g(vkx), "vy": k2g(vky)}
+
+
+def grid_U_planes_k(qk, K_d2, K2, kx_, ky_, shear_strength=0.0):
+    """Spectral-coefficient form of grid_U: the same six planes before k2g; the mean shear is the
+    (kx,ky)=(0,0) coefficient of u (grid_U.m:11)."""
+    psik = -qk / (K_d2 + K2)
+    planes = velocity_planes_k(psik, kx_, ky_)
+    kmax = (qk.shape[0] - 1) // 2
+    planes[0] = planes[0].copy()
+    planes[0][kmax, 0] += shear_strength
+    return planes
+
+
+# --------------------------------------------------------------------------------------------
+# interpolate.m -- 6x6 Lagrange stencil (reference semantics of "field at packet")
+# --------------------------------------------------------------------------------------------
+
+IORD = 2
+BUMP_LIVE = 1e-13     # ray_trace_sw/interpolate.m:13
+BUMP_PAR = 1e-10      # interpolate_par.m:13
+
+
+def _lagrange_weights(a, bump):
+    """interpolate.m:33-41: w_i = prod_{j != i, j=-2..3} (a - j + bump)/(j - i), multiply then
+    divide, j ascending.  ``a`` is an array of fractional positions; returns (6, n)."""
+    w = np.ones((2 * (IORD + 1),) + a.shape, dtype=np.float64)
+    for i in range(-IORD, IORD + 2):
+        for j in range(-IORD, IORD + 2):
+            if i != j:
+                w[i + IORD] = w[i + IORD] * (a - j + bump) / (j - i)
+    return w
+
+
+def interpolate(x, y, F, dx, dy, bump=BUMP_LIVE):
+    """ray_trace_sw/interpolate.m:12-49 (vectorised over packets, same per-packet operation
+    order): xl=mod(x/dx,nx); i0=1+floor(xl); ax=1+xl-i0; 36-term sum, i outer / j inner,
+    term (wx_i*wy_j)*F(ig,jg); BOTH indices wrap with nx (interpolate.m:45-46)."""
+    x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    shp = x.shape
+    x = x.ravel(); y = y.ravel()
+    nx, ny = F.shape
+    xl = matlab_mod(x / dx, nx)
+    yl = matlab_mod(y / dy, ny)
+    i0 = 1 + np.floor(xl)
+    j0 = 1 + np.floor(yl)
+    ax = 1 + xl - i0
+    ay = 1 + yl - j0
+    wx = _lagrange_weights(ax, bump)
+    wy = _lagrange_weights(ay, bump)
+    i0 = i0.astype(np.int64); j0 = j0.astype(np.int64)
+    FI = np.zeros_like(x)
+    for i in range(-IORD, IORD + 2):
+        ig = np.mod(i0 + i - 1, nx)            # zero-based (reference: 1 + mod(...))
+        for j in range(-IORD, IORD + 2):
+            jg = np.mod(j0 + j - 1, nx)        # wraps with nx, as the reference does
+            FI = FI + wx[i + IORD] * wy[j + IORD] * F[ig, jg]
+    return FI.reshape(shp)
+
+
+def interpolate_par(x, y, F, dx, dy):
+    """interpolate_par.m:12-51: the same stencil with bump=1e-10."""
+    return interpolate(x, y, F, dx, dy, bump=BUMP_PAR)
+
+
+def interpolate_U(bf1, bf2, alpha, x, h):
+    """qg_flow_ray_trace/interpolate_U.m:1-24.  x: (Np,2).  Returns U (Np,2) and dict nablaU with
+    u_x,u_y,v_x,v_y; linear blend (1-alpha)*F1 + alpha*F2 of twelve interpolations."""
+    xx = x[:, 0]; yy = x[:, 1]
+    U1 = np.stack([interpolate(xx, yy, bf1["u"], h, h), interpolate(xx, yy, bf1["v"], h, h)], axis=1)
+    U2 = np.stack([interpolate(xx, yy, bf2["u"], h, h), interpolate(xx, yy, bf2["v"], h, h)], axis=1)
+    U = (1 - alpha) * U1 + alpha * U2
+    nablaU = {}
+    for name, key in (("u_x", "ux"), ("u_y", "uy"), ("v_x", "vx"), ("v_y", "vy")):
+        g1 = interpolate(xx, yy, bf1[key], h, h)
+        g2 = interpolate(xx, yy, bf2[key], h, h)
+        nablaU[name] = (1 - alpha) * g1 + alpha * g2
+    return U, nablaU
+
+
+# --------------------------------------------------------------------------------------------
+# Exact trig-sum evaluation (the SPECTRAL mode's oracle)
+# --------------------------------------------------------------------------------------------
+
+def spectral_eval(x, y, fk, dx, nx, dtype=np.longdouble):
+    """Direct Fourier-series sum of a half-plane coefficient array at packet positions (pattern:
+    scratch/fourier_interpolate_test.m:125-136, generalised to complex coefficients):
+
+      F = sum_kx Fs(kx,0) e^{i kx tx} + 2 Re sum_{ky>=1} sum_kx F(kx,ky) e^{i(kx tx + ky ty)},
+      tx = 2 pi xl/nx, xl = mod(x/dx, nx)   (the reduced coordinate of interpolate.m:21-22).
+
+    Accumulates in ``dtype`` (long double by default) so the result is good to ~1e-17 relative."""
+    x = np.asarray(x, dtype=np.float64).ravel(); y = np.asarray(y, dtype=np.float64).ravel()
+    fk = symmetrise_ky0(fk)
+    nkx, nky = fk.shape
+    kmax = nky - 1
+    xl = matlab_mod(x / dx, nx).astype(dtype)
+    yl = matlab_mod(y / dx, nx).astype(dtype)
+    two_pi = 2 * np.arccos(dtype(-1))
+    tx = two_pi * xl / nx
+    ty = two_pi * yl / nx
+    kx = np.arange(-kmax, kmax + 1).astype(dtype)
+    ky = np.arange(0, kmax + 1).astype(dtype)
+    fr = fk.real.astype(dtype); fi = fk.imag.astype(dtype)
+    wy = np.full(nky, 2, dtype=dtype); wy[0] = 1
+    out = np.zeros(x.shape, dtype=dtype)
+    # chunk over packets to bound memory
+    step = max(1, 2_000_000 // (nkx * max(nky, 1)))
+    for s in range(0, x.size, max(step, 16)):
+        e = slice(s, s + max(step, 16))
+        ax = np.outer(tx[e], kx)                      # (p, nkx)
+        cx, sx = np.cos(ax), np.sin(ax)
+        gr = cx @ fr - sx @ fi                        # Re sum_kx F e^{i kx tx}, (p, nky)
+        gi = cx @ fi + sx @ fr
+        ay = np.outer(ty[e], ky)
+        cy, sy = np.cos(ay), np.sin(ay)
+        out[e] = ((gr * cy - gi * sy) * wy).sum(axis=1)
+    return out
+
+
+def spectral_eval_planes(x, y, planes_k, dx, nx, dtype=np.longdouble):
+    """Evaluate a list of coefficient planes; returns float64 array (nplanes, Np)."""
+    return np.stack([spectral_eval(x, y, p, dx, nx, dtype).astype(np.float64) for p in planes_k])
+
+
+# --------------------------------------------------------------------------------------------
+# Schemes (SpectralScheme.m / RaytracingScheme.m)
+# --------------------------------------------------------------------------------------------
+
+class SpectralScheme:
+    """SpectralScheme.m:6-68.  ``mode='lagrange'`` is the reference behaviour (gridded fields +
+    interpolate); ``mode='spectral'`` evaluates the same coefficient planes by exact trig sum."""
+
+    def __init__(self, L, nx, psi_field, mode="lagrange"):
+        self.L = float(L); self.nx = int(nx); self.mode = mode
+        kx_, ky_ = wavenumbers(nx)
+        kappa = 1.0  # SpectralScheme multiplies by integer kx,ky (domain 2*pi), SpectralScheme.m:18-25
+        psik = g2k(psi_field)
+        self.psik = psik
+        self.planes_k = velocity_planes_k(psik, kappa * kx_, kappa * ky_)
+        self.psi_field = k2g(psik)
+        names = ("u", "v", "u_x", "u_y", "v_x", "v_y")
+        self.fields = {n: k2g(p) for n, p in zip(names, self.planes_k)}
+
+    def _dx(self):
+        return self.L / self.psi_field.shape[0]          # SpectralScheme.m:39,46,57
+
+    def _eval(self, name, xx, yy):
+        dx = self._dx()
+        if self.mode == "lagrange":
+            return interpolate(xx, yy, self.fields[name], dx, dx)
+        idx = ("u", "v", "u_x", "u_y", "v_x", "v_y").index(name)
+        return spectral_eval(xx, yy, self.planes_k[idx], dx, self.nx).astype(np.float64)
+
+    def streamfunction(self, x, y, t=0):
+        dx = self._dx()
+        if self.mode == "lagrange":
+            return interpolate(x, y, self.psi_field, dx, dx)
+        return spectral_eval(x, y, self.psik, dx, self.nx).astype(np.float64).reshape(np.shape(x))
+
+    def U(self, x, t=0):
+        """x: (T,2,Np) as in the reference, or (Np,2).  SpectralScheme.m:45-54."""
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 2:
+            xx, yy = x[:, 0], x[:, 1]
+            return np.stack([self._eval("u", xx, yy), self._eval("v", xx, yy)], axis=1)
+        xx = x[:, 0, :]; yy = x[:, 1, :]
+        u = np.zeros_like(x)
+        u[:, 0, :] = self._eval("u", xx.ravel(), yy.ravel()).reshape(xx.shape)
+        u[:, 1, :] = self._eval("v", xx.ravel(), yy.ravel()).reshape(xx.shape)
+        return u
+
+    def grad_U(self, x, t=0):
+        """SpectralScheme.m:56-68: dict of flat arrays u_x,u_y,v_x,v_y."""
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 2:
+            xx, yy = x[:, 0], x[:, 1]
+        else:
+            xx = x[:, 0, :].ravel(); yy = x[:, 1, :].ravel()
+        return {n: self._eval(n, xx, yy) for n in ("u_x", "u_y", "v_x", "v_y")}
+
+    def grad_U_times_k(self, x, k, t=0):
+        """RaytracingScheme.m:9-16: [(u_x k + v_x l), (u_y k + v_y l)], same shape as k."""
+        g = self.grad_U(x, t)
+        k = np.asarray(k, dtype=np.float64)
+        out = np.zeros_like(k)
+        if k.ndim == 2:
+            kk, ll = k[:, 0], k[:, 1]
+            out[:, 0] = g["u_x"] * kk + g["v_x"] * ll
+            out[:, 1] = g["u_y"] * kk + g["v_y"] * ll
+            return out
+        kk = k[:, 0, :]; ll = k[:, 1, :]
+        out[:, 0, :] = (g["u_x"] * kk.ravel() + g["v_x"] * ll.ravel()).reshape(kk.shape)
+        out[:, 1, :] = (g["u_y"] * kk.ravel() + g["v_y"] * ll.ravel()).reshape(ll.shape)
+        return out
+
+
+class PlanesScheme:
+    """A scheme defined directly by six coefficient planes (u,v,ux,uy,vx,vy) on a domain of side L
+    (what grid_U builds for the qgsw drivers), evaluated either by k2g+interpolate or trig sum."""
+
+    def __init__(self, L, nx, planes_k, mode="lagrange", planes_k2=None):
+        self.L = float(L); self.nx = int(nx); self.mode = mode
+        self.planes_k = [np.asarray(p, dtype=np.complex128) for p in planes_k]
+        self.fields = [k2g(p) for p in self.planes_k] if mode == "lagrange" else None
+
+    def eval6(self, x, y):
+        dx = self.L / self.nx
+        if self.mode == "lagrange":
+            return np.stack([interpolate(x, y, F, dx, dx) for F in self.fields])
+        return spectral_eval_planes(x, y, self.planes_k, dx, self.nx)
+
+    def U(self, x, t=0):
+        e = self.eval6(x[:, 0], x[:, 1])
+        return np.stack([e[0], e[1]], axis=1)
+
+    def grad_U_times_k(self, x, k, t=0):
+        e = self.eval6(x[:, 0], x[:, 1])
+        return np.stack([e[2] * k[:, 0] + e[4] * k[:, 1], e[3] * k[:, 0] + e[5] * k[:, 1]], axis=1)
+
+
+# --------------------------------------------------------------------------------------------
+# Integrators
+# --------------------------------------------------------------------------------------------
+
+def omega_of_k(k, l, f, gH):
+    """ode_symplectic.m:10 / load_data.m:33: sqrt(f^2 + gH*(k^2+l^2))."""
+    return np.sqrt(f * f + gH * (k * k + l * l))
+
+
+def leapfrog_step(x, y, k, l, dt, f, gH, eval6):
+    """One step of ode_symplectic.m:13-21,33-37 on flat arrays.  ``eval6(x,y)`` returns the six
+    planes (u,v,ux,uy,vx,vy) at the packets.  phi1(dt/2): x += dt/2*gH*k/omega(k);
+    phi2(dt): x += dt*U(x1), k -= dt*(gradU(x1))^T k (old k on the right); phi1(dt/2)."""
+    h = dt / 2
+    w = np.sqrt(f ** 2 + gH * (k * k + l * l))
+    x1 = x + h * (gH * k / w)
+    y1 = y + h * (gH * l / w)
+    u, v, ux, uy, vx, vy = eval6(x1, y1)
+    x2 = x1 + dt * u
+    y2 = y1 + dt * v
+    k2 = k - dt * (ux * k + vx * l)
+    l2 = l - dt * (uy * k + vy * l)
+    w = np.sqrt(f ** 2 + gH * (k2 * k2 + l2 * l2))
+    x3 = x2 + h * (gH * k2 / w)
+    y3 = y2 + h * (gH * l2 / w)
+    return x3, y3, k2, l2
+
+
+def ode_symplectic(x0, k0, dt, T, f, gH, scheme, save_stride=1):
+    """ode_symplectic.m:1-37.  x0,k0: (1,2,Np).  Nsteps=floor(T/dt); rows 2..Nsteps hold the state
+    after 1..Nsteps-1 leapfrog steps; t(i)=(i-1)dt.  ``save_stride`` thins the stored history
+    (an extension: the reference stores every step, ode_symplectic.m:25-27)."""
+    Nsteps = int(math.floor(T / dt))
+    x0 = np.asarray(x0, dtype=np.float64); k0 = np.asarray(k0, dtype=np.float64)
+    rows = list(range(0, Nsteps, save_stride))
+    xs = np.zeros((len(rows),) + x0.shape[1:]); ks = np.zeros_like(xs); ts = np.zeros(len(rows))
+    xs[0] = x0[0]; ks[0] = k0[0]
+    x, y = x0[0, 0, :].copy(), x0[0, 1, :].copy()
+    k, l = k0[0, 0, :].copy(), k0[0, 1, :].copy()
+
+    def eval6(xx, yy):
+        xa = np.stack([xx, yy], axis=1)
+        U = scheme.U(xa)
+        g = scheme.grad_U(xa)
+        return U[:, 0], U[:, 1], g["u_x"], g["u_y"], g["v_x"], g["v_y"]
+
+    r = 1
+    for i in range(1, Nsteps):
+        x, y, k, l = leapfrog_step(x, y, k, l, dt, f, gH, eval6)
+        if i % save_stride == 0:
+            xs[r, 0], xs[r, 1], ks[r, 0], ks[r, 1] = x, y, k, l
+            ts[r] = i * dt
+            r += 1
+    return xs, ks, ts
+
+
+def odefun_rhs(x, y, k, l, alpha, bf1, bf2, f, Cg, h):
+    """qgsw_raytrace.m:259-265 (same in qg2layersw_raytrace.m:298-304): RHS of the ode23 system.
+    dxdt = U + Cg*k/sqrt(f^2+Cg^2|k|^2)  (note Cg, not Cg^2); dkdt = -(gradU)^T k."""
+    U, nab = interpolate_U(bf1, bf2, alpha, np.stack([x, y], axis=1), h)
+    w = np.sqrt(f ** 2 + Cg ** 2 * (k * k + l * l))
+    dxdt = U[:, 0] + Cg * k / w
+    dydt = U[:, 1] + Cg * l / w
+    dkdt = -(nab["u_x"] * k + nab["v_x"] * l)
+    dldt = -(nab["u_y"] * k + nab["v_y"] * l)
+    return dxdt, dydt, dkdt, dldt
+
+
+def rhs_from_eval(e6, k, l, f, Cg):
+    """The same RHS given the six evaluated planes (mode-independent part of odefun)."""
+    u, v, ux, uy, vx, vy = e6
+    w = np.sqrt(f ** 2 + Cg ** 2 * (k * k + l * l))
+    return u + Cg * k / w, v + Cg * l / w, -(ux * k + vx * l), -(uy * k + vy * l)
+
+
+def cg_sw(k, l, C0, f, U=None, H=None):
+    """ray_trace_sw/cg_sw.m:15-31.  With H (grid, or per-packet point values) gH=C0^2*H and every
+    output has H's shape.  Returns (Cx, Cy, omega, divC, gox, goy)."""
+    gH = C0 ** 2 * H if H is not None else C0 ** 2
+    K2 = k ** 2 + l ** 2
+    omega = np.sqrt(f ** 2 + gH * K2)
+    Cx = gH * k / omega
+    Cy = gH * l / omega
+    divC = gox = goy = None
+    if U is not None and H is not None:
+        divC = (k * f * U["v"] - l * f * U["u"] - Cx ** 2 - Cy ** 2) / omega
+        gox = f * K2 * U["v"] / (2 * omega)
+        goy = -f * K2 * U["u"] / (2 * omega)
+    return Cx, Cy, omega, divC, gox, goy
+
+
+def _rk4_linear_k(k, l, dt, uxi, uyi, vxi, vyi, oxi=0.0, oyi=0.0):
+    """step_packet.m:65-78 / step_packet_xka.m:69-82: RK4 on (k,l) with a frozen matrix."""
+    k1 = dt * (-uxi * k - vxi * l - oxi)
+    l1 = dt * (-uyi * k - vyi * l - oyi)
+    k2 = dt * (-uxi * (k + k1 / 2) - vxi * (l + l1 / 2) - oxi)
+    l2 = dt * (-uyi * (k + k1 / 2) - vyi * (l + l1 / 2) - oyi)
+    k3 = dt * (-uxi * (k + k2 / 2) - vxi * (l + l2 / 2) - oxi)
+    l3 = dt * (-uyi * (k + k2 / 2) - vyi * (l + l2 / 2) - oyi)
+    k4 = dt * (-uxi * (k + k3) - vxi * (l + l3) - oxi)
+    l4 = dt * (-uyi * (k + k3) - vyi * (l + l3) - oyi)
+    return k + (k1 + 2 * k2 + 2 * k3 + k4) / 6, l + (l1 + 2 * l2 + 2 * l3 + l4) / 6
+
+
+def step_packet(P, U, GradU, C0, f, dx, dy, dt):
+    """ray_trace_sw/step_packet.m:37-78 for ONE packet (scalars in dict P with x,y,k,l).
+    The reference interpolates the grid ``U.u + C.x`` (scalar added to every node)."""
+    Cx, Cy, *_ = cg_sw(P["k"], P["l"], C0, f)
+    Fu = U["u"] + Cx; Fv = U["v"] + Cy
+    ip = lambda xx, yy, F: float(interpolate(np.array([xx]), np.array([yy]), F, dx, dy)[0])
+    x1 = dt * ip(P["x"], P["y"], Fu); y1 = dt * ip(P["x"], P["y"], Fv)
+    x2 = dt * ip(P["x"] + x1 / 2, P["y"] + y1 / 2, Fu); y2 = dt * ip(P["x"] + x1 / 2, P["y"] + y1 / 2, Fv)
+    x3 = dt * ip(P["x"] + x2 / 2, P["y"] + y2 / 2, Fu); y3 = dt * ip(P["x"] + x2 / 2, P["y"] + y2 / 2, Fv)
+    x4 = dt * ip(P["x"] + x3, P["y"] + y3, Fu); y4 = dt * ip(P["x"] + x3, P["y"] + y3, Fv)
+    out = {"x": P["x"] + (x1 + 2 * x2 + 2 * x3 + x4) / 6, "y": P["y"] + (y1 + 2 * y2 + 2 * y3 + y4) / 6}
+    # gradients at the OLD position (step_packet.m:58-61)
+    g = [ip(P["x"], P["y"], GradU[n]) for n in ("u_x", "u_y", "v_x", "v_y")]
+    out["k"], out["l"] = _rk4_linear_k(P["k"], P["l"], dt, g[0], g[1], g[2], g[3])
+    return out
+
+
+def step_packet_xka(P, U, GradU, H, C0, f, dx, dy, dt):
+    """ray_trace_sw/step_packet_xka.m:38-91 for ONE packet; cg_sw fields are whole grids."""
+    Cx, Cy, om, divC, gox, goy = cg_sw(P["k"], P["l"], C0, f, U, H)
+    Fu = U["u"] + Cx; Fv = U["v"] + Cy
+    ip = lambda xx, yy, F: float(interpolate(np.array([xx]), np.array([yy]), F, dx, dy)[0])
+    x1 = dt * ip(P["x"], P["y"], Fu); y1 = dt * ip(P["x"], P["y"], Fv)
+    x2 = dt * ip(P["x"] + x1 / 2, P["y"] + y1 / 2, Fu); y2 = dt * ip(P["x"] + x1 / 2, P["y"] + y1 / 2, Fv)
+    x3 = dt * ip(P["x"] + x2 / 2, P["y"] + y2 / 2, Fu); y3 = dt * ip(P["x"] + x2 / 2, P["y"] + y2 / 2, Fv)
+    x4 = dt * ip(P["x"] + x3, P["y"] + y3, Fu); y4 = dt * ip(P["x"] + x3, P["y"] + y3, Fv)
+    out = {"x": P["x"] + (x1 + 2 * x2 + 2 * x3 + x4) / 6, "y": P["y"] + (y1 + 2 * y2 + 2 * y3 + y4) / 6}
+    # gradients, grad(omega), div C at the NEW position (step_packet_xka.m:59-65)
+    g = [ip(out["x"], out["y"], GradU[n]) for n in ("u_x", "u_y", "v_x", "v_y")]
+    oxi = ip(out["x"], out["y"], gox); oyi = ip(out["x"], out["y"], goy)
+    dci = ip(out["x"], out["y"], divC)
+    out["k"], out["l"] = _rk4_linear_k(P["k"], P["l"], dt, g[0], g[1], g[2], g[3], oxi, oyi)
+    a = P["a"]
+    a1 = dt * (-a * dci); a2 = dt * (-(a + a1 / 2) * dci); a3 = dt * (-(a + a2 / 2) * dci); a4 = dt * (-(a + a3) * dci)
+    out["a"] = a + (a1 + 2 * a2 + 2 * a3 + a4) / 6
+    return out
+
+
+def rk4_step_batch(x, y, k, l, a, dt, C0, f, fields, dx, xka, mode="lagrange", planes_k=None, nx=None):
+    """Vectorised-over-packets restatement of step_packet / step_packet_xka.
+
+    mode='lagrange': identical arithmetic to the reference, but the per-packet scalar that the
+    reference adds to every grid node (``U.u + C.x``) is added at the 36 stencil nodes only, i.e.
+    sum_ij w_ij (F_ij + c) -- the same value the reference computes, without forming nx^2 temps.
+    For xka the node-wise fields (C, divC, grad omega) are composed at the stencil nodes.
+    mode='spectral': the continuous ray equations -- U,V,H and gradients evaluated by exact trig sum
+    at the point and composed pointwise (SURVEY.md 7.2 'step_packet_xka composes fields ...').
+    fields: dict u,v,u_x,u_y,v_x,v_y[,H] of grids (lagrange) ; planes_k: list of 6 or 7 coefficient
+    planes (spectral; H plane is eta_g, H = 1 + eta_g is applied by putting 1 in its (0,0) mode)."""
+    n = x.size
+    K2 = k * k + l * l
+    if mode == "lagrange":
+        def ev(xx, yy, fn):
+            return _stencil_apply(xx, yy, fields["u"].shape[0], dx, fn)
+        if not xka:
+            w0 = np.sqrt(f ** 2 + C0 ** 2 * K2)
+            Cx = C0 ** 2 * k / w0; Cy = C0 ** 2 * l / w0
+            fu = lambda ig, jg: fields["u"][ig, jg] + Cx
+            fv = lambda ig, jg: fields["v"][ig, jg] + Cy
+        else:
+            def node(ig, jg):
+                gH = C0 ** 2 * fields["H"][ig, jg]
+                om = np.sqrt(f ** 2 + gH * K2)
+                return gH, om
+            def fu(ig, jg):
+                gH, om = node(ig, jg); return fields["u"][ig, jg] + gH * k / om
+            def fv(ig, jg):
+                gH, om = node(ig, jg); return fields["v"][ig, jg] + gH * l / om
+        x1 = dt * ev(x, y, fu); y1 = dt * ev(x, y, fv)
+        x2 = dt * ev(x + x1 / 2, y + y1 / 2, fu); y2 = dt * ev(x + x1 / 2, y + y1 / 2, fv)
+        x3 = dt * ev(x + x2 / 2, y + y2 / 2, fu); y3 = dt * ev(x + x2 / 2, y + y2 / 2, fv)
+        x4 = dt * ev(x + x3, y + y3, fu); y4 = dt * ev(x + x3, y + y3, fv)
+        xn = x + (x1 + 2 * x2 + 2 * x3 + x4) / 6
+        yn = y + (y1 + 2 * y2 + 2 * y3 + y4) / 6
+        gx, gy = (xn, yn) if xka else (x, y)
+        g = [ev(gx, gy, (lambda ig, jg, nm=nm: fields[nm][ig, jg])) for nm in ("u_x", "u_y", "v_x", "v_y")]
+        if xka:
+            def f_ox(ig, jg):
+                gH, om = node(ig, jg); return f * K2 * fields["v"][ig, jg] / (2 * om)
+            def f_oy(ig, jg):
+                gH, om = node(ig, jg); return -f * K2 * fields["u"][ig, jg] / (2 * om)
+            def f_dc(ig, jg):
+                gH, om = node(ig, jg)
+                cx = gH * k / om; cy = gH * l / om
+                return (k * f * fields["v"][ig, jg] - l * f * fields["u"][ig, jg] - cx ** 2 - cy ** 2) / om
+            oxi = ev(xn, yn, f_ox); oyi = ev(xn, yn, f_oy); dci = ev(xn, yn, f_dc)
+        else:
+            oxi = oyi = 0.0; dci = None
+    else:
+        npl = len(planes_k)
+        def e_all(xx, yy, idx):
+            return [spectral_eval(xx, yy, planes_k[i], dx, nx).astype(np.float64) for i in idx]
+        def vel(xx, yy):
+            if not xka:
+                u, v = e_all(xx, yy, (0, 1))
+                w0 = np.sqrt(f ** 2 + C0 ** 2 * K2)
+                return u + C0 ** 2 * k / w0, v + C0 ** 2 * l / w0
+            u, v, Hh = e_all(xx, yy, (0, 1, 6))
+            gH = C0 ** 2 * Hh; om = np.sqrt(f ** 2 + gH * K2)
+            return u + gH * k / om, v + gH * l / om
+        ux_, uy_ = vel(x, y); x1 = dt * ux_; y1 = dt * uy_
+        ux_, uy_ = vel(x + x1 / 2, y + y1 / 2); x2 = dt * ux_; y2 = dt * uy_
+        ux_, uy_ = vel(x + x2 / 2, y + y2 / 2); x3 = dt * ux_; y3 = dt * uy_
+        ux_, uy_ = vel(x + x3, y + y3); x4 = dt * ux_; y4 = dt * uy_
+        xn = x + (x1 + 2 * x2 + 2 * x3 + x4) / 6
+        yn = y + (y1 + 2 * y2 + 2 * y3 + y4) / 6
+        gx, gy = (xn, yn) if xka else (x, y)
+        if xka:
+            u, v, g0, g1, g2, g3, Hh = e_all(gx, gy, range(7))
+            g = [g0, g1, g2, g3]
+            gH = C0 ** 2 * Hh; om = np.sqrt(f ** 2 + gH * K2)
+            cx = gH * k / om; cy = gH * l / om
+            oxi = f * K2 * v / (2 * om); oyi = -f * K2 * u / (2 * om)
+            dci = (k * f * v - l * f * u - cx ** 2 - cy ** 2) / om
+        else:
+            g = e_all(gx, gy, (2, 3, 4, 5)); oxi = oyi = 0.0; dci = None
+    kn, ln = _rk4_linear_k(k, l, dt, g[0], g[1], g[2], g[3], oxi, oyi)
+    an = a
+    if xka:
+        a1 = dt * (-a * dci); a2 = dt * (-(a + a1 / 2) * dci); a3 = dt * (-(a + a2 / 2) * dci); a4 = dt * (-(a + a3) * dci)
+        an = a + (a1 + 2 * a2 + 2 * a3 + a4) / 6
+    return xn, yn, kn, ln, an
+
+
+def _stencil_apply(x, y, nx, dx, node_fn, bump=BUMP_LIVE):
+    """interpolate.m:18-49 with the gridded field replaced by ``node_fn(ig,jg)`` (zero-based index
+    arrays) evaluated at the 36 stencil nodes: sum_i sum_j (wx_i*wy_j)*node, i outer, j inner."""
+    xl = matlab_mod(x / dx, nx); yl = matlab_mod(y / dx, nx)
+    i0 = 1 + np.floor(xl); j0 = 1 + np.floor(yl)
+    ax = 1 + xl - i0; ay = 1 + yl - j0
+    wx = _lagrange_weights(ax, bump); wy = _lagrange_weights(ay, bump)
+    i0 = i0.astype(np.int64); j0 = j0.astype(np.int64)
+    FI = np.zeros_like(x)
+    for i in range(-IORD, IORD + 2):
+        ig = np.mod(i0 + i - 1, nx)
+        for j in range(-IORD, IORD + 2):
+            jg = np.mod(j0 + j - 1, nx)
+            FI = FI + wx[i + IORD] * wy[j + IORD] * node_fn(ig, jg)
+    return FI
+
+
+# --------------------------------------------------------------------------------------------
+# Driver-side restatements used to build test/bench inputs
+# --------------------------------------------------------------------------------------------
+
+def initial_q(X, Y, a_g, K_d2, rs, k_min=5, k_max=8, ring=False):
+    """qgsw_raytrace.m:191-214.  The chained comparison on :202 ``k_min^2 < k^2+l^2 <= k_max^2``
+    parses as ``(k_min^2 < K2) <= k_max^2`` = always true, so every |k|,|l|<=k_max mode is summed;
+    ``ring=True`` gives the evidently intended annulus.  ``rs`` = RandomState (rng(146))."""
+    q = np.zeros_like(X); U = np.zeros_like(X); V = np.zeros_like(X)
+    n = 2 * k_max + 1
+    phase = 2 * np.pi * rs.rand(n, n).T        # MATLAB fills column-major
+    for k in range(-k_max, k_max + 1):
+        for l in range(-k_max, k_max + 1):
+            K2 = k * k + l * l
+            if (not ring) or (k_min ** 2 < K2 <= k_max ** 2):
+                wp = k * X + l * Y + phase[k + k_max, l + k_max]
+                U = U - l * np.sin(wp)
+                V = V + k * np.sin(wp)
+                q = q - (K_d2 + K2) * np.cos(wp)
+    speed2 = U ** 2 + V ** 2
+    return a_g / np.sqrt(speed2.max()) * q
+
+
+def init_packets(Npackets, L, radius, rs):
+    """qgsw_raytrace.m:54-60 / symplectic_full_fourier.m:22-28: k on a ring, x ~ L*rand(1,2)-L/2
+    drawn per packet (x then y interleaved)."""
+    i = np.arange(1, Npackets + 1)
+    k = radius * np.cos(2 * np.pi * i / Npackets)
+    l = radius * np.sin(2 * np.pi * i / Npackets)
+    r = rs.rand(Npackets, 2)
+    return L * r[:, 0] - L / 2, L * r[:, 1] - L / 2, k, l
+
+
+def wrap_position(x, L):
+    """qgsw_raytrace.m:160: mod(x + L/2, L) - L/2 (applied only when saving)."""
+    return matlab_mod(x + L / 2, L) - L / 2
+
+
+def omega_histogram(k, l, f, Cg, edges):
+    """analysis/load_data.m:33,38-49: omega=sqrt(f^2+Cg^2 K^2) -> histcounts; energy=centre*count."""
+    w = np.sqrt(f ** 2 + Cg ** 2 * (k * k + l * l))
+    counts = histcounts(w, edges)
+    centre = (edges[1:] + edges[:-1]) / 2
+    return counts, centre * counts.astype(np.float64)
+
+
+def childress_soward(nx, L, U0, km, a):
+    """ray_trace_sw/raytrace.m:25-37 closed-form flow on the grid x=0:dx:dx*(nx-1) (ndgrid).  The
+    reference's line 36 uses ``*`` (matrix product) instead of ``.*`` in v_x; the elementwise form
+    (the evident intent, and equal to it when a=0) is used here."""
+    dx = L / nx
+    x = np.arange(nx) * dx
+    x_, y_ = np.meshgrid(x, x, indexing="ij")
+    s, c = np.sin, np.cos
+    psi = U0 / km * (s(km * x_) * s(km * y_) + a * c(km * x_) * c(km * y_))
+    U = {"u": -U0 * (s(km * x_) * c(km * y_) - a * c(km * x_) * s(km * y_)),
+         "v": U0 * (c(km * x_) * s(km * y_) - a * s(km * x_) * c(km * y_))}
+    G = {"u_x": -km * U0 * (c(km * x_) * c(km * y_) + a * s(km * x_) * s(km * y_)),
+         "u_y": km * U0 * (s(km * x_) * s(km * y_) + a * c(km * x_) * c(km * y_)),
+         "v_x": -km * U0 * (s(km * x_) * s(km * y_) + a * c(km * x_) * c(km * y_)),
+         "v_y": km * U0 * (c(km * x_) * c(km * y_) + a * s(km * x_) * s(km * y_))}
+    return psi, U, G
+
+
+def childress_soward_point(x, y, U0, km, a):
+    """The same closed form at arbitrary points (u,v,u_x,u_y,v_x,v_y)."""
+    s, c = np.sin, np.cos
+    return np.stack([-U0 * (s(km * x) * c(km * y) - a * c(km * x) * s(km * y)),
+                     U0 * (c(km * x) * s(km * y) - a * s(km * x) * c(km * y)),
+                     -km * U0 * (c(km * x) * c(km * y) + a * s(km * x) * s(km * y)),
+                     km * U0 * (s(km * x) * s(km * y) + a * c(km * x) * c(km * y)),
+                     -km * U0 * (s(km * x) * s(km * y) + a * c(km * x) * c(km * y)),
+                     km * U0 * (c(km * x) * c(km * y) + a * s(km * x) * s(km * y))])

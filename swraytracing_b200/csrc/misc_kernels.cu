@@ -1,0 +1,211 @@
+// misc_kernels.cu -- elementwise glue and diagnostics of libswrt: the ode23 RHS of
+// qgsw_raytrace.m:259-265, the point-wise RK4 glue used by the SPECTRAL mode of step_packet /
+// step_packet_xka, omega / Omega (symplectic_full_fourier.m:41,54-56), histcounts
+// (analysis/load_data.m:39-47) and the reduction diagnostics.
+#include "swrt_internal.h"
+
+namespace swrt {
+
+namespace {
+inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+__global__ void fill_kernel(double* p, double v, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// odefun: dxdt = U + Cg*k/sqrt(f^2 + Cg^2 |k|^2), dkdt = -(grad U)^T k
+struct E6 { const double* p[6]; };
+__global__ void rhs_kernel(long long n, const double* __restrict__ k, const double* __restrict__ l, E6 e, double f,
+                           double Cg, double* dxdt, double* dydt, double* dkdt, double* dldt) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double kk = k[i], ll = l[i];
+    const double w = sqrt(f * f + Cg * Cg * (kk * kk + ll * ll));
+    if (dxdt) dxdt[i] = e.p[0][i] + Cg * kk / w;
+    if (dydt) dydt[i] = e.p[1][i] + Cg * ll / w;
+    if (dkdt) dkdt[i] = -(e.p[2][i] * kk + e.p[4][i] * ll);
+    if (dldt) dldt[i] = -(e.p[3][i] * kk + e.p[5][i] * ll);
+}
+
+__global__ void omega_kernel(long long n, const double* __restrict__ k, const double* __restrict__ l,
+                             const double* __restrict__ u, const double* __restrict__ v, double f, double gH,
+                             double* omega, double* Omega_abs) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double kk = k[i], ll = l[i];
+    const double w = sqrt(f * f + gH * (kk * kk + ll * ll));
+    if (omega) omega[i] = w;
+    if (Omega_abs) Omega_abs[i] = w + (u[i] * kk + v[i] * ll);   // omega + dot(U,k)
+}
+
+// SPECTRAL-mode RK4 position stage: the continuous ray equations composed point-wise.
+//   velocity = U + C with C = gH k/omega, gH = C0^2 (packet) or C0^2*H(x) (xka)
+// stage 0..3 of step_packet.m:41-54; accumulates (x1 + 2x2 + 2x3 + x4) and writes the next stage
+// position into xs,ys.
+__global__ void rk4_stage_kernel(Rk4Args a) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const double k = a.k[i], l = a.l[i];
+    const double K2 = k * k + l * l;
+    const double gH = a.xka ? a.C0 * a.C0 * a.H[i] : a.C0 * a.C0;
+    const double om = sqrt(a.f * a.f + gH * K2);
+    const double dxs = a.dt * (a.u[i] + gH * k / om);
+    const double dys = a.dt * (a.v[i] + gH * l / om);
+    const double x = a.x[i], y = a.y[i];
+    switch (a.stage) {
+        case 0: a.ax[i] = dxs; a.ay[i] = dys; a.xs[i] = x + dxs / 2; a.ys[i] = y + dys / 2; break;
+        case 1: a.ax[i] += 2 * dxs; a.ay[i] += 2 * dys; a.xs[i] = x + dxs / 2; a.ys[i] = y + dys / 2; break;
+        case 2: a.ax[i] += 2 * dxs; a.ay[i] += 2 * dys; a.xs[i] = x + dxs; a.ys[i] = y + dys; break;
+        default: {
+            const double sx = a.ax[i] + dxs, sy = a.ay[i] + dys;
+            a.xs[i] = x + sx / 6; a.ys[i] = y + sy / 6;   // = Pout.x, Pout.y
+        }
+    }
+}
+
+// k (and a) update with frozen gradients; commits the new position held in xs,ys.
+__global__ void rk4_final_kernel(Rk4Args a) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const double k = a.k[i], l = a.l[i], dt = a.dt;
+    const double uxi = a.ux[i], uyi = a.uy[i], vxi = a.vx[i], vyi = a.vy[i];
+    double oxi = 0.0, oyi = 0.0, dci = 0.0;
+    if (a.xka) {   // cg_sw.m:22-31 evaluated at the point
+        const double K2 = k * k + l * l;
+        const double gH = a.C0 * a.C0 * a.H[i];
+        const double om = sqrt(a.f * a.f + gH * K2);
+        const double cx = gH * k / om, cy = gH * l / om;
+        const double u = a.u[i], v = a.v[i];
+        oxi = a.f * K2 * v / (2 * om);
+        oyi = -a.f * K2 * u / (2 * om);
+        dci = (k * a.f * v - l * a.f * u - cx * cx - cy * cy) / om;
+    }
+    const double k1 = dt * (-uxi * k - vxi * l - oxi);
+    const double l1 = dt * (-uyi * k - vyi * l - oyi);
+    const double k2 = dt * (-uxi * (k + k1 / 2) - vxi * (l + l1 / 2) - oxi);
+    const double l2 = dt * (-uyi * (k + k1 / 2) - vyi * (l + l1 / 2) - oyi);
+    const double k3 = dt * (-uxi * (k + k2 / 2) - vxi * (l + l2 / 2) - oxi);
+    const double l3 = dt * (-uyi * (k + k2 / 2) - vyi * (l + l2 / 2) - oyi);
+    const double k4 = dt * (-uxi * (k + k3) - vxi * (l + l3) - oxi);
+    const double l4 = dt * (-uyi * (k + k3) - vyi * (l + l3) - oyi);
+    a.k[i] = k + (k1 + 2 * k2 + 2 * k3 + k4) / 6;
+    a.l[i] = l + (l1 + 2 * l2 + 2 * l3 + l4) / 6;
+    if (a.xka) {
+        const double am = a.a[i];
+        const double a1 = dt * (-am * dci);
+        const double a2 = dt * (-(am + a1 / 2) * dci);
+        const double a3 = dt * (-(am + a2 / 2) * dci);
+        const double a4 = dt * (-(am + a3) * dci);
+        a.a[i] = am + (a1 + 2 * a2 + 2 * a3 + a4) / 6;
+    }
+    a.x[i] = a.xs[i];
+    a.y[i] = a.ys[i];
+}
+
+// histcounts(w, edges): bin i = [e_i, e_{i+1}), last bin closed; NaN / out of range dropped.
+constexpr int kMaxSmemBins = 4096;
+__global__ void hist_kernel(long long n, const double* __restrict__ w, const double* __restrict__ edges, int nedges,
+                            unsigned long long* __restrict__ counts) {
+    extern __shared__ unsigned char hs[];
+    double* se = reinterpret_cast<double*>(hs);
+    unsigned int* sc = reinterpret_cast<unsigned int*>(se + nedges);
+    const int nb = nedges - 1;
+    for (int i = threadIdx.x; i < nedges; i += blockDim.x) se[i] = edges[i];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) sc[i] = 0;
+    __syncthreads();
+    const double lo = se[0], hi = se[nb];
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = w[i];
+        if (!(v >= lo && v <= hi)) continue;   // also drops NaN
+        int a = 0, b = nb;                     // find last a with se[a] <= v
+        while (b - a > 1) {
+            int m = (a + b) >> 1;
+            if (se[m] <= v) a = m; else b = m;
+        }
+        atomicAdd(&sc[a], 1u);                 // v == hi lands in a = nb-1 because b never drops below nb
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (sc[i]) atomicAdd(&counts[i], (unsigned long long)sc[i]);
+}
+
+// partial sums per block, then one block reduces the partials in a fixed order (deterministic)
+constexpr int kDiagBlocks = 296;
+__global__ void __launch_bounds__(256) diag_partial_kernel(long long n, const double* __restrict__ x,
+                                                            const double* __restrict__ y, const double* __restrict__ k,
+                                                            const double* __restrict__ l, const double* __restrict__ a,
+                                                            const double* __restrict__ om, const double* __restrict__ Om,
+                                                            double* __restrict__ part) {
+    double s_om = 0, s_Om = 0, mx = -1e300, mn = 1e300, nf = 0, s_a = 0, s_oa = 0;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double w = om[i], W = Om[i];
+        const bool fin = isfinite(x[i]) && isfinite(y[i]) && isfinite(k[i]) && isfinite(l[i]);
+        if (!fin) { nf += 1.0; continue; }
+        const double am = a ? a[i] : 1.0;
+        s_om += w; s_Om += W; s_a += am; s_oa += w * am;
+        mx = fmax(mx, w); mn = fmin(mn, w);
+    }
+    __shared__ double sh[7][256];
+    const int t = threadIdx.x;
+    sh[0][t] = s_om; sh[1][t] = s_Om; sh[2][t] = mx; sh[3][t] = mn; sh[4][t] = nf; sh[5][t] = s_a; sh[6][t] = s_oa;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (t < s) {
+            sh[0][t] += sh[0][t + s]; sh[1][t] += sh[1][t + s];
+            sh[2][t] = fmax(sh[2][t], sh[2][t + s]); sh[3][t] = fmin(sh[3][t], sh[3][t + s]);
+            sh[4][t] += sh[4][t + s]; sh[5][t] += sh[5][t + s]; sh[6][t] += sh[6][t + s];
+        }
+        __syncthreads();
+    }
+    if (t == 0)
+        for (int q = 0; q < 7; q++) part[(size_t)blockIdx.x * 8 + q] = sh[q][0];
+}
+__global__ void diag_final_kernel(int nblocks, const double* __restrict__ part, long long n, double* __restrict__ out8) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s_om = 0, s_Om = 0, mx = -1e300, mn = 1e300, nf = 0, s_a = 0, s_oa = 0;
+    for (int b = 0; b < nblocks; b++) {
+        const double* p = part + (size_t)b * 8;
+        s_om += p[0]; s_Om += p[1]; mx = fmax(mx, p[2]); mn = fmin(mn, p[3]); nf += p[4]; s_a += p[5]; s_oa += p[6];
+    }
+    out8[0] = s_om; out8[1] = s_Om; out8[2] = mx; out8[3] = mn; out8[4] = nf; out8[5] = s_a; out8[6] = (double)n; out8[7] = s_oa;
+}
+}  // namespace
+
+void launch_fill(double* p, double v, long long n, cudaStream_t st) {
+    if (n > 0) fill_kernel<<<nblk(n, 256), 256, 0, st>>>(p, v, n);
+}
+void launch_rhs(long long n, const double* k, const double* l, const double* const* e6, double f, double Cg,
+                double* dxdt, double* dydt, double* dkdt, double* dldt, cudaStream_t st) {
+    E6 e; for (int i = 0; i < 6; i++) e.p[i] = e6[i];
+    if (n > 0) rhs_kernel<<<nblk(n, 256), 256, 0, st>>>(n, k, l, e, f, Cg, dxdt, dydt, dkdt, dldt);
+}
+void launch_omega(long long n, const double* k, const double* l, const double* u, const double* v, double f, double gH,
+                  double* omega, double* Omega_abs, cudaStream_t st) {
+    if (n > 0) omega_kernel<<<nblk(n, 256), 256, 0, st>>>(n, k, l, u, v, f, gH, omega, Omega_abs);
+}
+void launch_rk4_stage(const Rk4Args& a, cudaStream_t st) {
+    if (a.n > 0) rk4_stage_kernel<<<nblk(a.n, 256), 256, 0, st>>>(a);
+}
+void launch_rk4_final(const Rk4Args& a, cudaStream_t st) {
+    if (a.n > 0) rk4_final_kernel<<<nblk(a.n, 256), 256, 0, st>>>(a);
+}
+void launch_hist(long long n, const double* w, const double* edges_dev, int nedges, unsigned long long* counts_dev,
+                 cudaStream_t st) {
+    if (n <= 0) return;
+    size_t smem = (size_t)nedges * 8 + (size_t)(nedges - 1) * 4;
+    unsigned nb = nblk(n, 256 * 8);
+    if (nb > 148 * 8) nb = 148 * 8;
+    hist_kernel<<<nb, 256, smem, st>>>(n, w, edges_dev, nedges, counts_dev);
+}
+void launch_diag(long long n, const double* x, const double* y, const double* k, const double* l, const double* a,
+                 const double* omega, const double* Omega_abs, double* out8_dev, cudaStream_t st) {
+    // out8_dev must have room for 8 + kDiagBlocks*8 doubles: results first, partials after
+    double* part = out8_dev + 8;
+    diag_partial_kernel<<<kDiagBlocks, 256, 0, st>>>(n, x, y, k, l, a, omega, Omega_abs, part);
+    diag_final_kernel<<<1, 32, 0, st>>>(kDiagBlocks, part, n, out8_dev);
+}
+
+}  // namespace swrt

@@ -1,0 +1,485 @@
+// spectral_kernels.cu -- SPECTRAL mode of libswrt: evaluate the flow planes at every packet by the
+// exact Fourier-series sum, as a dense real-embedded complex contraction on the fp64 tensor pipe
+// (DMMA m8n8k4), fused with the leapfrog stepper of ode_symplectic.m:13-21,33-37.
+//
+//   F_c(p) = sum_ky w_ky Re[ e^{i ky ty_p} * G_c(p,ky) ],   G_c(p,ky) = sum_kx C_c(kx,ky) e^{i kx tx_p}
+//
+// Stage 1 (G) is the GEMM:  M = packets, K = kx, N = (plane, ky).  The +kx / -kx halves are folded
+// at pack time (S = C(+kx)+C(-kx), D = C(+kx)-C(-kx)), so K runs over kx >= 0 only:
+//       Gr += Er*Sr - Ei*Di ,   Gi += Er*Si + Ei*Dr          (E = e^{i kx tx})
+// which is the real GEMM  [Er Ei] (P x 2K)  x  [[Sr Si],[-Di Dr]] (2K x 2N).  A (the twiddles) is
+// generated in registers by rotation recurrence; B (the packed stack) streams L2 -> shared memory
+// with cp.async.bulk + mbarrier from one producer warp; stage 2 (the ky sum) is applied to the
+// accumulator fragments in registers, followed by a quad shuffle reduction.
+//
+// Reference behaviour replaced: SpectralScheme.U / grad_U (SpectralScheme.m:45-68) + interpolate
+// (interpolate.m:12-49) evaluated spectrally, and ode_symplectic's stage loop.
+#include "swrt_internal.h"
+#include <cstdio>
+
+namespace swrt {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// reduced angle of interpolate.m:21: xl = mod(x/dx, nx); returns t = 2*xl/nx so that theta = pi*t
+__device__ __forceinline__ double reduced_turns(double x, double dx, double nxd) {
+    double q = x / dx;
+    double r = fmod(q, nxd);
+    if (r < 0.0) r += nxd;
+    return 2.0 * r / nxd;
+}
+
+struct Cplx { double re, im; };
+__device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) {
+    Cplx r;
+    r.re = fma(a.re, b.re, -a.im * b.im);
+    r.im = fma(a.re, b.im, a.im * b.re);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack / setup kernels
+// ------------------------------------------------------------------------------------------------
+struct PlanePtrs { const double2* p[kMaxPlanes]; };
+
+__device__ __forceinline__ double2 load_coef(const double2* pl, int kx, int ky, int kmax, int nkx) {
+    // half-plane value with the ky=0 conjugate symmetrisation of fulspec.m:16 applied
+    if (ky == 0) {
+        if (kx < 0) { double2 v = pl[(-kx + kmax)]; v.y = -v.y; return v; }
+        double2 v = pl[kx + kmax];
+        if (kx == 0) v.y = 0.0;
+        return v;
+    }
+    return pl[(size_t)ky * nkx + (kx + kmax)];
+}
+
+__global__ void pack_kernel(PackGeom g, PlanePtrs src, double* __restrict__ stack) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.total_doubles) return;
+    int which = idx & 1;
+    int lane = (idx >> 1) & 31;
+    size_t rest = idx >> 6;
+    int half_nt = g.NT / 2;
+    int tp = rest % half_nt; rest /= half_nt;
+    int s = rest % g.ksteps;
+    int pass = rest / g.ksteps;
+    int t = 2 * tp + which;
+    int c = t / g.G, gg = t % g.G;
+    int krow = lane & 3, ncol = lane >> 2;
+    int kx = 2 * s + (krow >> 1), part_k = krow & 1;
+    int j = ncol >> 1, part_n = ncol & 1;
+    int ky = pass * 4 * g.G + 4 * gg + j;
+    double val = 0.0;
+    if (kx <= g.kmax && ky <= g.kmax) {
+        const double2* pl = src.p[g.plane_ids[c]];
+        double2 cp = load_coef(pl, kx, ky, g.kmax, g.nkx);
+        double2 cm = make_double2(0.0, 0.0);
+        double2 S, D;
+        if (kx == 0) { S = cp; D = make_double2(0.0, 0.0); }
+        else {
+            cm = load_coef(pl, -kx, ky, g.kmax, g.nkx);
+            S = make_double2(cp.x + cm.x, cp.y + cm.y);
+            D = make_double2(cp.x - cm.x, cp.y - cm.y);
+        }
+        double w = (ky == 0) ? 1.0 : 2.0;
+        if (part_k == 0) val = part_n == 0 ? S.x : S.y;
+        else             val = part_n == 0 ? -D.y : D.x;
+        val *= w;
+    }
+    stack[idx] = val;
+}
+
+void launch_pack(const PackGeom& g, const double2* const* planes_dev, double* stack_dev, cudaStream_t st) {
+    PlanePtrs pp;
+    for (int i = 0; i < kMaxPlanes; i++) pp.p[i] = planes_dev[i];
+    size_t n = g.total_doubles;
+    int bs = 256;
+    pack_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(g, pp, stack_dev);
+}
+
+struct PlaneOut { double2* p[6]; };
+// SpectralScheme.m:18-25 / grid_U.m:3-9 on the device: six planes from psi-hat.
+__global__ void psi_to_planes_kernel(const double2* __restrict__ psik, PlaneOut out, int nkx, int nky,
+                                     double kappa, double u_mean) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nkx * nky) return;
+    int kmax = (nkx - 1) / 2;
+    double kx = kappa * (double)((idx % nkx) - kmax);
+    double ky = kappa * (double)(idx / nkx);
+    double2 psi = psik[idx];
+    // u = -i ky psi ; v = i kx psi
+    double2 u = make_double2(ky * psi.y, -ky * psi.x);
+    double2 v = make_double2(-kx * psi.y, kx * psi.x);
+    // ux = i kx u, uy = i ky u, vx = i kx v, vy = i ky v
+    double2 ux = make_double2(-kx * u.y, kx * u.x);
+    double2 uy = make_double2(-ky * u.y, ky * u.x);
+    double2 vx = make_double2(-kx * v.y, kx * v.x);
+    double2 vy = make_double2(-ky * v.y, ky * v.x);
+    if (idx == kmax) u.x += u_mean;   // (kx,ky) = (0,0): mean shear, grid_U.m:11
+    out.p[0][idx] = u; out.p[1][idx] = v; out.p[2][idx] = ux; out.p[3][idx] = uy; out.p[4][idx] = vx; out.p[5][idx] = vy;
+}
+
+void launch_psi_to_planes(const double2* psik, double2* const* planes, int nkx, int nky, double kappa,
+                          double u_mean, cudaStream_t st) {
+    PlaneOut po;
+    for (int i = 0; i < 6; i++) po.p[i] = planes[i];
+    int n = nkx * nky;
+    psi_to_planes_kernel<<<(n + 255) / 256, 256, 0, st>>>(psik, po, nkx, nky, kappa, u_mean);
+}
+
+// out = wa*a + wb*b : the on-device frame blend of interpolate_U.m:19-23 applied to the
+// coefficient stack (linear, so identical to blending the evaluated fields).
+__global__ void axpby_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b,
+                             double wa, double wb, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = wa * a[i] + wb * b[i];
+}
+void launch_axpby(double* out, const double* a, const double* b, double wa, double wb, size_t n, cudaStream_t st) {
+    int bs = 256;
+    size_t nb = (n + bs - 1) / bs;
+    if (nb > 148 * 16) nb = 148 * 16;
+    axpby_kernel<<<(unsigned)nb, bs, 0, st>>>(out, a, b, wa, wb, n);
+}
+
+PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
+    PackGeom g{};
+    g.nx = nx; g.nkx = nx - 1; g.nky = nx / 2; g.kmax = nx / 2 - 1;
+    g.npl = npl;
+    // accumulator budget: MT * NT * 2 doubles per thread = 96..112 registers-pairs -> NT*MT ~ 24
+    int nt_target = 24 / mtiles;
+    int G = nt_target / npl; if (G < 1) G = 1;
+    if ((npl * G) & 1) G += 1;            // NT must be even (n-tiles are fetched in pairs)
+    // supported instantiations (see launch_spectral): keep in sync
+    g.G = G; g.NT = npl * G;
+    int kyp = 4 * G;
+    g.npass = (g.nky + kyp - 1) / kyp;
+    // ~24 KB chunks: kc k-steps of NT*256 bytes each
+    int kc = 96 / g.NT;
+    g.kc = kc >= 8 ? 8 : (kc >= 4 ? 4 : 2);
+    int ks = (g.kmax + 1 + 1) / 2;
+    g.ksteps = ((ks + g.kc - 1) / g.kc) * g.kc;
+    g.chunks_per_eval = g.npass * (g.ksteps / g.kc);
+    g.chunk_doubles = (size_t)g.kc * g.NT * 32;
+    g.total_doubles = (size_t)g.npass * g.ksteps * g.NT * 32;
+    size_t chunk_bytes = g.chunk_doubles * 8;
+    g.nstages = (int)((160 * 1024) / chunk_bytes);
+    if (g.nstages > 6) g.nstages = 6;
+    if (g.nstages < 2) g.nstages = 2;
+    for (int i = 0; i < kMaxPlanes; i++) g.plane_ids[i] = i < npl ? plane_ids[i] : 0;
+    return g;
+}
+
+size_t spectral_smem_bytes(const PackGeom& g) {
+    return (size_t)g.nstages * g.chunk_doubles * 8 + 2 * g.nstages * sizeof(uint64_t) + 128;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the contraction kernel
+// ------------------------------------------------------------------------------------------------
+template <int NPL, int G, int MT, int MODE>
+__global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArgs a) {
+    constexpr int NT = NPL * G;
+    constexpr int HALF_NT = NT / 2;
+    constexpr int TILE_P = kConsumerWarps * 8 * MT;
+    static_assert(NT % 2 == 0, "n-tiles are fetched in pairs");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const PackGeom& g = a.g;
+    const int nstages = g.nstages;
+    const uint32_t chunk_bytes = (uint32_t)(g.chunk_doubles * 8);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nstages * chunk_bytes);
+    uint64_t* empty_bar = full_bar + nstages;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long ntiles = (a.n + TILE_P - 1) / TILE_P;
+    const int nevals = (MODE == SPEC_LEAPFROG) ? a.nsteps : 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    long long my_tiles = 0;
+    if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - 1 - blockIdx.x) / gridDim.x + 1;
+    const long long total_chunks = my_tiles * nevals * (long long)g.chunks_per_eval;
+    const bool is_producer = (threadIdx.x == 0);
+    // The packed stack is streamed through a ring of nstages smem buffers by ONE elected thread
+    // (warp 0 lane 0) with cp.async.bulk; chunk j lives in stage j % nstages.  The refill for chunk
+    // ci + nstages - 2 is issued when warp 0 starts chunk ci, i.e. into the stage every warp left
+    // two chunks ago, so the empty-barrier wait is (almost) never a stall.
+    long long pj = 0;           // next chunk to issue
+    int pstage = 0, pcidx = 0; uint32_t pphase = 0;
+    auto producer_issue = [&]() {
+        if (pj >= nstages) mbar_wait(&empty_bar[pstage], pphase ^ 1);
+        mbar_expect_tx(&full_bar[pstage], chunk_bytes);
+        bulk_g2s(smem_raw + (size_t)pstage * chunk_bytes, a.stack + (size_t)pcidx * g.chunk_doubles, chunk_bytes,
+                 &full_bar[pstage]);
+        if (++pcidx == g.chunks_per_eval) pcidx = 0;
+        if (++pstage == nstages) { pstage = 0; pphase ^= 1; }
+        ++pj;
+    };
+    if (is_producer) {
+        for (int i = 0; i < nstages - 2 && pj < total_chunks; i++) producer_issue();
+    }
+
+    // ===== consumer warps =====
+    const int quad_row = lane >> 2;       // packet row inside an m-tile
+    const int jq = lane & 3;              // complex column inside an n-tile (C fragment) / k row (A fragment)
+    const int kx0 = jq >> 1;              // first kx handled by this lane's A element (0 or 1)
+    const bool odd = lane & 1;            // A element is Ei (odd) or Er (even)
+    const int chunks_per_pass = g.ksteps / g.kc;
+    const int kyp_passes = g.npass;
+
+    int stage = 0; uint32_t phase = 0;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        long long prow[MT];
+        double px[MT], py[MT], pk[MT], pl[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            long long r = tile * TILE_P + (long long)warp * 8 * MT + mt * 8 + quad_row;
+            prow[mt] = r;
+            long long rc = r < a.n ? r : a.n - 1;
+            if (MODE == SPEC_LEAPFROG) { px[mt] = a.x[rc]; py[mt] = a.y[rc]; pk[mt] = a.k[rc]; pl[mt] = a.l[rc]; }
+            else { px[mt] = a.xin[rc]; py[mt] = a.yin[rc]; pk[mt] = 0; pl[mt] = 0; }
+        }
+
+        for (int ev = 0; ev < nevals; ev++) {
+            if (MODE == SPEC_LEAPFROG) {
+                // phi1(dt/2): x += dt/2 * gH*k/omega(k)   (ode_symplectic.m:13-16,34)
+                const double h = 0.5 * a.dt;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    double om = sqrt(a.f2 + a.gH * (pk[mt] * pk[mt] + pl[mt] * pl[mt]));
+                    px[mt] = px[mt] + h * (a.gH * pk[mt] / om);
+                    py[mt] = py[mt] + h * (a.gH * pl[mt] / om);
+                }
+            }
+            // ---- twiddle seeds -------------------------------------------------------------
+            double tp_[MT], tq_[MT];            // x twiddle in (p,q) form: p = this lane's A element
+            double ep0[MT], eq0[MT];            // value at the start of every pass
+            double xdc[MT], xds[MT];            // rotation by e^{i 2 tx} minus one, sign-adjusted
+            Cplx ytw[MT][G];                    // e^{i ky ty} for this lane's ky of each group
+            Cplx yrot[MT];                      // e^{i 4G ty}
+            double F[MT][NPL];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                double s1, c1;
+                sincospi(reduced_turns(px[mt], a.dx, a.nxd), &s1, &c1);
+                double er = kx0 ? c1 : 1.0, ei = kx0 ? s1 : 0.0;
+                ep0[mt] = odd ? ei : er;
+                eq0[mt] = odd ? er : ei;
+                xdc[mt] = -2.0 * s1 * s1;
+                double ds = 2.0 * s1 * c1;
+                xds[mt] = odd ? ds : -ds;
+                double sy, cy;
+                sincospi(reduced_turns(py[mt], a.dx, a.nxd), &sy, &cy);
+                Cplx e1{cy, sy};
+                Cplx e2 = cmul(e1, e1);
+                Cplx e3 = cmul(e2, e1);
+                Cplx e4 = cmul(e2, e2);
+                Cplx cur = jq == 0 ? Cplx{1.0, 0.0} : (jq == 1 ? e1 : (jq == 2 ? e2 : e3));
+                Cplx rot{1.0, 0.0};
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
+                    ytw[mt][gg] = cur;
+                    cur = cmul(cur, e4);
+                    rot = cmul(rot, e4);
+                }
+                yrot[mt] = rot;
+#pragma unroll
+                for (int c = 0; c < NPL; c++) F[mt][c] = 0.0;
+            }
+
+            // ---- passes over ky blocks -----------------------------------------------------
+            for (int pass = 0; pass < kyp_passes; pass++) {
+                double acc[MT][NT][2];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+                    for (int t = 0; t < NT; t++) { acc[mt][t][0] = 0.0; acc[mt][t][1] = 0.0; }
+                    tp_[mt] = ep0[mt]; tq_[mt] = eq0[mt];
+                }
+                for (int ch = 0; ch < chunks_per_pass; ch++) {
+                    if (is_producer && pj < total_chunks) producer_issue();
+                    mbar_wait(&full_bar[stage], phase);
+                    const double2* sB = reinterpret_cast<const double2*>(smem_raw + (size_t)stage * chunk_bytes) + lane;
+#pragma unroll 2
+                    for (int s = 0; s < g.kc; s++) {
+#pragma unroll
+                        for (int tp = 0; tp < HALF_NT; tp++) {
+                            double2 b = sB[(s * HALF_NT + tp) * 32];
+#pragma unroll
+                            for (int mt = 0; mt < MT; mt++) {
+                                dmma884(acc[mt][2 * tp][0], acc[mt][2 * tp][1], tp_[mt], b.x);
+                                dmma884(acc[mt][2 * tp + 1][0], acc[mt][2 * tp + 1][1], tp_[mt], b.y);
+                            }
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < MT; mt++) {
+                            // E <- E + E*(e^{i 2 tx} - 1)
+                            double np = fma(tp_[mt], xdc[mt], fma(tq_[mt], xds[mt], tp_[mt]));
+                            double nq = fma(tq_[mt], xdc[mt], fma(-tp_[mt], xds[mt], tq_[mt]));
+                            tp_[mt] = np; tq_[mt] = nq;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+                // ---- stage 2: F_c += Gr*cos(ky ty) - Gi*sin(ky ty) for this lane's ky ----------
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+                    for (int gg = 0; gg < G; gg++) {
+                        const double cy = ytw[mt][gg].re, sy = ytw[mt][gg].im;
+#pragma unroll
+                        for (int c = 0; c < NPL; c++) {
+                            F[mt][c] = fma(acc[mt][c * G + gg][0], cy, F[mt][c]);
+                            F[mt][c] = fma(-acc[mt][c * G + gg][1], sy, F[mt][c]);
+                        }
+                        ytw[mt][gg] = cmul(ytw[mt][gg], yrot[mt]);
+                    }
+                }
+            }
+            // ---- quad reduction: the 4 lanes of a quad hold 4 interleaved ky subsets ----------
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+                for (int c = 0; c < NPL; c++) {
+                    double v = F[mt][c];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    F[mt][c] = v;
+                }
+            }
+            if (MODE == SPEC_LEAPFROG) {
+                if constexpr (NPL >= 6) {
+                    const double h = 0.5 * a.dt;
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        // phi2(dt): x += dt*U(x1); k -= dt*(grad U)^T k with the OLD k (ode_symplectic.m:18-21)
+                        const double u = F[mt][0], v = F[mt][1], ux = F[mt][2], uy = F[mt][3], vx = F[mt][4], vy = F[mt][5];
+                        px[mt] = px[mt] + a.dt * u;
+                        py[mt] = py[mt] + a.dt * v;
+                        const double k0 = pk[mt], l0 = pl[mt];
+                        pk[mt] = k0 - a.dt * (ux * k0 + vx * l0);
+                        pl[mt] = l0 - a.dt * (uy * k0 + vy * l0);
+                        // phi1(dt/2)
+                        double om = sqrt(a.f2 + a.gH * (pk[mt] * pk[mt] + pl[mt] * pl[mt]));
+                        px[mt] = px[mt] + h * (a.gH * pk[mt] / om);
+                        py[mt] = py[mt] + h * (a.gH * pl[mt] / om);
+                    }
+                }
+            } else {
+                if (jq == 0) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        if (prow[mt] < a.n) {
+#pragma unroll
+                            for (int c = 0; c < NPL; c++)
+                                if (a.out[c]) a.out[c][prow[mt]] = F[mt][c];
+                        }
+                    }
+                }
+            }
+        }
+        if (MODE == SPEC_LEAPFROG) {
+            if (jq == 0) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    if (prow[mt] < a.n) {
+                        a.x[prow[mt]] = px[mt]; a.y[prow[mt]] = py[mt];
+                        a.k[prow[mt]] = pk[mt]; a.l[prow[mt]] = pl[mt];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int NPL, int G, int MT, int MODE>
+static cudaError_t launch_inst(const SpecArgs& a, int num_sms, cudaStream_t st) {
+    constexpr int TILE_P = kConsumerWarps * 8 * MT;
+    size_t smem = spectral_smem_bytes(a.g);
+    auto kern = spectral_kernel<NPL, G, MT, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long ntiles = (a.n + TILE_P - 1) / TILE_P;
+    int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    if (grid < 1) grid = 1;
+    kern<<<grid, kSpecThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int NPL, int G, int MT>
+static cudaError_t dispatch_mode(const SpecArgs& a, int mode, int num_sms, cudaStream_t st) {
+    if (mode == SPEC_LEAPFROG) {
+        if constexpr (NPL == 6) return launch_inst<NPL, G, MT, SPEC_LEAPFROG>(a, num_sms, st);
+        else return cudaErrorInvalidValue;
+    }
+    return launch_inst<NPL, G, MT, SPEC_EVAL>(a, num_sms, st);
+}
+
+cudaError_t launch_spectral(const SpecArgs& a, int mode, int mtiles, int num_sms, cudaStream_t st) {
+    const int npl = a.g.npl, G = a.g.G;
+#define SWRT_INST(NPL_, G_, MT_) \
+    if (npl == NPL_ && G == G_ && mtiles == MT_) return dispatch_mode<NPL_, G_, MT_>(a, mode, num_sms, st);
+    SWRT_INST(6, 4, 1) SWRT_INST(6, 2, 2)
+    SWRT_INST(7, 4, 1) SWRT_INST(7, 2, 2)
+    SWRT_INST(2, 12, 1) SWRT_INST(2, 6, 2)
+    SWRT_INST(3, 8, 1) SWRT_INST(3, 4, 2)
+    SWRT_INST(4, 6, 1) SWRT_INST(4, 3, 2)
+    SWRT_INST(1, 24, 1) SWRT_INST(1, 12, 2)
+#undef SWRT_INST
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace swrt

@@ -1,0 +1,895 @@
+// swrt_api.cu -- the C ABI of libswrt.so (include/swrt.h): handle, flow upload, packet state,
+// evaluation, fused stepping, diagnostics.  Host logic only; all arithmetic is in the kernels.
+#include "../../include/swrt.h"
+#include "swrt_internal.h"
+
+#include <cufft.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace swrt;
+
+namespace {
+
+std::string g_create_error;
+
+enum Subset { SUB_SIX = 0, SUB_SEVEN = 1, SUB_UV = 2, SUB_UVH = 3, SUB_COUNT = 4 };
+const int kSubsetN[SUB_COUNT] = {6, 7, 2, 3};
+const int kSubsetIds[SUB_COUNT][kMaxPlanes] = {
+    {0, 1, 2, 3, 4, 5, 0}, {0, 1, 2, 3, 4, 5, 6}, {0, 1, 0, 0, 0, 0, 0}, {0, 1, 6, 0, 0, 0, 0}};
+
+struct Stack {
+    bool geom_ready = false;
+    PackGeom g{};
+    double* slot[2] = {nullptr, nullptr};
+    bool slot_valid[2] = {false, false};
+    double* blend = nullptr;
+};
+
+}  // namespace
+
+struct swrt_handle {
+    swrt_params p{};
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // packets
+    int64_t n = 0, cap = 0;
+    double *x = nullptr, *y = nullptr, *k = nullptr, *l = nullptr, *a = nullptr;
+    // spectral source planes per slot
+    bool slot_set[2] = {false, false};
+    int slot_npl[2] = {0, 0};
+    double2* planes[2][kMaxPlanes] = {};
+    Stack stacks[SUB_COUNT];
+    // lagrange grids per slot (node-interleaved, always 7 planes wide when H given else 6)
+    double* grid[2] = {nullptr, nullptr};
+    double* grid_blend = nullptr;
+    int grid_npl = 0;
+    // scratch
+    int64_t scratch_cap = 0;
+    double* e[kMaxPlanes] = {};
+    double *xs = nullptr, *ys = nullptr, *ax = nullptr, *ay = nullptr, *om = nullptr, *Om = nullptr;
+    double* diag_dev = nullptr;
+    double* edges_dev = nullptr; int edges_cap = 0;
+    unsigned long long* counts_dev = nullptr; int counts_cap = 0;
+    // instrumentation
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing_valid = false;
+    int last_nlaunch = 0;
+    int mtiles = 0;
+};
+
+namespace {
+
+int fail(swrt_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(h, expr)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? SWRT_ERR_ALLOC : SWRT_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define REQUIRE(h, cond, code, ...) \
+    do { if (!(cond)) return fail(h, code, __VA_ARGS__); } while (0)
+
+template <typename T> void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+int pick_mtiles(const swrt_handle* h, int64_t n) {
+    if (h->mtiles == 1 || h->mtiles == 2) return h->mtiles;
+    (void)n;
+    return 1;
+}
+
+int ensure_scratch(swrt_handle* h, int64_t n) {
+    if (n <= h->scratch_cap) return SWRT_OK;
+    for (auto& p : h->e) dfree(p);
+    dfree(h->xs); dfree(h->ys); dfree(h->ax); dfree(h->ay); dfree(h->om); dfree(h->Om);
+    size_t b = (size_t)n * sizeof(double);
+    for (auto& p : h->e) CU(h, cudaMalloc(&p, b));
+    CU(h, cudaMalloc(&h->xs, b)); CU(h, cudaMalloc(&h->ys, b)); CU(h, cudaMalloc(&h->ax, b));
+    CU(h, cudaMalloc(&h->ay, b)); CU(h, cudaMalloc(&h->om, b)); CU(h, cudaMalloc(&h->Om, b));
+    h->scratch_cap = n;
+    return SWRT_OK;
+}
+
+int ensure_packets(swrt_handle* h, int64_t n) {
+    if (n > h->cap) {
+        dfree(h->x); dfree(h->y); dfree(h->k); dfree(h->l); dfree(h->a);
+        size_t b = (size_t)n * sizeof(double);
+        CU(h, cudaMalloc(&h->x, b)); CU(h, cudaMalloc(&h->y, b)); CU(h, cudaMalloc(&h->k, b));
+        CU(h, cudaMalloc(&h->l, b)); CU(h, cudaMalloc(&h->a, b));
+        h->cap = n;
+    }
+    h->n = n;
+    return SWRT_OK;
+}
+
+// ---- spectral stacks ---------------------------------------------------------------------------
+int ensure_stack(swrt_handle* h, int sub, int slot, int mtiles) {
+    Stack& s = h->stacks[sub];
+    if (!s.geom_ready || (s.g.G != make_geom(h->p.nx, kSubsetN[sub], kSubsetIds[sub], mtiles).G)) {
+        s.g = make_geom(h->p.nx, kSubsetN[sub], kSubsetIds[sub], mtiles);
+        s.geom_ready = true;
+        for (int i = 0; i < 2; i++) { dfree(s.slot[i]); s.slot_valid[i] = false; }
+        dfree(s.blend);
+    }
+    if (s.slot_valid[slot]) return SWRT_OK;
+    REQUIRE(h, h->slot_set[slot], SWRT_ERR_STATE, "flow slot %d has not been set", slot);
+    REQUIRE(h, h->slot_npl[slot] >= (sub == SUB_SEVEN || sub == SUB_UVH ? 7 : 6), SWRT_ERR_STATE,
+            "flow slot %d has no H plane (needed by this scheme)", slot);
+    if (!s.slot[slot]) CU(h, cudaMalloc(&s.slot[slot], s.g.total_doubles * sizeof(double)));
+    const double2* src[kMaxPlanes];
+    for (int i = 0; i < kMaxPlanes; i++) src[i] = h->planes[slot][i] ? h->planes[slot][i] : h->planes[slot][0];
+    launch_pack(s.g, src, s.slot[slot], h->stream);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    s.slot_valid[slot] = true;
+    return SWRT_OK;
+}
+
+// returns the device stack holding (1-alpha)*slot0 + alpha*slot1 for this subset
+int active_stack(swrt_handle* h, int sub, double alpha, int mtiles, const double** out, PackGeom* g) {
+    int rc = ensure_stack(h, sub, 0, mtiles);
+    if (rc) return rc;
+    Stack& s = h->stacks[sub];
+    *g = s.g;
+    if (alpha == 0.0) { *out = s.slot[0]; return SWRT_OK; }
+    REQUIRE(h, h->slot_set[1], SWRT_ERR_STATE, "alpha = %g but flow slot 1 has not been set", alpha);
+    rc = ensure_stack(h, sub, 1, mtiles);
+    if (rc) return rc;
+    if (alpha == 1.0) { *out = s.slot[1]; return SWRT_OK; }
+    if (!s.blend) CU(h, cudaMalloc(&s.blend, s.g.total_doubles * sizeof(double)));
+    launch_axpby(s.blend, s.slot[0], s.slot[1], 1.0 - alpha, alpha, s.g.total_doubles, h->stream);
+    h->launches++;
+    *out = s.blend;
+    return SWRT_OK;
+}
+
+int active_grid(swrt_handle* h, double alpha, const double** out) {
+    REQUIRE(h, h->grid[0], SWRT_ERR_STATE, "flow slot 0 has not been set");
+    if (alpha == 0.0) { *out = h->grid[0]; return SWRT_OK; }
+    REQUIRE(h, h->grid[1], SWRT_ERR_STATE, "alpha = %g but flow slot 1 has not been set", alpha);
+    if (alpha == 1.0) { *out = h->grid[1]; return SWRT_OK; }
+    size_t nd = (size_t)h->p.nx * h->p.nx * h->grid_npl;
+    if (!h->grid_blend) CU(h, cudaMalloc(&h->grid_blend, nd * sizeof(double)));
+    launch_axpby(h->grid_blend, h->grid[0], h->grid[1], 1.0 - alpha, alpha, nd, h->stream);
+    h->launches++;
+    *out = h->grid_blend;
+    return SWRT_OK;
+}
+
+void invalidate_slot(swrt_handle* h, int slot) {
+    for (auto& s : h->stacks) s.slot_valid[slot] = false;
+}
+
+// evaluate subset planes at device positions into device outputs out[c] (c indexes subset planes)
+int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd, const double* yd,
+             double* const* out) {
+    if (n == 0) return SWRT_OK;
+    if (h->p.mode == SWRT_MODE_SPECTRAL) {
+        int mt = pick_mtiles(h, n);
+        SpecArgs a{};
+        int rc = active_stack(h, sub, alpha, mt, &a.stack, &a.g);
+        if (rc) return rc;
+        a.n = n; a.xin = xd; a.yin = yd;
+        for (int c = 0; c < kSubsetN[sub]; c++) a.out[c] = out[c];
+        a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
+        CU(h, launch_spectral(a, SPEC_EVAL, mt, h->num_sms, h->stream));
+        h->launches++;
+        return SWRT_OK;
+    }
+    LagArgs a{};
+    int rc = active_grid(h, alpha, &a.grid);
+    if (rc) return rc;
+    REQUIRE(h, !(sub == SUB_SEVEN || sub == SUB_UVH) || h->grid_npl == 7, SWRT_ERR_STATE, "no H grid was set");
+    a.nx = h->p.nx; a.npl = h->grid_npl; a.n = n; a.xin = xd; a.yin = yd;
+    for (int c = 0; c < kSubsetN[sub]; c++) a.out[kSubsetIds[sub][c]] = out[c];
+    a.dx = h->p.L / h->p.nx; a.bump = h->p.bump;
+    CU(h, launch_lagrange_eval(a, h->stream));
+    h->launches++;
+    return SWRT_OK;
+}
+
+int d2h(swrt_handle* h, double* dst, const double* src, int64_t n) {
+    if (!dst || n == 0) return SWRT_OK;
+    CU(h, cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return SWRT_OK;
+}
+int h2d(swrt_handle* h, double* dst, const double* src, int64_t n) {
+    if (n == 0) return SWRT_OK;
+    CU(h, cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return SWRT_OK;
+}
+
+// ---- cuFFT-backed g2k / k2g on the device (setup path) -------------------------------------------
+__global__ void real_to_complex_kernel(const double* __restrict__ in, double2* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(in[i], 0.0);
+}
+// g2k.m:5-9: keep kx=-kmax..kmax, ky=0..kmax of fft2(fg)/nx^2.  full[ky'*nx + kx'] (x fastest)
+__global__ void extract_half_kernel(const double2* __restrict__ full, int nx, double2* __restrict__ half) {
+    int nkx = nx - 1, nky = nx / 2, kmax = nx / 2 - 1;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nkx * nky) return;
+    int kx = idx % nkx - kmax, ky = idx / nkx;
+    int ix = kx < 0 ? kx + nx : kx;
+    double2 v = full[(size_t)ky * nx + ix];
+    double s = 1.0 / ((double)nx * (double)nx);
+    half[idx] = make_double2(v.x * s, v.y * s);
+}
+// fulspec.m:10-19 scattered into FFT order (no fftshift needed): full[ky'*nx + kx']
+__global__ void fulspec_kernel(const double2* __restrict__ half, int nx, double2* __restrict__ full) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nx * nx) return;
+    int nkx = nx - 1, kmax = nx / 2 - 1;
+    int ixp = idx % nx, iyp = idx / nx;
+    int kx = ixp <= nx / 2 ? ixp : ixp - nx;     // nx/2 is the (zeroed) Nyquist line
+    int ky = iyp <= nx / 2 ? iyp : iyp - nx;
+    double2 v = make_double2(0.0, 0.0);
+    if (kx != nx / 2 && ky != nx / 2 && kx >= -kmax && ky >= -kmax) {
+        if (ky > 0) v = half[(size_t)ky * nkx + kx + kmax];
+        else if (ky < 0) { v = half[(size_t)(-ky) * nkx + (-kx) + kmax]; v.y = -v.y; }
+        else {
+            if (kx >= 0) v = half[kx + kmax];
+            else { v = half[-kx + kmax]; v.y = -v.y; }
+        }
+    }
+    full[idx] = v;
+}
+__global__ void take_real_kernel(const double2* __restrict__ in, double* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i].x;
+}
+
+struct FftWork {
+    int nx = 0; cufftHandle plan = 0; bool has_plan = false; double2* full = nullptr;
+    ~FftWork() { if (has_plan) cufftDestroy(plan); if (full) cudaFree(full); }
+    int init(int nx_, cudaStream_t st, std::string& err) {
+        nx = nx_;
+        if (cudaMalloc(&full, (size_t)nx * nx * sizeof(double2)) != cudaSuccess) { err = "cudaMalloc(fft work) failed"; return SWRT_ERR_ALLOC; }
+        if (cufftPlan2d(&plan, nx, nx, CUFFT_Z2Z) != CUFFT_SUCCESS) { err = "cufftPlan2d failed"; return SWRT_ERR_CUDA; }
+        has_plan = true;
+        cufftSetStream(plan, st);
+        return SWRT_OK;
+    }
+};
+
+// grid (device, column-major real) -> half-plane coefficients (device double2, kx fastest)
+int g2k_dev(FftWork& w, const double* grid_dev, double2* half_dev, cudaStream_t st, std::string& err) {
+    size_t n = (size_t)w.nx * w.nx;
+    real_to_complex_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grid_dev, w.full, n);
+    if (cufftExecZ2Z(w.plan, (cufftDoubleComplex*)w.full, (cufftDoubleComplex*)w.full, CUFFT_FORWARD) != CUFFT_SUCCESS) {
+        err = "cufftExecZ2Z(forward) failed"; return SWRT_ERR_CUDA;
+    }
+    int nh = (w.nx - 1) * (w.nx / 2);
+    extract_half_kernel<<<(nh + 255) / 256, 256, 0, st>>>(w.full, w.nx, half_dev);
+    return SWRT_OK;
+}
+int k2g_dev(FftWork& w, const double2* half_dev, double* grid_dev, cudaStream_t st, std::string& err) {
+    size_t n = (size_t)w.nx * w.nx;
+    fulspec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(half_dev, w.nx, w.full);
+    if (cufftExecZ2Z(w.plan, (cufftDoubleComplex*)w.full, (cufftDoubleComplex*)w.full, CUFFT_INVERSE) != CUFFT_SUCCESS) {
+        err = "cufftExecZ2Z(inverse) failed"; return SWRT_ERR_CUDA;
+    }
+    take_real_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.full, grid_dev, n);
+    return SWRT_OK;
+}
+
+__global__ void interleave_complex_kernel(const double* __restrict__ re, const double* __restrict__ im,
+                                          double2* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(re[i], im ? im[i] : 0.0);
+}
+
+// upload a host complex plane (separate re/im) into a device double2 plane
+int upload_plane(swrt_handle* h, const double* re, const double* im, size_t n, double2** dst, double* tmp_re,
+                 double* tmp_im) {
+    if (!*dst) CU(h, cudaMalloc(dst, n * sizeof(double2)));
+    CU(h, cudaMemcpyAsync(tmp_re, re, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (im) CU(h, cudaMemcpyAsync(tmp_im, im, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    interleave_complex_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(tmp_re, im ? tmp_im : nullptr, *dst, n);
+    h->launches++;
+    return SWRT_OK;
+}
+
+// build the Lagrange grid of a slot from its spectral planes (k2g of every plane): grid_U.m:11-17
+int grid_from_planes(swrt_handle* h, int slot) {
+    const int nx = h->p.nx, npl = h->slot_npl[slot];
+    FftWork w;
+    int rc = w.init(nx, h->stream, h->err);
+    if (rc) return rc;
+    std::vector<double*> tmp(npl, nullptr);
+    size_t n = (size_t)nx * nx;
+    for (int c = 0; c < npl; c++) {
+        CU(h, cudaMalloc(&tmp[c], n * sizeof(double)));
+        rc = k2g_dev(w, h->planes[slot][c], tmp[c], h->stream, h->err);
+        if (rc) return rc;
+        h->launches += 3;
+    }
+    if (h->grid_npl != npl) { dfree(h->grid[0]); dfree(h->grid[1]); dfree(h->grid_blend); h->grid_npl = npl; }
+    if (!h->grid[slot]) CU(h, cudaMalloc(&h->grid[slot], n * npl * sizeof(double)));
+    launch_interleave_grid(tmp.data(), npl, nx, h->grid[slot], h->stream);
+    h->launches++;
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (auto p : tmp) cudaFree(p);
+    return SWRT_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int swrt_version(void) { return SWRT_VERSION; }
+
+int swrt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* swrt_last_error(const swrt_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int swrt_create(const swrt_params* p, swrt_handle** out) {
+    if (!p || !out) return fail(nullptr, SWRT_ERR_ARG, "swrt_create: null argument");
+    *out = nullptr;
+    if (p->nx < 8 || (p->nx & 1)) return fail(nullptr, SWRT_ERR_ARG, "swrt_create: nx must be even and >= 8 (got %d)", p->nx);
+    if (!(p->L > 0)) return fail(nullptr, SWRT_ERR_ARG, "swrt_create: L must be positive");
+    if (p->mode != SWRT_MODE_SPECTRAL && p->mode != SWRT_MODE_LAGRANGE6)
+        return fail(nullptr, SWRT_ERR_ARG, "swrt_create: unknown mode %d", p->mode);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: no CUDA device (%s); libswrt has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (p->device < 0 || p->device >= ndev) return fail(nullptr, SWRT_ERR_ARG, "swrt_create: device %d out of range", p->device);
+    if (cudaSetDevice(p->device) != cudaSuccess) return fail(nullptr, SWRT_ERR_CUDA, "cudaSetDevice failed");
+    swrt_handle* h = new (std::nothrow) swrt_handle();
+    if (!h) return fail(nullptr, SWRT_ERR_ALLOC, "out of host memory");
+    h->p = *p;
+    if (!(h->p.bump > 0)) h->p.bump = 1e-13;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete h;
+        return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: device is sm_%d%d; libswrt is built for sm_100a only", prop.major, prop.minor);
+    }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaMalloc(&h->diag_dev, (8 + 296 * 8) * sizeof(double)) != cudaSuccess) {
+        swrt_destroy(h);
+        return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: stream/event/alloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = h;
+    return SWRT_OK;
+}
+
+int swrt_destroy(swrt_handle* h) {
+    if (!h) return SWRT_OK;
+    cudaSetDevice(h->p.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    dfree(h->x); dfree(h->y); dfree(h->k); dfree(h->l); dfree(h->a);
+    for (int s = 0; s < 2; s++) {
+        for (auto& p : h->planes[s]) dfree(p);
+        dfree(h->grid[s]);
+    }
+    dfree(h->grid_blend);
+    for (auto& st : h->stacks) { dfree(st.slot[0]); dfree(st.slot[1]); dfree(st.blend); }
+    for (auto& p : h->e) dfree(p);
+    dfree(h->xs); dfree(h->ys); dfree(h->ax); dfree(h->ay); dfree(h->om); dfree(h->Om);
+    dfree(h->diag_dev); dfree(h->edges_dev); dfree(h->counts_dev);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SWRT_OK;
+}
+
+// ---- flow upload ------------------------------------------------------------------------------
+static int finish_spectral_slot(swrt_handle* h, int slot, int npl) {
+    h->slot_set[slot] = true;
+    h->slot_npl[slot] = npl;
+    invalidate_slot(h, slot);
+    if (h->p.mode == SWRT_MODE_LAGRANGE6) return grid_from_planes(h, slot);
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int swrt_set_flow_spectral(swrt_handle* h, int slot, const double* psik_re, const double* psik_im, int nkx, int nky,
+                           double u_mean) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
+    REQUIRE(h, psik_re && psik_im, SWRT_ERR_ARG, "null psi-hat pointer");
+    REQUIRE(h, nkx == h->p.nx - 1 && nky == h->p.nx / 2, SWRT_ERR_ARG, "psi-hat must be %d x %d (got %d x %d)",
+            h->p.nx - 1, h->p.nx / 2, nkx, nky);
+    size_t n = (size_t)nkx * nky;
+    double *tr = nullptr, *ti = nullptr;
+    double2* psi = nullptr;
+    CU(h, cudaMalloc(&tr, n * 8)); CU(h, cudaMalloc(&ti, n * 8));
+    int rc = upload_plane(h, psik_re, psik_im, n, &psi, tr, ti);
+    if (rc == SWRT_OK) {
+        for (int c = 0; c < 6 && rc == SWRT_OK; c++)
+            if (!h->planes[slot][c] && cudaMalloc(&h->planes[slot][c], n * sizeof(double2)) != cudaSuccess)
+                rc = fail(h, SWRT_ERR_ALLOC, "cudaMalloc(plane) failed");
+    }
+    if (rc == SWRT_OK) {
+        dfree(h->planes[slot][6]);
+        // wavenumbers kappa*kx: integers when L = 2*pi (SpectralScheme.m:12-25), 2*pi/L-scaled
+        // otherwise (qg2layersw_raytrace.m:19-22)
+        const double kappa = 2.0 * M_PI / h->p.L;
+        launch_psi_to_planes(psi, h->planes[slot], nkx, nky, kappa, u_mean, h->stream);
+        h->launches++;
+        rc = finish_spectral_slot(h, slot, 6);
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tr); cudaFree(ti); cudaFree(psi);
+    return rc;
+}
+
+int swrt_set_flow_planes_spectral(swrt_handle* h, int slot, const double* const* planes_re,
+                                  const double* const* planes_im, int nplanes, int nkx, int nky) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
+    REQUIRE(h, nplanes == 6 || nplanes == 7, SWRT_ERR_ARG, "nplanes must be 6 or 7");
+    REQUIRE(h, planes_re && planes_im, SWRT_ERR_ARG, "null plane table");
+    REQUIRE(h, nkx == h->p.nx - 1 && nky == h->p.nx / 2, SWRT_ERR_ARG, "planes must be %d x %d", h->p.nx - 1, h->p.nx / 2);
+    size_t n = (size_t)nkx * nky;
+    double *tr = nullptr, *ti = nullptr;
+    CU(h, cudaMalloc(&tr, n * 8)); CU(h, cudaMalloc(&ti, n * 8));
+    int rc = SWRT_OK;
+    for (int c = 0; c < nplanes && rc == SWRT_OK; c++) {
+        if (!planes_re[c] || !planes_im[c]) { rc = fail(h, SWRT_ERR_ARG, "null plane %d", c); break; }
+        rc = upload_plane(h, planes_re[c], planes_im[c], n, &h->planes[slot][c], tr, ti);
+        if (rc == SWRT_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, SWRT_ERR_CUDA, "sync failed");
+    }
+    if (nplanes == 6) dfree(h->planes[slot][6]);
+    if (rc == SWRT_OK) rc = finish_spectral_slot(h, slot, nplanes);
+    cudaFree(tr); cudaFree(ti);
+    return rc;
+}
+
+int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* v, const double* ux, const double* uy,
+                       const double* vx, const double* vy, const double* H, int nx) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
+    REQUIRE(h, nx == h->p.nx, SWRT_ERR_ARG, "grid is %d^2 but the handle was created with nx = %d", nx, h->p.nx);
+    REQUIRE(h, u && v && ux && uy && vx && vy, SWRT_ERR_ARG, "null grid plane");
+    const double* src[kMaxPlanes] = {u, v, ux, uy, vx, vy, H};
+    const int npl = H ? 7 : 6;
+    size_t n = (size_t)nx * nx;
+    std::vector<double*> tmp(npl, nullptr);
+    int rc = SWRT_OK;
+    for (int c = 0; c < npl; c++) {
+        CU(h, cudaMalloc(&tmp[c], n * 8));
+        CU(h, cudaMemcpyAsync(tmp[c], src[c], n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (h->p.mode == SWRT_MODE_LAGRANGE6) {
+        if (h->grid_npl != npl) { dfree(h->grid[0]); dfree(h->grid[1]); dfree(h->grid_blend); h->grid_npl = npl; }
+        if (!h->grid[slot]) CU(h, cudaMalloc(&h->grid[slot], n * npl * 8));
+        launch_interleave_grid(tmp.data(), npl, nx, h->grid[slot], h->stream);
+        h->launches++;
+        h->slot_set[slot] = true; h->slot_npl[slot] = npl;
+    } else {
+        // SPECTRAL mode: g2k of every plane on the device (g2k.m:5-9)
+        FftWork w;
+        rc = w.init(nx, h->stream, h->err);
+        size_t nh = (size_t)(nx - 1) * (nx / 2);
+        for (int c = 0; c < npl && rc == SWRT_OK; c++) {
+            if (!h->planes[slot][c] && cudaMalloc(&h->planes[slot][c], nh * sizeof(double2)) != cudaSuccess) {
+                rc = fail(h, SWRT_ERR_ALLOC, "cudaMalloc(plane) failed"); break;
+            }
+            rc = g2k_dev(w, tmp[c], h->planes[slot][c], h->stream, h->err);
+            h->launches += 3;
+        }
+        if (npl == 6) dfree(h->planes[slot][6]);
+        if (rc == SWRT_OK) { h->slot_set[slot] = true; h->slot_npl[slot] = npl; invalidate_slot(h, slot); }
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaStreamSynchronize(h->stream);
+    for (auto p : tmp) cudaFree(p);
+    if (rc == SWRT_OK) CU(h, cudaGetLastError());
+    return rc;
+}
+
+// ---- packets ----------------------------------------------------------------------------------
+int swrt_packets_alloc_dev(swrt_handle* h, int64_t n) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, n >= 0, SWRT_ERR_ARG, "negative packet count");
+    int rc = ensure_packets(h, n);
+    if (rc) return rc;
+    launch_fill(h->a, 1.0, n, h->stream);
+    return SWRT_OK;
+}
+
+int swrt_packets_dev(swrt_handle* h, double** x, double** y, double** k, double** l, double** a) {
+    if (!h) return SWRT_ERR_ARG;
+    if (x) *x = h->x; if (y) *y = h->y; if (k) *k = h->k; if (l) *l = h->l; if (a) *a = h->a;
+    return SWRT_OK;
+}
+
+int swrt_set_packets(swrt_handle* h, int64_t n, const double* x, const double* y, const double* k, const double* l,
+                     const double* a) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, n >= 0, SWRT_ERR_ARG, "negative packet count");
+    REQUIRE(h, n == 0 || (x && y && k && l), SWRT_ERR_ARG, "null packet array");
+    int rc = ensure_packets(h, n);
+    if (rc) return rc;
+    if ((rc = h2d(h, h->x, x, n)) || (rc = h2d(h, h->y, y, n)) || (rc = h2d(h, h->k, k, n)) || (rc = h2d(h, h->l, l, n)))
+        return rc;
+    if (a) { if ((rc = h2d(h, h->a, a, n))) return rc; }
+    else { launch_fill(h->a, 1.0, n, h->stream); h->launches++; }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int swrt_get_packets(swrt_handle* h, double* x, double* y, double* k, double* l, double* a) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    int rc;
+    if ((rc = d2h(h, x, h->x, h->n)) || (rc = d2h(h, y, h->y, h->n)) || (rc = d2h(h, k, h->k, h->n)) ||
+        (rc = d2h(h, l, h->l, h->n)) || (rc = d2h(h, a, h->a, h->n)))
+        return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int64_t swrt_num_packets(const swrt_handle* h) { return h ? h->n : 0; }
+
+// ---- evaluation -------------------------------------------------------------------------------
+int swrt_eval(swrt_handle* h, double alpha, double* U, double* V, double* Ux, double* Uy, double* Vx, double* Vy) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
+    int rc = ensure_scratch(h, h->n);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    if ((rc = eval_dev(h, SUB_SIX, alpha, h->n, h->x, h->y, h->e))) return rc;
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timing_valid = true; h->last_nlaunch = 1;
+    double* outs[6] = {U, V, Ux, Uy, Vx, Vy};
+    for (int c = 0; c < 6; c++)
+        if ((rc = d2h(h, outs[c], h->e[c], h->n))) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int swrt_eval_at(swrt_handle* h, double alpha, int64_t n, const double* x, const double* y, double* U, double* V,
+                 double* Ux, double* Uy, double* Vx, double* Vy, double* H) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, n >= 0 && (n == 0 || (x && y)), SWRT_ERR_ARG, "bad positions");
+    REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
+    if (n == 0) return SWRT_OK;
+    int rc = ensure_scratch(h, n);
+    if (rc) return rc;
+    if ((rc = h2d(h, h->xs, x, n)) || (rc = h2d(h, h->ys, y, n))) return rc;
+    const int sub = H ? SUB_SEVEN : SUB_SIX;
+    if ((rc = eval_dev(h, sub, alpha, n, h->xs, h->ys, h->e))) return rc;
+    double* outs[7] = {U, V, Ux, Uy, Vx, Vy, H};
+    for (int c = 0; c < 7; c++)
+        if ((rc = d2h(h, outs[c], h->e[c], n))) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int swrt_rhs(swrt_handle* h, double alpha, double* dxdt, double* dydt, double* dkdt, double* dldt) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
+    int rc = ensure_scratch(h, h->n);
+    if (rc) return rc;
+    if ((rc = eval_dev(h, SUB_SIX, alpha, h->n, h->x, h->y, h->e))) return rc;
+    // odefun uses Cg (not Cg^2): qgsw_raytrace.m:262
+    const double Cg = sqrt(h->p.gH);
+    launch_rhs(h->n, h->k, h->l, h->e, h->p.f, Cg, h->xs, h->ys, h->ax, h->ay, h->stream);
+    h->launches++;
+    if ((rc = d2h(h, dxdt, h->xs, h->n)) || (rc = d2h(h, dydt, h->ys, h->n)) || (rc = d2h(h, dkdt, h->ax, h->n)) ||
+        (rc = d2h(h, dldt, h->ay, h->n)))
+        return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int swrt_interpolate(int device, const double* x, const double* y, int64_t n, const double* F, int nx, int ny,
+                     double dx, double dy, double bump, double* FI) {
+    if (!x || !y || !F || !FI || n < 0 || nx < 1 || ny < 1) return fail(nullptr, SWRT_ERR_ARG, "swrt_interpolate: bad argument");
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_interpolate: no CUDA device"); }
+    if (n == 0) return SWRT_OK;
+    double *dF = nullptr, *dx_ = nullptr, *dy_ = nullptr, *dout = nullptr;
+    int rc = SWRT_OK;
+    size_t nb = (size_t)n * 8, gb = (size_t)nx * ny * 8;
+    if (cudaMalloc(&dF, gb) || cudaMalloc(&dx_, nb) || cudaMalloc(&dy_, nb) || cudaMalloc(&dout, nb)) rc = fail(nullptr, SWRT_ERR_ALLOC, "swrt_interpolate: cudaMalloc failed");
+    if (!rc) {
+        cudaMemcpy(dF, F, gb, cudaMemcpyHostToDevice);
+        cudaMemcpy(dx_, x, nb, cudaMemcpyHostToDevice);
+        cudaMemcpy(dy_, y, nb, cudaMemcpyHostToDevice);
+        cudaError_t e = launch_interpolate_single(dF, nx, ny, dx_, dy_, n, dx, dy, bump > 0 ? bump : 1e-13, dout, 0);
+        if (e == cudaSuccess) e = cudaMemcpy(FI, dout, nb, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(nullptr, SWRT_ERR_CUDA, "swrt_interpolate: %s", cudaGetErrorString(e));
+    }
+    cudaFree(dF); cudaFree(dx_); cudaFree(dy_); cudaFree(dout);
+    return rc;
+}
+
+// ---- stepping ---------------------------------------------------------------------------------
+static int step_leapfrog(swrt_handle* h, double dt, int nsteps, double alpha0, double dalpha) {
+    const bool steady = (dalpha == 0.0);
+    const int outer = steady ? 1 : nsteps;
+    const int inner = steady ? nsteps : 1;
+    int rc;
+    h->last_nlaunch = 0;
+    for (int j = 0; j < outer; j++) {
+        const double alpha = alpha0 + j * dalpha;
+        if (h->p.mode == SWRT_MODE_SPECTRAL) {
+            int mt = pick_mtiles(h, h->n);
+            SpecArgs a{};
+            if ((rc = active_stack(h, SUB_SIX, alpha, mt, &a.stack, &a.g))) return rc;
+            a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l;
+            a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
+            a.f2 = h->p.f * h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = inner;
+            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
+            CU(h, launch_spectral(a, SPEC_LEAPFROG, mt, h->num_sms, h->stream));
+        } else {
+            LagArgs a{};
+            if ((rc = active_grid(h, alpha, &a.grid))) return rc;
+            a.nx = h->p.nx; a.npl = h->grid_npl; a.n = h->n;
+            a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
+            a.dx = h->p.L / h->p.nx; a.bump = h->p.bump; a.f = h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = inner;
+            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
+            CU(h, launch_lagrange_leapfrog(a, h->stream));
+        }
+        h->launches++; h->last_nlaunch++;
+    }
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timing_valid = true;
+    return SWRT_OK;
+}
+
+static int step_rk4(swrt_handle* h, bool xka, double dt, int nsteps, double alpha0, double dalpha) {
+    int rc;
+    const double C0 = sqrt(h->p.gH);
+    h->last_nlaunch = 0;
+    if (h->p.mode == SWRT_MODE_LAGRANGE6) {
+        REQUIRE(h, !xka || h->grid_npl == 7, SWRT_ERR_STATE, "step_packet_xka needs the H grid");
+        const bool steady = (dalpha == 0.0);
+        const int outer = steady ? 1 : nsteps, inner = steady ? nsteps : 1;
+        for (int j = 0; j < outer; j++) {
+            LagArgs a{};
+            if ((rc = active_grid(h, alpha0 + j * dalpha, &a.grid))) return rc;
+            a.nx = h->p.nx; a.npl = h->grid_npl; a.n = h->n;
+            a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
+            a.dx = h->p.L / h->p.nx; a.bump = h->p.bump; a.f = h->p.f; a.gH = h->p.gH; a.C0 = C0; a.dt = dt; a.nsteps = inner;
+            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
+            CU(h, launch_lagrange_rk4(a, xka, h->stream));
+            h->launches++; h->last_nlaunch++;
+        }
+        CU(h, cudaEventRecord(h->ev1, h->stream));
+        h->timing_valid = true;
+        return SWRT_OK;
+    }
+    // SPECTRAL: continuous ray equations composed point-wise; 5 evaluations per step
+    if ((rc = ensure_scratch(h, h->n))) return rc;
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    for (int j = 0; j < nsteps; j++) {
+        const double alpha = alpha0 + j * dalpha;
+        Rk4Args r{};
+        r.n = h->n; r.x = h->x; r.y = h->y; r.k = h->k; r.l = h->l; r.a = h->a;
+        r.xs = h->xs; r.ys = h->ys; r.ax = h->ax; r.ay = h->ay;
+        r.dt = dt; r.f = h->p.f; r.C0 = C0; r.xka = xka;
+        for (int stage = 0; stage < 4; stage++) {
+            const double* px = stage == 0 ? h->x : h->xs;
+            const double* py = stage == 0 ? h->y : h->ys;
+            if (xka) {
+                double* outs[3] = {h->e[0], h->e[1], h->e[6]};
+                if ((rc = eval_dev(h, SUB_UVH, alpha, h->n, px, py, outs))) return rc;
+            } else if (stage == 0) {
+                // u,v and the gradients at the OLD position in one six-plane pass (step_packet.m:58-61)
+                // (later stages only overwrite e[0], e[1], so e[2..5] keep the old-position gradients)
+                if ((rc = eval_dev(h, SUB_SIX, alpha, h->n, px, py, h->e))) return rc;
+            } else {
+                double* outs[2] = {h->e[0], h->e[1]};
+                if ((rc = eval_dev(h, SUB_UV, alpha, h->n, px, py, outs))) return rc;
+            }
+            h->last_nlaunch++;
+            r.stage = stage; r.u = h->e[0]; r.v = h->e[1]; r.H = h->e[6];
+            launch_rk4_stage(r, h->stream);
+            h->launches++;
+        }
+        if (xka) {
+            if ((rc = eval_dev(h, SUB_SEVEN, alpha, h->n, h->xs, h->ys, h->e))) return rc;
+            h->last_nlaunch++;
+        }
+        r.u = h->e[0]; r.v = h->e[1]; r.H = h->e[6];
+        r.ux = h->e[2]; r.uy = h->e[3]; r.vx = h->e[4]; r.vy = h->e[5];
+        launch_rk4_final(r, h->stream);
+        h->launches++;
+    }
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timing_valid = true;
+    return SWRT_OK;
+}
+
+int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, nsteps >= 0, SWRT_ERR_ARG, "negative step count");
+    REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
+    REQUIRE(h, std::isfinite(dt), SWRT_ERR_ARG, "dt is not finite");
+    if (nsteps == 0 || h->n == 0) return SWRT_OK;
+    int rc;
+    switch (scheme) {
+        case SWRT_SCHEME_LEAPFROG: rc = step_leapfrog(h, dt, nsteps, alpha0, dalpha); break;
+        case SWRT_SCHEME_RK4_PACKET: rc = step_rk4(h, false, dt, nsteps, alpha0, dalpha); break;
+        case SWRT_SCHEME_RK4_XKA: rc = step_rk4(h, true, dt, nsteps, alpha0, dalpha); break;
+        default: return fail(h, SWRT_ERR_ARG, "unknown scheme %d", scheme);
+    }
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+// ---- diagnostics ------------------------------------------------------------------------------
+static int compute_omega(swrt_handle* h, double alpha, bool need_abs) {
+    int rc = ensure_scratch(h, h->n);
+    if (rc) return rc;
+    if (need_abs) {
+        REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "absolute frequency needs a flow");
+        double* outs[2] = {h->e[0], h->e[1]};
+        if (h->p.mode == SWRT_MODE_SPECTRAL) {
+            if ((rc = eval_dev(h, SUB_UV, alpha, h->n, h->x, h->y, outs))) return rc;
+        } else if ((rc = eval_dev(h, SUB_SIX, alpha, h->n, h->x, h->y, h->e))) return rc;
+    }
+    launch_omega(h->n, h->k, h->l, h->e[0], h->e[1], h->p.f, h->p.gH, h->om, need_abs ? h->Om : nullptr, h->stream);
+    h->launches++;
+    return SWRT_OK;
+}
+
+int swrt_omega(swrt_handle* h, double alpha, double* omega, double* Omega_abs) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = compute_omega(h, alpha, Omega_abs != nullptr);
+    if (rc) return rc;
+    if ((rc = d2h(h, omega, h->om, h->n)) || (rc = d2h(h, Omega_abs, h->Om, h->n))) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges, int nedges, uint64_t* counts,
+                    int accumulate) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, edges && counts && nedges >= 2 && nedges <= 4096, SWRT_ERR_ARG, "bad edges (2 <= nedges <= 4096)");
+    REQUIRE(h, kind == SWRT_HIST_INTRINSIC || kind == SWRT_HIST_ABSOLUTE, SWRT_ERR_ARG, "bad histogram kind");
+    for (int i = 1; i < nedges; i++) REQUIRE(h, edges[i] >= edges[i - 1], SWRT_ERR_ARG, "edges must be non-decreasing");
+    int rc = compute_omega(h, alpha, kind == SWRT_HIST_ABSOLUTE);
+    if (rc) return rc;
+    if (nedges > h->edges_cap) { dfree(h->edges_dev); CU(h, cudaMalloc(&h->edges_dev, (size_t)nedges * 8)); h->edges_cap = nedges; }
+    if (nedges - 1 > h->counts_cap) { dfree(h->counts_dev); CU(h, cudaMalloc(&h->counts_dev, (size_t)(nedges - 1) * 8)); h->counts_cap = nedges - 1; }
+    CU(h, cudaMemcpyAsync(h->edges_dev, edges, (size_t)nedges * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->counts_dev, 0, (size_t)(nedges - 1) * 8, h->stream));
+    launch_hist(h->n, kind == SWRT_HIST_ABSOLUTE ? h->Om : h->om, h->edges_dev, nedges, h->counts_dev, h->stream);
+    h->launches++;
+    std::vector<uint64_t> tmp(nedges - 1);
+    CU(h, cudaMemcpyAsync(tmp.data(), h->counts_dev, (size_t)(nedges - 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    for (int i = 0; i < nedges - 1; i++) counts[i] = accumulate ? counts[i] + tmp[i] : tmp[i];
+    return SWRT_OK;
+}
+
+int swrt_diag(swrt_handle* h, double alpha, double out[8]) {
+    if (!h || !out) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = compute_omega(h, alpha, h->slot_set[0]);
+    if (rc) return rc;
+    launch_diag(h->n, h->x, h->y, h->k, h->l, h->a, h->om, h->slot_set[0] ? h->Om : h->om, h->diag_dev, h->stream);
+    h->launches += 2;
+    CU(h, cudaMemcpyAsync(out, h->diag_dev, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+// ---- spectral <-> grid kit ----------------------------------------------------------------------
+int swrt_g2k(int device, const double* fg, int nx, double* fk_re, double* fk_im) {
+    if (!fg || !fk_re || !fk_im || nx < 4 || (nx & 1)) return fail(nullptr, SWRT_ERR_ARG, "swrt_g2k: bad argument");
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_g2k: no CUDA device"); }
+    FftWork w; std::string err;
+    int rc = w.init(nx, 0, err);
+    if (rc) return fail(nullptr, rc, "swrt_g2k: %s", err.c_str());
+    size_t n = (size_t)nx * nx, nh = (size_t)(nx - 1) * (nx / 2);
+    double* dg = nullptr; double2* dh = nullptr;
+    if (cudaMalloc(&dg, n * 8) || cudaMalloc(&dh, nh * 16)) { cudaFree(dg); return fail(nullptr, SWRT_ERR_ALLOC, "swrt_g2k: cudaMalloc failed"); }
+    cudaMemcpy(dg, fg, n * 8, cudaMemcpyHostToDevice);
+    rc = g2k_dev(w, dg, dh, 0, err);
+    std::vector<double2> hh(nh);
+    if (!rc && cudaMemcpy(hh.data(), dh, nh * 16, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SWRT_ERR_CUDA;
+    cudaFree(dg); cudaFree(dh);
+    if (rc) return fail(nullptr, rc, "swrt_g2k: %s", err.c_str());
+    for (size_t i = 0; i < nh; i++) { fk_re[i] = hh[i].x; fk_im[i] = hh[i].y; }
+    return SWRT_OK;
+}
+
+int swrt_k2g(int device, const double* fk_re, const double* fk_im, int nx, double* fg) {
+    if (!fg || !fk_re || !fk_im || nx < 4 || (nx & 1)) return fail(nullptr, SWRT_ERR_ARG, "swrt_k2g: bad argument");
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_k2g: no CUDA device"); }
+    FftWork w; std::string err;
+    int rc = w.init(nx, 0, err);
+    if (rc) return fail(nullptr, rc, "swrt_k2g: %s", err.c_str());
+    size_t n = (size_t)nx * nx, nh = (size_t)(nx - 1) * (nx / 2);
+    std::vector<double2> hh(nh);
+    for (size_t i = 0; i < nh; i++) hh[i] = make_double2(fk_re[i], fk_im[i]);
+    double* dg = nullptr; double2* dh = nullptr;
+    if (cudaMalloc(&dg, n * 8) || cudaMalloc(&dh, nh * 16)) { cudaFree(dg); return fail(nullptr, SWRT_ERR_ALLOC, "swrt_k2g: cudaMalloc failed"); }
+    cudaMemcpy(dh, hh.data(), nh * 16, cudaMemcpyHostToDevice);
+    rc = k2g_dev(w, dh, dg, 0, err);
+    if (!rc && cudaMemcpy(fg, dg, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SWRT_ERR_CUDA;
+    cudaFree(dg); cudaFree(dh);
+    if (rc) return fail(nullptr, rc, "swrt_k2g: %s", err.c_str());
+    return SWRT_OK;
+}
+
+// ---- instrumentation --------------------------------------------------------------------------
+int64_t swrt_launch_count(swrt_handle* h, int reset) {
+    if (!h) return 0;
+    int64_t v = h->launches;
+    if (reset) h->launches = 0;
+    return v;
+}
+
+double swrt_last_kernel_ms(swrt_handle* h, int* nlaunch) {
+    if (!h || !h->timing_valid) return -1.0;
+    cudaSetDevice(h->p.device);
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+    if (nlaunch) *nlaunch = h->last_nlaunch;
+    return (double)ms;
+}
+
+double swrt_work_per_eval(const swrt_handle* h, int nplanes) {
+    if (!h) return 0.0;
+    if (h->p.mode == SWRT_MODE_SPECTRAL) {
+        // executed DMMA flops per packet per evaluation: (kx>=0 count) * (ky count) * planes * 8
+        // flops per folded complex MAC ... = 2 * nplanes * nx^2 for the unpadded problem
+        return 2.0 * nplanes * (double)h->p.nx * (double)h->p.nx;
+    }
+    return 36.0 * nplanes * 8.0;   // gathered bytes
+}
+
+int swrt_synchronize(swrt_handle* h) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int swrt_set_tuning(swrt_handle* h, int mtiles, int reserved) {
+    (void)reserved;
+    if (!h) return SWRT_ERR_ARG;
+    REQUIRE(h, mtiles >= 0 && mtiles <= 2, SWRT_ERR_ARG, "mtiles must be 0, 1 or 2");
+    h->mtiles = mtiles;
+    return SWRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// swrt_internal.h -- shared declarations between the kernels and the C-ABI layer of libswrt.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+
+namespace swrt {
+
+constexpr int kMaxPlanes = 7;          // u,v,ux,uy,vx,vy,eta_g
+constexpr int kConsumerWarps = 8;      // MMA warps per CTA in the spectral kernel
+constexpr int kSpecThreads = kConsumerWarps * 32;         // warp 0 lane 0 also issues the bulk copies
+
+// ---------------------------------------------------------------------------------------------
+// Packed coefficient stack ("B operand") geometry.  See DESIGN.md section 3.
+//   A pass covers KYP = 4*G consecutive ky for all NPL planes: NT = NPL*G n-tiles of 8 real
+//   columns (4 complex (re,im) column pairs).  One k-step covers two kx>=0 wavenumbers
+//   (rows Er(kx),Ei(kx),Er(kx+1),Ei(kx+1)).  Storage order (doubles):
+//       [pass][kstep][tile pair tp][lane 0..31][2]
+//   so that lane reads ONE 16-byte word per pair of n-tiles and a whole chunk of KC k-steps is
+//   one contiguous block that a single cp.async.bulk moves into shared memory.
+// ---------------------------------------------------------------------------------------------
+struct PackGeom {
+    int nx, nkx, nky, kmax;
+    int npl, G, NT;
+    int npass;            // ceil(nky / (4G))
+    int ksteps;           // k-steps per pass, padded to a multiple of kc
+    int kc;               // k-steps per chunk (pipeline stage)
+    int chunks_per_eval;  // npass * ksteps / kc
+    int nstages;
+    size_t chunk_doubles; // kc * NT * 32
+    size_t total_doubles; // npass * ksteps * NT * 32
+    int plane_ids[kMaxPlanes];   // which of the 7 source planes each stack plane is
+};
+
+PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles);
+
+// one source slot: complex planes on the device, [plane][ky][kx+kmax] as double2 (kx fastest)
+void launch_pack(const PackGeom& g, const double2* const* planes_dev /*[7] device ptrs (host array)*/,
+                 double* stack_dev, cudaStream_t st);
+void launch_psi_to_planes(const double2* psik, double2* const* planes /*host array of 6 dev ptrs*/,
+                          int nkx, int nky, double kappa, double u_mean, cudaStream_t st);
+void launch_axpby(double* out, const double* a, const double* b, double wa, double wb, size_t n,
+                  cudaStream_t st);
+
+struct SpecArgs {
+    const double* stack;
+    PackGeom g;
+    long long n;            // packets
+    const double* xin; const double* yin;    // EVAL: positions
+    double* x; double* y; double* k; double* l;   // LEAPFROG: state (in/out)
+    double* out[kMaxPlanes];                  // EVAL: outputs per stack plane (may be null)
+    double dx, nxd;         // grid spacing and nx as double
+    double f2, gH, dt;
+    int nsteps;
+};
+
+enum SpecMode { SPEC_EVAL = 0, SPEC_LEAPFROG = 1 };
+
+// returns cudaError; grid is sized to the SM count (persistent CTAs)
+cudaError_t launch_spectral(const SpecArgs& a, int mode, int mtiles, int num_sms, cudaStream_t st);
+size_t spectral_smem_bytes(const PackGeom& g);
+
+// ---------------------------------------------------------------------------------------------
+// Lagrange (reference-semantics) kernels.  Grid planes are node-interleaved: F[ix][iy][NPL].
+// ---------------------------------------------------------------------------------------------
+struct LagArgs {
+    const double* grid;     // [nx][nx][npl] doubles
+    int nx, npl;            // npl = 6 or 7 (7th = H)
+    long long n;
+    const double* xin; const double* yin;
+    double* x; double* y; double* k; double* l; double* a;
+    double* out[kMaxPlanes];
+    double dx, bump;
+    double f, gH, C0, dt;
+    int nsteps;
+};
+void launch_interleave_grid(const double* const* planes_dev, int npl, int nx, double* grid, cudaStream_t st);
+cudaError_t launch_lagrange_eval(const LagArgs& a, cudaStream_t st);
+cudaError_t launch_lagrange_leapfrog(const LagArgs& a, cudaStream_t st);
+cudaError_t launch_lagrange_rk4(const LagArgs& a, bool xka, cudaStream_t st);
+cudaError_t launch_interpolate_single(const double* F, int nx, int ny, const double* x, const double* y,
+                                      long long n, double dx, double dy, double bump, double* out, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// Elementwise / diagnostics kernels
+// ---------------------------------------------------------------------------------------------
+struct Rk4Args {   // spectral-mode RK4 glue (point-wise composition), all device SoA arrays
+    long long n;
+    double *x, *y, *k, *l, *a;
+    double *xs, *ys;                 // stage positions
+    double *ax, *ay;                 // accumulated (x1+2x2+2x3+x4)
+    const double *u, *v, *H;         // evaluated at stage position
+    const double *ux, *uy, *vx, *vy; // final evaluation
+    double dt, f, C0;
+    int stage; bool xka;
+};
+void launch_rk4_stage(const Rk4Args& a, cudaStream_t st);
+void launch_rk4_final(const Rk4Args& a, cudaStream_t st);
+void launch_rhs(long long n, const double* k, const double* l, const double* const* e6, double f, double Cg,
+                double* dxdt, double* dydt, double* dkdt, double* dldt, cudaStream_t st);
+void launch_omega(long long n, const double* k, const double* l, const double* u, const double* v,
+                  double f, double gH, double* omega, double* Omega_abs, cudaStream_t st);
+void launch_hist(long long n, const double* w, const double* edges_dev, int nedges,
+                 unsigned long long* counts_dev, cudaStream_t st);
+void launch_diag(long long n, const double* x, const double* y, const double* k, const double* l, const double* a,
+                 const double* omega, const double* Omega_abs, double* out8_dev, cudaStream_t st);
+void launch_fill(double* p, double v, long long n, cudaStream_t st);
+
+}  // namespace swrt

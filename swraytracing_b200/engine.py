@@ -1,0 +1,286 @@
+"""ctypes binding of libswrt.so (include/swrt.h) -- the tested skin of the C ABI.
+
+``Engine`` is a thin 1:1 wrapper: every method is one C call on host numpy buffers.  There is no
+CPU fallback: if the library is missing or no CUDA device is present the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libswrt.so"
+
+MODE_SPECTRAL, MODE_LAGRANGE6 = 0, 1
+SCHEME_LEAPFROG, SCHEME_RK4_PACKET, SCHEME_RK4_XKA = 0, 1, 2
+HIST_INTRINSIC, HIST_ABSOLUTE = 0, 1
+
+_dp = C.POINTER(C.c_double)
+
+
+class SwrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libswrt error {code}: {msg}")
+        self.code = code
+
+
+class _Params(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("mode", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32),
+                ("L", C.c_double), ("f", C.c_double), ("gH", C.c_double), ("bump", C.c_double)]
+
+
+# name -> (restype, argtypes); every symbol include/swrt.h declares
+SIGNATURES = {
+    "swrt_version": (C.c_int, []),
+    "swrt_device_count": (C.c_int, []),
+    "swrt_create": (C.c_int, [C.POINTER(_Params), C.POINTER(C.c_void_p)]),
+    "swrt_destroy": (C.c_int, [C.c_void_p]),
+    "swrt_last_error": (C.c_char_p, [C.c_void_p]),
+    "swrt_set_flow_spectral": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_double]),
+    "swrt_set_flow_planes_spectral": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_dp), C.POINTER(_dp), C.c_int, C.c_int, C.c_int]),
+    "swrt_set_flow_grid": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int]),
+    "swrt_set_packets": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
+    "swrt_get_packets": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp]),
+    "swrt_num_packets": (C.c_int64, [C.c_void_p]),
+    "swrt_packets_alloc_dev": (C.c_int, [C.c_void_p, C.c_int64]),
+    "swrt_packets_dev": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5),
+    "swrt_eval": (C.c_int, [C.c_void_p, C.c_double] + [_dp] * 6),
+    "swrt_eval_at": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, _dp, _dp] + [_dp] * 7),
+    "swrt_rhs": (C.c_int, [C.c_void_p, C.c_double] + [_dp] * 4),
+    "swrt_interpolate": (C.c_int, [C.c_int, _dp, _dp, C.c_int64, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp]),
+    "swrt_step": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
+    "swrt_hist_omega": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_uint64), C.c_int]),
+    "swrt_diag": (C.c_int, [C.c_void_p, C.c_double, _dp]),
+    "swrt_omega": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp]),
+    "swrt_g2k": (C.c_int, [C.c_int, _dp, C.c_int, _dp, _dp]),
+    "swrt_k2g": (C.c_int, [C.c_int, _dp, _dp, C.c_int, _dp]),
+    "swrt_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
+    "swrt_last_kernel_ms": (C.c_double, [C.c_void_p, C.POINTER(C.c_int)]),
+    "swrt_work_per_eval": (C.c_double, [C.c_void_p, C.c_int]),
+    "swrt_synchronize": (C.c_int, [C.c_void_p]),
+    "swrt_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+}
+
+_lib = None
+
+
+def load_library(path: os.PathLike | None = None):
+    """dlopen libswrt.so and declare every prototype.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(f"{p} not found: build it with `make` or `python -c 'import __graft_entry__ as g; g.build()'`"
+                                " (libswrt has no CPU fallback)")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _colmajor(a):
+    """host array -> flat column-major (MATLAB) float64 copy"""
+    return np.asfortranarray(np.asarray(a, dtype=np.float64)).ravel(order="F").copy()
+
+
+class Engine:
+    """One handle = one CUDA device + device-resident packets + flow stacks."""
+
+    def __init__(self, nx, L, f, gH, mode=MODE_SPECTRAL, device=0, bump=1e-13):
+        self.lib = load_library()
+        self.nx, self.L, self.f, self.gH, self.mode, self.device = int(nx), float(L), float(f), float(gH), int(mode), int(device)
+        self._h = C.c_void_p()
+        prm = _Params(self.nx, self.mode, self.device, 0, self.L, self.f, self.gH, float(bump))
+        rc = self.lib.swrt_create(C.byref(prm), C.byref(self._h))
+        if rc != 0:
+            raise SwrtError(rc, (self.lib.swrt_last_error(None) or b"").decode())
+        self.n = 0
+
+    # -- plumbing --
+    def _check(self, rc):
+        if rc != 0:
+            raise SwrtError(rc, (self.lib.swrt_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.swrt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- flow --
+    def set_flow_spectral(self, psik, slot=0, u_mean=0.0):
+        """psik: complex (nkx, nky) array in g2k layout (kx = first index)."""
+        psik = np.asarray(psik, dtype=np.complex128)
+        nkx, nky = psik.shape
+        re, im = _colmajor(psik.real), _colmajor(psik.imag)
+        self._check(self.lib.swrt_set_flow_spectral(self._h, slot, _ptr(re), _ptr(im), nkx, nky, float(u_mean)))
+
+    def set_flow_planes_spectral(self, planes, slot=0):
+        planes = [np.asarray(p, dtype=np.complex128) for p in planes]
+        nkx, nky = planes[0].shape
+        res = [_colmajor(p.real) for p in planes]
+        ims = [_colmajor(p.imag) for p in planes]
+        n = len(planes)
+        tr = (_dp * n)(*[_ptr(a) for a in res])
+        ti = (_dp * n)(*[_ptr(a) for a in ims])
+        self._check(self.lib.swrt_set_flow_planes_spectral(self._h, slot, tr, ti, n, nkx, nky))
+
+    def set_flow_grid(self, u, v, ux, uy, vx, vy, H=None, slot=0):
+        """gridded planes F[ix, iy] (x = first index, as MATLAB)."""
+        arrs = [_colmajor(a) for a in (u, v, ux, uy, vx, vy)]
+        h = _colmajor(H) if H is not None else None
+        nx = np.asarray(u).shape[0]
+        self._check(self.lib.swrt_set_flow_grid(self._h, slot, *[_ptr(a) for a in arrs], _ptr(h), nx))
+
+    # -- packets --
+    def set_packets(self, x, y, k, l, a=None):
+        x, y, k, l = map(_f64, (x, y, k, l))
+        a = _f64(a) if a is not None else None
+        self.n = x.size
+        self._check(self.lib.swrt_set_packets(self._h, self.n, _ptr(x), _ptr(y), _ptr(k), _ptr(l), _ptr(a)))
+
+    def get_packets(self, with_a=False):
+        n = self.n
+        out = [np.empty(n) for _ in range(5 if with_a else 4)]
+        ptrs = [_ptr(o) for o in out] + ([] if with_a else [None])
+        self._check(self.lib.swrt_get_packets(self._h, *ptrs))
+        return tuple(out)
+
+    def alloc_packets_dev(self, n):
+        self._check(self.lib.swrt_packets_alloc_dev(self._h, int(n)))
+        self.n = int(n)
+
+    def packets_dev(self):
+        """raw device pointers (ints) of the SoA buffers x,y,k,l,a"""
+        ps = [C.c_void_p() for _ in range(5)]
+        self._check(self.lib.swrt_packets_dev(self._h, *[C.byref(p) for p in ps]))
+        return tuple(p.value for p in ps)
+
+    # -- evaluation --
+    def eval(self, alpha=0.0):
+        outs = [np.empty(self.n) for _ in range(6)]
+        self._check(self.lib.swrt_eval(self._h, float(alpha), *[_ptr(o) for o in outs]))
+        return np.stack(outs)
+
+    def eval_at(self, x, y, alpha=0.0, with_H=False):
+        x, y = _f64(x).ravel(), _f64(y).ravel()
+        n = x.size
+        outs = [np.empty(n) for _ in range(7 if with_H else 6)]
+        ptrs = [_ptr(o) for o in outs] + ([] if with_H else [None])
+        self._check(self.lib.swrt_eval_at(self._h, float(alpha), n, _ptr(x), _ptr(y), *ptrs))
+        return np.stack(outs)
+
+    def rhs(self, alpha=0.0):
+        outs = [np.empty(self.n) for _ in range(4)]
+        self._check(self.lib.swrt_rhs(self._h, float(alpha), *[_ptr(o) for o in outs]))
+        return tuple(outs)
+
+    def step(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
+        self._check(self.lib.swrt_step(self._h, int(scheme), float(dt), int(nsteps), float(alpha0), float(dalpha)))
+
+    # -- diagnostics --
+    def hist_omega(self, edges, kind=HIST_INTRINSIC, alpha=0.0, counts=None):
+        edges = _f64(edges)
+        acc = counts is not None
+        if counts is None:
+            counts = np.zeros(edges.size - 1, dtype=np.uint64)
+        self._check(self.lib.swrt_hist_omega(self._h, kind, float(alpha), _ptr(edges), edges.size,
+                                             counts.ctypes.data_as(C.POINTER(C.c_uint64)), int(acc)))
+        return counts
+
+    def diag(self, alpha=0.0):
+        out = np.empty(8)
+        self._check(self.lib.swrt_diag(self._h, float(alpha), _ptr(out)))
+        return out
+
+    def omega(self, alpha=0.0, absolute=True):
+        om = np.empty(self.n)
+        Om = np.empty(self.n) if absolute else None
+        self._check(self.lib.swrt_omega(self._h, float(alpha), _ptr(om), _ptr(Om)))
+        return om, Om
+
+    # -- instrumentation --
+    def launch_count(self, reset=False):
+        return int(self.lib.swrt_launch_count(self._h, int(reset)))
+
+    def last_kernel_ms(self):
+        n = C.c_int(0)
+        ms = self.lib.swrt_last_kernel_ms(self._h, C.byref(n))
+        return float(ms), int(n.value)
+
+    def work_per_eval(self, nplanes=6):
+        return float(self.lib.swrt_work_per_eval(self._h, nplanes))
+
+    def synchronize(self):
+        self._check(self.lib.swrt_synchronize(self._h))
+
+    def set_tuning(self, mtiles=0):
+        self._check(self.lib.swrt_set_tuning(self._h, int(mtiles), 0))
+
+
+# -- handle-free helpers ---------------------------------------------------------------------------
+
+def interpolate_dev(x, y, F, dx, dy, bump=1e-13, device=0):
+    lib = load_library()
+    x = _f64(x); shp = x.shape
+    x = x.ravel(); y = _f64(y).ravel()
+    F = np.asarray(F, dtype=np.float64)
+    nx, ny = F.shape
+    Ff = _colmajor(F)
+    out = np.empty(x.size)
+    rc = lib.swrt_interpolate(device, _ptr(x), _ptr(y), x.size, _ptr(Ff), nx, ny, float(dx), float(dy), float(bump), _ptr(out))
+    if rc != 0:
+        raise SwrtError(rc, (lib.swrt_last_error(None) or b"").decode())
+    return out.reshape(shp)
+
+
+def g2k_dev(fg, device=0):
+    lib = load_library()
+    fg = np.asarray(fg, dtype=np.float64)
+    nx = fg.shape[0]
+    nkx, nky = nx - 1, nx // 2
+    re = np.empty(nkx * nky); im = np.empty(nkx * nky)
+    f = _colmajor(fg)
+    rc = lib.swrt_g2k(device, _ptr(f), nx, _ptr(re), _ptr(im))
+    if rc != 0:
+        raise SwrtError(rc, (lib.swrt_last_error(None) or b"").decode())
+    return (re + 1j * im).reshape((nkx, nky), order="F")
+
+
+def k2g_dev(fk, device=0):
+    lib = load_library()
+    fk = np.asarray(fk, dtype=np.complex128)
+    nx = fk.shape[0] + 1
+    re, im = _colmajor(fk.real), _colmajor(fk.imag)
+    out = np.empty(nx * nx)
+    rc = lib.swrt_k2g(device, _ptr(re), _ptr(im), nx, _ptr(out))
+    if rc != 0:
+        raise SwrtError(rc, (lib.swrt_last_error(None) or b"").decode())
+    return out.reshape((nx, nx), order="F")
