@@ -1,6 +1,6 @@
 # Builds libswrt.so (sm_100a only) and the CPU oracle's C restatement.
 NVCC      ?= nvcc
-CC        ?= gcc
+CC        := gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
 CSRC      := swraytracing_b200/csrc
@@ -19,7 +19,7 @@ $(LIB): $(OBJ)/spectral_kernels.o $(OBJ)/lagrange_kernels.o $(OBJ)/misc_kernels.
 
 $(ORACLE): oracle/swrt_oracle.c
 	@mkdir -p oracle/build
-	$(CC) -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -o $@ $< -lm
+	$(CC) -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp -fPIC -shared -o $@ $< -lm
 
 clean:
 	rm -rf $(OBJ) $(LIB) oracle/build

@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- packet-steps/sec of the SWRaytracing hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One bench "step" = one fused pass of the hot path over the whole packet batch: ``--substeps`` leapfrog
+steps (ode_symplectic.m:33-37: half drift, six-plane spectral evaluation, kick, half drift) in ONE
+kernel launch, followed by the omega histogram (the diagnostic the multi-GPU path all-reduces).
+Workload at N=1 = BASELINE.json configs[1] (C2: steady 128^2 spectral grid, 65,536 packets); for N>1
+every rank holds its own 65,536-packet shard (weak scaling, no data-path collective; one integer
+histogram all-reduce per step).
+
+Keys (see the task contract): value = device-resident throughput (CUDA events on the handle's
+stream, L2 flushed between timed steps, max over ranks); e2e = the same through the C ABI with HOST
+buffers (pinned h2d of x,y,k,l + step + d2h of x,y,k,l inside the timed region); roofline = executed
+DMMA flops of the dominant kernel / its event-timed duration against the measured fp64 peak;
+cpu_baseline = the oracle's C port of the reference's own path (6x6 Lagrange leapfrog) on the host
+cores.  ``--impl reference`` times that CPU port alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "packet-steps/sec (spectral U,gradU eval + symplectic step)"
+UNIT = "packet-steps/s"
+# fp64 roofline denominator: measured on this pool's B200 with tools/dgemm_peak.py (cuBLAS DGEMM
+# 8192^3, burst = sustained) and tools/fp64_peak.cu (DMMA m8n8k4 issue-rate microbenchmark);
+# MEASURED_PEAKS.json records no fp64 figure.  See profiles/r01_fp64_peak.json.
+FP64_DGEMM_TFLOPS = 35.5
+FP64_DMMA_TFLOPS = 37.1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="swrt", choices=["swrt", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--packets", type=int, default=0, help="packets per GPU (0 = the workload's own count)")
+    ap.add_argument("--substeps", type=int, default=16, help="fused leapfrog steps per bench step")
+    ap.add_argument("--mtiles", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lagrange", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port; the only places bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def _cpu_setup(w):
+    from swraytracing_b200 import workloads as W
+    if id(w) not in _CPU_CACHE:
+        planes = W.planes_from_psik(w.psik, w.L, w.u_mean)
+        _CPU_CACHE[id(w)] = [W._fulspec_ifft(p) for p in planes]      # gridded planes (what grid_U / SpectralScheme build)
+    return _CPU_CACHE[id(w)]
+
+
+def cpu_reference_rate(w, target_s=12.0, nsteps=8):
+    """packet-steps/s of the reference's own path -- ode_symplectic leapfrog with 6x6 Lagrange
+    interpolation of the six gridded planes (SpectralScheme.m:45-68, interpolate.m) -- restated in C
+    (oracle/swrt_oracle.c: orc_leapfrog_lagrange), all host threads.  Bounded sample of ~target_s."""
+    from oracle import c_oracle as CO
+    grids = _cpu_setup(w)
+    n = min(w.n_packets, 65536)
+    x, y, k, l = (a[:n].copy() for a in (w.x, w.y, w.k, w.l))
+    t0 = time.perf_counter()
+    CO.leapfrog_lagrange(x, y, k, l, grids, w.dx, w.f, w.gH, w.dt, nsteps)          # calibration (also warms caches)
+    t1 = time.perf_counter() - t0
+    reps = min(2000, max(1, int(target_s / max(t1, 1e-4))))
+    t0 = time.perf_counter()
+    CO.leapfrog_lagrange(x, y, k, l, grids, w.dx, w.f, w.gH, w.dt, nsteps * reps)
+    el = time.perf_counter() - t0
+    return n * nsteps * reps / el, CO.num_threads(), (f"{n} packets x {nsteps * reps} leapfrog steps of {w.name} ({el:.1f} s), "
+                                                       "6x6 Lagrange (reference semantics), C port + OpenMP")
+
+
+def cpu_spectral_rate(w, target_s=8.0):
+    """the dense Fourier-sum evaluation (what the GPU arm computes) as a C port on the host cores"""
+    from oracle import c_oracle as CO
+    from swraytracing_b200 import workloads as W
+    planes = W.planes_from_psik(w.psik, w.L)
+    n = 2048
+    x, y, k, l = (a[:n].copy() for a in (w.x, w.y, w.k, w.l))
+    t0 = time.perf_counter()
+    CO.leapfrog_spectral(x, y, k, l, planes, w.dx, w.nx, w.f, w.gH, w.dt, 1, precise=False)
+    t1 = time.perf_counter() - t0
+    reps = max(1, min(64, int(target_s / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    CO.leapfrog_spectral(x, y, k, l, planes, w.dx, w.nx, w.f, w.gH, w.dt, reps, precise=False)
+    el = time.perf_counter() - t0
+    return n * reps / el, CO.num_threads(), f"{n} packets x {reps} leapfrog steps, dense trig sum in double, C port + OpenMP ({el:.1f} s)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from swraytracing_b200 import workloads as W
+    w = W.make_workload(args.workload, n_packets=args.packets or None)
+    vals = []
+    t_each = max(1.0, min(10.0, 150.0 / max(1, args.steps + args.warmup)))
+    threads, sample = 1, ""
+    for _ in range(args.warmup):
+        cpu_reference_rate(w, target_s=t_each)
+    for _ in range(args.steps):
+        v, threads, sample = cpu_reference_rate(w, target_s=t_each)
+        vals.append(v)
+    value = float(np.median(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{w.name}: steady {w.nx}^2 spectral grid, {w.n_packets} packets, leapfrog (ode_symplectic)",
+                       "note": "reference's own CPU path (gridded planes + 6x6 Lagrange interpolate) restated in C; the MATLAB original cannot run here"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import swraytracing_b200 as S
+    from swraytracing_b200 import workloads as W
+    from swraytracing_b200.distributed import ShardedEnsemble
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the swrt arm has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = W.make_workload(args.workload, n_packets=args.packets or None, seed_packets=123 + rank)
+    n = w.n_packets
+    sub = args.substeps
+    eng = S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_SPECTRAL, device=local)
+    eng.set_tuning(args.mtiles)
+    eng.set_flow_spectral(w.psik, slot=0, u_mean=w.u_mean)
+    time_dependent = w.psik2 is not None
+    if time_dependent:
+        eng.set_flow_spectral(w.psik2, slot=1, u_mean=w.u_mean)
+    ens = ShardedEnsemble(eng, n * world, rank, world, dist, device=torch.device("cuda", local))
+    om_max = float(np.sqrt(w.f ** 2 + w.gH * 4 * (w.k ** 2 + w.l ** 2).max()))
+    edges = np.linspace(0.0, om_max, 300)            # 299 bins (analysis/load_data.m:38-39)
+
+    # pinned host staging for the e2e leg
+    pin = [torch.from_numpy(a.copy()).pin_memory() for a in (w.x, w.y, w.k, w.l)]
+    pin_np = [p.numpy() for p in pin]
+    out_pin = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(4)]
+    out_np = [p.numpy() for p in out_pin]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def alpha_args(step_idx):
+        if not time_dependent:
+            return 0.0, 0.0
+        return 0.5 / sub, 1.0 / sub       # time-centred alpha_j = (j + 1/2)/m over one flow step
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step_resident():
+        a0, da = alpha_args(0)
+        eng.step(S.SCHEME_LEAPFROG, w.dt, sub, a0, da)
+        return ens.hist_omega(edges)
+
+    def one_step_e2e():
+        eng.set_packets(*pin_np)                                     # h2d from pinned host memory
+        a0, da = alpha_args(0)
+        eng.step(S.SCHEME_LEAPFROG, w.dt, sub, a0, da)
+        import ctypes as C
+        eng._check(eng.lib.swrt_get_packets(eng._h, *[o.ctypes.data_as(C.POINTER(C.c_double)) for o in out_np], None))
+        return out_np
+
+    # ---- device-resident leg: `value` ----
+    eng.set_packets(w.x, w.y, w.k, w.l)
+    for _ in range(max(3, args.warmup)):
+        one_step_resident()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    eng.launch_count(reset=True)
+    step_ms = []
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                                        # flush L2 between timed iterations
+        torch.cuda.synchronize()
+        eng.timer_start()
+        counts = one_step_resident()
+        step_ms.append(eng.timer_stop())
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = eng.launch_count()
+    clocks = sampler.stop() if sampler else None
+
+    # dominant-kernel time: re-time the fused leapfrog kernel alone with its own event pair
+    k_ms = []
+    for i in range(min(args.steps, 10)):
+        flush.fill_(i & 0xFF); torch.cuda.synchronize()
+        a0, da = alpha_args(0)
+        eng.step(S.SCHEME_LEAPFROG, w.dt, sub, a0, da)
+        ms, nl = eng.last_kernel_ms()
+        k_ms.append(ms)
+    kernel_ms = float(np.mean(k_ms))
+
+    total_ms = float(np.sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = n * world * sub * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e leg: host buffers through the C ABI ----
+    for _ in range(2):
+        one_step_e2e()
+    barrier()
+    e2e_ms = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        one_step_e2e()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)             # host clock: the call blocks until d2h is done
+    e2e_total = float(np.sum(e2e_ms))
+    if dist is not None:
+        t = torch.tensor([e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = n * world * sub * args.steps / (e2e_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (spectral_kernel<6,4,1,LEAPFROG>) ----
+    flops_per_packet_step = eng.work_per_eval(6)                    # 12 nx^2 executed DMMA flops (folded +-kx)
+    flops_per_launch = flops_per_packet_step * n * sub
+    achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
+    roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
+                "frac": round(achieved / FP64_DGEMM_TFLOPS, 4), "traffic": None,
+                "kernel": "swrt::spectral_kernel<6,4,1,LEAPFROG> (fp64 DMMA m8n8k4)", "kernel_ms": round(kernel_ms, 4),
+                "flops_per_packet_step": flops_per_packet_step,
+                "peak_source": "measured: cuBLAS DGEMM 8192^3 on this pool's B200 (tools/dgemm_peak.py); DMMA issue peak 37.1 (tools/fp64_peak.cu); MEASURED_PEAKS.json has no fp64 entry",
+                "frac_of_dmma_issue_peak": round(achieved / FP64_DMMA_TFLOPS, 4),
+                "hbm_bytes_per_packet_step": 64.0 / sub}
+
+    # ---- reference-semantics mode (LAGRANGE6), reported beside the headline ----
+    lag = None
+    if not args.no_lagrange and rank == 0:
+        le = S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_LAGRANGE6, device=local)
+        le.set_flow_spectral(w.psik, u_mean=w.u_mean)
+        le.set_packets(w.x, w.y, w.k, w.l)
+        for _ in range(3):
+            le.step(S.SCHEME_LEAPFROG, w.dt, sub)
+        lms = []
+        for i in range(min(args.steps, 10)):
+            flush.fill_(i & 0xFF); torch.cuda.synchronize()
+            le.step(S.SCHEME_LEAPFROG, w.dt, sub)
+            lms.append(le.last_kernel_ms()[0])
+        lm = float(np.mean(lms))
+        gathered = le.work_per_eval(6) * n * sub
+        lag = {"value": n * sub / (lm * 1e-3), "unit": UNIT, "kernel_ms": round(lm, 4),
+               "gather_GBps": round(gathered / (lm * 1e-3) * 1e-9, 1),
+               "note": "LAGRANGE6 mode = the reference's own 6x6 stencil semantics (interpolate.m), L2-gather bound"}
+        le.close()
+
+    cpu = cpu_spec = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_reference_rate(w)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        v2, cores2, sample2 = cpu_spectral_rate(w)
+        cpu_spec = {"value": v2, "unit": UNIT, "cores": cores2, "kind": "port", "sample": sample2}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{w.name}: {'time-dependent' if time_dependent else 'steady'} {w.nx}^2 spectral grid, {n} packets/GPU, "
+                                       f"full-spectrum random-phase QG field, leapfrog (ode_symplectic)",
+                           "packets_per_gpu": n, "nx": w.nx, "substeps_per_step": sub, "mode": "SPECTRAL",
+                           "l2": "flushed between timed steps (256 MiB write)", "histogram_bins": 299,
+                           "parallelism": f"packets sharded x{world}, flow replicated"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n,
+                        "ms_per_step": e2e_total / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+                "wall_s_timed_region": round(wall, 3)}
+        if cpu:
+            line["cpu_baseline"] = cpu
+            line["cpu_baseline_spectral"] = cpu_spec
+        if lag:
+            line["lagrange6"] = lag
+        line["histogram_total"] = int(np.asarray(counts).sum())
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

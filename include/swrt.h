@@ -138,6 +138,13 @@ double  swrt_last_kernel_ms(swrt_handle* h, int* nlaunch);
 /* executed real fp64 flops (spectral) or gathered bytes (Lagrange) per packet per evaluation   */
 double  swrt_work_per_eval(const swrt_handle* h, int nplanes);
 int     swrt_synchronize(swrt_handle* h);
+/* run on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL = the handle's own) so
+ * that the caller's events (e.g. torch.cuda.Event on torch's current stream) bracket the work   */
+int     swrt_set_stream(swrt_handle* h, void* cuda_stream);
+/* device-side stopwatch on the handle's stream: start records an event, stop records another,
+ * waits for it and returns the elapsed milliseconds (<0 on error)                               */
+int     swrt_timer_start(swrt_handle* h);
+double  swrt_timer_stop(swrt_handle* h);
 /* tuning knob: 1 or 2 m-tiles per warp in the spectral kernel (0 = automatic)                  */
 int     swrt_set_tuning(swrt_handle* h, int mtiles, int reserved);
 

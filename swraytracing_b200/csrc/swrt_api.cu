@@ -36,6 +36,8 @@ struct swrt_handle {
     swrt_params p{};
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     std::string err;
     // packets
     int64_t n = 0, cap = 0;
@@ -370,12 +372,14 @@ int swrt_create(const swrt_params* p, swrt_handle** out) {
         delete h;
         return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: device is sm_%d%d; libswrt is built for sm_100a only", prop.major, prop.minor);
     }
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreate(&h->tm0) != cudaSuccess || cudaEventCreate(&h->tm1) != cudaSuccess ||
         cudaMalloc(&h->diag_dev, (8 + 296 * 8) * sizeof(double)) != cudaSuccess) {
         swrt_destroy(h);
         return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: stream/event/alloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
+    h->stream = h->own_stream;
     *out = h;
     return SWRT_OK;
 }
@@ -396,7 +400,9 @@ int swrt_destroy(swrt_handle* h) {
     dfree(h->diag_dev); dfree(h->edges_dev); dfree(h->counts_dev);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->tm0) cudaEventDestroy(h->tm0);
+    if (h->tm1) cudaEventDestroy(h->tm1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return SWRT_OK;
 }
@@ -882,6 +888,33 @@ int swrt_synchronize(swrt_handle* h) {
     CU(h, cudaSetDevice(h->p.device));
     CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
+}
+
+int swrt_set_stream(swrt_handle* h, void* cuda_stream) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return SWRT_OK;
+}
+
+int swrt_timer_start(swrt_handle* h) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    CU(h, cudaEventRecord(h->tm0, h->stream));
+    return SWRT_OK;
+}
+
+double swrt_timer_stop(swrt_handle* h) {
+    if (!h) return -1.0;
+    cudaSetDevice(h->p.device);
+    float ms = 0.f;
+    if (cudaEventRecord(h->tm1, h->stream) != cudaSuccess || cudaEventSynchronize(h->tm1) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, h->tm0, h->tm1) != cudaSuccess) {
+        h->err = "swrt_timer_stop: event timing failed";
+        return -1.0;
+    }
+    return (double)ms;
 }
 
 int swrt_set_tuning(swrt_handle* h, int mtiles, int reserved) {

@@ -1,0 +1,90 @@
+"""Multi-GPU layer: packets shard, the flow replicates, only histograms / diagnostics reduce.
+
+One process per GPU (torchrun); ``torch.distributed`` is plumbing only.  The step has NO data-path
+collective (packets are independent); the collectives are an integer SUM all-reduce
+of the omega / energy histogram (analysis/load_data.m:39-49) and of a handful of diagnostic
+scalars, once per diagnostic interval.  Integer histograms are bit-exact under any sharding.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """contiguous packet slice [lo, hi) owned by ``rank``."""
+    return (rank * n) // world, ((rank + 1) * n) // world
+
+
+class ShardedEnsemble:
+    """A rank-local engine holding this rank's packet shard.
+
+    ``engine`` is any object with the Engine methods used here (set_packets/get_packets/step/
+    hist_omega/diag); tests on CPU (gloo) pass an oracle-backed stand-in, production passes
+    ``swraytracing_b200.Engine`` bound to the local CUDA device."""
+
+    def __init__(self, engine, n_total, rank=0, world=1, dist=None, device=None):
+        self.engine, self.n_total, self.rank, self.world = engine, int(n_total), int(rank), int(world)
+        self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
+        self.dist = dist
+        self.device = device
+
+    # -- packets --
+    def set_packets_global(self, x, y, k, l, a=None):
+        s = slice(self.lo, self.hi)
+        self.engine.set_packets(x[s], y[s], k[s], l[s], None if a is None else a[s])
+
+    def step(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
+        self.engine.step(scheme, dt, nsteps, alpha0, dalpha)
+
+    # -- reductions --
+    def _allreduce_sum(self, arr_i64):
+        if self.dist is None or self.world == 1:
+            return arr_i64
+        import torch
+        t = torch.from_numpy(arr_i64.copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def hist_omega(self, edges, kind=0, alpha=0.0):
+        """global histcounts over all shards: local u64 counts -> SUM all-reduce (bit-exact)."""
+        local = self.engine.hist_omega(edges, kind, alpha)
+        return self._allreduce_sum(local.astype(np.int64)).astype(np.uint64)
+
+    def energy_vs_omega(self, edges, kind=0, alpha=0.0):
+        """energy = centre .* counts (analysis/load_data.m:40,49)"""
+        counts = self.hist_omega(edges, kind, alpha)
+        edges = np.asarray(edges, dtype=np.float64)
+        centre = (edges[1:] + edges[:-1]) / 2
+        return centre, centre * counts.astype(np.float64), counts
+
+    def diag(self, alpha=0.0):
+        """sum/max/min diagnostics all-reduced: sums add, extrema reduce with max/min."""
+        d = np.asarray(self.engine.diag(alpha), dtype=np.float64)
+        if self.dist is None or self.world == 1:
+            return d
+        import torch
+        sums = torch.tensor([d[0], d[1], d[4], d[5], d[6], d[7]], dtype=torch.float64)
+        mx = torch.tensor([d[2]], dtype=torch.float64)
+        mn = torch.tensor([d[3]], dtype=torch.float64)
+        if self.device is not None:
+            sums, mx, mn = sums.to(self.device), mx.to(self.device), mn.to(self.device)
+        self.dist.all_reduce(sums, op=self.dist.ReduceOp.SUM)
+        self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(mn, op=self.dist.ReduceOp.MIN)
+        s = sums.cpu().numpy()
+        return np.array([s[0], s[1], float(mx.cpu()[0]), float(mn.cpu()[0]), s[2], s[3], s[4], s[5]])
+
+    def gather_packets(self):
+        """all shards' packets on every rank (for tests / small runs)."""
+        loc = self.engine.get_packets()
+        if self.dist is None or self.world == 1:
+            return loc
+        import torch
+        out = []
+        for arr in loc:
+            pieces = [None] * self.world
+            self.dist.all_gather_object(pieces, arr)
+            out.append(np.concatenate(pieces))
+        return tuple(out)

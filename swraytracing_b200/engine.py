@@ -62,6 +62,9 @@ SIGNATURES = {
     "swrt_work_per_eval": (C.c_double, [C.c_void_p, C.c_int]),
     "swrt_synchronize": (C.c_int, [C.c_void_p]),
     "swrt_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "swrt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "swrt_timer_start": (C.c_int, [C.c_void_p]),
+    "swrt_timer_stop": (C.c_double, [C.c_void_p]),
 }
 
 _lib = None
@@ -240,6 +243,18 @@ class Engine:
 
     def synchronize(self):
         self._check(self.lib.swrt_synchronize(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.swrt_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def timer_start(self):
+        self._check(self.lib.swrt_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = float(self.lib.swrt_timer_stop(self._h))
+        if ms < 0:
+            raise SwrtError(-3, "timer failed")
+        return ms
 
     def set_tuning(self, mtiles=0):
         self._check(self.lib.swrt_set_tuning(self._h, int(mtiles), 0))

@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference's MATLAB calling surface for the packet hot path.
+
+Same function names, argument order/meaning and array shapes as the reference (file:line cited per
+function, relative to the reference tree), implemented on top of the C ABI (engine.py ->
+libswrt.so).  Everything numeric runs on the GPU; there is no CPU fallback -- constructing any of
+these without the CUDA library raises.
+
+Array conventions follow the reference: gridded fields are ``F[ix, iy]`` (x first, MATLAB
+``ndgrid``), spectral fields are ``fk[kx + kmax, ky]`` (g2k layout), packet positions for the
+scheme classes are ``(T, 2, Np)`` and for the ``qgsw`` drivers ``(Np, 2)``.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import engine as _e
+from .engine import Engine, MODE_LAGRANGE6, MODE_SPECTRAL, SCHEME_LEAPFROG, SCHEME_RK4_PACKET, SCHEME_RK4_XKA
+
+# ------------------------------------------------------------------------------------------------
+# spectral <-> grid kit (setup path; device cuFFT through the C ABI)
+# ------------------------------------------------------------------------------------------------
+
+def g2k(fg, device=0):
+    """qg_flow_ray_trace/g2k.m:1-9"""
+    return _e.g2k_dev(fg, device)
+
+
+def k2g(fk, device=0):
+    """qg_flow_ray_trace/k2g.m:1-6 (+ fulspec.m:10-19)"""
+    return _e.k2g_dev(fk, device)
+
+
+def grid_U(qk, K_d2, K2, kx_, ky_, shear_strength=0.0, device=0):
+    """qg_flow_ray_trace/grid_U.m:1-18 -> dict(u,v,ux,uy,vx,vy) of nx x nx grids.
+    The six k2g transforms run on the device; the ik-multiplications are O(nx^2) setup."""
+    psik = -np.asarray(qk) / (K_d2 + K2)
+    vk = 1j * kx_ * psik
+    uk = -1j * ky_ * psik
+    planes = {"u": uk, "v": vk, "ux": 1j * kx_ * uk, "uy": 1j * ky_ * uk, "vx": 1j * kx_ * vk, "vy": 1j * ky_ * vk}
+    out = {name: k2g(p, device) for name, p in planes.items()}
+    out["u"] = out["u"] + shear_strength
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# interpolate / interpolate_par / interpolate2 / interpolate_U
+# ------------------------------------------------------------------------------------------------
+
+def interpolate(x, y, F, dx, dy, device=0):
+    """ray_trace_sw/interpolate.m:1-50 -- FI = interpolate(x,y,F,dx,dy), bump 1e-13."""
+    return _e.interpolate_dev(x, y, F, dx, dy, 1e-13, device)
+
+
+def interpolate_par(x, y, F, dx, dy, device=0):
+    """interpolate_par.m:1-53 -- the same stencil with bump 1e-10."""
+    return _e.interpolate_dev(x, y, F, dx, dy, 1e-10, device)
+
+
+def interpolate2(x, y, F, dx, dy, device=0):
+    """interpolate2.m:1-19 is an abandoned ``interp2(...,'cubic')`` experiment whose call sites are all
+    commented out (SpectralScheme.m:41,52-53,64-67); the name is kept as an alias of ``interpolate``."""
+    return interpolate(x, y, F, dx, dy, device)
+
+
+class FlowFrames:
+    """Two background-flow frames resident on the device (what interpolate_U.m:5-17 re-interpolates
+    on every call).  ``bf`` dicts use the reference's field names u,v,ux,uy,vx,vy (grid_U.m:11-17)."""
+
+    def __init__(self, bf1, bf2, h, f=1.0, gH=1.0, mode=MODE_LAGRANGE6, device=0):
+        nx = np.asarray(bf1["u"]).shape[0]
+        self.eng = Engine(nx, h * nx, f, gH, mode, device)
+        self.eng.set_flow_grid(*[bf1[n] for n in ("u", "v", "ux", "uy", "vx", "vy")], slot=0)
+        if bf2 is not None:
+            self.eng.set_flow_grid(*[bf2[n] for n in ("u", "v", "ux", "uy", "vx", "vy")], slot=1)
+
+    def interpolate_U(self, alpha, x):
+        x = np.asarray(x, dtype=np.float64)
+        e = self.eng.eval_at(x[:, 0], x[:, 1], alpha)
+        U = np.stack([e[0], e[1]], axis=1)
+        return U, {"u_x": e[2], "u_y": e[3], "v_x": e[4], "v_y": e[5]}
+
+
+def interpolate_U(background_flow1, background_flow2, alpha, x, h, device=0):
+    """qg_flow_ray_trace/interpolate_U.m:1-24 -- [U, nablaU] = interpolate_U(bf1, bf2, alpha, x, h)."""
+    return FlowFrames(background_flow1, background_flow2, h, device=device).interpolate_U(alpha, x)
+
+
+def generate_raytracing_ode(background_flow1, background_flow2, Npackets, f, Cg, tmax, h, device=0, mode=MODE_LAGRANGE6):
+    """qgsw_raytrace.m:258-268 -- returns odefun(t, y) with y = [x; y; k; l] (4*Np,)."""
+    frames = FlowFrames(background_flow1, background_flow2, h, f=f, gH=Cg * Cg, mode=mode, device=device)
+
+    def odefun(t, y):
+        y = np.asarray(y, dtype=np.float64).ravel()
+        n = Npackets
+        frames.eng.set_packets(y[0:n], y[n:2 * n], y[2 * n:3 * n], y[3 * n:4 * n])
+        return np.concatenate(frames.eng.rhs(t / tmax))
+
+    return odefun
+
+
+# ------------------------------------------------------------------------------------------------
+# SpectralScheme / ode_symplectic
+# ------------------------------------------------------------------------------------------------
+
+class SpectralScheme:
+    """SpectralScheme.m:1-69 (+ RaytracingScheme.m:9-16).  ``SpectralScheme(L, nx, psi_field)``.
+
+    ``mode=MODE_SPECTRAL`` evaluates the planes by exact Fourier sum (the B200 contraction kernel);
+    ``mode=MODE_LAGRANGE6`` reproduces the reference's gridded 6x6 Lagrange evaluation."""
+
+    def __init__(self, L, nx, psi_field, mode=MODE_SPECTRAL, f=1.0, gH=1.0, device=0):
+        self.L, self.nx, self.mode = float(L), int(nx), mode
+        self.psik = g2k(np.asarray(psi_field, dtype=np.float64), device)
+        self.eng = Engine(nx, L, f, gH, mode, device)
+        self.eng.set_flow_spectral(self.psik)
+        self._psi_eng = None
+        self.device = device
+
+    @staticmethod
+    def _split(x):
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 2:          # (Np, 2)
+            return x[:, 0], x[:, 1], None
+        return x[:, 0, :].ravel(), x[:, 1, :].ravel(), x[:, 0, :].shape
+
+    def streamfunction(self, x, y, t=0):
+        """SpectralScheme.m:38-43"""
+        dx = self.L / self.nx
+        return interpolate(x, y, k2g(self.psik, self.device), dx, dx, self.device)
+
+    def U(self, x, t=0):
+        """SpectralScheme.m:45-54"""
+        xx, yy, shp = self._split(x)
+        e = self.eng.eval_at(xx, yy)
+        if shp is None:
+            return np.stack([e[0], e[1]], axis=1)
+        u = np.zeros_like(np.asarray(x, dtype=np.float64))
+        u[:, 0, :] = e[0].reshape(shp)
+        u[:, 1, :] = e[1].reshape(shp)
+        return u
+
+    def grad_U(self, x, t=0):
+        """SpectralScheme.m:56-68"""
+        xx, yy, _ = self._split(x)
+        e = self.eng.eval_at(xx, yy)
+        return {"u_x": e[2], "u_y": e[3], "v_x": e[4], "v_y": e[5]}
+
+    def grad_U_times_k(self, x, k, t=0):
+        """RaytracingScheme.m:9-16"""
+        g = self.grad_U(x, t)
+        k = np.asarray(k, dtype=np.float64)
+        out = np.zeros_like(k)
+        if k.ndim == 2:
+            out[:, 0] = g["u_x"] * k[:, 0] + g["v_x"] * k[:, 1]
+            out[:, 1] = g["u_y"] * k[:, 0] + g["v_y"] * k[:, 1]
+            return out
+        kk, ll = k[:, 0, :], k[:, 1, :]
+        out[:, 0, :] = (g["u_x"] * kk.ravel() + g["v_x"] * ll.ravel()).reshape(kk.shape)
+        out[:, 1, :] = (g["u_y"] * kk.ravel() + g["v_y"] * ll.ravel()).reshape(ll.shape)
+        return out
+
+
+def ode_symplectic(x0, k0, dt, T, f, gH, scheme, save_stride=1):
+    """ode_symplectic.m:1-37 -- [x, k, t] = ode_symplectic(x0, k0, dt, T, f, gH, scheme).
+
+    x0, k0: (1, 2, Np).  Nsteps = floor(T/dt); row i holds the state after i leapfrog steps,
+    t(i) = i*dt (zero-based).  ``save_stride`` (extension; the reference stores every step) keeps
+    every stride-th row so the history fits at 64k-16M packets; all steps between two saved rows
+    run as ONE fused kernel launch with the packet state in registers."""
+    x0 = np.asarray(x0, dtype=np.float64); k0 = np.asarray(k0, dtype=np.float64)
+    Nsteps = int(math.floor(T / dt))
+    rows = list(range(0, Nsteps, save_stride))
+    x = np.zeros((len(rows),) + x0.shape[1:]); k = np.zeros_like(x); t = np.zeros(len(rows))
+    x[0] = x0[0]; k[0] = k0[0]
+    eng = _engine_with(scheme, f, gH)   # the handle's f, gH are creation parameters
+    eng.set_packets(x0[0, 0, :], x0[0, 1, :], k0[0, 0, :], k0[0, 1, :])
+    done = 0
+    for r in range(1, len(rows)):
+        eng.step(SCHEME_LEAPFROG, dt, rows[r] - done)
+        done = rows[r]
+        xs, ys, ks, ls = eng.get_packets()
+        x[r, 0], x[r, 1], k[r, 0], k[r, 1] = xs, ys, ks, ls
+        t[r] = rows[r] * dt
+    return x, k, t
+
+
+def _engine_with(scheme, f, gH):
+    """engine for ``scheme``'s flow with the integrator's f and gH (cached on the scheme)."""
+    cache = scheme.__dict__.setdefault("_eng_cache", {})
+    key = (float(f), float(gH))
+    if key not in cache:
+        e = Engine(scheme.nx, scheme.L, f, gH, scheme.mode, scheme.device)
+        e.set_flow_spectral(scheme.psik)
+        cache[key] = e
+    return cache[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# step_packet / step_packet_xka
+# ------------------------------------------------------------------------------------------------
+
+class PacketStepper:
+    """Device-resident flow for the RK4 packet steppers (ray_trace_sw/step_packet.m,
+    step_packet_xka.m).  U = dict(u,v), GradU = dict(u_x,u_y,v_x,v_y), H optional grid."""
+
+    def __init__(self, U, GradU, H, C0, f, dx, mode=MODE_LAGRANGE6, device=0):
+        nx = np.asarray(U["u"]).shape[0]
+        self.eng = Engine(nx, dx * nx, f, C0 * C0, mode, device)
+        self.eng.set_flow_grid(U["u"], U["v"], GradU["u_x"], GradU["u_y"], GradU["v_x"], GradU["v_y"], H)
+        self.xka = H is not None
+
+    def step(self, P, dt, nsteps=1):
+        x, y, k, l = (np.atleast_1d(np.asarray(P[n], dtype=np.float64)) for n in ("x", "y", "k", "l"))
+        a = np.atleast_1d(np.asarray(P["a"], dtype=np.float64)) if "a" in P else None
+        self.eng.set_packets(x, y, k, l, a)
+        self.eng.step(SCHEME_RK4_XKA if self.xka else SCHEME_RK4_PACKET, dt, nsteps)
+        out = self.eng.get_packets(with_a=self.xka)
+        names = ("x", "y", "k", "l", "a")[:len(out)]
+        scalar = np.ndim(P["x"]) == 0
+        return {n: (float(v[0]) if scalar else v) for n, v in zip(names, out)}
+
+
+def step_packet(P, U, GradU, C0, f, dx, dy, dt, mode=MODE_LAGRANGE6, device=0):
+    """ray_trace_sw/step_packet.m:1-78 -- Pout = step_packet(P,U,GradU,C0,f,dx,dy,dt).
+    P may hold scalars (one packet, as the reference) or arrays (a struct array of packets)."""
+    return PacketStepper(U, GradU, None, C0, f, dx, mode, device).step(P, dt)
+
+
+def step_packet_xka(P, U, GradU, H, C0, f, dx, dy, dt, mode=MODE_LAGRANGE6, device=0):
+    """ray_trace_sw/step_packet_xka.m:1-91 -- adds refraction by H and wave action a."""
+    return PacketStepper(U, GradU, H, C0, f, dx, mode, device).step(P, dt)
+
+
+def omega(k, f, gH):
+    """symplectic_full_fourier.m:62-64 -- host helper, O(Np)."""
+    k = np.asarray(k, dtype=np.float64)
+    return np.sqrt(f * f + gH * np.sum(k * k, axis=1))

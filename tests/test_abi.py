@@ -1,0 +1,77 @@
+"""The C-ABI library loads and exports every symbol include/swrt.h declares (no compute calls)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+import swraytracing_b200 as S
+from swraytracing_b200 import engine
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "swrt.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(swrt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    lib = S.load_library()
+    syms = _declared_symbols()
+    assert len(syms) >= 25
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in swrt.h but not exported by libswrt.so"
+
+
+def test_ctypes_table_matches_header():
+    assert sorted(engine.SIGNATURES) == _declared_symbols()
+
+
+def test_version_and_struct_layout():
+    lib = S.load_library()
+    assert lib.swrt_version() == 100
+    assert ctypes.sizeof(engine._Params) == 48      # 4 x int32 + 4 x double, as swrt_params
+
+
+def test_no_cpu_fallback_without_device():
+    lib = S.load_library()
+    if lib.swrt_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(S.SwrtError) as ei:
+        S.Engine(32, 6.28, 3.0, 1.0)
+    assert ei.value.code == -3 and "no CPU path" in str(ei.value)
+    import numpy as np
+    with pytest.raises(S.SwrtError):
+        S.interpolate_dev(np.zeros(4), np.zeros(4), np.zeros((8, 8)), 1.0, 1.0)
+
+
+def test_create_argument_validation():
+    lib = S.load_library()
+    h = ctypes.c_void_p()
+    bad = engine._Params(7, 0, 0, 0, 6.28, 3.0, 1.0, 1e-13)      # odd nx
+    assert lib.swrt_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+    assert b"nx" in lib.swrt_last_error(None)
+    bad = engine._Params(32, 5, 0, 0, 6.28, 3.0, 1.0, 1e-13)     # unknown mode
+    assert lib.swrt_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+    assert lib.swrt_create(None, ctypes.byref(h)) == -1
+    assert lib.swrt_destroy(None) == 0
+
+
+def test_product_does_not_import_oracle():
+    for py in (ROOT / "swraytracing_b200").glob("*.py"):
+        src = py.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, py
+    for cu in (ROOT / "swraytracing_b200" / "csrc").glob("*"):
+        assert "oracle" not in cu.read_text().lower(), cu
+
+
+def test_library_is_sm100a_with_dmma_and_bulk_copy():
+    import shutil, subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-sass", str(engine.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "DMMA.8x8x4" in out          # fp64 tensor pipe
+    assert "UBLKCP" in out              # cp.async.bulk (TMA engine) staging of the coefficient stack

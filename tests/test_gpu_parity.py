@@ -1,0 +1,490 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, against the committed golden fixture, and -- at BASELINE.json's full sizes -- through
+size-independent properties.  Parity contract: SURVEY.md 8c P1-P6.
+
+Tolerances (fp64):  field / RHS values 1e-12 relative to max|plane|;  trajectories over <= 100
+steps 1e-9 absolute;  histogram counts bit-exact."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import swraytracing_b200 as S
+from swraytracing_b200 import reference_api as R
+from swraytracing_b200 import workloads as W
+from oracle import swrt_oracle as O
+from oracle import c_oracle as CO
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(Path(__file__).parent / "golden" / "hotpath_nx32.npz")
+TOL_FIELD = 1e-12
+TOL_TRAJ = 1e-9
+F0, GH0 = 3.0, 1.0
+
+
+def scaled_err(got, ref):
+    got = np.asarray(got); ref = np.asarray(ref)
+    scale = np.abs(ref).reshape(ref.shape[0], -1).max(axis=1)
+    scale = np.where(scale > 0, scale, 1.0)
+    return float((np.abs(got - ref).reshape(ref.shape[0], -1).max(axis=1) / scale).max())
+
+
+def make_flow(nx, seed=7, slope=1.5, amp=0.3):
+    rs = np.random.RandomState(seed)
+    kx_, ky_ = O.wavenumbers(nx)
+    psik = (rs.randn(nx - 1, nx // 2) + 1j * rs.randn(nx - 1, nx // 2)) / (1 + kx_ ** 2 + ky_ ** 2) ** slope * amp
+    planes = O.velocity_planes_k(psik, kx_, ky_)
+    return psik, planes
+
+
+def make_packets(n, L, seed=5):
+    rs = np.random.RandomState(seed)
+    i = np.arange(n)
+    return rs.uniform(-3 * L, 3 * L, n), rs.uniform(-3 * L, 3 * L, n), 3 * np.cos(0.37 * i), 3 * np.sin(0.37 * i)
+
+
+# ------------------------------------------------------------------------------------------------
+# P2: SPECTRAL kernel vs exact-sum oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx", [16, 32, 36, 48, 64, 128])
+@pytest.mark.parametrize("mt", [1, 2])
+def test_spectral_eval_vs_exact_sum(nx, mt):
+    L = 2 * np.pi; dx = L / nx
+    psik, planes = make_flow(nx)
+    n = 517 if nx <= 64 else 300
+    x, y, k, l = make_packets(n, L)
+    ref = CO.spectral_eval(x, y, planes, dx, nx, precise=True)
+    with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
+        e.set_tuning(mt)
+        e.set_flow_spectral(psik)
+        e.set_packets(x, y, k, l)
+        got = e.eval()
+        assert scaled_err(got, ref) < TOL_FIELD
+        got2 = e.eval_at(x[::-1].copy(), y[::-1].copy())
+        assert np.array_equal(got2[:, ::-1], got)      # a packet's value does not depend on its tile slot
+
+
+def test_spectral_full_spectrum_flat_is_within_tolerance():
+    # white (slope 0) spectrum up to the truncation: the hardest case for the twiddle recurrences
+    nx = 128; L = 2 * np.pi; dx = L / nx
+    psik, planes = make_flow(nx, slope=0.0, amp=1e-3)
+    x, y, k, l = make_packets(200, L, seed=9)
+    ref = CO.spectral_eval(x, y, planes, dx, nx, precise=True)
+    with S.Engine(nx, L, F0, GH0) as e:
+        e.set_flow_planes_spectral(planes)
+        got = e.eval_at(x, y)
+    assert scaled_err(got, ref) < TOL_FIELD
+
+
+def test_spectral_planes_upload_and_domain_L20():
+    # qg2layersw_raytrace.m:13,19-22: L = 20, wavenumbers scaled by 2*pi/L, mean shear on u
+    nx = 32; L = 20.0; dx = L / nx
+    rs = np.random.RandomState(3)
+    kx_, ky_ = O.wavenumbers(nx)
+    kap = 2 * np.pi / L
+    psik = (rs.randn(nx - 1, nx // 2) + 1j * rs.randn(nx - 1, nx // 2)) / (1 + kx_ ** 2 + ky_ ** 2)
+    planes = O.velocity_planes_k(psik, kap * kx_, kap * ky_)
+    planes[0] = planes[0].copy(); planes[0][nx // 2 - 1, 0] += 0.5
+    x, y, k, l = make_packets(333, L)
+    ref = CO.spectral_eval(x, y, planes, dx, nx)
+    with S.Engine(nx, L, F0, GH0) as e:
+        e.set_flow_spectral(psik, u_mean=0.5)
+        assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+        e.set_flow_planes_spectral(planes)
+        assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+
+
+# ------------------------------------------------------------------------------------------------
+# P1: LAGRANGE6 kernel vs restated interpolate / interpolate_U
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx", [16, 32, 64])
+def test_lagrange_eval_vs_interpolate(nx):
+    L = 2 * np.pi; dx = L / nx
+    psik, planes = make_flow(nx)
+    grids = [O.k2g(p) for p in planes]
+    x, y, k, l = make_packets(777, L)
+    ref = CO.interpolate6(x, y, grids, dx)
+    with S.Engine(nx, L, F0, GH0, S.MODE_LAGRANGE6) as e:
+        e.set_flow_grid(*grids)
+        assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+    with S.Engine(nx, L, F0, GH0, S.MODE_LAGRANGE6) as e:      # grid_U on the device (k2g via cuFFT)
+        e.set_flow_spectral(psik)
+        assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+    # standalone interpolate(x,y,F,dx,dy) and the bump = 1e-10 variant
+    assert np.abs(S.interpolate_dev(x, y, grids[0], dx, dx) - ref[0]).max() / np.abs(ref[0]).max() < TOL_FIELD
+    par = O.interpolate_par(x, y, grids[1], dx, dx)
+    assert np.abs(R.interpolate_par(x, y, grids[1], dx, dx) - par).max() / np.abs(par).max() < TOL_FIELD
+
+
+def test_interpolate_U_time_blend_both_modes():
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx
+    alpha = float(GOLD["alpha"])
+    kx_, ky_ = O.wavenumbers(nx)
+    g1 = [O.k2g(p) for p in O.velocity_planes_k(GOLD["psik"], kx_, ky_)]
+    g2 = [O.k2g(p) for p in O.velocity_planes_k(GOLD["psik2"], kx_, ky_)]
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    bf1 = dict(zip(names, g1)); bf2 = dict(zip(names, g2))
+    xy = np.stack([GOLD["x"], GOLD["y"]], axis=1)
+    U, nab = R.interpolate_U(bf1, bf2, alpha, xy, dx)
+    got = np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])
+    assert scaled_err(got, GOLD["interpU_lagrange"]) < TOL_FIELD
+    with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
+        e.set_flow_spectral(GOLD["psik"], slot=0)
+        e.set_flow_spectral(GOLD["psik2"], slot=1)
+        assert scaled_err(e.eval_at(GOLD["x"], GOLD["y"], alpha), GOLD["interpU_spectral"]) < TOL_FIELD
+        assert scaled_err(e.eval_at(GOLD["x"], GOLD["y"], 0.0), GOLD["eval_spectral"]) < TOL_FIELD
+        with pytest.raises(S.SwrtError):
+            S.Engine(nx, L, F0, GH0).eval_at(GOLD["x"], GOLD["y"], 0.0)       # no flow set
+
+
+# ------------------------------------------------------------------------------------------------
+# P3: SPECTRAL kernel vs the reference's Lagrange stencil
+# ------------------------------------------------------------------------------------------------
+def test_spectral_vs_reference_lagrange_at_grid_nodes_and_bound_off_grid():
+    nx = 64; L = 2 * np.pi; dx = L / nx
+    rs = np.random.RandomState(1)
+    kx_, ky_ = O.wavenumbers(nx)
+    kcut = 8
+    psik = (rs.randn(nx - 1, nx // 2) + 1j * rs.randn(nx - 1, nx // 2)) * ((np.abs(kx_) <= kcut) & (ky_ <= kcut)) * 0.01
+    planes = O.velocity_planes_k(psik, kx_, ky_)
+    grids = [O.k2g(p) for p in planes]
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(nx), indexing="ij")
+    xn = (ix * dx).ravel(); yn = (iy * dx).ravel()
+    with S.Engine(nx, L, F0, GH0) as e:
+        e.set_flow_spectral(psik)
+        got = e.eval_at(xn, yn)
+        ref = CO.interpolate6(xn, yn, grids, dx)          # reference semantics at grid nodes
+        assert scaled_err(got, ref) < TOL_FIELD
+        x, y, _, _ = make_packets(500, L)
+        gap = np.abs(e.eval_at(x, y) - CO.interpolate6(x, y, grids, dx))
+        for c in range(6):
+            # degree-5 Lagrange bound per direction (3.52/720) (kmax dx)^6 * sum|coefficients|
+            csum = 2 * np.abs(planes[c]).sum()
+            assert gap[c].max() <= 2 * (3.52 / 720) * (kcut * dx) ** 6 * csum
+
+
+# ------------------------------------------------------------------------------------------------
+# P4: RHS and short trajectories, each mode against its oracle
+# ------------------------------------------------------------------------------------------------
+def test_rhs_both_modes():
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx
+    alpha = float(GOLD["alpha"])
+    x, y, k, l = GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"]
+    with S.Engine(nx, L, F0, GH0, S.MODE_LAGRANGE6) as e:
+        e.set_flow_spectral(GOLD["psik"], slot=0); e.set_flow_spectral(GOLD["psik2"], slot=1)
+        e.set_packets(x, y, k, l)
+        assert scaled_err(np.stack(e.rhs(alpha)), GOLD["rhs_lagrange"]) < TOL_FIELD
+    ref = np.stack(O.rhs_from_eval(GOLD["interpU_spectral"], k, l, F0, 1.0))
+    with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
+        e.set_flow_spectral(GOLD["psik"], slot=0); e.set_flow_spectral(GOLD["psik2"], slot=1)
+        e.set_packets(x, y, k, l)
+        assert scaled_err(np.stack(e.rhs(alpha)), ref) < TOL_FIELD
+    # generate_raytracing_ode closure (qgsw_raytrace.m:258-268), y = [x;y;k;l]
+    kx_, ky_ = O.wavenumbers(nx)
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    bf1 = dict(zip(names, [O.k2g(p) for p in O.velocity_planes_k(GOLD["psik"], kx_, ky_)]))
+    bf2 = dict(zip(names, [O.k2g(p) for p in O.velocity_planes_k(GOLD["psik2"], kx_, ky_)]))
+    ode = R.generate_raytracing_ode(bf1, bf2, x.size, F0, 1.0, 2.0, dx)
+    dydt = ode(alpha * 2.0, np.concatenate([x, y, k, l]))
+    assert scaled_err(dydt.reshape(4, -1), GOLD["rhs_lagrange"]) < TOL_FIELD
+
+
+@pytest.mark.parametrize("mt", [1, 2])
+def test_leapfrog_trajectory_spectral_golden_and_oracle(mt):
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx; dt = float(GOLD["dt"])
+    with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
+        e.set_tuning(mt)
+        e.set_flow_spectral(GOLD["psik"])
+        e.set_packets(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
+        e.step(S.SCHEME_LEAPFROG, dt, 20)
+        assert np.abs(np.stack(e.get_packets()) - GOLD["leapfrog20_spectral"]).max() < TOL_TRAJ
+        # 100 steps, fused (one launch) == 100 single-step launches, and both match the oracle
+        e.set_packets(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
+        e.step(S.SCHEME_LEAPFROG, dt, 100)
+        fused = np.stack(e.get_packets())
+        e.set_packets(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
+        for _ in range(100):
+            e.step(S.SCHEME_LEAPFROG, dt, 1)
+        assert np.array_equal(fused, np.stack(e.get_packets()))
+    kx_, ky_ = O.wavenumbers(nx)
+    ref = CO.leapfrog_spectral(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"], O.velocity_planes_k(GOLD["psik"], kx_, ky_),
+                               dx, nx, F0, GH0, dt, 100, precise=True)
+    assert np.abs(fused - np.stack(ref)).max() < TOL_TRAJ
+
+
+def test_leapfrog_trajectory_lagrange():
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx; dt = float(GOLD["dt"])
+    with S.Engine(nx, L, F0, GH0, S.MODE_LAGRANGE6) as e:
+        e.set_flow_grid(*list(GOLD["grids"]))
+        e.set_packets(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
+        e.step(S.SCHEME_LEAPFROG, dt, 20)
+        assert np.abs(np.stack(e.get_packets()) - GOLD["leapfrog20_lagrange"]).max() < TOL_TRAJ
+        e.step(S.SCHEME_LEAPFROG, dt, 80)
+        ref = CO.leapfrog_lagrange(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"], list(GOLD["grids"]), dx, F0, GH0, dt, 100)
+        assert np.abs(np.stack(e.get_packets()) - np.stack(ref)).max() < TOL_TRAJ
+
+
+def test_leapfrog_time_dependent_flow_blend_on_device():
+    # swrt_step(alpha0, dalpha): step j evaluates (1-a_j) frame0 + a_j frame1, a_j = alpha0 + j*dalpha
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx; dt = float(GOLD["dt"])
+    kx_, ky_ = O.wavenumbers(nx)
+    p1 = O.velocity_planes_k(GOLD["psik"], kx_, ky_); p2 = O.velocity_planes_k(GOLD["psik2"], kx_, ky_)
+    m = 8
+    st = (GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
+    for j in range(m):
+        a = (j + 0.5) / m
+        pl = [(1 - a) * u + a * v for u, v in zip(p1, p2)]
+        st = O.leapfrog_step(*st, dt, F0, GH0, lambda xx, yy: CO.spectral_eval(xx, yy, pl, dx, nx))
+    with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
+        e.set_flow_spectral(GOLD["psik"], slot=0); e.set_flow_spectral(GOLD["psik2"], slot=1)
+        e.set_packets(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
+        e.step(S.SCHEME_LEAPFROG, dt, m, alpha0=0.5 / m, dalpha=1.0 / m)
+        assert np.abs(np.stack(e.get_packets()) - np.stack(st)).max() < TOL_TRAJ
+        with pytest.raises(S.SwrtError):
+            e2 = S.Engine(nx, L, F0, GH0); e2.set_flow_spectral(GOLD["psik"]); e2.set_packets(*st)
+            e2.step(S.SCHEME_LEAPFROG, dt, 2, alpha0=0.25, dalpha=0.5)         # slot 1 never set
+
+
+@pytest.mark.parametrize("xka", [False, True])
+def test_rk4_packet_steps_lagrange(xka):
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx; dt = float(GOLD["dt"])
+    key = "rk4x3_xka_lagrange" if xka else "rk4x3_packet_lagrange"
+    g = list(GOLD["grids"])
+    with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
+        e.set_flow_grid(*g, H=GOLD["H"] if xka else None)
+        e.set_packets(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
+        e.step(S.SCHEME_RK4_XKA if xka else S.SCHEME_RK4_PACKET, dt, 3)
+        got = np.stack(e.get_packets(with_a=True))
+    ref = GOLD[key]
+    assert np.abs(got[:4] - ref[:4]).max() < TOL_TRAJ
+    if xka:
+        assert np.abs(got[4] - ref[4]).max() < TOL_TRAJ
+    # reference calling surface: Pout = step_packet(_xka)(P, U, GradU, [H,] C0, f, dx, dy, dt), one packet
+    U = {"u": g[0], "v": g[1]}; G = {"u_x": g[2], "u_y": g[3], "v_x": g[4], "v_y": g[5]}
+    P = {"x": float(GOLD["x"][0]), "y": float(GOLD["y"][0]), "k": float(GOLD["k"][0]), "l": float(GOLD["l"][0]), "a": 1.0}
+    if xka:
+        Pg = R.step_packet_xka(P, U, G, GOLD["H"], 1.0, F0, dx, dx, dt)
+        Po = O.step_packet_xka(P, U, G, GOLD["H"], 1.0, F0, dx, dx, dt)
+    else:
+        Pg = R.step_packet(P, U, G, 1.0, F0, dx, dx, dt)
+        Po = O.step_packet(P, U, G, 1.0, F0, dx, dx, dt)
+    for name in Po:
+        assert abs(Pg[name] - Po[name]) < 1e-12
+
+
+@pytest.mark.parametrize("xka", [False, True])
+def test_rk4_packet_steps_spectral(xka):
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx; dt = float(GOLD["dt"])
+    kx_, ky_ = O.wavenumbers(nx)
+    planes = O.velocity_planes_k(GOLD["psik"], kx_, ky_)
+    Hk = O.g2k(GOLD["H"])
+    n = 120
+    st = tuple(GOLD[q][:n] for q in ("x", "y", "k", "l")) + (np.ones(n),)
+    ref = st
+    for _ in range(2):
+        ref = O.rk4_step_batch(*ref, dt, 1.0, F0, None, dx, xka, mode="spectral", planes_k=planes + [Hk], nx=nx)
+    with S.Engine(nx, L, F0, 1.0, S.MODE_SPECTRAL) as e:
+        e.set_flow_planes_spectral(planes + ([Hk] if xka else []))
+        e.set_packets(*st)
+        e.step(S.SCHEME_RK4_XKA if xka else S.SCHEME_RK4_PACKET, dt, 2)
+        got = np.stack(e.get_packets(with_a=True))
+    assert np.abs(got - np.stack(ref)).max() < TOL_TRAJ
+    if not xka:
+        with pytest.raises(S.SwrtError):       # xka without an H plane is a state error, not a crash
+            with S.Engine(nx, L, F0, 1.0) as e:
+                e.set_flow_planes_spectral(planes); e.set_packets(*st); e.step(S.SCHEME_RK4_XKA, dt, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# P5 / properties at full size
+# ------------------------------------------------------------------------------------------------
+def test_zero_flow_analytic_dispersion_C1():
+    w = W.make_workload("C1")
+    for mode in (S.MODE_SPECTRAL, S.MODE_LAGRANGE6):
+        with S.Engine(w.nx, w.L, w.f, w.gH, mode) as e:
+            e.set_flow_spectral(w.psik)
+            e.set_packets(w.x, w.y, w.k, w.l)
+            e.step(S.SCHEME_LEAPFROG, w.dt, 100)
+            x, y, k, l = e.get_packets()
+        om = np.sqrt(w.f ** 2 + w.gH * (w.k ** 2 + w.l ** 2))
+        assert np.array_equal(k, w.k) and np.array_equal(l, w.l)
+        assert np.abs(x - (w.x + w.gH * w.k / om * 100 * w.dt)).max() < 1e-12
+        assert np.abs(y - (w.y + w.gH * w.l / om * 100 * w.dt)).max() < 1e-12
+
+
+def test_C2_full_size_against_cpu_port_and_sharding_identity():
+    w = W.make_workload("C2")                      # 128^2, 65,536 packets: BASELINE configs[1]
+    planes = W.planes_from_psik(w.psik, w.L)
+    with S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_SPECTRAL) as e:
+        e.set_flow_spectral(w.psik)
+        e.set_packets(w.x, w.y, w.k, w.l)
+        got = e.eval()
+        ref = CO.spectral_eval(w.x, w.y, planes, w.dx, w.nx, precise=False)     # double sums: 1e-11 is their own accuracy
+        assert scaled_err(got, ref) < 1e-11
+        sub = np.arange(0, w.n_packets, 97)
+        refp = CO.spectral_eval(w.x[sub], w.y[sub], planes, w.dx, w.nx, precise=True)
+        assert scaled_err(got[:, sub], refp) < TOL_FIELD
+        e.step(S.SCHEME_LEAPFROG, w.dt, 10)
+        full = np.stack(e.get_packets())
+        # the same packets split into two unequal shards give bit-identical states
+        cut = 30011
+        parts = []
+        for sl in (slice(0, cut), slice(cut, None)):
+            e.set_packets(w.x[sl], w.y[sl], w.k[sl], w.l[sl])
+            e.step(S.SCHEME_LEAPFROG, w.dt, 10)
+            parts.append(np.stack(e.get_packets()))
+        assert np.array_equal(np.concatenate(parts, axis=1), full)
+        ref10 = CO.leapfrog_spectral(w.x[sub], w.y[sub], w.k[sub], w.l[sub], planes, w.dx, w.nx, w.f, w.gH, w.dt, 10)
+        assert np.abs(full[:, sub] - np.stack(ref10)).max() < TOL_TRAJ
+        assert np.all(np.isfinite(full))
+
+
+def test_omega_drift_and_conserved_absolute_frequency():
+    # steady flow: Omega = omega + U.k is conserved by the ray equations; the leapfrog keeps the drift
+    # bounded and shrinking with dt (images/Symplectic_error: <~ 5e-3 at dt = 0.01 for a weak flow)
+    w = W.make_workload("C2", n_packets=4096, nx=64, kind="band")
+    with S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_SPECTRAL) as e:
+        e.set_flow_spectral(w.psik)
+        worst = {}
+        for dt, nst in ((0.01, 100), (0.005, 200)):
+            e.set_packets(w.x, w.y, w.k, w.l)
+            om0, Om0 = e.omega()
+            worst[dt] = 0.0
+            for _ in range(4):
+                e.step(S.SCHEME_LEAPFROG, dt, nst)
+                om, Om = e.omega()
+                worst[dt] = max(worst[dt], np.abs((Om - Om0) / Om0).max())
+        assert worst[0.01] < 5e-2                      # U_g = 0.5, |k| <= 8: a strong, sharp flow
+        # the reference's phi2 is an explicit Euler step of H2 = U.k (ode_symplectic.m:18-21: x and k both
+        # advance from the same x1), so the composite is FIRST order: the drift halves with dt
+        # (CPU oracle on the same inputs: 1.6e-2, 8.4e-3, 4.3e-3 at dt = 0.01, 0.005, 0.0025)
+        assert 0.35 * worst[0.01] < worst[0.005] < 0.65 * worst[0.01]
+        assert np.abs(om - om0).max() > 1e-3           # intrinsic frequency does change (refraction happens)
+        d = e.diag()
+        assert d[4] == 0 and d[6] == 4096 and abs(d[0] - om.sum()) < 1e-8 * om.sum() and abs(d[1] - Om.sum()) < 1e-8 * abs(Om.sum())
+        assert d[2] == om.max() and d[3] == om.min()
+
+
+# ------------------------------------------------------------------------------------------------
+# P6: histogram
+# ------------------------------------------------------------------------------------------------
+def test_histogram_bit_exact():
+    nx = int(GOLD["nx"]); L = float(GOLD["L"])
+    with S.Engine(nx, L, F0, GH0) as e:
+        e.set_flow_spectral(GOLD["psik"])
+        e.set_packets(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
+        c = e.hist_omega(GOLD["hist_edges"])
+        assert np.array_equal(c, GOLD["hist_counts"])
+        c2 = e.hist_omega(GOLD["hist_edges"], counts=c.copy())      # accumulate
+        assert np.array_equal(c2, 2 * GOLD["hist_counts"])
+        # larger, after stepping: identical states -> identical counts (load_data.m:33-49 rule)
+        rs = np.random.RandomState(4)
+        n = 200000
+        k = rs.normal(0, 3, n); l = rs.normal(0, 3, n)
+        e.set_packets(rs.uniform(-3, 3, n), rs.uniform(-3, 3, n), k, l)
+        om, Om = e.omega()
+        assert np.array_equal(om, np.sqrt(F0 * F0 + GH0 * (k * k + l * l)))
+        edges = O.matlab_linspace(0, om.max(), 300)
+        assert np.array_equal(e.hist_omega(edges), O.histcounts(om, edges))
+        assert int(e.hist_omega(edges).sum()) == n                  # max lands in the closed last bin
+        edges_abs = O.matlab_linspace(Om.min(), Om.max(), 300)
+        assert np.array_equal(e.hist_omega(edges_abs, kind=S.HIST_ABSOLUTE), O.histcounts(Om, edges_abs))
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases and error behaviour
+# ------------------------------------------------------------------------------------------------
+def test_edge_cases_empty_single_ragged_nonfinite():
+    nx = 32; L = 2 * np.pi
+    psik, planes = make_flow(nx)
+    for mode in (S.MODE_SPECTRAL, S.MODE_LAGRANGE6):
+        with S.Engine(nx, L, F0, GH0, mode) as e:
+            e.set_flow_spectral(psik)
+            z = np.zeros(0)
+            e.set_packets(z, z, z, z)
+            e.step(S.SCHEME_LEAPFROG, 0.01, 3)                     # empty: no-op
+            assert e.eval().shape == (6, 0)
+            for n in (1, 7, 8, 63, 64, 65, 129):                    # around the 8/64/128 tile edges
+                x, y, k, l = make_packets(n, L, seed=n)
+                e.set_packets(x, y, k, l)
+                ref = (CO.spectral_eval(x, y, planes, L / nx, nx) if mode == S.MODE_SPECTRAL
+                       else CO.interpolate6(x, y, [O.k2g(p) for p in planes], L / nx))
+                assert scaled_err(e.eval(), ref) < TOL_FIELD
+            # huge and negative positions reduce exactly like mod(x/dx, nx)
+            x = np.array([1e6 + 0.123, -1e6 - 0.456, 0.0, -1e-20, L, -L]); y = x[::-1].copy()
+            ref = (CO.spectral_eval(x, y, planes, L / nx, nx) if mode == S.MODE_SPECTRAL
+                   else CO.interpolate6(x, y, [O.k2g(p) for p in planes], L / nx))
+            assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+            # a non-finite packet is counted by the sentinel and does not poison the others
+            x, y, k, l = make_packets(100, L)
+            k2 = k.copy(); k2[17] = np.nan
+            e.set_packets(x, y, k2, l)
+            e.step(S.SCHEME_LEAPFROG, 0.01, 2)
+            d = e.diag()
+            assert d[4] == 1 and d[6] == 100
+            xs, _, ks, _ = e.get_packets()
+            assert np.isfinite(np.delete(ks, 17)).all() and np.isfinite(np.delete(xs, 17)).all()
+
+
+def test_error_behaviour():
+    with pytest.raises(S.SwrtError) as ei:
+        S.Engine(33, 1.0, 1.0, 1.0)
+    assert ei.value.code == -1
+    with S.Engine(32, 2 * np.pi, F0, GH0) as e:
+        z = np.zeros(4)
+        e.set_packets(z, z, z, z)
+        with pytest.raises(S.SwrtError) as ei:
+            e.step(S.SCHEME_LEAPFROG, 0.1, 1)                       # no flow
+        assert ei.value.code == -2
+        with pytest.raises(S.SwrtError):
+            e.set_flow_spectral(np.zeros((15, 8), dtype=complex))    # wrong shape
+        e.set_flow_spectral(np.zeros((31, 16), dtype=complex))
+        with pytest.raises(S.SwrtError):
+            e.step(99, 0.1, 1)
+        with pytest.raises(S.SwrtError):
+            e.hist_omega(np.array([1.0]))
+        assert e.launch_count() > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference calling surface (SpectralScheme / ode_symplectic / grid_U / g2k / k2g)
+# ------------------------------------------------------------------------------------------------
+def test_reference_surface_spectral_scheme_and_ode_symplectic():
+    nx = 32; L = 2 * np.pi
+    psik, planes = make_flow(nx)
+    psi = O.k2g(psik)
+    n = 41
+    x0 = np.zeros((1, 2, n)); k0 = np.zeros((1, 2, n))
+    x0[0, 0], x0[0, 1], k0[0, 0], k0[0, 1] = make_packets(n, L)
+    dt = 0.02; T = 0.5
+    for mode, omode in ((S.MODE_SPECTRAL, "spectral"), (S.MODE_LAGRANGE6, "lagrange")):
+        sch = R.SpectralScheme(L, nx, psi, mode=mode)
+        osch = O.SpectralScheme(L, nx, psi, mode=omode)
+        assert np.abs(sch.U(x0) - osch.U(x0)).max() < 1e-12
+        g, og = sch.grad_U(x0), osch.grad_U(x0)
+        for name in og:
+            assert np.abs(g[name] - og[name]).max() < 1e-11
+        assert np.abs(sch.grad_U_times_k(x0, k0) - osch.grad_U_times_k(x0, k0)).max() < 1e-11
+        xs, ks, ts = R.ode_symplectic(x0, k0, dt, T, F0, GH0, sch)
+        xo, ko, to = O.ode_symplectic(x0, k0, dt, T, F0, GH0, osch)
+        assert xs.shape == xo.shape == (25, 2, n) and np.allclose(ts, to)
+        assert np.abs(xs - xo).max() < TOL_TRAJ and np.abs(ks - ko).max() < TOL_TRAJ
+        xs5, ks5, ts5 = R.ode_symplectic(x0, k0, dt, T, F0, GH0, sch, save_stride=5)
+        assert np.array_equal(xs5, xs[::5]) and np.allclose(ts5, ts[::5])
+    assert np.abs(sch.streamfunction(x0[0, 0], x0[0, 1]) - osch.streamfunction(x0[0, 0], x0[0, 1])).max() < 1e-12
+
+
+def test_device_g2k_k2g_grid_U():
+    nx = 64
+    psik, planes = make_flow(nx)
+    fg = O.k2g(planes[0])
+    assert np.abs(S.k2g_dev(planes[0]) - fg).max() < 1e-13 * max(1, np.abs(fg).max())
+    assert np.abs(S.g2k_dev(fg) - O.symmetrise_ky0(planes[0])).max() < 1e-15
+    kx_, ky_ = O.wavenumbers(nx)
+    K2 = kx_ ** 2 + ky_ ** 2
+    qk = -(3.0 + K2) * psik
+    bf = R.grid_U(qk, 3.0, K2, kx_, ky_, 0.5)
+    ref = O.grid_U(qk, 3.0, K2, kx_, ky_, 0.5)
+    for name in ref:
+        assert np.abs(bf[name] - ref[name]).max() < 1e-12

@@ -1,0 +1,120 @@
+"""Host-side logic on CPU: synthetic workloads, sharding, the gloo world_size=2 reduction path."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import swrt_oracle as O
+from oracle import c_oracle as CO
+from swraytracing_b200 import workloads as W
+from swraytracing_b200.distributed import ShardedEnsemble, shard_range
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_workload_generator_matches_oracle_kit():
+    w = W.make_workload("C2", n_packets=100, nx=32)
+    planes = W.planes_from_psik(w.psik, w.L)
+    kx_, ky_ = O.wavenumbers(32)
+    ref = O.velocity_planes_k(w.psik, kx_, ky_)
+    for a, b in zip(planes, ref):
+        assert np.abs(a - b).max() < 1e-15
+    u = O.k2g(ref[0]); v = O.k2g(ref[1])
+    assert abs(np.sqrt((u * u + v * v).max()) - w.U0) < 1e-12       # normalised so max|U| = U_g
+    assert abs(W._fulspec_ifft(ref[0]) - u).max() < 1e-13
+    w2 = W.make_workload("C2", n_packets=100, nx=32)
+    assert np.array_equal(w.psik, w2.psik) and np.array_equal(w.x, w2.x)   # seeded
+    assert np.allclose(w.k ** 2 + w.l ** 2, 27.0)                  # k0^2 = (nif^2-1) f^2/Cg^2
+
+
+@pytest.mark.parametrize("name", ["C1", "C3", "C4", "C5"])
+def test_other_workloads_build_small(name):
+    w = W.make_workload(name, n_packets=64, nx=32)
+    assert w.x.shape == (64,) and np.isfinite(w.dt) and w.dt > 0
+    if name in ("C3", "C4"):
+        assert w.psik2 is not None and np.abs(w.psik2 - w.psik).max() > 0
+    if name == "C4":
+        assert w.L == 20.0 and w.u_mean == 0.5
+    if name == "C5":
+        assert len(W.planes_from_psik(w.psik, w.L, etak=w.extra["etak"])) == 7
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 65536, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+class OracleEngine:
+    """oracle-backed stand-in with the Engine interface (CPU tests of the multi-rank host logic)"""
+
+    def __init__(self, grids, dx, f, gH):
+        self.grids, self.dx, self.f, self.gH = grids, dx, f, gH
+
+    def set_packets(self, x, y, k, l, a=None):
+        self.s = [np.array(v, dtype=np.float64) for v in (x, y, k, l)]
+
+    def get_packets(self, with_a=False):
+        return tuple(self.s)
+
+    def step(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
+        self.s = list(CO.leapfrog_lagrange(*self.s, self.grids, self.dx, self.f, self.gH, dt, nsteps))
+
+    def hist_omega(self, edges, kind=0, alpha=0.0):
+        return CO.histcounts(O.omega_of_k(self.s[2], self.s[3], self.f, self.gH), edges)
+
+    def diag(self, alpha=0.0):
+        w = O.omega_of_k(self.s[2], self.s[3], self.f, self.gH)
+        return np.array([w.sum(), w.sum(), w.max(), w.min(), 0.0, float(w.size), float(w.size), w.sum()])
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT))
+    w = W.make_workload("C2", n_packets=1001, nx=32)
+    kx_, ky_ = O.wavenumbers(32)
+    grids = [O.k2g(p) for p in O.velocity_planes_k(w.psik, kx_, ky_)]
+    ens = ShardedEnsemble(OracleEngine(grids, w.dx, w.f, w.gH), w.n_packets, rank, world, dist)
+    ens.set_packets_global(w.x, w.y, w.k, w.l)
+    ens.step(0, w.dt, 7)
+    edges = O.matlab_linspace(0, 6.5, 300)
+    counts = ens.hist_omega(edges)
+    d = ens.diag()
+    allp = ens.gather_packets()
+    if rank == 0:
+        np.savez(tmp, counts=counts, diag=d, x=allp[0], k=allp[2])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_two_ranks_match_single_rank(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    w = W.make_workload("C2", n_packets=1001, nx=32)
+    kx_, ky_ = O.wavenumbers(32)
+    grids = [O.k2g(p) for p in O.velocity_planes_k(w.psik, kx_, ky_)]
+    ens = ShardedEnsemble(OracleEngine(grids, w.dx, w.f, w.gH), w.n_packets)
+    ens.set_packets_global(w.x, w.y, w.k, w.l)
+    ens.step(0, w.dt, 7)
+    edges = O.matlab_linspace(0, 6.5, 300)
+    assert np.array_equal(got["counts"], ens.hist_omega(edges))        # integer histogram: bit-exact
+    assert int(got["counts"].sum()) == 1001
+    x1, _, k1, _ = ens.gather_packets()
+    assert np.array_equal(got["x"], x1) and np.array_equal(got["k"], k1)   # per-packet states identical
+    d1 = ens.diag()
+    assert np.allclose(got["diag"], d1, rtol=1e-13) and got["diag"][6] == 1001
