@@ -34,9 +34,11 @@ __global__ void omega_kernel(long long n, const double* __restrict__ k, const do
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double kk = k[i], ll = l[i];
-    const double w = sqrt(f * f + gH * (kk * kk + ll * ll));
+    // un-fused, in the reference's order (load_data.m:33: sqrt(f^2 + Cg^2.*dot(k,k,2))) so that omega --
+    // and therefore the histogram built from it -- is bit-identical to a host evaluation
+    const double w = sqrt(__dadd_rn(__dmul_rn(f, f), __dmul_rn(gH, __dadd_rn(__dmul_rn(kk, kk), __dmul_rn(ll, ll)))));
     if (omega) omega[i] = w;
-    if (Omega_abs) Omega_abs[i] = w + (u[i] * kk + v[i] * ll);   // omega + dot(U,k)
+    if (Omega_abs) Omega_abs[i] = __dadd_rn(w, __dadd_rn(__dmul_rn(u[i], kk), __dmul_rn(v[i], ll)));   // omega + dot(U,k)
 }
 
 // SPECTRAL-mode RK4 position stage: the continuous ray equations composed point-wise.

@@ -16,8 +16,14 @@
 // (interpolate.m:12-49) evaluated spectrally, and ode_symplectic's stage loop.
 #include "swrt_internal.h"
 #include <cstdio>
+#include <cstdlib>
 
 namespace swrt {
+
+#ifndef SWRT_KUNROLL
+#define SWRT_KUNROLL 4
+#endif
+constexpr int kKUnroll = SWRT_KUNROLL;   // k-steps per unrolled loop body
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers (sm_100a)
@@ -47,6 +53,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// non-blocking probe of an mbarrier phase (test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -195,17 +215,33 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     int kyp = 4 * G;
     g.npass = (g.nky + kyp - 1) / kyp;
     // ~24 KB chunks: kc k-steps of NT*256 bytes each
-    int kc = 96 / g.NT;
-    g.kc = kc >= 8 ? 8 : (kc >= 4 ? 4 : 2);
+    // ~48 KB chunks (kc k-steps of NT*256 bytes), kc a multiple of the k-loop unroll
+    int kc = 192 / g.NT;
+    g.kc = kc >= 16 ? 16 : (kc >= 8 ? 8 : 4);
+    if (const char* e = getenv("SWRT_KC")) g.kc = atoi(e);
+    if (g.kc % kKUnroll) g.kc = ((g.kc + kKUnroll - 1) / kKUnroll) * kKUnroll;
     int ks = (g.kmax + 1 + 1) / 2;
     g.ksteps = ((ks + g.kc - 1) / g.kc) * g.kc;
     g.chunks_per_eval = g.npass * (g.ksteps / g.kc);
     g.chunk_doubles = (size_t)g.kc * g.NT * 32;
     g.total_doubles = (size_t)g.npass * g.ksteps * g.NT * 32;
     size_t chunk_bytes = g.chunk_doubles * 8;
-    g.nstages = (int)((160 * 1024) / chunk_bytes);
-    if (g.nstages > 6) g.nstages = 6;
-    if (g.nstages < 2) g.nstages = 2;
+    g.nstages = (int)((200 * 1024) / chunk_bytes);
+    if (g.nstages > 8) g.nstages = 8;
+    if (g.nstages < 3) g.nstages = 3;
+    // Warps 4..7 (the second warp of every SM sub-partition) start ~1.5 chunks after warps 0..3, so
+    // that one group's non-MMA phases (chunk hand-over, per-pass stage 2, per-step twiddle seeds)
+    // run under the other group's DMMAs instead of leaving the fp64 pipe idle.  A stage is
+    // refilled `lag` chunks after its issuing warp left it, which must exceed the skew.
+    g.lag = g.nstages - 1;
+    if (g.lag > 4) g.lag = 4;
+    g.desync_ns = (int)((g.lag >= 3 ? 1.5 : 0.6) * g.kc * g.NT * 16 / 1.9);
+    // developer tuning overrides (experiments only; defaults above are the shipped configuration)
+    if (const char* e = getenv("SWRT_LAG")) g.lag = atoi(e);
+    if (const char* e = getenv("SWRT_DESYNC_NS")) g.desync_ns = atoi(e);
+    if (const char* e = getenv("SWRT_NSTAGES")) g.nstages = atoi(e);
+    if (g.lag >= g.nstages) g.lag = g.nstages - 1;
+    if (g.lag < 1) g.lag = 1;
     for (int i = 0; i < kMaxPlanes; i++) g.plane_ids[i] = i < npl ? plane_ids[i] : 0;
     return g;
 }
@@ -249,24 +285,32 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
     long long my_tiles = 0;
     if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - 1 - blockIdx.x) / gridDim.x + 1;
     const long long total_chunks = my_tiles * nevals * (long long)g.chunks_per_eval;
-    const bool is_producer = (threadIdx.x == 0);
-    // The packed stack is streamed through a ring of nstages smem buffers by ONE elected thread
-    // (warp 0 lane 0) with cp.async.bulk; chunk j lives in stage j % nstages.  The refill for chunk
-    // ci + nstages - 2 is issued when warp 0 starts chunk ci, i.e. into the stage every warp left
-    // two chunks ago, so the empty-barrier wait is (almost) never a stall.
-    long long pj = 0;           // next chunk to issue
-    int pstage = 0, pcidx = 0; uint32_t pphase = 0;
-    auto producer_issue = [&]() {
-        if (pj >= nstages) mbar_wait(&empty_bar[pstage], pphase ^ 1);
-        mbar_expect_tx(&full_bar[pstage], chunk_bytes);
-        bulk_g2s(smem_raw + (size_t)pstage * chunk_bytes, a.stack + (size_t)pcidx * g.chunk_doubles, chunk_bytes,
-                 &full_bar[pstage]);
-        if (++pcidx == g.chunks_per_eval) pcidx = 0;
-        if (++pstage == nstages) { pstage = 0; pphase ^= 1; }
-        ++pj;
+    // The packed stack streams through a ring of nstages smem buffers with cp.async.bulk; chunk j
+    // lives in stage j % nstages.  Producer duty rotates over the warps (lane 0 of warp j % 8 issues
+    // chunk j) so that no single warp paces the CTA.  Chunk j is issued when its warp STARTS chunk
+    // j - D (D = nstages - lag): the stage it refills was left `lag` chunks ago by that warp, and lag
+    // exceeds the deliberate skew between the two warp groups, so the empty-barrier wait inside is
+    // (almost) never a stall.  No deadlock: the issue of chunk j happens before its warp waits on the
+    // full barrier of chunk j - D, and only needs chunks < j - D, which were issued earlier.
+    const int D = nstages - g.lag;
+    auto producer_issue = [&](long long j) {
+        const int st = (int)(j % nstages);
+        const long long it = j / nstages;
+        if (it > 0) mbar_wait(&empty_bar[st], (uint32_t)((it - 1) & 1));
+        mbar_expect_tx(&full_bar[st], chunk_bytes);
+        bulk_g2s(smem_raw + (size_t)st * chunk_bytes, a.stack + (size_t)(j % g.chunks_per_eval) * g.chunk_doubles,
+                 chunk_bytes, &full_bar[st]);
     };
-    if (is_producer) {
-        for (int i = 0; i < nstages - 2 && pj < total_chunks; i++) producer_issue();
+    if (lane == 0) {
+        for (int j = 0; j < D && j < total_chunks; j++)
+            if (j % kConsumerWarps == warp) producer_issue(j);
+    }
+
+    if (warp >= kConsumerWarps / 2 && g.desync_ns > 0) {
+        // __nanosleep returns far too early for this purpose (measured ~250 cycles for 2000 ns): spin on
+        // the SM clock instead (desync_ns is converted with the nominal 1.9 GHz it was computed for)
+        const long long until = clock64() + (long long)(g.desync_ns * 1.9);
+        while (clock64() < until) {}
     }
 
     // ===== consumer warps =====
@@ -278,6 +322,18 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
     const int kyp_passes = g.npass;
 
     int stage = 0; uint32_t phase = 0;
+    long long ci = 0;        // chunks consumed so far by this warp
+    bool ready = false;      // next chunk's full barrier already observed complete
+#ifdef SWRT_TRACE
+    int trace_n = 0;
+#define SWRT_TRACE_EV(id)                                                                      \
+    do {                                                                                       \
+        if (a.trace && blockIdx.x == 3 && lane == 0 && trace_n < 4 * 160)                      \
+            a.trace[(size_t)warp * 4 * 160 + trace_n++] = (unsigned long long)clock64();       \
+    } while (0)
+#else
+#define SWRT_TRACE_EV(id) do {} while (0)
+#endif
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         long long prow[MT];
@@ -348,31 +404,48 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
                     tp_[mt] = ep0[mt]; tq_[mt] = eq0[mt];
                 }
                 for (int ch = 0; ch < chunks_per_pass; ch++) {
-                    if (is_producer && pj < total_chunks) producer_issue();
-                    mbar_wait(&full_bar[stage], phase);
+                    SWRT_TRACE_EV(0);
+                    {   // producer duty for chunk ci + D (one warp in eight, lane 0 only)
+                        const long long j = ci + D;
+                        if (lane == 0 && j < total_chunks && (int)(j % kConsumerWarps) == warp) producer_issue(j);
+                    }
+                    SWRT_TRACE_EV(1);
+                    if (!ready) mbar_wait(&full_bar[stage], phase);
+                    SWRT_TRACE_EV(2);
                     const double2* sB = reinterpret_cast<const double2*>(smem_raw + (size_t)stage * chunk_bytes) + lane;
-#pragma unroll 2
-                    for (int s = 0; s < g.kc; s++) {
+                    int nstage = stage + 1; uint32_t nphase = phase;
+                    if (nstage == nstages) { nstage = 0; nphase ^= 1; }
+                    for (int s0 = 0; s0 < g.kc; s0 += kKUnroll) {
+                        // probe the NEXT chunk's full barrier while this chunk's last k-steps run, so the
+                        // hand-over at the chunk boundary does not wait on the barrier round trip
+                        if (s0 + kKUnroll >= g.kc) ready = mbar_test(&full_bar[nstage], nphase);
 #pragma unroll
-                        for (int tp = 0; tp < HALF_NT; tp++) {
-                            double2 b = sB[(s * HALF_NT + tp) * 32];
+                        for (int su = 0; su < kKUnroll; su++) {
+                            const int s = s0 + su;
+#pragma unroll
+                            for (int tp = 0; tp < HALF_NT; tp++) {
+                                double2 b = sB[(s * HALF_NT + tp) * 32];
+#pragma unroll
+                                for (int mt = 0; mt < MT; mt++) {
+                                    dmma884(acc[mt][2 * tp][0], acc[mt][2 * tp][1], tp_[mt], b.x);
+                                    dmma884(acc[mt][2 * tp + 1][0], acc[mt][2 * tp + 1][1], tp_[mt], b.y);
+                                }
+                            }
 #pragma unroll
                             for (int mt = 0; mt < MT; mt++) {
-                                dmma884(acc[mt][2 * tp][0], acc[mt][2 * tp][1], tp_[mt], b.x);
-                                dmma884(acc[mt][2 * tp + 1][0], acc[mt][2 * tp + 1][1], tp_[mt], b.y);
+                                // E <- E + E*(e^{i 2 tx} - 1)
+                                double np = fma(tp_[mt], xdc[mt], fma(tq_[mt], xds[mt], tp_[mt]));
+                                double nq = fma(tq_[mt], xdc[mt], fma(-tp_[mt], xds[mt], tq_[mt]));
+                                tp_[mt] = np; tq_[mt] = nq;
                             }
                         }
-#pragma unroll
-                        for (int mt = 0; mt < MT; mt++) {
-                            // E <- E + E*(e^{i 2 tx} - 1)
-                            double np = fma(tp_[mt], xdc[mt], fma(tq_[mt], xds[mt], tp_[mt]));
-                            double nq = fma(tq_[mt], xdc[mt], fma(-tp_[mt], xds[mt], tq_[mt]));
-                            tp_[mt] = np; tq_[mt] = nq;
-                        }
                     }
-                    __syncwarp();
+                    SWRT_TRACE_EV(3);
+                    // every lane's LDS of this stage has been consumed by the DMMAs above (mma.sync is
+                    // warp-convergent), so lane 0 may hand the stage back
                     if (lane == 0) mbar_arrive(&empty_bar[stage]);
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    stage = nstage; phase = nphase;
+                    ++ci;
                 }
                 // ---- stage 2: F_c += Gr*cos(ky ty) - Gi*sin(ky ty) for this lane's ky ----------
 #pragma unroll

@@ -654,8 +654,26 @@ static int step_leapfrog(swrt_handle* h, double dt, int nsteps, double alpha0, d
             a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l;
             a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
             a.f2 = h->p.f * h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = inner;
+#ifdef SWRT_TRACE
+            static unsigned long long* tr = nullptr;
+            if (!tr) { cudaMalloc(&tr, 8 * 640 * 8); }
+            cudaMemset(tr, 0, 8 * 640 * 8);
+            a.trace = tr;
+#endif
             if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
             CU(h, launch_spectral(a, SPEC_LEAPFROG, mt, h->num_sms, h->stream));
+#ifdef SWRT_TRACE
+            {
+                std::vector<unsigned long long> hb(8 * 640);
+                cudaStreamSynchronize(h->stream);
+                cudaMemcpy(hb.data(), tr, hb.size() * 8, cudaMemcpyDeviceToHost);
+                FILE* fp = fopen("gpurun_out/trace.txt", "w");
+                if (fp) {
+                    for (int w = 0; w < 8; w++) { for (int i = 0; i < 640; i++) fprintf(fp, "%llu ", hb[w * 640 + i]); fprintf(fp, "\n"); }
+                    fclose(fp);
+                }
+            }
+#endif
         } else {
             LagArgs a{};
             if ((rc = active_grid(h, alpha, &a.grid))) return rc;

@@ -7,7 +7,10 @@
 namespace swrt {
 
 constexpr int kMaxPlanes = 7;          // u,v,ux,uy,vx,vy,eta_g
-constexpr int kConsumerWarps = 8;      // MMA warps per CTA in the spectral kernel
+#ifndef SWRT_CONSUMER_WARPS
+#define SWRT_CONSUMER_WARPS 8
+#endif
+constexpr int kConsumerWarps = SWRT_CONSUMER_WARPS;      // MMA warps per CTA in the spectral kernel
 constexpr int kSpecThreads = kConsumerWarps * 32;         // warp 0 lane 0 also issues the bulk copies
 
 // ---------------------------------------------------------------------------------------------
@@ -27,6 +30,8 @@ struct PackGeom {
     int kc;               // k-steps per chunk (pipeline stage)
     int chunks_per_eval;  // npass * ksteps / kc
     int nstages;
+    int lag;              // a stage is refilled `lag` chunks after warp 0 released it
+    int desync_ns;        // start-up skew of warps 4..7 (0 = none)
     size_t chunk_doubles; // kc * NT * 32
     size_t total_doubles; // npass * ksteps * NT * 32
     int plane_ids[kMaxPlanes];   // which of the 7 source planes each stack plane is
@@ -52,6 +57,7 @@ struct SpecArgs {
     double dx, nxd;         // grid spacing and nx as double
     double f2, gH, dt;
     int nsteps;
+    unsigned long long* trace;   // developer timeline buffer (only read when built with -DSWRT_TRACE)
 };
 
 enum SpecMode { SPEC_EVAL = 0, SPEC_LEAPFROG = 1 };

@@ -75,7 +75,7 @@ def load_library(path: os.PathLike | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("SWRT_LIB", LIB_PATH))   # SWRT_LIB: developer A/B builds
     if not p.exists():
         raise FileNotFoundError(f"{p} not found: build it with `make` or `python -c 'import __graft_entry__ as g; g.build()'`"
                                 " (libswrt has no CPU fallback)")

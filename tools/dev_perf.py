@@ -11,7 +11,8 @@ kx_, ky_ = O.wavenumbers(nx); K2 = kx_**2 + ky_**2
 psik = (rs.randn(nx - 1, nx // 2) + 1j * rs.randn(nx - 1, nx // 2)) / (1 + K2) ** 1.5 * 0.3
 x = rs.uniform(-L / 2, L / 2, n); y = rs.uniform(-L / 2, L / 2, n)
 k = 3 * np.cos(2 * np.pi * np.arange(n) / n); l = 3 * np.sin(2 * np.pi * np.arange(n) / n)
-for mt in ((1, 2) if mode == S.MODE_SPECTRAL else (1,)):
+mts = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [1, 2]
+for mt in (mts if mode == S.MODE_SPECTRAL else (1,)):
     e = S.Engine(nx, L, f, gH, mode)
     e.set_tuning(mt)
     e.set_flow_spectral(psik)
