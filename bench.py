@@ -298,13 +298,15 @@ def main():
         e2e_total = float(t.item())
     e2e_value = n * world * sub * args.steps / (e2e_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (spectral_kernel<6,4,1,LEAPFROG>) ----
-    flops_per_packet_step = eng.work_per_eval(6)                    # 12 nx^2 executed DMMA flops (folded +-kx)
+    # ---- roofline of the dominant kernel (the fused spectral leapfrog kernel) ----
+    ncontract = eng.contracted_planes()                             # 3: psi-hat moments (6 nx^2 flops); 6: six planes (12 nx^2)
+    flops_per_packet_step = eng.work_per_eval(ncontract)            # EXECUTED DMMA flops per packet-step (+-kx folded)
     flops_per_launch = flops_per_packet_step * n * sub
     achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
                 "frac": round(achieved / FP64_DGEMM_TFLOPS, 4), "traffic": None,
-                "kernel": "swrt::spectral_kernel<6,4,1,LEAPFROG> (fp64 DMMA m8n8k4)", "kernel_ms": round(kernel_ms, 4),
+                "kernel": f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'}> (fp64 DMMA m8n8k4)",
+                "kernel_ms": round(kernel_ms, 4), "contracted_planes": ncontract,
                 "flops_per_packet_step": flops_per_packet_step,
                 "peak_source": "measured: cuBLAS DGEMM 8192^3 on this pool's B200 (tools/dgemm_peak.py); DMMA issue peak 37.1 (tools/fp64_peak.cu); MEASURED_PEAKS.json has no fp64 entry",
                 "frac_of_dmma_issue_peak": round(achieved / FP64_DMMA_TFLOPS, 4),

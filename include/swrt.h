@@ -145,8 +145,12 @@ int     swrt_set_stream(swrt_handle* h, void* cuda_stream);
  * waits for it and returns the elapsed milliseconds (<0 on error)                               */
 int     swrt_timer_start(swrt_handle* h);
 double  swrt_timer_stop(swrt_handle* h);
-/* tuning knob: 1 or 2 m-tiles per warp in the spectral kernel (0 = automatic)                  */
-int     swrt_set_tuning(swrt_handle* h, int mtiles, int reserved);
+/* tuning knobs: 1 or 2 m-tiles per warp in the spectral kernel (0 = automatic); flags bit 0 = do
+ * not use the psi-hat moment contraction (always contract the six planes)                      */
+int     swrt_set_tuning(swrt_handle* h, int mtiles, int flags);
+/* planes the spectral kernel contracts for a six-plane evaluation: 3 when every flow slot was
+ * given as psi-hat (moments N0,N1,N2; 6 nx^2 flops), else 6 (12 nx^2 flops); 0 in LAGRANGE6    */
+int     swrt_contracted_planes(const swrt_handle* h);
 
 #ifdef __cplusplus
 }

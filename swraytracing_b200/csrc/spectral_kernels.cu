@@ -100,7 +100,7 @@ __device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) {
 // ------------------------------------------------------------------------------------------------
 // pack / setup kernels
 // ------------------------------------------------------------------------------------------------
-struct PlanePtrs { const double2* p[kMaxPlanes]; };
+struct PlanePtrs { const double2* p[kNumSrcPlanes]; };
 
 __device__ __forceinline__ double2 load_coef(const double2* pl, int kx, int ky, int kmax, int nkx) {
     // half-plane value with the ky=0 conjugate symmetrisation of fulspec.m:16 applied
@@ -151,7 +151,7 @@ __global__ void pack_kernel(PackGeom g, PlanePtrs src, double* __restrict__ stac
 
 void launch_pack(const PackGeom& g, const double2* const* planes_dev, double* stack_dev, cudaStream_t st) {
     PlanePtrs pp;
-    for (int i = 0; i < kMaxPlanes; i++) pp.p[i] = planes_dev[i];
+    for (int i = 0; i < kNumSrcPlanes; i++) pp.p[i] = planes_dev[i];
     size_t n = g.total_doubles;
     int bs = 256;
     pack_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(g, pp, stack_dev);
@@ -177,6 +177,23 @@ __global__ void psi_to_planes_kernel(const double2* __restrict__ psik, PlaneOut 
     double2 vy = make_double2(-ky * v.y, ky * v.x);
     if (idx == kmax) u.x += u_mean;   // (kx,ky) = (0,0): mean shear, grid_U.m:11
     out.p[0][idx] = u; out.p[1][idx] = v; out.p[2][idx] = ux; out.p[3][idx] = uy; out.p[4][idx] = vx; out.p[5][idx] = vy;
+}
+
+// psi-hat moment planes (spectra of REAL fields, so the ky = 0 symmetrisation of fulspec.m:16 applies):
+//   N0 = psi, N1 = i kx psi, N2 = -kx^2 psi   with INTEGER kx
+__global__ void psi_moments_kernel(const double2* __restrict__ psik, double2* n0, double2* n1, double2* n2, int nkx, int nky) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nkx * nky) return;
+    const int kmax = (nkx - 1) / 2;
+    const double kx = (double)((idx % nkx) - kmax);
+    const double2 psi = psik[idx];
+    n0[idx] = psi;
+    n1[idx] = make_double2(-kx * psi.y, kx * psi.x);
+    n2[idx] = make_double2(-kx * kx * psi.x, -kx * kx * psi.y);
+}
+void launch_psi_moments(const double2* psik, double2* n0, double2* n1, double2* n2, int nkx, int nky, cudaStream_t st) {
+    int n = nkx * nky;
+    psi_moments_kernel<<<(n + 255) / 256, 256, 0, st>>>(psik, n0, n1, n2, nkx, nky);
 }
 
 void launch_psi_to_planes(const double2* psik, double2* const* planes, int nkx, int nky, double kappa,
@@ -253,9 +270,15 @@ size_t spectral_smem_bytes(const PackGeom& g) {
 // ------------------------------------------------------------------------------------------------
 // the contraction kernel
 // ------------------------------------------------------------------------------------------------
-template <int NPL, int G, int MT, int MODE>
+// PSI = true: the stack holds the three psi-hat moment planes N0 = psi, N1 = i kx psi, N2 = -kx^2 psi
+// (integer kx); the six velocity/gradient planes of SpectralScheme.m:18-25 are assembled in stage 2:
+//   u = kap ky Im[T G0], v = kap Re[T G1], ux = kap^2 ky Im[T G1], uy = kap^2 ky^2 Re[T G0],
+//   vx = kap^2 Re[T G2], vy = -ux   (T = e^{i ky ty}),  which halves the DMMA work (6 nx^2 flops).
+template <int NPL, int G, int MT, int MODE, bool PSI>
 __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArgs a) {
     constexpr int NT = NPL * G;
+    constexpr int NF = PSI ? 6 : NPL;          // planes produced per packet
+    static_assert(!PSI || NPL == 3, "psi mode contracts exactly three moment planes");
     constexpr int HALF_NT = NT / 2;
     constexpr int TILE_P = kConsumerWarps * 8 * MT;
     static_assert(NT % 2 == 0, "n-tiles are fetched in pairs");
@@ -364,7 +387,8 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
             double xdc[MT], xds[MT];            // rotation by e^{i 2 tx} minus one, sign-adjusted
             Cplx ytw[MT][G];                    // e^{i ky ty} for this lane's ky of each group
             Cplx yrot[MT];                      // e^{i 4G ty}
-            double F[MT][NPL];
+            double F[MT][NF];
+            double kyd[MT];                     // PSI: this lane's ky of group 0 in the current pass (as double)
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
                 double s1, c1;
@@ -391,7 +415,8 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
                 }
                 yrot[mt] = rot;
 #pragma unroll
-                for (int c = 0; c < NPL; c++) F[mt][c] = 0.0;
+                for (int c = 0; c < NF; c++) F[mt][c] = 0.0;
+                kyd[mt] = (double)jq;
             }
 
             // ---- passes over ky blocks -----------------------------------------------------
@@ -453,28 +478,53 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
 #pragma unroll
                     for (int gg = 0; gg < G; gg++) {
                         const double cy = ytw[mt][gg].re, sy = ytw[mt][gg].im;
+                        if constexpr (PSI) {
+                            const double ky = kyd[mt] + (double)(4 * gg);
+                            const double g0r = acc[mt][0 * G + gg][0], g0i = acc[mt][0 * G + gg][1];
+                            const double g1r = acc[mt][1 * G + gg][0], g1i = acc[mt][1 * G + gg][1];
+                            const double g2r = acc[mt][2 * G + gg][0], g2i = acc[mt][2 * G + gg][1];
+                            const double a0 = fma(g0r, cy, -g0i * sy), b0 = fma(g0i, cy, g0r * sy);
+                            const double a1 = fma(g1r, cy, -g1i * sy), b1 = fma(g1i, cy, g1r * sy);
+                            const double a2 = fma(g2r, cy, -g2i * sy);
+                            F[mt][0] = fma(ky, b0, F[mt][0]);          // u  / kap
+                            F[mt][1] += a1;                            // v  / kap
+                            F[mt][2] = fma(ky, b1, F[mt][2]);          // ux / kap^2
+                            F[mt][3] = fma(ky * ky, a0, F[mt][3]);     // uy / kap^2
+                            F[mt][4] += a2;                            // vx / kap^2
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < NPL; c++) {
-                            F[mt][c] = fma(acc[mt][c * G + gg][0], cy, F[mt][c]);
-                            F[mt][c] = fma(-acc[mt][c * G + gg][1], sy, F[mt][c]);
+                            for (int c = 0; c < NPL; c++) {
+                                F[mt][c] = fma(acc[mt][c * G + gg][0], cy, F[mt][c]);
+                                F[mt][c] = fma(-acc[mt][c * G + gg][1], sy, F[mt][c]);
+                            }
                         }
                         ytw[mt][gg] = cmul(ytw[mt][gg], yrot[mt]);
                     }
+                    kyd[mt] += (double)(4 * G);
                 }
             }
             // ---- quad reduction: the 4 lanes of a quad hold 4 interleaved ky subsets ----------
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
-                for (int c = 0; c < NPL; c++) {
+                for (int c = 0; c < (PSI ? 5 : NPL); c++) {
                     double v = F[mt][c];
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
                     F[mt][c] = v;
                 }
+                if constexpr (PSI) {
+                    const double kap = a.kappa, kap2 = a.kappa * a.kappa;
+                    F[mt][0] = fma(kap, F[mt][0], a.u_mean);
+                    F[mt][1] = kap * F[mt][1];
+                    F[mt][2] = kap2 * F[mt][2];
+                    F[mt][3] = kap2 * F[mt][3];
+                    F[mt][4] = kap2 * F[mt][4];
+                    F[mt][5] = -F[mt][2];
+                }
             }
             if (MODE == SPEC_LEAPFROG) {
-                if constexpr (NPL >= 6) {
+                if constexpr (NF >= 6) {
                     const double h = 0.5 * a.dt;
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {
@@ -497,7 +547,7 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
                     for (int mt = 0; mt < MT; mt++) {
                         if (prow[mt] < a.n) {
 #pragma unroll
-                            for (int c = 0; c < NPL; c++)
+                            for (int c = 0; c < NF; c++)
                                 if (a.out[c]) a.out[c][prow[mt]] = F[mt][c];
                         }
                     }
@@ -518,11 +568,11 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
     }
 }
 
-template <int NPL, int G, int MT, int MODE>
+template <int NPL, int G, int MT, int MODE, bool PSI>
 static cudaError_t launch_inst(const SpecArgs& a, int num_sms, cudaStream_t st) {
     constexpr int TILE_P = kConsumerWarps * 8 * MT;
     size_t smem = spectral_smem_bytes(a.g);
-    auto kern = spectral_kernel<NPL, G, MT, MODE>;
+    auto kern = spectral_kernel<NPL, G, MT, MODE, PSI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long ntiles = (a.n + TILE_P - 1) / TILE_P;
@@ -534,11 +584,17 @@ static cudaError_t launch_inst(const SpecArgs& a, int num_sms, cudaStream_t st) 
 
 template <int NPL, int G, int MT>
 static cudaError_t dispatch_mode(const SpecArgs& a, int mode, int num_sms, cudaStream_t st) {
+    if (a.psi) {
+        if constexpr (NPL == 3) {
+            if (mode == SPEC_LEAPFROG) return launch_inst<NPL, G, MT, SPEC_LEAPFROG, true>(a, num_sms, st);
+            return launch_inst<NPL, G, MT, SPEC_EVAL, true>(a, num_sms, st);
+        } else return cudaErrorInvalidValue;
+    }
     if (mode == SPEC_LEAPFROG) {
-        if constexpr (NPL == 6) return launch_inst<NPL, G, MT, SPEC_LEAPFROG>(a, num_sms, st);
+        if constexpr (NPL == 6) return launch_inst<NPL, G, MT, SPEC_LEAPFROG, false>(a, num_sms, st);
         else return cudaErrorInvalidValue;
     }
-    return launch_inst<NPL, G, MT, SPEC_EVAL>(a, num_sms, st);
+    return launch_inst<NPL, G, MT, SPEC_EVAL, false>(a, num_sms, st);
 }
 
 cudaError_t launch_spectral(const SpecArgs& a, int mode, int mtiles, int num_sms, cudaStream_t st) {

@@ -17,10 +17,11 @@ namespace {
 
 std::string g_create_error;
 
-enum Subset { SUB_SIX = 0, SUB_SEVEN = 1, SUB_UV = 2, SUB_UVH = 3, SUB_COUNT = 4 };
-const int kSubsetN[SUB_COUNT] = {6, 7, 2, 3};
+// plane subsets that get their own packed stack; SUB_PSI3 = the psi-hat moment planes (ids 7,8,9)
+enum Subset { SUB_SIX = 0, SUB_SEVEN = 1, SUB_UV = 2, SUB_UVH = 3, SUB_PSI3 = 4, SUB_COUNT = 5 };
+const int kSubsetN[SUB_COUNT] = {6, 7, 2, 3, 3};
 const int kSubsetIds[SUB_COUNT][kMaxPlanes] = {
-    {0, 1, 2, 3, 4, 5, 0}, {0, 1, 2, 3, 4, 5, 6}, {0, 1, 0, 0, 0, 0, 0}, {0, 1, 6, 0, 0, 0, 0}};
+    {0, 1, 2, 3, 4, 5, 0}, {0, 1, 2, 3, 4, 5, 6}, {0, 1, 0, 0, 0, 0, 0}, {0, 1, 6, 0, 0, 0, 0}, {7, 8, 9, 0, 0, 0, 0}};
 
 struct Stack {
     bool geom_ready = false;
@@ -45,7 +46,10 @@ struct swrt_handle {
     // spectral source planes per slot
     bool slot_set[2] = {false, false};
     int slot_npl[2] = {0, 0};
-    double2* planes[2][kMaxPlanes] = {};
+    double2* planes[2][kNumSrcPlanes] = {};
+    bool psi_ok[2] = {false, false};      // slot was given as psi-hat: moment planes 7..9 are valid
+    double u_mean[2] = {0.0, 0.0};
+    bool disable_psi = false;
     Stack stacks[SUB_COUNT];
     // lagrange grids per slot (node-interleaved, always 7 planes wide when H given else 6)
     double* grid[2] = {nullptr, nullptr};
@@ -131,9 +135,10 @@ int ensure_stack(swrt_handle* h, int sub, int slot, int mtiles) {
     REQUIRE(h, h->slot_set[slot], SWRT_ERR_STATE, "flow slot %d has not been set", slot);
     REQUIRE(h, h->slot_npl[slot] >= (sub == SUB_SEVEN || sub == SUB_UVH ? 7 : 6), SWRT_ERR_STATE,
             "flow slot %d has no H plane (needed by this scheme)", slot);
+    REQUIRE(h, sub != SUB_PSI3 || h->psi_ok[slot], SWRT_ERR_STATE, "flow slot %d was not given as psi-hat", slot);
     if (!s.slot[slot]) CU(h, cudaMalloc(&s.slot[slot], s.g.total_doubles * sizeof(double)));
-    const double2* src[kMaxPlanes];
-    for (int i = 0; i < kMaxPlanes; i++) src[i] = h->planes[slot][i] ? h->planes[slot][i] : h->planes[slot][0];
+    const double2* src[kNumSrcPlanes];
+    for (int i = 0; i < kNumSrcPlanes; i++) src[i] = h->planes[slot][i] ? h->planes[slot][i] : h->planes[slot][0];
     launch_pack(s.g, src, s.slot[slot], h->stream);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -176,6 +181,17 @@ void invalidate_slot(swrt_handle* h, int slot) {
     for (auto& s : h->stacks) s.slot_valid[slot] = false;
 }
 
+// the six velocity/gradient planes can come from the three psi-hat moment planes when every slot
+// involved was uploaded with swrt_set_flow_spectral (halves the contraction work)
+bool use_psi(const swrt_handle* h, double alpha) {
+    return !h->disable_psi && h->psi_ok[0] && (alpha == 0.0 || h->psi_ok[1]);
+}
+void fill_psi_args(const swrt_handle* h, double alpha, SpecArgs& a) {
+    a.psi = true;
+    a.kappa = 2.0 * M_PI / h->p.L;
+    a.u_mean = alpha == 0.0 ? h->u_mean[0] : (1.0 - alpha) * h->u_mean[0] + alpha * h->u_mean[1];
+}
+
 // evaluate subset planes at device positions into device outputs out[c] (c indexes subset planes)
 int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd, const double* yd,
              double* const* out) {
@@ -183,8 +199,10 @@ int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd,
     if (h->p.mode == SWRT_MODE_SPECTRAL) {
         int mt = pick_mtiles(h, n);
         SpecArgs a{};
-        int rc = active_stack(h, sub, alpha, mt, &a.stack, &a.g);
+        const bool psi = (sub == SUB_SIX) && use_psi(h, alpha);
+        int rc = active_stack(h, psi ? (int)SUB_PSI3 : sub, alpha, mt, &a.stack, &a.g);
         if (rc) return rc;
+        if (psi) fill_psi_args(h, alpha, a);
         a.n = n; a.xin = xd; a.yin = yd;
         for (int c = 0; c < kSubsetN[sub]; c++) a.out[c] = out[c];
         a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
@@ -409,6 +427,7 @@ int swrt_destroy(swrt_handle* h) {
 
 // ---- flow upload ------------------------------------------------------------------------------
 static int finish_spectral_slot(swrt_handle* h, int slot, int npl) {
+    h->psi_ok[slot] = false;
     h->slot_set[slot] = true;
     h->slot_npl[slot] = npl;
     invalidate_slot(h, slot);
@@ -442,7 +461,15 @@ int swrt_set_flow_spectral(swrt_handle* h, int slot, const double* psik_re, cons
         const double kappa = 2.0 * M_PI / h->p.L;
         launch_psi_to_planes(psi, h->planes[slot], nkx, nky, kappa, u_mean, h->stream);
         h->launches++;
-        rc = finish_spectral_slot(h, slot, 6);
+        for (int c = 7; c < 10 && rc == SWRT_OK; c++)
+            if (!h->planes[slot][c] && cudaMalloc(&h->planes[slot][c], n * sizeof(double2)) != cudaSuccess)
+                rc = fail(h, SWRT_ERR_ALLOC, "cudaMalloc(moment plane) failed");
+        if (rc == SWRT_OK) {
+            launch_psi_moments(psi, h->planes[slot][7], h->planes[slot][8], h->planes[slot][9], nkx, nky, h->stream);
+            h->launches++;
+            rc = finish_spectral_slot(h, slot, 6);
+            if (rc == SWRT_OK) { h->psi_ok[slot] = true; h->u_mean[slot] = u_mean; }
+        }
     }
     cudaStreamSynchronize(h->stream);
     cudaFree(tr); cudaFree(ti); cudaFree(psi);
@@ -507,7 +534,7 @@ int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* 
             h->launches += 3;
         }
         if (npl == 6) dfree(h->planes[slot][6]);
-        if (rc == SWRT_OK) { h->slot_set[slot] = true; h->slot_npl[slot] = npl; invalidate_slot(h, slot); }
+        if (rc == SWRT_OK) { h->slot_set[slot] = true; h->slot_npl[slot] = npl; h->psi_ok[slot] = false; invalidate_slot(h, slot); }
         cudaStreamSynchronize(h->stream);
     }
     cudaStreamSynchronize(h->stream);
@@ -650,7 +677,9 @@ static int step_leapfrog(swrt_handle* h, double dt, int nsteps, double alpha0, d
         if (h->p.mode == SWRT_MODE_SPECTRAL) {
             int mt = pick_mtiles(h, h->n);
             SpecArgs a{};
-            if ((rc = active_stack(h, SUB_SIX, alpha, mt, &a.stack, &a.g))) return rc;
+            const bool psi = use_psi(h, alpha);
+            if ((rc = active_stack(h, psi ? SUB_PSI3 : SUB_SIX, alpha, mt, &a.stack, &a.g))) return rc;
+            if (psi) fill_psi_args(h, alpha, a);
             a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l;
             a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
             a.f2 = h->p.f * h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = inner;
@@ -935,12 +964,17 @@ double swrt_timer_stop(swrt_handle* h) {
     return (double)ms;
 }
 
-int swrt_set_tuning(swrt_handle* h, int mtiles, int reserved) {
-    (void)reserved;
+int swrt_set_tuning(swrt_handle* h, int mtiles, int flags) {
     if (!h) return SWRT_ERR_ARG;
     REQUIRE(h, mtiles >= 0 && mtiles <= 2, SWRT_ERR_ARG, "mtiles must be 0, 1 or 2");
     h->mtiles = mtiles;
+    h->disable_psi = (flags & 1) != 0;
     return SWRT_OK;
+}
+
+int swrt_contracted_planes(const swrt_handle* h) {
+    if (!h || h->p.mode != SWRT_MODE_SPECTRAL) return 0;
+    return use_psi(h, h->slot_set[1] ? 0.5 : 0.0) ? 3 : 6;
 }
 
 }  // extern "C"

@@ -6,7 +6,8 @@
 
 namespace swrt {
 
-constexpr int kMaxPlanes = 7;          // u,v,ux,uy,vx,vy,eta_g
+constexpr int kMaxPlanes = 7;          // u,v,ux,uy,vx,vy,H
+constexpr int kNumSrcPlanes = 10;      // + the three psi-hat moment planes N0,N1,N2 (ids 7,8,9)
 #ifndef SWRT_CONSUMER_WARPS
 #define SWRT_CONSUMER_WARPS 8
 #endif
@@ -40,8 +41,9 @@ struct PackGeom {
 PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles);
 
 // one source slot: complex planes on the device, [plane][ky][kx+kmax] as double2 (kx fastest)
-void launch_pack(const PackGeom& g, const double2* const* planes_dev /*[7] device ptrs (host array)*/,
+void launch_pack(const PackGeom& g, const double2* const* planes_dev /*[kNumSrcPlanes] device ptrs (host array)*/,
                  double* stack_dev, cudaStream_t st);
+void launch_psi_moments(const double2* psik, double2* n0, double2* n1, double2* n2, int nkx, int nky, cudaStream_t st);
 void launch_psi_to_planes(const double2* psik, double2* const* planes /*host array of 6 dev ptrs*/,
                           int nkx, int nky, double kappa, double u_mean, cudaStream_t st);
 void launch_axpby(double* out, const double* a, const double* b, double wa, double wb, size_t n,
@@ -57,6 +59,8 @@ struct SpecArgs {
     double dx, nxd;         // grid spacing and nx as double
     double f2, gH, dt;
     int nsteps;
+    bool psi;               // stack = psi-hat moment planes; assemble the six planes in stage 2
+    double kappa, u_mean;   // psi mode: 2*pi/L and the mean shear added to u
     unsigned long long* trace;   // developer timeline buffer (only read when built with -DSWRT_TRACE)
 };
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "swrt_work_per_eval": (C.c_double, [C.c_void_p, C.c_int]),
     "swrt_synchronize": (C.c_int, [C.c_void_p]),
     "swrt_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "swrt_contracted_planes": (C.c_int, [C.c_void_p]),
     "swrt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "swrt_timer_start": (C.c_int, [C.c_void_p]),
     "swrt_timer_stop": (C.c_double, [C.c_void_p]),
@@ -256,8 +257,11 @@ class Engine:
             raise SwrtError(-3, "timer failed")
         return ms
 
-    def set_tuning(self, mtiles=0):
-        self._check(self.lib.swrt_set_tuning(self._h, int(mtiles), 0))
+    def set_tuning(self, mtiles=0, use_psi_moments=True):
+        self._check(self.lib.swrt_set_tuning(self._h, int(mtiles), 0 if use_psi_moments else 1))
+
+    def contracted_planes(self):
+        return int(self.lib.swrt_contracted_planes(self._h))
 
 
 # -- handle-free helpers ---------------------------------------------------------------------------

@@ -49,15 +49,19 @@ def make_packets(n, L, seed=5):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nx", [16, 32, 36, 48, 64, 128])
 @pytest.mark.parametrize("mt", [1, 2])
-def test_spectral_eval_vs_exact_sum(nx, mt):
+@pytest.mark.parametrize("psi", [True, False])
+def test_spectral_eval_vs_exact_sum(nx, mt, psi):
+    # psi=True: three psi-hat moment planes contracted, six planes assembled in stage 2;
+    # psi=False: the six planes contracted directly.  Same oracle, same tolerance.
     L = 2 * np.pi; dx = L / nx
     psik, planes = make_flow(nx)
     n = 517 if nx <= 64 else 300
     x, y, k, l = make_packets(n, L)
     ref = CO.spectral_eval(x, y, planes, dx, nx, precise=True)
     with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
-        e.set_tuning(mt)
+        e.set_tuning(mt, use_psi_moments=psi)
         e.set_flow_spectral(psik)
+        assert e.contracted_planes() == (3 if psi else 6)
         e.set_packets(x, y, k, l)
         got = e.eval()
         assert scaled_err(got, ref) < TOL_FIELD
@@ -90,8 +94,13 @@ def test_spectral_planes_upload_and_domain_L20():
     ref = CO.spectral_eval(x, y, planes, dx, nx)
     with S.Engine(nx, L, F0, GH0) as e:
         e.set_flow_spectral(psik, u_mean=0.5)
+        assert e.contracted_planes() == 3
         assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+        e.set_tuning(0, use_psi_moments=False)
+        assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+        e.set_tuning(0, use_psi_moments=True)
         e.set_flow_planes_spectral(planes)
+        assert e.contracted_planes() == 6          # arbitrary planes: no psi-hat to take moments of
         assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
 
 
@@ -191,10 +200,11 @@ def test_rhs_both_modes():
 
 
 @pytest.mark.parametrize("mt", [1, 2])
-def test_leapfrog_trajectory_spectral_golden_and_oracle(mt):
+@pytest.mark.parametrize("psi", [True, False])
+def test_leapfrog_trajectory_spectral_golden_and_oracle(mt, psi):
     nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx; dt = float(GOLD["dt"])
     with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
-        e.set_tuning(mt)
+        e.set_tuning(mt, use_psi_moments=psi)
         e.set_flow_spectral(GOLD["psik"])
         e.set_packets(GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"])
         e.step(S.SCHEME_LEAPFROG, dt, 20)

@@ -1,5 +1,5 @@
 """Developer perf probe: fused leapfrog throughput for a config (run under gpurun)."""
-import sys; sys.path.insert(0, '.')
+import os, sys; sys.path.insert(0, '.')
 import numpy as np
 from oracle import swrt_oracle as O
 import swraytracing_b200 as S
@@ -14,7 +14,7 @@ k = 3 * np.cos(2 * np.pi * np.arange(n) / n); l = 3 * np.sin(2 * np.pi * np.aran
 mts = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [1, 2]
 for mt in (mts if mode == S.MODE_SPECTRAL else (1,)):
     e = S.Engine(nx, L, f, gH, mode)
-    e.set_tuning(mt)
+    e.set_tuning(mt, use_psi_moments=os.environ.get('SWRT_NOPSI') is None)
     e.set_flow_spectral(psik)
     e.set_packets(x, y, k, l)
     dt = 0.1 * dx
@@ -24,6 +24,6 @@ for mt in (mts if mode == S.MODE_SPECTRAL else (1,)):
         e.step(S.SCHEME_LEAPFROG, dt, steps)
         ms, nl = e.last_kernel_ms(); best = min(best, ms)
     pps = n * steps / (best * 1e-3)
-    w = e.work_per_eval(6)
+    w = e.work_per_eval(e.contracted_planes() or 6)
     print(f"nx={nx} n={n} steps={steps} mt={mt} mode={mode}: {best:.3f} ms  {pps:.3e} packet-steps/s  {pps*w*1e-12:.2f} T(work)/s")
     e.close()
