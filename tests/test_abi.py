@@ -75,3 +75,20 @@ def test_library_is_sm100a_with_dmma_and_bulk_copy():
     assert "sm_100a" in out
     assert "DMMA.8x8x4" in out          # fp64 tensor pipe
     assert "UBLKCP" in out              # cp.async.bulk (TMA engine) staging of the coefficient stack
+
+
+def test_mex_gateway_compiles():
+    """matlab/swrt_mex.c against the stub mex.h (neither mkoctfile nor mex exists in this image)"""
+    import shutil, subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not on PATH")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", f"-I{ROOT / 'matlab' / 'stub'}",
+                        f"-I{ROOT / 'include'}", str(ROOT / "matlab" / "swrt_mex.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = (ROOT / "matlab" / "swrt_mex.c").read_text()
+    # every command the .m shims send exists in the gateway
+    import re
+    cmds = set()
+    for m in (ROOT / "matlab" / "shims").glob("*.m"):
+        cmds |= set(re.findall(r"swrt_mex\('([a-z0-9_]+)'", m.read_text()))
+    assert cmds and all(f'"{c}"' in text for c in cmds), cmds
