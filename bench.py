@@ -45,7 +45,7 @@ FP64_DMMA_TFLOPS = 37.1
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="swrt", choices=["swrt", "reference"])
     ap.add_argument("--workload", default="C2")
@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
@@ -262,7 +262,6 @@ def main():
     barrier()
     wall = time.perf_counter() - t_wall0
     launches = eng.launch_count()
-    clocks = sampler.stop() if sampler else None
 
     # dominant-kernel time: re-time the fused leapfrog kernel alone with its own event pair
     k_ms = []
@@ -297,6 +296,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_total = float(t.item())
     e2e_value = n * world * sub * args.steps / (e2e_total * 1e-3)
+    clocks = sampler.stop() if sampler else None       # sampled across the resident, kernel-only and e2e timed regions
 
     # ---- roofline of the dominant kernel (the fused spectral leapfrog kernel) ----
     ncontract = eng.contracted_planes()                             # 3: psi-hat moments (6 nx^2 flops); 6: six planes (12 nx^2)
