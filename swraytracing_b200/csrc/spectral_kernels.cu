@@ -82,8 +82,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // reduced angle of interpolate.m:21: xl = mod(x/dx, nx); returns t = 2*xl/nx so that theta = pi*t
-__device__ __forceinline__ double reduced_turns(double x, double dx, double nxd) {
-    double q = x / dx;
+// When nx is a power of two (inv_nx > 0) q/nx, floor(.)*nx and the subtraction are all exact, so
+// the result equals fmod's to the last bit without fmod's loop.
+__device__ __forceinline__ double reduced_turns(double x, double dx, double nxd, double inv_nx) {
+    const double q = x / dx;
+    if (inv_nx > 0.0) {
+        const double r = q - floor(q * inv_nx) * nxd;
+        return r * (2.0 * inv_nx);
+    }
     double r = fmod(q, nxd);
     if (r < 0.0) r += nxd;
     return 2.0 * r / nxd;
@@ -95,6 +101,21 @@ __device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) {
     r.re = fma(a.re, b.re, -a.im * b.im);
     r.im = fma(a.re, b.im, a.im * b.re);
     return r;
+}
+// dt/2 * gH*k/omega(k) with every rounding pinned (explicit fma / mul), so that the value is the same
+// doubles wherever it is evaluated (tile start, after a kick, fused or single-step launches)
+__device__ __forceinline__ void half_drift(double k, double l, double f2, double gH, double hg, double& hx, double& hy) {
+    const double K2 = fma(k, k, __dmul_rn(l, l));
+    const double s = __dmul_rn(hg, rsqrt(fma(gH, K2, f2)));
+    hx = __dmul_rn(s, k);
+    hy = __dmul_rn(s, l);
+}
+// e^N by binary exponentiation, N a compile-time constant
+template <int N>
+__device__ __forceinline__ Cplx cpow(Cplx e) {
+    if constexpr (N == 1) return e;
+    else if constexpr (N % 2 == 0) { Cplx h = cpow<N / 2>(e); return cmul(h, h); }
+    else return cmul(cpow<N - 1>(e), e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -231,7 +252,6 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     g.G = G; g.NT = npl * G;
     int kyp = 4 * G;
     g.npass = (g.nky + kyp - 1) / kyp;
-    // ~24 KB chunks: kc k-steps of NT*256 bytes each
     // ~48 KB chunks (kc k-steps of NT*256 bytes), kc a multiple of the k-loop unroll
     int kc = 192 / g.NT;
     g.kc = kc >= 16 ? 16 : (kc >= 8 ? 8 : 4);
@@ -243,7 +263,7 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     g.chunk_doubles = (size_t)g.kc * g.NT * 32;
     g.total_doubles = (size_t)g.npass * g.ksteps * g.NT * 32;
     size_t chunk_bytes = g.chunk_doubles * 8;
-    g.nstages = (int)((200 * 1024) / chunk_bytes);
+    g.nstages = (int)((200 * 1024 / kCtasPerSm) / chunk_bytes);
     if (g.nstages > 8) g.nstages = 8;
     if (g.nstages < 3) g.nstages = 3;
     // Warps 4..7 (the second warp of every SM sub-partition) start ~1.5 chunks after warps 0..3, so
@@ -275,7 +295,7 @@ size_t spectral_smem_bytes(const PackGeom& g) {
 //   u = kap ky Im[T G0], v = kap Re[T G1], ux = kap^2 ky Im[T G1], uy = kap^2 ky^2 Re[T G0],
 //   vx = kap^2 Re[T G2], vy = -ux   (T = e^{i ky ty}),  which halves the DMMA work (6 nx^2 flops).
 template <int NPL, int G, int MT, int MODE, bool PSI>
-__global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArgs a) {
+__global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(const SpecArgs a) {
     constexpr int NT = NPL * G;
     constexpr int NF = PSI ? 6 : NPL;          // planes produced per packet
     static_assert(!PSI || NPL == 3, "psi mode contracts exactly three moment planes");
@@ -329,7 +349,7 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
             if (j % kConsumerWarps == warp) producer_issue(j);
     }
 
-    if (warp >= kConsumerWarps / 2 && g.desync_ns > 0) {
+    if (warp >= kConsumerWarps / 2 && g.desync_ns > 0 && kCtasPerSm == 1) {
         // __nanosleep returns far too early for this purpose (measured ~250 cycles for 2000 ns): spin on
         // the SM clock instead (desync_ns is converted with the nominal 1.9 GHz it was computed for)
         const long long until = clock64() + (long long)(g.desync_ns * 1.9);
@@ -370,16 +390,21 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
             else { px[mt] = a.xin[rc]; py[mt] = a.yin[rc]; pk[mt] = 0; pl[mt] = 0; }
         }
 
+        // half-drift displacement dt/2 * gH*k/omega(k): k only changes in the kick, so the value computed
+        // after a kick serves the second half drift of that step AND the first half drift of the next
+        double hcx[MT], hcy[MT];
+        if (MODE == SPEC_LEAPFROG) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                half_drift(pk[mt], pl[mt], a.f2, a.gH, __dmul_rn(__dmul_rn(0.5, a.dt), a.gH), hcx[mt], hcy[mt]);
+            }
+        }
+
         for (int ev = 0; ev < nevals; ev++) {
             if (MODE == SPEC_LEAPFROG) {
                 // phi1(dt/2): x += dt/2 * gH*k/omega(k)   (ode_symplectic.m:13-16,34)
-                const double h = 0.5 * a.dt;
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-                    double om = sqrt(a.f2 + a.gH * (pk[mt] * pk[mt] + pl[mt] * pl[mt]));
-                    px[mt] = px[mt] + h * (a.gH * pk[mt] / om);
-                    py[mt] = py[mt] + h * (a.gH * pl[mt] / om);
-                }
+                for (int mt = 0; mt < MT; mt++) { px[mt] = __dadd_rn(px[mt], hcx[mt]); py[mt] = __dadd_rn(py[mt], hcy[mt]); }
             }
             // ---- twiddle seeds -------------------------------------------------------------
             double tp_[MT], tq_[MT];            // x twiddle in (p,q) form: p = this lane's A element
@@ -392,7 +417,7 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
                 double s1, c1;
-                sincospi(reduced_turns(px[mt], a.dx, a.nxd), &s1, &c1);
+                sincospi(reduced_turns(px[mt], a.dx, a.nxd, a.inv_nx), &s1, &c1);
                 double er = kx0 ? c1 : 1.0, ei = kx0 ? s1 : 0.0;
                 ep0[mt] = odd ? ei : er;
                 eq0[mt] = odd ? er : ei;
@@ -400,20 +425,18 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
                 double ds = 2.0 * s1 * c1;
                 xds[mt] = odd ? ds : -ds;
                 double sy, cy;
-                sincospi(reduced_turns(py[mt], a.dx, a.nxd), &sy, &cy);
+                sincospi(reduced_turns(py[mt], a.dx, a.nxd, a.inv_nx), &sy, &cy);
                 Cplx e1{cy, sy};
                 Cplx e2 = cmul(e1, e1);
                 Cplx e3 = cmul(e2, e1);
                 Cplx e4 = cmul(e2, e2);
                 Cplx cur = jq == 0 ? Cplx{1.0, 0.0} : (jq == 1 ? e1 : (jq == 2 ? e2 : e3));
-                Cplx rot{1.0, 0.0};
 #pragma unroll
                 for (int gg = 0; gg < G; gg++) {
                     ytw[mt][gg] = cur;
                     cur = cmul(cur, e4);
-                    rot = cmul(rot, e4);
                 }
-                yrot[mt] = rot;
+                yrot[mt] = cpow<G>(e4);
 #pragma unroll
                 for (int c = 0; c < NF; c++) F[mt][c] = 0.0;
                 kyd[mt] = (double)jq;
@@ -525,7 +548,6 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
             }
             if (MODE == SPEC_LEAPFROG) {
                 if constexpr (NF >= 6) {
-                    const double h = 0.5 * a.dt;
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {
                         // phi2(dt): x += dt*U(x1); k -= dt*(grad U)^T k with the OLD k (ode_symplectic.m:18-21)
@@ -535,10 +557,12 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_kernel(const SpecArg
                         const double k0 = pk[mt], l0 = pl[mt];
                         pk[mt] = k0 - a.dt * (ux * k0 + vx * l0);
                         pl[mt] = l0 - a.dt * (uy * k0 + vy * l0);
-                        // phi1(dt/2)
-                        double om = sqrt(a.f2 + a.gH * (pk[mt] * pk[mt] + pl[mt] * pl[mt]));
-                        px[mt] = px[mt] + h * (a.gH * pk[mt] / om);
-                        py[mt] = py[mt] + h * (a.gH * pl[mt] / om);
+                        // phi1(dt/2) with the new k
+                        // (explicit un-fused mul/add so that a fused run of n steps and n single-step
+                        // launches produce bit-identical states)
+                        half_drift(pk[mt], pl[mt], a.f2, a.gH, __dmul_rn(__dmul_rn(0.5, a.dt), a.gH), hcx[mt], hcy[mt]);
+                        px[mt] = __dadd_rn(px[mt], hcx[mt]);
+                        py[mt] = __dadd_rn(py[mt], hcy[mt]);
                     }
                 }
             } else {
@@ -576,7 +600,7 @@ static cudaError_t launch_inst(const SpecArgs& a, int num_sms, cudaStream_t st) 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long ntiles = (a.n + TILE_P - 1) / TILE_P;
-    int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    int grid = (int)(ntiles < (long long)num_sms * kCtasPerSm ? ntiles : (long long)num_sms * kCtasPerSm);
     if (grid < 1) grid = 1;
     kern<<<grid, kSpecThreads, smem, st>>>(a);
     return cudaGetLastError();

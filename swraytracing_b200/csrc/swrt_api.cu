@@ -206,6 +206,7 @@ int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd,
         a.n = n; a.xin = xd; a.yin = yd;
         for (int c = 0; c < kSubsetN[sub]; c++) a.out[c] = out[c];
         a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
+        a.inv_nx = (h->p.nx & (h->p.nx - 1)) == 0 ? 1.0 / h->p.nx : 0.0;
         CU(h, launch_spectral(a, SPEC_EVAL, mt, h->num_sms, h->stream));
         h->launches++;
         return SWRT_OK;
@@ -682,6 +683,7 @@ static int step_leapfrog(swrt_handle* h, double dt, int nsteps, double alpha0, d
             if (psi) fill_psi_args(h, alpha, a);
             a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l;
             a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
+        a.inv_nx = (h->p.nx & (h->p.nx - 1)) == 0 ? 1.0 / h->p.nx : 0.0;
             a.f2 = h->p.f * h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = inner;
 #ifdef SWRT_TRACE
             static unsigned long long* tr = nullptr;

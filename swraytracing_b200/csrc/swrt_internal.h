@@ -12,6 +12,10 @@ constexpr int kNumSrcPlanes = 10;      // + the three psi-hat moment planes N0,N
 #define SWRT_CONSUMER_WARPS 8
 #endif
 constexpr int kConsumerWarps = SWRT_CONSUMER_WARPS;      // MMA warps per CTA in the spectral kernel
+#ifndef SWRT_CTAS_PER_SM
+#define SWRT_CTAS_PER_SM 1
+#endif
+constexpr int kCtasPerSm = SWRT_CTAS_PER_SM;             // independent CTAs per SM (each with its own smem ring)
 constexpr int kSpecThreads = kConsumerWarps * 32;         // warp 0 lane 0 also issues the bulk copies
 
 // ---------------------------------------------------------------------------------------------
@@ -57,6 +61,7 @@ struct SpecArgs {
     double* x; double* y; double* k; double* l;   // LEAPFROG: state (in/out)
     double* out[kMaxPlanes];                  // EVAL: outputs per stack plane (may be null)
     double dx, nxd;         // grid spacing and nx as double
+    double inv_nx;          // 1/nx when nx is a power of two (exact), else 0
     double f2, gH, dt;
     int nsteps;
     bool psi;               // stack = psi-hat moment planes; assemble the six planes in stage 2
