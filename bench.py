@@ -204,10 +204,14 @@ def main():
     sub = args.substeps
     eng = S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_SPECTRAL, device=local)
     eng.set_tuning(args.mtiles)
-    eng.set_flow_spectral(w.psik, slot=0, u_mean=w.u_mean)
     time_dependent = w.psik2 is not None
-    if time_dependent:
-        eng.set_flow_spectral(w.psik2, slot=1, u_mean=w.u_mean)
+    scheme = {"leapfrog": S.SCHEME_LEAPFROG, "rk4_packet": S.SCHEME_RK4_PACKET, "rk4_xka": S.SCHEME_RK4_XKA}[w.scheme]
+    if w.scheme == "rk4_xka":
+        eng.set_flow_planes_spectral(W.planes_from_psik(w.psik, w.L, w.u_mean, etak=w.extra["etak"]), slot=0)
+    else:
+        eng.set_flow_spectral(w.psik, slot=0, u_mean=w.u_mean)
+        if time_dependent:
+            eng.set_flow_spectral(w.psik2, slot=1, u_mean=w.u_mean)
     ens = ShardedEnsemble(eng, n * world, rank, world, dist, device=torch.device("cuda", local))
     om_max = float(np.sqrt(w.f ** 2 + w.gH * 4 * (w.k ** 2 + w.l ** 2).max()))
     edges = np.linspace(0.0, om_max, 300)            # 299 bins (analysis/load_data.m:38-39)
@@ -231,13 +235,13 @@ def main():
 
     def one_step_resident():
         a0, da = alpha_args(0)
-        eng.step(S.SCHEME_LEAPFROG, w.dt, sub, a0, da)
+        eng.step(scheme, w.dt, sub, a0, da)
         return ens.hist_omega(edges)
 
     def one_step_e2e():
         eng.set_packets(*pin_np)                                     # h2d from pinned host memory
         a0, da = alpha_args(0)
-        eng.step(S.SCHEME_LEAPFROG, w.dt, sub, a0, da)
+        eng.step(scheme, w.dt, sub, a0, da)
         import ctypes as C
         eng._check(eng.lib.swrt_get_packets(eng._h, *[o.ctypes.data_as(C.POINTER(C.c_double)) for o in out_np], None))
         return out_np
@@ -268,7 +272,7 @@ def main():
     for i in range(min(args.steps, 10)):
         flush.fill_(i & 0xFF); torch.cuda.synchronize()
         a0, da = alpha_args(0)
-        eng.step(S.SCHEME_LEAPFROG, w.dt, sub, a0, da)
+        eng.step(scheme, w.dt, sub, a0, da)
         ms, nl = eng.last_kernel_ms()
         k_ms.append(ms)
     kernel_ms = float(np.mean(k_ms))
@@ -300,12 +304,16 @@ def main():
 
     # ---- roofline of the dominant kernel (the fused spectral leapfrog kernel) ----
     ncontract = eng.contracted_planes()                             # 3: psi-hat moments (6 nx^2 flops); 6: six planes (12 nx^2)
-    flops_per_packet_step = eng.work_per_eval(ncontract)            # EXECUTED DMMA flops per packet-step (+-kx folded)
+    # plane-evaluations contracted per packet-step: leapfrog = one six-plane evaluation (3 moment planes when
+    # the flow is psi-hat); step_packet = six planes + 3 x (u,v); step_packet_xka = 4 x (u,v,H) + seven planes
+    plane_evals = {"leapfrog": ncontract, "rk4_packet": ncontract + 6, "rk4_xka": 19}[w.scheme]
+    flops_per_packet_step = eng.work_per_eval(plane_evals)          # EXECUTED DMMA flops per packet-step (+-kx folded)
     flops_per_launch = flops_per_packet_step * n * sub
     achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
                 "frac": round(achieved / FP64_DGEMM_TFLOPS, 4), "traffic": None,
-                "kernel": f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'}> (fp64 DMMA m8n8k4)",
+                "kernel": (f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'}> (fp64 DMMA m8n8k4)"
+                           if w.scheme == "leapfrog" else "swrt::spectral_kernel<*,EVAL> x5 per step + glue (fp64 DMMA m8n8k4)"),
                 "kernel_ms": round(kernel_ms, 4), "contracted_planes": ncontract,
                 "flops_per_packet_step": flops_per_packet_step,
                 "peak_source": "measured: cuBLAS DGEMM 8192^3 on this pool's B200 (tools/dgemm_peak.py); DMMA issue peak 37.1 (tools/fp64_peak.cu); MEASURED_PEAKS.json has no fp64 entry",
@@ -316,14 +324,17 @@ def main():
     lag = None
     if not args.no_lagrange and rank == 0:
         le = S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_LAGRANGE6, device=local)
-        le.set_flow_spectral(w.psik, u_mean=w.u_mean)
+        if w.scheme == "rk4_xka":
+            le.set_flow_planes_spectral(W.planes_from_psik(w.psik, w.L, w.u_mean, etak=w.extra["etak"]))
+        else:
+            le.set_flow_spectral(w.psik, u_mean=w.u_mean)
         le.set_packets(w.x, w.y, w.k, w.l)
         for _ in range(3):
-            le.step(S.SCHEME_LEAPFROG, w.dt, sub)
+            le.step(scheme, w.dt, sub)
         lms = []
         for i in range(min(args.steps, 10)):
             flush.fill_(i & 0xFF); torch.cuda.synchronize()
-            le.step(S.SCHEME_LEAPFROG, w.dt, sub)
+            le.step(scheme, w.dt, sub)
             lms.append(le.last_kernel_ms()[0])
         lm = float(np.mean(lms))
         gathered = le.work_per_eval(6) * n * sub
@@ -333,7 +344,7 @@ def main():
         le.close()
 
     cpu = cpu_spec = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and w.scheme == "leapfrog":
         v, cores, sample = cpu_reference_rate(w)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         v2, cores2, sample2 = cpu_spectral_rate(w)
@@ -344,7 +355,7 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{w.name}: {'time-dependent' if time_dependent else 'steady'} {w.nx}^2 spectral grid, {n} packets/GPU, "
-                                       f"full-spectrum random-phase QG field, leapfrog (ode_symplectic)",
+                                       f"full-spectrum random-phase QG field, {w.scheme}",
                            "packets_per_gpu": n, "nx": w.nx, "substeps_per_step": sub, "mode": "SPECTRAL",
                            "l2": "flushed between timed steps (256 MiB write)", "histogram_bins": 299,
                            "parallelism": f"packets sharded x{world}, flow replicated"},

@@ -350,6 +350,76 @@ def test_C2_full_size_against_cpu_port_and_sharding_identity():
         assert np.all(np.isfinite(full))
 
 
+def test_C3_full_size_two_frame_blend():
+    # BASELINE configs[2]: 256^2, time-evolving flow (two frames blended on the device), 1M packets
+    w = W.make_workload("C3")
+    m = 2
+    p1 = W.planes_from_psik(w.psik, w.L); p2 = W.planes_from_psik(w.psik2, w.L)
+    sub = np.arange(0, w.n_packets, 9973)
+    st = tuple(a[sub] for a in (w.x, w.y, w.k, w.l))
+    for j in range(m):
+        al = (j + 0.5) / m
+        pl = [(1 - al) * u + al * v for u, v in zip(p1, p2)]
+        st = CO.leapfrog_spectral(*st, pl, w.dx, w.nx, w.f, w.gH, w.dt / m, 1, precise=True)
+    with S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_SPECTRAL) as e:
+        e.set_flow_spectral(w.psik, slot=0); e.set_flow_spectral(w.psik2, slot=1)
+        assert e.contracted_planes() == 3
+        e.set_packets(w.x, w.y, w.k, w.l)
+        e.step(S.SCHEME_LEAPFROG, w.dt / m, m, alpha0=0.5 / m, dalpha=1.0 / m)
+        got = np.stack(e.get_packets())
+        assert np.abs(got[:, sub] - np.stack(st)).max() < TOL_TRAJ
+        assert np.all(np.isfinite(got))
+        # histogram of all 1M packets: counts add up, and equal the host histogram of the returned k,l
+        om = np.sqrt(w.f ** 2 + w.gH * (got[2] ** 2 + got[3] ** 2))
+        edges = O.matlab_linspace(0, om.max(), 300)
+        c = e.hist_omega(edges)
+        assert int(c.sum()) == w.n_packets and np.array_equal(c, O.histcounts(om, edges))
+
+
+def test_C4_shard_size_L20_shear():
+    # BASELINE configs[3]: 512^2, L = 20, mean shear on u (qg2layersw_raytrace.m:13,28,187-188); one GPU's
+    # shard of the 16M packets (2M).  Checked on a subsample against the long-double CPU sum.
+    w = W.make_workload("C4", n_packets=2 * 1024 * 1024)
+    planes = W.planes_from_psik(w.psik, w.L, w.u_mean)
+    sub = np.arange(0, w.n_packets, 40009)
+    with S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_SPECTRAL) as e:
+        e.set_flow_spectral(w.psik, u_mean=w.u_mean)
+        e.set_packets(w.x, w.y, w.k, w.l)
+        got = e.eval()
+        ref = CO.spectral_eval(w.x[sub], w.y[sub], planes, w.dx, w.nx, precise=True)
+        assert scaled_err(got[:, sub], ref) < TOL_FIELD
+        assert abs(got[0].mean() - w.u_mean) < 0.05           # the mean shear is there
+        e.step(S.SCHEME_LEAPFROG, w.dt, 1)
+        st = CO.leapfrog_spectral(w.x[sub], w.y[sub], w.k[sub], w.l[sub], planes, w.dx, w.nx, w.f, w.gH, w.dt, 1)
+        assert np.abs(np.stack(e.get_packets())[:, sub] - np.stack(st)).max() < TOL_TRAJ
+
+
+@pytest.mark.parametrize("mode", [S.MODE_LAGRANGE6, S.MODE_SPECTRAL])
+def test_C5_step_packet_xka_large(mode):
+    # BASELINE configs[4]: step_packet_xka with amplitude transport on a geostrophic [u,v,eta] state
+    # (synthetic: the bundled wavevort restart frame is not in the reference tree), 256^2.
+    n = 4 * 1024 * 1024 if mode == S.MODE_LAGRANGE6 else 256 * 1024
+    w = W.make_workload("C5", n_packets=n)
+    planes = W.planes_from_psik(w.psik, w.L, etak=w.extra["etak"])
+    sub = np.arange(0, n, max(1, n // 150))
+    a0 = np.ones(n)
+    with S.Engine(w.nx, w.L, w.f, w.gH, mode) as e:
+        e.set_flow_planes_spectral(planes)
+        e.set_packets(w.x, w.y, w.k, w.l, a0)
+        e.step(S.SCHEME_RK4_XKA, w.dt, 2)
+        got = np.stack(e.get_packets(with_a=True))
+    st = tuple(v[sub] for v in (w.x, w.y, w.k, w.l, a0))
+    if mode == S.MODE_LAGRANGE6:
+        grids = [O.k2g(p) for p in planes]
+        ref = CO.rk4_lagrange(*st, grids, w.dx, w.f, w.Cg, w.dt, 2, True)
+    else:
+        ref = st
+        for _ in range(2):
+            ref = O.rk4_step_batch(*ref, w.dt, w.Cg, w.f, None, w.dx, True, mode="spectral", planes_k=planes, nx=w.nx)
+    assert np.abs(got[:, sub] - np.stack(ref)).max() < TOL_TRAJ
+    assert np.all(np.isfinite(got)) and np.abs(got[4] - 1).max() > 1e-6      # wave action does evolve
+
+
 def test_omega_drift_and_conserved_absolute_frequency():
     # steady flow: Omega = omega + U.k is conserved by the ray equations; the leapfrog keeps the drift
     # bounded and shrinking with dt (images/Symplectic_error: <~ 5e-3 at dt = 0.01 for a weak flow)
