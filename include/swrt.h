@@ -118,6 +118,11 @@ int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, 
  * last bin closed; accumulate != 0 adds to counts instead of overwriting.                      */
 int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges, int nedges,
                     uint64_t* counts, int accumulate);
+/* the same, but the counts stay on the device (u64[nedges-1], owned by the handle, valid until the
+ * next histogram call) so that a multi-GPU host can all-reduce them in place (NCCL) without a
+ * round trip through host memory; the handle's stream is synchronised on return              */
+int swrt_hist_omega_dev(swrt_handle* h, int kind, double alpha, const double* edges, int nedges,
+                        uint64_t** counts_dev);
 /* out[0]=sum omega, out[1]=sum Omega (omega+U.k), out[2]=max omega, out[3]=min omega,
  * out[4]=number of non-finite packets, out[5]=sum a, out[6]=n, out[7]=sum omega*a              */
 int swrt_diag(swrt_handle* h, double alpha, double out[8]);

@@ -61,6 +61,7 @@ struct swrt_handle {
     double *xs = nullptr, *ys = nullptr, *ax = nullptr, *ay = nullptr, *om = nullptr, *Om = nullptr;
     double* diag_dev = nullptr;
     double* edges_dev = nullptr; int edges_cap = 0;
+    std::vector<double> edges_host;       // what edges_dev currently holds
     unsigned long long* counts_dev = nullptr; int counts_cap = 0;
     // instrumentation
     int64_t launches = 0;
@@ -830,26 +831,48 @@ int swrt_omega(swrt_handle* h, double alpha, double* omega, double* Omega_abs) {
     return SWRT_OK;
 }
 
-int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges, int nedges, uint64_t* counts,
-                    int accumulate) {
-    if (!h) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
-    REQUIRE(h, edges && counts && nedges >= 2 && nedges <= 4096, SWRT_ERR_ARG, "bad edges (2 <= nedges <= 4096)");
+// histogram into the handle's device counts buffer (left on the device, stream synchronised)
+static int hist_to_device(swrt_handle* h, int kind, double alpha, const double* edges, int nedges) {
+    REQUIRE(h, edges && nedges >= 2 && nedges <= 4096, SWRT_ERR_ARG, "bad edges (2 <= nedges <= 4096)");
     REQUIRE(h, kind == SWRT_HIST_INTRINSIC || kind == SWRT_HIST_ABSOLUTE, SWRT_ERR_ARG, "bad histogram kind");
     for (int i = 1; i < nedges; i++) REQUIRE(h, edges[i] >= edges[i - 1], SWRT_ERR_ARG, "edges must be non-decreasing");
     int rc = compute_omega(h, alpha, kind == SWRT_HIST_ABSOLUTE);
     if (rc) return rc;
-    if (nedges > h->edges_cap) { dfree(h->edges_dev); CU(h, cudaMalloc(&h->edges_dev, (size_t)nedges * 8)); h->edges_cap = nedges; }
+    if (nedges > h->edges_cap) { dfree(h->edges_dev); CU(h, cudaMalloc(&h->edges_dev, (size_t)nedges * 8)); h->edges_cap = nedges; h->edges_host.clear(); }
     if (nedges - 1 > h->counts_cap) { dfree(h->counts_dev); CU(h, cudaMalloc(&h->counts_dev, (size_t)(nedges - 1) * 8)); h->counts_cap = nedges - 1; }
-    CU(h, cudaMemcpyAsync(h->edges_dev, edges, (size_t)nedges * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((int)h->edges_host.size() != nedges || memcmp(h->edges_host.data(), edges, (size_t)nedges * 8) != 0) {
+        h->edges_host.assign(edges, edges + nedges);          // upload only when the edges changed
+        CU(h, cudaMemcpyAsync(h->edges_dev, h->edges_host.data(), (size_t)nedges * 8, cudaMemcpyHostToDevice, h->stream));
+    }
     CU(h, cudaMemsetAsync(h->counts_dev, 0, (size_t)(nedges - 1) * 8, h->stream));
     launch_hist(h->n, kind == SWRT_HIST_ABSOLUTE ? h->Om : h->om, h->edges_dev, nedges, h->counts_dev, h->stream);
     h->launches++;
+    return SWRT_OK;
+}
+
+int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges, int nedges, uint64_t* counts,
+                    int accumulate) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, counts, SWRT_ERR_ARG, "null counts");
+    int rc = hist_to_device(h, kind, alpha, edges, nedges);
+    if (rc) return rc;
     std::vector<uint64_t> tmp(nedges - 1);
     CU(h, cudaMemcpyAsync(tmp.data(), h->counts_dev, (size_t)(nedges - 1) * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaGetLastError());
     for (int i = 0; i < nedges - 1; i++) counts[i] = accumulate ? counts[i] + tmp[i] : tmp[i];
+    return SWRT_OK;
+}
+
+int swrt_hist_omega_dev(swrt_handle* h, int kind, double alpha, const double* edges, int nedges, uint64_t** counts_dev) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, counts_dev, SWRT_ERR_ARG, "null counts_dev");
+    int rc = hist_to_device(h, kind, alpha, edges, nedges);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    *counts_dev = reinterpret_cast<uint64_t*>(h->counts_dev);
     return SWRT_OK;
 }
 

@@ -15,6 +15,14 @@ def shard_range(n, rank, world):
     return (rank * n) // world, ((rank + 1) * n) // world
 
 
+class _DeviceI64:
+    """__cuda_array_interface__ view of n int64 at a raw device pointer (the engine's histogram counts;
+    u64 counts reinterpreted as i64 -- identical bits for counts < 2^63)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+
+
 class ShardedEnsemble:
     """A rank-local engine holding this rank's packet shard.
 
@@ -48,7 +56,16 @@ class ShardedEnsemble:
         return t.cpu().numpy()
 
     def hist_omega(self, edges, kind=0, alpha=0.0):
-        """global histcounts over all shards: local u64 counts -> SUM all-reduce (bit-exact)."""
+        """global histcounts over all shards: local u64 counts -> SUM all-reduce (bit-exact).
+        With NCCL the counts are reduced in place in the engine's device buffer (no host round trip)."""
+        on_gpu = (self.dist is not None and self.world > 1 and self.device is not None
+                  and getattr(self.device, "type", "cpu") == "cuda" and hasattr(self.engine, "hist_omega_dev"))
+        if on_gpu:
+            import torch
+            ptr, nb = self.engine.hist_omega_dev(edges, kind, alpha)
+            t = torch.as_tensor(_DeviceI64(ptr, nb), device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            return t.cpu().numpy().astype(np.uint64)
         local = self.engine.hist_omega(edges, kind, alpha)
         return self._allreduce_sum(local.astype(np.int64)).astype(np.uint64)
 

@@ -53,6 +53,7 @@ SIGNATURES = {
     "swrt_interpolate": (C.c_int, [C.c_int, _dp, _dp, C.c_int64, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp]),
     "swrt_step": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
     "swrt_hist_omega": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_uint64), C.c_int]),
+    "swrt_hist_omega_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_void_p)]),
     "swrt_diag": (C.c_int, [C.c_void_p, C.c_double, _dp]),
     "swrt_omega": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp]),
     "swrt_g2k": (C.c_int, [C.c_int, _dp, C.c_int, _dp, _dp]),
@@ -218,6 +219,13 @@ class Engine:
         self._check(self.lib.swrt_hist_omega(self._h, kind, float(alpha), _ptr(edges), edges.size,
                                              counts.ctypes.data_as(C.POINTER(C.c_uint64)), int(acc)))
         return counts
+
+    def hist_omega_dev(self, edges, kind=HIST_INTRINSIC, alpha=0.0):
+        """histogram left on the device: returns (device pointer, nbins) of the handle-owned u64 counts"""
+        edges = _f64(edges)
+        ptr = C.c_void_p()
+        self._check(self.lib.swrt_hist_omega_dev(self._h, kind, float(alpha), _ptr(edges), edges.size, C.byref(ptr)))
+        return ptr.value, edges.size - 1
 
     def diag(self, alpha=0.0):
         out = np.empty(8)
