@@ -40,6 +40,10 @@ UNIT = "packet-steps/s"
 # MEASURED_PEAKS.json records no fp64 figure.  See profiles/r01_fp64_peak.json.
 FP64_DGEMM_TFLOPS = 35.5
 FP64_DMMA_TFLOPS = 37.1
+# dram__bytes_read.sum + dram__bytes_write.sum of the leapfrog kernel from the committed ncu --set full
+# capture (profiles/r01_spectral_leapfrog_ncu_summary.json): C2, 16 fused steps/launch.  Algorithmic HBM
+# bytes per launch = 64 B x 65,536 packets = 4.19 MB (x,y,k,l in + out) + the 0.39 MB coefficient stack.
+NCU_TRAFFIC_BYTES = {("C2", 16): 2.54e6}
 
 
 def parse():
@@ -311,7 +315,7 @@ def main():
     flops_per_launch = flops_per_packet_step * n * sub
     achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
-                "frac": round(achieved / FP64_DGEMM_TFLOPS, 4), "traffic": None,
+                "frac": round(achieved / FP64_DGEMM_TFLOPS, 4), "traffic": NCU_TRAFFIC_BYTES.get((w.name, sub)) if w.n_packets == 65536 else None,
                 "kernel": (f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'}> (fp64 DMMA m8n8k4)"
                            if w.scheme == "leapfrog" else "swrt::spectral_kernel<*,EVAL> x5 per step + glue (fp64 DMMA m8n8k4)"),
                 "kernel_ms": round(kernel_ms, 4), "contracted_planes": ncontract,
