@@ -113,6 +113,17 @@ int swrt_interpolate(int device, const double* x, const double* y, int64_t n, co
 /* nsteps fused steps of the chosen scheme; step j evaluates the flow at alpha0 + j*dalpha.    */
 int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha);
 
+/* ---- ode23 (Bogacki-Shampine 3(2), MATLAB builtin called by qgsw_raytrace.m:149 and
+ * qg2layersw_raytrace.m:195 on y = [x;y;k;l]) -- device building blocks.  The HOST owns the step-size
+ * controller (swraytracing_b200/reference_api.py: ode23) so that a multi-GPU host can MAX-all-reduce
+ * the error norm, which in the reference couples all packets.  alpha = t/tmax per stage.
+ *   begin:   f1 = odefun(alpha, y); rh = max_i |f1_i| / max(|y_i|, threshold)
+ *   attempt: stages 2,3, ynew, f4; err = max_i |(f*E)_i| / max(|y_i|, |ynew_i|, threshold)
+ *   accept:  y <- ynew, f1 <- f4 (first-same-as-last)                                           */
+int swrt_bs23_begin(swrt_handle* h, double alpha, double threshold, double* rh_norm);
+int swrt_bs23_attempt(swrt_handle* h, double hstep, const double alpha[3], double threshold, double* err_norm);
+int swrt_bs23_accept(swrt_handle* h);
+
 /* ---- diagnostics -------------------------------------------------------------------------- */
 /* histcounts(omega, edges) (analysis/load_data.m:39-47): counts[nedges-1], bin i = [e_i,e_i+1),
  * last bin closed; accumulate != 0 adds to counts instead of overwriting.                      */

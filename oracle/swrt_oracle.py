@@ -676,3 +676,84 @@ def childress_soward_point(x, y, U0, km, a):
                      km * U0 * (s(km * x) * s(km * y) + a * c(km * x) * c(km * y)),
                      -km * U0 * (s(km * x) * s(km * y) + a * c(km * x) * c(km * y)),
                      km * U0 * (c(km * x) * c(km * y) + a * s(km * x) * s(km * y))])
+
+
+# --------------------------------------------------------------------------------------------
+# ode23 (MATLAB builtin; un-vendored third-party arithmetic, MATLAB R2020b per run.log:4)
+# --------------------------------------------------------------------------------------------
+
+def ode23(odefun, tspan, y0, rtol=1e-3, atol=1e-6):
+    """Restatement of the published algorithm behind MATLAB's ``ode23`` as the reference calls it
+    (``[~,Y] = ode23(ray_ode, [0 dt], y0)``, qgsw_raytrace.m:149): the Bogacki-Shampine 3(2) pair with
+    FSAL and the step-size controller described in Shampine & Reichelt, "The MATLAB ODE Suite" (1997):
+    A = [1/2 3/4 1], B = [1/2 0 2/9; 0 3/4 1/3; 0 0 4/9], E = [-5/72 1/12 1/9 -1/8], pow = 1/3,
+    threshold = atol/rtol, hmax = 0.1*|tf-t0|, err = |h| * ||(f*E) ./ max(|y|,|ynew|,thr)||_inf,
+    rejection factor max(0.5, 0.8 (rtol/err)^pow) (then 0.5), growth 1/(1.25 (err/rtol)^pow) capped at 5.
+    PARITY UNPINNED: MATLAB is proprietary and absent; no reference test stores an ode23 output.
+    Returns (y_final, stats)."""
+    t0, tfinal = float(tspan[0]), float(tspan[1])
+    y = np.array(y0, dtype=np.float64)
+    pw = 1.0 / 3.0
+    threshold = atol / rtol
+    hmax = min(abs(tfinal - t0), abs(0.1 * (tfinal - t0)))
+    t = t0
+    f1 = odefun(t, y)
+    nfevals = 1
+    hmin = 16 * np.spacing(abs(t))
+    absh = min(hmax, abs(tfinal - t0))
+    rh = np.max(np.abs(f1) / np.maximum(np.abs(y), threshold)) / (0.8 * rtol ** pw)
+    if absh * rh > 1:
+        absh = 1 / rh
+    absh = max(absh, hmin)
+    nsteps = nfailed = 0
+    done = False
+    while not done:
+        hmin = 16 * np.spacing(abs(t))
+        absh = min(hmax, max(hmin, absh))
+        h = absh
+        if 1.1 * absh >= abs(tfinal - t):
+            h = tfinal - t; absh = abs(h); done = True
+        nofailed = True
+        while True:
+            f2 = odefun(t + 0.5 * h, y + f1 * (h * 0.5))
+            f3 = odefun(t + 0.75 * h, y + f2 * (h * 0.75))
+            tnew = tfinal if done else t + h
+            ynew = y + (f1 * (h * 2 / 9) + f2 * (h / 3) + f3 * (h * 4 / 9))
+            f4 = odefun(tnew, ynew)
+            nfevals += 3
+            fE = f1 * (-5 / 72) + f2 * (1 / 12) + f3 * (1 / 9) + f4 * (-1 / 8)
+            err = absh * np.max(np.abs(fE) / np.maximum(np.maximum(np.abs(y), np.abs(ynew)), threshold))
+            if not (err <= rtol):
+                nfailed += 1
+                if absh <= hmin:
+                    raise RuntimeError("ode23: step size below hmin")
+                if nofailed:
+                    nofailed = False
+                    absh = max(hmin, absh * max(0.5, 0.8 * (rtol / err) ** pw))
+                else:
+                    absh = max(hmin, 0.5 * absh)
+                h = absh; done = False
+            else:
+                break
+        nsteps += 1
+        if nofailed:
+            temp = 1.25 * (err / rtol) ** pw
+            absh = absh / temp if temp > 0.2 else 5.0 * absh
+        t = tnew; y = ynew; f1 = f4
+    return y, {"nsteps": nsteps, "nfailed": nfailed, "nfevals": nfevals, "t": t}
+
+
+def generate_raytracing_ode(bf1, bf2, Npackets, f, Cg, tmax, h, eval6=None):
+    """qgsw_raytrace.m:258-268: odefun(t, y) on y = [x; y; k; l].  ``eval6(x, y, alpha)`` overrides the
+    Lagrange interpolate_U evaluation (used for the SPECTRAL mode oracle)."""
+    n = Npackets
+
+    def odefun(t, y):
+        x, yy, k, l = y[0:n], y[n:2 * n], y[2 * n:3 * n], y[3 * n:4 * n]
+        if eval6 is None:
+            d = odefun_rhs(x, yy, k, l, t / tmax, bf1, bf2, f, Cg, h)
+        else:
+            d = rhs_from_eval(eval6(x, yy, t / tmax), k, l, f, Cg)
+        return np.concatenate(d)
+
+    return odefun

@@ -174,7 +174,72 @@ __global__ void diag_final_kernel(int nblocks, const double* __restrict__ part, 
     }
     out8[0] = s_om; out8[1] = s_Om; out8[2] = mx; out8[3] = mn; out8[4] = nf; out8[5] = s_a; out8[6] = (double)n; out8[7] = s_oa;
 }
+// ---- Bogacki-Shampine 3(2) building blocks (MATLAB ode23, called by qgsw_raytrace.m:149) ----------
+// stage state: yt = y + h*(b1 f1 + b2 f2 + b3 f3) for the four components x,y,k,l
+__global__ void bs23_stage_kernel(Bs23Args a, double hb1, double hb2, double hb3) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        double acc = a.f[0][c][i] * hb1;
+        if (hb2 != 0.0) acc += a.f[1][c][i] * hb2;
+        if (hb3 != 0.0) acc += a.f[2][c][i] * hb3;
+        a.yt[c][i] = a.y[c][i] + acc;
+    }
+}
+// err = max_i |(f*E)_i| / max(max(|y_i|,|ynew_i|), threshold)   (without the absh factor);
+// mode 1: rh = max_i |f1_i| / max(|y_i|, threshold) for the initial step size
+__global__ void __launch_bounds__(256) bs23_norm_kernel(Bs23Args a, int mode, double thr, unsigned long long* out) {
+    const double E1 = -5.0 / 72.0, E2 = 1.0 / 12.0, E3 = 1.0 / 9.0, E4 = -1.0 / 8.0;
+    double m = 0.0;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            double num, den;
+            if (mode == 1) { num = fabs(a.f[0][c][i]); den = fmax(fabs(a.y[c][i]), thr); }
+            else {
+                num = fabs(a.f[0][c][i] * E1 + a.f[1][c][i] * E2 + a.f[2][c][i] * E3 + a.f[3][c][i] * E4);
+                den = fmax(fmax(fabs(a.y[c][i]), fabs(a.yt[c][i])), thr);
+            }
+            const double r = num / den;
+            m = (r > m || r != r) ? r : m;          // NaN propagates (a blown-up packet fails the step)
+        }
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { double o = sh[threadIdx.x + s], v = sh[threadIdx.x]; sh[threadIdx.x] = (o > v || o != o) ? o : v; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double v = sh[0];
+        if (v != v) v = __longlong_as_double(0x7ff0000000000000LL);     // NaN -> +inf so that the integer max orders it last
+        atomicMax(out, (unsigned long long)__double_as_longlong(v));     // non-negative doubles order like their bit patterns
+    }
+}
+__global__ void bs23_accept_kernel(Bs23Args a) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+#pragma unroll
+    for (int c = 0; c < 4; c++) { a.y[c][i] = a.yt[c][i]; a.f[0][c][i] = a.f[3][c][i]; }
+}
 }  // namespace
+
+void launch_bs23_stage(const Bs23Args& a, double hb1, double hb2, double hb3, cudaStream_t st) {
+    if (a.n > 0) bs23_stage_kernel<<<nblk(a.n, 256), 256, 0, st>>>(a, hb1, hb2, hb3);
+}
+void launch_bs23_norm(const Bs23Args& a, int mode, double thr, unsigned long long* out, cudaStream_t st) {
+    cudaMemsetAsync(out, 0, sizeof(unsigned long long), st);
+    if (a.n <= 0) return;
+    unsigned nb = nblk(a.n, 256 * 4);
+    if (nb > 148 * 8) nb = 148 * 8;
+    bs23_norm_kernel<<<nb, 256, 0, st>>>(a, mode, thr, out);
+}
+void launch_bs23_accept(const Bs23Args& a, cudaStream_t st) {
+    if (a.n > 0) bs23_accept_kernel<<<nblk(a.n, 256), 256, 0, st>>>(a);
+}
 
 void launch_fill(double* p, double v, long long n, cudaStream_t st) {
     if (n > 0) fill_kernel<<<nblk(n, 256), 256, 0, st>>>(p, v, n);

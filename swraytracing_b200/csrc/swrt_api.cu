@@ -60,6 +60,12 @@ struct swrt_handle {
     double* e[kMaxPlanes] = {};
     double *xs = nullptr, *ys = nullptr, *ax = nullptr, *ay = nullptr, *om = nullptr, *Om = nullptr;
     double* diag_dev = nullptr;
+    // ode23 (Bogacki-Shampine) work arrays: yt[4], f[4][4]
+    int64_t bs_cap = 0;
+    double* bs_yt[4] = {};
+    double* bs_f[4][4] = {};
+    unsigned long long* bs_norm_dev = nullptr;
+    bool bs_ready = false;
     double* edges_dev = nullptr; int edges_cap = 0;
     std::vector<double> edges_host;       // what edges_dev currently holds
     unsigned long long* counts_dev = nullptr; int counts_cap = 0;
@@ -417,7 +423,9 @@ int swrt_destroy(swrt_handle* h) {
     for (auto& st : h->stacks) { dfree(st.slot[0]); dfree(st.slot[1]); dfree(st.blend); }
     for (auto& p : h->e) dfree(p);
     dfree(h->xs); dfree(h->ys); dfree(h->ax); dfree(h->ay); dfree(h->om); dfree(h->Om);
-    dfree(h->diag_dev); dfree(h->edges_dev); dfree(h->counts_dev);
+    dfree(h->diag_dev); dfree(h->edges_dev); dfree(h->counts_dev); dfree(h->bs_norm_dev);
+    for (auto& p : h->bs_yt) dfree(p);
+    for (auto& row : h->bs_f) for (auto& p : row) dfree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->tm0) cudaEventDestroy(h->tm0);
@@ -570,6 +578,7 @@ int swrt_set_packets(swrt_handle* h, int64_t n, const double* x, const double* y
     REQUIRE(h, n == 0 || (x && y && k && l), SWRT_ERR_ARG, "null packet array");
     int rc = ensure_packets(h, n);
     if (rc) return rc;
+    h->bs_ready = false;
     if ((rc = h2d(h, h->x, x, n)) || (rc = h2d(h, h->y, y, n)) || (rc = h2d(h, h->k, k, n)) || (rc = h2d(h, h->l, l, n)))
         return rc;
     if (a) { if ((rc = h2d(h, h->a, a, n))) return rc; }
@@ -884,6 +893,91 @@ int swrt_diag(swrt_handle* h, double alpha, double out[8]) {
     launch_diag(h->n, h->x, h->y, h->k, h->l, h->a, h->om, h->slot_set[0] ? h->Om : h->om, h->diag_dev, h->stream);
     h->launches += 2;
     CU(h, cudaMemcpyAsync(out, h->diag_dev, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+// ---- ode23 building blocks --------------------------------------------------------------------
+static int bs23_setup(swrt_handle* h, Bs23Args& a) {
+    int rc = ensure_scratch(h, h->n);
+    if (rc) return rc;
+    if (h->n > h->bs_cap) {
+        for (auto& p : h->bs_yt) dfree(p);
+        for (auto& row : h->bs_f) for (auto& p : row) dfree(p);
+        size_t b = (size_t)h->n * sizeof(double);
+        for (auto& p : h->bs_yt) CU(h, cudaMalloc(&p, b));
+        for (auto& row : h->bs_f) for (auto& p : row) CU(h, cudaMalloc(&p, b));
+        h->bs_cap = h->n; h->bs_ready = false;
+    }
+    if (!h->bs_norm_dev) CU(h, cudaMalloc(&h->bs_norm_dev, sizeof(unsigned long long)));
+    a.n = h->n;
+    a.y[0] = h->x; a.y[1] = h->y; a.y[2] = h->k; a.y[3] = h->l;
+    for (int c = 0; c < 4; c++) { a.yt[c] = h->bs_yt[c]; for (int j = 0; j < 4; j++) a.f[j][c] = h->bs_f[j][c]; }
+    return SWRT_OK;
+}
+// f_j = odefun(alpha, state) with state = (sx, sy, sk, sl) device arrays
+static int bs23_rhs(swrt_handle* h, double alpha, double* const st[4], double* const fj[4]) {
+    int rc = eval_dev(h, SUB_SIX, alpha, h->n, st[0], st[1], h->e);
+    if (rc) return rc;
+    launch_rhs(h->n, st[2], st[3], h->e, h->p.f, sqrt(h->p.gH), fj[0], fj[1], fj[2], fj[3], h->stream);
+    h->launches++;
+    return SWRT_OK;
+}
+static int bs23_read_norm(swrt_handle* h, double* out) {
+    unsigned long long bits = 0;
+    CU(h, cudaMemcpyAsync(&bits, h->bs_norm_dev, sizeof bits, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    memcpy(out, &bits, sizeof bits);
+    return SWRT_OK;
+}
+
+int swrt_bs23_begin(swrt_handle* h, double alpha, double threshold, double* rh_norm) {
+    if (!h || !rh_norm) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
+    Bs23Args a{};
+    int rc = bs23_setup(h, a);
+    if (rc) return rc;
+    double* f1[4] = {a.f[0][0], a.f[0][1], a.f[0][2], a.f[0][3]};
+    if ((rc = bs23_rhs(h, alpha, a.y, f1))) return rc;
+    launch_bs23_norm(a, 1, threshold, h->bs_norm_dev, h->stream);
+    h->launches++;
+    h->bs_ready = true;
+    return bs23_read_norm(h, rh_norm);
+}
+
+int swrt_bs23_attempt(swrt_handle* h, double hstep, const double alpha[3], double threshold, double* err_norm) {
+    if (!h || !alpha || !err_norm) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, h->bs_ready && h->bs_cap >= h->n, SWRT_ERR_STATE, "swrt_bs23_begin has not been called");
+    Bs23Args a{};
+    int rc = bs23_setup(h, a);
+    if (rc) return rc;
+    double* f2[4] = {a.f[1][0], a.f[1][1], a.f[1][2], a.f[1][3]};
+    double* f3[4] = {a.f[2][0], a.f[2][1], a.f[2][2], a.f[2][3]};
+    double* f4[4] = {a.f[3][0], a.f[3][1], a.f[3][2], a.f[3][3]};
+    // A = [1/2 3/4 1], B = [1/2 0 2/9; 0 3/4 1/3; 0 0 4/9; 0 0 0]
+    launch_bs23_stage(a, hstep * 0.5, 0.0, 0.0, h->stream);
+    if ((rc = bs23_rhs(h, alpha[0], a.yt, f2))) return rc;
+    launch_bs23_stage(a, 0.0, hstep * 0.75, 0.0, h->stream);
+    if ((rc = bs23_rhs(h, alpha[1], a.yt, f3))) return rc;
+    launch_bs23_stage(a, hstep * (2.0 / 9.0), hstep * (1.0 / 3.0), hstep * (4.0 / 9.0), h->stream);   // ynew
+    if ((rc = bs23_rhs(h, alpha[2], a.yt, f4))) return rc;
+    launch_bs23_norm(a, 0, threshold, h->bs_norm_dev, h->stream);
+    h->launches += 4;
+    return bs23_read_norm(h, err_norm);
+}
+
+int swrt_bs23_accept(swrt_handle* h) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, h->bs_ready, SWRT_ERR_STATE, "swrt_bs23_begin has not been called");
+    Bs23Args a{};
+    int rc = bs23_setup(h, a);
+    if (rc) return rc;
+    launch_bs23_accept(a, h->stream);
+    h->launches++;
     CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
 }

@@ -121,4 +121,14 @@ void launch_diag(long long n, const double* x, const double* y, const double* k,
                  const double* omega, const double* Omega_abs, double* out8_dev, cudaStream_t st);
 void launch_fill(double* p, double v, long long n, cudaStream_t st);
 
+struct Bs23Args {          // ode23 work arrays, component order x,y,k,l
+    long long n;
+    double* y[4];          // the packet state itself
+    double* yt[4];         // stage state / ynew
+    double* f[4][4];       // f1..f4
+};
+void launch_bs23_stage(const Bs23Args& a, double hb1, double hb2, double hb3, cudaStream_t st);
+void launch_bs23_norm(const Bs23Args& a, int mode, double thr, unsigned long long* out, cudaStream_t st);
+void launch_bs23_accept(const Bs23Args& a, cudaStream_t st);
+
 }  // namespace swrt

@@ -44,6 +44,22 @@ class ShardedEnsemble:
     def step(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
         self.engine.step(scheme, dt, nsteps, alpha0, dalpha)
 
+    def ode23(self, tspan, tmax, rtol=1e-3, atol=1e-6):
+        """the reference's per-flow-step ode23 solve over ALL shards: the error norm is MAX-all-reduced so
+        that every rank accepts/rejects the same steps (the reference's norm couples all packets)."""
+        from .reference_api import ode23
+        return ode23(self.engine, tspan, tmax, rtol, atol, reduce_max=self._allreduce_max)
+
+    def _allreduce_max(self, v):
+        if self.dist is None or self.world == 1:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        if self.device is not None:
+            t = t.to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.cpu()[0])
+
     # -- reductions --
     def _allreduce_sum(self, arr_i64):
         if self.dist is None or self.world == 1:

@@ -53,6 +53,9 @@ SIGNATURES = {
     "swrt_interpolate": (C.c_int, [C.c_int, _dp, _dp, C.c_int64, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp]),
     "swrt_step": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
     "swrt_hist_omega": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_uint64), C.c_int]),
+    "swrt_bs23_begin": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _dp]),
+    "swrt_bs23_attempt": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, _dp]),
+    "swrt_bs23_accept": (C.c_int, [C.c_void_p]),
     "swrt_hist_omega_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_void_p)]),
     "swrt_diag": (C.c_int, [C.c_void_p, C.c_double, _dp]),
     "swrt_omega": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp]),
@@ -209,6 +212,21 @@ class Engine:
 
     def step(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
         self._check(self.lib.swrt_step(self._h, int(scheme), float(dt), int(nsteps), float(alpha0), float(dalpha)))
+
+    # -- ode23 building blocks (the controller lives in reference_api.ode23) --
+    def bs23_begin(self, alpha, threshold):
+        out = C.c_double(0.0)
+        self._check(self.lib.swrt_bs23_begin(self._h, float(alpha), float(threshold), C.byref(out)))
+        return out.value
+
+    def bs23_attempt(self, hstep, alphas, threshold):
+        al = (C.c_double * 3)(*[float(a) for a in alphas])
+        out = C.c_double(0.0)
+        self._check(self.lib.swrt_bs23_attempt(self._h, float(hstep), al, float(threshold), C.byref(out)))
+        return out.value
+
+    def bs23_accept(self):
+        self._check(self.lib.swrt_bs23_accept(self._h))
 
     # -- diagnostics --
     def hist_omega(self, edges, kind=HIST_INTRINSIC, alpha=0.0, counts=None):

@@ -237,3 +237,68 @@ def omega(k, f, gH):
     """symplectic_full_fourier.m:62-64 -- host helper, O(Np)."""
     k = np.asarray(k, dtype=np.float64)
     return np.sqrt(f * f + gH * np.sum(k * k, axis=1))
+
+
+# ------------------------------------------------------------------------------------------------
+# ode23 -- the production drivers' integrator (qgsw_raytrace.m:149, qg2layersw_raytrace.m:195)
+# ------------------------------------------------------------------------------------------------
+
+def ode23(target, tspan, tmax, rtol=1e-3, atol=1e-6, reduce_max=None):
+    """``[~, Y] = ode23(ray_ode, [0 dt], y0)`` for the packets resident in ``target`` (an Engine):
+    MATLAB's ode23 = Bogacki-Shampine 3(2) pair with first-same-as-last, restated from its published
+    description (Shampine & Reichelt, "The MATLAB ODE Suite", SIAM J. Sci. Comput. 18, 1997; MATLAB
+    R2020b defaults RelTol 1e-3, AbsTol 1e-6, MaxStep 0.1*|tf-t0|).  MATLAB itself is not available,
+    so parity is against the oracle's restatement of the same algorithm (parity unpinned).
+
+    The stages run on the device (swrt_bs23_*); this controller is host logic.  The error norm is the
+    inf-norm over ALL packets (the reference bundles them in one 4*Np system), so a multi-GPU caller
+    passes ``reduce_max`` (an all-reduce MAX over ranks) and every rank takes identical decisions.
+    RHS time dependence: alpha = t/tmax (qgsw_raytrace.m:261).  Returns dict(nsteps, nfailed, nfevals, t)."""
+    red = reduce_max if reduce_max is not None else (lambda v: v)
+    t0, tfinal = float(tspan[0]), float(tspan[1])
+    pw = 1.0 / 3.0
+    threshold = atol / rtol
+    hmax = min(abs(tfinal - t0), abs(0.1 * (tfinal - t0)))
+    t = t0
+    rh = red(target.bs23_begin(t / tmax, threshold)) / (0.8 * rtol ** pw)
+    nfevals = 1
+    hmin = 16 * np.spacing(abs(t))            # 16*eps(t)
+    absh = min(hmax, abs(tfinal - t0))
+    if absh * rh > 1:
+        absh = 1 / rh
+    absh = max(absh, hmin)
+    nsteps = nfailed = 0
+    done = False
+    while not done:
+        hmin = 16 * np.spacing(abs(t))
+        absh = min(hmax, max(hmin, absh))
+        h = absh
+        if 1.1 * absh >= abs(tfinal - t):
+            h = tfinal - t
+            absh = abs(h)
+            done = True
+        nofailed = True
+        while True:
+            tnew = tfinal if done else t + h
+            err = absh * red(target.bs23_attempt(h, [(t + 0.5 * h) / tmax, (t + 0.75 * h) / tmax, tnew / tmax], threshold))
+            nfevals += 3
+            if not (err <= rtol):            # also catches NaN
+                nfailed += 1
+                if absh <= hmin:
+                    raise RuntimeError(f"ode23: step size below hmin at t = {t!r} (a packet blew up?)")
+                if nofailed:
+                    nofailed = False
+                    absh = max(hmin, absh * max(0.5, 0.8 * (rtol / err) ** pw)) if np.isfinite(err) else max(hmin, 0.5 * absh)
+                else:
+                    absh = max(hmin, 0.5 * absh)
+                h = absh
+                done = False
+            else:
+                break
+        nsteps += 1
+        target.bs23_accept()
+        if nofailed:
+            temp = 1.25 * (err / rtol) ** pw
+            absh = absh / temp if temp > 0.2 else 5.0 * absh
+        t = tnew
+    return {"nsteps": nsteps, "nfailed": nfailed, "nfevals": nfevals, "t": t}

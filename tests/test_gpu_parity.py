@@ -568,3 +568,58 @@ def test_device_g2k_k2g_grid_U():
     ref = O.grid_U(qk, 3.0, K2, kx_, ky_, 0.5)
     for name in ref:
         assert np.abs(bf[name] - ref[name]).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# "next" row f2: the production drivers' ode23 solve (qgsw_raytrace.m:143-150)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [S.MODE_LAGRANGE6, S.MODE_SPECTRAL])
+def test_ode23_flow_step_matches_oracle(mode):
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx
+    kx_, ky_ = O.wavenumbers(nx)
+    p1 = O.velocity_planes_k(GOLD["psik"], kx_, ky_); p2 = O.velocity_planes_k(GOLD["psik2"], kx_, ky_)
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    bf1 = dict(zip(names, [O.k2g(p) for p in p1])); bf2 = dict(zip(names, [O.k2g(p) for p in p2]))
+    x, y, k, l = GOLD["x"], GOLD["y"], GOLD["k"], GOLD["l"]
+    n = x.size
+    tmax = 0.4                                # one (long) flow step, so that the controller takes several steps
+    if mode == S.MODE_LAGRANGE6:
+        ode = O.generate_raytracing_ode(bf1, bf2, n, F0, 1.0, tmax, dx)
+    else:
+        ev = lambda xx, yy, al: CO.spectral_eval(xx, yy, [(1 - al) * a + al * b for a, b in zip(p1, p2)], dx, nx)
+        ode = O.generate_raytracing_ode(None, None, n, F0, 1.0, tmax, dx, eval6=ev)
+    yref, sref = O.ode23(ode, [0, tmax], np.concatenate([x, y, k, l]))
+    with S.Engine(nx, L, F0, GH0, mode) as e:
+        e.set_flow_spectral(GOLD["psik"], slot=0); e.set_flow_spectral(GOLD["psik2"], slot=1)
+        e.set_packets(x, y, k, l)
+        st = R.ode23(e, [0, tmax], tmax)
+        got = np.concatenate(e.get_packets())
+        assert (st["nsteps"], st["nfailed"], st["nfevals"]) == (sref["nsteps"], sref["nfailed"], sref["nfevals"])
+        assert st["nsteps"] >= 10              # MaxStep = 0.1*(tf - t0)
+        assert np.abs(got - yref).max() < TOL_TRAJ
+        # tighter tolerances: more steps, same agreement
+        e.set_packets(x, y, k, l)
+        st2 = R.ode23(e, [0, tmax], tmax, rtol=1e-6, atol=1e-7)      # SW_zero_background_raytracing.m:71-72
+        yref2, sref2 = O.ode23(ode, [0, tmax], np.concatenate([x, y, k, l]), rtol=1e-6, atol=1e-7)
+        # At RelTol 1e-6 the estimator sits at the kinks of the piecewise-polynomial Lagrange interpolant, so
+        # accept/reject decisions hinge on 1e-16-level differences: the two runs may take slightly different
+        # step sequences, each a valid solution to the requested tolerance.
+        assert st2["nsteps"] > st["nsteps"] and abs(st2["nsteps"] - sref2["nsteps"]) <= 0.1 * sref2["nsteps"]
+        assert np.abs(np.concatenate(e.get_packets()) - yref2).max() < (TOL_TRAJ if mode == S.MODE_SPECTRAL else 1e-5)
+        with pytest.raises(S.SwrtError):
+            e.set_packets(x, y, k, l)
+            e.bs23_attempt(0.1, [0, 0, 0], 1e-3)          # attempt without begin after new packets
+
+
+def test_ode23_error_norm_couples_all_packets():
+    # one stiff packet (huge k) shrinks everybody's step: the reference solves ONE 4*Np system
+    nx = int(GOLD["nx"]); L = float(GOLD["L"])
+    x, y, k, l = (GOLD[q].copy() for q in ("x", "y", "k", "l"))
+    with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
+        e.set_flow_spectral(GOLD["psik"] * 20)
+        e.set_packets(x, y, k, l)
+        base = R.ode23(e, [0, 0.5], np.inf)              # steady flow: alpha = t/inf = 0
+        k[3] *= 300.0
+        e.set_packets(x, y, k, l)
+        stiff = R.ode23(e, [0, 0.5], np.inf)
+        assert stiff["nsteps"] > base["nsteps"]

@@ -70,6 +70,27 @@ class OracleEngine:
     def hist_omega(self, edges, kind=0, alpha=0.0):
         return CO.histcounts(O.omega_of_k(self.s[2], self.s[3], self.f, self.gH), edges)
 
+    # ode23 building blocks (same contract as swrt_bs23_*), numpy arithmetic
+    def _F(self, alpha, st):
+        e6 = CO.interpolate6(st[0], st[1], self.grids, self.dx)
+        return list(O.rhs_from_eval(e6, st[2], st[3], self.f, np.sqrt(self.gH)))
+
+    def bs23_begin(self, alpha, thr):
+        self.f1 = self._F(alpha, self.s)
+        return max(np.max(np.abs(f) / np.maximum(np.abs(y), thr)) for f, y in zip(self.f1, self.s))
+
+    def bs23_attempt(self, h, alphas, thr):
+        y = self.s
+        f2 = self._F(alphas[0], [a + b * (h * 0.5) for a, b in zip(y, self.f1)])
+        f3 = self._F(alphas[1], [a + b * (h * 0.75) for a, b in zip(y, f2)])
+        self.yn = [a + (b * (h * 2 / 9) + c * (h / 3) + d * (h * 4 / 9)) for a, b, c, d in zip(y, self.f1, f2, f3)]
+        self.f4 = self._F(alphas[2], self.yn)
+        fE = [b * (-5 / 72) + c * (1 / 12) + d * (1 / 9) + e * (-1 / 8) for b, c, d, e in zip(self.f1, f2, f3, self.f4)]
+        return max(np.max(np.abs(g) / np.maximum(np.maximum(np.abs(a), np.abs(b)), thr)) for g, a, b in zip(fE, y, self.yn))
+
+    def bs23_accept(self):
+        self.s, self.f1 = self.yn, self.f4
+
     def diag(self, alpha=0.0):
         w = O.omega_of_k(self.s[2], self.s[3], self.f, self.gH)
         return np.array([w.sum(), w.sum(), w.max(), w.min(), 0.0, float(w.size), float(w.size), w.sum()])
@@ -94,8 +115,10 @@ def _worker(rank, world, port, tmp):
     counts = ens.hist_omega(edges)
     d = ens.diag()
     allp = ens.gather_packets()
+    st = ens.ode23([0, 20 * w.dt], np.inf)            # global error norm: MAX all-reduce per attempted step
+    allq = ens.gather_packets()
     if rank == 0:
-        np.savez(tmp, counts=counts, diag=d, x=allp[0], k=allp[2])
+        np.savez(tmp, counts=counts, diag=d, x=allp[0], k=allp[2], nsteps=st["nsteps"], nfailed=st["nfailed"], x23=allq[0], k23=allq[2])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -118,3 +141,8 @@ def test_gloo_two_ranks_match_single_rank(tmp_path):
     assert np.array_equal(got["x"], x1) and np.array_equal(got["k"], k1)   # per-packet states identical
     d1 = ens.diag()
     assert np.allclose(got["diag"], d1, rtol=1e-13) and got["diag"][6] == 1001
+    # ode23 over two ranks == ode23 over one: same accepted/rejected steps, bit-identical packets
+    st = ens.ode23([0, 20 * w.dt], np.inf)
+    assert (int(got["nsteps"]), int(got["nfailed"])) == (st["nsteps"], st["nfailed"]) and st["nsteps"] >= 10
+    x2, _, k2, _ = ens.gather_packets()
+    assert np.array_equal(got["x23"], x2) and np.array_equal(got["k23"], k2)

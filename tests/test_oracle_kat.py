@@ -206,3 +206,28 @@ def test_step_packet_matches_batch_restatement(small_flow):
         bat = O.rk4_step_batch(arr(P["x"]), arr(P["y"]), arr(P["k"]), arr(P["l"]), arr(P["a"]), 0.02, 1.0, 3.0, fields, dx, xka)
         for i, name in enumerate(["x", "y", "k", "l"] + (["a"] if xka else [])):
             assert abs(lit[name] - bat[i][0]) < 1e-15
+
+
+def test_ode23_restatement_known_answers():
+    # Bogacki-Shampine 3(2) as MATLAB's ode23 drives it (parity unpinned: MATLAB is absent).  Pins what can be
+    # pinned: third-order convergence of the propagated solution, the MaxStep = 0.1*(tf-t0) default (>= 10
+    # steps), FSAL function-evaluation count 1 + 3*(accepted + rejected), exactness on cubics' derivatives.
+    y, st = O.ode23(lambda t, y: -y, [0, 2.0], np.array([1.0]))
+    assert st["nsteps"] >= 10 and st["nfevals"] == 1 + 3 * (st["nsteps"] + st["nfailed"])
+    assert abs(y[0] - np.exp(-2.0)) < 1e-3
+    errs = []
+    for rtol in (1e-4, 1e-6, 1e-8):
+        y, st = O.ode23(lambda t, y: np.array([y[1], -y[0]]), [0, 3.0], np.array([1.0, 0.0]), rtol=rtol, atol=rtol * 1e-3)
+        errs.append(np.abs(y - np.array([np.cos(3.0), -np.sin(3.0)])).max())
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-6
+    # y' = 3 t^2 is integrated exactly by the third-order formula
+    y, st = O.ode23(lambda t, y: np.array([3 * t * t]), [0, 1.0], np.array([0.0]))
+    assert abs(y[0] - 1.0) < 1e-13
+    # zero-flow packets: x advances with the constant group velocity, k is untouched
+    n = 5; f, Cg = 3.0, 1.0
+    zero = lambda xx, yy, al: np.zeros((6, xx.size))
+    ode = O.generate_raytracing_ode(None, None, n, f, Cg, 1.0, 0.1, eval6=zero)
+    y0 = np.concatenate([np.zeros(n), np.zeros(n), 3 * np.ones(n), 4 * np.ones(n)])
+    y, st = O.ode23(ode, [0, 1.0], y0)
+    w = np.sqrt(f * f + Cg * Cg * 25.0)
+    assert np.allclose(y[:n], Cg * 3 / w, atol=1e-14) and np.allclose(y[2 * n:3 * n], 3.0)
