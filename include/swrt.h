@@ -134,6 +134,12 @@ int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges,
  * round trip through host memory; the handle's stream is synchronised on return              */
 int swrt_hist_omega_dev(swrt_handle* h, int kind, double alpha, const double* edges, int nedges,
                         uint64_t** counts_dev);
+/* theoretical omega pdf of ideal_omega_distribution.m:3-11: omega_abs = omega0 + U(x_i).kvec_j over npts
+ * points (the caller's grid XX(:),YY(:)) x nangles wavevectors (kvx,kvy = k_0*[cos(t) sin(t)]), counted
+ * into histcounts-style bins; counts[nedges-1].                                                   */
+int swrt_ideal_omega_hist(swrt_handle* h, double alpha, int64_t npts, const double* x, const double* y,
+                          const double* kvx, const double* kvy, int nangles, double omega0,
+                          const double* edges, int nedges, uint64_t* counts);
 /* out[0]=sum omega, out[1]=sum Omega (omega+U.k), out[2]=max omega, out[3]=min omega,
  * out[4]=number of non-finite packets, out[5]=sum a, out[6]=n, out[7]=sum omega*a              */
 int swrt_diag(swrt_handle* h, double alpha, double out[8]);

@@ -133,6 +133,38 @@ __global__ void hist_kernel(long long n, const double* __restrict__ w, const dou
         if (sc[i]) atomicAdd(&counts[i], (unsigned long long)sc[i]);
 }
 
+// ideal_omega_distribution.m:3-11: omega_abs = omega_0 + U(:,1)*kx' + U(:,2)*ky' over (grid point, angle),
+// histogrammed with explicit edges.  Un-fused arithmetic in the reference's order, so the counts are
+// bit-identical to a host histogram of the same U.
+__global__ void ideal_hist_kernel(long long npts, const double* __restrict__ u, const double* __restrict__ v,
+                                  const double* __restrict__ kvx, const double* __restrict__ kvy, int nang, double omega0,
+                                  const double* __restrict__ edges, int nedges, unsigned long long* __restrict__ counts) {
+    extern __shared__ unsigned char hs[];
+    double* se = reinterpret_cast<double*>(hs);
+    double* sk = se + nedges;                       // kvx then kvy
+    unsigned int* sc = reinterpret_cast<unsigned int*>(sk + 2 * nang);
+    const int nb = nedges - 1;
+    for (int i = threadIdx.x; i < nedges; i += blockDim.x) se[i] = edges[i];
+    for (int i = threadIdx.x; i < nang; i += blockDim.x) { sk[i] = kvx[i]; sk[nang + i] = kvy[i]; }
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) sc[i] = 0;
+    __syncthreads();
+    const double lo = se[0], hi = se[nb];
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += stride) {
+        const double uu = u[i], vv = v[i];
+        for (int j = 0; j < nang; j++) {
+            const double w = __dadd_rn(omega0, __dadd_rn(__dmul_rn(uu, sk[j]), __dmul_rn(vv, sk[nang + j])));
+            if (!(w >= lo && w <= hi)) continue;
+            int a = 0, b = nb;
+            while (b - a > 1) { int m = (a + b) >> 1; if (se[m] <= w) a = m; else b = m; }
+            atomicAdd(&sc[a], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (sc[i]) atomicAdd(&counts[i], (unsigned long long)sc[i]);
+}
+
 // partial sums per block, then one block reduces the partials in a fixed order (deterministic)
 constexpr int kDiagBlocks = 296;
 __global__ void __launch_bounds__(256) diag_partial_kernel(long long n, const double* __restrict__ x,
@@ -266,6 +298,14 @@ void launch_hist(long long n, const double* w, const double* edges_dev, int nedg
     unsigned nb = nblk(n, 256 * 8);
     if (nb > 148 * 8) nb = 148 * 8;
     hist_kernel<<<nb, 256, smem, st>>>(n, w, edges_dev, nedges, counts_dev);
+}
+void launch_ideal_hist(long long npts, const double* u, const double* v, const double* kvx, const double* kvy, int nang,
+                       double omega0, const double* edges_dev, int nedges, unsigned long long* counts_dev, cudaStream_t st) {
+    if (npts <= 0) return;
+    size_t smem = (size_t)nedges * 8 + (size_t)2 * nang * 8 + (size_t)(nedges - 1) * 4;
+    unsigned nb = nblk(npts, 256);
+    if (nb > 148 * 8) nb = 148 * 8;
+    ideal_hist_kernel<<<nb, 256, smem, st>>>(npts, u, v, kvx, kvy, nang, omega0, edges_dev, nedges, counts_dev);
 }
 void launch_diag(long long n, const double* x, const double* y, const double* k, const double* l, const double* a,
                  const double* omega, const double* Omega_abs, double* out8_dev, cudaStream_t st) {

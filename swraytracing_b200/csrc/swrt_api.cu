@@ -885,6 +885,39 @@ int swrt_hist_omega_dev(swrt_handle* h, int kind, double alpha, const double* ed
     return SWRT_OK;
 }
 
+int swrt_ideal_omega_hist(swrt_handle* h, double alpha, int64_t npts, const double* x, const double* y, const double* kvx,
+                          const double* kvy, int nangles, double omega0, const double* edges, int nedges, uint64_t* counts) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, npts >= 0 && x && y && kvx && kvy && edges && counts, SWRT_ERR_ARG, "null argument");
+    REQUIRE(h, nangles >= 1 && nangles <= 1024 && nedges >= 2 && nedges <= 4096, SWRT_ERR_ARG, "bad nangles / nedges");
+    REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
+    for (int i = 1; i < nedges; i++) REQUIRE(h, edges[i] >= edges[i - 1], SWRT_ERR_ARG, "edges must be non-decreasing");
+    int rc = ensure_scratch(h, npts > h->n ? npts : h->n);
+    if (rc) return rc;
+    if ((rc = h2d(h, h->xs, x, npts)) || (rc = h2d(h, h->ys, y, npts))) return rc;
+    // the same six-plane evaluation swrt_eval_at performs, so U is bit-identical to what the caller can read back
+    rc = eval_dev(h, SUB_SIX, alpha, npts, h->xs, h->ys, h->e);
+    if (rc) return rc;
+    double *dk = nullptr, *de = nullptr; unsigned long long* dc = nullptr;
+    if (cudaMalloc(&dk, (size_t)2 * nangles * 8) || cudaMalloc(&de, (size_t)nedges * 8) || cudaMalloc(&dc, (size_t)(nedges - 1) * 8)) {
+        cudaFree(dk); cudaFree(de); cudaFree(dc);
+        return fail(h, SWRT_ERR_ALLOC, "cudaMalloc failed");
+    }
+    cudaMemcpyAsync(dk, kvx, (size_t)nangles * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(dk + nangles, kvy, (size_t)nangles * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(de, edges, (size_t)nedges * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemsetAsync(dc, 0, (size_t)(nedges - 1) * 8, h->stream);
+    launch_ideal_hist(npts, h->e[0], h->e[1], dk, dk + nangles, nangles, omega0, de, nedges, dc, h->stream);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(counts, dc, (size_t)(nedges - 1) * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(dk); cudaFree(de); cudaFree(dc);
+    if (e != cudaSuccess) return fail(h, SWRT_ERR_CUDA, "swrt_ideal_omega_hist: %s", cudaGetErrorString(e));
+    return SWRT_OK;
+}
+
 int swrt_diag(swrt_handle* h, double alpha, double out[8]) {
     if (!h || !out) return SWRT_ERR_ARG;
     CU(h, cudaSetDevice(h->p.device));

@@ -117,6 +117,8 @@ void launch_omega(long long n, const double* k, const double* l, const double* u
                   double f, double gH, double* omega, double* Omega_abs, cudaStream_t st);
 void launch_hist(long long n, const double* w, const double* edges_dev, int nedges,
                  unsigned long long* counts_dev, cudaStream_t st);
+void launch_ideal_hist(long long npts, const double* u, const double* v, const double* kvx, const double* kvy, int nang,
+                       double omega0, const double* edges_dev, int nedges, unsigned long long* counts_dev, cudaStream_t st);
 void launch_diag(long long n, const double* x, const double* y, const double* k, const double* l, const double* a,
                  const double* omega, const double* Omega_abs, double* out8_dev, cudaStream_t st);
 void launch_fill(double* p, double v, long long n, cudaStream_t st);

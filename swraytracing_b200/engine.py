@@ -57,6 +57,8 @@ SIGNATURES = {
     "swrt_bs23_attempt": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, _dp]),
     "swrt_bs23_accept": (C.c_int, [C.c_void_p]),
     "swrt_hist_omega_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_void_p)]),
+    "swrt_ideal_omega_hist": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, C.c_double, _dp, C.c_int,
+                                        C.POINTER(C.c_uint64)]),
     "swrt_diag": (C.c_int, [C.c_void_p, C.c_double, _dp]),
     "swrt_omega": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp]),
     "swrt_g2k": (C.c_int, [C.c_int, _dp, C.c_int, _dp, _dp]),
@@ -244,6 +246,13 @@ class Engine:
         ptr = C.c_void_p()
         self._check(self.lib.swrt_hist_omega_dev(self._h, kind, float(alpha), _ptr(edges), edges.size, C.byref(ptr)))
         return ptr.value, edges.size - 1
+
+    def ideal_omega_hist(self, x, y, kvx, kvy, omega0, edges, alpha=0.0):
+        x, y, kvx, kvy, edges = (_f64(a).ravel() for a in (x, y, kvx, kvy, edges))
+        counts = np.zeros(edges.size - 1, dtype=np.uint64)
+        self._check(self.lib.swrt_ideal_omega_hist(self._h, float(alpha), x.size, _ptr(x), _ptr(y), _ptr(kvx), _ptr(kvy), kvx.size,
+                                                   float(omega0), _ptr(edges), edges.size, counts.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return counts
 
     def diag(self, alpha=0.0):
         out = np.empty(8)

@@ -302,3 +302,20 @@ def ode23(target, tspan, tmax, rtol=1e-3, atol=1e-6, reduce_max=None):
             absh = absh / temp if temp > 0.2 else 5.0 * absh
         t = tnew
     return {"nsteps": nsteps, "nfailed": nfailed, "nfevals": nfevals, "t": t}
+
+
+def ideal_omega_distribution(scheme, f, Cg, k_0, edges, nangles=100):
+    """ideal_omega_distribution.m:3-11: theoretical pdf of the absolute frequency omega_0 + U.k over the
+    grid ``X = linspace(0, L, nx); [XX,YY] = meshgrid(X)`` (symplectic_full_fourier.m:14-15) and
+    ``t = linspace(0, 2*pi)`` wavevector directions.  MATLAB's ``histogram`` picks its own bins; here the
+    caller passes ``edges`` (histcounts rule).  Returns (counts, pdf) with pdf = counts/(N*binwidth)."""
+    X = np.linspace(0.0, scheme.L, scheme.nx)
+    XX, YY = np.meshgrid(X, X)
+    t = np.linspace(0.0, 2 * np.pi, nangles)
+    kvx, kvy = k_0 * np.cos(t), k_0 * np.sin(t)
+    omega_0 = math.sqrt(f ** 2 + Cg ** 2 * k_0 ** 2)
+    edges = np.asarray(edges, dtype=np.float64)
+    counts = scheme.eng.ideal_omega_hist(XX.ravel(order="F"), YY.ravel(order="F"), kvx, kvy, omega_0, edges)
+    width = np.diff(edges)
+    total = XX.size * nangles
+    return counts, counts / (total * np.where(width > 0, width, 1.0))

@@ -623,3 +623,25 @@ def test_ode23_error_norm_couples_all_packets():
         e.set_packets(x, y, k, l)
         stiff = R.ode23(e, [0, 0.5], np.inf)
         assert stiff["nsteps"] > base["nsteps"]
+
+
+def test_ideal_omega_distribution_theoretical_pdf():
+    # "next" row f4 (ideal_omega_distribution.m:3-11): counts over (grid point, angle), bit-exact against a host
+    # histogram of the same U; pdf integrates to one; mean sits at omega_0 (the flow has zero mean)
+    nx = 64; L = 2 * np.pi; f, Cg, k0 = 3.0, 1.0, 3.0
+    psik, planes = make_flow(nx)
+    psi = O.k2g(psik)
+    for mode in (S.MODE_SPECTRAL, S.MODE_LAGRANGE6):
+        sch = R.SpectralScheme(L, nx, psi, mode=mode)
+        X = np.linspace(0.0, L, nx); XX, YY = np.meshgrid(X, X)
+        U = sch.U(np.stack([XX.ravel(order="F"), YY.ravel(order="F")], axis=1))
+        t = np.linspace(0, 2 * np.pi, 100)
+        om0 = np.sqrt(f * f + Cg * Cg * k0 * k0)
+        om_abs = om0 + (np.outer(U[:, 0], k0 * np.cos(t)) + np.outer(U[:, 1], k0 * np.sin(t)))
+        edges = O.matlab_linspace(om_abs.min(), om_abs.max(), 61)
+        counts, pdf = R.ideal_omega_distribution(sch, f, Cg, k0, edges)
+        assert np.array_equal(counts, O.histcounts(om_abs, edges))
+        assert int(counts.sum()) == nx * nx * 100
+        assert abs((pdf * np.diff(edges)).sum() - 1.0) < 1e-12
+        centre = (edges[1:] + edges[:-1]) / 2
+        assert abs((pdf * np.diff(edges) * centre).sum() - om0) < 0.05
