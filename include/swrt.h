@@ -151,6 +151,19 @@ int swrt_omega(swrt_handle* h, double alpha, double* omega, double* Omega_abs);
 int swrt_g2k(int device, const double* fg, int nx, double* fk_re, double* fk_im);
 int swrt_k2g(int device, const double* fk_re, const double* fk_im, int nx, double* fg);
 
+/* ---- on-device one-layer QG frame producer (setup for time-evolving runs; not the hot path) --
+ * qgsw_raytrace.m:111-137 (AB3 loop), :222-230 (filter), :216-220 (forcing), :270-286 (update()).
+ * swrt_set_flow_from_qg fills a flow slot with psi = -q/(K_d2+K2) (grid_U.m:2) without leaving
+ * the device.                                                                                   */
+typedef struct swrt_qg swrt_qg;
+int swrt_qg_create(int device, int nx, double L, double K_d2, double beta, double r_drag,
+                   double force_strength, double f, double Cg, double dt,
+                   const double* qk_re, const double* qk_im, swrt_qg** out);
+int swrt_qg_step(swrt_qg* q, int nsteps);
+int swrt_qg_get(swrt_qg* q, double* qk_re, double* qk_im);
+int swrt_qg_destroy(swrt_qg* q);
+int swrt_set_flow_from_qg(swrt_handle* h, int slot, swrt_qg* q, double u_mean);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* number of kernel launches issued by this handle since creation / since the last reset        */
 int64_t swrt_launch_count(swrt_handle* h, int reset);

@@ -757,3 +757,58 @@ def generate_raytracing_ode(bf1, bf2, Npackets, f, Cg, tmax, h, eval6=None):
         return np.concatenate(d)
 
     return odefun
+
+
+# --------------------------------------------------------------------------------------------
+# One-layer QG flow solver of the drivers (producer of the background-flow frames)
+# --------------------------------------------------------------------------------------------
+
+def qg_filter(kx_, ky_, dx):
+    """qgsw_raytrace.m:222-230: exponential cutoff filter Ef."""
+    Ef = np.ones_like(kx_)
+    kstar = np.sqrt((kx_ * dx) ** 2 + (ky_ * dx) ** 2)
+    kc = 0.75 * np.pi
+    const = np.log(1e-15) / (0.25 * np.pi) ** 4
+    res = np.exp(const * (kstar - kc) ** 4)
+    Ef[kstar >= kc] = res[kstar >= kc]
+    return Ef
+
+
+def qg_inertial_ring(force_strength, K2, f, Cg):
+    """qgsw_raytrace.m:216-220"""
+    om = np.sqrt(f ** 2 + Cg ** 2 * K2)
+    forces = np.zeros_like(K2)
+    forces[(0.9 * f < om) & (om < 1.1 * f)] = force_strength
+    return forces
+
+
+def qg_update(qk, K2, K_d2, beta, r_drag, surface_forces, kx_, ky_):
+    """qgsw_raytrace.m:270-286 ``update`` (including ``r_drag * K2`` exactly as written on :285)."""
+    psik = -qk / (K_d2 + K2)
+    psikx = 1j * kx_ * psik; psiky = 1j * ky_ * psik
+    qkx = 1j * kx_ * qk; qky = 1j * ky_ * qk
+    J = k2g(psikx) * k2g(qky) - k2g(psiky) * k2g(qkx)
+    return g2k(J) - beta * psikx + r_drag * K2 + surface_forces
+
+
+def qg_run(qk, nsteps, dt, nx, L, K_d2, f, Cg, beta=0.0, r_drag=0.1, force_strength=0.1):
+    """qgsw_raytrace.m:111-137: Euler / AB2 start-up then AB3, filter after every step."""
+    kx_, ky_ = wavenumbers(nx)
+    kap = 2 * np.pi / L
+    kx_, ky_ = kap * kx_, kap * ky_
+    K2 = kx_ ** 2 + ky_ ** 2
+    Ef = qg_filter(kx_, ky_, L / nx)
+    forces = qg_inertial_ring(force_strength, K2, f, Cg)
+    Qm = [np.zeros_like(qk), np.zeros_like(qk)]
+    qk = np.array(qk, dtype=np.complex128)
+    for step in range(1, nsteps + 1):
+        Qn = qg_update(qk, K2, K_d2, beta, r_drag, forces, kx_, ky_)
+        if step == 1:
+            dq = dt * Qn
+        elif step == 2:
+            dq = dt / 2 * (3 * Qn - Qm[0])
+        else:
+            dq = dt / 12 * (23 * Qn - 16 * Qm[0] + 5 * Qm[1])
+        Qm[1] = Qm[0]; Qm[0] = Qn
+        qk = Ef * (qk + dq)
+    return qk

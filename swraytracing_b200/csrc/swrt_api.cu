@@ -446,6 +446,32 @@ static int finish_spectral_slot(swrt_handle* h, int slot, int npl) {
     return SWRT_OK;
 }
 
+// psi-hat already on the device (double2, g2k layout) -> six planes + moment planes of a slot
+static int set_flow_spectral_dev(swrt_handle* h, int slot, const double2* psi, double u_mean) {
+    const int nkx = h->p.nx - 1, nky = h->p.nx / 2;
+    const size_t n = (size_t)nkx * nky;
+    int rc = SWRT_OK;
+    for (int c = 0; c < 6 && rc == SWRT_OK; c++)
+        if (!h->planes[slot][c] && cudaMalloc(&h->planes[slot][c], n * sizeof(double2)) != cudaSuccess)
+            rc = fail(h, SWRT_ERR_ALLOC, "cudaMalloc(plane) failed");
+    if (rc) return rc;
+    dfree(h->planes[slot][6]);
+    // wavenumbers kappa*kx: integers when L = 2*pi (SpectralScheme.m:12-25), 2*pi/L-scaled
+    // otherwise (qg2layersw_raytrace.m:19-22)
+    const double kappa = 2.0 * M_PI / h->p.L;
+    launch_psi_to_planes(psi, h->planes[slot], nkx, nky, kappa, u_mean, h->stream);
+    h->launches++;
+    for (int c = 7; c < 10 && rc == SWRT_OK; c++)
+        if (!h->planes[slot][c] && cudaMalloc(&h->planes[slot][c], n * sizeof(double2)) != cudaSuccess)
+            rc = fail(h, SWRT_ERR_ALLOC, "cudaMalloc(moment plane) failed");
+    if (rc) return rc;
+    launch_psi_moments(psi, h->planes[slot][7], h->planes[slot][8], h->planes[slot][9], nkx, nky, h->stream);
+    h->launches++;
+    rc = finish_spectral_slot(h, slot, 6);
+    if (rc == SWRT_OK) { h->psi_ok[slot] = true; h->u_mean[slot] = u_mean; }
+    return rc;
+}
+
 int swrt_set_flow_spectral(swrt_handle* h, int slot, const double* psik_re, const double* psik_im, int nkx, int nky,
                            double u_mean) {
     if (!h) return SWRT_ERR_ARG;
@@ -459,28 +485,7 @@ int swrt_set_flow_spectral(swrt_handle* h, int slot, const double* psik_re, cons
     double2* psi = nullptr;
     CU(h, cudaMalloc(&tr, n * 8)); CU(h, cudaMalloc(&ti, n * 8));
     int rc = upload_plane(h, psik_re, psik_im, n, &psi, tr, ti);
-    if (rc == SWRT_OK) {
-        for (int c = 0; c < 6 && rc == SWRT_OK; c++)
-            if (!h->planes[slot][c] && cudaMalloc(&h->planes[slot][c], n * sizeof(double2)) != cudaSuccess)
-                rc = fail(h, SWRT_ERR_ALLOC, "cudaMalloc(plane) failed");
-    }
-    if (rc == SWRT_OK) {
-        dfree(h->planes[slot][6]);
-        // wavenumbers kappa*kx: integers when L = 2*pi (SpectralScheme.m:12-25), 2*pi/L-scaled
-        // otherwise (qg2layersw_raytrace.m:19-22)
-        const double kappa = 2.0 * M_PI / h->p.L;
-        launch_psi_to_planes(psi, h->planes[slot], nkx, nky, kappa, u_mean, h->stream);
-        h->launches++;
-        for (int c = 7; c < 10 && rc == SWRT_OK; c++)
-            if (!h->planes[slot][c] && cudaMalloc(&h->planes[slot][c], n * sizeof(double2)) != cudaSuccess)
-                rc = fail(h, SWRT_ERR_ALLOC, "cudaMalloc(moment plane) failed");
-        if (rc == SWRT_OK) {
-            launch_psi_moments(psi, h->planes[slot][7], h->planes[slot][8], h->planes[slot][9], nkx, nky, h->stream);
-            h->launches++;
-            rc = finish_spectral_slot(h, slot, 6);
-            if (rc == SWRT_OK) { h->psi_ok[slot] = true; h->u_mean[slot] = u_mean; }
-        }
-    }
+    if (rc == SWRT_OK) rc = set_flow_spectral_dev(h, slot, psi, u_mean);
     cudaStreamSynchronize(h->stream);
     cudaFree(tr); cudaFree(ti); cudaFree(psi);
     return rc;
@@ -1053,6 +1058,173 @@ int swrt_k2g(int device, const double* fk_re, const double* fk_im, int nx, doubl
     if (rc) return fail(nullptr, rc, "swrt_k2g: %s", err.c_str());
     return SWRT_OK;
 }
+
+}  // extern "C"
+
+// ================================================================================================
+// On-device one-layer QG frame producer ("next" row f3): qgsw_raytrace.m:111-137 (AB3 time loop),
+// :222-230 (exponential cutoff filter), :216-220 (inertial-ring forcing), :270-286 (update()).
+// Setup for the hot path, not the hot path: it exists so that time-evolving runs never leave the GPU.
+// ================================================================================================
+namespace {
+__global__ void qg_spec_kernel(const double2* __restrict__ qk, int nkx, int nky, double kappa, double K_d2,
+                               double2* psikx, double2* psiky, double2* qkx, double2* qky) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nkx * nky) return;
+    const int kmax = (nkx - 1) / 2;
+    const double kx = kappa * (double)(idx % nkx - kmax), ky = kappa * (double)(idx / nkx);
+    const double2 q = qk[idx];
+    const double d = K_d2 + (kx * kx + ky * ky);
+    const double2 psi = make_double2(-q.x / d, -q.y / d);                 // psik = -qk./(K_d2 + K2)
+    psikx[idx] = make_double2(-kx * psi.y, kx * psi.x);                   // 1i*kx_.*psik
+    psiky[idx] = make_double2(-ky * psi.y, ky * psi.x);
+    qkx[idx] = make_double2(-kx * q.y, kx * q.x);
+    qky[idx] = make_double2(-ky * q.y, ky * q.x);
+}
+__global__ void qg_jacobian_kernel(const double* psix, const double* psiy, const double* qx, const double* qy, double* J, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) J[i] = psix[i] * qy[i] - psiy[i] * qx[i];                  // J = psix.*qy - psiy.*qx
+}
+// Qn = g2k(J) - beta*psikx + r_drag*K2 + surface_forces  (as written in update(), qgsw_raytrace.m:285)
+__global__ void qg_rhs_kernel(const double2* __restrict__ Jk, const double2* __restrict__ psikx, int nkx, int nky, double kappa,
+                              double beta, double r_drag, double force, double f, double Cg, double2* Qn) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nkx * nky) return;
+    const int kmax = (nkx - 1) / 2;
+    const double kx = kappa * (double)(idx % nkx - kmax), ky = kappa * (double)(idx / nkx);
+    const double K2 = kx * kx + ky * ky;
+    const double om = sqrt(f * f + Cg * Cg * K2);
+    const double frc = (0.9 * f < om && om < 1.1 * f) ? force : 0.0;      // inertial_ring, :216-220
+    Qn[idx] = make_double2(Jk[idx].x - beta * psikx[idx].x + r_drag * K2 + frc, Jk[idx].y - beta * psikx[idx].y);
+}
+// AB1/AB2/AB3 increment (qgsw_raytrace.m:123-132), history rotation (:134-135), filter (:137)
+__global__ void qg_ab_kernel(double2* qk, const double2* Qn, double2* Qm1, double2* Qm2, int order, double dt, int nkx, int nky,
+                             double kappa, double dx) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nkx * nky) return;
+    const int kmax = (nkx - 1) / 2;
+    const double kx = kappa * (double)(idx % nkx - kmax), ky = kappa * (double)(idx / nkx);
+    const double2 a = Qn[idx], b = Qm1[idx], c = Qm2[idx];
+    double2 dq;
+    if (order == 1) dq = make_double2(dt * a.x, dt * a.y);
+    else if (order == 2) dq = make_double2(dt / 2 * (3 * a.x - b.x), dt / 2 * (3 * a.y - b.y));
+    else dq = make_double2(dt / 12 * (23 * a.x - 16 * b.x + 5 * c.x), dt / 12 * (23 * a.y - 16 * b.y + 5 * c.y));
+    Qm2[idx] = b; Qm1[idx] = a;
+    // Ef: exponential cutoff above kstar = 0.75*pi (:222-230)
+    const double kstar = sqrt((kx * dx) * (kx * dx) + (ky * dx) * (ky * dx));
+    const double kc = 0.75 * M_PI;
+    double Ef = 1.0;
+    if (kstar >= kc) { const double cst = log(1e-15) / pow(0.25 * M_PI, 4.0); Ef = exp(cst * pow(kstar - kc, 4.0)); }
+    qk[idx] = make_double2(Ef * (qk[idx].x + dq.x), Ef * (qk[idx].y + dq.y));
+}
+__global__ void qg_psi_kernel(const double2* __restrict__ qk, int nkx, int nky, double kappa, double K_d2, double2* psi) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nkx * nky) return;
+    const int kmax = (nkx - 1) / 2;
+    const double kx = kappa * (double)(idx % nkx - kmax), ky = kappa * (double)(idx / nkx);
+    const double d = K_d2 + (kx * kx + ky * ky);
+    psi[idx] = make_double2(-qk[idx].x / d, -qk[idx].y / d);
+}
+}  // namespace
+
+struct swrt_qg {
+    int device = 0, nx = 0;
+    double L = 0, K_d2 = 0, beta = 0, r_drag = 0, force = 0, f = 0, Cg = 0, dt = 0;
+    long long step = 0;
+    cudaStream_t stream = nullptr;
+    FftWork fft;
+    double2 *qk = nullptr, *Qn = nullptr, *Qm1 = nullptr, *Qm2 = nullptr, *s[4] = {}, *Jk = nullptr, *psi = nullptr;
+    double* g[5] = {};
+    std::string err;
+};
+
+extern "C" {
+
+int swrt_qg_create(int device, int nx, double L, double K_d2, double beta, double r_drag, double force_strength, double f,
+                   double Cg, double dt, const double* qk_re, const double* qk_im, swrt_qg** out) {
+    if (!out || !qk_re || !qk_im || nx < 8 || (nx & 1) || !(L > 0) || !(dt > 0)) return fail(nullptr, SWRT_ERR_ARG, "swrt_qg_create: bad argument");
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_qg_create: no CUDA device; libswrt has no CPU path"); }
+    swrt_qg* q = new (std::nothrow) swrt_qg();
+    if (!q) return fail(nullptr, SWRT_ERR_ALLOC, "out of host memory");
+    q->device = device; q->nx = nx; q->L = L; q->K_d2 = K_d2; q->beta = beta; q->r_drag = r_drag; q->force = force_strength;
+    q->f = f; q->Cg = Cg; q->dt = dt;
+    const size_t nh = (size_t)(nx - 1) * (nx / 2), ng = (size_t)nx * nx;
+    bool ok = cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) == cudaSuccess && q->fft.init(nx, q->stream, q->err) == SWRT_OK;
+    double2** cplx[] = {&q->qk, &q->Qn, &q->Qm1, &q->Qm2, &q->s[0], &q->s[1], &q->s[2], &q->s[3], &q->Jk, &q->psi};
+    for (auto p : cplx) ok = ok && cudaMalloc(p, nh * sizeof(double2)) == cudaSuccess;
+    for (auto& p : q->g) ok = ok && cudaMalloc(&p, ng * sizeof(double)) == cudaSuccess;
+    if (!ok) { swrt_qg_destroy(q); return fail(nullptr, SWRT_ERR_ALLOC, "swrt_qg_create: allocation failed"); }
+    std::vector<double2> hq(nh);
+    for (size_t i = 0; i < nh; i++) hq[i] = make_double2(qk_re[i], qk_im[i]);
+    cudaMemcpy(q->qk, hq.data(), nh * sizeof(double2), cudaMemcpyHostToDevice);
+    cudaMemset(q->Qm1, 0, nh * sizeof(double2)); cudaMemset(q->Qm2, 0, nh * sizeof(double2));
+    *out = q;
+    return SWRT_OK;
+}
+
+int swrt_qg_destroy(swrt_qg* q) {
+    if (!q) return SWRT_OK;
+    cudaSetDevice(q->device);
+    if (q->stream) cudaStreamSynchronize(q->stream);
+    double2* cplx[] = {q->qk, q->Qn, q->Qm1, q->Qm2, q->s[0], q->s[1], q->s[2], q->s[3], q->Jk, q->psi};
+    for (auto p : cplx) if (p) cudaFree(p);
+    for (auto p : q->g) if (p) cudaFree(p);
+    if (q->stream) cudaStreamDestroy(q->stream);
+    delete q;
+    return SWRT_OK;
+}
+
+int swrt_qg_step(swrt_qg* q, int nsteps) {
+    if (!q || nsteps < 0) return SWRT_ERR_ARG;
+    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
+    const int nkx = q->nx - 1, nky = q->nx / 2, nh = nkx * nky;
+    const size_t ng = (size_t)q->nx * q->nx;
+    const double kappa = 2.0 * M_PI / q->L, dx = q->L / q->nx;
+    const int bs = 256, gb = (nh + bs - 1) / bs;
+    for (int it = 0; it < nsteps; it++) {
+        qg_spec_kernel<<<gb, bs, 0, q->stream>>>(q->qk, nkx, nky, kappa, q->K_d2, q->s[0], q->s[1], q->s[2], q->s[3]);
+        for (int c = 0; c < 4; c++)
+            if (k2g_dev(q->fft, q->s[c], q->g[c], q->stream, q->err)) return SWRT_ERR_CUDA;
+        qg_jacobian_kernel<<<(unsigned)((ng + bs - 1) / bs), bs, 0, q->stream>>>(q->g[0], q->g[1], q->g[2], q->g[3], q->g[4], ng);
+        if (g2k_dev(q->fft, q->g[4], q->Jk, q->stream, q->err)) return SWRT_ERR_CUDA;
+        qg_rhs_kernel<<<gb, bs, 0, q->stream>>>(q->Jk, q->s[0], nkx, nky, kappa, q->beta, q->r_drag, q->force, q->f, q->Cg, q->Qn);
+        const int order = q->step == 0 ? 1 : (q->step == 1 ? 2 : 3);
+        qg_ab_kernel<<<gb, bs, 0, q->stream>>>(q->qk, q->Qn, q->Qm1, q->Qm2, order, q->dt, nkx, nky, kappa, dx);
+        q->step++;
+    }
+    cudaError_t e = cudaStreamSynchronize(q->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { q->err = cudaGetErrorString(e); return SWRT_ERR_CUDA; }
+    return SWRT_OK;
+}
+
+int swrt_qg_get(swrt_qg* q, double* qk_re, double* qk_im) {
+    if (!q || !qk_re || !qk_im) return SWRT_ERR_ARG;
+    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
+    const size_t nh = (size_t)(q->nx - 1) * (q->nx / 2);
+    std::vector<double2> hq(nh);
+    if (cudaMemcpy(hq.data(), q->qk, nh * sizeof(double2), cudaMemcpyDeviceToHost) != cudaSuccess) return SWRT_ERR_CUDA;
+    for (size_t i = 0; i < nh; i++) { qk_re[i] = hq[i].x; qk_im[i] = hq[i].y; }
+    return SWRT_OK;
+}
+
+// flow slot <- psi = -q/(K_d2 + K2) of the QG state, entirely on the device (grid_U.m:2 without the host)
+int swrt_set_flow_from_qg(swrt_handle* h, int slot, swrt_qg* q, double u_mean) {
+    if (!h || !q) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
+    REQUIRE(h, q->nx == h->p.nx && q->device == h->p.device && q->L == h->p.L, SWRT_ERR_ARG, "QG state and handle differ in nx / L / device");
+    const int nkx = q->nx - 1, nky = q->nx / 2, nh = nkx * nky;
+    CU(h, cudaStreamSynchronize(q->stream));
+    qg_psi_kernel<<<(nh + 255) / 256, 256, 0, h->stream>>>(q->qk, nkx, nky, 2.0 * M_PI / q->L, q->K_d2, q->psi);
+    h->launches++;
+    return set_flow_spectral_dev(h, slot, q->psi, u_mean);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- instrumentation --------------------------------------------------------------------------
 int64_t swrt_launch_count(swrt_handle* h, int reset) {

@@ -63,6 +63,11 @@ SIGNATURES = {
     "swrt_omega": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp]),
     "swrt_g2k": (C.c_int, [C.c_int, _dp, C.c_int, _dp, _dp]),
     "swrt_k2g": (C.c_int, [C.c_int, _dp, _dp, C.c_int, _dp]),
+    "swrt_qg_create": (C.c_int, [C.c_int, C.c_int] + [C.c_double] * 8 + [_dp, _dp, C.POINTER(C.c_void_p)]),
+    "swrt_qg_step": (C.c_int, [C.c_void_p, C.c_int]),
+    "swrt_qg_get": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "swrt_qg_destroy": (C.c_int, [C.c_void_p]),
+    "swrt_set_flow_from_qg": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double]),
     "swrt_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "swrt_last_kernel_ms": (C.c_double, [C.c_void_p, C.POINTER(C.c_int)]),
     "swrt_work_per_eval": (C.c_double, [C.c_void_p, C.c_int]),
@@ -297,6 +302,49 @@ class Engine:
 
     def contracted_planes(self):
         return int(self.lib.swrt_contracted_planes(self._h))
+
+
+class QGFlow:
+    """On-device one-layer QG solver producing the background-flow frames (qgsw_raytrace.m:111-137,
+    :270-286): q-hat lives on the GPU; ``to_flow(engine, slot)`` fills a flow slot without a host copy."""
+
+    def __init__(self, nx, L, qk, K_d2, dt, f, Cg, beta=0.0, r_drag=0.1, force_strength=0.1, device=0):
+        self.lib = load_library()
+        self.nx, self.L = int(nx), float(L)
+        qk = np.asarray(qk, dtype=np.complex128)
+        re, im = _colmajor(qk.real), _colmajor(qk.imag)
+        self._q = C.c_void_p()
+        rc = self.lib.swrt_qg_create(int(device), self.nx, self.L, float(K_d2), float(beta), float(r_drag), float(force_strength),
+                                     float(f), float(Cg), float(dt), _ptr(re), _ptr(im), C.byref(self._q))
+        if rc != 0:
+            raise SwrtError(rc, (self.lib.swrt_last_error(None) or b"").decode())
+
+    def step(self, nsteps=1):
+        rc = self.lib.swrt_qg_step(self._q, int(nsteps))
+        if rc != 0:
+            raise SwrtError(rc, "swrt_qg_step failed")
+
+    def get(self):
+        nkx, nky = self.nx - 1, self.nx // 2
+        re = np.empty(nkx * nky); im = np.empty(nkx * nky)
+        rc = self.lib.swrt_qg_get(self._q, _ptr(re), _ptr(im))
+        if rc != 0:
+            raise SwrtError(rc, "swrt_qg_get failed")
+        return (re + 1j * im).reshape((nkx, nky), order="F")
+
+    def to_flow(self, engine, slot=0, u_mean=0.0):
+        engine._check(self.lib.swrt_set_flow_from_qg(engine._h, int(slot), self._q, float(u_mean)))
+
+    def close(self):
+        if getattr(self, "_q", None) and self._q.value:
+            self.lib.swrt_qg_destroy(self._q)
+            self._q = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # -- handle-free helpers ---------------------------------------------------------------------------

@@ -645,3 +645,76 @@ def test_ideal_omega_distribution_theoretical_pdf():
         assert abs((pdf * np.diff(edges)).sum() - 1.0) < 1e-12
         centre = (edges[1:] + edges[:-1]) / 2
         assert abs((pdf * np.diff(edges) * centre).sum() - om0) < 0.05
+
+
+def test_device_qg_frame_producer_and_time_evolving_run():
+    # "next" row f3: the one-layer QG solver of qgsw_raytrace.m:111-137,270-286 on the device, feeding the two
+    # flow slots without a host copy; packets advanced per flow step with frame blending (config C3's shape)
+    nx = 64; L = 2 * np.pi; f, Cg = 3.0, 1.0; K_d2 = f / Cg
+    xg = np.linspace(-L / 2, L / 2, nx)
+    X, Y = np.meshgrid(xg, xg)
+    q0 = O.initial_q(X, Y, 0.5, K_d2, O.matlab_rand_stream(146))
+    qk0 = O.g2k(q0)
+    kx_, ky_ = O.wavenumbers(nx); K2 = kx_ ** 2 + ky_ ** 2
+    flow = O.grid_U(qk0, K_d2, K2, kx_, ky_)
+    U0 = np.sqrt((flow["u"] ** 2 + flow["v"] ** 2).max())
+    dt = 0.05 * (L / nx) / U0                                  # qgsw_raytrace.m:29,70
+    # update() as written adds the constant source r_drag*K2 to every mode (qgsw_raytrace.m:285); with the
+    # driver's r_drag = 0.1 the restated solver overflows within ~12 steps on this grid, so the parity run uses
+    # r_drag = 0.01 (12 steps: Euler, AB2, then AB3; |q| grows 3x) -- the term itself is still exercised
+    rd = 0.01
+    qg = S.QGFlow(nx, L, qk0, K_d2, dt, f, Cg, r_drag=rd)
+    nsteps = 12
+    ref = O.qg_run(qk0, nsteps, dt, nx, L, K_d2, f, Cg, r_drag=rd)
+    qg.step(nsteps)
+    got = qg.get()
+    assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+    # flow slots straight from the device state == uploading psi-hat from the host
+    x, y, k, l = make_packets(300, L)
+    with S.Engine(nx, L, f, Cg ** 2) as e, S.Engine(nx, L, f, Cg ** 2) as e2:
+        qg.to_flow(e, 0)
+        e2.set_flow_spectral(-got / (K_d2 + K2))
+        assert np.abs(e.eval_at(x, y) - e2.eval_at(x, y)).max() < 1e-13
+        # one flow step of the production loop: frame 0 = prev_qk, frame 1 = qk (qgsw_raytrace.m:141-143)
+        qg.step(1)
+        qg.to_flow(e, 1)
+        e.set_packets(x, y, k, l)
+        st = R.ode23(e, [0, dt], dt)
+        p1 = O.velocity_planes_k(-got / (K_d2 + K2), kx_, ky_)
+        p2 = O.velocity_planes_k(-O.qg_run(qk0, nsteps + 1, dt, nx, L, K_d2, f, Cg, r_drag=rd) / (K_d2 + K2), kx_, ky_)
+        ev = lambda xx, yy, al: CO.spectral_eval(xx, yy, [(1 - al) * a + al * b for a, b in zip(p1, p2)], L / nx, nx)
+        yref, sref = O.ode23(O.generate_raytracing_ode(None, None, x.size, f, Cg, dt, L / nx, eval6=ev), [0, dt], np.concatenate([x, y, k, l]))
+        assert st["nsteps"] == sref["nsteps"] and np.abs(np.concatenate(e.get_packets()) - yref).max() < TOL_TRAJ
+    qg.close()
+
+
+def test_qgsw_raytrace_driver_on_device(tmp_path):
+    # the reference's production driver signature (qgsw_raytrace.m:1) end to end: QG frames, flow slots and the
+    # per-step ode23 packet solve on the GPU, packet frames in the reference's file format
+    from swraytracing_b200 import drivers, fieldio
+    nx, Np, nif, U_g, f, Cg = 32, 12, 2.0, 0.5, 3.0, 1.0
+    nst = 6
+    out = drivers.qgsw_raytrace(nx, Np, nif, 6000, 0, U_g, f, Cg, outdir=str(tmp_path), max_steps=nst, r_drag=0.01, log=lambda s: None)
+    # --- oracle-side restatement of the same loop
+    L = 2 * np.pi; K_d2 = f / Cg
+    xg = np.linspace(-L / 2, L / 2, nx); X, Y = np.meshgrid(xg, xg)
+    rs = O.matlab_rand_stream(146)
+    qk0 = O.g2k(O.initial_q(X, Y, U_g, K_d2, rs))
+    x, y, k, l = O.init_packets(Np, L, np.sqrt((nif ** 2 - 1) * f ** 2 / Cg ** 2), rs)
+    kx_, ky_ = O.wavenumbers(nx); K2 = kx_ ** 2 + ky_ ** 2
+    fl = O.grid_U(qk0, K_d2, K2, kx_, ky_)
+    U0 = np.sqrt((fl["u"] ** 2 + fl["v"] ** 2).max()); dt = 0.05 * (L / nx) / U0
+    assert abs(out["dt"] - dt) < 1e-15 and abs(out["U0"] - U0) < 1e-13
+    yv = np.concatenate([x, y, k, l])
+    for step in range(1, nst + 1):
+        p1 = O.velocity_planes_k(-O.qg_run(qk0, step - 1, dt, nx, L, K_d2, f, Cg, r_drag=0.01) / (K_d2 + K2), kx_, ky_)
+        p2 = O.velocity_planes_k(-O.qg_run(qk0, step, dt, nx, L, K_d2, f, Cg, r_drag=0.01) / (K_d2 + K2), kx_, ky_)
+        ev = lambda xx, yy, al: CO.spectral_eval(xx, yy, [(1 - al) * a + al * b for a, b in zip(p1, p2)], L / nx, nx)
+        yv, _ = O.ode23(O.generate_raytracing_ode(None, None, Np, f, Cg, dt, L / nx, eval6=ev), [0, dt], yv)
+    assert np.abs(np.concatenate(out["packets"]) - yv).max() < TOL_TRAJ
+    assert out["packet_steps"] == nst and out["ode23_steps"] >= 10 * nst
+    # files: initial frame + one frame when mod(step - packet_step_start + 1, 5) == 0, i.e. step 4 with
+    # packet_step_start = ceil(0/dt) = 0 (qgsw_raytrace.m:73,153); wrapped positions
+    t, xs, ks = fieldio.load_packet_frames(tmp_path, Np)
+    assert xs.shape == (Np, 2, 2) and abs(t[1] - 4 * dt) < 1e-12 and np.abs(xs).max() <= L / 2
+    assert np.array_equal(ks[:, 0, 0], k)
