@@ -99,6 +99,17 @@ int fail(swrt_handle* h, int code, const char* fmt, ...) {
 
 template <typename T> void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
+// scoped device temporary: freed on every exit path (the CU()/REQUIRE() macros return early)
+template <typename T>
+struct DevTmp {
+    T* p = nullptr;
+    DevTmp() = default;
+    DevTmp(const DevTmp&) = delete;
+    DevTmp& operator=(const DevTmp&) = delete;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
+};
+
 int pick_mtiles(const swrt_handle* h, int64_t n) {
     if (h->mtiles == 1 || h->mtiles == 2) return h->mtiles;
     (void)n;
@@ -338,10 +349,12 @@ int grid_from_planes(swrt_handle* h, int slot) {
     FftWork w;
     int rc = w.init(nx, h->stream, h->err);
     if (rc) return rc;
+    std::vector<DevTmp<double>> tmpbuf(npl);
     std::vector<double*> tmp(npl, nullptr);
     size_t n = (size_t)nx * nx;
     for (int c = 0; c < npl; c++) {
-        CU(h, cudaMalloc(&tmp[c], n * sizeof(double)));
+        CU(h, tmpbuf[c].alloc(n));
+        tmp[c] = tmpbuf[c].p;
         rc = k2g_dev(w, h->planes[slot][c], tmp[c], h->stream, h->err);
         if (rc) return rc;
         h->launches += 3;
@@ -350,8 +363,7 @@ int grid_from_planes(swrt_handle* h, int slot) {
     if (!h->grid[slot]) CU(h, cudaMalloc(&h->grid[slot], n * npl * sizeof(double)));
     launch_interleave_grid(tmp.data(), npl, nx, h->grid[slot], h->stream);
     h->launches++;
-    CU(h, cudaStreamSynchronize(h->stream));
-    for (auto p : tmp) cudaFree(p);
+    CU(h, cudaStreamSynchronize(h->stream));      // the temporaries are released on return
     return SWRT_OK;
 }
 
@@ -481,13 +493,12 @@ int swrt_set_flow_spectral(swrt_handle* h, int slot, const double* psik_re, cons
     REQUIRE(h, nkx == h->p.nx - 1 && nky == h->p.nx / 2, SWRT_ERR_ARG, "psi-hat must be %d x %d (got %d x %d)",
             h->p.nx - 1, h->p.nx / 2, nkx, nky);
     size_t n = (size_t)nkx * nky;
-    double *tr = nullptr, *ti = nullptr;
-    double2* psi = nullptr;
-    CU(h, cudaMalloc(&tr, n * 8)); CU(h, cudaMalloc(&ti, n * 8));
-    int rc = upload_plane(h, psik_re, psik_im, n, &psi, tr, ti);
-    if (rc == SWRT_OK) rc = set_flow_spectral_dev(h, slot, psi, u_mean);
+    DevTmp<double> tr, ti;
+    DevTmp<double2> psi;
+    CU(h, tr.alloc(n)); CU(h, ti.alloc(n)); CU(h, psi.alloc(n));
+    int rc = upload_plane(h, psik_re, psik_im, n, &psi.p, tr.p, ti.p);
+    if (rc == SWRT_OK) rc = set_flow_spectral_dev(h, slot, psi.p, u_mean);
     cudaStreamSynchronize(h->stream);
-    cudaFree(tr); cudaFree(ti); cudaFree(psi);
     return rc;
 }
 
@@ -500,17 +511,16 @@ int swrt_set_flow_planes_spectral(swrt_handle* h, int slot, const double* const*
     REQUIRE(h, planes_re && planes_im, SWRT_ERR_ARG, "null plane table");
     REQUIRE(h, nkx == h->p.nx - 1 && nky == h->p.nx / 2, SWRT_ERR_ARG, "planes must be %d x %d", h->p.nx - 1, h->p.nx / 2);
     size_t n = (size_t)nkx * nky;
-    double *tr = nullptr, *ti = nullptr;
-    CU(h, cudaMalloc(&tr, n * 8)); CU(h, cudaMalloc(&ti, n * 8));
+    DevTmp<double> tr, ti;
+    CU(h, tr.alloc(n)); CU(h, ti.alloc(n));
     int rc = SWRT_OK;
     for (int c = 0; c < nplanes && rc == SWRT_OK; c++) {
         if (!planes_re[c] || !planes_im[c]) { rc = fail(h, SWRT_ERR_ARG, "null plane %d", c); break; }
-        rc = upload_plane(h, planes_re[c], planes_im[c], n, &h->planes[slot][c], tr, ti);
+        rc = upload_plane(h, planes_re[c], planes_im[c], n, &h->planes[slot][c], tr.p, ti.p);
         if (rc == SWRT_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(h, SWRT_ERR_CUDA, "sync failed");
     }
     if (nplanes == 6) dfree(h->planes[slot][6]);
     if (rc == SWRT_OK) rc = finish_spectral_slot(h, slot, nplanes);
-    cudaFree(tr); cudaFree(ti);
     return rc;
 }
 
@@ -524,10 +534,12 @@ int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* 
     const double* src[kMaxPlanes] = {u, v, ux, uy, vx, vy, H};
     const int npl = H ? 7 : 6;
     size_t n = (size_t)nx * nx;
+    std::vector<DevTmp<double>> tmpbuf(npl);
     std::vector<double*> tmp(npl, nullptr);
     int rc = SWRT_OK;
     for (int c = 0; c < npl; c++) {
-        CU(h, cudaMalloc(&tmp[c], n * 8));
+        CU(h, tmpbuf[c].alloc(n));
+        tmp[c] = tmpbuf[c].p;
         CU(h, cudaMemcpyAsync(tmp[c], src[c], n * 8, cudaMemcpyHostToDevice, h->stream));
     }
     if (h->p.mode == SWRT_MODE_LAGRANGE6) {
@@ -552,8 +564,7 @@ int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* 
         if (rc == SWRT_OK) { h->slot_set[slot] = true; h->slot_npl[slot] = npl; h->psi_ok[slot] = false; invalidate_slot(h, slot); }
         cudaStreamSynchronize(h->stream);
     }
-    cudaStreamSynchronize(h->stream);
-    for (auto p : tmp) cudaFree(p);
+    cudaStreamSynchronize(h->stream);              // the temporaries are released on return
     if (rc == SWRT_OK) CU(h, cudaGetLastError());
     return rc;
 }
