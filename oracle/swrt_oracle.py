@@ -5,15 +5,26 @@ this repository accelerates (evaluate U, V, grad U at every wave packet + integr
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it; the product (``swraytracing_b200``) never does.
 
-Parity status: **parity unpinned** at the MATLAB-builtin boundaries.  The reference
-(/root/reference, ~9k lines of MATLAB) ships no tests, no golden vectors and no stored outputs,
-and neither MATLAB nor GNU Octave exists in this image, so the reference cannot be executed
-here.  The oracle is pinned instead by the known-answer tests derived from the reference's own
-scripts (``tests/test_oracle_kat.py``): grid-node identity of
-``interpolate``, the closed-form Childress-Soward flow of ``ray_trace_sw/raytrace.m:31-37``,
-the zero-flow analytic trajectory, the direct trig-sum pattern of
-``scratch/fourier_interpolate_test.m:92-136``, the ``g2k(k2g(.))`` round trip, and the
-Omega-drift bound of ``symplectic_full_fourier.m:54-57``.
+Parity status -- what is pinned and what is not:
+
+* **Pinned against the reference's own stored outputs** (``tests/test_reference_goldens.py``,
+  fixture ``tests/golden/reference_runlogs.json`` extracted from /root/reference by the committed
+  script ``tests/golden/make_reference_goldens.py``): the chain ``rng(146)``/``rand`` ->
+  ``initial_q`` (with the always-true chained comparison of qgsw_raytrace.m:202) -> ``g2k`` ->
+  ``grid_U`` -> ``k2g``/``fulspec`` -> ``U0`` -> ``dt``.  The 19 MATLAB R2020b run logs the
+  reference ships (run.log, analysis/job-*/run-*/run.log) print U0, Fr and dt to six decimals for
+  ten U_g -- reproduced digit for digit -- and the stored ``pv_time`` frame stream (2,682 frames of
+  ``t = t + dt``) is reproduced bit for bit but for three frames at 1-2 ulps, which fixes U0 to a
+  few ulps of what MATLAB computed.
+* **parity unpinned** for the packet arithmetic itself (``interpolate``, ``interpolate_U``,
+  ``ode_symplectic``, ``step_packet*``) and at the MATLAB-builtin boundary ``ode23``: the reference
+  stores no packet outputs (``packet_*.bin`` are git-ignored), has no tests, and neither MATLAB nor
+  GNU Octave exists in this image.  Those functions are pinned by the known-answer tests derived
+  from the reference's own scripts (``tests/test_oracle_kat.py``):
+  grid-node identity of ``interpolate``, the closed-form Childress-Soward flow of
+  ``ray_trace_sw/raytrace.m:31-37``, the zero-flow analytic trajectory, the direct trig-sum pattern
+  of ``scratch/fourier_interpolate_test.m:92-136``, the ``g2k(k2g(.))`` round trip, and the
+  Omega-drift bound of ``symplectic_full_fourier.m:54-57``.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 Array layout follows MATLAB: ``F[ix, iy]`` with x the first index; in memory the oracle keeps
