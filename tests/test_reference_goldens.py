@@ -135,3 +135,50 @@ def test_device_spectral_kit_reproduces_logged_U0():
     assert _fmt(U0) == 1.013140
     for row in LOGS:
         assert _fmt(U0 * row["U_g"]) == row["U0"]
+
+
+# ------------------------------------------------------------------------------------------------
+# MATLAB's own k2g / fulspec / ik-multiplication outputs, from the workspace dump rsw/matlab.mat
+# (tests/golden/rsw_workspace_frame.npz, extracted by tests/golden/make_rsw_goldens.py)
+# ------------------------------------------------------------------------------------------------
+RSW = np.load(Path(__file__).parent / "golden" / "rsw_workspace_frame.npz")
+
+
+def _rsw_cases():
+    """(name, half-plane spectrum, MATLAB's gridded rows) -- rsw/swk.m:205-209 (getrhs)"""
+    Sk, dm = RSW["Sk"], RSW["damask"].astype(np.float64)
+    nx = int(RSW["nx"])
+    kmax = nx // 2 - 1
+    kx = np.arange(-kmax, kmax + 1, dtype=np.float64)[:, None]
+    ky = np.arange(0, kmax + 1, dtype=np.float64)[None, :]
+    return [("u", dm * Sk[:, :, 0], RSW["u_rows"]), ("v", dm * Sk[:, :, 1], RSW["v_rows"]), ("h", dm * Sk[:, :, 2], RSW["h_rows"]),
+            ("zeta", dm * (1j * kx * Sk[:, :, 1] - 1j * ky * Sk[:, :, 0]), RSW["zeta_rows"])]
+
+
+@pytest.mark.parametrize("case", _rsw_cases(), ids=lambda c: c[0])
+def test_oracle_k2g_matches_matlab_workspace(case):
+    from oracle import swrt_oracle as O
+    name, fk, rows = case
+    got = O.k2g(fk)[::int(RSW["row_stride"])]
+    assert np.abs(rows).max() > 1e-2
+    assert np.abs(got - rows).max() <= 1e-15, name          # measured 6e-17 (FFTW vs pocketfft round-off)
+
+
+def test_oracle_g2k_inverts_matlab_grid():
+    """g2k of MATLAB's gridded field returns MATLAB's (dealiased) spectrum: pins g2k.m's normalisation,
+    fftshift and the rows 2:end / columns kmax+2:end window against a MATLAB-produced pair."""
+    from oracle import swrt_oracle as O
+    fk = _rsw_cases()[2][1]
+    full = O.k2g(fk)                                         # == MATLAB's real(h) on the stored rows (test above)
+    back = O.g2k(full)
+    sym = O.symmetrise_ky0(fk)
+    assert np.abs(back - sym).max() <= 1e-16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _rsw_cases(), ids=lambda c: c[0])
+def test_device_k2g_matches_matlab_workspace(case):
+    from swraytracing_b200 import reference_api as R
+    name, fk, rows = case
+    got = R.k2g(fk)[::int(RSW["row_stride"])]
+    assert np.abs(got - rows).max() <= 1e-15, name
