@@ -44,6 +44,10 @@ extern "C" {
 #define SWRT_SCHEME_RK4_PACKET 1  /* ray_trace_sw/step_packet.m:37-78                           */
 #define SWRT_SCHEME_RK4_XKA    2  /* ray_trace_sw/step_packet_xka.m:38-91 (+ cg_sw.m:15-31)     */
 
+/* swrt_params.flags */
+#define SWRT_FLAG_RHS_GH    1  /* odefun group velocity gH*k/omega (SW_zero_background_raytracing.m:182-184,
+                                  initialize_raytracing :134-145) instead of Cg*k/omega (qgsw_raytrace.m:262) */
+
 /* histogram kind */
 #define SWRT_HIST_INTRINSIC 0  /* omega = sqrt(f^2 + gH K^2), analysis/load_data.m:33           */
 #define SWRT_HIST_ABSOLUTE  1  /* Omega = omega + U.k, symplectic_full_fourier.m:41,55          */
@@ -54,7 +58,7 @@ typedef struct swrt_params {
     int32_t nx;        /* grid size (even); spectral arrays are (nx-1) x (nx/2), g2k.m:5-9      */
     int32_t mode;      /* SWRT_MODE_*                                                           */
     int32_t device;    /* CUDA device ordinal                                                   */
-    int32_t reserved;
+    int32_t flags;     /* SWRT_FLAG_* bits (0 = the qgsw_raytrace.m conventions)                  */
     double  L;         /* domain side; dx = L/nx (qgsw_raytrace.m:13-14)                        */
     double  f;         /* Coriolis parameter                                                    */
     double  gH;        /* Cg^2 = C0^2 (ode_symplectic.m:10-11)                                  */
@@ -123,6 +127,10 @@ int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, 
 int swrt_bs23_begin(swrt_handle* h, double alpha, double threshold, double* rh_norm);
 int swrt_bs23_attempt(swrt_handle* h, double hstep, const double alpha[3], double threshold, double* err_norm);
 int swrt_bs23_accept(swrt_handle* h);
+/* dense output of the LAST attempted step (MATLAB ntrp23, used by ode23 when tspan lists output times:
+ * SW_zero_background_raytracing.m:73-78): y(t + s*hstep) = y + hstep * [f1 f2 f3 f4] * BI * [s; s^2; s^3],
+ * BI = [1 -4/3 5/9; 0 1 -2/3; 0 4/3 -8/9; 0 -1 1].  Call between attempt and accept; s in (0, 1].     */
+int swrt_bs23_interp(swrt_handle* h, double hstep, double s, double* x, double* y, double* k, double* l);
 
 /* ---- diagnostics -------------------------------------------------------------------------- */
 /* histcounts(omega, edges) (analysis/load_data.m:39-47): counts[nedges-1], bin i = [e_i,e_i+1),

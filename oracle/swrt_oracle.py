@@ -700,10 +700,19 @@ def ode23(odefun, tspan, y0, rtol=1e-3, atol=1e-6):
     A = [1/2 3/4 1], B = [1/2 0 2/9; 0 3/4 1/3; 0 0 4/9], E = [-5/72 1/12 1/9 -1/8], pow = 1/3,
     threshold = atol/rtol, hmax = 0.1*|tf-t0|, err = |h| * ||(f*E) ./ max(|y|,|ynew|,thr)||_inf,
     rejection factor max(0.5, 0.8 (rtol/err)^pow) (then 0.5), growth 1/(1.25 (err/rtol)^pow) capped at 5.
-    PARITY UNPINNED: MATLAB is proprietary and absent; no reference test stores an ode23 output.
-    Returns (y_final, stats)."""
-    t0, tfinal = float(tspan[0]), float(tspan[1])
+    PARITY UNPINNED: MATLAB is proprietary and absent; no reference test stores an ode23 output (the
+    tableau and the dense-output polynomial are cross-checked against scipy's independent RK23 in
+    tests/test_oracle_kat.py).
+    ``tspan = [t0 tf]`` returns (y_final, stats).  A longer ``tspan`` (SW_zero_background_raytracing.m:73-78)
+    returns (Y, stats) with one row per requested time: the steps are chosen exactly as before and the
+    rows come from the cubic dense output ``ntrp23`` (BI = [1 -4/3 5/9; 0 1 -2/3; 0 4/3 -8/9; 0 -1 1]),
+    or ``ynew`` itself where an output time coincides with a step end."""
+    tspan = np.asarray(tspan, dtype=np.float64)
+    t0, tfinal = float(tspan[0]), float(tspan[-1])
+    dense = tspan.size > 2
     y = np.array(y0, dtype=np.float64)
+    if dense:
+        Y = np.zeros((tspan.size, y.size)); Y[0] = y; nxt = 1
     pw = 1.0 / 3.0
     threshold = atol / rtol
     hmax = min(abs(tfinal - t0), abs(0.1 * (tfinal - t0)))
@@ -747,11 +756,22 @@ def ode23(odefun, tspan, y0, rtol=1e-3, atol=1e-6):
             else:
                 break
         nsteps += 1
+        if dense:
+            while nxt < tspan.size and tnew - tspan[nxt] >= 0:
+                if tspan[nxt] == tnew:
+                    Y[nxt] = ynew
+                else:
+                    sfrac = (tspan[nxt] - t) / h
+                    s2, s3 = sfrac * sfrac, sfrac * sfrac * sfrac
+                    Y[nxt] = y + (f1 * (h * (sfrac - 4.0 / 3.0 * s2 + 5.0 / 9.0 * s3)) + f2 * (h * (s2 - 2.0 / 3.0 * s3))
+                                  + f3 * (h * (4.0 / 3.0 * s2 - 8.0 / 9.0 * s3)) + f4 * (h * (-s2 + s3)))
+                nxt += 1
         if nofailed:
             temp = 1.25 * (err / rtol) ** pw
             absh = absh / temp if temp > 0.2 else 5.0 * absh
         t = tnew; y = ynew; f1 = f4
-    return y, {"nsteps": nsteps, "nfailed": nfailed, "nfevals": nfevals, "t": t}
+    stats = {"nsteps": nsteps, "nfailed": nfailed, "nfevals": nfevals, "t": t}
+    return (Y, stats) if dense else (y, stats)
 
 
 def generate_raytracing_ode(bf1, bf2, Npackets, f, Cg, tmax, h, eval6=None):
@@ -823,3 +843,158 @@ def qg_run(qk, nsteps, dt, nx, L, K_d2, f, Cg, beta=0.0, r_drag=0.1, force_stren
         Qm[1] = Qm[0]; Qm[0] = Qn
         qk = Ef * (qk + dq)
     return qk
+
+
+# --------------------------------------------------------------------------------------------
+# The scripts BASELINE.json's configs name, restated (checkers for swraytracing_b200/drivers.py)
+# --------------------------------------------------------------------------------------------
+
+def childress_soward_as_written(nx, L, U0, km, a):
+    """ray_trace_sw/raytrace.m:31-37 literally: line 36 reads ``a*cos(km*x_)*cos(km*y_)`` -- a MATRIX
+    product -- so the reference's v_x differs from the closed form when a ~= 0 (``childress_soward``
+    above is the intended element-wise form)."""
+    psi, U, G = childress_soward(nx, L, U0, km, a)
+    dx = L / nx
+    x = np.arange(nx) * dx
+    x_, y_ = np.meshgrid(x, x, indexing="ij")
+    G = dict(G)
+    G["v_x"] = -km * U0 * (np.sin(km * x_) * np.sin(km * y_) + (a * np.cos(km * x_)) @ np.cos(km * y_))
+    return psi, U, G
+
+
+def raytrace_driver(C0=1.0, Fr=0.1, f=4.0, a=0.25, np_=5, nx=256, nsteps=None, seed=5489):
+    """ray_trace_sw/raytrace.m:1-54 with the packet-major loops kept (one packet at a time through
+    ``step_packet``).  ``seed`` 5489 = MATLAB's start-up mt19937ar state (no rng call in the script);
+    ``rand*L`` is drawn x then y per packet (:45-46).  Returns x,y,k,l histories (np, nsteps)."""
+    U0 = Fr; L = 2 * np.pi
+    kd = f / C0 ** 2; km = kd; ki = km * 10
+    dx = L / nx
+    dt = 0.3 * dx / max(C0, U0)
+    Tend = 1 / (f * Fr ** 2)
+    nsteps = int(round(Tend / dt)) if nsteps is None else int(nsteps)
+    _, U, GradU = childress_soward_as_written(nx, L, U0, km, a)
+    rs = matlab_rand_stream(seed)
+    hist = {n: np.zeros((np_, nsteps)) for n in ("x", "y", "k", "l")}
+    for i in range(1, np_ + 1):
+        hist["x"][i - 1, 0] = rs.rand() * L
+        hist["y"][i - 1, 0] = rs.rand() * L
+        hist["k"][i - 1, 0] = ki * np.cos(2 * np.pi * i / np_)
+        hist["l"][i - 1, 0] = ki * np.sin(2 * np.pi * i / np_)
+    for i in range(np_):
+        for j in range(1, nsteps):
+            P = {n: hist[n][i, j - 1] for n in hist}
+            out = step_packet(P, U, GradU, C0, f, dx, dx, dt)
+            for n in hist:
+                hist[n][i, j] = out[n]
+    return hist, dt, nsteps
+
+
+def geostrophic_fields(S, f, Cg):
+    """ray_trace_sw/raytrace_sw.m:14-52: geostrophic mode of S(:,:,1:3) = [u,v,eta] and its gradients."""
+    nx = S.shape[0]
+    kx_, ky_ = wavenumbers(nx)
+    K2_ = kx_ ** 2 + ky_ ** 2
+    gH0 = Cg ** 2
+    sig2_ = f ** 2 + gH0 * K2_
+    uk, vk, etak = g2k(S[:, :, 0]), g2k(S[:, :, 1]), g2k(S[:, :, 2])
+    zetak = 1j * (kx_ * vk - ky_ * uk)
+    etagk = (f * etak - zetak) * f / sig2_
+    ugk = -1j * ky_ * (gH0 / f * etagk)
+    vgk = 1j * kx_ * (gH0 / f * etagk)
+    H = 1 + k2g(etagk)
+    U = {"u": k2g(ugk), "v": k2g(vgk)}
+    GradU = {"u_x": k2g(1j * kx_ * ugk), "u_y": k2g(1j * ky_ * ugk), "v_x": k2g(1j * kx_ * vgk), "v_y": k2g(1j * ky_ * vgk)}
+    return U, GradU, H
+
+
+def raytrace_sw_driver(S, f, Cg, np_=10, nsteps=None, seed=5489):
+    """ray_trace_sw/raytrace_sw.m:80-130 (packet-major loops, ``step_packet_xka`` one packet at a time)."""
+    nx = S.shape[0]
+    C0 = Cg
+    U, GradU, H = geostrophic_fields(S, f, Cg)
+    L = 2 * np.pi
+    kd = f / C0; ki = kd * 10
+    U0 = float(np.sqrt(U["u"] ** 2 + U["v"] ** 2).max())
+    Fr = U0 / C0
+    dx = L / nx
+    dt = 0.3 * dx / max(C0, U0)
+    if nsteps is None:
+        nsteps = int(round(20 / (f * Fr ** 2) / dt))
+    rs = matlab_rand_stream(seed)
+    hist = {n: np.zeros((np_, nsteps)) for n in ("x", "y", "k", "l", "a")}
+    for i in range(1, np_ + 1):
+        hist["x"][i - 1, 0] = rs.rand() * L
+        hist["y"][i - 1, 0] = rs.rand() * L
+        hist["k"][i - 1, 0] = ki * np.cos(2 * np.pi * i / np_)
+        hist["l"][i - 1, 0] = ki * np.sin(2 * np.pi * i / np_)
+        hist["a"][i - 1, 0] = 1.0
+    for i in range(np_):
+        for j in range(1, nsteps):
+            P = {n: hist[n][i, j - 1] for n in hist}
+            out = step_packet_xka(P, U, GradU, H, C0, f, dx, dx, dt)
+            for n in hist:
+                hist[n][i, j] = out[n]
+    return hist, {"dt": dt, "nsteps": nsteps, "U0": U0, "Fr": Fr, "U": U, "GradU": GradU, "H": H}
+
+
+def frozen_flow_setup(q, nx, f, Cg, Nparticles, grid_lo, mode="lagrange", seed=123):
+    """symplectic_full_fourier.m:5-38 / SW_zero_background_raytracing.m:6-50: scheme from a PV frame, ring
+    of packets (rng(123)), U0 = max speed over the nx^2 points of ``meshgrid(linspace(lo, lo+L, nx))``."""
+    L = 2 * np.pi
+    K_d2 = f / Cg
+    kx_, ky_ = wavenumbers(nx)
+    K2 = kx_ ** 2 + ky_ ** 2
+    rs = matlab_rand_stream(seed)
+    X = matlab_linspace(grid_lo, grid_lo + L, nx)
+    XX, YY = np.meshgrid(X, X)
+    scheme = SpectralScheme(L, nx, k2g(-g2k(q) / (K_d2 + K2)), mode=mode)
+    x = np.zeros((1, 2, Nparticles)); k = np.zeros((1, 2, Nparticles))
+    for i in range(1, Nparticles + 1):
+        k[0, :, i - 1] = 3 * np.array([np.cos(2 * np.pi * i / Nparticles), np.sin(2 * np.pi * i / Nparticles)])
+        x[0, :, i - 1] = L * rs.rand(2) - L / 2
+    U = scheme.U(np.stack([XX.ravel(order="F"), YY.ravel(order="F")], axis=1))
+    U0 = float(np.sqrt((U ** 2).sum(axis=1)).max())
+    gH = Cg ** 2
+    return L, gH, scheme, x, k, U0, U0 / Cg, 0.1 * (L / nx) / max(Cg, U0)
+
+
+def omega_abs_history(scheme, x, k, f, gH):
+    """omega(k,f,gH) + dot(scheme.U(x), k, 2) (symplectic_full_fourier.m:41,55,62-64)"""
+    return np.sqrt(f * f + gH * (k ** 2).sum(axis=1)) + (scheme.U(x) * k).sum(axis=1)
+
+
+def symplectic_full_fourier_driver(q, nx, f, Cg, Nparticles=10, Tend=None, mode="lagrange", seed=123):
+    """symplectic_full_fourier.m:1-60 from the PV frame on."""
+    L, gH, scheme, x, k, U0, Fr, dt = frozen_flow_setup(q, nx, f, Cg, Nparticles, 0.0, mode, seed)
+    Tend = 10 / (f * Fr ** 2) if Tend is None else Tend
+    Omega_0 = omega_abs_history(scheme, x, k, f, gH)
+    sx, sk, st = ode_symplectic(x, k, dt, Tend, f, gH, scheme)
+    err = (omega_abs_history(scheme, sx, sk, f, gH) - Omega_0) / Omega_0
+    return {"solver_x": sx, "solver_k": sk, "solver_t": st, "solver_error": err, "U0": U0, "Fr": Fr, "dt": dt, "Tend": Tend}
+
+
+def sw_zero_background_driver(q, nx, f, Cg, Nparticles=10, Tend=None, rtol=1e-6, atol=1e-7, mode="lagrange", seed=123):
+    """SW_zero_background_raytracing.m:1-132 from the PV frame on: ode23 with output at dt*(0:Nsteps),
+    RHS dx/dt = U + gH k/omega, dk/dt = -(grad U)^T k (:134-145,182-184)."""
+    L, gH, scheme, x, k, U0, Fr, dt = frozen_flow_setup(q, nx, f, Cg, Nparticles, -np.pi, mode, seed)
+    Tend = 1 / (f * Fr ** 2) if Tend is None else Tend
+    Nsteps = int(math.floor(Tend / dt))
+    n = Nparticles
+
+    def odefun(t, y):
+        xa = np.stack([y[0:n], y[n:2 * n]], axis=1)
+        ka = np.stack([y[2 * n:3 * n], y[3 * n:4 * n]], axis=1)
+        cg = gH * ka / np.sqrt(f * f + gH * (ka ** 2).sum(axis=1))[:, None]
+        dx = scheme.U(xa) + cg
+        dk = -scheme.grad_U_times_k(xa, ka)
+        return np.concatenate([dx[:, 0], dx[:, 1], dk[:, 0], dk[:, 1]])
+
+    y0 = np.concatenate([x[0, 0], x[0, 1], k[0, 0], k[0, 1]])
+    t_hist = dt * np.arange(0, Nsteps + 1)
+    Y, stats = ode23(odefun, t_hist, y0, rtol=rtol, atol=atol)
+    sx = np.stack([Y[:, 0:n], Y[:, n:2 * n]], axis=1)
+    sk = np.stack([Y[:, 2 * n:3 * n], Y[:, 3 * n:4 * n]], axis=1)
+    Omega_0 = omega_abs_history(scheme, x, k, f, gH)[0]
+    err = (omega_abs_history(scheme, sx, sk, f, gH) - Omega_0) / Omega_0
+    return {"t_hist": t_hist, "solver_x": sx, "solver_k": sk, "solver_error": err, "U0": U0, "Fr": Fr, "dt": dt, "Nsteps": Nsteps,
+            "stats": stats}

@@ -16,14 +16,15 @@ __global__ void fill_kernel(double* p, double v, long long n) {
 
 // odefun: dxdt = U + Cg*k/sqrt(f^2 + Cg^2 |k|^2), dkdt = -(grad U)^T k
 struct E6 { const double* p[6]; };
+// cgfac = Cg (qgsw_raytrace.m:262) or gH (SW_zero_background_raytracing.m:182-184)
 __global__ void rhs_kernel(long long n, const double* __restrict__ k, const double* __restrict__ l, E6 e, double f,
-                           double Cg, double* dxdt, double* dydt, double* dkdt, double* dldt) {
+                           double gH, double cgfac, double* dxdt, double* dydt, double* dkdt, double* dldt) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double kk = k[i], ll = l[i];
-    const double w = sqrt(f * f + Cg * Cg * (kk * kk + ll * ll));
-    if (dxdt) dxdt[i] = e.p[0][i] + Cg * kk / w;
-    if (dydt) dydt[i] = e.p[1][i] + Cg * ll / w;
+    const double w = sqrt(f * f + gH * (kk * kk + ll * ll));
+    if (dxdt) dxdt[i] = e.p[0][i] + cgfac * kk / w;
+    if (dydt) dydt[i] = e.p[1][i] + cgfac * ll / w;
     if (dkdt) dkdt[i] = -(e.p[2][i] * kk + e.p[4][i] * ll);
     if (dldt) dldt[i] = -(e.p[3][i] * kk + e.p[5][i] * ll);
 }
@@ -257,8 +258,22 @@ __global__ void bs23_accept_kernel(Bs23Args a) {
 #pragma unroll
     for (int c = 0; c < 4; c++) { a.y[c][i] = a.yt[c][i]; a.f[0][c][i] = a.f[3][c][i]; }
 }
+// ntrp23: out = y + (f1 w1 + f2 w2 + f3 w3 + f4 w4), w_j = hstep * (BI_j . [s s^2 s^3])
+struct Bs23Interp { double w[4]; double* out[4]; };
+__global__ void bs23_interp_kernel(Bs23Args a, Bs23Interp q) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        q.out[c][i] = a.y[c][i] + (a.f[0][c][i] * q.w[0] + a.f[1][c][i] * q.w[1] + a.f[2][c][i] * q.w[2] + a.f[3][c][i] * q.w[3]);
+}
 }  // namespace
 
+void launch_bs23_interp(const Bs23Args& a, const double w[4], double* const out[4], cudaStream_t st) {
+    Bs23Interp q;
+    for (int j = 0; j < 4; j++) { q.w[j] = w[j]; q.out[j] = out[j]; }
+    if (a.n > 0) bs23_interp_kernel<<<nblk(a.n, 256), 256, 0, st>>>(a, q);
+}
 void launch_bs23_stage(const Bs23Args& a, double hb1, double hb2, double hb3, cudaStream_t st) {
     if (a.n > 0) bs23_stage_kernel<<<nblk(a.n, 256), 256, 0, st>>>(a, hb1, hb2, hb3);
 }
@@ -276,10 +291,10 @@ void launch_bs23_accept(const Bs23Args& a, cudaStream_t st) {
 void launch_fill(double* p, double v, long long n, cudaStream_t st) {
     if (n > 0) fill_kernel<<<nblk(n, 256), 256, 0, st>>>(p, v, n);
 }
-void launch_rhs(long long n, const double* k, const double* l, const double* const* e6, double f, double Cg,
+void launch_rhs(long long n, const double* k, const double* l, const double* const* e6, double f, double gH, double cgfac,
                 double* dxdt, double* dydt, double* dkdt, double* dldt, cudaStream_t st) {
     E6 e; for (int i = 0; i < 6; i++) e.p[i] = e6[i];
-    if (n > 0) rhs_kernel<<<nblk(n, 256), 256, 0, st>>>(n, k, l, e, f, Cg, dxdt, dydt, dkdt, dldt);
+    if (n > 0) rhs_kernel<<<nblk(n, 256), 256, 0, st>>>(n, k, l, e, f, gH, cgfac, dxdt, dydt, dkdt, dldt);
 }
 void launch_omega(long long n, const double* k, const double* l, const double* u, const double* v, double f, double gH,
                   double* omega, double* Omega_abs, cudaStream_t st) {

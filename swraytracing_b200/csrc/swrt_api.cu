@@ -653,6 +653,10 @@ int swrt_eval_at(swrt_handle* h, double alpha, int64_t n, const double* x, const
     return SWRT_OK;
 }
 
+// odefun uses Cg (not Cg^2) in the production drivers (qgsw_raytrace.m:262, qg2layersw_raytrace.m:301) and gH in
+// SW_zero_background_raytracing.m:182-184 (SWRT_FLAG_RHS_GH)
+static inline double rhs_cgfac(const swrt_handle* h) { return (h->p.flags & SWRT_FLAG_RHS_GH) ? h->p.gH : sqrt(h->p.gH); }
+
 int swrt_rhs(swrt_handle* h, double alpha, double* dxdt, double* dydt, double* dkdt, double* dldt) {
     if (!h) return SWRT_ERR_ARG;
     CU(h, cudaSetDevice(h->p.device));
@@ -660,9 +664,7 @@ int swrt_rhs(swrt_handle* h, double alpha, double* dxdt, double* dydt, double* d
     int rc = ensure_scratch(h, h->n);
     if (rc) return rc;
     if ((rc = eval_dev(h, SUB_SIX, alpha, h->n, h->x, h->y, h->e))) return rc;
-    // odefun uses Cg (not Cg^2): qgsw_raytrace.m:262
-    const double Cg = sqrt(h->p.gH);
-    launch_rhs(h->n, h->k, h->l, h->e, h->p.f, Cg, h->xs, h->ys, h->ax, h->ay, h->stream);
+    launch_rhs(h->n, h->k, h->l, h->e, h->p.f, h->p.gH, rhs_cgfac(h), h->xs, h->ys, h->ax, h->ay, h->stream);
     h->launches++;
     if ((rc = d2h(h, dxdt, h->xs, h->n)) || (rc = d2h(h, dydt, h->ys, h->n)) || (rc = d2h(h, dkdt, h->ax, h->n)) ||
         (rc = d2h(h, dldt, h->ay, h->n)))
@@ -968,7 +970,7 @@ static int bs23_setup(swrt_handle* h, Bs23Args& a) {
 static int bs23_rhs(swrt_handle* h, double alpha, double* const st[4], double* const fj[4]) {
     int rc = eval_dev(h, SUB_SIX, alpha, h->n, st[0], st[1], h->e);
     if (rc) return rc;
-    launch_rhs(h->n, st[2], st[3], h->e, h->p.f, sqrt(h->p.gH), fj[0], fj[1], fj[2], fj[3], h->stream);
+    launch_rhs(h->n, st[2], st[3], h->e, h->p.f, h->p.gH, rhs_cgfac(h), fj[0], fj[1], fj[2], fj[3], h->stream);
     h->launches++;
     return SWRT_OK;
 }
@@ -1027,6 +1029,34 @@ int swrt_bs23_accept(swrt_handle* h) {
     if (rc) return rc;
     launch_bs23_accept(a, h->stream);
     h->launches++;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SWRT_OK;
+}
+
+int swrt_bs23_interp(swrt_handle* h, double hstep, double s, double* x, double* y, double* k, double* l) {
+    if (!h || !x || !y || !k || !l) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, h->bs_ready && h->bs_cap >= h->n, SWRT_ERR_STATE, "swrt_bs23_attempt has not been called");
+    Bs23Args a{};
+    int rc = bs23_setup(h, a);
+    if (rc) return rc;
+    if (s == 1.0) {   // an output time that coincides with the step end gets ynew itself (ode23: tspan(next) == tnew)
+        if ((rc = d2h(h, x, a.yt[0], h->n)) || (rc = d2h(h, y, a.yt[1], h->n)) || (rc = d2h(h, k, a.yt[2], h->n)) ||
+            (rc = d2h(h, l, a.yt[3], h->n)))
+            return rc;
+        CU(h, cudaStreamSynchronize(h->stream));
+        return SWRT_OK;
+    }
+    // BI = [1 -4/3 5/9; 0 1 -2/3; 0 4/3 -8/9; 0 -1 1] (ntrp23), columns weighted by s, s^2, s^3
+    const double s2 = s * s, s3 = s2 * s;
+    const double w[4] = {hstep * (s - 4.0 / 3.0 * s2 + 5.0 / 9.0 * s3), hstep * (s2 - 2.0 / 3.0 * s3),
+                         hstep * (4.0 / 3.0 * s2 - 8.0 / 9.0 * s3), hstep * (-s2 + s3)};
+    double* out[4] = {h->xs, h->ys, h->ax, h->ay};
+    launch_bs23_interp(a, w, out, h->stream);
+    h->launches++;
+    if ((rc = d2h(h, x, h->xs, h->n)) || (rc = d2h(h, y, h->ys, h->n)) || (rc = d2h(h, k, h->ax, h->n)) ||
+        (rc = d2h(h, l, h->ay, h->n)))
+        return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
 }

@@ -111,7 +111,7 @@ struct Rk4Args {   // spectral-mode RK4 glue (point-wise composition), all devic
 };
 void launch_rk4_stage(const Rk4Args& a, cudaStream_t st);
 void launch_rk4_final(const Rk4Args& a, cudaStream_t st);
-void launch_rhs(long long n, const double* k, const double* l, const double* const* e6, double f, double Cg,
+void launch_rhs(long long n, const double* k, const double* l, const double* const* e6, double f, double gH, double cgfac,
                 double* dxdt, double* dydt, double* dkdt, double* dldt, cudaStream_t st);
 void launch_omega(long long n, const double* k, const double* l, const double* u, const double* v,
                   double f, double gH, double* omega, double* Omega_abs, cudaStream_t st);
@@ -132,5 +132,6 @@ struct Bs23Args {          // ode23 work arrays, component order x,y,k,l
 void launch_bs23_stage(const Bs23Args& a, double hb1, double hb2, double hb3, cudaStream_t st);
 void launch_bs23_norm(const Bs23Args& a, int mode, double thr, unsigned long long* out, cudaStream_t st);
 void launch_bs23_accept(const Bs23Args& a, cudaStream_t st);
+void launch_bs23_interp(const Bs23Args& a, const double w[4], double* const out[4], cudaStream_t st);
 
 }  // namespace swrt

@@ -17,7 +17,8 @@ import time
 import numpy as np
 
 from . import fieldio
-from .engine import Engine, QGFlow, MODE_SPECTRAL, SCHEME_LEAPFROG, k2g_dev, g2k_dev
+from .engine import (Engine, QGFlow, MODE_SPECTRAL, SCHEME_LEAPFROG, SCHEME_RK4_PACKET, SCHEME_RK4_XKA, k2g_dev,
+                     g2k_dev)
 from .reference_api import ode23
 
 
@@ -127,3 +128,244 @@ def qgsw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_delay_da
            "packet_frames": writer.frames}
     qg.close(); eng.close()
     return out
+
+
+# =====================================================================================================
+# The other four scripts BASELINE.json's configs name, each with its own control flow and defaults kept.
+# They are scripts (no arguments) in the reference; here the constants edited in-file become keyword
+# arguments whose defaults are the reference's values, and inputs the reference loads from files that are
+# not in the tree (analysis/pv.bin, wavevort_231058_restart_frame100.mat) are arguments.
+# =====================================================================================================
+
+def parse_data(filename):
+    """symplectic_full_fourier.m:66-82 / SW_zero_background_raytracing.m:146-162: read nx, Npackets, f, Cg,
+    U_g back from a run log header (qgsw_raytrace.m:76-88) -> (resolution, Npackets, f, Cg, Ug)."""
+    import re
+    with open(filename, "r", errors="replace") as fh:
+        text = fh.read(8192)
+    def grab(pat, cast=float):
+        m = re.search(pat, text)
+        if not m:
+            raise ValueError(f"parse_data: {pat!r} not found in {filename}")
+        return cast(m.group(1))
+    return (grab(r"Resolution: (\d+)x\d+", int), grab(r"Number of packets: (\d+)", int), grab(r"Coriolis parameter: ([-\d.eE+]+)"),
+            grab(r"Group velocity: ([-\d.eE+]+)"), grab(r"Background velocity \(parameter,computed\): \(([-\d.eE+]+),"))
+
+
+def _ring_packets(Nparticles, L, radius, rs):
+    """symplectic_full_fourier.m:22-28: k on a ring, x = L*rand(1,2) - L/2 drawn per packet -> (1,2,Np) arrays"""
+    i = np.arange(1, Nparticles + 1)
+    r = rs.rand(Nparticles, 2)
+    x = np.zeros((1, 2, Nparticles)); k = np.zeros((1, 2, Nparticles))
+    k[0, 0] = radius * np.cos(2 * np.pi * i / Nparticles); k[0, 1] = radius * np.sin(2 * np.pi * i / Nparticles)
+    x[0, 0] = L * r[:, 0] - L / 2; x[0, 1] = L * r[:, 1] - L / 2
+    return x, k
+
+
+def _frozen_flow_setup(q, nx, f, Cg, Nparticles, grid_lo, mode, device, seed, ring_radius=3.0):
+    """the common head of symplectic_full_fourier.m:5-38 and SW_zero_background_raytracing.m:6-50"""
+    from .reference_api import SpectralScheme, g2k, k2g
+    L = 2 * np.pi
+    K_d2 = f / Cg
+    kx_, ky_ = wavenumber_grids(nx)
+    K2 = kx_ ** 2 + ky_ ** 2
+    rs = np.random.RandomState(seed)                                   # rng(123)
+    X = np.linspace(grid_lo, grid_lo + L, nx)                          # linspace(0,L,nx) / linspace(-L/2,L/2,nx)
+    XX, YY = np.meshgrid(X, X)
+    gH = Cg ** 2
+    scheme = SpectralScheme(L, nx, k2g(-g2k(q, device) / (K_d2 + K2), device), mode=mode, f=f, gH=gH, device=device)
+    x, k = _ring_packets(Nparticles, L, ring_radius, rs)
+    U = scheme.U(np.stack([XX.ravel(order="F"), YY.ravel(order="F")], axis=1))     # scheme.U([XX(:), YY(:)])
+    U0 = float(np.sqrt((U ** 2).sum(axis=1)).max())
+    Fr = U0 / Cg
+    dt = 0.1 * (L / nx) / max(Cg, U0)
+    return L, gH, scheme, x, k, U0, Fr, dt
+
+
+def _omega_abs(scheme, x, k, f, gH):
+    """omega(k) + dot(scheme.U(x), k, 2) over a (T,2,Np) history (symplectic_full_fourier.m:41,55)"""
+    U = scheme.U(x)
+    return np.sqrt(f * f + gH * (k ** 2).sum(axis=1)) + (U * k).sum(axis=1)
+
+
+def symplectic_full_fourier(q=None, *, nx=None, f=None, Cg=None, run_log_file=None, pv=None, frame=2000, Nparticles=10,
+                            Tend=None, save_stride=1, mode=MODE_SPECTRAL, seed=123, device=0):
+    """symplectic_full_fourier.m:1-60 (BASELINE config 2): frozen QG frame -> SpectralScheme -> ring of packets
+    -> ``ode_symplectic`` -> relative drift of the absolute frequency Omega = omega + U.k.
+
+    The PV frame comes from ``q`` (nx x nx), or from frame ``frame`` of the write_field stream ``pv`` (the
+    reference reads frame 2000 of analysis/pv, which is git-ignored); nx, f, Cg from ``run_log_file`` via
+    ``parse_data`` when not given.  Returns dict(solver_x, solver_k, solver_t, solver_error, Omega_0, U0, Fr, dt,
+    Tend).  ``save_stride`` > 1 keeps every stride-th row of the history (extension for large Nparticles)."""
+    from .reference_api import ode_symplectic
+    if run_log_file is not None:
+        lnx, _, lf, lCg, _ = parse_data(run_log_file)
+        nx, f, Cg = nx or lnx, f if f is not None else lf, Cg if Cg is not None else lCg
+    if q is None:
+        q = fieldio.read_field(pv, nx, nx, 1, [frame])[:, :, 0, 0] if pv is not None else None
+    if q is None:
+        raise ValueError("symplectic_full_fourier: pass the PV frame q, or pv=<write_field stream> (analysis/pv is not in the tree)")
+    q = np.asarray(q, dtype=np.float64).reshape(nx, nx)
+    L, gH, scheme, x, k, U0, Fr, dt = _frozen_flow_setup(q, nx, f, Cg, Nparticles, 0.0, mode, device, seed)
+    Tend = 10 / (f * Fr ** 2) if Tend is None else Tend
+    Omega_0 = _omega_abs(scheme, x, k, f, gH)
+    sx, sk, st = ode_symplectic(x, k, dt, Tend, f, gH, scheme, save_stride=save_stride)
+    Omega_abs = _omega_abs(scheme, sx, sk, f, gH)
+    return {"solver_x": sx, "solver_k": sk, "solver_t": st, "solver_error": (Omega_abs - Omega_0) / Omega_0, "Omega_0": Omega_0,
+            "U0": U0, "Fr": Fr, "dt": dt, "Tend": Tend, "scheme": scheme}
+
+
+def SW_zero_background_raytracing(q=None, *, nx=None, f=None, Cg=None, run_log_file=None, pv=None, frame=2000, Nparticles=10,
+                                  Tend=None, rtol=1e-6, atol=1e-7, mode=MODE_SPECTRAL, seed=123, device=0):
+    """SW_zero_background_raytracing.m:1-132 (BASELINE config 1): the same frozen frame and packet ring, integrated
+    by ``ode23`` with RelTol 1e-6 / AbsTol 1e-7 and output requested at ``t_hist = dt*(0:Nsteps)`` (:70-78), RHS
+    ``dx/dt = U + gH k/omega`` (:134-145,182-184).  ``q = zeros`` is the "zero background" of the file name
+    (the hint on :28-29).  Returns dict(t_hist, solver_x, solver_k, solver_error, w, Omega_0, U0, Fr, dt, stats)."""
+    from .engine import FLAG_RHS_GH
+    from .reference_api import ode23
+    if run_log_file is not None:
+        lnx, _, lf, lCg, _ = parse_data(run_log_file)
+        nx, f, Cg = nx or lnx, f if f is not None else lf, Cg if Cg is not None else lCg
+    if q is None and pv is not None:
+        q = fieldio.read_field(pv, nx, nx, 1, [frame])[:, :, 0, 0]
+    if q is None:
+        raise ValueError("SW_zero_background_raytracing: pass the PV frame q (zeros for the zero-background case) or pv=<stream>")
+    q = np.asarray(q, dtype=np.float64).reshape(nx, nx)
+    L, gH, scheme, x, k, U0, Fr, dt = _frozen_flow_setup(q, nx, f, Cg, Nparticles, -np.pi, mode, device, seed)
+    if Tend is None:
+        if Fr == 0:
+            raise ValueError("zero background flow: Fr = 0, pass Tend explicitly (the reference's 1/(f*Fr^2) is infinite)")
+        Tend = 1 / (f * Fr ** 2)
+    Nsteps = int(math.floor(Tend / dt))
+    Omega_0 = _omega_abs(scheme, x, k, f, gH)[0]
+    t_hist = dt * np.arange(0, Nsteps + 1)
+    eng = Engine(nx, L, f, gH, mode, device, flags=FLAG_RHS_GH)
+    eng.set_flow_spectral(scheme.psik)
+    eng.set_packets(x[0, 0], x[0, 1], k[0, 0], k[0, 1])
+    stats = ode23(eng, t_hist, None, rtol=rtol, atol=atol)             # steady flow: one slot, alpha = 0
+    Y = stats.pop("Y")
+    eng.close()
+    solver_x, solver_k = Y[:, 0:2, :], Y[:, 2:4, :]
+    w = np.sqrt(f * f + gH * (solver_k ** 2).sum(axis=1))
+    Omega_abs = _omega_abs(scheme, solver_x, solver_k, f, gH)
+    return {"t_hist": t_hist, "solver_x": solver_x, "solver_k": solver_k, "w": w, "solver_error": (Omega_abs - Omega_0) / Omega_0,
+            "Omega_0": Omega_0, "U0": U0, "Fr": Fr, "dt": dt, "Nsteps": Nsteps, "stats": stats, "scheme": scheme}
+
+
+def childress_soward_fields(nx, L, U0, km, a, faithful=True):
+    """ray_trace_sw/raytrace.m:26-37 on ``[x_,y_] = ndgrid(0:dx:dx*(nx-1))``.  ``faithful=True`` keeps line 36 as
+    written -- ``a*cos(km*x_)*cos(km*y_)`` is a MATRIX product there -- so v_x is what the reference computes;
+    ``faithful=False`` uses the element-wise product the formula intends."""
+    dx = L / nx
+    x = dx * np.arange(nx)
+    x_, y_ = np.meshgrid(x, x, indexing="ij")
+    sx, cx, sy, cy = np.sin(km * x_), np.cos(km * x_), np.sin(km * y_), np.cos(km * y_)
+    cc = (cx @ cy) if faithful else cx * cy
+    U = {"u": -U0 * (sx * cy - a * cx * sy), "v": U0 * (cx * sy - a * sx * cy)}
+    GradU = {"u_x": -km * U0 * (cx * cy + a * sx * sy), "u_y": km * U0 * (sx * sy + a * cx * cy),
+             "v_x": -km * U0 * (sx * sy + a * cc), "v_y": km * U0 * (cx * cy + a * sx * sy)}
+    psi = U0 / km * (sx * sy + a * cx * cy)
+    return psi, U, GradU
+
+
+def _packet_history_run(stepper, P0, dt, nsteps, save_stride, with_a):
+    """the packet-major double loop of raytrace.m:50-54 / raytrace_sw.m:125-130 with all packets advanced together:
+    column j of the history = state after j-1 steps (P(i,j)); every save_stride-th column is kept."""
+    cols = list(range(0, nsteps, save_stride))
+    names = ("x", "y", "k", "l") + (("a",) if with_a else ())
+    hist = {n: np.zeros((P0["x"].size, len(cols))) for n in names}
+    for n in names:
+        hist[n][:, 0] = P0[n]
+    eng = stepper.eng
+    eng.set_packets(P0["x"], P0["y"], P0["k"], P0["l"], P0["a"] if with_a else None)
+    done = 0
+    for c in range(1, len(cols)):
+        eng.step(SCHEME_RK4_XKA if with_a else SCHEME_RK4_PACKET, dt, cols[c] - done)
+        done = cols[c]
+        for n, v in zip(names, eng.get_packets(with_a=with_a)):
+            hist[n][:, c] = v
+    return hist, np.asarray(cols)
+
+
+def raytrace(*, C0=1.0, Fr=0.1, f=4.0, a=0.25, np_=5, nx=256, nsteps=None, save_stride=1, faithful=True, mode=None, seed=5489,
+             device=0):
+    """ray_trace_sw/raytrace.m:1-64: packets in an analytic Childress-Soward flow advanced by ``step_packet``.
+    Returns dict(P={x,y,k,l: (np, nsaved)}, t, omega, Cmag, K, psi, U, GradU, dt, nsteps).  ``seed`` 5489 is
+    MATLAB's start-up generator state (the script never calls rng)."""
+    from .engine import MODE_LAGRANGE6
+    from .reference_api import PacketStepper
+    mode = MODE_LAGRANGE6 if mode is None else mode
+    U0 = Fr; L = 2 * np.pi
+    kd = f / C0 ** 2; km = kd; ki = km * 10
+    dx = L / nx
+    dt = 0.3 * dx / max(C0, U0)
+    Tend = 1 / (f * Fr ** 2)
+    nsteps = int(round(Tend / dt)) if nsteps is None else int(nsteps)
+    psi, U, GradU = childress_soward_fields(nx, L, U0, km, a, faithful)
+    rs = np.random.RandomState(seed)
+    r = rs.rand(np_, 2); i = np.arange(1, np_ + 1)
+    P0 = {"x": r[:, 0] * L, "y": r[:, 1] * L, "k": ki * np.cos(2 * np.pi * i / np_), "l": ki * np.sin(2 * np.pi * i / np_)}
+    stepper = PacketStepper(U, GradU, None, C0, f, dx, mode, device)
+    P, cols = _packet_history_run(stepper, P0, dt, nsteps, save_stride, False)
+    stepper.eng.close()
+    K2 = P["k"] ** 2 + P["l"] ** 2
+    omega = np.sqrt(f ** 2 + C0 ** 2 * K2)                              # cg_sw.m:22 without H
+    return {"P": P, "t": dt * cols, "omega": omega, "Cmag": C0 ** 2 * np.sqrt(K2) / omega, "K": np.sqrt(K2), "psi": psi, "U": U,
+            "GradU": GradU, "dt": dt, "nsteps": nsteps}
+
+
+def geostrophic_fields(S, f, Cg, device=0):
+    """ray_trace_sw/raytrace_sw.m:14-52: geostrophic mode of an [u,v,eta] state (the recipe of
+    rsw/wavevortdecomp.m:41-45) and its gradients on the grid -> (U, GradU, H); transforms on the device."""
+    S = np.asarray(S, dtype=np.float64)
+    nx = S.shape[0]
+    kx_, ky_ = wavenumber_grids(nx)
+    K2_ = kx_ ** 2 + ky_ ** 2
+    gH0 = Cg ** 2
+    sig2_ = f ** 2 + gH0 * K2_
+    uk, vk, etak = (g2k_dev(S[:, :, j], device) for j in range(3))
+    zetak = 1j * (kx_ * vk - ky_ * uk)
+    etagk = (f * etak - zetak) * f / sig2_
+    ugk = -1j * ky_ * (gH0 / f * etagk)
+    vgk = 1j * kx_ * (gH0 / f * etagk)
+    H = 1 + k2g_dev(etagk, device)
+    U = {"u": k2g_dev(ugk, device), "v": k2g_dev(vgk, device)}
+    GradU = {"u_x": k2g_dev(1j * kx_ * ugk, device), "u_y": k2g_dev(1j * ky_ * ugk, device),
+             "v_x": k2g_dev(1j * kx_ * vgk, device), "v_y": k2g_dev(1j * ky_ * vgk, device)}
+    return U, GradU, H
+
+
+def raytrace_sw(S, f, Cg, *, np_=10, nsteps=None, save_stride=1, mode=None, seed=5489, device=0):
+    """ray_trace_sw/raytrace_sw.m:11-140 (BASELINE config 5): geostrophic part of a shallow-water state
+    ``S(:,:,1:3) = [u,v,eta]`` (what ``load wavevort_231058_restart_frame100`` provides, with f and Cg), packets on
+    the ring ki = 10 kd advanced by ``step_packet_xka`` with wave action.  Returns dict(P={x,y,k,l,a}, t, omega,
+    Cmag, K, U, GradU, H, U0, Fr, dt, nsteps); omega/Cmag are cg_sw (:135) evaluated with H at each packet."""
+    from .engine import MODE_LAGRANGE6
+    from .reference_api import PacketStepper
+    mode = MODE_LAGRANGE6 if mode is None else mode
+    S = np.asarray(S, dtype=np.float64)
+    nx = S.shape[0]
+    gH0 = Cg ** 2; C0 = Cg
+    U, GradU, H = geostrophic_fields(S, f, Cg, device)
+    L = 2 * np.pi
+    kd = f / C0; ki = kd * 10
+    U0 = float(np.sqrt(U["u"] ** 2 + U["v"] ** 2).max())
+    Fr = U0 / C0
+    dx = L / nx
+    dt = 0.3 * dx / max(C0, U0)
+    if nsteps is None:
+        nsteps = int(round(20 / (f * Fr ** 2) / dt))
+    rs = np.random.RandomState(seed)
+    r = rs.rand(np_, 2); i = np.arange(1, np_ + 1)
+    P0 = {"x": r[:, 0] * L, "y": r[:, 1] * L, "k": ki * np.cos(2 * np.pi * i / np_), "l": ki * np.sin(2 * np.pi * i / np_),
+          "a": np.ones(np_)}
+    stepper = PacketStepper(U, GradU, H, C0, f, dx, mode, device)
+    P, cols = _packet_history_run(stepper, P0, dt, int(nsteps), save_stride, True)
+    # [C, omega] = cg_sw(k,l,C0,f,H) is a whole-grid field per packet in the reference (:135); the per-packet number
+    # that is meaningful (and that the plots average) is the one at the packet: H interpolated to (x,y)
+    Hp = stepper.eng.eval_at(P["x"].ravel(order="F"), P["y"].ravel(order="F"), with_H=True)[6].reshape(P["x"].shape, order="F")
+    stepper.eng.close()
+    K2 = P["k"] ** 2 + P["l"] ** 2
+    omega = np.sqrt(f ** 2 + gH0 * Hp * K2)
+    return {"P": P, "t": dt * cols, "omega": omega, "Cmag": gH0 * Hp * np.sqrt(K2) / omega, "K": np.sqrt(K2), "U": U, "GradU": GradU,
+            "H": H, "U0": U0, "Fr": Fr, "dt": dt, "nsteps": int(nsteps)}

@@ -17,6 +17,7 @@ LIB_PATH = _HERE / "libswrt.so"
 MODE_SPECTRAL, MODE_LAGRANGE6 = 0, 1
 SCHEME_LEAPFROG, SCHEME_RK4_PACKET, SCHEME_RK4_XKA = 0, 1, 2
 HIST_INTRINSIC, HIST_ABSOLUTE = 0, 1
+FLAG_RHS_GH = 1
 
 _dp = C.POINTER(C.c_double)
 
@@ -28,7 +29,7 @@ class SwrtError(RuntimeError):
 
 
 class _Params(C.Structure):
-    _fields_ = [("nx", C.c_int32), ("mode", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("nx", C.c_int32), ("mode", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32),
                 ("L", C.c_double), ("f", C.c_double), ("gH", C.c_double), ("bump", C.c_double)]
 
 
@@ -56,6 +57,7 @@ SIGNATURES = {
     "swrt_bs23_begin": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _dp]),
     "swrt_bs23_attempt": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, _dp]),
     "swrt_bs23_accept": (C.c_int, [C.c_void_p]),
+    "swrt_bs23_interp": (C.c_int, [C.c_void_p, C.c_double, C.c_double] + [_dp] * 4),
     "swrt_hist_omega_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_void_p)]),
     "swrt_ideal_omega_hist": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, C.c_double, _dp, C.c_int,
                                         C.POINTER(C.c_uint64)]),
@@ -117,11 +119,11 @@ def _colmajor(a):
 class Engine:
     """One handle = one CUDA device + device-resident packets + flow stacks."""
 
-    def __init__(self, nx, L, f, gH, mode=MODE_SPECTRAL, device=0, bump=1e-13):
+    def __init__(self, nx, L, f, gH, mode=MODE_SPECTRAL, device=0, bump=1e-13, flags=0):
         self.lib = load_library()
         self.nx, self.L, self.f, self.gH, self.mode, self.device = int(nx), float(L), float(f), float(gH), int(mode), int(device)
         self._h = C.c_void_p()
-        prm = _Params(self.nx, self.mode, self.device, 0, self.L, self.f, self.gH, float(bump))
+        prm = _Params(self.nx, self.mode, self.device, int(flags), self.L, self.f, self.gH, float(bump))
         rc = self.lib.swrt_create(C.byref(prm), C.byref(self._h))
         if rc != 0:
             raise SwrtError(rc, (self.lib.swrt_last_error(None) or b"").decode())
@@ -234,6 +236,12 @@ class Engine:
 
     def bs23_accept(self):
         self._check(self.lib.swrt_bs23_accept(self._h))
+
+    def bs23_interp(self, hstep, s):
+        """ntrp23 dense output of the last attempted step at t + s*hstep -> (x, y, k, l)"""
+        out = [np.empty(self.n) for _ in range(4)]
+        self._check(self.lib.swrt_bs23_interp(self._h, float(hstep), float(s), *[_ptr(o) for o in out]))
+        return tuple(out)
 
     # -- diagnostics --
     def hist_omega(self, edges, kind=HIST_INTRINSIC, alpha=0.0, counts=None):

@@ -253,14 +253,23 @@ def ode23(target, tspan, tmax, rtol=1e-3, atol=1e-6, reduce_max=None):
     The stages run on the device (swrt_bs23_*); this controller is host logic.  The error norm is the
     inf-norm over ALL packets (the reference bundles them in one 4*Np system), so a multi-GPU caller
     passes ``reduce_max`` (an all-reduce MAX over ranks) and every rank takes identical decisions.
-    RHS time dependence: alpha = t/tmax (qgsw_raytrace.m:261).  Returns dict(nsteps, nfailed, nfevals, t)."""
+    RHS time dependence: alpha = t/tmax (qgsw_raytrace.m:261); ``tmax=None`` for a steady flow (one slot).  Returns dict(nsteps, nfailed, nfevals, t).
+
+    A ``tspan`` with more than two entries (SW_zero_background_raytracing.m:73-78) additionally returns
+    ``Y`` (len(tspan), 4, Np): the state at every requested time from the device-side cubic dense output
+    (MATLAB ``ntrp23``, swrt_bs23_interp) -- the steps themselves are chosen exactly as without it."""
     red = reduce_max if reduce_max is not None else (lambda v: v)
-    t0, tfinal = float(tspan[0]), float(tspan[1])
+    al = (lambda tt: tt / tmax) if tmax else (lambda tt: 0.0)       # tmax=None: steady flow, slot 0 only
+    tspan = np.asarray(tspan, dtype=np.float64)
+    t0, tfinal = float(tspan[0]), float(tspan[-1])
+    dense = tspan.size > 2
+    if dense:
+        Y = np.zeros((tspan.size, 4, target.n)); Y[0] = np.stack(target.get_packets()); nxt = 1
     pw = 1.0 / 3.0
     threshold = atol / rtol
     hmax = min(abs(tfinal - t0), abs(0.1 * (tfinal - t0)))
     t = t0
-    rh = red(target.bs23_begin(t / tmax, threshold)) / (0.8 * rtol ** pw)
+    rh = red(target.bs23_begin(al(t), threshold)) / (0.8 * rtol ** pw)
     nfevals = 1
     hmin = 16 * np.spacing(abs(t))            # 16*eps(t)
     absh = min(hmax, abs(tfinal - t0))
@@ -280,7 +289,7 @@ def ode23(target, tspan, tmax, rtol=1e-3, atol=1e-6, reduce_max=None):
         nofailed = True
         while True:
             tnew = tfinal if done else t + h
-            err = absh * red(target.bs23_attempt(h, [(t + 0.5 * h) / tmax, (t + 0.75 * h) / tmax, tnew / tmax], threshold))
+            err = absh * red(target.bs23_attempt(h, [al(t + 0.5 * h), al(t + 0.75 * h), al(tnew)], threshold))
             nfevals += 3
             if not (err <= rtol):            # also catches NaN
                 nfailed += 1
@@ -296,12 +305,19 @@ def ode23(target, tspan, tmax, rtol=1e-3, atol=1e-6, reduce_max=None):
             else:
                 break
         nsteps += 1
+        if dense:
+            while nxt < tspan.size and tnew - tspan[nxt] >= 0:
+                Y[nxt] = np.stack(target.bs23_interp(h, 1.0 if tspan[nxt] == tnew else (tspan[nxt] - t) / h))
+                nxt += 1
         target.bs23_accept()
         if nofailed:
             temp = 1.25 * (err / rtol) ** pw
             absh = absh / temp if temp > 0.2 else 5.0 * absh
         t = tnew
-    return {"nsteps": nsteps, "nfailed": nfailed, "nfevals": nfevals, "t": t}
+    stats = {"nsteps": nsteps, "nfailed": nfailed, "nfevals": nfevals, "t": t}
+    if dense:
+        stats["Y"] = Y
+    return stats
 
 
 def ideal_omega_distribution(scheme, f, Cg, k_0, edges, nangles=100):
