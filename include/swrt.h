@@ -172,6 +172,21 @@ int swrt_qg_get(swrt_qg* q, double* qk_re, double* qk_im);
 int swrt_qg_destroy(swrt_qg* q);
 int swrt_set_flow_from_qg(swrt_handle* h, int slot, swrt_qg* q, double u_mean);
 
+/* ---- on-device TWO-layer QG frame producer (qg2layersw_raytrace.m:120-181, update() :309-323) ------------
+ * q1,q2: layer PV spectra (g2k layout).  The inversion matrix B (:137-143), the linear operator factor_L
+ * (:146-150: shear advection + hyperdiffusion nu*K^(2 alpha) + drag r + beta) and expm(factor_L*dt) live on
+ * the device; the CFL logic that picks dt (:156-165) is host control flow built on swrt_qg2_max_speed.     */
+typedef struct swrt_qg2 swrt_qg2;
+int swrt_qg2_create(int device, int nx, double L, double K_d2, double beta, double shear_strength, double r, double nu,
+                    double alpha, const double* q1_re, const double* q1_im, const double* q2_re, const double* q2_im,
+                    swrt_qg2** out);
+int swrt_qg2_max_speed(swrt_qg2* q, double* U0);   /* sqrt(max(u.^2+v.^2)) of grid_U over both layers (:155-157) */
+int swrt_qg2_step(swrt_qg2* q, double dt);         /* one AB1/AB2/AB3 + integrating-factor step (:166-181)       */
+int swrt_qg2_get(swrt_qg2* q, int layer, double* qk_re, double* qk_im);
+int swrt_qg2_destroy(swrt_qg2* q);
+/* flow slot <- grid_U(qk(:,:,1), ..., shear_strength): top layer, one-layer inversion, mean shear (:187-188)  */
+int swrt_set_flow_from_qg2(swrt_handle* h, int slot, swrt_qg2* q);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* number of kernel launches issued by this handle since creation / since the last reset        */
 int64_t swrt_launch_count(swrt_handle* h, int reset);

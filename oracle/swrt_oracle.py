@@ -998,3 +998,130 @@ def sw_zero_background_driver(q, nx, f, Cg, Nparticles=10, Tend=None, rtol=1e-6,
     err = (omega_abs_history(scheme, sx, sk, f, gH) - Omega_0) / Omega_0
     return {"t_hist": t_hist, "solver_x": sx, "solver_k": sk, "solver_error": err, "U0": U0, "Fr": Fr, "dt": dt, "Nsteps": Nsteps,
             "stats": stats}
+
+
+# --------------------------------------------------------------------------------------------
+# Two-layer QG solver and driver loop of qg2layersw_raytrace.m
+# --------------------------------------------------------------------------------------------
+
+def qg2_operators(kx_, ky_, K_d2, beta, shear_strength, r, nu, alpha):
+    """qg2layersw_raytrace.m:136-150: B (2,2,nkx,nky), factor_L, and its page-wise eigendecomposition
+    ``[LV,LD] = pageeig(factor_L); LV1 = pageinv(LV)`` (numpy.linalg.eig per page; eigenvector scaling and
+    order are arbitrary in both and cancel in V exp(D t) V^-1)."""
+    K2 = kx_ ** 2 + ky_ ** 2
+    F = K_d2 / 2
+    B = np.zeros((2, 2) + K2.shape)
+    B[0, 0] = -F - K2; B[0, 1] = -F; B[1, 0] = -F; B[1, 1] = -F - K2
+    detB = K2 * (K2 + 2 * F)
+    with np.errstate(divide="ignore"):
+        detB = np.where(K2 == 0, np.inf, detB)
+    B = B / detB
+    diffusion_factor = (nu * K2 ** alpha + r) * K2 - 1j * kx_ * beta
+    diffusion_terms = B * diffusion_factor
+    shear_factor = 1j * kx_ * shear_strength
+    M = np.einsum("ij,jkab->ikab", np.array([[-1.0, 0.0], [0.0, 1.0]]), np.eye(2)[:, :, None, None] + 2 * F * B)
+    factor_L = shear_factor * M + diffusion_terms
+    pages = np.moveaxis(factor_L, (0, 1), (2, 3))                      # (nkx, nky, 2, 2)
+    LD, LV = np.linalg.eig(pages)
+    LV1 = np.linalg.inv(LV)
+    return B, factor_L, LV, LD, LV1
+
+
+def qg2_expL(LV, LD, LV1, t):
+    """pagemtimes(pagemtimes(LV, diag_exp(LD, t)), LV1) (:149-150,341-343) -> (2,2,nkx,nky)"""
+    E = np.einsum("abij,abj,abjk->abik", LV, np.exp(t * LD), LV1)
+    return np.moveaxis(E, (2, 3), (0, 1))
+
+
+def mmult3(A, x):
+    """qg2layersw_raytrace.m:333-338: y(:,:,i) = A(i,1,:,:).*x(:,:,1) + A(i,2,:,:).*x(:,:,2); x: (nkx,nky,2)"""
+    return np.stack([A[i, 0] * x[:, :, 0] + A[i, 1] * x[:, :, 1] for i in range(2)], axis=2)
+
+
+def qg2_update(qk, B, kx_, ky_):
+    """qg2layersw_raytrace.m:309-323"""
+    psik = mmult3(B, qk)
+    out = []
+    for i in range(2):
+        psix = k2g(1j * kx_ * psik[:, :, i]); psiy = k2g(1j * ky_ * psik[:, :, i])
+        qx = k2g(1j * kx_ * qk[:, :, i]); qy = k2g(1j * ky_ * qk[:, :, i])
+        out.append(g2k(psix * qy - psiy * qx))
+    return np.stack(out, axis=2)
+
+
+def qg2_max_speed(qk, K_d2, K2, kx_, ky_, shear_strength):
+    """:155-157: grid_U applied to the 3-D qk (one-layer inversion per layer, shear added to u), max speed"""
+    m = 0.0
+    for i in range(2):
+        flow = grid_U(qk[:, :, i], K_d2, K2, kx_, ky_, shear_strength)
+        m = max(m, float((flow["u"] ** 2 + flow["v"] ** 2).max()))
+    return math.sqrt(m)
+
+
+def qg2layersw_driver(nx, Npackets, near_inertial_factor, T_Fr_days, packet_delay_Fr_days, U_g, f, Cg, max_steps, k_max=30,
+                      seed=5, eval_mode="lagrange"):
+    """qg2layersw_raytrace.m:12-196 without the I/O and plotting: returns the state after ``max_steps`` passes of
+    the while loop.  ``eval_mode``: 'lagrange' (interpolate_U, the reference) or 'spectral' (exact trig sum of the
+    same six planes, the oracle of the SPECTRAL product mode)."""
+    L = 20.0
+    dx = L / nx
+    xg = matlab_linspace(-L / 2, L / 2, nx)
+    X, Y = np.meshgrid(xg, xg, indexing="ij")
+    kx_, ky_ = wavenumbers(nx)
+    kx_ = kx_ * (2 * np.pi / L); ky_ = ky_ * (2 * np.pi / L)
+    K2 = kx_ ** 2 + ky_ ** 2
+    rs = matlab_rand_stream(seed)
+    beta = 0.0; K_d2 = f / Cg; shear_strength = 0.5
+    T_Fr = T_Fr_days / f
+    packet_delay_steps = (packet_delay_Fr_days / f) / f
+    CFL_fraction = 0.25; alpha = 4; r = 0.4; nutune = 0.1
+    q1 = initial_q(X, Y, U_g, K_d2, rs, k_min=10, k_max=k_max)
+    qk = np.stack([g2k(q1), g2k(-q1)], axis=2)
+    wf = math.sqrt((near_inertial_factor ** 2 - 1) * f ** 2 / Cg ** 2)
+    i = np.arange(1, Npackets + 1)
+    pk = wf * np.cos(2 * np.pi * i / Npackets); pl = wf * np.sin(2 * np.pi * i / Npackets)
+    rr = rs.rand(Npackets, 2)
+    px, py = L * rr[:, 0] - L / 2, L * rr[:, 1] - L / 2
+    U0 = qg2_max_speed(qk, K_d2, K2, kx_, ky_, shear_strength)
+    Fr = U0 / Cg
+    T = T_Fr / Fr ** 2
+    dt = CFL_fraction * dx / U0
+    nu = nutune * dx ** (2 * alpha)
+    B, _, LV, LD, LV1 = qg2_operators(kx_, ky_, K_d2, beta, shear_strength, r, nu, alpha)
+    expLdt = qg2_expL(LV, LD, LV1, dt); expL2dt = qg2_expL(LV, LD, LV1, 2 * dt)
+    Qm = [np.zeros_like(qk), np.zeros_like(qk)]
+    t = 0.0; step = 0
+    stats = {"packet_steps": 0, "ode23_steps": 0, "ode23_failed": 0, "dt_changes": 0}
+    while t <= T and step < max_steps:
+        step += 1
+        U0 = qg2_max_speed(qk, K_d2, K2, kx_, ky_, shear_strength)
+        CFL_condition = CFL_fraction * dx / U0
+        if CFL_condition < dt or dt < CFL_condition / 4:
+            dt = CFL_fraction / 2 * dx / U0
+            stats["dt_changes"] += 1
+            expLdt = qg2_expL(LV, LD, LV1, dt); expL2dt = qg2_expL(LV, LD, LV1, 2 * dt)
+        prev_qk = qk
+        Qn = qg2_update(qk, B, kx_, ky_)
+        if step == 1:
+            dq = dt * Qn
+        elif step == 2:
+            dq = dt / 2 * (3 * Qn - mmult3(expLdt, Qm[0]))
+        else:
+            dq = dt / 12 * (23 * Qn - 16 * mmult3(expLdt, Qm[0]) + 5 * mmult3(expL2dt, Qm[1]))
+        t = t + dt
+        Qm = [Qn, Qm[0]]
+        qk = mmult3(expLdt, qk + dq)
+        if Npackets > 0 and t > packet_delay_steps:
+            if eval_mode == "lagrange":
+                bf1 = grid_U(prev_qk[:, :, 0], K_d2, K2, kx_, ky_, shear_strength)
+                bf2 = grid_U(qk[:, :, 0], K_d2, K2, kx_, ky_, shear_strength)
+                ode = generate_raytracing_ode(bf1, bf2, Npackets, f, Cg, dt, dx)
+            else:
+                p1 = grid_U_planes_k(prev_qk[:, :, 0], K_d2, K2, kx_, ky_, shear_strength)
+                p2 = grid_U_planes_k(qk[:, :, 0], K_d2, K2, kx_, ky_, shear_strength)
+                ev = lambda x, y, a: spectral_eval_planes(x, y, [(1 - a) * c1 + a * c2 for c1, c2 in zip(p1, p2)], dx, nx)
+                ode = generate_raytracing_ode(None, None, Npackets, f, Cg, dt, dx, eval6=ev)
+            y, st = ode23(ode, [0.0, dt], np.concatenate([px, py, pk, pl]))
+            px, py, pk, pl = (y[j * Npackets:(j + 1) * Npackets] for j in range(4))
+            stats["packet_steps"] += 1; stats["ode23_steps"] += st["nsteps"]; stats["ode23_failed"] += st["nfailed"]
+    return {"qk": qk, "t": t, "dt": dt, "U0": U0, "Fr": Fr, "T": T, "steps": step, "packets": (px, py, pk, pl), **stats}

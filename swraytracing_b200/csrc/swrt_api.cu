@@ -1265,6 +1265,287 @@ int swrt_set_flow_from_qg(swrt_handle* h, int slot, swrt_qg* q, double u_mean) {
 
 }  // extern "C"
 
+// ================================================================================================
+// On-device TWO-layer QG frame producer: qg2layersw_raytrace.m:120-181 (inversion matrix B, linear
+// operator factor_L and its exponentials, AB3 with integrating factor) and :309-323 (update()).
+// MATLAB builds exp(L dt) as V exp(D dt) V^-1 from pageeig (:147-150); the 2x2 matrix exponential is
+// evaluated here in closed form (the same matrix; pageeig is a proprietary builtin -> parity unpinned).
+// ================================================================================================
+namespace {
+struct c2 { double x, y; };
+__device__ __forceinline__ c2 cmul(c2 a, c2 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ c2 cadd(c2 a, c2 b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ c2 csub(c2 a, c2 b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ c2 cscale(c2 a, double r) { return {a.x * r, a.y * r}; }
+__device__ __forceinline__ c2 csqrt2(c2 z) {
+    const double m = hypot(z.x, z.y);
+    if (m == 0.0) return {0.0, 0.0};
+    double re = sqrt(0.5 * (m + fabs(z.x)));
+    double im = 0.5 * z.y / re;
+    if (z.x < 0.0) { const double t = re; re = fabs(im); im = copysign(t, z.y); }
+    return {re, im};
+}
+__device__ __forceinline__ c2 cexp2(c2 z) { const double e = exp(z.x); double s, c; sincos(z.y, &s, &c); return {e * c, e * s}; }
+// exp(t*M) for the 2x2 complex M = [a b; c d]:  e^{ts} [cosh(t D) I + sinh(t D)/D (M - s I)],  s = (a+d)/2, D^2 = ((a-d)/2)^2 + bc
+__device__ void expm2(c2 a, c2 b, c2 c, c2 d, double t, c2 out[4]) {
+    const c2 s = cscale(cadd(a, d), 0.5), p = cscale(csub(a, d), 0.5);
+    const c2 D2 = cadd(cmul(p, p), cmul(b, c));
+    const c2 D = csqrt2(D2);
+    const c2 tD = cscale(D, t);
+    c2 ch, shc;                                  // cosh(tD), sinh(tD)/D
+    if (hypot(tD.x, tD.y) < 1e-4) {              // series: cosh z = 1 + z^2/2 + z^4/24, sinh z / z = 1 + z^2/6 + z^4/120
+        const c2 z2 = cmul(tD, tD), z4 = cmul(z2, z2);
+        ch = cadd(cadd({1.0, 0.0}, cscale(z2, 0.5)), cscale(z4, 1.0 / 24.0));
+        shc = cscale(cadd(cadd({1.0, 0.0}, cscale(z2, 1.0 / 6.0)), cscale(z4, 1.0 / 120.0)), t);
+    } else {
+        const c2 ep = cexp2(tD), em = cexp2({-tD.x, -tD.y});
+        ch = cscale(cadd(ep, em), 0.5);
+        const c2 sh = cscale(csub(ep, em), 0.5);
+        const double n2 = D.x * D.x + D.y * D.y;
+        shc = cmul(sh, {D.x / n2, -D.y / n2});
+    }
+    const c2 es = cexp2(cscale(s, t));
+    out[0] = cmul(es, cadd(ch, cmul(shc, p)));
+    out[1] = cmul(es, cmul(shc, b));
+    out[2] = cmul(es, cmul(shc, c));
+    out[3] = cmul(es, csub(ch, cmul(shc, p)));
+}
+struct Qg2Par { int nkx, nky; double kappa, K_d2, beta, shear, r, nu, alpha; };
+__device__ __forceinline__ void qg2_B(const Qg2Par& P, double K2, double& B11, double& B12) {
+    // B = [-F-K2, -F; -F, -F-K2] ./ detB, detB = K2.*(K2+2F), detB(K2==0) = Inf  (:137-143)
+    const double F = 0.5 * P.K_d2;
+    if (K2 == 0.0) { B11 = 0.0; B12 = 0.0; return; }
+    const double det = K2 * (K2 + 2.0 * F);
+    B11 = (-F - K2) / det; B12 = -F / det;
+}
+// expLdt = expm(factor_L*dt), expL2dt = expm(factor_L*2dt); factor_L = mean_flow_terms + diffusion_terms (:146-153)
+__global__ void qg2_expl_kernel(Qg2Par P, double dt, double2* E1, double2* E2) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nh = P.nkx * P.nky;
+    if (idx >= nh) return;
+    const int kmax = (P.nkx - 1) / 2;
+    const double kx = P.kappa * (double)(idx % P.nkx - kmax), ky = P.kappa * (double)(idx / P.nkx);
+    const double K2 = kx * kx + ky * ky, F = 0.5 * P.K_d2;
+    double B11, B12; qg2_B(P, K2, B11, B12);
+    const c2 dfac = {(P.nu * pow(K2, P.alpha) + P.r) * K2, -kx * P.beta};       // (nu K2^alpha + r) K2 - i kx beta
+    const c2 sh = {0.0, kx * P.shear};                                              // i kx shear
+    // [-1 0; 0 1] * (I + 2F B) = [-(1+2F B11), -2F B12; 2F B12, 1+2F B11]
+    const double m11 = -(1.0 + 2.0 * F * B11), m12 = -2.0 * F * B12, m21 = 2.0 * F * B12, m22 = 1.0 + 2.0 * F * B11;
+    const c2 a = cadd(cscale(sh, m11), cscale(dfac, B11)), b = cadd(cscale(sh, m12), cscale(dfac, B12));
+    const c2 c = cadd(cscale(sh, m21), cscale(dfac, B12)), d = cadd(cscale(sh, m22), cscale(dfac, B11));
+    c2 o[4];
+    expm2(a, b, c, d, dt, o);
+    for (int j = 0; j < 4; j++) E1[(size_t)j * nh + idx] = make_double2(o[j].x, o[j].y);
+    expm2(a, b, c, d, 2.0 * dt, o);
+    for (int j = 0; j < 4; j++) E2[(size_t)j * nh + idx] = make_double2(o[j].x, o[j].y);
+}
+// update(), spectral half (:310-314): psik = mmult3(B, qk); i kx/i ky multiples of psik and qk for BOTH layers
+__global__ void qg2_spec_kernel(Qg2Par P, const double2* __restrict__ q1, const double2* __restrict__ q2, double2* const* s) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P.nkx * P.nky) return;
+    const int kmax = (P.nkx - 1) / 2;
+    const double kx = P.kappa * (double)(idx % P.nkx - kmax), ky = P.kappa * (double)(idx / P.nkx);
+    double B11, B12; qg2_B(P, kx * kx + ky * ky, B11, B12);
+    const double2 a = q1[idx], b = q2[idx];
+    const double2 p1 = make_double2(B11 * a.x + B12 * b.x, B11 * a.y + B12 * b.y);
+    const double2 p2 = make_double2(B12 * a.x + B11 * b.x, B12 * a.y + B11 * b.y);
+    const double2 ps[2] = {p1, p2}, qs[2] = {a, b};
+    for (int l = 0; l < 2; l++) {
+        s[4 * l + 0][idx] = make_double2(-kx * ps[l].y, kx * ps[l].x);
+        s[4 * l + 1][idx] = make_double2(-ky * ps[l].y, ky * ps[l].x);
+        s[4 * l + 2][idx] = make_double2(-kx * qs[l].y, kx * qs[l].x);
+        s[4 * l + 3][idx] = make_double2(-ky * qs[l].y, ky * qs[l].x);
+    }
+}
+__device__ __forceinline__ double2 mm(const double2* E, size_t nh, int row, int idx, double2 x1, double2 x2) {
+    const double2 e1 = E[(size_t)(2 * row) * nh + idx], e2 = E[(size_t)(2 * row + 1) * nh + idx];      // mmult3 (:333-338)
+    return make_double2(e1.x * x1.x - e1.y * x1.y + e2.x * x2.x - e2.y * x2.y, e1.x * x1.y + e1.y * x1.x + e2.x * x2.y + e2.y * x2.x);
+}
+// AB1/AB2/AB3 with integrating factor (:167-181): dq, history rotation, qk = expLdt*(qk + dq)
+__global__ void qg2_ab_kernel(int nh, int order, double dt, const double2* __restrict__ E1, const double2* __restrict__ E2,
+                              double2* q1, double2* q2, const double2* Qn1, const double2* Qn2, double2* A1, double2* A2,
+                              double2* C1, double2* C2) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nh) return;
+    const double2 n1 = Qn1[idx], n2 = Qn2[idx], a1 = A1[idx], a2 = A2[idx], c1 = C1[idx], c2v = C2[idx];
+    double2 d1, d2;
+    if (order == 1) { d1 = make_double2(dt * n1.x, dt * n1.y); d2 = make_double2(dt * n2.x, dt * n2.y); }
+    else {
+        const double2 ea1 = mm(E1, nh, 0, idx, a1, a2), ea2 = mm(E1, nh, 1, idx, a1, a2);
+        if (order == 2) {
+            d1 = make_double2(dt / 2 * (3 * n1.x - ea1.x), dt / 2 * (3 * n1.y - ea1.y));
+            d2 = make_double2(dt / 2 * (3 * n2.x - ea2.x), dt / 2 * (3 * n2.y - ea2.y));
+        } else {
+            const double2 ec1 = mm(E2, nh, 0, idx, c1, c2v), ec2 = mm(E2, nh, 1, idx, c1, c2v);
+            d1 = make_double2(dt / 12 * (23 * n1.x - 16 * ea1.x + 5 * ec1.x), dt / 12 * (23 * n1.y - 16 * ea1.y + 5 * ec1.y));
+            d2 = make_double2(dt / 12 * (23 * n2.x - 16 * ea2.x + 5 * ec2.x), dt / 12 * (23 * n2.y - 16 * ea2.y + 5 * ec2.y));
+        }
+    }
+    C1[idx] = a1; C2[idx] = a2; A1[idx] = n1; A2[idx] = n2;
+    const double2 y1 = make_double2(q1[idx].x + d1.x, q1[idx].y + d1.y), y2 = make_double2(q2[idx].x + d2.x, q2[idx].y + d2.y);
+    q1[idx] = mm(E1, nh, 0, idx, y1, y2);
+    q2[idx] = mm(E1, nh, 1, idx, y1, y2);
+}
+// grid_U.m:2-4 for one layer: uk = -i ky psik, vk = i kx psik with psik = -qk./(K_d2 + K2)  (the ONE-layer inversion,
+// which is what qg2layersw_raytrace.m:155,187-188 applies to each layer)
+__global__ void qg2_uv_kernel(Qg2Par P, const double2* __restrict__ q, double2* uk, double2* vk) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P.nkx * P.nky) return;
+    const int kmax = (P.nkx - 1) / 2;
+    const double kx = P.kappa * (double)(idx % P.nkx - kmax), ky = P.kappa * (double)(idx / P.nkx);
+    const double d = P.K_d2 + (kx * kx + ky * ky);
+    const double2 psi = make_double2(-q[idx].x / d, -q[idx].y / d);
+    uk[idx] = make_double2(ky * psi.y, -ky * psi.x);
+    vk[idx] = make_double2(-kx * psi.y, kx * psi.x);
+}
+__global__ void qg2_speed_kernel(const double* u, const double* v, double shear, size_t n, unsigned long long* out) {
+    double m = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double uu = u[i] + shear, s2 = uu * uu + v[i] * v[i];
+        m = (s2 > m || s2 != s2) ? s2 : m;
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = m; __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) { double o = sh[threadIdx.x + s], w = sh[threadIdx.x]; sh[threadIdx.x] = (o > w || o != o) ? o : w; } __syncthreads(); }
+    if (threadIdx.x == 0) { double w = sh[0]; if (w != w) w = __longlong_as_double(0x7ff0000000000000LL); atomicMax(out, (unsigned long long)__double_as_longlong(w)); }
+}
+}  // namespace
+
+struct swrt_qg2 {
+    int device = 0, nx = 0;
+    double L = 0;
+    Qg2Par par{};
+    double dt_cached = -1.0;
+    long long step = 0;
+    cudaStream_t stream = nullptr;
+    FftWork fft;
+    double2 *q[2] = {}, *Qn[2] = {}, *Qm1[2] = {}, *Qm2[2] = {}, *s[8] = {}, *E1 = nullptr, *E2 = nullptr, *psi = nullptr;
+    double2** s_dev = nullptr;
+    double* g[5] = {};
+    unsigned long long* red = nullptr;
+    std::string err;
+};
+
+extern "C" {
+
+int swrt_qg2_create(int device, int nx, double L, double K_d2, double beta, double shear_strength, double r, double nu, double alpha,
+                    const double* q1_re, const double* q1_im, const double* q2_re, const double* q2_im, swrt_qg2** out) {
+    if (!out || !q1_re || !q1_im || !q2_re || !q2_im || nx < 8 || (nx & 1) || !(L > 0)) return fail(nullptr, SWRT_ERR_ARG, "swrt_qg2_create: bad argument");
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_qg2_create: no CUDA device; libswrt has no CPU path"); }
+    swrt_qg2* q = new (std::nothrow) swrt_qg2();
+    if (!q) return fail(nullptr, SWRT_ERR_ALLOC, "out of host memory");
+    q->device = device; q->nx = nx; q->L = L;
+    q->par = Qg2Par{nx - 1, nx / 2, 2.0 * M_PI / L, K_d2, beta, shear_strength, r, nu, alpha};
+    const size_t nh = (size_t)(nx - 1) * (nx / 2), ng = (size_t)nx * nx;
+    bool ok = cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) == cudaSuccess && q->fft.init(nx, q->stream, q->err) == SWRT_OK;
+    std::vector<double2**> cplx;
+    for (int l = 0; l < 2; l++) { cplx.push_back(&q->q[l]); cplx.push_back(&q->Qn[l]); cplx.push_back(&q->Qm1[l]); cplx.push_back(&q->Qm2[l]); }
+    for (auto& p : q->s) cplx.push_back(&p);
+    cplx.push_back(&q->psi);
+    for (auto p : cplx) ok = ok && cudaMalloc(p, nh * sizeof(double2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&q->E1, 4 * nh * sizeof(double2)) == cudaSuccess && cudaMalloc(&q->E2, 4 * nh * sizeof(double2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&q->s_dev, 8 * sizeof(double2*)) == cudaSuccess && cudaMalloc(&q->red, sizeof(unsigned long long)) == cudaSuccess;
+    for (auto& p : q->g) ok = ok && cudaMalloc(&p, ng * sizeof(double)) == cudaSuccess;
+    if (!ok) { swrt_qg2_destroy(q); return fail(nullptr, SWRT_ERR_ALLOC, "swrt_qg2_create: allocation failed"); }
+    cudaMemcpy(q->s_dev, q->s, 8 * sizeof(double2*), cudaMemcpyHostToDevice);
+    std::vector<double2> hq(nh);
+    const double* re[2] = {q1_re, q2_re}; const double* im[2] = {q1_im, q2_im};
+    for (int l = 0; l < 2; l++) {
+        for (size_t i = 0; i < nh; i++) hq[i] = make_double2(re[l][i], im[l][i]);
+        cudaMemcpy(q->q[l], hq.data(), nh * sizeof(double2), cudaMemcpyHostToDevice);
+        cudaMemset(q->Qm1[l], 0, nh * sizeof(double2)); cudaMemset(q->Qm2[l], 0, nh * sizeof(double2));
+    }
+    *out = q;
+    return SWRT_OK;
+}
+
+int swrt_qg2_destroy(swrt_qg2* q) {
+    if (!q) return SWRT_OK;
+    cudaSetDevice(q->device);
+    if (q->stream) cudaStreamSynchronize(q->stream);
+    for (int l = 0; l < 2; l++) { cudaFree(q->q[l]); cudaFree(q->Qn[l]); cudaFree(q->Qm1[l]); cudaFree(q->Qm2[l]); }
+    for (auto p : q->s) cudaFree(p);
+    cudaFree(q->psi); cudaFree(q->E1); cudaFree(q->E2); cudaFree(q->s_dev); cudaFree(q->red);
+    for (auto p : q->g) cudaFree(p);
+    if (q->stream) cudaStreamDestroy(q->stream);
+    delete q;
+    return SWRT_OK;
+}
+
+// U0 = sqrt(max(flow.u.^2 + flow.v.^2)) over BOTH layers of grid_U(qk, ..., shear) (qg2layersw_raytrace.m:69-71,155-157)
+int swrt_qg2_max_speed(swrt_qg2* q, double* U0) {
+    if (!q || !U0) return SWRT_ERR_ARG;
+    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
+    const int nh = q->par.nkx * q->par.nky;
+    const size_t ng = (size_t)q->nx * q->nx;
+    cudaMemsetAsync(q->red, 0, sizeof(unsigned long long), q->stream);
+    for (int l = 0; l < 2; l++) {
+        qg2_uv_kernel<<<(nh + 255) / 256, 256, 0, q->stream>>>(q->par, q->q[l], q->s[0], q->s[1]);
+        if (k2g_dev(q->fft, q->s[0], q->g[0], q->stream, q->err) || k2g_dev(q->fft, q->s[1], q->g[1], q->stream, q->err)) return SWRT_ERR_CUDA;
+        qg2_speed_kernel<<<296, 256, 0, q->stream>>>(q->g[0], q->g[1], q->par.shear, ng, q->red);
+    }
+    unsigned long long bits = 0;
+    if (cudaMemcpyAsync(&bits, q->red, sizeof bits, cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
+        cudaStreamSynchronize(q->stream) != cudaSuccess) { q->err = "swrt_qg2_max_speed: CUDA failure"; return SWRT_ERR_CUDA; }
+    double s2; memcpy(&s2, &bits, sizeof s2);
+    *U0 = sqrt(s2);
+    return SWRT_OK;
+}
+
+// one step of the while-loop body (:166-181) with the caller's dt (the CFL logic of :156-165 is host control flow)
+int swrt_qg2_step(swrt_qg2* q, double dt) {
+    if (!q || !(dt > 0)) return SWRT_ERR_ARG;
+    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
+    const int nh = q->par.nkx * q->par.nky;
+    const size_t ng = (size_t)q->nx * q->nx;
+    const int bs = 256, gb = (nh + bs - 1) / bs;
+    if (dt != q->dt_cached) {
+        qg2_expl_kernel<<<gb, bs, 0, q->stream>>>(q->par, dt, q->E1, q->E2);
+        q->dt_cached = dt;
+    }
+    qg2_spec_kernel<<<gb, bs, 0, q->stream>>>(q->par, q->q[0], q->q[1], q->s_dev);
+    for (int l = 0; l < 2; l++) {
+        for (int c = 0; c < 4; c++)
+            if (k2g_dev(q->fft, q->s[4 * l + c], q->g[c], q->stream, q->err)) return SWRT_ERR_CUDA;
+        qg_jacobian_kernel<<<(unsigned)((ng + bs - 1) / bs), bs, 0, q->stream>>>(q->g[0], q->g[1], q->g[2], q->g[3], q->g[4], ng);
+        if (g2k_dev(q->fft, q->g[4], q->Qn[l], q->stream, q->err)) return SWRT_ERR_CUDA;
+    }
+    const int order = q->step == 0 ? 1 : (q->step == 1 ? 2 : 3);
+    qg2_ab_kernel<<<gb, bs, 0, q->stream>>>(nh, order, dt, q->E1, q->E2, q->q[0], q->q[1], q->Qn[0], q->Qn[1], q->Qm1[0], q->Qm1[1],
+                                           q->Qm2[0], q->Qm2[1]);
+    q->step++;
+    cudaError_t e = cudaStreamSynchronize(q->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { q->err = cudaGetErrorString(e); return SWRT_ERR_CUDA; }
+    return SWRT_OK;
+}
+
+int swrt_qg2_get(swrt_qg2* q, int layer, double* qk_re, double* qk_im) {
+    if (!q || !qk_re || !qk_im || layer < 0 || layer > 1) return SWRT_ERR_ARG;
+    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
+    const size_t nh = (size_t)(q->nx - 1) * (q->nx / 2);
+    std::vector<double2> hq(nh);
+    if (cudaMemcpy(hq.data(), q->q[layer], nh * sizeof(double2), cudaMemcpyDeviceToHost) != cudaSuccess) return SWRT_ERR_CUDA;
+    for (size_t i = 0; i < nh; i++) { qk_re[i] = hq[i].x; qk_im[i] = hq[i].y; }
+    return SWRT_OK;
+}
+
+// flow slot <- grid_U(qk(:,:,1), K_d2, K2, kx_, ky_, shear) of the TOP layer (:187-188), entirely on the device
+int swrt_set_flow_from_qg2(swrt_handle* h, int slot, swrt_qg2* q) {
+    if (!h || !q) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
+    REQUIRE(h, q->nx == h->p.nx && q->device == h->p.device && q->L == h->p.L, SWRT_ERR_ARG, "QG state and handle differ in nx / L / device");
+    const int nkx = q->nx - 1, nky = q->nx / 2, nh = nkx * nky;
+    CU(h, cudaStreamSynchronize(q->stream));
+    qg_psi_kernel<<<(nh + 255) / 256, 256, 0, h->stream>>>(q->q[0], nkx, nky, 2.0 * M_PI / q->L, q->par.K_d2, q->psi);
+    h->launches++;
+    return set_flow_spectral_dev(h, slot, q->psi, q->par.shear);
+}
+
+}  // extern "C"
+
 extern "C" {
 
 // ---- instrumentation --------------------------------------------------------------------------

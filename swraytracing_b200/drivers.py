@@ -17,7 +17,7 @@ import time
 import numpy as np
 
 from . import fieldio
-from .engine import (Engine, QGFlow, MODE_SPECTRAL, SCHEME_LEAPFROG, SCHEME_RK4_PACKET, SCHEME_RK4_XKA, k2g_dev,
+from .engine import (Engine, QGFlow, QG2Flow, MODE_SPECTRAL, SCHEME_LEAPFROG, SCHEME_RK4_PACKET, SCHEME_RK4_XKA, k2g_dev,
                      g2k_dev)
 from .reference_api import ode23
 
@@ -95,7 +95,7 @@ def qgsw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_delay_da
     log("Deformation wavenumber: %f" % K_d2)
 
     writer = fieldio.PacketFrameWriter(outdir, L)
-    writer.write(px, py, pk, pl, dt * (packet_step_start - 1))         # initial positions, :103-106
+    writer.write(px, py, pk, pl, dt * (packet_step_start - 1), wrap=False)   # initial positions as drawn, :103-106
     fieldio.write_field(q, f"{outdir}/pv", 1); fieldio.write_field(0.0, f"{outdir}/pv_time", 1)
 
     qg = QGFlow(nx, L, qk, K_d2, dt, f, Cg, beta=beta, r_drag=r_drag, force_strength=force_strength, device=device)
@@ -369,3 +369,100 @@ def raytrace_sw(S, f, Cg, *, np_=10, nsteps=None, save_stride=1, mode=None, seed
     omega = np.sqrt(f ** 2 + gH0 * Hp * K2)
     return {"P": P, "t": dt * cols, "omega": omega, "Cmag": gH0 * Hp * np.sqrt(K2) / omega, "K": np.sqrt(K2), "U": U, "GradU": GradU,
             "H": H, "U0": U0, "Fr": Fr, "dt": dt, "nsteps": int(nsteps)}
+
+
+
+def initial_q_2layer(X, Y, a_g, K_d2, rs, k_min=10, k_max=30, ring=False):
+    """qg2layersw_raytrace.m:250-273: the same random-phase sum as the one-layer driver with k_max = 30 (and the
+    same always-true chained comparison on :262)."""
+    return initial_q(X, Y, a_g, K_d2, rs, k_min=k_min, k_max=k_max, ring=ring)
+
+
+def qg2layersw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_delay_Fr_days, U_g, f, Cg, *, outdir="data",
+                        mode=MODE_SPECTRAL, max_steps=None, seed=5, device=0, log=print, k_max=30, integrator="ode23",
+                        leapfrog_substeps=4):
+    """qg_flow_ray_trace/qg2layersw_raytrace.m:1-247 (BASELINE config 4) on the device: two-layer QG with mean shear on
+    L = 20, adaptive dt (:156-165), AB3 + integrating factor, packets advected through the TOP layer's
+    ``grid_U`` frames (:187-196) by ode23 over [0, dt], packet frames every 25 steps.  ``k_max`` (30 in the reference)
+    and ``max_steps`` exist for tests."""
+    L = 20.0
+    dx = L / nx
+    xg = np.linspace(-L / 2, L / 2, nx)
+    X, Y = np.meshgrid(xg, xg, indexing="ij")                          # ndgrid (:16)
+    rs = np.random.RandomState(seed)                                   # rng(5)
+    beta = 0.0
+    K_d2 = f / Cg
+    shear_strength = 0.5
+    T_Fr = T_Fr_days / f
+    packet_delay_Fr = packet_delay_Fr_days / f
+    CFL_fraction = 0.25
+    alpha = 4; r = 0.4; nutune = 0.1
+    steps_per_save = 10
+    packet_delay_steps = packet_delay_Fr / f
+    packet_steps_per_save = 25
+
+    q1 = initial_q_2layer(X, Y, U_g, K_d2, rs, k_max=k_max)
+    q1k = g2k_dev(q1, device)
+    wavenumber_factor = math.sqrt((near_inertial_factor ** 2 - 1) * f ** 2 / Cg ** 2)
+    i = np.arange(1, Npackets + 1)
+    pk = wavenumber_factor * np.cos(2 * np.pi * i / Npackets)
+    pl = wavenumber_factor * np.sin(2 * np.pi * i / Npackets)
+    rr = rs.rand(Npackets, 2)
+    px, py = L * rr[:, 0] - L / 2, L * rr[:, 1] - L / 2
+
+    nu = nutune * dx ** (2 * alpha)
+    qg = QG2Flow(nx, L, q1k, -q1k, K_d2, beta, shear_strength, r, nu, alpha, device)      # q2 = -q1 (:57)
+    U0 = qg.max_speed()
+    Fr = U0 / Cg
+    T = T_Fr / Fr ** 2
+    dt = CFL_fraction * dx / U0
+    Nsteps = int(math.ceil(T / dt))
+    packet_step_start = int(math.ceil(packet_delay_steps / dt))
+
+    log("Resolution: %dx%d" % (nx, nx)); log("Number of packets: %d" % Npackets)
+    log("Initial wavenumber radius: %f" % (near_inertial_factor * f)); log("Initial time step: %f" % dt)
+    log("Simulation time: %f" % T); log("Spin-up time: %f" % packet_delay_steps)
+    log("Steps per save: %d" % steps_per_save); log("Steps per packet save: %d" % packet_steps_per_save)
+    log("Coriolis parameter: %f" % f); log("Group velocity: %f" % Cg)
+    log("Background velocity (parameter,computed): (%f,%f)" % (U_g, U0)); log("Froude Number: %f" % Fr)
+    log("Deformation wavenumber: %f" % K_d2)
+
+    writer = fieldio.PacketFrameWriter(outdir, L)
+    writer.write(px, py, pk, pl, dt * (packet_step_start - 1), wrap=False)            # :114-116 (unwrapped initial frame)
+    fieldio.write_field(np.stack([q1, -q1], axis=2), f"{outdir}/pv", 1); fieldio.write_field(0.0, f"{outdir}/pv_time", 1)
+
+    eng = Engine(nx, L, f, Cg ** 2, mode, device)
+    eng.set_packets(px, py, pk, pl)
+    t = 0.0
+    step = 0
+    tic = time.time()
+    stats = {"packet_steps": 0, "ode23_steps": 0, "ode23_failed": 0, "dt_changes": 0}
+    while t <= T and (max_steps is None or step < max_steps):
+        step += 1
+        U0 = qg.max_speed()
+        CFL_condition = CFL_fraction * dx / U0
+        if CFL_condition < dt or dt < CFL_condition / 4:
+            dt = CFL_fraction / 2 * dx / U0
+            stats["dt_changes"] += 1
+            log("CFL condition not met, max|u|=%f, new dt=%f" % (U0, dt))
+        advect = Npackets > 0 and t + dt > packet_delay_steps
+        if advect:
+            qg.to_flow(eng, 0)                                         # background_flow1 = grid_U(prev_qk(:,:,:,1)), :187
+        qg.step(dt)
+        t = t + dt
+        if advect:
+            qg.to_flow(eng, 1)                                         # background_flow2 = grid_U(qk(:,:,:,1)), :188
+            if integrator == "ode23":
+                st = ode23(eng, [0.0, dt], dt)
+                stats["ode23_steps"] += st["nsteps"]; stats["ode23_failed"] += st["nfailed"]
+            else:
+                m = leapfrog_substeps
+                eng.step(SCHEME_LEAPFROG, dt / m, m, 0.5 / m, 1.0 / m)
+            stats["packet_steps"] += 1
+            if (step - packet_step_start + 1) % packet_steps_per_save == 0:
+                writer.write(*eng.get_packets(), t)
+    log("Real time elapsed: %.3f seconds" % (time.time() - tic))
+    out = {"dt": dt, "Nsteps": Nsteps, "steps": step, "U0": U0, "Fr": Fr, "t": t, "T": T, "packets": eng.get_packets(),
+           "qk": (qg.get(0), qg.get(1)), **stats, "packet_frames": writer.frames}
+    qg.close(); eng.close()
+    return out

@@ -70,6 +70,12 @@ SIGNATURES = {
     "swrt_qg_get": (C.c_int, [C.c_void_p, _dp, _dp]),
     "swrt_qg_destroy": (C.c_int, [C.c_void_p]),
     "swrt_set_flow_from_qg": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double]),
+    "swrt_qg2_create": (C.c_int, [C.c_int, C.c_int] + [C.c_double] * 7 + [_dp] * 4 + [C.POINTER(C.c_void_p)]),
+    "swrt_qg2_max_speed": (C.c_int, [C.c_void_p, _dp]),
+    "swrt_qg2_step": (C.c_int, [C.c_void_p, C.c_double]),
+    "swrt_qg2_get": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "swrt_qg2_destroy": (C.c_int, [C.c_void_p]),
+    "swrt_set_flow_from_qg2": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "swrt_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "swrt_last_kernel_ms": (C.c_double, [C.c_void_p, C.POINTER(C.c_int)]),
     "swrt_work_per_eval": (C.c_double, [C.c_void_p, C.c_int]),
@@ -346,6 +352,57 @@ class QGFlow:
     def close(self):
         if getattr(self, "_q", None) and self._q.value:
             self.lib.swrt_qg_destroy(self._q)
+            self._q = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class QG2Flow:
+    """On-device two-layer QG solver (qg2layersw_raytrace.m:120-181, :309-323): both layer PV spectra, the
+    inversion matrix B and expm(factor_L*dt) live on the GPU; ``to_flow`` fills a flow slot with
+    ``grid_U(qk(:,:,1), ..., shear_strength)`` of the top layer without a host copy."""
+
+    def __init__(self, nx, L, q1k, q2k, K_d2, beta, shear_strength, r, nu, alpha, device=0):
+        self.lib = load_library()
+        self.nx, self.L = int(nx), float(L)
+        parts = []
+        for qk in (q1k, q2k):
+            qk = np.asarray(qk, dtype=np.complex128)
+            parts += [_colmajor(qk.real), _colmajor(qk.imag)]
+        self._q = C.c_void_p()
+        rc = self.lib.swrt_qg2_create(int(device), self.nx, self.L, float(K_d2), float(beta), float(shear_strength), float(r),
+                                      float(nu), float(alpha), *[_ptr(a) for a in parts], C.byref(self._q))
+        if rc != 0:
+            raise SwrtError(rc, (self.lib.swrt_last_error(None) or b"").decode())
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SwrtError(rc, f"{what} failed")
+
+    def max_speed(self):
+        out = C.c_double(0.0)
+        self._check(self.lib.swrt_qg2_max_speed(self._q, C.byref(out)), "swrt_qg2_max_speed")
+        return out.value
+
+    def step(self, dt):
+        self._check(self.lib.swrt_qg2_step(self._q, float(dt)), "swrt_qg2_step")
+
+    def get(self, layer):
+        nkx, nky = self.nx - 1, self.nx // 2
+        re = np.empty(nkx * nky); im = np.empty(nkx * nky)
+        self._check(self.lib.swrt_qg2_get(self._q, int(layer), _ptr(re), _ptr(im)), "swrt_qg2_get")
+        return (re + 1j * im).reshape((nkx, nky), order="F")
+
+    def to_flow(self, engine, slot=0):
+        engine._check(self.lib.swrt_set_flow_from_qg2(engine._h, int(slot), self._q))
+
+    def close(self):
+        if getattr(self, "_q", None) and self._q.value:
+            self.lib.swrt_qg2_destroy(self._q)
             self._q = C.c_void_p()
 
     def __del__(self):

@@ -65,9 +65,13 @@ class PacketFrameWriter:
         self.dir = Path(directory); self.dir.mkdir(parents=True, exist_ok=True)
         self.L = float(L); self.prefix = prefix; self.frames = 0
 
-    def write(self, x, y, k, l, t):
+    def write(self, x, y, k, l, t, wrap=True):
+        """``wrap=False`` for the initial frame, which the drivers write as drawn (qgsw_raytrace.m:104)"""
         L = self.L
-        px = np.stack([np.mod(np.asarray(x) + L / 2, L) - L / 2, np.mod(np.asarray(y) + L / 2, L) - L / 2], axis=1)
+        if wrap:
+            px = np.stack([np.mod(np.asarray(x) + L / 2, L) - L / 2, np.mod(np.asarray(y) + L / 2, L) - L / 2], axis=1)
+        else:
+            px = np.stack([np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)], axis=1)
         self.frames += 1
         write_field(px, self.dir / f"{self.prefix}_x", self.frames)
         write_field(np.stack([k, l], axis=1), self.dir / f"{self.prefix}_k", self.frames)

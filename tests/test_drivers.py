@@ -214,3 +214,92 @@ def test_SW_zero_background_true_zero_flow_is_analytic():
         assert np.abs(got["solver_x"][j] - (x0 + 4.0 * k0 / w * t)).max() < 1e-13
     with pytest.raises(ValueError):
         drivers.SW_zero_background_raytracing(np.zeros((nx, nx)), nx=nx, f=3.0, Cg=1.0)   # Tend = 1/(f Fr^2) is infinite
+
+
+# ------------------------------------------------------------------------------------------------
+# config 4: qg2layersw_raytrace.m (two-layer QG + packets through the top layer)
+# ------------------------------------------------------------------------------------------------
+def _qg2_setup(nx=32, L=20.0):
+    kx_, ky_ = O.wavenumbers(nx)
+    kap = 2 * np.pi / L
+    return kx_ * kap, ky_ * kap
+
+
+def test_qg2_inversion_matrix_and_exponential():
+    """B is the inverse of the two-layer PV operator [-K2-F, F; F, -K2-F] (F = K_d2/2), zero at K = 0; the
+    eig-based exp(L t) of the restatement equals scipy's expm"""
+    from scipy.linalg import expm
+    kx_, ky_ = _qg2_setup()
+    K2 = kx_ ** 2 + ky_ ** 2
+    B, FL, LV, LD, LV1 = O.qg2_operators(kx_, ky_, 3.0, 0.0, 0.5, 0.4, 0.1 * (20 / 32) ** 8, 4)
+    F = 1.5
+    for a, b in ((3, 2), (15, 0), (20, 7), (30, 15)):
+        A = np.array([[-K2[a, b] - F, F], [F, -K2[a, b] - F]])
+        want = np.zeros((2, 2)) if K2[a, b] == 0 else np.eye(2)
+        assert np.allclose(B[:, :, a, b] @ A, want, atol=1e-13)
+    E = O.qg2_expL(LV, LD, LV1, 0.05)
+    for a in range(0, 31, 5):
+        for b in range(0, 16, 3):
+            assert np.abs(E[:, :, a, b] - expm(0.05 * FL[:, :, a, b])).max() < 1e-13
+    assert np.abs(E[:, :, 15, 0] - np.eye(2)).max() == 0.0       # K = 0: factor_L = 0
+
+
+def test_qg2_restated_driver_runs_and_changes_dt():
+    r = O.qg2layersw_driver(32, 8, 2, 30.0, 0.0, 0.3, 3.0, 1.0, max_steps=4, k_max=6)
+    assert r["steps"] == 4 and r["packet_steps"] == 4 and r["ode23_failed"] == 0
+    assert np.all(np.isfinite(r["packets"][0])) and np.isfinite(np.abs(r["qk"]).max())
+
+
+@pytest.mark.gpu
+def test_qg2_device_steps_match_restatement():
+    from swraytracing_b200.engine import QG2Flow
+    nx, L = 32, 20.0
+    kx_, ky_ = _qg2_setup(nx, L)
+    K2 = kx_ ** 2 + ky_ ** 2
+    x = O.matlab_linspace(-L / 2, L / 2, nx)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    q1 = O.initial_q(X, Y, 0.3, 3.0, O.matlab_rand_stream(5), k_min=10, k_max=6)
+    qk = np.stack([O.g2k(q1), O.g2k(-q1)], axis=2)
+    nu = 0.1 * (L / nx) ** 8
+    B, _, LV, LD, LV1 = O.qg2_operators(kx_, ky_, 3.0, 0.0, 0.5, 0.4, nu, 4)
+    qg = QG2Flow(nx, L, qk[:, :, 0], qk[:, :, 1], 3.0, 0.0, 0.5, 0.4, nu, 4)
+    assert abs(qg.max_speed() - O.qg2_max_speed(qk, 3.0, K2, kx_, ky_, 0.5)) < 1e-13
+    Qm = [np.zeros_like(qk), np.zeros_like(qk)]
+    dts = [0.05, 0.05, 0.05, 0.05, 0.02, 0.02, 0.02]              # a dt change re-builds expLdt/expL2dt (:156-165)
+    for step, dt in enumerate(dts, 1):
+        E1, E2 = O.qg2_expL(LV, LD, LV1, dt), O.qg2_expL(LV, LD, LV1, 2 * dt)
+        Qn = O.qg2_update(qk, B, kx_, ky_)
+        if step == 1:
+            dq = dt * Qn
+        elif step == 2:
+            dq = dt / 2 * (3 * Qn - O.mmult3(E1, Qm[0]))
+        else:
+            dq = dt / 12 * (23 * Qn - 16 * O.mmult3(E1, Qm[0]) + 5 * O.mmult3(E2, Qm[1]))
+        Qm = [Qn, Qm[0]]
+        qk = O.mmult3(E1, qk + dq)
+        qg.step(dt)
+        scale = np.abs(qk).max()
+        for layer in range(2):
+            assert np.abs(qg.get(layer) - O.symmetrise_ky0(qk[:, :, layer])).max() / scale < 1e-12 or \
+                   np.abs(qg.get(layer) - qk[:, :, layer]).max() / scale < 1e-12, (step, layer)
+    qg.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["lagrange", "spectral"])
+def test_qg2layersw_raytrace_script(mode, tmp_path):
+    import swraytracing_b200 as S
+    from swraytracing_b200 import drivers, fieldio
+    ref = O.qg2layersw_driver(32, 12, 2, 30.0, 0.0, 0.3, 3.0, 1.0, max_steps=5, k_max=6, eval_mode=mode)
+    got = drivers.qg2layersw_raytrace(32, 12, 2, 30.0, 0.0, 0.3, 3.0, 1.0, outdir=str(tmp_path), max_steps=5, k_max=6,
+                                      mode=S.MODE_LAGRANGE6 if mode == "lagrange" else S.MODE_SPECTRAL, log=lambda s: None)
+    assert got["steps"] == ref["steps"] and abs(got["t"] - ref["t"]) < 1e-13 and abs(got["dt"] - ref["dt"]) < 1e-14
+    for key in ("packet_steps", "ode23_steps", "ode23_failed", "dt_changes"):
+        assert got[key] == ref[key], key
+    for g, r in zip(got["packets"], ref["packets"]):
+        assert _relerr(g, r) < 1e-9
+    scale = np.abs(ref["qk"]).max()
+    for layer in range(2):
+        assert np.abs(got["qk"][layer] - ref["qk"][:, :, layer]).max() / scale < 1e-10
+    t, x, k = fieldio.load_packet_frames(tmp_path, 12)
+    assert x.shape == (12, 2, got["packet_frames"]) and np.all(np.abs(x) <= 10.0)
