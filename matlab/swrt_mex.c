@@ -36,12 +36,13 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (!g_locked) { mexLock(); mexAtExit(destroy_all); g_locked = 1; }
     (void)nlhs;
 
-    if (!strcmp(cmd, "create")) {           /* h = swrt_mex('create', nx, L, f, gH, mode, device, bump) */
+    if (!strcmp(cmd, "create")) {           /* h = swrt_mex('create', nx, L, f, gH, mode, device, bump, flags) */
         swrt_params p; memset(&p, 0, sizeof p);
         p.nx = (int)mxGetScalar(prhs[1]); p.L = mxGetScalar(prhs[2]); p.f = mxGetScalar(prhs[3]); p.gH = mxGetScalar(prhs[4]);
         p.mode = nrhs > 5 ? (int)mxGetScalar(prhs[5]) : SWRT_MODE_SPECTRAL;
         p.device = nrhs > 6 ? (int)mxGetScalar(prhs[6]) : 0;
         p.bump = nrhs > 7 ? mxGetScalar(prhs[7]) : 1e-13;
+        p.flags = nrhs > 8 ? (int)mxGetScalar(prhs[8]) : 0;
         int slot = 0; while (slot < MAXH && g_handles[slot]) slot++;
         if (slot == MAXH) mexErrMsgIdAndTxt("swrt:handle", "too many handles");
         if (swrt_create(&p, &g_handles[slot])) fail(NULL, "swrt_create");
@@ -101,6 +102,18 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     } else if (!strcmp(cmd, "step")) {                /* (h, scheme, dt, nsteps [, alpha0, dalpha]) */
         if (swrt_step(h, (int)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[4]), nrhs > 5 ? mxGetScalar(prhs[5]) : 0.0,
                       nrhs > 6 ? mxGetScalar(prhs[6]) : 0.0)) fail(h, cmd);
+    } else if (!strcmp(cmd, "bs23_begin")) {          /* rh = (h, alpha, threshold)          -- ode23 building blocks */
+        plhs[0] = mxCreateDoubleMatrix(1, 1, mxREAL);
+        if (swrt_bs23_begin(h, mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), mxGetPr(plhs[0]))) fail(h, cmd);
+    } else if (!strcmp(cmd, "bs23_attempt")) {        /* err = (h, hstep, [a2 a3 a4], threshold) */
+        plhs[0] = mxCreateDoubleMatrix(1, 1, mxREAL);
+        if (mxGetNumberOfElements(prhs[3]) != 3) mexErrMsgIdAndTxt("swrt:usage", "bs23_attempt: alpha must have 3 entries");
+        if (swrt_bs23_attempt(h, mxGetScalar(prhs[2]), mxGetPr(prhs[3]), mxGetScalar(prhs[4]), mxGetPr(plhs[0]))) fail(h, cmd);
+    } else if (!strcmp(cmd, "bs23_accept")) {         /* (h) */
+        if (swrt_bs23_accept(h)) fail(h, cmd);
+    } else if (!strcmp(cmd, "bs23_interp")) {         /* [x, y, k, l] = (h, hstep, s)        -- ntrp23 */
+        double* o[4]; for (int i = 0; i < 4; i++) o[i] = vec(&plhs[i], n);
+        if (swrt_bs23_interp(h, mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), o[0], o[1], o[2], o[3])) fail(h, cmd);
     } else if (!strcmp(cmd, "hist_omega")) {          /* counts = (h, kind, alpha, edges) */
         int ne = (int)mxGetNumberOfElements(prhs[4]);
         plhs[0] = mxCreateNumericMatrix(1, ne - 1, mxUINT64_CLASS, mxREAL);
