@@ -116,6 +116,9 @@ int swrt_interpolate(int device, const double* x, const double* y, int64_t n, co
 /* ---- stepping ----------------------------------------------------------------------------- */
 /* nsteps fused steps of the chosen scheme; step j evaluates the flow at alpha0 + j*dalpha.    */
 int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha);
+/* the same launches without the host wait (swrt_step returns when the kernels are done; this returns when they are
+ * queued): host work of the previous diagnostic interval overlaps the kernel.  swrt_synchronize completes it.   */
+int swrt_step_async(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha);
 
 /* ---- ode23 (Bogacki-Shampine 3(2), MATLAB builtin called by qgsw_raytrace.m:149 and
  * qg2layersw_raytrace.m:195 on y = [x;y;k;l]) -- device building blocks.  The HOST owns the step-size
@@ -142,6 +145,12 @@ int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges,
  * round trip through host memory; the handle's stream is synchronised on return              */
 int swrt_hist_omega_dev(swrt_handle* h, int kind, double alpha, const double* edges, int nedges,
                         uint64_t** counts_dev);
+/* pipelined form for multi-GPU diagnostics: _launch queues the histogram kernel behind the work already on the
+ * handle's stream and returns at once; _wait blocks until THAT kernel has finished (not later work), after which
+ * counts_dev may be snapshotted and all-reduced while the next interval's packet kernel runs                  */
+int swrt_hist_omega_launch(swrt_handle* h, int kind, double alpha, const double* edges, int nedges,
+                           uint64_t** counts_dev);
+int swrt_hist_omega_wait(swrt_handle* h);
 /* theoretical omega pdf of ideal_omega_distribution.m:3-11: omega_abs = omega0 + U(x_i).kvec_j over npts
  * points (the caller's grid XX(:),YY(:)) x nangles wavevectors (kvx,kvy = k_0*[cos(t) sin(t)]), counted
  * into histcounts-style bins; counts[nedges-1].                                                   */

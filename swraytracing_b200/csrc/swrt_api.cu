@@ -71,7 +71,7 @@ struct swrt_handle {
     unsigned long long* counts_dev = nullptr; int counts_cap = 0;
     // instrumentation
     int64_t launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, hist_ev = nullptr;
     bool timing_valid = false;
     int last_nlaunch = 0;
     int mtiles = 0;
@@ -440,6 +440,7 @@ int swrt_destroy(swrt_handle* h) {
     for (auto& row : h->bs_f) for (auto& p : row) dfree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->hist_ev) cudaEventDestroy(h->hist_ev);
     if (h->tm0) cudaEventDestroy(h->tm0);
     if (h->tm1) cudaEventDestroy(h->tm1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -813,7 +814,7 @@ static int step_rk4(swrt_handle* h, bool xka, double dt, int nsteps, double alph
     return SWRT_OK;
 }
 
-int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha) {
+static int step_impl(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha, bool sync) {
     if (!h) return SWRT_ERR_ARG;
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, nsteps >= 0, SWRT_ERR_ARG, "negative step count");
@@ -828,8 +829,16 @@ int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, 
         default: return fail(h, SWRT_ERR_ARG, "unknown scheme %d", scheme);
     }
     if (rc) return rc;
-    CU(h, cudaStreamSynchronize(h->stream));
+    if (sync) CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
+}
+int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha) {
+    return step_impl(h, scheme, dt, nsteps, alpha0, dalpha, true);
+}
+// same launches, no host wait: the caller overlaps host work (diagnostics of the previous interval, the next
+// frame's upload) with the kernel; swrt_synchronize / any blocking call completes it
+int swrt_step_async(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha) {
+    return step_impl(h, scheme, dt, nsteps, alpha0, dalpha, false);
 }
 
 // ---- diagnostics ------------------------------------------------------------------------------
@@ -900,6 +909,27 @@ int swrt_hist_omega_dev(swrt_handle* h, int kind, double alpha, const double* ed
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     *counts_dev = reinterpret_cast<uint64_t*>(h->counts_dev);
+    return SWRT_OK;
+}
+
+// non-blocking form: the histogram kernel is queued behind whatever is on the handle's stream and an event is
+// recorded after it; swrt_hist_omega_wait blocks on that event only (not on work queued afterwards)
+int swrt_hist_omega_launch(swrt_handle* h, int kind, double alpha, const double* edges, int nedges, uint64_t** counts_dev) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, counts_dev, SWRT_ERR_ARG, "null counts_dev");
+    int rc = hist_to_device(h, kind, alpha, edges, nedges);
+    if (rc) return rc;
+    if (!h->hist_ev) CU(h, cudaEventCreateWithFlags(&h->hist_ev, cudaEventDisableTiming));
+    CU(h, cudaEventRecord(h->hist_ev, h->stream));
+    *counts_dev = reinterpret_cast<uint64_t*>(h->counts_dev);
+    return SWRT_OK;
+}
+int swrt_hist_omega_wait(swrt_handle* h) {
+    if (!h) return SWRT_ERR_ARG;
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, h->hist_ev, SWRT_ERR_STATE, "swrt_hist_omega_launch has not been called");
+    CU(h, cudaEventSynchronize(h->hist_ev));
     return SWRT_OK;
 }
 

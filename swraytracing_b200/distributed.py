@@ -23,6 +23,70 @@ class _DeviceI64:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
 
 
+class HistPipeline:
+    """Histogram diagnostics pipelined against the packet kernel (the only collective of the path).
+
+    Per diagnostic interval the caller does
+        engine.step(...)          # asynchronous launch of the interval's packet kernel
+        done = pipe.rotate()      # host work hidden under that kernel (see below)
+        pipe.launch(alpha)        # local histogram kernel queued behind the packet kernel, no host wait
+    ``rotate`` takes the histogram launched in the PREVIOUS interval (its kernel has long finished), snapshots the
+    counts with a device-to-device copy, issues the SUM all-reduce asynchronously, and returns the globally reduced
+    counts of the interval before that (or None while the pipeline fills).  No rank ever blocks on another inside an
+    interval; ``drain()`` returns the results still in flight.  Without a process group (1 GPU, or the CPU stand-in
+    engines of the gloo tests) the same calls degrade to local / synchronous reductions."""
+
+    def __init__(self, ens, edges, kind=0):
+        self.ens, self.edges, self.kind = ens, np.ascontiguousarray(edges, dtype=np.float64), kind
+        self.nccl = (ens.dist is not None and ens.world > 1 and ens.device is not None
+                     and getattr(ens.device, "type", "cpu") == "cuda")
+        self.device_side = hasattr(ens.engine, "hist_omega_launch")
+        self._launched = None      # (ptr, nbins) of a histogram kernel in flight
+        self._reducing = None      # (work, tensor) of an all-reduce in flight
+        self._ready = []           # finished results not yet handed out (non-NCCL paths)
+
+    def launch(self, alpha=0.0):
+        if self.device_side:
+            self._launched = self.ens.engine.hist_omega_launch(self.edges, self.kind, alpha)
+        else:
+            self._ready.append(self.ens.hist_omega(self.edges, self.kind, alpha))
+
+    def _collect(self):
+        if self._reducing is None:
+            return None
+        work, t = self._reducing
+        self._reducing = None
+        if work is not None:
+            work.wait()
+        return t.cpu().numpy().astype(np.uint64)
+
+    def rotate(self):
+        out = self._collect()
+        if self._launched is not None:
+            import torch
+            ptr, nb = self._launched
+            self._launched = None
+            self.ens.engine.hist_omega_wait()                         # that kernel only, not the work queued after it
+            dev = self.ens.device if self.ens.device is not None else torch.device("cuda", self.ens.engine.device)
+            t = torch.empty(nb, dtype=torch.int64, device=dev)
+            t.copy_(torch.as_tensor(_DeviceI64(ptr, nb), device=dev))   # D2D snapshot: the engine reuses its buffer
+            torch.cuda.current_stream(dev).synchronize()
+            work = self.ens.dist.all_reduce(t, op=self.ens.dist.ReduceOp.SUM, async_op=True) if self.nccl else None
+            self._reducing = (work, t)
+        if out is None and self._ready:
+            out = self._ready.pop(0)
+        return out
+
+    def drain(self):
+        """results still in flight, oldest first"""
+        outs = []
+        for _ in range(3):
+            r = self.rotate()
+            if r is not None:
+                outs.append(r)
+        return outs
+
+
 class ShardedEnsemble:
     """A rank-local engine holding this rank's packet shard.
 
@@ -84,6 +148,9 @@ class ShardedEnsemble:
             return t.cpu().numpy().astype(np.uint64)
         local = self.engine.hist_omega(edges, kind, alpha)
         return self._allreduce_sum(local.astype(np.int64)).astype(np.uint64)
+
+    def hist_pipeline(self, edges, kind=0):
+        return HistPipeline(self, edges, kind)
 
     def energy_vs_omega(self, edges, kind=0, alpha=0.0):
         """energy = centre .* counts (analysis/load_data.m:40,49)"""

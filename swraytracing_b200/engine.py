@@ -53,12 +53,15 @@ SIGNATURES = {
     "swrt_rhs": (C.c_int, [C.c_void_p, C.c_double] + [_dp] * 4),
     "swrt_interpolate": (C.c_int, [C.c_int, _dp, _dp, C.c_int64, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp]),
     "swrt_step": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
+    "swrt_step_async": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
     "swrt_hist_omega": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_uint64), C.c_int]),
     "swrt_bs23_begin": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _dp]),
     "swrt_bs23_attempt": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, _dp]),
     "swrt_bs23_accept": (C.c_int, [C.c_void_p]),
     "swrt_bs23_interp": (C.c_int, [C.c_void_p, C.c_double, C.c_double] + [_dp] * 4),
     "swrt_hist_omega_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_void_p)]),
+    "swrt_hist_omega_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_void_p)]),
+    "swrt_hist_omega_wait": (C.c_int, [C.c_void_p]),
     "swrt_ideal_omega_hist": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, C.c_double, _dp, C.c_int,
                                         C.POINTER(C.c_uint64)]),
     "swrt_diag": (C.c_int, [C.c_void_p, C.c_double, _dp]),
@@ -228,6 +231,10 @@ class Engine:
     def step(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
         self._check(self.lib.swrt_step(self._h, int(scheme), float(dt), int(nsteps), float(alpha0), float(dalpha)))
 
+    def step_async(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
+        """queue the step's kernels and return at once (``synchronize()`` or any blocking call completes them)"""
+        self._check(self.lib.swrt_step_async(self._h, int(scheme), float(dt), int(nsteps), float(alpha0), float(dalpha)))
+
     # -- ode23 building blocks (the controller lives in reference_api.ode23) --
     def bs23_begin(self, alpha, threshold):
         out = C.c_double(0.0)
@@ -265,6 +272,16 @@ class Engine:
         ptr = C.c_void_p()
         self._check(self.lib.swrt_hist_omega_dev(self._h, kind, float(alpha), _ptr(edges), edges.size, C.byref(ptr)))
         return ptr.value, edges.size - 1
+
+    def hist_omega_launch(self, edges, kind=HIST_INTRINSIC, alpha=0.0):
+        """non-blocking: queue the histogram kernel on the handle's stream -> (device pointer, nbins)"""
+        edges = _f64(edges)
+        ptr = C.c_void_p()
+        self._check(self.lib.swrt_hist_omega_launch(self._h, kind, float(alpha), _ptr(edges), edges.size, C.byref(ptr)))
+        return ptr.value, edges.size - 1
+
+    def hist_omega_wait(self):
+        self._check(self.lib.swrt_hist_omega_wait(self._h))
 
     def ideal_omega_hist(self, x, y, kvx, kvy, omega0, edges, alpha=0.0):
         x, y, kvx, kvy, edges = (_f64(a).ravel() for a in (x, y, kvx, kvy, edges))

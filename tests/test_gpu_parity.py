@@ -718,3 +718,30 @@ def test_qgsw_raytrace_driver_on_device(tmp_path):
     t, xs, ks = fieldio.load_packet_frames(tmp_path, Np)
     assert xs.shape == (Np, 2, 2) and abs(t[1] - 4 * dt) < 1e-12 and np.abs(xs).max() <= L / 2
     assert np.array_equal(ks[:, 0, 0], k)
+
+
+@pytest.mark.gpu
+def test_hist_pipeline_matches_blocking_histogram(small_flow, packets):
+    """HistPipeline (non-blocking histogram launch + snapshot, results two rotations later) returns exactly the
+    counts of the blocking swrt_hist_omega for every interval, in order"""
+    import swraytracing_b200 as S
+    from swraytracing_b200.distributed import ShardedEnsemble
+    eng = S.Engine(small_flow["nx"], small_flow["L"], 3.0, 1.0, S.MODE_SPECTRAL)
+    eng.set_flow_spectral(small_flow["psik"])
+    eng.set_packets(packets["x"], packets["y"], packets["k"], packets["l"])
+    ens = ShardedEnsemble(eng, packets["n"])
+    edges = np.linspace(0.0, 9.0, 300)
+    pipe = ens.hist_pipeline(edges)
+    want, got = [], []
+    for it in range(5):
+        eng.step_async(S.SCHEME_LEAPFROG, 0.01, 3)
+        r = pipe.rotate()
+        if r is not None:
+            got.append(r)
+        pipe.launch()
+        want.append(eng.hist_omega(edges))            # blocking reference of the same state
+    got += pipe.drain()
+    assert len(got) == 5
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g, w_) and int(g.sum()) <= packets["n"]
+    eng.close()

@@ -113,7 +113,11 @@ def _worker(rank, world, port, tmp):
     ens.step(0, w.dt, 7)
     edges = O.matlab_linspace(0, 6.5, 300)
     counts = ens.hist_omega(edges)
+    pipe = ens.hist_pipeline(edges)                 # pipelined form: same counts, handed out by rotate()/drain()
+    pipe.launch(); pipe.launch()
     d = ens.diag()
+    outs = pipe.drain()
+    assert len(outs) == 2 and all(np.array_equal(o, counts) for o in outs)
     allp = ens.gather_packets()
     st = ens.ode23([0, 20 * w.dt], np.inf)            # global error norm: MAX all-reduce per attempted step
     allq = ens.gather_packets()
