@@ -14,6 +14,11 @@ $(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/swrt_internal.h include/swrt.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
+# LAGRANGE6 = the reference's arithmetic, operation for operation: no fused multiply-add contraction
+$(OBJ)/lagrange_kernels.o: $(CSRC)/lagrange_kernels.cu $(CSRC)/swrt_internal.h include/swrt.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+
 $(LIB): $(OBJ)/spectral_kernels.o $(OBJ)/lagrange_kernels.o $(OBJ)/misc_kernels.o $(OBJ)/swrt_api.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
 

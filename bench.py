@@ -355,9 +355,24 @@ def main():
             lms.append(le.last_kernel_ms()[0])
         lm = float(np.mean(lms))
         gathered = le.work_per_eval(6) * n * sub
+        # the same mode end to end: host buffers in, step, host buffers out (apples to apples with the CPU arm,
+        # which runs exactly this arithmetic)
+        import ctypes as C
+        le2e = []
+        for i in range(min(args.steps, 10) + 2):
+            flush.fill_(i & 0xFF); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            le.set_packets(*pin_np)
+            le.step(scheme, w.dt, sub)
+            le._check(le.lib.swrt_get_packets(le._h, *[o.ctypes.data_as(C.POINTER(C.c_double)) for o in out_np], None))
+            le2e.append((time.perf_counter() - t0) * 1e3)
+        le_ms = float(np.mean(le2e[2:]))
         lag = {"value": n * sub / (lm * 1e-3), "unit": UNIT, "kernel_ms": round(lm, 4),
                "gather_GBps": round(gathered / (lm * 1e-3) * 1e-9, 1),
-               "note": "LAGRANGE6 mode = the reference's own 6x6 stencil semantics (interpolate.m), L2-gather bound"}
+               "e2e": {"value": n * sub / (le_ms * 1e-3), "unit": UNIT, "ms_per_step": round(le_ms, 4),
+                       "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n},
+               "note": "LAGRANGE6 mode = the reference's own 6x6 stencil semantics (interpolate.m), L2-gather bound; this is the "
+                       "arithmetic the CPU arm (--impl reference) executes"}
         le.close()
 
     cpu = cpu_spec = None

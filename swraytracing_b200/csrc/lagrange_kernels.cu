@@ -27,21 +27,22 @@ __device__ __forceinline__ double matlab_mod(double a, double m) {
     return r;
 }
 
-// interpolate.m:33-41: w_i = prod_{j != i} (a - j + bump)/(j - i).  The reference divides factor by
-// factor; here the five numerator factors are multiplied in the same j order and divided once by the
-// exact integer denominator prod (j - i) = {120,-24,12,-12,24,-120} (differs by rounding only).
+// interpolate.m:33-41, operation for operation:  w_i = 1; for j ~= i (ascending):  w_i = w_i*(a - j + bump)/(j - i)
+// -- multiply by the numerator factor, then divide by the integer (j - i), five times per weight.  This translation
+// unit is compiled with -fmad=false (Makefile / __graft_entry__.py) so that no product is fused into a following
+// add: with IEEE division, sqrt, floor and fmod the LAGRANGE6 kernels then reproduce the reference's double
+// arithmetic bit for bit (tests/test_gpu_parity.py::test_lagrange_mode_is_bit_identical_to_the_restatement).
 __device__ __forceinline__ void lagrange_weights(double a, double bump, double* w) {
     double t[NW];
 #pragma unroll
     for (int j = 0; j < NW; j++) t[j] = a - (double)(j - IORD) + bump;
-    const double den[NW] = {120.0, -24.0, 12.0, -12.0, 24.0, -120.0};
 #pragma unroll
     for (int i = 0; i < NW; i++) {
         double p = 1.0;
 #pragma unroll
         for (int j = 0; j < NW; j++)
-            if (j != i) p *= t[j];
-        w[i] = p / den[i];
+            if (j != i) p = p * t[j] / (double)(j - i);
+        w[i] = p;
     }
 }
 

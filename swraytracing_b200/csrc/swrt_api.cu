@@ -120,6 +120,7 @@ int ensure_scratch(swrt_handle* h, int64_t n) {
     if (n <= h->scratch_cap) return SWRT_OK;
     for (auto& p : h->e) dfree(p);
     dfree(h->xs); dfree(h->ys); dfree(h->ax); dfree(h->ay); dfree(h->om); dfree(h->Om);
+    h->scratch_cap = 0;                       // a failed allocation below must not leave a stale capacity behind
     size_t b = (size_t)n * sizeof(double);
     for (auto& p : h->e) CU(h, cudaMalloc(&p, b));
     CU(h, cudaMalloc(&h->xs, b)); CU(h, cudaMalloc(&h->ys, b)); CU(h, cudaMalloc(&h->ax, b));
@@ -131,6 +132,7 @@ int ensure_scratch(swrt_handle* h, int64_t n) {
 int ensure_packets(swrt_handle* h, int64_t n) {
     if (n > h->cap) {
         dfree(h->x); dfree(h->y); dfree(h->k); dfree(h->l); dfree(h->a);
+        h->cap = 0; h->n = 0;
         size_t b = (size_t)n * sizeof(double);
         CU(h, cudaMalloc(&h->x, b)); CU(h, cudaMalloc(&h->y, b)); CU(h, cudaMalloc(&h->k, b));
         CU(h, cudaMalloc(&h->l, b)); CU(h, cudaMalloc(&h->a, b));
@@ -985,6 +987,7 @@ static int bs23_setup(swrt_handle* h, Bs23Args& a) {
     if (h->n > h->bs_cap) {
         for (auto& p : h->bs_yt) dfree(p);
         for (auto& row : h->bs_f) for (auto& p : row) dfree(p);
+        h->bs_cap = 0; h->bs_ready = false;
         size_t b = (size_t)h->n * sizeof(double);
         for (auto& p : h->bs_yt) CU(h, cudaMalloc(&p, b));
         for (auto& row : h->bs_f) for (auto& p : row) CU(h, cudaMalloc(&p, b));

@@ -745,3 +745,71 @@ def test_hist_pipeline_matches_blocking_histogram(small_flow, packets):
     for g, w_ in zip(got, want):
         assert np.array_equal(g, w_) and int(g.sum()) <= packets["n"]
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# LAGRANGE6 = the reference's double arithmetic, operation for operation (steady flow): bit-identical
+# ------------------------------------------------------------------------------------------------
+def _bit_equal(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def _ulps(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float((np.abs(a - b) / np.spacing(np.maximum(np.abs(a), np.abs(b)))).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx", [16, 64])
+def test_lagrange_mode_is_bit_identical_to_the_restatement(nx):
+    """interpolate.m's weights (multiply by (a-j+bump), divide by (j-i), five times), the i-outer/j-inner 36-term sum
+    without fused multiply-adds, ode_symplectic's drift/kick expressions, step_packet's and step_packet_xka's RK4
+    stages: the kernel executes the same IEEE operations in the same order as the line-by-line restatement, so every
+    output double is the same double -- not merely within 1e-12."""
+    L = 2 * np.pi; dx = L / nx
+    psik, planes = make_flow(nx)
+    grids = [O.k2g(p) for p in planes]
+    n = 513
+    rs = np.random.RandomState(nx)
+    x = rs.uniform(-3 * L, 3 * L, n); y = rs.uniform(-3 * L, 3 * L, n)
+    x[:4] = [0.0, -dx, 5 * dx, L]; y[:4] = [0.0, 2 * dx, -L, 7 * dx - 1e-14]        # grid nodes, wrap, negative side
+    k = 3 * np.cos(np.arange(n) * 0.37); l = 3 * np.sin(np.arange(n) * 0.37)
+    # (1) interpolate(x,y,F,dx,dy), both bumps
+    for bump, ref_fn in ((1e-13, O.interpolate), (1e-10, O.interpolate_par)):
+        got = S.interpolate_dev(x, y, grids[0], dx, dx, bump)
+        assert _bit_equal(got, ref_fn(x, y, grids[0], dx, dx)), _ulps(got, ref_fn(x, y, grids[0], dx, dx))
+    with S.Engine(nx, L, F0, GH0, S.MODE_LAGRANGE6) as e:
+        e.set_flow_grid(*grids)
+        # (2) the six planes of SpectralScheme.U / grad_U
+        got = e.eval_at(x, y)
+        for c in range(6):
+            assert _bit_equal(got[c], O.interpolate(x, y, grids[c], dx, dx)), (c, _ulps(got[c], O.interpolate(x, y, grids[c], dx, dx)))
+        # (3) ode_symplectic: 25 leapfrog steps
+        dt = 0.1 * dx
+        e.set_packets(x, y, k, l)
+        e.step(S.SCHEME_LEAPFROG, dt, 25)
+        got = e.get_packets()
+        ev = lambda xx, yy: tuple(O.interpolate(xx, yy, g, dx, dx) for g in grids)
+        ref = (x, y, k, l)
+        for _ in range(25):
+            ref = O.leapfrog_step(*ref, dt, F0, GH0, ev)
+        for g_, r_, name in zip(got, ref, "xykl"):
+            assert _bit_equal(g_, r_), (name, _ulps(g_, r_))
+    # (4) step_packet / step_packet_xka: 3 RK4 steps of a few packets through the reference's own per-packet functions
+    H = 1.0 + 0.2 * grids[0] / np.abs(grids[0]).max()
+    U = {"u": grids[0], "v": grids[1]}; G = {"u_x": grids[2], "u_y": grids[3], "v_x": grids[4], "v_y": grids[5]}
+    dt = 0.3 * dx
+    for xka in (False, True):
+        with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
+            e.set_flow_grid(*grids, H=H if xka else None)
+            m = 12
+            e.set_packets(x[:m], y[:m], 10 * k[:m], 10 * l[:m], np.ones(m))
+            e.step(S.SCHEME_RK4_XKA if xka else S.SCHEME_RK4_PACKET, dt, 3)
+            got = e.get_packets(with_a=True)
+        for p in range(m):
+            P = {"x": x[p], "y": y[p], "k": 10 * k[p], "l": 10 * l[p], "a": 1.0}
+            for _ in range(3):
+                P = {**P, **(O.step_packet_xka(P, U, G, H, 1.0, F0, dx, dx, dt) if xka else O.step_packet(P, U, G, 1.0, F0, dx, dx, dt))}
+            for j, name in enumerate(("x", "y", "k", "l") + (("a",) if xka else ())):
+                assert got[j][p] == P[name], (xka, p, name, got[j][p], P[name])
