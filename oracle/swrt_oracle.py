@@ -345,6 +345,59 @@ class SpectralScheme:
         return out
 
 
+    # RaytracingScheme.m:18-31 (inherited diagnostics)
+    def vorticity(self, x, t=0):
+        g = self.grad_U(x, t)
+        return g["v_x"] - g["u_y"]
+
+    def strain(self, x, t=0):
+        g = self.grad_U(x, t)
+        return np.sqrt((g["u_x"] - g["v_y"]) ** 2 + (g["v_x"] + g["u_y"]) ** 2)
+
+    def okuboWeiss(self, x, t=0):
+        """RaytracingScheme.m:28-31 calls ``obj.grad_U(x, k, t)`` with an undefined ``k`` (it errors in MATLAB);
+        the formula on :30 is what is restated: D = v_y^2 + v_x*u_y."""
+        g = self.grad_U(x, t)
+        return g["v_y"] ** 2 + g["v_x"] * g["u_y"]
+
+
+class DifferenceScheme:
+    """DifferenceScheme.m:1-46: U and grad U by centred finite differences of an analytic streamfunction
+    handle ``psi(x, y, t)`` with h = eps^(1/3).  Not on the packet path of any driver (the only call site is the
+    commented hint in SW_zero_background_raytracing.m:22-23); restated because it is the reference's own
+    independent check of SpectralScheme: both schemes must agree to the finite-difference error."""
+
+    def __init__(self, stream):
+        self.h = np.finfo(np.float64).eps ** (1.0 / 3.0)        # nthroot(eps, 3)
+        self.psi = stream
+
+    def streamfunction(self, x, y, t=0):
+        return self.psi(x, y, t)
+
+    def U(self, x, t=0):
+        x = np.asarray(x, dtype=np.float64)
+        xx, yy = (x[:, 0], x[:, 1]) if x.ndim == 2 else (x[:, 0, :], x[:, 1, :])
+        h = self.h
+        u = np.zeros_like(x)
+        v_ = (self.psi(xx + h / 2, yy, t) - self.psi(xx - h / 2, yy, t)) / h
+        u_ = -(self.psi(xx, yy + h / 2, t) - self.psi(xx, yy - h / 2, t)) / h
+        if x.ndim == 2:
+            u[:, 0], u[:, 1] = u_, v_
+        else:
+            u[:, 0, :], u[:, 1, :] = u_, v_
+        return u
+
+    def grad_U(self, x, t=0):
+        x = np.asarray(x, dtype=np.float64)
+        xx, yy = (x[:, 0], x[:, 1]) if x.ndim == 2 else (x[:, 0, :].ravel(), x[:, 1, :].ravel())
+        h, p = self.h, self.psi
+        v_x = (p(xx + h, yy, t) - 2 * p(xx, yy, t) + p(xx - h, yy, t)) / h / h
+        u_y = -(p(xx, yy + h, t) - 2 * p(xx, yy, t) + p(xx, yy - h, t)) / h / h
+        v_y = (p(xx + h / 2, yy + h / 2, t) + p(xx - h / 2, yy - h / 2, t) - p(xx - h / 2, yy + h / 2, t)
+               - p(xx + h / 2, yy - h / 2, t)) / h / h
+        return {"u_x": -v_y, "u_y": u_y, "v_x": v_x, "v_y": v_y}
+
+
 class PlanesScheme:
     """A scheme defined directly by six coefficient planes (u,v,ux,uy,vx,vy) on a domain of side L
     (what grid_U builds for the qgsw drivers), evaluated either by k2g+interpolate or trig sum."""

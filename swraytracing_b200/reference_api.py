@@ -162,6 +162,21 @@ class SpectralScheme:
         return out
 
 
+    # RaytracingScheme.m:18-31: diagnostics every scheme inherits (host arithmetic on the device-evaluated gradients)
+    def vorticity(self, x, t=0):
+        g = self.grad_U(x, t)
+        return g["v_x"] - g["u_y"]
+
+    def strain(self, x, t=0):
+        g = self.grad_U(x, t)
+        return np.sqrt((g["u_x"] - g["v_y"]) ** 2 + (g["v_x"] + g["u_y"]) ** 2)
+
+    def okuboWeiss(self, x, t=0):
+        """D = v_y^2 + v_x*u_y (RaytracingScheme.m:30; the reference's own call on :29 passes an undefined ``k``)"""
+        g = self.grad_U(x, t)
+        return g["v_y"] ** 2 + g["v_x"] * g["u_y"]
+
+
 def ode_symplectic(x0, k0, dt, T, f, gH, scheme, save_stride=1):
     """ode_symplectic.m:1-37 -- [x, k, t] = ode_symplectic(x0, k0, dt, T, f, gH, scheme).
 

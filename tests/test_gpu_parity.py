@@ -813,3 +813,22 @@ def test_lagrange_mode_is_bit_identical_to_the_restatement(nx):
                 P = {**P, **(O.step_packet_xka(P, U, G, H, 1.0, F0, dx, dx, dt) if xka else O.step_packet(P, U, G, 1.0, F0, dx, dx, dt))}
             for j, name in enumerate(("x", "y", "k", "l") + (("a",) if xka else ())):
                 assert got[j][p] == P[name], (xka, p, name, got[j][p], P[name])
+
+
+@pytest.mark.gpu
+def test_scheme_diagnostics_and_difference_scheme_cross_check():
+    """product SpectralScheme (device) vs the reference's independent DifferenceScheme on the analytic
+    Childress-Soward streamfunction, and the inherited RaytracingScheme diagnostics vs the oracle scheme"""
+    nx, L, U0, km, a = 64, 2 * np.pi, 0.1, 4.0, 0.25
+    psi, _, _ = O.childress_soward(nx, L, U0, km, a)
+    ds = O.DifferenceScheme(lambda x, y, t: U0 / km * (np.sin(km * x) * np.sin(km * y) + a * np.cos(km * x) * np.cos(km * y)))
+    x = np.random.RandomState(0).uniform(-5, 5, (200, 2))
+    for mode, omode, tolU in ((S.MODE_SPECTRAL, "spectral", 1e-10), (S.MODE_LAGRANGE6, "lagrange", 1e-4)):
+        sch = R.SpectralScheme(L, nx, psi, mode=mode)
+        osch = O.SpectralScheme(L, nx, psi, mode=omode)
+        assert np.abs(sch.U(x) - ds.U(x)).max() < tolU
+        assert np.abs(sch.vorticity(x) - osch.vorticity(x)).max() < 1e-12
+        assert np.abs(sch.strain(x) - osch.strain(x)).max() < 1e-12
+        assert np.abs(sch.okuboWeiss(x) - osch.okuboWeiss(x)).max() < 1e-12
+    zeta = -2 * km ** 2 * ds.streamfunction(x[:, 0], x[:, 1])
+    assert np.abs(R.SpectralScheme(L, nx, psi).vorticity(x) - zeta).max() < 1e-12

@@ -231,3 +231,28 @@ def test_ode23_restatement_known_answers():
     y, st = O.ode23(ode, [0, 1.0], y0)
     w = np.sqrt(f * f + Cg * Cg * 25.0)
     assert np.allclose(y[:n], Cg * 3 / w, atol=1e-14) and np.allclose(y[2 * n:3 * n], 3.0)
+
+
+def test_difference_scheme_cross_checks_spectral_scheme():
+    """DifferenceScheme.m (finite differences of the analytic streamfunction, h = eps^(1/3)) and SpectralScheme.m
+    (spectral derivatives of the gridded streamfunction) are the reference's two implementations of the same
+    RaytracingScheme interface; on the Childress-Soward flow of raytrace.m:30 they must agree to the
+    finite-difference error: ~eps/h = 4e-11 for U, ~eps/h^2 = 6e-6 (x |psi|) for grad U."""
+    nx, L, U0, km, a = 64, 2 * np.pi, 0.1, 4.0, 0.25
+    psi, _, _ = O.childress_soward(nx, L, U0, km, a)
+    sch = O.SpectralScheme(L, nx, psi, mode="spectral")
+    ds = O.DifferenceScheme(lambda x, y, t: U0 / km * (np.sin(km * x) * np.sin(km * y) + a * np.cos(km * x) * np.cos(km * y)))
+    assert abs(ds.h - 6.055454452393343e-06) < 1e-20
+    x = np.random.RandomState(0).uniform(-5, 5, (200, 2))
+    assert np.abs(sch.U(x) - ds.U(x)).max() < 1e-10
+    gs, gd = sch.grad_U(x), ds.grad_U(x)
+    for n in ("u_x", "u_y", "v_x", "v_y"):
+        assert np.abs(gs[n] - gd[n]).max() < 2e-6, n
+    assert np.abs(gs["u_x"] + gs["v_y"]).max() < 1e-14 and np.array_equal(gd["u_x"], -gd["v_y"])
+    # inherited diagnostics (RaytracingScheme.m:18-31) against the closed form: vorticity = -2 km^2 psi for this flow
+    zeta = -2 * km ** 2 * ds.streamfunction(x[:, 0], x[:, 1])
+    assert np.abs(sch.vorticity(x) - zeta).max() < 1e-13
+    assert np.all(sch.strain(x) >= 0) and np.abs(sch.okuboWeiss(x) - (gs["v_y"] ** 2 + gs["v_x"] * gs["u_y"])).max() == 0
+    # (T,2,Np) calling shape of ode_symplectic's histories
+    x3 = np.transpose(x.reshape(4, 50, 2), (0, 2, 1))
+    assert np.abs(sch.U(x3) - ds.U(x3)).max() < 1e-10
