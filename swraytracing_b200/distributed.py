@@ -152,6 +152,15 @@ class ShardedEnsemble:
     def hist_pipeline(self, edges, kind=0):
         return HistPipeline(self, edges, kind)
 
+    def ideal_omega_hist(self, x, y, kvx, kvy, omega0, edges, alpha=0.0):
+        """theoretical omega pdf (ideal_omega_distribution.m:3-11) over ALL grid points, sharded: each rank bins
+        omega0 + U(x_i).k_j for its contiguous slice of the points, then the same integer SUM all-reduce as the packet
+        histogram.  Every rank passes the full point list; counts are bit-exact under any sharding."""
+        x = np.asarray(x, dtype=np.float64).ravel(); y = np.asarray(y, dtype=np.float64).ravel()
+        lo, hi = shard_range(x.size, self.rank, self.world)
+        local = self.engine.ideal_omega_hist(x[lo:hi], y[lo:hi], kvx, kvy, omega0, edges, alpha)
+        return self._allreduce_sum(np.asarray(local).astype(np.int64)).astype(np.uint64)
+
     def energy_vs_omega(self, edges, kind=0, alpha=0.0):
         """energy = centre .* counts (analysis/load_data.m:40,49)"""
         counts = self.hist_omega(edges, kind, alpha)

@@ -91,6 +91,11 @@ class OracleEngine:
     def bs23_accept(self):
         self.s, self.f1 = self.yn, self.f4
 
+    def ideal_omega_hist(self, x, y, kvx, kvy, omega0, edges, alpha=0.0):
+        e6 = CO.interpolate6(np.asarray(x), np.asarray(y), self.grids, self.dx)
+        Uk = np.outer(e6[0], kvx) + np.outer(e6[1], kvy)           # U*kv, ideal_omega_distribution.m:9-10
+        return CO.histcounts((omega0 + Uk).ravel(), edges)
+
     def diag(self, alpha=0.0):
         w = O.omega_of_k(self.s[2], self.s[3], self.f, self.gH)
         return np.array([w.sum(), w.sum(), w.max(), w.min(), 0.0, float(w.size), float(w.size), w.sum()])
@@ -119,10 +124,14 @@ def _worker(rank, world, port, tmp):
     outs = pipe.drain()
     assert len(outs) == 2 and all(np.array_equal(o, counts) for o in outs)
     allp = ens.gather_packets()
+    gx, gy = np.meshgrid(np.linspace(0, w.L, 32), np.linspace(0, w.L, 32))
+    th = np.linspace(0, 2 * np.pi, 100)
+    ideal = ens.ideal_omega_hist(gx.ravel(order="F"), gy.ravel(order="F"), 3 * np.cos(th), 3 * np.sin(th), np.sqrt(18.0),
+                                 O.matlab_linspace(2.0, 6.5, 120))
     st = ens.ode23([0, 20 * w.dt], np.inf)            # global error norm: MAX all-reduce per attempted step
     allq = ens.gather_packets()
     if rank == 0:
-        np.savez(tmp, counts=counts, diag=d, x=allp[0], k=allp[2], nsteps=st["nsteps"], nfailed=st["nfailed"], x23=allq[0], k23=allq[2])
+        np.savez(tmp, counts=counts, ideal=ideal, diag=d, x=allp[0], k=allp[2], nsteps=st["nsteps"], nfailed=st["nfailed"], x23=allq[0], k23=allq[2])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -145,6 +154,11 @@ def test_gloo_two_ranks_match_single_rank(tmp_path):
     assert np.array_equal(got["x"], x1) and np.array_equal(got["k"], k1)   # per-packet states identical
     d1 = ens.diag()
     assert np.allclose(got["diag"], d1, rtol=1e-13) and got["diag"][6] == 1001
+    gx, gy = np.meshgrid(np.linspace(0, w.L, 32), np.linspace(0, w.L, 32))
+    th = np.linspace(0, 2 * np.pi, 100)
+    ideal1 = ens.ideal_omega_hist(gx.ravel(order="F"), gy.ravel(order="F"), 3 * np.cos(th), 3 * np.sin(th), np.sqrt(18.0),
+                                  O.matlab_linspace(2.0, 6.5, 120))
+    assert np.array_equal(got["ideal"], ideal1) and int(ideal1.sum()) == 32 * 32 * 100     # sharded grid points, same counts
     # ode23 over two ranks == ode23 over one: same accepted/rejected steps, bit-identical packets
     st = ens.ode23([0, 20 * w.dt], np.inf)
     assert (int(got["nsteps"]), int(got["nfailed"])) == (st["nsteps"], st["nfailed"]) and st["nsteps"] >= 10
