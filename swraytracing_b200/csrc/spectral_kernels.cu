@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
             // ---- twiddle seeds -------------------------------------------------------------
             double tp_[MT], tq_[MT];            // x twiddle in (p,q) form: p = this lane's A element
             double ep0[MT], eq0[MT];            // value at the start of every pass
-            double xdc[MT], xds[MT];            // rotation by e^{i 2 tx} minus one, sign-adjusted
+            double xdc[MT], xds[MT];            // rotation by e^{i 4 tx} minus one (two k-steps), sign-adjusted
+            double ep1[MT], eq1[MT];            // second chain: value at k-step 1 of every pass
+            double tpB[MT], tqB[MT];
             Cplx ytw[MT][G];                    // e^{i ky ty} for this lane's ky of each group
             Cplx yrot[MT];                      // e^{i 4G ty}
             double F[MT][NF];
@@ -424,6 +426,16 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                 xdc[mt] = -2.0 * s1 * s1;
                 double ds = 2.0 * s1 * c1;
                 xds[mt] = odd ? ds : -ds;
+                // two interleaved recurrences (even / odd k-steps), each advancing by e^{i 4 tx}: half the dependent
+                // chain length per k-step; ep1 = ep0 rotated once by e^{i 2 tx}
+                ep1[mt] = fma(ep0[mt], xdc[mt], fma(eq0[mt], xds[mt], ep0[mt]));
+                eq1[mt] = fma(eq0[mt], xdc[mt], fma(-ep0[mt], xds[mt], eq0[mt]));
+                {
+                    const double s2 = ds, c2 = fma(-2.0 * s1, s1, 1.0);     // sin 2tx, cos 2tx
+                    xdc[mt] = -2.0 * s2 * s2;
+                    const double ds2 = 2.0 * s2 * c2;
+                    xds[mt] = odd ? ds2 : -ds2;
+                }
                 double sy, cy;
                 sincospi(reduced_turns(py[mt], a.dx, a.nxd, a.inv_nx), &sy, &cy);
                 Cplx e1{cy, sy};
@@ -450,6 +462,7 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
 #pragma unroll
                     for (int t = 0; t < NT; t++) { acc[mt][t][0] = 0.0; acc[mt][t][1] = 0.0; }
                     tp_[mt] = ep0[mt]; tq_[mt] = eq0[mt];
+                    tpB[mt] = ep1[mt]; tqB[mt] = eq1[mt];
                 }
                 for (int ch = 0; ch < chunks_per_pass; ch++) {
                     SWRT_TRACE_EV(0);
@@ -481,10 +494,11 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                             }
 #pragma unroll
                             for (int mt = 0; mt < MT; mt++) {
-                                // E <- E + E*(e^{i 2 tx} - 1)
+                                // this chain's next value (two k-steps ahead): E <- E + E*(e^{i 4 tx} - 1); then swap chains
                                 double np = fma(tp_[mt], xdc[mt], fma(tq_[mt], xds[mt], tp_[mt]));
                                 double nq = fma(tq_[mt], xdc[mt], fma(-tp_[mt], xds[mt], tq_[mt]));
-                                tp_[mt] = np; tq_[mt] = nq;
+                                tp_[mt] = tpB[mt]; tq_[mt] = tqB[mt];
+                                tpB[mt] = np; tqB[mt] = nq;
                             }
                         }
                     }
