@@ -466,3 +466,34 @@ def qg2layersw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_de
            "qk": (qg.get(0), qg.get(1)), **stats, "packet_frames": writer.frames}
     qg.close(); eng.close()
     return out
+
+
+def load_data(directory, *, times=None, offset=500, bins=300, device=0):
+    """analysis/load_data.m:11-64, the computational half (the plots are out of scope): read ``run.log`` and the
+    ``packet_time / packet_x / packet_k`` frame streams a driver wrote, form omega = sqrt(f^2 + Cg^2 k.k) per packet and
+    frame (:33), ``edges = linspace(0, max omega, 300)`` (:38-39), and for every window ``times(i) +- offset`` frames
+    (:36-37,44-49) the histcounts distribution and ``energy = center .* distribution``; plus mean omega(t)/f (:63).
+    The histograms run on the device (u64 counts, the reference's bin rule).  ``times`` are 1-based frame numbers as in
+    the script; its default ``[1000, 30000, nframes - offset]`` is clipped to the frames that exist."""
+    from pathlib import Path
+    from .engine import HIST_INTRINSIC
+    d = Path(directory)
+    nx, Npackets, f, Cg, Ug = parse_data(d / "run.log")
+    t, x_save, k_save = fieldio.load_packet_frames(d, Npackets)
+    nfr = t.size
+    omega = np.sqrt(f ** 2 + Cg ** 2 * (k_save ** 2).sum(axis=1))                   # (Np, frames)
+    edges = np.linspace(0.0, omega.max(), bins)
+    center = (edges[1:] + edges[:-1]) / 2
+    if times is None:
+        times = [tt for tt in (1000, 30000, nfr - offset) if offset < tt <= nfr - offset] or [max(1, nfr // 2)]
+    eng = Engine(8, 2 * np.pi, f, Cg ** 2, MODE_SPECTRAL, device)                   # only its packet/histogram kernels are used
+    windows = []
+    for tc in times:
+        lo, hi = max(1, tc - offset), min(nfr, tc + offset)                         # frames tc-offset : tc+offset, 1-based inclusive
+        kk = k_save[:, 0, lo - 1:hi].ravel(order="F"); ll = k_save[:, 1, lo - 1:hi].ravel(order="F")
+        eng.set_packets(np.zeros_like(kk), np.zeros_like(kk), kk, ll)
+        counts = eng.hist_omega(edges, kind=HIST_INTRINSIC)
+        windows.append({"time_index": int(tc), "frames": (lo, hi), "distribution": counts, "energy": center * counts.astype(np.float64)})
+    eng.close()
+    return {"nx": nx, "Npackets": Npackets, "f": f, "Cg": Cg, "Ug": Ug, "t_packet_save": t, "omega": omega, "edges": edges,
+            "center": center, "windows": windows, "mean_omega": omega.mean(axis=0) / f}

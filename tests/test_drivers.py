@@ -303,3 +303,25 @@ def test_qg2layersw_raytrace_script(mode, tmp_path):
         assert np.abs(got["qk"][layer] - ref["qk"][:, :, layer]).max() / scale < 1e-10
     t, x, k = fieldio.load_packet_frames(tmp_path, 12)
     assert x.shape == (12, 2, got["packet_frames"]) and np.all(np.abs(x) <= 10.0)
+
+
+@pytest.mark.gpu
+def test_load_data_reads_back_driver_output(tmp_path):
+    """analysis/load_data.m on the files the device driver wrote: log header -> parse_data, packet frames -> omega,
+    window histograms bit-exact against the restated histcounts, energy = center .* counts"""
+    from swraytracing_b200 import drivers
+    lines = []
+    out = drivers.qgsw_raytrace(32, 40, 2, 1.0, 0.0, 0.3, 3.0, 1.0, outdir=str(tmp_path), max_steps=40, r_drag=0.01,
+                                integrator="leapfrog", log=lines.append)
+    (tmp_path / "run.log").write_text("\n".join(["banner"] * 10 + lines))
+    assert out["packet_frames"] >= 5
+    ld = drivers.load_data(tmp_path, times=[3, 5], offset=2)
+    assert (ld["nx"], ld["Npackets"], ld["f"], ld["Cg"], ld["Ug"]) == (32, 40, 3.0, 1.0, 0.3)
+    assert ld["omega"].shape == (40, out["packet_frames"]) and ld["edges"].size == 300 and ld["edges"][-1] == ld["omega"].max()
+    assert np.allclose(ld["omega"][:, 0], 6.0)                       # initial ring: omega0 = near_inertial_factor * f
+    for win in ld["windows"]:
+        lo, hi = win["frames"]
+        ref = O.histcounts(ld["omega"][:, lo - 1:hi].ravel(order="F"), ld["edges"])
+        assert np.array_equal(win["distribution"], ref) and int(ref.sum()) == 40 * (hi - lo + 1)
+        assert np.array_equal(win["energy"], ld["center"] * ref)
+    assert ld["mean_omega"].shape == (out["packet_frames"],) and abs(ld["mean_omega"][0] - 2.0) < 1e-12
