@@ -19,7 +19,7 @@ $(OBJ)/lagrange_kernels.o: $(CSRC)/lagrange_kernels.cu $(CSRC)/swrt_internal.h i
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 
-$(LIB): $(OBJ)/spectral_kernels.o $(OBJ)/lagrange_kernels.o $(OBJ)/misc_kernels.o $(OBJ)/swrt_api.o
+$(LIB): $(OBJ)/spectral_kernels.o $(OBJ)/lagrange_kernels.o $(OBJ)/nufft_kernels.o $(OBJ)/misc_kernels.o $(OBJ)/swrt_api.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
 
 $(ORACLE): oracle/swrt_oracle.c

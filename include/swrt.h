@@ -38,6 +38,11 @@ extern "C" {
 /* field-evaluation mode */
 #define SWRT_MODE_SPECTRAL  0  /* exact Fourier-series sum (dense DMMA contraction)            */
 #define SWRT_MODE_LAGRANGE6 1  /* the reference's 6x6 Lagrange stencil, interpolate.m:12-49     */
+#define SWRT_MODE_NUFFT     2  /* the SAME exact Fourier series as SPECTRAL (<= 1e-12 of max|plane|), evaluated as a
+                                  type-2 non-uniform FFT: oversampled cuFFT grid of u,v per frame (setup) + an 18x18
+                                  kernel gather per evaluation, gradients from the kernel's analytic derivative (= the
+                                  spectral derivatives of SpectralScheme.m:20-23 / grid_U.m:6-9).  Cost independent of
+                                  nx.  No H plane (step_packet_xka is not available in this mode).               */
 
 /* integrator */
 #define SWRT_SCHEME_LEAPFROG   0  /* ode_symplectic.m:13-21,33-37                               */

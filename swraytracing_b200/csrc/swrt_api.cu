@@ -55,6 +55,11 @@ struct swrt_handle {
     double* grid[2] = {nullptr, nullptr};
     double* grid_blend = nullptr;
     int grid_npl = 0;
+    // NUFFT mode: (u,v) fine grids per slot + blend, deconvolution factors, nf-point FFT work
+    double* nufft_grid[2] = {nullptr, nullptr};
+    double* nufft_blend = nullptr;
+    double* nufft_invphi = nullptr;
+    void* nufft_fft = nullptr;            // FftWork* for the nf-point transforms
     // scratch
     int64_t scratch_cap = 0;
     double* e[kMaxPlanes] = {};
@@ -212,6 +217,9 @@ void fill_psi_args(const swrt_handle* h, double alpha, SpecArgs& a) {
     a.u_mean = alpha == 0.0 ? h->u_mean[0] : (1.0 - alpha) * h->u_mean[0] + alpha * h->u_mean[1];
 }
 
+int active_nufft_grid(swrt_handle* h, double alpha, const double** out);
+void fill_nufft_args(const swrt_handle* h, const double* grid, NufftArgs& a);
+
 // evaluate subset planes at device positions into device outputs out[c] (c indexes subset planes)
 int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd, const double* yd,
              double* const* out) {
@@ -228,6 +236,19 @@ int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd,
         a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
         a.inv_nx = (h->p.nx & (h->p.nx - 1)) == 0 ? 1.0 / h->p.nx : 0.0;
         CU(h, launch_spectral(a, SPEC_EVAL, mt, h->num_sms, h->stream));
+        h->launches++;
+        return SWRT_OK;
+    }
+    if (h->p.mode == SWRT_MODE_NUFFT) {
+        REQUIRE(h, sub == SUB_SIX || sub == SUB_UV, SWRT_ERR_STATE, "NUFFT mode has no H plane (step_packet_xka needs SPECTRAL or LAGRANGE6)");
+        const double* g = nullptr;
+        int rc = active_nufft_grid(h, alpha, &g);
+        if (rc) return rc;
+        NufftArgs a{};
+        fill_nufft_args(h, g, a);
+        a.n = n; a.xin = xd; a.yin = yd;
+        for (int c = 0; c < kSubsetN[sub]; c++) a.out[kSubsetIds[sub][c]] = out[c];
+        CU(h, launch_nufft_eval(a, h->stream));
         h->launches++;
         return SWRT_OK;
     }
@@ -345,6 +366,87 @@ int upload_plane(swrt_handle* h, const double* re, const double* im, size_t n, d
     return SWRT_OK;
 }
 
+// ---- NUFFT mode set-up ---------------------------------------------------------------------------
+// Gauss-Legendre nodes/weights on [-1,1] (Newton iteration on P_n)
+static void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w) {
+    x.assign(n, 0.0); w.assign(n, 0.0);
+    for (int i = 0; i < (n + 1) / 2; i++) {
+        double z = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 1.0;
+        for (int it = 0; it < 100; it++) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 0; j < n; j++) { const double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0); }
+            pp = n * (z * p1 - p2) / (z * z - 1.0);
+            const double z1 = z; z = z1 - p1 / pp;
+            if (fabs(z - z1) < 1e-16) break;
+        }
+        x[i] = -z; x[n - 1 - i] = z;
+        w[i] = w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+    }
+}
+// 1 / phihat(k), k = 0..kmax: phihat(k) = (w/2) * int_{-1}^{1} phi(z) cos(2 pi k (w/2) z / nf) dz  (unit fine-grid spacing)
+static int nufft_init(swrt_handle* h) {
+    if (h->nufft_invphi) return SWRT_OK;
+    const int nx = h->p.nx, nf = (int)(kNufftSigma * nx), nky = nx / 2;
+    std::vector<double> q, wq, inv(nky);
+    gauss_legendre(128, q, wq);
+    const double hw = kNufftW / 2.0;
+    for (int k = 0; k < nky; k++) {
+        double acc = 0.0;
+        for (size_t j = 0; j < q.size(); j++) {
+            const double phi = exp(kNufftBeta * (sqrt(fmax(0.0, 1.0 - q[j] * q[j])) - 1.0));
+            acc += wq[j] * phi * cos(2.0 * M_PI * k * hw * q[j] / nf);
+        }
+        inv[k] = 1.0 / (hw * acc);
+    }
+    CU(h, cudaMalloc(&h->nufft_invphi, nky * sizeof(double)));
+    CU(h, cudaMemcpy(h->nufft_invphi, inv.data(), nky * sizeof(double), cudaMemcpyHostToDevice));
+    FftWork* fw = new (std::nothrow) FftWork();
+    REQUIRE(h, fw, SWRT_ERR_ALLOC, "out of host memory");
+    h->nufft_fft = fw;
+    return fw->init(nf, h->stream, h->err);
+}
+// fine (u,v) grid of a slot from its u-hat, v-hat planes: deconvolve, zero-pad to nf, inverse FFT, interleave
+int nufft_grid_from_planes(swrt_handle* h, int slot) {
+    REQUIRE(h, h->slot_npl[slot] == 6, SWRT_ERR_STATE, "NUFFT mode has no H plane (step_packet_xka needs SPECTRAL or LAGRANGE6)");
+    int rc = nufft_init(h);
+    if (rc) return rc;
+    const int nx = h->p.nx, nf = (int)(kNufftSigma * nx);
+    const size_t n = (size_t)nf * nf;
+    if (!h->nufft_grid[slot]) CU(h, cudaMalloc(&h->nufft_grid[slot], 2 * n * sizeof(double)));
+    FftWork* fw = static_cast<FftWork*>(h->nufft_fft);
+    cufftSetStream(fw->plan, h->stream);
+    for (int c = 0; c < 2; c++) {
+        launch_nufft_spread(h->planes[slot][c], nx, nf, h->nufft_invphi, fw->full, h->stream);
+        if (cufftExecZ2Z(fw->plan, (cufftDoubleComplex*)fw->full, (cufftDoubleComplex*)fw->full, CUFFT_INVERSE) != CUFFT_SUCCESS)
+            return fail(h, SWRT_ERR_CUDA, "cufftExecZ2Z(nufft) failed");
+        launch_nufft_store(fw->full, nf, c, h->nufft_grid[slot], h->stream);
+        h->launches += 3;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    return SWRT_OK;
+}
+int active_nufft_grid(swrt_handle* h, double alpha, const double** out) {
+    REQUIRE(h, h->nufft_grid[0], SWRT_ERR_STATE, "flow slot 0 has not been set");
+    if (alpha == 0.0) { *out = h->nufft_grid[0]; return SWRT_OK; }
+    REQUIRE(h, h->nufft_grid[1] && h->slot_set[1], SWRT_ERR_STATE, "alpha = %g but flow slot 1 has not been set", alpha);
+    if (alpha == 1.0) { *out = h->nufft_grid[1]; return SWRT_OK; }
+    const int nf = (int)(kNufftSigma * h->p.nx);
+    const size_t nd = (size_t)2 * nf * nf;
+    if (!h->nufft_blend) CU(h, cudaMalloc(&h->nufft_blend, nd * sizeof(double)));
+    launch_axpby(h->nufft_blend, h->nufft_grid[0], h->nufft_grid[1], 1.0 - alpha, alpha, nd, h->stream);   // interpolate_U.m:19-23
+    h->launches++;
+    *out = h->nufft_blend;
+    return SWRT_OK;
+}
+void fill_nufft_args(const swrt_handle* h, const double* grid, NufftArgs& a) {
+    a.grid = reinterpret_cast<const double2*>(grid);
+    a.nf = (int)(kNufftSigma * h->p.nx);
+    a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx; a.beta = kNufftBeta;
+    a.dscale = -kNufftSigma / (a.dx * (kNufftW / 2.0));
+    a.f2 = h->p.f * h->p.f; a.gH = h->p.gH;
+}
+
 // build the Lagrange grid of a slot from its spectral planes (k2g of every plane): grid_U.m:11-17
 int grid_from_planes(swrt_handle* h, int slot) {
     const int nx = h->p.nx, npl = h->slot_npl[slot];
@@ -391,7 +493,7 @@ int swrt_create(const swrt_params* p, swrt_handle** out) {
     *out = nullptr;
     if (p->nx < 8 || (p->nx & 1)) return fail(nullptr, SWRT_ERR_ARG, "swrt_create: nx must be even and >= 8 (got %d)", p->nx);
     if (!(p->L > 0)) return fail(nullptr, SWRT_ERR_ARG, "swrt_create: L must be positive");
-    if (p->mode != SWRT_MODE_SPECTRAL && p->mode != SWRT_MODE_LAGRANGE6)
+    if (p->mode != SWRT_MODE_SPECTRAL && p->mode != SWRT_MODE_LAGRANGE6 && p->mode != SWRT_MODE_NUFFT)
         return fail(nullptr, SWRT_ERR_ARG, "swrt_create: unknown mode %d", p->mode);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -434,6 +536,8 @@ int swrt_destroy(swrt_handle* h) {
         dfree(h->grid[s]);
     }
     dfree(h->grid_blend);
+    dfree(h->nufft_grid[0]); dfree(h->nufft_grid[1]); dfree(h->nufft_blend); dfree(h->nufft_invphi);
+    if (h->nufft_fft) { delete static_cast<FftWork*>(h->nufft_fft); h->nufft_fft = nullptr; }
     for (auto& st : h->stacks) { dfree(st.slot[0]); dfree(st.slot[1]); dfree(st.blend); }
     for (auto& p : h->e) dfree(p);
     dfree(h->xs); dfree(h->ys); dfree(h->ax); dfree(h->ay); dfree(h->om); dfree(h->Om);
@@ -457,6 +561,7 @@ static int finish_spectral_slot(swrt_handle* h, int slot, int npl) {
     h->slot_npl[slot] = npl;
     invalidate_slot(h, slot);
     if (h->p.mode == SWRT_MODE_LAGRANGE6) return grid_from_planes(h, slot);
+    if (h->p.mode == SWRT_MODE_NUFFT) return nufft_grid_from_planes(h, slot);
     CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
 }
@@ -566,6 +671,7 @@ int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* 
         if (npl == 6) dfree(h->planes[slot][6]);
         if (rc == SWRT_OK) { h->slot_set[slot] = true; h->slot_npl[slot] = npl; h->psi_ok[slot] = false; invalidate_slot(h, slot); }
         cudaStreamSynchronize(h->stream);
+        if (rc == SWRT_OK && h->p.mode == SWRT_MODE_NUFFT) rc = nufft_grid_from_planes(h, slot);
     }
     cudaStreamSynchronize(h->stream);              // the temporaries are released on return
     if (rc == SWRT_OK) CU(h, cudaGetLastError());
@@ -736,6 +842,14 @@ static int step_leapfrog(swrt_handle* h, double dt, int nsteps, double alpha0, d
                 }
             }
 #endif
+        } else if (h->p.mode == SWRT_MODE_NUFFT) {
+            const double* g = nullptr;
+            if ((rc = active_nufft_grid(h, alpha, &g))) return rc;
+            NufftArgs a{};
+            fill_nufft_args(h, g, a);
+            a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.dt = dt; a.nsteps = inner;
+            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
+            CU(h, launch_nufft_leapfrog(a, h->stream));
         } else {
             LagArgs a{};
             if ((rc = active_grid(h, alpha, &a.grid))) return rc;
@@ -774,7 +888,8 @@ static int step_rk4(swrt_handle* h, bool xka, double dt, int nsteps, double alph
         h->timing_valid = true;
         return SWRT_OK;
     }
-    // SPECTRAL: continuous ray equations composed point-wise; 5 evaluations per step
+    // SPECTRAL / NUFFT: continuous ray equations composed point-wise; 5 evaluations per step
+    REQUIRE(h, !(xka && h->p.mode == SWRT_MODE_NUFFT), SWRT_ERR_STATE, "step_packet_xka needs the H plane: not available in NUFFT mode");
     if ((rc = ensure_scratch(h, h->n))) return rc;
     CU(h, cudaEventRecord(h->ev0, h->stream));
     for (int j = 0; j < nsteps; j++) {
@@ -850,7 +965,7 @@ static int compute_omega(swrt_handle* h, double alpha, bool need_abs) {
     if (need_abs) {
         REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "absolute frequency needs a flow");
         double* outs[2] = {h->e[0], h->e[1]};
-        if (h->p.mode == SWRT_MODE_SPECTRAL) {
+        if (h->p.mode != SWRT_MODE_LAGRANGE6) {
             if ((rc = eval_dev(h, SUB_UV, alpha, h->n, h->x, h->y, outs))) return rc;
         } else if ((rc = eval_dev(h, SUB_SIX, alpha, h->n, h->x, h->y, h->e))) return rc;
     }
@@ -1606,6 +1721,7 @@ double swrt_work_per_eval(const swrt_handle* h, int nplanes) {
         // flops per folded complex MAC ... = 2 * nplanes * nx^2 for the unpadded problem
         return 2.0 * nplanes * (double)h->p.nx * (double)h->p.nx;
     }
+    if (h->p.mode == SWRT_MODE_NUFFT) return (double)kNufftW * kNufftW * 16.0;   // gathered bytes: w^2 = 324 (u,v) nodes, all six planes
     return 36.0 * nplanes * 8.0;   // gathered bytes
 }
 

@@ -123,6 +123,28 @@ void launch_diag(long long n, const double* x, const double* y, const double* k,
                  const double* omega, const double* Omega_abs, double* out8_dev, cudaStream_t st);
 void launch_fill(double* p, double v, long long n, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------
+// NUFFT mode (type-2 non-uniform FFT evaluation of the same Fourier series; nufft_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+constexpr int kNufftW = 18;             // ES-kernel width in fine-grid points (16 gives 2e-12 on the gradients at 512^2, 18 gives 1.4e-13)
+constexpr double kNufftSigma = 2.0;     // oversampling: nf = 2 nx
+constexpr double kNufftBeta = 2.30 * kNufftW;
+struct NufftArgs {
+    const double2* grid;    // (u,v) fine grid, [iy*nf + ix]
+    int nf;
+    long long n;
+    const double* xin; const double* yin;
+    double* x; double* y; double* k; double* l;
+    double* out[6];
+    double dx, nxd, beta, dscale;       // dscale = -sigma / (dx * w/2): d/dx of the kernel argument
+    double f2, gH, dt;
+    int nsteps;
+};
+void launch_nufft_spread(const double2* half, int nx, int nf, const double* invphi_dev, double2* full, cudaStream_t st);
+void launch_nufft_store(const double2* full, int nf, int c, double* grid2, cudaStream_t st);
+cudaError_t launch_nufft_eval(const NufftArgs& a, cudaStream_t st);
+cudaError_t launch_nufft_leapfrog(const NufftArgs& a, cudaStream_t st);
+
 struct Bs23Args {          // ode23 work arrays, component order x,y,k,l
     long long n;
     double* y[4];          // the packet state itself

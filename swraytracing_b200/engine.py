@@ -14,7 +14,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libswrt.so"
 
-MODE_SPECTRAL, MODE_LAGRANGE6 = 0, 1
+MODE_SPECTRAL, MODE_LAGRANGE6, MODE_NUFFT = 0, 1, 2
 SCHEME_LEAPFROG, SCHEME_RK4_PACKET, SCHEME_RK4_XKA = 0, 1, 2
 HIST_INTRINSIC, HIST_ABSOLUTE = 0, 1
 FLAG_RHS_GH = 1

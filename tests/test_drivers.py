@@ -325,3 +325,19 @@ def test_load_data_reads_back_driver_output(tmp_path):
         assert np.array_equal(win["distribution"], ref) and int(ref.sum()) == 40 * (hi - lo + 1)
         assert np.array_equal(win["energy"], ld["center"] * ref)
     assert ld["mean_omega"].shape == (out["packet_frames"],) and abs(ld["mean_omega"][0] - 2.0) < 1e-12
+
+
+@pytest.mark.gpu
+def test_production_driver_in_nufft_mode_matches_dense_spectral(tmp_path):
+    """qgsw_raytrace end to end (device QG frames -> flow slots -> per-step ode23) with the NUFFT evaluation instead of
+    the dense contraction: same accept/reject decisions, packets equal to 1e-9"""
+    import swraytracing_b200 as S
+    from swraytracing_b200 import drivers
+    outs = []
+    for mode, sub in ((S.MODE_SPECTRAL, "a"), (S.MODE_NUFFT, "b")):
+        outs.append(drivers.qgsw_raytrace(32, 64, 2, 1.0, 0.0, 0.3, 3.0, 1.0, outdir=str(tmp_path / sub), max_steps=12, r_drag=0.01,
+                                          mode=mode, log=lambda s: None))
+    a, b = outs
+    assert (a["ode23_steps"], a["ode23_failed"], a["packet_steps"]) == (b["ode23_steps"], b["ode23_failed"], b["packet_steps"])
+    for pa, pb in zip(a["packets"], b["packets"]):
+        assert np.abs(pa - pb).max() < 1e-9

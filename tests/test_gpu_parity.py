@@ -832,3 +832,105 @@ def test_scheme_diagnostics_and_difference_scheme_cross_check():
         assert np.abs(sch.okuboWeiss(x) - osch.okuboWeiss(x)).max() < 1e-12
     zeta = -2 * km ** 2 * ds.streamfunction(x[:, 0], x[:, 1])
     assert np.abs(R.SpectralScheme(L, nx, psi).vorticity(x) - zeta).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# NUFFT mode: the same exact Fourier series as SPECTRAL (P2 contract), evaluated by a type-2 non-uniform FFT
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx", [16, 32, 36, 48, 64, 128, 256])
+def test_nufft_eval_vs_exact_sum(nx):
+    L = 2 * np.pi; dx = L / nx
+    psik, planes = make_flow(nx)
+    n = 517 if nx <= 64 else 200
+    x, y, k, l = make_packets(n, L)
+    x[:4] = [0.0, -dx, 5 * dx, L]; y[:4] = [0.0, 2 * dx, -L, 7 * dx]                 # grid nodes: kernel argument hits |z| = 1
+    ref = CO.spectral_eval(x, y, planes, dx, nx, precise=True)
+    with S.Engine(nx, L, F0, GH0, S.MODE_NUFFT) as e:
+        e.set_flow_spectral(psik)
+        e.set_packets(x, y, k, l)
+        got = e.eval()
+        assert scaled_err(got, ref) < TOL_FIELD, [float(np.abs(got[c] - ref[c]).max() / np.abs(ref[c]).max()) for c in range(6)]
+        assert np.array_equal(e.eval_at(x[::-1].copy(), y[::-1].copy())[:, ::-1], got)
+        # the six planes handed over explicitly (grid_U output as coefficients) and as grids: same flow, same answer
+        e.set_flow_planes_spectral(planes)
+        assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+        e.set_flow_grid(*[O.k2g(p) for p in planes])
+        assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
+
+
+@pytest.mark.gpu
+def test_nufft_white_spectrum_L20_shear_and_time_blend():
+    # the hardest spectrum (flat up to the truncation), the two-layer driver's domain (L = 20, mean shear), two frames
+    nx = 64; L = 20.0; dx = L / nx
+    kap = 2 * np.pi / L
+    kx_, ky_ = O.wavenumbers(nx)
+    rs = np.random.RandomState(12)
+    psis = [(rs.randn(nx - 1, nx // 2) + 1j * rs.randn(nx - 1, nx // 2)) * 1e-3 for _ in range(2)]
+    pl = []
+    for p in psis:
+        q = O.velocity_planes_k(p, kap * kx_, kap * ky_)
+        q[0] = q[0].copy(); q[0][nx // 2 - 1, 0] += 0.5
+        pl.append(q)
+    x, y, k, l = make_packets(300, L, seed=2)
+    with S.Engine(nx, L, F0, GH0, S.MODE_NUFFT) as e:
+        e.set_flow_spectral(psis[0], slot=0, u_mean=0.5); e.set_flow_spectral(psis[1], slot=1, u_mean=0.5)
+        for alpha in (0.0, 0.3, 1.0):
+            blend = [(1 - alpha) * a + alpha * b for a, b in zip(pl[0], pl[1])]
+            ref = CO.spectral_eval(x, y, blend, dx, nx, precise=True)
+            assert scaled_err(e.eval_at(x, y, alpha), ref) < TOL_FIELD, alpha
+        e.set_packets(x, y, k, l)
+        d = np.stack(e.rhs(0.3))
+        blend = [0.7 * a + 0.3 * b for a, b in zip(pl[0], pl[1])]
+        want = np.stack(O.rhs_from_eval(CO.spectral_eval(x, y, blend, dx, nx, precise=True), k, l, F0, 1.0))
+        assert scaled_err(d, want) < TOL_FIELD
+
+
+@pytest.mark.gpu
+def test_nufft_trajectories_ode23_and_rk4_match_spectral_oracle():
+    nx = int(GOLD["nx"]); L = float(GOLD["L"]); dx = L / nx; dt = float(GOLD["dt"])
+    psik, planes = make_flow(nx)
+    x, y, k, l = make_packets(400, L)
+    ref = CO.leapfrog_spectral(x, y, k, l, planes, dx, nx, F0, GH0, dt, 100)
+    with S.Engine(nx, L, F0, GH0, S.MODE_NUFFT) as e, S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as es:
+        for eng in (e, es):
+            eng.set_flow_spectral(psik); eng.set_packets(x, y, k, l)
+        e.step(S.SCHEME_LEAPFROG, dt, 100)
+        assert np.abs(np.stack(e.get_packets()) - np.stack(ref)).max() < TOL_TRAJ
+        # fused 100 steps == 100 single-step launches, bit for bit
+        e.set_packets(x, y, k, l)
+        for _ in range(100):
+            e.step(S.SCHEME_LEAPFROG, dt, 1)
+        e2 = np.stack(e.get_packets())
+        e.set_packets(x, y, k, l); e.step(S.SCHEME_LEAPFROG, dt, 100)
+        assert np.array_equal(e2, np.stack(e.get_packets()))
+        # ode23 and step_packet run through the mode-independent stage code: same decisions / states as SPECTRAL mode
+        for eng in (e, es):
+            eng.set_packets(x, y, k, l)
+        st, sts = R.ode23(e, [0.0, 20 * dt], None), R.ode23(es, [0.0, 20 * dt], None)
+        assert (st["nsteps"], st["nfailed"]) == (sts["nsteps"], sts["nfailed"])
+        assert np.abs(np.stack(e.get_packets()) - np.stack(es.get_packets())).max() < TOL_TRAJ
+        for eng in (e, es):
+            eng.set_packets(x, y, k, l); eng.step(S.SCHEME_RK4_PACKET, dt, 5)
+        assert np.abs(np.stack(e.get_packets()) - np.stack(es.get_packets())).max() < TOL_TRAJ
+        edges = np.linspace(0, 9, 300)
+        assert np.array_equal(e.hist_omega(edges, kind=S.HIST_ABSOLUTE), es.hist_omega(edges, kind=S.HIST_ABSOLUTE))
+        with pytest.raises(S.SwrtError):
+            e.step(S.SCHEME_RK4_XKA, dt, 1)                               # no H plane in this mode
+
+
+@pytest.mark.gpu
+def test_nufft_full_size_C4_shard_agrees_with_dense_contraction():
+    """512^2, L = 20, shear, two-frame blend: the dense DMMA contraction and the NUFFT gather are two evaluations of one
+    Fourier series; on 4,096 packets of the C4 workload they agree to 1e-12 of max|plane|, and 16 leapfrog steps to 1e-9"""
+    w = W.make_workload("C4", n_packets=4096)
+    outs = []
+    for mode in (S.MODE_SPECTRAL, S.MODE_NUFFT):
+        with S.Engine(w.nx, w.L, w.f, w.gH, mode) as e:
+            e.set_flow_spectral(w.psik, 0, u_mean=w.u_mean); e.set_flow_spectral(w.psik2, 1, u_mean=w.u_mean)
+            e.set_packets(w.x, w.y, w.k, w.l)
+            ev = e.eval(0.4)
+            e.step(S.SCHEME_LEAPFROG, w.dt / 16, 16, 1 / 32, 1 / 16)
+            outs.append((ev, np.stack(e.get_packets())))
+    assert scaled_err(outs[1][0], outs[0][0]) < TOL_FIELD
+    assert np.abs(outs[1][1] - outs[0][1]).max() < TOL_TRAJ
