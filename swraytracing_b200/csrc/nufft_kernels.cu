@@ -20,11 +20,7 @@ namespace {
 
 constexpr int W = kNufftW;          // kernel width in fine-grid points
 constexpr double HALF_W = W / 2.0;
-#ifndef SWRT_NUFFT_UNROLL
-#define SWRT_NUFFT_UNROLL 1
-#endif
-constexpr int kRowUnroll = SWRT_NUFFT_UNROLL;   // rows of the stencil per unrolled loop body (1, 4, 18: within 5 %; L1TEX-bound)
-constexpr int kBlock = 64;          // one packet per thread; small blocks balance small ensembles over 148 SMs (164 regs -> 6 blocks/SM)
+constexpr int kBlock = 128;         // four lanes per packet: 32 packets per block
 
 __device__ __forceinline__ double reduced_coord(double x, double dx, double nxd) {
     // xl = mod(x/dx, nx), the reduced coordinate of interpolate.m:21 (same as the other two modes)
@@ -53,58 +49,89 @@ __device__ __forceinline__ void stencil_origin(double xl, int nf, int& base, dou
     base = i0;
 }
 
-// u,v,ux,uy,vx,vy at one point.  grid: double2 (u,v) at [(iy*nf + ix)], x fastest (cuFFT's output order).
+// u,v,ux,uy,vx,vy at one point, computed by a QUAD of lanes (4 lanes per packet, 8 packets per warp).
+// grid: double2 (u,v) at [(iy*nf + ix)], x fastest (cuFFT's output order).  Lane q of the quad owns the stencil
+// columns a = q, q+4, q+8, ... (so the quad's four loads of one round are four consecutive 16-byte nodes: one 64-byte
+// segment instead of four scattered lines -- the kernel is bound by L1 data-pipe wavefronts) and evaluates the kernel
+// for those columns and for the rows b = q, q+4, ...; row weights travel inside the quad by shuffle.  All four lanes end
+// with bit-identical sums (the butterfly adds are commutative), so the redundant packet state stays consistent.
+constexpr int QR = (W + 3) / 4;      // columns (and rows) owned per lane, the last round partly empty
+
 __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, int nf, double beta, double dscale,
-                                            double xl, double yl, double* F) {
+                                            double xl, double yl, int q, int quad_base, double* F) {
     int ib, jb; double tx, ty;
     stencil_origin(xl, nf, ib, tx);
     stencil_origin(yl, nf, jb, ty);
-    double wx0[W], wx1[W];
+    double wx0[QR], wx1[QR], my0[QR], my1[QR];
+    int ixr[QR];
 #pragma unroll
-    for (int a = 0; a < W; a++) es_kernel((tx + (double)a) * (1.0 / HALF_W), beta, wx0[a], wx1[a]);
+    for (int r = 0; r < QR; r++) {
+        const int a = q + 4 * r;
+        const bool on = a < W;
+        es_kernel((tx + (double)a) * (1.0 / HALF_W), beta, wx0[r], wx1[r]);
+        es_kernel((ty + (double)a) * (1.0 / HALF_W), beta, my0[r], my1[r]);
+        if (!on) { wx0[r] = 0.0; wx1[r] = 0.0; my0[r] = 0.0; my1[r] = 0.0; }
+        int ix = ib + (on ? a : 0); if (ix >= nf) ix -= nf;
+        ixr[r] = ix;
+    }
     double U = 0, V = 0, Ux = 0, Uy = 0, Vx = 0, Vy = 0;
-#pragma unroll (kRowUnroll)
+#pragma unroll
     for (int b = 0; b < W; b++) {
-        double wy0, wy1;
-        es_kernel((ty + (double)b) * (1.0 / HALF_W), beta, wy0, wy1);
+        const double wy0 = __shfl_sync(0xffffffffu, my0[b >> 2], quad_base | (b & 3));
+        const double wy1 = __shfl_sync(0xffffffffu, my1[b >> 2], quad_base | (b & 3));
         int iy = jb + b; if (iy >= nf) iy -= nf;
         const double2* row = grid + (size_t)iy * nf;
         double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0;
 #pragma unroll
-        for (int a = 0; a < W; a++) {
-            int ix = ib + a; if (ix >= nf) ix -= nf;
-            const double2 g = __ldg(row + ix);
-            su0 = fma(wx0[a], g.x, su0); su1 = fma(wx1[a], g.x, su1);
-            sv0 = fma(wx0[a], g.y, sv0); sv1 = fma(wx1[a], g.y, sv1);
+        for (int r = 0; r < QR; r++) {
+            const double2 g = __ldg(row + ixr[r]);
+            su0 = fma(wx0[r], g.x, su0); su1 = fma(wx1[r], g.x, su1);
+            sv0 = fma(wx0[r], g.y, sv0); sv1 = fma(wx1[r], g.y, sv1);
         }
         U = fma(wy0, su0, U);  Ux = fma(wy0, su1, Ux); Uy = fma(wy1, su0, Uy);
         V = fma(wy0, sv0, V);  Vx = fma(wy0, sv1, Vx); Vy = fma(wy1, sv0, Vy);
     }
-    F[0] = U; F[1] = V; F[2] = Ux * dscale; F[3] = Uy * dscale; F[4] = Vx * dscale; F[5] = Vy * dscale;
+    double o[6] = {U, V, Ux * dscale, Uy * dscale, Vx * dscale, Vy * dscale};
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        double v = o[c];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        F[c] = v;
+    }
 }
 
-__global__ void __launch_bounds__(kBlock, 6) nufft_eval_kernel(const NufftArgs a) {
-    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.n) return;
+__global__ void __launch_bounds__(kBlock) nufft_eval_kernel(const NufftArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t >> 2;
+    const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
+    const long long pc = p < a.n ? p : a.n - 1;              // idle quads of the last warp still take part in the shuffles
     double F[6];
-    nufft_eval6(a.grid, a.nf, a.beta, a.dscale, reduced_coord(a.xin[p], a.dx, a.nxd), reduced_coord(a.yin[p], a.dx, a.nxd), F);
+    nufft_eval6(a.grid, a.nf, a.beta, a.dscale, reduced_coord(a.xin[pc], a.dx, a.nxd), reduced_coord(a.yin[pc], a.dx, a.nxd), q, qb, F);
+    if (p < a.n && q == 0) {
 #pragma unroll
-    for (int c = 0; c < 6; c++)
-        if (a.out[c]) a.out[c][p] = F[c];
+        for (int c = 0; c < 6; c++)
+            if (a.out[c]) a.out[c][p] = F[c];
+    }
 }
 
 // ode_symplectic.m:13-21,33-37 with the six planes from the NUFFT evaluation at x1
-__global__ void __launch_bounds__(kBlock, 6) nufft_leapfrog_kernel(const NufftArgs a) {
-    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.n) return;
-    double x = a.x[p], y = a.y[p], k = a.k[p], l = a.l[p];
+#ifndef SWRT_NUFFT_MINB
+#define SWRT_NUFFT_MINB 5     /* 96 registers: 4 / 5 / 6 / 8 blocks per SM give 1.75 / 1.84 / 1.70 / 1.15e9 packet-steps/s at C3 */
+#endif
+__global__ void __launch_bounds__(kBlock, SWRT_NUFFT_MINB) nufft_leapfrog_kernel(const NufftArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t >> 2;
+    const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
+    const long long pc = p < a.n ? p : a.n - 1;
+    double x = a.x[pc], y = a.y[pc], k = a.k[pc], l = a.l[pc];
     const double h = 0.5 * a.dt;
     for (int st = 0; st < a.nsteps; st++) {
         double om = sqrt(a.f2 + a.gH * (k * k + l * l));
         x = x + h * (a.gH * k / om);
         y = y + h * (a.gH * l / om);
         double F[6];
-        nufft_eval6(a.grid, a.nf, a.beta, a.dscale, reduced_coord(x, a.dx, a.nxd), reduced_coord(y, a.dx, a.nxd), F);
+        nufft_eval6(a.grid, a.nf, a.beta, a.dscale, reduced_coord(x, a.dx, a.nxd), reduced_coord(y, a.dx, a.nxd), q, qb, F);
         x = x + a.dt * F[0];
         y = y + a.dt * F[1];
         const double k0 = k, l0 = l;
@@ -114,7 +141,7 @@ __global__ void __launch_bounds__(kBlock, 6) nufft_leapfrog_kernel(const NufftAr
         x = x + h * (a.gH * k / om);
         y = y + h * (a.gH * l / om);
     }
-    a.x[p] = x; a.y[p] = y; a.k[p] = k; a.l[p] = l;
+    if (p < a.n && q == 0) { a.x[p] = x; a.y[p] = y; a.k[p] = k; a.l[p] = l; }
 }
 
 // half-plane coefficients (g2k layout, the ky = 0 symmetrisation of fulspec.m:16 applied) -> deconvolved, zero-padded
@@ -156,12 +183,12 @@ void launch_nufft_store(const double2* full, int nf, int c, double* grid2, cudaS
 }
 cudaError_t launch_nufft_eval(const NufftArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    nufft_eval_kernel<<<(unsigned)((a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
+    nufft_eval_kernel<<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_nufft_leapfrog(const NufftArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    nufft_leapfrog_kernel<<<(unsigned)((a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
+    nufft_leapfrog_kernel<<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
     return cudaGetLastError();
 }
 
