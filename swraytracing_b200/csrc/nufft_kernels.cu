@@ -10,7 +10,8 @@
 //       i kx u-hat, ... of SpectralScheme.m:20-23 / grid_U.m:6-9.
 // Accuracy (tests/test_gpu_parity.py): <= 1e-12 of max|plane| against the exact trig-sum oracle on all six planes
 // (measured 1e-14 for u,v and 2e-13 for the gradients).  Work per evaluation is 324 nodes x 16 bytes, independent of
-// nx, against 6 nx^2 flops for the dense contraction: the crossover is below nx = 64.
+// nx, against 6 nx^2 flops for the dense contraction: the crossover is below nx = 64.  An optional H plane
+// (step_packet_xka, cg_sw.m) rides on a second, 8-byte-per-node fine grid gathered with the same weights.
 // Replaces: SpectralScheme.U / grad_U (SpectralScheme.m:45-68), interpolate_U.m:5-23, ode_symplectic.m:13-37.
 #include "swrt_internal.h"
 
@@ -57,8 +58,9 @@ __device__ __forceinline__ void stencil_origin(double xl, int nf, int& base, dou
 // with bit-identical sums (the butterfly adds are commutative), so the redundant packet state stays consistent.
 constexpr int QR = (W + 3) / 4;      // columns (and rows) owned per lane, the last round partly empty
 
-__device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, int nf, double beta, double dscale,
-                                            double xl, double yl, int q, int quad_base, double* F) {
+template <bool WITH_H>
+__device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, const double* __restrict__ hgrid, int nf,
+                                            double beta, double dscale, double xl, double yl, int q, int quad_base, double* F) {
     int ib, jb; double tx, ty;
     stencil_origin(xl, nf, ib, tx);
     stencil_origin(yl, nf, jb, ty);
@@ -74,26 +76,28 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, in
         int ix = ib + (on ? a : 0); if (ix >= nf) ix -= nf;
         ixr[r] = ix;
     }
-    double U = 0, V = 0, Ux = 0, Uy = 0, Vx = 0, Vy = 0;
+    double U = 0, V = 0, Ux = 0, Uy = 0, Vx = 0, Vy = 0, Hs = 0;
 #pragma unroll
     for (int b = 0; b < W; b++) {
         const double wy0 = __shfl_sync(0xffffffffu, my0[b >> 2], quad_base | (b & 3));
         const double wy1 = __shfl_sync(0xffffffffu, my1[b >> 2], quad_base | (b & 3));
         int iy = jb + b; if (iy >= nf) iy -= nf;
         const double2* row = grid + (size_t)iy * nf;
-        double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0;
+        double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0, sh0 = 0;
 #pragma unroll
         for (int r = 0; r < QR; r++) {
             const double2 g = __ldg(row + ixr[r]);
             su0 = fma(wx0[r], g.x, su0); su1 = fma(wx1[r], g.x, su1);
             sv0 = fma(wx0[r], g.y, sv0); sv1 = fma(wx1[r], g.y, sv1);
+            if constexpr (WITH_H) sh0 = fma(wx0[r], __ldg(hgrid + (size_t)iy * nf + ixr[r]), sh0);
         }
         U = fma(wy0, su0, U);  Ux = fma(wy0, su1, Ux); Uy = fma(wy1, su0, Uy);
         V = fma(wy0, sv0, V);  Vx = fma(wy0, sv1, Vx); Vy = fma(wy1, sv0, Vy);
+        if constexpr (WITH_H) Hs = fma(wy0, sh0, Hs);
     }
-    double o[6] = {U, V, Ux * dscale, Uy * dscale, Vx * dscale, Vy * dscale};
+    double o[7] = {U, V, Ux * dscale, Uy * dscale, Vx * dscale, Vy * dscale, Hs};
 #pragma unroll
-    for (int c = 0; c < 6; c++) {
+    for (int c = 0; c < (WITH_H ? 7 : 6); c++) {
         double v = o[c];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -101,16 +105,18 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, in
     }
 }
 
+template <bool WITH_H>
 __global__ void __launch_bounds__(kBlock) nufft_eval_kernel(const NufftArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long p = t >> 2;
     const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
     const long long pc = p < a.n ? p : a.n - 1;              // idle quads of the last warp still take part in the shuffles
-    double F[6];
-    nufft_eval6(a.grid, a.nf, a.beta, a.dscale, reduced_coord(a.xin[pc], a.dx, a.nxd), reduced_coord(a.yin[pc], a.dx, a.nxd), q, qb, F);
+    double F[7];
+    nufft_eval6<WITH_H>(a.grid, a.hgrid, a.nf, a.beta, a.dscale, reduced_coord(a.xin[pc], a.dx, a.nxd),
+                        reduced_coord(a.yin[pc], a.dx, a.nxd), q, qb, F);
     if (p < a.n && q == 0) {
 #pragma unroll
-        for (int c = 0; c < 6; c++)
+        for (int c = 0; c < (WITH_H ? 7 : 6); c++)
             if (a.out[c]) a.out[c][p] = F[c];
     }
 }
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_MINB) nufft_leapfrog_kernel
         x = x + h * (a.gH * k / om);
         y = y + h * (a.gH * l / om);
         double F[6];
-        nufft_eval6(a.grid, a.nf, a.beta, a.dscale, reduced_coord(x, a.dx, a.nxd), reduced_coord(y, a.dx, a.nxd), q, qb, F);
+        nufft_eval6<false>(a.grid, nullptr, a.nf, a.beta, a.dscale, reduced_coord(x, a.dx, a.nxd), reduced_coord(y, a.dx, a.nxd), q, qb, F);
         x = x + a.dt * F[0];
         y = y + a.dt * F[1];
         const double k0 = k, l0 = l;
@@ -165,10 +171,10 @@ __global__ void nufft_spread_kernel(const double2* __restrict__ half, int nx, in
     }
     full[idx] = v;
 }
-// real part of the inverse transform -> component c of the interleaved (u,v) fine grid
-__global__ void nufft_store_kernel(const double2* __restrict__ full, size_t n, int c, double* __restrict__ grid2) {
+// real part of the inverse transform -> component c of a fine grid with `stride` doubles per node
+__global__ void nufft_store_kernel(const double2* __restrict__ full, size_t n, int c, int stride, double* __restrict__ grid2) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) grid2[2 * i + c] = full[i].x;
+    if (i < n) grid2[(size_t)stride * i + c] = full[i].x;
 }
 
 }  // namespace
@@ -177,13 +183,14 @@ void launch_nufft_spread(const double2* half, int nx, int nf, const double* invp
     size_t n = (size_t)nf * nf;
     nufft_spread_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(half, nx, nf, invphi_dev, full);
 }
-void launch_nufft_store(const double2* full, int nf, int c, double* grid2, cudaStream_t st) {
+void launch_nufft_store(const double2* full, int nf, int c, int stride, double* grid2, cudaStream_t st) {
     size_t n = (size_t)nf * nf;
-    nufft_store_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(full, n, c, grid2);
+    nufft_store_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(full, n, c, stride, grid2);
 }
 cudaError_t launch_nufft_eval(const NufftArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    nufft_eval_kernel<<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
+    if (a.hgrid) nufft_eval_kernel<true><<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
+    else nufft_eval_kernel<false><<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_nufft_leapfrog(const NufftArgs& a, cudaStream_t st) {

@@ -58,6 +58,8 @@ struct swrt_handle {
     // NUFFT mode: (u,v) fine grids per slot + blend, deconvolution factors, nf-point FFT work
     double* nufft_grid[2] = {nullptr, nullptr};
     double* nufft_blend = nullptr;
+    double* nufft_h[2] = {nullptr, nullptr};   // optional H fine grid per slot (step_packet_xka)
+    double* nufft_hblend = nullptr;
     double* nufft_invphi = nullptr;
     void* nufft_fft = nullptr;            // FftWork* for the nf-point transforms
     // scratch
@@ -217,7 +219,7 @@ void fill_psi_args(const swrt_handle* h, double alpha, SpecArgs& a) {
     a.u_mean = alpha == 0.0 ? h->u_mean[0] : (1.0 - alpha) * h->u_mean[0] + alpha * h->u_mean[1];
 }
 
-int active_nufft_grid(swrt_handle* h, double alpha, const double** out);
+int active_nufft_grid(swrt_handle* h, double alpha, const double** out, const double** hout);
 void fill_nufft_args(const swrt_handle* h, const double* grid, NufftArgs& a);
 
 // evaluate subset planes at device positions into device outputs out[c] (c indexes subset planes)
@@ -240,12 +242,15 @@ int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd,
         return SWRT_OK;
     }
     if (h->p.mode == SWRT_MODE_NUFFT) {
-        REQUIRE(h, sub == SUB_SIX || sub == SUB_UV, SWRT_ERR_STATE, "NUFFT mode has no H plane (step_packet_xka needs SPECTRAL or LAGRANGE6)");
-        const double* g = nullptr;
-        int rc = active_nufft_grid(h, alpha, &g);
+        REQUIRE(h, sub != SUB_PSI3, SWRT_ERR_ARG, "bad plane subset");
+        const bool need_h = (sub == SUB_SEVEN || sub == SUB_UVH);
+        const double *g = nullptr, *gh = nullptr;
+        int rc = active_nufft_grid(h, alpha, &g, need_h ? &gh : nullptr);
         if (rc) return rc;
+        REQUIRE(h, !need_h || gh, SWRT_ERR_STATE, "flow has no H plane (needed by this scheme)");
         NufftArgs a{};
         fill_nufft_args(h, g, a);
+        a.hgrid = gh;
         a.n = n; a.xin = xd; a.yin = yd;
         for (int c = 0; c < kSubsetN[sub]; c++) a.out[kSubsetIds[sub][c]] = out[c];
         CU(h, launch_nufft_eval(a, h->stream));
@@ -407,7 +412,6 @@ static int nufft_init(swrt_handle* h) {
 }
 // fine (u,v) grid of a slot from its u-hat, v-hat planes: deconvolve, zero-pad to nf, inverse FFT, interleave
 int nufft_grid_from_planes(swrt_handle* h, int slot) {
-    REQUIRE(h, h->slot_npl[slot] == 6, SWRT_ERR_STATE, "NUFFT mode has no H plane (step_packet_xka needs SPECTRAL or LAGRANGE6)");
     int rc = nufft_init(h);
     if (rc) return rc;
     const int nx = h->p.nx, nf = (int)(kNufftSigma * nx);
@@ -419,24 +423,41 @@ int nufft_grid_from_planes(swrt_handle* h, int slot) {
         launch_nufft_spread(h->planes[slot][c], nx, nf, h->nufft_invphi, fw->full, h->stream);
         if (cufftExecZ2Z(fw->plan, (cufftDoubleComplex*)fw->full, (cufftDoubleComplex*)fw->full, CUFFT_INVERSE) != CUFFT_SUCCESS)
             return fail(h, SWRT_ERR_CUDA, "cufftExecZ2Z(nufft) failed");
-        launch_nufft_store(fw->full, nf, c, h->nufft_grid[slot], h->stream);
+        launch_nufft_store(fw->full, nf, c, 2, h->nufft_grid[slot], h->stream);
         h->launches += 3;
     }
+    if (h->slot_npl[slot] == 7) {          // H = 1 + eta_g (raytrace_sw.m:49): its own 8-byte-per-node fine grid
+        if (!h->nufft_h[slot]) CU(h, cudaMalloc(&h->nufft_h[slot], n * sizeof(double)));
+        launch_nufft_spread(h->planes[slot][6], nx, nf, h->nufft_invphi, fw->full, h->stream);
+        if (cufftExecZ2Z(fw->plan, (cufftDoubleComplex*)fw->full, (cufftDoubleComplex*)fw->full, CUFFT_INVERSE) != CUFFT_SUCCESS)
+            return fail(h, SWRT_ERR_CUDA, "cufftExecZ2Z(nufft H) failed");
+        launch_nufft_store(fw->full, nf, 0, 1, h->nufft_h[slot], h->stream);
+        h->launches += 3;
+    } else dfree(h->nufft_h[slot]);
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaGetLastError());
     return SWRT_OK;
 }
-int active_nufft_grid(swrt_handle* h, double alpha, const double** out) {
+// fine grids holding (1-alpha)*slot0 + alpha*slot1; *hout is null when no H plane was set (or not wanted)
+int active_nufft_grid(swrt_handle* h, double alpha, const double** out, const double** hout) {
     REQUIRE(h, h->nufft_grid[0], SWRT_ERR_STATE, "flow slot 0 has not been set");
-    if (alpha == 0.0) { *out = h->nufft_grid[0]; return SWRT_OK; }
+    const bool want_h = hout != nullptr;
+    if (want_h) *hout = nullptr;
+    if (alpha == 0.0) { *out = h->nufft_grid[0]; if (want_h) *hout = h->nufft_h[0]; return SWRT_OK; }
     REQUIRE(h, h->nufft_grid[1] && h->slot_set[1], SWRT_ERR_STATE, "alpha = %g but flow slot 1 has not been set", alpha);
-    if (alpha == 1.0) { *out = h->nufft_grid[1]; return SWRT_OK; }
+    if (alpha == 1.0) { *out = h->nufft_grid[1]; if (want_h) *hout = h->nufft_h[1]; return SWRT_OK; }
     const int nf = (int)(kNufftSigma * h->p.nx);
     const size_t nd = (size_t)2 * nf * nf;
     if (!h->nufft_blend) CU(h, cudaMalloc(&h->nufft_blend, nd * sizeof(double)));
     launch_axpby(h->nufft_blend, h->nufft_grid[0], h->nufft_grid[1], 1.0 - alpha, alpha, nd, h->stream);   // interpolate_U.m:19-23
     h->launches++;
     *out = h->nufft_blend;
+    if (want_h && h->nufft_h[0] && h->nufft_h[1]) {
+        if (!h->nufft_hblend) CU(h, cudaMalloc(&h->nufft_hblend, nd / 2 * sizeof(double)));
+        launch_axpby(h->nufft_hblend, h->nufft_h[0], h->nufft_h[1], 1.0 - alpha, alpha, nd / 2, h->stream);
+        h->launches++;
+        *hout = h->nufft_hblend;
+    }
     return SWRT_OK;
 }
 void fill_nufft_args(const swrt_handle* h, const double* grid, NufftArgs& a) {
@@ -537,6 +558,7 @@ int swrt_destroy(swrt_handle* h) {
     }
     dfree(h->grid_blend);
     dfree(h->nufft_grid[0]); dfree(h->nufft_grid[1]); dfree(h->nufft_blend); dfree(h->nufft_invphi);
+    dfree(h->nufft_h[0]); dfree(h->nufft_h[1]); dfree(h->nufft_hblend);
     if (h->nufft_fft) { delete static_cast<FftWork*>(h->nufft_fft); h->nufft_fft = nullptr; }
     for (auto& st : h->stacks) { dfree(st.slot[0]); dfree(st.slot[1]); dfree(st.blend); }
     for (auto& p : h->e) dfree(p);
@@ -844,7 +866,7 @@ static int step_leapfrog(swrt_handle* h, double dt, int nsteps, double alpha0, d
 #endif
         } else if (h->p.mode == SWRT_MODE_NUFFT) {
             const double* g = nullptr;
-            if ((rc = active_nufft_grid(h, alpha, &g))) return rc;
+            if ((rc = active_nufft_grid(h, alpha, &g, nullptr))) return rc;
             NufftArgs a{};
             fill_nufft_args(h, g, a);
             a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.dt = dt; a.nsteps = inner;
@@ -889,7 +911,6 @@ static int step_rk4(swrt_handle* h, bool xka, double dt, int nsteps, double alph
         return SWRT_OK;
     }
     // SPECTRAL / NUFFT: continuous ray equations composed point-wise; 5 evaluations per step
-    REQUIRE(h, !(xka && h->p.mode == SWRT_MODE_NUFFT), SWRT_ERR_STATE, "step_packet_xka needs the H plane: not available in NUFFT mode");
     if ((rc = ensure_scratch(h, h->n))) return rc;
     CU(h, cudaEventRecord(h->ev0, h->stream));
     for (int j = 0; j < nsteps; j++) {

@@ -916,7 +916,26 @@ def test_nufft_trajectories_ode23_and_rk4_match_spectral_oracle():
         edges = np.linspace(0, 9, 300)
         assert np.array_equal(e.hist_omega(edges, kind=S.HIST_ABSOLUTE), es.hist_omega(edges, kind=S.HIST_ABSOLUTE))
         with pytest.raises(S.SwrtError):
-            e.step(S.SCHEME_RK4_XKA, dt, 1)                               # no H plane in this mode
+            e.step(S.SCHEME_RK4_XKA, dt, 1)                               # this flow has no H plane
+
+
+@pytest.mark.gpu
+def test_nufft_step_packet_xka_matches_dense_spectral():
+    """config 5 in NUFFT mode: u, v, H at the four RK4 stage positions and the seven planes at the new position come from
+    the (u,v) and H fine grids; states equal the dense-contraction path to 1e-9, H itself to 1e-12"""
+    w = W.make_workload("C5", n_packets=3000, nx=64)
+    planes = W.planes_from_psik(w.psik, w.L, w.u_mean, etak=w.extra["etak"])
+    outs = []
+    for mode in (S.MODE_SPECTRAL, S.MODE_NUFFT):
+        with S.Engine(w.nx, w.L, w.f, w.gH, mode) as e:
+            e.set_flow_planes_spectral(planes)
+            ev = e.eval_at(w.x, w.y, with_H=True)
+            e.set_packets(w.x, w.y, w.k, w.l, np.ones(w.n_packets))
+            e.step(S.SCHEME_RK4_XKA, w.dt, 4)
+            outs.append((ev, np.stack(e.get_packets(with_a=True))))
+    assert scaled_err(outs[1][0], outs[0][0]) < TOL_FIELD
+    assert np.abs(outs[1][1] - outs[0][1]).max() < TOL_TRAJ
+    assert np.abs(outs[0][1][4] - 1.0).max() > 1e-6                      # the wave action actually evolved
 
 
 @pytest.mark.gpu
