@@ -16,6 +16,11 @@ buffers (pinned h2d of x,y,k,l + step + d2h of x,y,k,l inside the timed region);
 DMMA flops of the dominant kernel / its event-timed duration against the measured fp64 peak;
 cpu_baseline = the oracle's C port of the reference's own path (6x6 Lagrange leapfrog) on the host
 cores.  ``--impl reference`` times that CPU port alone.
+
+``--mode`` picks the evaluation mode of the headline legs: ``spectral`` (default: the dense fp64 DMMA contraction
+BASELINE.json's north_star names), ``nufft`` (the same Fourier series as a type-2 non-uniform FFT, <= 1e-12, cost
+independent of nx) or ``lagrange6`` (the reference's own stencil arithmetic).  The other two modes are always reported
+beside the headline as ``"nufft"`` / ``"lagrange6"``.
 """
 from __future__ import annotations
 
@@ -57,7 +62,10 @@ def parse():
     ap.add_argument("--substeps", type=int, default=16, help="fused leapfrog steps per bench step")
     ap.add_argument("--mtiles", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-lagrange", action="store_true")
+    ap.add_argument("--no-lagrange", action="store_true", help="skip the LAGRANGE6 / NUFFT side legs")
+    ap.add_argument("--mode", default="spectral", choices=["spectral", "nufft", "lagrange6"],
+                    help="evaluation mode of the HEADLINE legs (value, e2e, roofline); default = the dense DMMA contraction "
+                         "BASELINE.json's north_star names")
     return ap.parse_args()
 
 
@@ -206,7 +214,8 @@ def main():
     w = W.make_workload(args.workload, n_packets=args.packets or None, seed_packets=123 + rank)
     n = w.n_packets
     sub = args.substeps
-    eng = S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_SPECTRAL, device=local)
+    mode = {"spectral": S.MODE_SPECTRAL, "nufft": S.MODE_NUFFT, "lagrange6": S.MODE_LAGRANGE6}[args.mode]
+    eng = S.Engine(w.nx, w.L, w.f, w.gH, mode, device=local)
     eng.set_tuning(args.mtiles)
     time_dependent = w.psik2 is not None
     scheme = {"leapfrog": S.SCHEME_LEAPFROG, "rk4_packet": S.SCHEME_RK4_PACKET, "rk4_xka": S.SCHEME_RK4_XKA}[w.scheme]
@@ -319,23 +328,41 @@ def main():
     e2e_value = n * world * sub * args.steps / (e2e_total * 1e-3)
     clocks = sampler.stop() if sampler else None       # sampled across the resident, kernel-only and e2e timed regions
 
-    # ---- roofline of the dominant kernel (the fused spectral leapfrog kernel) ----
-    ncontract = eng.contracted_planes()                             # 3: psi-hat moments (6 nx^2 flops); 6: six planes (12 nx^2)
-    # plane-evaluations contracted per packet-step: leapfrog = one six-plane evaluation (3 moment planes when
-    # the flow is psi-hat); step_packet = six planes + 3 x (u,v); step_packet_xka = 4 x (u,v,H) + seven planes
-    plane_evals = {"leapfrog": ncontract, "rk4_packet": ncontract + 6, "rk4_xka": 19}[w.scheme]
-    flops_per_packet_step = eng.work_per_eval(plane_evals)          # EXECUTED DMMA flops per packet-step (+-kx folded)
-    flops_per_launch = flops_per_packet_step * n * sub
-    achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
-    roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
-                "frac": round(achieved / FP64_DGEMM_TFLOPS, 4), "traffic": NCU_TRAFFIC_BYTES.get((w.name, sub)) if w.n_packets == 65536 else None,
-                "kernel": (f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'}> (fp64 DMMA m8n8k4)"
-                           if w.scheme == "leapfrog" else "swrt::spectral_kernel<*,EVAL> x5 per step + glue (fp64 DMMA m8n8k4)"),
-                "kernel_ms": round(kernel_ms, 4), "contracted_planes": ncontract,
-                "flops_per_packet_step": flops_per_packet_step,
-                "peak_source": "measured: cuBLAS DGEMM 8192^3 on this pool's B200 (tools/dgemm_peak.py); DMMA issue peak 37.1 (tools/fp64_peak.cu); MEASURED_PEAKS.json has no fp64 entry",
-                "frac_of_dmma_issue_peak": round(achieved / FP64_DMMA_TFLOPS, 4),
-                "hbm_bytes_per_packet_step": 64.0 / sub}
+    # ---- roofline of the dominant kernel ----
+    if args.mode == "spectral":
+        ncontract = eng.contracted_planes()                         # 3: psi-hat moments (6 nx^2 flops); 6: six planes (12 nx^2)
+        # plane-evaluations contracted per packet-step: leapfrog = one six-plane evaluation (3 moment planes when
+        # the flow is psi-hat); step_packet = six planes + 3 x (u,v); step_packet_xka = 4 x (u,v,H) + seven planes
+        plane_evals = {"leapfrog": ncontract, "rk4_packet": ncontract + 6, "rk4_xka": 19}[w.scheme]
+        flops_per_packet_step = eng.work_per_eval(plane_evals)      # EXECUTED DMMA flops per packet-step (+-kx folded)
+        flops_per_launch = flops_per_packet_step * n * sub
+        achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
+        roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
+                    "frac": round(achieved / FP64_DGEMM_TFLOPS, 4), "traffic": NCU_TRAFFIC_BYTES.get((w.name, sub)) if w.n_packets == 65536 else None,
+                    "kernel": (f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'}> (fp64 DMMA m8n8k4)"
+                               if w.scheme == "leapfrog" else "swrt::spectral_kernel<*,EVAL> x5 per step + glue (fp64 DMMA m8n8k4)"),
+                    "kernel_ms": round(kernel_ms, 4), "contracted_planes": ncontract,
+                    "flops_per_packet_step": flops_per_packet_step,
+                    "peak_source": "measured: cuBLAS DGEMM 8192^3 on this pool's B200 (tools/dgemm_peak.py); DMMA issue peak 37.1 (tools/fp64_peak.cu); MEASURED_PEAKS.json has no fp64 entry",
+                    "frac_of_dmma_issue_peak": round(achieved / FP64_DMMA_TFLOPS, 4),
+                    "hbm_bytes_per_packet_step": 64.0 / sub}
+    else:
+        # gather modes: algorithmic bytes = stencil-node bytes gathered per evaluation x evaluations per launch.  The nodes are
+        # L2-resident (the grids are 0.4-17 MB), so this is reported against the measured HBM copy bandwidth only as the
+        # contract's denominator: a fraction above 1 means "served from L2", which is the design; the real bound is the L1
+        # data pipe (profiles/README.md)
+        evals = {"leapfrog": 1, "rk4_packet": 4 if args.mode == "nufft" else 5, "rk4_xka": 5 if args.mode == "nufft" else 19 / 6}[w.scheme]
+        gbytes = eng.work_per_eval(6) * evals * n * sub
+        try:
+            hbm_peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]); src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            hbm_peak = 6650.0; src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+        ach = gbytes / (kernel_ms * 1e-3) * 1e-9
+        roofline = {"bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None,
+                    "kernel": "swrt::nufft_leapfrog_kernel" if args.mode == "nufft" else "swrt::lagrange_leapfrog_kernel<6>",
+                    "kernel_ms": round(kernel_ms, 4), "gathered_bytes_per_packet_step": eng.work_per_eval(6) * evals,
+                    "peak_source": src + "; the gathered nodes are L2-resident, the kernel is L1 data-pipe bound",
+                    "hbm_bytes_per_packet_step": 64.0 / sub}
 
     # ---- reference-semantics mode (LAGRANGE6), reported beside the headline ----
     lag = None
@@ -424,7 +451,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{w.name}: {'time-dependent' if time_dependent else 'steady'} {w.nx}^2 spectral grid, {n} packets/GPU, "
                                        f"full-spectrum random-phase QG field, {w.scheme}",
-                           "packets_per_gpu": n, "nx": w.nx, "substeps_per_step": sub, "mode": "SPECTRAL",
+                           "packets_per_gpu": n, "nx": w.nx, "substeps_per_step": sub, "mode": args.mode.upper(),
                            "l2": "flushed between timed steps (256 MiB write)", "histogram_bins": 299,
                            "parallelism": f"packets sharded x{world}, flow replicated"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n,
