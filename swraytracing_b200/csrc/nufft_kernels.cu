@@ -8,7 +8,7 @@
 //       (Barnett, Magland & af Klinteberg, SIAM J. Sci. Comput. 41, 2019); the four velocity gradients come from the
 //       ANALYTIC derivative phi'(z) applied to the same u_f, v_f nodes, i.e. they are the spectral derivatives
 //       i kx u-hat, ... of SpectralScheme.m:20-23 / grid_U.m:6-9.
-// Accuracy (tests/test_gpu_parity.py): <= 1e-12 of max|plane| against the exact trig-sum oracle on all six planes
+// Accuracy (tests/test_gpu_parity.py): <= 1e-12 of max|plane| against the exact trigonometric sum (CPU checker) on all six planes
 // (measured 1e-14 for u,v and 2e-13 for the gradients).  Work per evaluation is 324 nodes x 16 bytes, independent of
 // nx, against 6 nx^2 flops for the dense contraction: the crossover is below nx = 64.  An optional H plane
 // (step_packet_xka, cg_sw.m) rides on a second, 8-byte-per-node fine grid gathered with the same weights.
