@@ -94,34 +94,118 @@ __device__ __forceinline__ void gather_planes(const double* __restrict__ grid, i
     }
 }
 
+// ---- quad-per-packet evaluation (eval + leapfrog kernels) ----------------------------------------------------------
+// Four lanes share one packet: lane q gathers the plane pair (2q, 2q+1) of every stencil node, so the quad's loads of a
+// node are 48 (56) contiguous bytes instead of three instructions that each scatter over 32 different lines -- the
+// thread-per-packet version is bound by L1 data-pipe wavefronts.  Each lane evaluates three of the twelve 1-D weights
+// (the divisions are the expensive part) and the quad exchanges them by shuffle; every plane is still accumulated by
+// ONE lane in the reference's order (i outer, j inner, interpolate.m:43-49), so the results stay bit-identical.
+__device__ __forceinline__ void lagrange_weights3(double a, double bump, int i_lo, double* w3) {
+    double t[NW];
+#pragma unroll
+    for (int j = 0; j < NW; j++) t[j] = a - (double)(j - IORD) + bump;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const int i = i_lo + m;
+        double p = 1.0;
+#pragma unroll
+        for (int j = 0; j < NW; j++)
+            if (j != i) p = p * t[j] / (double)(j - i);
+        w3[m] = p;
+    }
+}
+
+__device__ __forceinline__ void make_stencil_quad(double x, double y, double dx, int nx, double bump, int q, int quad_base,
+                                                  Stencil& s) {
+    // interpolate.m:21-31 (every lane of the quad computes the same reduced coordinates)
+    const double xl = matlab_mod(x / dx, (double)nx);
+    const double yl = matlab_mod(y / dx, (double)nx);
+    const double fx = floor(xl), fy = floor(yl);
+    const double ax = 1.0 + xl - (1.0 + fx);
+    const double ay = 1.0 + yl - (1.0 + fy);
+    double mine[3];
+    // lanes 0,1: wx[0..2], wx[3..5];  lanes 2,3: wy[0..2], wy[3..5]
+    lagrange_weights3(q < 2 ? ax : ay, bump, (q & 1) * 3, mine);
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        s.wx[i] = __shfl_sync(0xffffffffu, mine[i % 3], quad_base + i / 3);
+        s.wy[i] = __shfl_sync(0xffffffffu, mine[i % 3], quad_base + 2 + i / 3);
+    }
+    const int i0 = (int)fx, j0 = (int)fy;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        int a = (i0 + i - IORD) % nx; if (a < 0) a += nx;
+        int b = (j0 + i - IORD) % nx; if (b < 0) b += nx;
+        s.ig[i] = a; s.jg[i] = b;
+    }
+}
+
+// lane q accumulates planes c0 = 2q and c1 = 2q+1 (those below NPL) over the 36 nodes
+template <int NPL>
+__device__ __forceinline__ void gather_pair(const double* __restrict__ grid, int nx, const Stencil& s, int q, double& F0, double& F1) {
+    F0 = 0.0; F1 = 0.0;
+    const int c0 = 2 * q;
+    const bool on0 = c0 < NPL, on1 = c0 + 1 < NPL;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const double* row = grid + (size_t)s.ig[i] * nx * NPL;
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            const double w = s.wx[i] * s.wy[j];
+            const double* node = row + (size_t)s.jg[j] * NPL + c0;
+            double v0 = 0.0, v1 = 0.0;
+            if constexpr (NPL % 2 == 0) {
+                if (on0) { const double2 v = __ldg(reinterpret_cast<const double2*>(node)); v0 = v.x; v1 = v.y; }
+            } else {
+                if (on0) v0 = __ldg(node);
+                if (on1) v1 = __ldg(node + 1);
+            }
+            F0 = F0 + w * v0;
+            F1 = F1 + w * v1;
+        }
+    }
+}
+
 template <int NPL>
 __global__ void __launch_bounds__(128) lagrange_eval_kernel(const LagArgs a) {
-    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.n) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t >> 2;
+    const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
+    const long long pc = p < a.n ? p : a.n - 1;          // idle quads of the last warp still take part in the shuffles
     Stencil s;
-    make_stencil(a.xin[p], a.yin[p], a.dx, a.dx, a.nx, a.nx, a.bump, s);
-    double F[NPL];
-    gather_planes<NPL>(a.grid, a.nx, s, F);
-#pragma unroll
-    for (int c = 0; c < NPL; c++)
-        if (a.out[c]) a.out[c][p] = F[c];
+    make_stencil_quad(a.xin[pc], a.yin[pc], a.dx, a.nx, a.bump, q, qb, s);
+    double F0, F1;
+    gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
+    if (p < a.n) {
+        if (2 * q < NPL && a.out[2 * q]) a.out[2 * q][p] = F0;
+        if (2 * q + 1 < NPL && a.out[2 * q + 1]) a.out[2 * q + 1][p] = F1;
+    }
 }
 
 // ode_symplectic.m:13-21,33-37 with scheme.U / grad_U = six Lagrange interpolations at x1
 template <int NPL>
 __global__ void __launch_bounds__(128) lagrange_leapfrog_kernel(const LagArgs a) {
-    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.n) return;
-    double x = a.x[p], y = a.y[p], k = a.k[p], l = a.l[p];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t >> 2;
+    const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
+    const long long pc = p < a.n ? p : a.n - 1;
+    double x = a.x[pc], y = a.y[pc], k = a.k[pc], l = a.l[pc];
     const double f2 = a.f * a.f, h = 0.5 * a.dt;
     for (int st = 0; st < a.nsteps; st++) {
         double om = sqrt(f2 + a.gH * (k * k + l * l));
         x = x + h * (a.gH * k / om);
         y = y + h * (a.gH * l / om);
         Stencil s;
-        make_stencil(x, y, a.dx, a.dx, a.nx, a.nx, a.bump, s);
-        double F[NPL];
-        gather_planes<NPL>(a.grid, a.nx, s, F);
+        make_stencil_quad(x, y, a.dx, a.nx, a.bump, q, qb, s);
+        double F0, F1;
+        gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
+        // every lane needs all six planes for the kick: lane 0 holds (u,v), lane 1 (ux,uy), lane 2 (vx,vy)
+        double F[6];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            F[2 * c] = __shfl_sync(0xffffffffu, F0, qb + c);
+            F[2 * c + 1] = __shfl_sync(0xffffffffu, F1, qb + c);
+        }
         x = x + a.dt * F[0];
         y = y + a.dt * F[1];
         const double k0 = k, l0 = l;
@@ -131,7 +215,7 @@ __global__ void __launch_bounds__(128) lagrange_leapfrog_kernel(const LagArgs a)
         x = x + h * (a.gH * k / om);
         y = y + h * (a.gH * l / om);
     }
-    a.x[p] = x; a.y[p] = y; a.k[p] = k; a.l[p] = l;
+    if (p < a.n && q == 0) { a.x[p] = x; a.y[p] = y; a.k[p] = k; a.l[p] = l; }
 }
 
 // One RK4 position stage of step_packet(.m:41-51) / step_packet_xka(.m:42-52): interpolate the
@@ -292,16 +376,16 @@ void launch_interleave_grid(const double* const* planes_dev, int npl, int nx, do
 
 cudaError_t launch_lagrange_eval(const LagArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.npl == 6) lagrange_eval_kernel<6><<<blocks_for(a.n, 128), 128, 0, st>>>(a);
-    else if (a.npl == 7) lagrange_eval_kernel<7><<<blocks_for(a.n, 128), 128, 0, st>>>(a);
+    if (a.npl == 6) lagrange_eval_kernel<6><<<blocks_for(4 * a.n, 128), 128, 0, st>>>(a);
+    else if (a.npl == 7) lagrange_eval_kernel<7><<<blocks_for(4 * a.n, 128), 128, 0, st>>>(a);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
 cudaError_t launch_lagrange_leapfrog(const LagArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.npl == 6) lagrange_leapfrog_kernel<6><<<blocks_for(a.n, 128), 128, 0, st>>>(a);
-    else if (a.npl == 7) lagrange_leapfrog_kernel<7><<<blocks_for(a.n, 128), 128, 0, st>>>(a);
+    if (a.npl == 6) lagrange_leapfrog_kernel<6><<<blocks_for(4 * a.n, 128), 128, 0, st>>>(a);
+    else if (a.npl == 7) lagrange_leapfrog_kernel<7><<<blocks_for(4 * a.n, 128), 128, 0, st>>>(a);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
