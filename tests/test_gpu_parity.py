@@ -478,7 +478,7 @@ def test_histogram_bit_exact():
 def test_edge_cases_empty_single_ragged_nonfinite():
     nx = 32; L = 2 * np.pi
     psik, planes = make_flow(nx)
-    for mode in (S.MODE_SPECTRAL, S.MODE_LAGRANGE6):
+    for mode in (S.MODE_SPECTRAL, S.MODE_LAGRANGE6, S.MODE_NUFFT):
         with S.Engine(nx, L, F0, GH0, mode) as e:
             e.set_flow_spectral(psik)
             z = np.zeros(0)
@@ -488,12 +488,12 @@ def test_edge_cases_empty_single_ragged_nonfinite():
             for n in (1, 7, 8, 63, 64, 65, 129):                    # around the 8/64/128 tile edges
                 x, y, k, l = make_packets(n, L, seed=n)
                 e.set_packets(x, y, k, l)
-                ref = (CO.spectral_eval(x, y, planes, L / nx, nx) if mode == S.MODE_SPECTRAL
+                ref = (CO.spectral_eval(x, y, planes, L / nx, nx) if mode != S.MODE_LAGRANGE6
                        else CO.interpolate6(x, y, [O.k2g(p) for p in planes], L / nx))
                 assert scaled_err(e.eval(), ref) < TOL_FIELD
             # huge and negative positions reduce exactly like mod(x/dx, nx)
             x = np.array([1e6 + 0.123, -1e6 - 0.456, 0.0, -1e-20, L, -L]); y = x[::-1].copy()
-            ref = (CO.spectral_eval(x, y, planes, L / nx, nx) if mode == S.MODE_SPECTRAL
+            ref = (CO.spectral_eval(x, y, planes, L / nx, nx) if mode != S.MODE_LAGRANGE6
                    else CO.interpolate6(x, y, [O.k2g(p) for p in planes], L / nx))
             assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD
             # a non-finite packet is counted by the sentinel and does not poison the others
@@ -505,6 +505,13 @@ def test_edge_cases_empty_single_ragged_nonfinite():
             assert d[4] == 1 and d[6] == 100
             xs, _, ks, _ = e.get_packets()
             assert np.isfinite(np.delete(ks, 17)).all() and np.isfinite(np.delete(xs, 17)).all()
+            # non-finite POSITIONS (the quad kernels index the grid from them): no fault, neighbours untouched
+            x2 = x.copy(); x2[3] = np.inf; x2[40] = np.nan; x2[77] = 1e300
+            e.set_packets(x2, y, k, l)
+            e.step(S.SCHEME_LEAPFROG, 0.01, 2)
+            xs, ys, ks, _ = e.get_packets()
+            good = np.ones(100, bool); good[[3, 40]] = False
+            assert np.isfinite(xs[good]).all() and np.isfinite(ks[good]).all() and not np.isfinite(xs[~good]).any()
 
 
 def test_error_behaviour():
