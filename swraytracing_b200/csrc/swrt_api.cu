@@ -62,6 +62,8 @@ struct swrt_handle {
     double* nufft_hblend = nullptr;
     double* nufft_invphi = nullptr;
     void* nufft_fft = nullptr;            // FftWork* for the nf-point transforms
+    void* grid_fft = nullptr;             // FftWork* for the nx-point g2k / k2g of flow uploads (plan kept across calls)
+    double* grid_tmp = nullptr;           // kMaxPlanes x nx^2 gridded planes before interleaving (kept across calls)
     // scratch
     int64_t scratch_cap = 0;
     double* e[kMaxPlanes] = {};
@@ -468,18 +470,33 @@ void fill_nufft_args(const swrt_handle* h, const double* grid, NufftArgs& a) {
     a.f2 = h->p.f * h->p.f; a.gH = h->p.gH;
 }
 
+// the handle's nx-point FFT work area and plan, created on first use (plan creation costs ~1 ms: a per-call plan
+// dominated every flow upload of the time-evolving drivers)
+static int handle_fft(swrt_handle* h, FftWork** out) {
+    if (!h->grid_fft) {
+        FftWork* fw = new (std::nothrow) FftWork();
+        REQUIRE(h, fw, SWRT_ERR_ALLOC, "out of host memory");
+        int rc = fw->init(h->p.nx, h->stream, h->err);
+        if (rc) { delete fw; return fail(h, rc, "FFT plan: %s", h->err.c_str()); }
+        h->grid_fft = fw;
+    }
+    *out = static_cast<FftWork*>(h->grid_fft);
+    cufftSetStream((*out)->plan, h->stream);
+    return SWRT_OK;
+}
+
 // build the Lagrange grid of a slot from its spectral planes (k2g of every plane): grid_U.m:11-17
 int grid_from_planes(swrt_handle* h, int slot) {
     const int nx = h->p.nx, npl = h->slot_npl[slot];
-    FftWork w;
-    int rc = w.init(nx, h->stream, h->err);
+    FftWork* wp = nullptr;
+    int rc = handle_fft(h, &wp);
     if (rc) return rc;
-    std::vector<DevTmp<double>> tmpbuf(npl);
+    FftWork& w = *wp;
     std::vector<double*> tmp(npl, nullptr);
     size_t n = (size_t)nx * nx;
+    if (!h->grid_tmp) CU(h, cudaMalloc(&h->grid_tmp, (size_t)kMaxPlanes * n * sizeof(double)));
     for (int c = 0; c < npl; c++) {
-        CU(h, tmpbuf[c].alloc(n));
-        tmp[c] = tmpbuf[c].p;
+        tmp[c] = h->grid_tmp + (size_t)c * n;
         rc = k2g_dev(w, h->planes[slot][c], tmp[c], h->stream, h->err);
         if (rc) return rc;
         h->launches += 3;
@@ -488,7 +505,7 @@ int grid_from_planes(swrt_handle* h, int slot) {
     if (!h->grid[slot]) CU(h, cudaMalloc(&h->grid[slot], n * npl * sizeof(double)));
     launch_interleave_grid(tmp.data(), npl, nx, h->grid[slot], h->stream);
     h->launches++;
-    CU(h, cudaStreamSynchronize(h->stream));      // the temporaries are released on return
+    CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
 }
 
@@ -560,6 +577,8 @@ int swrt_destroy(swrt_handle* h) {
     dfree(h->nufft_grid[0]); dfree(h->nufft_grid[1]); dfree(h->nufft_blend); dfree(h->nufft_invphi);
     dfree(h->nufft_h[0]); dfree(h->nufft_h[1]); dfree(h->nufft_hblend);
     if (h->nufft_fft) { delete static_cast<FftWork*>(h->nufft_fft); h->nufft_fft = nullptr; }
+    if (h->grid_fft) { delete static_cast<FftWork*>(h->grid_fft); h->grid_fft = nullptr; }
+    dfree(h->grid_tmp);
     for (auto& st : h->stacks) { dfree(st.slot[0]); dfree(st.slot[1]); dfree(st.blend); }
     for (auto& p : h->e) dfree(p);
     dfree(h->xs); dfree(h->ys); dfree(h->ax); dfree(h->ay); dfree(h->om); dfree(h->Om);
@@ -679,9 +698,11 @@ int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* 
         h->launches++;
         h->slot_set[slot] = true; h->slot_npl[slot] = npl;
     } else {
-        // SPECTRAL mode: g2k of every plane on the device (g2k.m:5-9)
-        FftWork w;
-        rc = w.init(nx, h->stream, h->err);
+        // SPECTRAL / NUFFT mode: g2k of every plane on the device (g2k.m:5-9)
+        FftWork* wp = nullptr;
+        rc = handle_fft(h, &wp);
+        if (rc) return rc;
+        FftWork& w = *wp;
         size_t nh = (size_t)(nx - 1) * (nx / 2);
         for (int c = 0; c < npl && rc == SWRT_OK; c++) {
             if (!h->planes[slot][c] && cudaMalloc(&h->planes[slot][c], nh * sizeof(double2)) != cudaSuccess) {
