@@ -183,6 +183,7 @@ int swrt_qg_create(int device, int nx, double L, double K_d2, double beta, doubl
                    const double* qk_re, const double* qk_im, swrt_qg** out);
 int swrt_qg_step(swrt_qg* q, int nsteps);
 int swrt_qg_get(swrt_qg* q, double* qk_re, double* qk_im);
+int swrt_qg_get_grid(swrt_qg* q, double* qgrid);   /* q = k2g(qk), nx x nx column-major (the pv frame of :165-170) */
 int swrt_qg_destroy(swrt_qg* q);
 int swrt_set_flow_from_qg(swrt_handle* h, int slot, swrt_qg* q, double u_mean);
 

@@ -1440,6 +1440,17 @@ int swrt_qg_get(swrt_qg* q, double* qk_re, double* qk_im) {
     return SWRT_OK;
 }
 
+// q = k2g(qk) on the device with the solver's own FFT plan (the PV frame qgsw_raytrace.m:165-170 writes every 50 steps)
+int swrt_qg_get_grid(swrt_qg* q, double* qgrid) {
+    if (!q || !qgrid) return SWRT_ERR_ARG;
+    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
+    const size_t ng = (size_t)q->nx * q->nx;
+    if (k2g_dev(q->fft, q->qk, q->g[4], q->stream, q->err)) return SWRT_ERR_CUDA;
+    if (cudaMemcpyAsync(qgrid, q->g[4], ng * sizeof(double), cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
+        cudaStreamSynchronize(q->stream) != cudaSuccess) return SWRT_ERR_CUDA;
+    return SWRT_OK;
+}
+
 // flow slot <- psi = -q/(K_d2 + K2) of the QG state, entirely on the device (grid_U.m:2 without the host)
 int swrt_set_flow_from_qg(swrt_handle* h, int slot, swrt_qg* q, double u_mean) {
     if (!h || !q) return SWRT_ERR_ARG;

@@ -121,7 +121,7 @@ def qgsw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_delay_da
             if (step - packet_step_start + 1) % packet_steps_per_save == 0:
                 writer.write(*eng.get_packets(), t)                    # wrapped on save only, :160
         if step % steps_per_save == 0:
-            fieldio.write_field(k2g_dev(qg.get(), device), f"{outdir}/pv", 0)
+            fieldio.write_field(qg.get_grid(), f"{outdir}/pv", 0)
             fieldio.write_field(t, f"{outdir}/pv_time", 0)
     log("Real time elapsed: %.3f seconds" % (time.time() - tic))
     out = {"dt": dt, "Nsteps": Nsteps, "U0": U0, "Fr": Fr, "t": t, "packets": eng.get_packets(), "qk": qg.get(), **stats,

@@ -71,6 +71,7 @@ SIGNATURES = {
     "swrt_qg_create": (C.c_int, [C.c_int, C.c_int] + [C.c_double] * 8 + [_dp, _dp, C.POINTER(C.c_void_p)]),
     "swrt_qg_step": (C.c_int, [C.c_void_p, C.c_int]),
     "swrt_qg_get": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "swrt_qg_get_grid": (C.c_int, [C.c_void_p, _dp]),
     "swrt_qg_destroy": (C.c_int, [C.c_void_p]),
     "swrt_set_flow_from_qg": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double]),
     "swrt_qg2_create": (C.c_int, [C.c_int, C.c_int] + [C.c_double] * 7 + [_dp] * 4 + [C.POINTER(C.c_void_p)]),
@@ -362,6 +363,14 @@ class QGFlow:
         if rc != 0:
             raise SwrtError(rc, "swrt_qg_get failed")
         return (re + 1j * im).reshape((nkx, nky), order="F")
+
+    def get_grid(self):
+        """q = k2g(qk) (nx, nx), transformed on the device with the solver's own FFT plan"""
+        out = np.empty(self.nx * self.nx)
+        rc = self.lib.swrt_qg_get_grid(self._q, _ptr(out))
+        if rc != 0:
+            raise SwrtError(rc, "swrt_qg_get_grid failed")
+        return out.reshape((self.nx, self.nx), order="F")
 
     def to_flow(self, engine, slot=0, u_mean=0.0):
         engine._check(self.lib.swrt_set_flow_from_qg(engine._h, int(slot), self._q, float(u_mean)))

@@ -341,3 +341,15 @@ def test_production_driver_in_nufft_mode_matches_dense_spectral(tmp_path):
     assert (a["ode23_steps"], a["ode23_failed"], a["packet_steps"]) == (b["ode23_steps"], b["ode23_failed"], b["packet_steps"])
     for pa, pb in zip(a["packets"], b["packets"]):
         assert np.abs(pa - pb).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_qg_get_grid_is_k2g_of_the_state():
+    import swraytracing_b200 as S
+    nx = 32
+    q = _pv_frame(nx)
+    qk = O.g2k(q)
+    qg = S.QGFlow(nx, L, qk, 3.0, 0.01, 3.0, 1.0, r_drag=0.0, force_strength=0.0)
+    qg.step(3)
+    assert np.abs(qg.get_grid() - O.k2g(qg.get())).max() < 1e-13
+    qg.close()
