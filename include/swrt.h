@@ -42,7 +42,9 @@ extern "C" {
                                   type-2 non-uniform FFT: oversampled cuFFT grid of u,v per frame (setup) + an 18x18
                                   kernel gather per evaluation, gradients from the kernel's analytic derivative (= the
                                   spectral derivatives of SpectralScheme.m:20-23 / grid_U.m:6-9).  Cost independent of
-                                  nx.  An H plane (step_packet_xka) rides on a second fine grid.                  */
+                                  nx.  An H plane (step_packet_xka) rides on a second fine grid.  The ux,uy,vx,vy planes
+                                  handed to swrt_set_flow_planes_spectral / swrt_set_flow_grid are NOT used in this mode:
+                                  the gradients are always the spectral derivatives of the u and v supplied.      */
 
 /* integrator */
 #define SWRT_SCHEME_LEAPFROG   0  /* ode_symplectic.m:13-21,33-37                               */
