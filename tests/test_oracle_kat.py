@@ -256,3 +256,28 @@ def test_difference_scheme_cross_checks_spectral_scheme():
     # (T,2,Np) calling shape of ode_symplectic's histories
     x3 = np.transpose(x.reshape(4, 50, 2), (0, 2, 1))
     assert np.abs(sch.U(x3) - ds.U(x3)).max() < 1e-10
+
+
+def test_interpolate_is_degree5_tensor_lagrange_interpolation_independent_check():
+    """interpolate.m's weight products against an independent construction: scipy's Lagrange polynomial through the six
+    nodes -2..3 of each axis, evaluated at the fractional position (the 1e-13 bump moves the abscissa by 1e-13)."""
+    import warnings
+    from scipy.interpolate import lagrange
+    warnings.simplefilter("ignore")              # scipy.lagrange warns about its own conditioning for degree > ~20; degree 5 is fine
+    rs = np.random.RandomState(4)
+    nx = 16; dx = 2 * np.pi / nx
+    F = rs.randn(nx, nx)
+    x = rs.uniform(-20, 20, 40); y = rs.uniform(-20, 20, 40)
+    got = O.interpolate(x, y, F, dx, dx)
+    nodes = np.arange(-2, 4)
+    for m in range(x.size):
+        xl = np.mod(x[m] / dx, nx); yl = np.mod(y[m] / dx, nx)
+        i0 = int(np.floor(xl)); j0 = int(np.floor(yl)); ax = xl - i0; ay = yl - j0
+        block = F[np.ix_((i0 + nodes) % nx, (j0 + nodes) % nx)]
+        col = np.array([lagrange(nodes, block[i, :])(ay) for i in range(6)])      # interpolate along y for each x node
+        want = lagrange(nodes, col)(ax)
+        assert abs(got[m] - want) < 1e-10 * max(1.0, np.abs(block).max()), (m, got[m], want)
+    # the 1-D weights are minus the Lagrange basis (five negative denominators' worth of sign); the 2-D product restores it
+    w = O._lagrange_weights(np.array([0.3]), 0.0)[:, 0]
+    basis = np.array([lagrange(nodes, np.eye(6)[i])(0.3) for i in range(6)])
+    assert np.allclose(w, -basis, atol=1e-14) and abs(w.sum() + 1.0) < 1e-14
