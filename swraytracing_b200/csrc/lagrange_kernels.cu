@@ -176,6 +176,12 @@ __global__ void __launch_bounds__(128) lagrange_eval_kernel(const LagArgs a) {
     make_stencil_quad(a.xin[pc], a.yin[pc], a.dx, a.nx, a.bump, q, qb, s);
     double F0, F1;
     gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
+    if (a.grid2) {   // interpolate_U.m:19-23: interpolate BOTH frames, then (1 - alpha)*F1 + alpha*F2
+        double G0, G1;
+        gather_pair<NPL>(a.grid2, a.nx, s, q, G0, G1);
+        F0 = (1.0 - a.alpha) * F0 + a.alpha * G0;
+        F1 = (1.0 - a.alpha) * F1 + a.alpha * G1;
+    }
     if (p < a.n) {
         if (2 * q < NPL && a.out[2 * q]) a.out[2 * q][p] = F0;
         if (2 * q + 1 < NPL && a.out[2 * q + 1]) a.out[2 * q + 1][p] = F1;
@@ -199,6 +205,12 @@ __global__ void __launch_bounds__(128) lagrange_leapfrog_kernel(const LagArgs a)
         make_stencil_quad(x, y, a.dx, a.nx, a.bump, q, qb, s);
         double F0, F1;
         gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
+        if (a.grid2) {
+            double G0, G1;
+            gather_pair<NPL>(a.grid2, a.nx, s, q, G0, G1);
+            F0 = (1.0 - a.alpha) * F0 + a.alpha * G0;
+            F1 = (1.0 - a.alpha) * F1 + a.alpha * G1;
+        }
         // every lane needs all six planes for the kick: lane 0 holds (u,v), lane 1 (ux,uy), lane 2 (vx,vy)
         double F[6];
 #pragma unroll

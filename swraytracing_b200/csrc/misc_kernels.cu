@@ -22,11 +22,13 @@ __global__ void rhs_kernel(long long n, const double* __restrict__ k, const doub
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double kk = k[i], ll = l[i];
-    const double w = sqrt(f * f + gH * (kk * kk + ll * ll));
-    if (dxdt) dxdt[i] = e.p[0][i] + cgfac * kk / w;
-    if (dydt) dydt[i] = e.p[1][i] + cgfac * ll / w;
-    if (dkdt) dkdt[i] = -(e.p[2][i] * kk + e.p[4][i] * ll);
-    if (dldt) dldt[i] = -(e.p[3][i] * kk + e.p[5][i] * ll);
+    // every product and sum rounded on its own (no FMA contraction): with the LAGRANGE6 evaluation in front, odefun is then
+    // the reference's double arithmetic operation for operation (qgsw_raytrace.m:262-263)
+    const double w = sqrt(__dadd_rn(__dmul_rn(f, f), __dmul_rn(gH, __dadd_rn(__dmul_rn(kk, kk), __dmul_rn(ll, ll)))));
+    if (dxdt) dxdt[i] = __dadd_rn(e.p[0][i], __dmul_rn(cgfac, kk) / w);
+    if (dydt) dydt[i] = __dadd_rn(e.p[1][i], __dmul_rn(cgfac, ll) / w);
+    if (dkdt) dkdt[i] = -__dadd_rn(__dmul_rn(e.p[2][i], kk), __dmul_rn(e.p[4][i], ll));
+    if (dldt) dldt[i] = -__dadd_rn(__dmul_rn(e.p[3][i], kk), __dmul_rn(e.p[5][i], ll));
 }
 
 __global__ void omega_kernel(long long n, const double* __restrict__ k, const double* __restrict__ l,

@@ -50,6 +50,7 @@ struct swrt_handle {
     bool psi_ok[2] = {false, false};      // slot was given as psi-hat: moment planes 7..9 are valid
     double u_mean[2] = {0.0, 0.0};
     bool disable_psi = false;
+    bool preblend_grid = false;       // LAGRANGE6: blend the two grids before the gather (fast) instead of after (exact)
     Stack stacks[SUB_COUNT];
     // lagrange grids per slot (node-interleaved, always 7 planes wide when H given else 6)
     double* grid[2] = {nullptr, nullptr};
@@ -206,6 +207,18 @@ int active_grid(swrt_handle* h, double alpha, const double** out) {
     return SWRT_OK;
 }
 
+// LAGRANGE6 frames for an evaluation at alpha: by default BOTH grids go to the kernel, which interpolates each and blends
+// the results exactly as interpolate_U.m:19-23 does; with the pre-blend tuning flag one blended grid (half the gathers,
+// equal in exact arithmetic, 1-ulp-level different in floating point)
+int lag_frames(swrt_handle* h, double alpha, bool allow_exact, LagArgs& a) {
+    a.grid2 = nullptr; a.alpha = 0.0;
+    if (alpha == 0.0 || alpha == 1.0 || h->preblend_grid || !allow_exact) return active_grid(h, alpha, &a.grid);
+    REQUIRE(h, h->grid[0], SWRT_ERR_STATE, "flow slot 0 has not been set");
+    REQUIRE(h, h->grid[1], SWRT_ERR_STATE, "alpha = %g but flow slot 1 has not been set", alpha);
+    a.grid = h->grid[0]; a.grid2 = h->grid[1]; a.alpha = alpha;
+    return SWRT_OK;
+}
+
 void invalidate_slot(swrt_handle* h, int slot) {
     for (auto& s : h->stacks) s.slot_valid[slot] = false;
 }
@@ -260,7 +273,7 @@ int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd,
         return SWRT_OK;
     }
     LagArgs a{};
-    int rc = active_grid(h, alpha, &a.grid);
+    int rc = lag_frames(h, alpha, true, a);
     if (rc) return rc;
     REQUIRE(h, !(sub == SUB_SEVEN || sub == SUB_UVH) || h->grid_npl == 7, SWRT_ERR_STATE, "no H grid was set");
     a.nx = h->p.nx; a.npl = h->grid_npl; a.n = n; a.xin = xd; a.yin = yd;
@@ -895,7 +908,7 @@ static int step_leapfrog(swrt_handle* h, double dt, int nsteps, double alpha0, d
             CU(h, launch_nufft_leapfrog(a, h->stream));
         } else {
             LagArgs a{};
-            if ((rc = active_grid(h, alpha, &a.grid))) return rc;
+            if ((rc = lag_frames(h, alpha, true, a))) return rc;
             a.nx = h->p.nx; a.npl = h->grid_npl; a.n = h->n;
             a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
             a.dx = h->p.L / h->p.nx; a.bump = h->p.bump; a.f = h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = inner;
@@ -919,7 +932,7 @@ static int step_rk4(swrt_handle* h, bool xka, double dt, int nsteps, double alph
         const int outer = steady ? 1 : nsteps, inner = steady ? nsteps : 1;
         for (int j = 0; j < outer; j++) {
             LagArgs a{};
-            if ((rc = active_grid(h, alpha0 + j * dalpha, &a.grid))) return rc;
+            if ((rc = lag_frames(h, alpha0 + j * dalpha, false, a))) return rc;      // the RK4 kernels take one (blended) grid
             a.nx = h->p.nx; a.npl = h->grid_npl; a.n = h->n;
             a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
             a.dx = h->p.L / h->p.nx; a.bump = h->p.bump; a.f = h->p.f; a.gH = h->p.gH; a.C0 = C0; a.dt = dt; a.nsteps = inner;
@@ -1817,6 +1830,7 @@ int swrt_set_tuning(swrt_handle* h, int mtiles, int flags) {
     REQUIRE(h, mtiles >= 0 && mtiles <= 2, SWRT_ERR_ARG, "mtiles must be 0, 1 or 2");
     h->mtiles = mtiles;
     h->disable_psi = (flags & 1) != 0;
+    h->preblend_grid = (flags & 2) != 0;
     return SWRT_OK;
 }
 

@@ -80,6 +80,8 @@ size_t spectral_smem_bytes(const PackGeom& g);
 // ---------------------------------------------------------------------------------------------
 struct LagArgs {
     const double* grid;     // [nx][nx][npl] doubles
+    const double* grid2;    // second frame for the exact two-frame blend (eval / leapfrog kernels), else null
+    double alpha;           // blend weight of grid2
     int nx, npl;            // npl = 6 or 7 (7th = H)
     long long n;
     const double* xin; const double* yin;

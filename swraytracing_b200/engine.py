@@ -329,8 +329,10 @@ class Engine:
             raise SwrtError(-3, "timer failed")
         return ms
 
-    def set_tuning(self, mtiles=0, use_psi_moments=True):
-        self._check(self.lib.swrt_set_tuning(self._h, int(mtiles), 0 if use_psi_moments else 1))
+    def set_tuning(self, mtiles=0, use_psi_moments=True, preblend_grid=False):
+        """``preblend_grid`` (LAGRANGE6): blend two frames on the grid before the gather (faster) instead of
+        interpolating both frames and blending the results as interpolate_U.m does (default, bit-faithful)"""
+        self._check(self.lib.swrt_set_tuning(self._h, int(mtiles), (0 if use_psi_moments else 1) | (2 if preblend_grid else 0)))
 
     def contracted_planes(self):
         return int(self.lib.swrt_contracted_planes(self._h))

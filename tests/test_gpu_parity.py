@@ -803,6 +803,29 @@ def test_lagrange_mode_is_bit_identical_to_the_restatement(nx):
             ref = O.leapfrog_step(*ref, dt, F0, GH0, ev)
         for g_, r_, name in zip(got, ref, "xykl"):
             assert _bit_equal(g_, r_), (name, _ulps(g_, r_))
+    # (3b) two flow frames: interpolate_U interpolates BOTH frames and blends the results (interpolate_U.m:19-23); odefun
+    psik2, planes2 = make_flow(nx, seed=8)
+    grids2 = [O.k2g(p) for p in planes2]
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    bf1 = dict(zip(names, grids)); bf2 = dict(zip(names, grids2))
+    with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
+        e.set_flow_grid(*grids, slot=0); e.set_flow_grid(*grids2, slot=1)
+        for alpha in (0.0, 0.37, 1.0):
+            U, nab = O.interpolate_U(bf1, bf2, alpha, np.stack([x, y], axis=1), dx)
+            got = e.eval_at(x, y, alpha)
+            want = [U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]]
+            for c in range(6):
+                assert _bit_equal(got[c], want[c]), (alpha, c, _ulps(got[c], want[c]))
+        e.set_packets(x, y, k, l)
+        d = e.rhs(0.37)
+        ref = O.odefun_rhs(x, y, k, l, 0.37, bf1, bf2, F0, 1.0, dx)
+        for g_, r_, name in zip(d, ref, ("dxdt", "dydt", "dkdt", "dldt")):
+            assert _bit_equal(g_, r_), (name, _ulps(g_, r_))
+        # the pre-blend tuning (one blended grid, half the gathers) agrees to rounding, not to the bit
+        e.set_tuning(0, preblend_grid=True)
+        fast = e.eval_at(x, y, 0.37)
+        U, nab = O.interpolate_U(bf1, bf2, 0.37, np.stack([x, y], axis=1), dx)
+        assert scaled_err(fast, np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])) < 1e-13
     # (4) step_packet / step_packet_xka: 3 RK4 steps of a few packets through the reference's own per-packet functions
     H = 1.0 + 0.2 * grids[0] / np.abs(grids[0]).max()
     U = {"u": grids[0], "v": grids[1]}; G = {"u_x": grids[2], "u_y": grids[3], "v_x": grids[4], "v_y": grids[5]}
