@@ -791,7 +791,7 @@ def ode23(odefun, tspan, y0, rtol=1e-3, atol=1e-6):
             f2 = odefun(t + 0.5 * h, y + f1 * (h * 0.5))
             f3 = odefun(t + 0.75 * h, y + f2 * (h * 0.75))
             tnew = tfinal if done else t + h
-            ynew = y + (f1 * (h * 2 / 9) + f2 * (h / 3) + f3 * (h * 4 / 9))
+            ynew = y + (f1 * (h * (2.0 / 9.0)) + f2 * (h * (1.0 / 3.0)) + f3 * (h * (4.0 / 9.0)))      # y + f*hB(:,3), hB = h*B
             f4 = odefun(tnew, ynew)
             nfevals += 3
             fE = f1 * (-5 / 72) + f2 * (1 / 12) + f3 * (1 / 9) + f4 * (-1 / 8)

@@ -216,10 +216,11 @@ __global__ void bs23_stage_kernel(Bs23Args a, double hb1, double hb2, double hb3
     if (i >= a.n) return;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        double acc = a.f[0][c][i] * hb1;
-        if (hb2 != 0.0) acc += a.f[1][c][i] * hb2;
-        if (hb3 != 0.0) acc += a.f[2][c][i] * hb3;
-        a.yt[c][i] = a.y[c][i] + acc;
+        // y + f*hB(:,j), hB = h*B, accumulated column by column with every product and sum rounded on its own
+        double acc = __dmul_rn(a.f[0][c][i], hb1);
+        if (hb2 != 0.0) acc = __dadd_rn(acc, __dmul_rn(a.f[1][c][i], hb2));
+        if (hb3 != 0.0) acc = __dadd_rn(acc, __dmul_rn(a.f[2][c][i], hb3));
+        a.yt[c][i] = __dadd_rn(a.y[c][i], acc);
     }
 }
 // err = max_i |(f*E)_i| / max(max(|y_i|,|ynew_i|), threshold)   (without the absh factor);
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(256) bs23_norm_kernel(Bs23Args a, int mode, do
             double num, den;
             if (mode == 1) { num = fabs(a.f[0][c][i]); den = fmax(fabs(a.y[c][i]), thr); }
             else {
-                num = fabs(a.f[0][c][i] * E1 + a.f[1][c][i] * E2 + a.f[2][c][i] * E3 + a.f[3][c][i] * E4);
+                num = fabs(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.f[0][c][i], E1), __dmul_rn(a.f[1][c][i], E2)),
+                                              __dmul_rn(a.f[2][c][i], E3)), __dmul_rn(a.f[3][c][i], E4)));
                 den = fmax(fmax(fabs(a.y[c][i]), fabs(a.yt[c][i])), thr);
             }
             const double r = num / den;
@@ -267,7 +269,8 @@ __global__ void bs23_interp_kernel(Bs23Args a, Bs23Interp q) {
     if (i >= a.n) return;
 #pragma unroll
     for (int c = 0; c < 4; c++)
-        q.out[c][i] = a.y[c][i] + (a.f[0][c][i] * q.w[0] + a.f[1][c][i] * q.w[1] + a.f[2][c][i] * q.w[2] + a.f[3][c][i] * q.w[3]);
+        q.out[c][i] = __dadd_rn(a.y[c][i], __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.f[0][c][i], q.w[0]), __dmul_rn(a.f[1][c][i], q.w[1])),
+                                                               __dmul_rn(a.f[2][c][i], q.w[2])), __dmul_rn(a.f[3][c][i], q.w[3])));
 }
 }  // namespace
 

@@ -983,3 +983,35 @@ def test_nufft_full_size_C4_shard_agrees_with_dense_contraction():
             outs.append((ev, np.stack(e.get_packets())))
     assert scaled_err(outs[1][0], outs[0][0]) < TOL_FIELD
     assert np.abs(outs[1][1] - outs[0][1]).max() < TOL_TRAJ
+
+
+@pytest.mark.gpu
+def test_ode23_in_lagrange_mode_is_bit_identical_to_the_restatement():
+    """qgsw_raytrace.m:141-150 in LAGRANGE6 mode: interpolate_U (both frames, blended results), odefun and the
+    Bogacki-Shampine stages (y + f*hB, the error estimate f*E) are all executed without fused multiply-adds in the
+    restatement's order, so the whole adaptive solve -- every accept/reject decision and the final packets -- is the same
+    doubles as oracle.ode23 on the restated odefun, not merely within 1e-9."""
+    nx = 32; L = 2 * np.pi; h = L / nx
+    _, p1 = make_flow(nx, seed=7); _, p2 = make_flow(nx, seed=8)
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    bf1 = {n: O.k2g(p) for n, p in zip(names, p1)}; bf2 = {n: O.k2g(p) for n, p in zip(names, p2)}
+    n = 257
+    x, y, k, l = make_packets(n, L)
+    tmax = 0.05
+    ode = O.generate_raytracing_ode(bf1, bf2, n, F0, 1.0, tmax, h)
+    yref, sref = O.ode23(ode, [0.0, tmax], np.concatenate([x, y, k, l]))
+    with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
+        e.set_flow_grid(*[bf1[n_] for n_ in names], slot=0); e.set_flow_grid(*[bf2[n_] for n_ in names], slot=1)
+        e.set_packets(x, y, k, l)
+        st = R.ode23(e, [0.0, tmax], tmax)
+        got = np.concatenate(e.get_packets())
+    assert (st["nsteps"], st["nfailed"], st["nfevals"]) == (sref["nsteps"], sref["nfailed"], sref["nfevals"]) and st["nsteps"] >= 10
+    assert _bit_equal(got, yref), _ulps(got, yref)
+    # dense output (SW_zero_background_raytracing.m:73-78) through the same stages
+    ts = tmax * np.linspace(0.0, 1.0, 7)
+    Yref, _ = O.ode23(ode, ts, np.concatenate([x, y, k, l]))
+    with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
+        e.set_flow_grid(*[bf1[n_] for n_ in names], slot=0); e.set_flow_grid(*[bf2[n_] for n_ in names], slot=1)
+        e.set_packets(x, y, k, l)
+        Y = R.ode23(e, ts, tmax)["Y"].reshape(len(ts), 4 * n)
+    assert _bit_equal(Y, Yref), _ulps(Y, Yref)
