@@ -1015,3 +1015,22 @@ def test_ode23_in_lagrange_mode_is_bit_identical_to_the_restatement():
         e.set_packets(x, y, k, l)
         Y = R.ode23(e, ts, tmax)["Y"].reshape(len(ts), 4 * n)
     assert _bit_equal(Y, Yref), _ulps(Y, Yref)
+
+
+@pytest.mark.gpu
+def test_C2_C3_full_size_lagrange_mode_bit_identical_to_the_cpu_port():
+    """The CPU arm of bench.py (--impl reference: oracle/swrt_oracle.c, -ffp-contract=off) and the LAGRANGE6 GPU arm execute
+    the same IEEE operations: at BASELINE's full sizes every packet of the two runs is the same four doubles.
+    C2: 65,536 packets x 48 steps on 128^2; C3 field (256^2): 1,048,576 packets x 8 steps."""
+    for name, nsteps in (("C2", 48), ("C3", 8)):
+        w = W.make_workload(name)
+        kx_, ky_ = O.wavenumbers(w.nx)
+        grids = [O.k2g(p) for p in O.velocity_planes_k(w.psik, kx_, ky_)]
+        ref = CO.leapfrog_lagrange(w.x, w.y, w.k, w.l, grids, w.dx, w.f, w.gH, w.dt, nsteps)
+        with S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_LAGRANGE6) as e:
+            e.set_flow_grid(*grids)
+            e.set_packets(w.x, w.y, w.k, w.l)
+            e.step(S.SCHEME_LEAPFROG, w.dt, nsteps)
+            got = e.get_packets()
+        for g_, r_, comp in zip(got, ref, "xykl"):
+            assert _bit_equal(g_, r_), (name, comp, _ulps(g_, r_))
