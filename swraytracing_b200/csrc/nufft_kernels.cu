@@ -73,7 +73,9 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, co
         es_kernel((tx + (double)a) * (1.0 / HALF_W), beta, wx0[r], wx1[r]);
         es_kernel((ty + (double)a) * (1.0 / HALF_W), beta, my0[r], my1[r]);
         if (!on) { wx0[r] = 0.0; wx1[r] = 0.0; my0[r] = 0.0; my1[r] = 0.0; }
-        int ix = ib + (on ? a : 0); if (ix >= nf) ix -= nf;
+        int ix = ib + (on ? a : 0);
+        if (ix >= nf) ix -= nf;
+        if (ix >= nf) ix -= nf;                // nx = 8: nf = 16 < w, the stencil wraps twice
         ixr[r] = ix;
     }
     double U = 0, V = 0, Ux = 0, Uy = 0, Vx = 0, Vy = 0, Hs = 0;
@@ -81,7 +83,9 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, co
     for (int b = 0; b < W; b++) {
         const double wy0 = __shfl_sync(0xffffffffu, my0[b >> 2], quad_base | (b & 3));
         const double wy1 = __shfl_sync(0xffffffffu, my1[b >> 2], quad_base | (b & 3));
-        int iy = jb + b; if (iy >= nf) iy -= nf;
+        int iy = jb + b;
+        if (iy >= nf) iy -= nf;
+        if (iy >= nf) iy -= nf;
         const double2* row = grid + (size_t)iy * nf;
         double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0, sh0 = 0;
 #pragma unroll
