@@ -1074,3 +1074,53 @@ def test_randomised_sizes_all_modes_agree_with_their_checkers():
                 outs[mode] = np.stack(e.get_packets())
         assert np.abs(outs[S.MODE_NUFFT] - outs[S.MODE_SPECTRAL]).max() < TOL_TRAJ * max(1.0, 50 * L), (nx, n)
         assert np.isfinite(outs[S.MODE_LAGRANGE6]).all()
+
+
+@pytest.mark.gpu
+def test_randomised_schemes_two_frames_awkward_sizes():
+    """second differential sweep: two flow frames with random alpha, RK4 steppers with and without H, ode23, at grid sizes
+    that are not powers of two and ragged packet counts; NUFFT and SPECTRAL must agree (same series), LAGRANGE6 must match
+    the restated RK4 batch stepper"""
+    rs = np.random.RandomState(77)
+    for nx in (8, 12, 18, 30, 44, 70):
+        L = 2 * np.pi; dx = L / nx
+        kx_, ky_ = O.wavenumbers(nx)
+        amp = 0.05 / (1 + kx_ ** 2 + ky_ ** 2)
+        psi1 = (rs.randn(nx - 1, nx // 2) + 1j * rs.randn(nx - 1, nx // 2)) * amp
+        psi2 = (rs.randn(nx - 1, nx // 2) + 1j * rs.randn(nx - 1, nx // 2)) * amp
+        etak = 3.0 * psi1
+        planes7 = W.planes_from_psik(psi1, L, 0.0, etak=etak)
+        n = int(rs.randint(1, 200))
+        x = rs.uniform(-5 * L, 5 * L, n); y = rs.uniform(-5 * L, 5 * L, n)
+        k = rs.randn(n) * 5; l = rs.randn(n) * 5
+        alpha = float(rs.uniform(0.05, 0.95)); dt = 0.1 * dx
+        res = {}
+        for mode in (S.MODE_SPECTRAL, S.MODE_NUFFT):
+            with S.Engine(nx, L, F0, 1.0, mode) as e:
+                e.set_flow_spectral(psi1, 0); e.set_flow_spectral(psi2, 1)
+                e.set_packets(x, y, k, l)
+                rhs = np.stack(e.rhs(alpha))
+                e.step(S.SCHEME_LEAPFROG, dt, 3, alpha, 0.01)
+                e.step(S.SCHEME_RK4_PACKET, dt, 2, alpha)
+                st = R.ode23(e, [0.0, 5 * dt], 5 * dt)
+                a_ = np.stack(e.get_packets())
+                e.set_flow_planes_spectral(planes7, 0)
+                e.set_packets(x, y, k, l, np.ones(n))
+                e.step(S.SCHEME_RK4_XKA, dt, 2)
+                res[mode] = (rhs, a_, (st["nsteps"], st["nfailed"]), np.stack(e.get_packets(with_a=True)))
+        a, b = res[S.MODE_SPECTRAL], res[S.MODE_NUFFT]
+        assert scaled_err(b[0], a[0]) < 5e-12, (nx, n)
+        assert np.abs(b[1] - a[1]).max() < TOL_TRAJ * 50 and a[2] == b[2], (nx, n)
+        assert np.abs(b[3] - a[3]).max() < TOL_TRAJ * 50, (nx, n)
+        # LAGRANGE6 RK4 (with H) against the restated batch stepper on the same grids
+        grids = [O.k2g(p) for p in planes7[:6]]; H = O.k2g(planes7[6])
+        fields = {"u": grids[0], "v": grids[1], "u_x": grids[2], "u_y": grids[3], "v_x": grids[4], "v_y": grids[5], "H": H}
+        with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
+            e.set_flow_grid(*grids, H=H)
+            e.set_packets(x, y, k, l, np.ones(n))
+            e.step(S.SCHEME_RK4_XKA, dt, 2)
+            got = np.stack(e.get_packets(with_a=True))
+        st_ = (x, y, k, l, np.ones(n))
+        for _ in range(2):
+            st_ = O.rk4_step_batch(*st_, dt, 1.0, F0, fields, dx, True)
+        assert np.abs(got - np.stack(st_)).max() < TOL_TRAJ, (nx, n)
