@@ -183,14 +183,36 @@ def run_reference(args):
                        "note": "reference's own CPU path (gridded planes + 6x6 Lagrange interpolate) restated in C; the MATLAB original cannot run here"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL prints its version banner there, library
+    chatter) is sent to stderr from here on."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -209,6 +231,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")        # NCCL otherwise prints its version banner on stdout, next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w = W.make_workload(args.workload, n_packets=args.packets or None, seed_packets=123 + rank)
@@ -468,7 +491,7 @@ def main():
         if nuf:
             line["nufft"] = nuf
         line["histogram_total"] = int(np.asarray(counts).sum())
-        print(json.dumps(line))
+        _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
