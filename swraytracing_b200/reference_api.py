@@ -248,6 +248,23 @@ def step_packet_xka(P, U, GradU, H, C0, f, dx, dy, dt, mode=MODE_LAGRANGE6, devi
     return PacketStepper(U, GradU, H, C0, f, dx, mode, device).step(P, dt)
 
 
+def cg_sw(k, l, C0, f, U=None, H=None):
+    """ray_trace_sw/cg_sw.m:1-32 -- [C, omega, omega_abs, divC, gradomega] = cg_sw(k,l,C0,f,U,H) as the post-processing
+    loops of raytrace.m:57-63 / raytrace_sw.m:133-139 call it: host arithmetic on whatever shape ``H`` / ``U`` have
+    (inside the steppers the same formulas run on the device, composed node-wise or point-wise).
+    Returns (C dict x,y; omega; omega_abs; divC or None; gradomega dict or None)."""
+    gH = C0 ** 2 * np.asarray(H, dtype=np.float64) if H is not None else C0 ** 2
+    K2 = k ** 2 + l ** 2
+    om = np.sqrt(f ** 2 + gH * K2)
+    C = {"x": gH * k / om, "y": gH * l / om}
+    divC = grad = None
+    if U is not None:
+        u, v = np.asarray(U["u"], dtype=np.float64), np.asarray(U["v"], dtype=np.float64)
+        divC = (k * f * v - l * f * u - C["x"] ** 2 - C["y"] ** 2) / om
+        grad = {"x": f * K2 * v / (2 * om), "y": -f * K2 * u / (2 * om)}
+    return C, om, np.abs(om), divC, grad
+
+
 def omega(k, f, gH):
     """symplectic_full_fourier.m:62-64 -- host helper, O(Np)."""
     k = np.asarray(k, dtype=np.float64)

@@ -164,3 +164,16 @@ def test_gloo_two_ranks_match_single_rank(tmp_path):
     assert (int(got["nsteps"]), int(got["nfailed"])) == (st["nsteps"], st["nfailed"]) and st["nsteps"] >= 10
     x2, _, k2, _ = ens.gather_packets()
     assert np.array_equal(got["x23"], x2) and np.array_equal(got["k23"], k2)
+
+
+def test_cg_sw_mirror_matches_restatement():
+    from swraytracing_b200 import reference_api as R
+    rs = np.random.RandomState(1)
+    U = {"u": rs.randn(8, 8) * 0.1, "v": rs.randn(8, 8) * 0.1}
+    H = 1 + 0.1 * rs.randn(8, 8)
+    C, om, oma, divC, grad = R.cg_sw(1.5, -2.0, 1.2, 3.0, U, H)
+    Cx, Cy, om0, d0, gx, gy = O.cg_sw(1.5, -2.0, 1.2, 3.0, U, H)
+    assert np.array_equal(C["x"], Cx) and np.array_equal(C["y"], Cy) and np.array_equal(om, om0) and np.array_equal(oma, np.abs(om0))
+    assert np.array_equal(divC, d0) and np.array_equal(grad["x"], gx) and np.array_equal(grad["y"], gy)
+    C, om, _, divC, grad = R.cg_sw(1.5, -2.0, 1.2, 3.0)
+    assert divC is None and grad is None and om == np.sqrt(9 + 1.44 * 6.25)
