@@ -353,3 +353,42 @@ def test_qg_get_grid_is_k2g_of_the_state():
     qg.step(3)
     assert np.abs(qg.get_grid() - O.k2g(qg.get())).max() < 1e-13
     qg.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx", [12, 20, 36, 50])
+def test_qg_solvers_at_grid_sizes_that_are_not_powers_of_two(nx):
+    """both frame producers against their restatements where cuFFT runs mixed-radix transforms"""
+    import swraytracing_b200 as S
+    rs = np.random.RandomState(nx)
+    Ld = 2 * np.pi
+    kx_, ky_ = O.wavenumbers(nx)
+    amp = 1.0 / (1 + kx_ ** 2 + ky_ ** 2)
+    qk = O.symmetrise_ky0((rs.randn(nx - 1, nx // 2) + 1j * rs.randn(nx - 1, nx // 2)) * amp)
+    dt = 0.02
+    qg = S.QGFlow(nx, Ld, qk, 3.0, dt, 3.0, 1.0, beta=0.3, r_drag=0.01, force_strength=0.05)
+    qg.step(6)
+    ref = O.qg_run(qk, 6, dt, nx, Ld, 3.0, 3.0, 1.0, beta=0.3, r_drag=0.01, force_strength=0.05)
+    got = qg.get()
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-12
+    qg.close()
+    # two-layer, L = 20
+    Lq = 20.0
+    kap = 2 * np.pi / Lq
+    kxs, kys = kx_ * kap, ky_ * kap
+    nu = 0.1 * (Lq / nx) ** 8
+    B, _, LV, LD, LV1 = O.qg2_operators(kxs, kys, 3.0, 0.0, 0.5, 0.4, nu, 4)
+    q2 = np.stack([qk, -0.7 * qk], axis=2)
+    g2 = S.QG2Flow(nx, Lq, q2[:, :, 0], q2[:, :, 1], 3.0, 0.0, 0.5, 0.4, nu, 4)
+    Qm = [np.zeros_like(q2), np.zeros_like(q2)]
+    for step in range(1, 5):
+        E1, E2 = O.qg2_expL(LV, LD, LV1, dt), O.qg2_expL(LV, LD, LV1, 2 * dt)
+        Qn = O.qg2_update(q2, B, kxs, kys)
+        dq = dt * Qn if step == 1 else (dt / 2 * (3 * Qn - O.mmult3(E1, Qm[0])) if step == 2 else
+                                        dt / 12 * (23 * Qn - 16 * O.mmult3(E1, Qm[0]) + 5 * O.mmult3(E2, Qm[1])))
+        Qm = [Qn, Qm[0]]
+        q2 = O.mmult3(E1, q2 + dq)
+        g2.step(dt)
+    for layer in range(2):
+        assert np.abs(g2.get(layer) - q2[:, :, layer]).max() / np.abs(q2).max() < 1e-12
+    g2.close()
