@@ -223,7 +223,9 @@ double  swrt_timer_stop(swrt_handle* h);
 /* tuning knobs: 1 or 2 m-tiles per warp in the spectral kernel (0 = automatic); flags bit 0 = do
  * not use the psi-hat moment contraction (always contract the six planes); flags bit 1 (LAGRANGE6) =
  * blend two flow frames on the grid before the gather (half the gathers) instead of interpolating both
- * frames and blending the results as interpolate_U.m:19-23 does (the default, bit-faithful)      */
+ * frames and blending the results as interpolate_U.m:19-23 does (the default, bit-faithful); flags
+ * bit 2 (NUFFT) = run step_packet / step_packet_xka as separate evaluation + stage launches (the
+ * dense mode's route) instead of the fused kernel                                                 */
 int     swrt_set_tuning(swrt_handle* h, int mtiles, int flags);
 /* planes the spectral kernel contracts for a six-plane evaluation: 3 when every flow slot was
  * given as psi-hat (moments N0,N1,N2; 6 nx^2 flops), else 6 (12 nx^2 flops); 0 in LAGRANGE6    */

@@ -11,7 +11,8 @@
 // Accuracy (tests/test_gpu_parity.py): <= 1e-12 of max|plane| against the exact trigonometric sum (CPU checker) on all six planes
 // (measured 1e-14 for u,v and 2e-13 for the gradients).  Work per evaluation is 324 nodes x 16 bytes, independent of
 // nx, against 6 nx^2 flops for the dense contraction: the crossover is below nx = 64.  An optional H plane
-// (step_packet_xka, cg_sw.m) rides on a second, 8-byte-per-node fine grid gathered with the same weights.
+// (step_packet_xka, cg_sw.m) rides on a second fine grid of 32-byte nodes (u, v, H, 0) gathered with the same weights:
+// one 256-bit load per node, a quad's four loads are one aligned-or-straddling 128-byte segment.
 // Replaces: SpectralScheme.U / grad_U (SpectralScheme.m:45-68), interpolate_U.m:5-23, ode_symplectic.m:13-37.
 #include "swrt_internal.h"
 
@@ -58,8 +59,15 @@ __device__ __forceinline__ void stencil_origin(double xl, int nf, int& base, dou
 // with bit-identical sums (the butterfly adds are commutative), so the redundant packet state stays consistent.
 constexpr int QR = (W + 3) / 4;      // columns (and rows) owned per lane, the last round partly empty
 
-template <bool WITH_H>
-__device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, const double* __restrict__ hgrid, int nf,
+struct __align__(32) Node4 { double u, v, h, pad; };
+__device__ __forceinline__ Node4 ldg_node4(const Node4* p) {        // SASS LDG.E.256 (read-only path)
+    Node4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.u), "=d"(r.v), "=d"(r.h), "=d"(r.pad) : "l"(p));
+    return r;
+}
+
+template <bool WITH_H, bool WITH_GRAD = true>
+__device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, const double* __restrict__ uvh, int nf,
                                             double beta, double dscale, double xl, double yl, int q, int quad_base, double* F) {
     int ib, jb; double tx, ty;
     stencil_origin(xl, nf, ib, tx);
@@ -73,6 +81,7 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, co
         es_kernel((tx + (double)a) * (1.0 / HALF_W), beta, wx0[r], wx1[r]);
         es_kernel((ty + (double)a) * (1.0 / HALF_W), beta, my0[r], my1[r]);
         if (!on) { wx0[r] = 0.0; wx1[r] = 0.0; my0[r] = 0.0; my1[r] = 0.0; }
+        if constexpr (!WITH_GRAD) { wx1[r] = 0.0; my1[r] = 0.0; }     // u, v (, H) only: the derivative sums fold away
         int ix = ib + (on ? a : 0);
         if (ix >= nf) ix -= nf;
         if (ix >= nf) ix -= nf;                // nx = 8: nf = 16 < w, the stencil wraps twice
@@ -82,26 +91,35 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, co
 #pragma unroll
     for (int b = 0; b < W; b++) {
         const double wy0 = __shfl_sync(0xffffffffu, my0[b >> 2], quad_base | (b & 3));
-        const double wy1 = __shfl_sync(0xffffffffu, my1[b >> 2], quad_base | (b & 3));
+        const double wy1 = WITH_GRAD ? __shfl_sync(0xffffffffu, my1[b >> 2], quad_base | (b & 3)) : 0.0;
         int iy = jb + b;
         if (iy >= nf) iy -= nf;
         if (iy >= nf) iy -= nf;
-        const double2* row = grid + (size_t)iy * nf;
         double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0, sh0 = 0;
 #pragma unroll
         for (int r = 0; r < QR; r++) {
-            const double2 g = __ldg(row + ixr[r]);
-            su0 = fma(wx0[r], g.x, su0); su1 = fma(wx1[r], g.x, su1);
-            sv0 = fma(wx0[r], g.y, sv0); sv1 = fma(wx1[r], g.y, sv1);
-            if constexpr (WITH_H) sh0 = fma(wx0[r], __ldg(hgrid + (size_t)iy * nf + ixr[r]), sh0);
+            double2 g;
+            if constexpr (WITH_H) {
+                const Node4 nd = ldg_node4(reinterpret_cast<const Node4*>(uvh) + (size_t)iy * nf + ixr[r]);
+                g.x = nd.u; g.y = nd.v;
+                sh0 = fma(wx0[r], nd.h, sh0);
+            } else {
+                g = __ldg(grid + (size_t)iy * nf + ixr[r]);
+            }
+            su0 = fma(wx0[r], g.x, su0); sv0 = fma(wx0[r], g.y, sv0);
+            if constexpr (WITH_GRAD) { su1 = fma(wx1[r], g.x, su1); sv1 = fma(wx1[r], g.y, sv1); }
         }
-        U = fma(wy0, su0, U);  Ux = fma(wy0, su1, Ux); Uy = fma(wy1, su0, Uy);
-        V = fma(wy0, sv0, V);  Vx = fma(wy0, sv1, Vx); Vy = fma(wy1, sv0, Vy);
+        U = fma(wy0, su0, U);  V = fma(wy0, sv0, V);
+        if constexpr (WITH_GRAD) {
+            Ux = fma(wy0, su1, Ux); Uy = fma(wy1, su0, Uy);
+            Vx = fma(wy0, sv1, Vx); Vy = fma(wy1, sv0, Vy);
+        }
         if constexpr (WITH_H) Hs = fma(wy0, sh0, Hs);
     }
     double o[7] = {U, V, Ux * dscale, Uy * dscale, Vx * dscale, Vy * dscale, Hs};
 #pragma unroll
     for (int c = 0; c < (WITH_H ? 7 : 6); c++) {
+        if (!WITH_GRAD && c >= 2 && c < 6) { F[c] = 0.0; continue; }
         double v = o[c];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -154,6 +172,88 @@ __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_MINB) nufft_leapfrog_kernel
     if (p < a.n && q == 0) { a.x[p] = x; a.y[p] = y; a.k[p] = k; a.l[p] = l; }
 }
 
+// step_packet.m:37-78 / step_packet_xka.m:38-91 with the continuous fields of this mode: RK4 in x with k frozen (u, v and,
+// for xka, H at the four stage positions), then RK4 in k (and a) with the gradients frozen -- at the OLD position for
+// step_packet (:58-61), at the NEW one for step_packet_xka (:62-70, with cg_sw.m:22-31 evaluated at the point).  One
+// launch runs `nsteps` whole steps with the packet in registers; the stage arithmetic is the expression-for-expression
+// twin of rk4_stage_kernel / rk4_final_kernel (misc_kernels.cu), which the dense mode composes from separate launches.
+#ifndef SWRT_NUFFT_RK4_MINB
+#define SWRT_NUFFT_RK4_MINB 4
+#endif
+template <bool XKA>
+__global__ void __launch_bounds__(kBlock, SWRT_NUFFT_RK4_MINB) nufft_rk4_kernel(const NufftArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t >> 2;
+    const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
+    const long long pc = p < a.n ? p : a.n - 1;
+    double x = a.x[pc], y = a.y[pc], k = a.k[pc], l = a.l[pc];
+    double am = XKA ? a.a[pc] : 0.0;
+    const double dt = a.dt;
+    for (int st = 0; st < a.nsteps; st++) {
+        const double K2 = k * k + l * l;
+        double F[7];
+        double gux = 0, guy = 0, gvx = 0, gvy = 0;       // step_packet: gradients at the old position
+        double xs = x, ys = y, ax = 0, ay = 0;
+#pragma unroll 1
+        for (int stage = 0; stage < 4; stage++) {
+            const double xl = reduced_coord(xs, a.dx, a.nxd), yl = reduced_coord(ys, a.dx, a.nxd);
+            if (!XKA && stage == 0) {
+                nufft_eval6<false, true>(a.grid, nullptr, a.nf, a.beta, a.dscale, xl, yl, q, qb, F);
+                gux = F[2]; guy = F[3]; gvx = F[4]; gvy = F[5];
+            } else {
+                nufft_eval6<XKA, false>(a.grid, a.hgrid, a.nf, a.beta, a.dscale, xl, yl, q, qb, F);
+            }
+            const double gH = XKA ? a.C0 * a.C0 * F[6] : a.C0 * a.C0;
+            const double om = sqrt(a.f * a.f + gH * K2);
+            const double dxs = dt * (F[0] + gH * k / om);
+            const double dys = dt * (F[1] + gH * l / om);
+            switch (stage) {
+                case 0: ax = dxs; ay = dys; xs = x + dxs / 2; ys = y + dys / 2; break;
+                case 1: ax += 2 * dxs; ay += 2 * dys; xs = x + dxs / 2; ys = y + dys / 2; break;
+                case 2: ax += 2 * dxs; ay += 2 * dys; xs = x + dxs; ys = y + dys; break;
+                default: {
+                    const double sx = ax + dxs, sy = ay + dys;
+                    xs = x + sx / 6; ys = y + sy / 6;
+                }
+            }
+        }
+        double oxi = 0.0, oyi = 0.0, dci = 0.0;
+        if constexpr (XKA) {
+            nufft_eval6<true, true>(a.grid, a.hgrid, a.nf, a.beta, a.dscale, reduced_coord(xs, a.dx, a.nxd),
+                                    reduced_coord(ys, a.dx, a.nxd), q, qb, F);
+            gux = F[2]; guy = F[3]; gvx = F[4]; gvy = F[5];
+            const double gH = a.C0 * a.C0 * F[6];
+            const double om = sqrt(a.f * a.f + gH * K2);
+            const double cx = gH * k / om, cy = gH * l / om;
+            oxi = a.f * K2 * F[1] / (2 * om);
+            oyi = -a.f * K2 * F[0] / (2 * om);
+            dci = (k * a.f * F[1] - l * a.f * F[0] - cx * cx - cy * cy) / om;
+        }
+        const double k1 = dt * (-gux * k - gvx * l - oxi);
+        const double l1 = dt * (-guy * k - gvy * l - oyi);
+        const double k2 = dt * (-gux * (k + k1 / 2) - gvx * (l + l1 / 2) - oxi);
+        const double l2 = dt * (-guy * (k + k1 / 2) - gvy * (l + l1 / 2) - oyi);
+        const double k3 = dt * (-gux * (k + k2 / 2) - gvx * (l + l2 / 2) - oxi);
+        const double l3 = dt * (-guy * (k + k2 / 2) - gvy * (l + l2 / 2) - oyi);
+        const double k4 = dt * (-gux * (k + k3) - gvx * (l + l3) - oxi);
+        const double l4 = dt * (-guy * (k + k3) - gvy * (l + l3) - oyi);
+        k = k + (k1 + 2 * k2 + 2 * k3 + k4) / 6;
+        l = l + (l1 + 2 * l2 + 2 * l3 + l4) / 6;
+        if constexpr (XKA) {
+            const double a1 = dt * (-am * dci);
+            const double a2 = dt * (-(am + a1 / 2) * dci);
+            const double a3 = dt * (-(am + a2 / 2) * dci);
+            const double a4 = dt * (-(am + a3) * dci);
+            am = am + (a1 + 2 * a2 + 2 * a3 + a4) / 6;
+        }
+        x = xs; y = ys;
+    }
+    if (p < a.n && q == 0) {
+        a.x[p] = x; a.y[p] = y; a.k[p] = k; a.l[p] = l;
+        if (XKA) a.a[p] = am;
+    }
+}
+
 // half-plane coefficients (g2k layout, the ky = 0 symmetrisation of fulspec.m:16 applied) -> deconvolved, zero-padded
 // full spectrum of the nf x nf fine grid in FFT order: full[ky'*nf + kx'] (x fastest)
 __global__ void nufft_spread_kernel(const double2* __restrict__ half, int nx, int nf, const double* __restrict__ invphi,
@@ -200,6 +300,14 @@ cudaError_t launch_nufft_eval(const NufftArgs& a, cudaStream_t st) {
 cudaError_t launch_nufft_leapfrog(const NufftArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
     nufft_leapfrog_kernel<<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nufft_rk4(const NufftArgs& a, bool xka, cudaStream_t st) {
+    if (a.n <= 0) return cudaSuccess;
+    const unsigned nb = (unsigned)((4 * a.n + kBlock - 1) / kBlock);
+    if (xka) nufft_rk4_kernel<true><<<nb, kBlock, 0, st>>>(a);
+    else nufft_rk4_kernel<false><<<nb, kBlock, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -51,6 +51,7 @@ struct swrt_handle {
     double u_mean[2] = {0.0, 0.0};
     bool disable_psi = false;
     bool preblend_grid = false;       // LAGRANGE6: blend the two grids before the gather (fast) instead of after (exact)
+    bool unfused_rk4 = false;         // NUFFT: compose step_packet* from evaluation + glue launches (the dense mode's route)
     Stack stacks[SUB_COUNT];
     // lagrange grids per slot (node-interleaved, always 7 planes wide when H given else 6)
     double* grid[2] = {nullptr, nullptr};
@@ -434,21 +435,22 @@ int nufft_grid_from_planes(swrt_handle* h, int slot) {
     if (!h->nufft_grid[slot]) CU(h, cudaMalloc(&h->nufft_grid[slot], 2 * n * sizeof(double)));
     FftWork* fw = static_cast<FftWork*>(h->nufft_fft);
     cufftSetStream(fw->plan, h->stream);
-    for (int c = 0; c < 2; c++) {
-        launch_nufft_spread(h->planes[slot][c], nx, nf, h->nufft_invphi, fw->full, h->stream);
+    // flows that carry H = 1 + eta_g (raytrace_sw.m:49) also get a fine grid of 32-byte (u, v, H, 0) nodes, so that the
+    // evaluations of step_packet_xka fetch a node with one 256-bit load
+    const bool with_h = h->slot_npl[slot] == 7;
+    if (with_h && !h->nufft_h[slot]) {
+        CU(h, cudaMalloc(&h->nufft_h[slot], 4 * n * sizeof(double)));
+        CU(h, cudaMemsetAsync(h->nufft_h[slot], 0, 4 * n * sizeof(double), h->stream));
+    }
+    if (!with_h) dfree(h->nufft_h[slot]);
+    for (int c = 0; c < (with_h ? 3 : 2); c++) {
+        launch_nufft_spread(h->planes[slot][c < 2 ? c : 6], nx, nf, h->nufft_invphi, fw->full, h->stream);
         if (cufftExecZ2Z(fw->plan, (cufftDoubleComplex*)fw->full, (cufftDoubleComplex*)fw->full, CUFFT_INVERSE) != CUFFT_SUCCESS)
             return fail(h, SWRT_ERR_CUDA, "cufftExecZ2Z(nufft) failed");
-        launch_nufft_store(fw->full, nf, c, 2, h->nufft_grid[slot], h->stream);
-        h->launches += 3;
+        if (c < 2) { launch_nufft_store(fw->full, nf, c, 2, h->nufft_grid[slot], h->stream); h->launches++; }
+        if (with_h) { launch_nufft_store(fw->full, nf, c, 4, h->nufft_h[slot], h->stream); h->launches++; }
+        h->launches += 2;
     }
-    if (h->slot_npl[slot] == 7) {          // H = 1 + eta_g (raytrace_sw.m:49): its own 8-byte-per-node fine grid
-        if (!h->nufft_h[slot]) CU(h, cudaMalloc(&h->nufft_h[slot], n * sizeof(double)));
-        launch_nufft_spread(h->planes[slot][6], nx, nf, h->nufft_invphi, fw->full, h->stream);
-        if (cufftExecZ2Z(fw->plan, (cufftDoubleComplex*)fw->full, (cufftDoubleComplex*)fw->full, CUFFT_INVERSE) != CUFFT_SUCCESS)
-            return fail(h, SWRT_ERR_CUDA, "cufftExecZ2Z(nufft H) failed");
-        launch_nufft_store(fw->full, nf, 0, 1, h->nufft_h[slot], h->stream);
-        h->launches += 3;
-    } else dfree(h->nufft_h[slot]);
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaGetLastError());
     return SWRT_OK;
@@ -468,8 +470,8 @@ int active_nufft_grid(swrt_handle* h, double alpha, const double** out, const do
     h->launches++;
     *out = h->nufft_blend;
     if (want_h && h->nufft_h[0] && h->nufft_h[1]) {
-        if (!h->nufft_hblend) CU(h, cudaMalloc(&h->nufft_hblend, nd / 2 * sizeof(double)));
-        launch_axpby(h->nufft_hblend, h->nufft_h[0], h->nufft_h[1], 1.0 - alpha, alpha, nd / 2, h->stream);
+        if (!h->nufft_hblend) CU(h, cudaMalloc(&h->nufft_hblend, 2 * nd * sizeof(double)));
+        launch_axpby(h->nufft_hblend, h->nufft_h[0], h->nufft_h[1], 1.0 - alpha, alpha, 2 * nd, h->stream);   // (u,v,H,0) nodes
         h->launches++;
         *hout = h->nufft_hblend;
     }
@@ -944,7 +946,28 @@ static int step_rk4(swrt_handle* h, bool xka, double dt, int nsteps, double alph
         h->timing_valid = true;
         return SWRT_OK;
     }
-    // SPECTRAL / NUFFT: continuous ray equations composed point-wise; 5 evaluations per step
+    if (h->p.mode == SWRT_MODE_NUFFT && !h->unfused_rk4) {
+        // one launch per run of steps on one flow (steady: all of them): stages, evaluations and the k / a update fused
+        const bool steady = (dalpha == 0.0);
+        const int outer = steady ? 1 : nsteps, inner = steady ? nsteps : 1;
+        for (int j = 0; j < outer; j++) {
+            const double *g = nullptr, *gh = nullptr;
+            if ((rc = active_nufft_grid(h, alpha0 + j * dalpha, &g, xka ? &gh : nullptr))) return rc;
+            REQUIRE(h, !xka || gh, SWRT_ERR_STATE, "flow has no H plane (needed by this scheme)");
+            NufftArgs a{};
+            fill_nufft_args(h, g, a);
+            a.hgrid = gh;
+            a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
+            a.f = h->p.f; a.C0 = C0; a.dt = dt; a.nsteps = inner;
+            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
+            CU(h, launch_nufft_rk4(a, xka, h->stream));
+            h->launches++; h->last_nlaunch++;
+        }
+        CU(h, cudaEventRecord(h->ev1, h->stream));
+        h->timing_valid = true;
+        return SWRT_OK;
+    }
+    // SPECTRAL (and NUFFT with the un-fused tuning flag): continuous ray equations composed point-wise; 5 evaluations per step
     if ((rc = ensure_scratch(h, h->n))) return rc;
     CU(h, cudaEventRecord(h->ev0, h->stream));
     for (int j = 0; j < nsteps; j++) {
@@ -1831,6 +1854,7 @@ int swrt_set_tuning(swrt_handle* h, int mtiles, int flags) {
     h->mtiles = mtiles;
     h->disable_psi = (flags & 1) != 0;
     h->preblend_grid = (flags & 2) != 0;
+    h->unfused_rk4 = (flags & 4) != 0;
     return SWRT_OK;
 }
 

@@ -133,20 +133,22 @@ constexpr double kNufftSigma = 2.0;     // oversampling: nf = 2 nx
 constexpr double kNufftBeta = 2.30 * kNufftW;
 struct NufftArgs {
     const double2* grid;    // (u,v) fine grid, [iy*nf + ix]
-    const double* hgrid;    // optional H fine grid (same indexing); EVAL only
+    const double* hgrid;    // optional (u,v,H,0) fine grid, 4 doubles per node, same indexing (flows that carry H)
     int nf;
     long long n;
     const double* xin; const double* yin;
-    double* x; double* y; double* k; double* l;
+    double* x; double* y; double* k; double* l; double* a;
     double* out[7];
     double dx, nxd, beta, dscale;       // dscale = -sigma / (dx * w/2): d/dx of the kernel argument
     double f2, gH, dt;
+    double f, C0;                       // RK4 steppers (step_packet / step_packet_xka)
     int nsteps;
 };
 void launch_nufft_spread(const double2* half, int nx, int nf, const double* invphi_dev, double2* full, cudaStream_t st);
 void launch_nufft_store(const double2* full, int nf, int c, int stride, double* grid2, cudaStream_t st);
 cudaError_t launch_nufft_eval(const NufftArgs& a, cudaStream_t st);
 cudaError_t launch_nufft_leapfrog(const NufftArgs& a, cudaStream_t st);
+cudaError_t launch_nufft_rk4(const NufftArgs& a, bool xka, cudaStream_t st);
 
 struct Bs23Args {          // ode23 work arrays, component order x,y,k,l
     long long n;

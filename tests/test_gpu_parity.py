@@ -969,6 +969,41 @@ def test_nufft_step_packet_xka_matches_dense_spectral():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("xka", [False, True])
+def test_nufft_fused_rk4_kernel_equals_the_composed_launches(xka):
+    """step_packet / step_packet_xka in NUFFT mode: the fused kernel (stages, evaluations, k / a update in one launch)
+    against the evaluation + stage launches the dense mode composes (tuning flag): same expressions, so 1e-13 on the
+    state; steady (6 steps in one launch) and two-frame (one launch per step, alpha advancing)"""
+    w = W.make_workload("C5", n_packets=2500, nx=48)
+    planes = W.planes_from_psik(w.psik, w.L, w.u_mean, etak=w.extra["etak"])
+    rs = np.random.RandomState(3)
+    planes2 = [pl * np.exp(1j * rs.uniform(-0.05, 0.05, pl.shape)) for pl in planes]
+    scheme = S.SCHEME_RK4_XKA if xka else S.SCHEME_RK4_PACKET
+    for two_frames in (False, True):
+        outs = []
+        for unfused in (False, True):
+            with S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_NUFFT) as e:
+                e.set_tuning(unfused_rk4=unfused)
+                e.set_flow_planes_spectral(planes)
+                if two_frames:
+                    e.set_flow_planes_spectral(planes2, 1)
+                e.set_packets(w.x, w.y, w.k, w.l, np.ones(w.n_packets))
+                n0 = e.launch_count()
+                if two_frames:
+                    e.step(scheme, w.dt, 6, 1 / 12, 1 / 6)
+                else:
+                    e.step(scheme, w.dt, 6)
+                outs.append((np.stack(e.get_packets(with_a=True)), e.launch_count() - n0))
+        (fused, nl_f), (comp, nl_c) = outs
+        assert np.abs(fused - comp).max() < 1e-13 * max(1.0, np.abs(comp).max())
+        assert nl_f < nl_c
+        if not two_frames:
+            assert nl_f == 1
+        if xka:
+            assert np.abs(fused[4] - 1.0).max() > 1e-6
+
+
+@pytest.mark.gpu
 def test_nufft_full_size_C4_shard_agrees_with_dense_contraction():
     """512^2, L = 20, shear, two-frame blend: the dense DMMA contraction and the NUFFT gather are two evaluations of one
     Fourier series; on 4,096 packets of the C4 workload they agree to 1e-12 of max|plane|, and 16 leapfrog steps to 1e-9"""
