@@ -456,11 +456,14 @@ def main():
             ne2e.append((time.perf_counter() - t0) * 1e3)
         nm, ne_ms = float(np.mean(nms)), float(np.mean(ne2e[2:]))
         nuf = {"value": n * sub / (nm * 1e-3), "unit": UNIT, "ms_per_step": round(nm, 4),
-               "gather_GBps": round(ne.work_per_eval(6) * n * sub * {"leapfrog": 1, "rk4_packet": 4, "rk4_xka": 5}[w.scheme] / (nm * 1e-3) * 1e-9, 1),
+               "gather_GBps": round(ne.work_per_eval(7 if w.scheme == "rk4_xka" else 6) * n * sub
+                                    * {"leapfrog": 1, "rk4_packet": 4, "rk4_xka": 5}[w.scheme] / (nm * 1e-3) * 1e-9, 1),
+               "launches_per_step": ne.last_kernel_ms()[1],
                "e2e": {"value": n * sub / (ne_ms * 1e-3), "unit": UNIT, "ms_per_step": round(ne_ms, 4),
                        "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n},
                "note": "NUFFT mode: identical Fourier-series semantics to the headline (parity <= 1e-12), cost independent of nx; "
-                       "L1TEX/L2-gather bound (324 nodes x 16 B per evaluation), fine grids built per frame by cuFFT (untimed setup)"}
+                       "L1TEX/L2-gather bound (324 nodes x 16 B per evaluation; 32-byte (u,v,H,0) nodes for step_packet_xka, whose "
+                       "stages, evaluations and k / a update are one fused launch), fine grids built per frame by cuFFT (untimed setup)"}
         ne.close()
 
     cpu = cpu_spec = None

@@ -57,7 +57,15 @@ __device__ __forceinline__ void stencil_origin(double xl, int nf, int& base, dou
 // segment instead of four scattered lines -- the kernel is bound by L1 data-pipe wavefronts) and evaluates the kernel
 // for those columns and for the rows b = q, q+4, ...; row weights travel inside the quad by shuffle.  All four lanes end
 // with bit-identical sums (the butterfly adds are commutative), so the redundant packet state stays consistent.
-constexpr int QR = (W + 3) / 4;      // columns (and rows) owned per lane, the last round partly empty
+#ifndef SWRT_NUFFT_LPP
+#define SWRT_NUFFT_LPP 4
+#endif
+// lanes per packet: 4 = quad (shipped).  8 = octet (a 128-byte segment per round, 3 rounds instead of 5) was measured and
+// is slower: 1.62e9 against 1.85e9 packet-steps/s at C3, the extra redundant per-packet work outweighs the wider segments
+constexpr int LPP = SWRT_NUFFT_LPP;
+constexpr int LPP_SHIFT = LPP == 8 ? 3 : 2;
+static_assert(LPP == 4 || LPP == 8, "lanes per packet");
+constexpr int QR = (W + LPP - 1) / LPP;          // columns (and rows) owned per lane, the last round partly empty
 
 struct __align__(32) Node4 { double u, v, h, pad; };
 __device__ __forceinline__ Node4 ldg_node4(const Node4* p) {        // SASS LDG.E.256 (read-only path)
@@ -76,7 +84,7 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, co
     int ixr[QR];
 #pragma unroll
     for (int r = 0; r < QR; r++) {
-        const int a = q + 4 * r;
+        const int a = q + LPP * r;
         const bool on = a < W;
         es_kernel((tx + (double)a) * (1.0 / HALF_W), beta, wx0[r], wx1[r]);
         es_kernel((ty + (double)a) * (1.0 / HALF_W), beta, my0[r], my1[r]);
@@ -87,24 +95,27 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, co
         if (ix >= nf) ix -= nf;                // nx = 8: nf = 16 < w, the stencil wraps twice
         ixr[r] = ix;
     }
+    const bool last_on = q + LPP * (QR - 1) < W;
     double U = 0, V = 0, Ux = 0, Uy = 0, Vx = 0, Vy = 0, Hs = 0;
 #pragma unroll
     for (int b = 0; b < W; b++) {
-        const double wy0 = __shfl_sync(0xffffffffu, my0[b >> 2], quad_base | (b & 3));
-        const double wy1 = WITH_GRAD ? __shfl_sync(0xffffffffu, my1[b >> 2], quad_base | (b & 3)) : 0.0;
+        const double wy0 = __shfl_sync(0xffffffffu, my0[b >> LPP_SHIFT], quad_base | (b & (LPP - 1)));
+        const double wy1 = WITH_GRAD ? __shfl_sync(0xffffffffu, my1[b >> LPP_SHIFT], quad_base | (b & (LPP - 1))) : 0.0;
         int iy = jb + b;
         if (iy >= nf) iy -= nf;
         if (iy >= nf) iy -= nf;
         double su0 = 0, su1 = 0, sv0 = 0, sv1 = 0, sh0 = 0;
 #pragma unroll
         for (int r = 0; r < QR; r++) {
-            double2 g;
-            if constexpr (WITH_H) {
-                const Node4 nd = ldg_node4(reinterpret_cast<const Node4*>(uvh) + (size_t)iy * nf + ixr[r]);
-                g.x = nd.u; g.y = nd.v;
-                sh0 = fma(wx0[r], nd.h, sh0);
-            } else {
-                g = __ldg(grid + (size_t)iy * nf + ixr[r]);
+            double2 g = make_double2(0.0, 0.0);
+            if (r < QR - 1 || last_on) {            // lanes whose column of the last round is past the stencil issue no load
+                if constexpr (WITH_H) {
+                    const Node4 nd = ldg_node4(reinterpret_cast<const Node4*>(uvh) + (size_t)iy * nf + ixr[r]);
+                    g.x = nd.u; g.y = nd.v;
+                    sh0 = fma(wx0[r], nd.h, sh0);
+                } else {
+                    g = __ldg(grid + (size_t)iy * nf + ixr[r]);
+                }
             }
             su0 = fma(wx0[r], g.x, su0); sv0 = fma(wx0[r], g.y, sv0);
             if constexpr (WITH_GRAD) { su1 = fma(wx1[r], g.x, su1); sv1 = fma(wx1[r], g.y, sv1); }
@@ -123,6 +134,7 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, co
         double v = o[c];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if constexpr (LPP == 8) v += __shfl_xor_sync(0xffffffffu, v, 4);
         F[c] = v;
     }
 }
@@ -130,8 +142,8 @@ __device__ __forceinline__ void nufft_eval6(const double2* __restrict__ grid, co
 template <bool WITH_H>
 __global__ void __launch_bounds__(kBlock) nufft_eval_kernel(const NufftArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = t >> 2;
-    const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
+    const long long p = t >> LPP_SHIFT;
+    const int lane = threadIdx.x & 31, q = lane & (LPP - 1), qb = lane & ~(LPP - 1);
     const long long pc = p < a.n ? p : a.n - 1;              // idle quads of the last warp still take part in the shuffles
     double F[7];
     nufft_eval6<WITH_H>(a.grid, a.hgrid, a.nf, a.beta, a.dscale, reduced_coord(a.xin[pc], a.dx, a.nxd),
@@ -149,8 +161,8 @@ __global__ void __launch_bounds__(kBlock) nufft_eval_kernel(const NufftArgs a) {
 #endif
 __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_MINB) nufft_leapfrog_kernel(const NufftArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = t >> 2;
-    const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
+    const long long p = t >> LPP_SHIFT;
+    const int lane = threadIdx.x & 31, q = lane & (LPP - 1), qb = lane & ~(LPP - 1);
     const long long pc = p < a.n ? p : a.n - 1;
     double x = a.x[pc], y = a.y[pc], k = a.k[pc], l = a.l[pc];
     const double h = 0.5 * a.dt;
@@ -183,8 +195,8 @@ __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_MINB) nufft_leapfrog_kernel
 template <bool XKA>
 __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_RK4_MINB) nufft_rk4_kernel(const NufftArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = t >> 2;
-    const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
+    const long long p = t >> LPP_SHIFT;
+    const int lane = threadIdx.x & 31, q = lane & (LPP - 1), qb = lane & ~(LPP - 1);
     const long long pc = p < a.n ? p : a.n - 1;
     double x = a.x[pc], y = a.y[pc], k = a.k[pc], l = a.l[pc];
     double am = XKA ? a.a[pc] : 0.0;
@@ -293,19 +305,19 @@ void launch_nufft_store(const double2* full, int nf, int c, int stride, double* 
 }
 cudaError_t launch_nufft_eval(const NufftArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.hgrid) nufft_eval_kernel<true><<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
-    else nufft_eval_kernel<false><<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
+    if (a.hgrid) nufft_eval_kernel<true><<<(unsigned)(((long long)LPP * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
+    else nufft_eval_kernel<false><<<(unsigned)(((long long)LPP * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_nufft_leapfrog(const NufftArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    nufft_leapfrog_kernel<<<(unsigned)((4 * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
+    nufft_leapfrog_kernel<<<(unsigned)(((long long)LPP * a.n + kBlock - 1) / kBlock), kBlock, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_nufft_rk4(const NufftArgs& a, bool xka, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    const unsigned nb = (unsigned)((4 * a.n + kBlock - 1) / kBlock);
+    const unsigned nb = (unsigned)(((long long)LPP * a.n + kBlock - 1) / kBlock);
     if (xka) nufft_rk4_kernel<true><<<nb, kBlock, 0, st>>>(a);
     else nufft_rk4_kernel<false><<<nb, kBlock, 0, st>>>(a);
     return cudaGetLastError();

@@ -1810,7 +1810,8 @@ double swrt_work_per_eval(const swrt_handle* h, int nplanes) {
         // flops per folded complex MAC ... = 2 * nplanes * nx^2 for the unpadded problem
         return 2.0 * nplanes * (double)h->p.nx * (double)h->p.nx;
     }
-    if (h->p.mode == SWRT_MODE_NUFFT) return (double)kNufftW * kNufftW * 16.0;   // gathered bytes: w^2 = 324 (u,v) nodes, all six planes
+    // gathered bytes: w^2 = 324 nodes; 16-byte (u,v) nodes give all six planes, 32-byte (u,v,H,0) nodes the seven
+    if (h->p.mode == SWRT_MODE_NUFFT) return (double)kNufftW * kNufftW * (nplanes >= 7 ? 32.0 : 16.0);
     return 36.0 * nplanes * 8.0;   // gathered bytes
 }
 
