@@ -263,7 +263,15 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     g.chunk_doubles = (size_t)g.kc * g.NT * 32;
     g.total_doubles = (size_t)g.npass * g.ksteps * g.NT * 32;
     size_t chunk_bytes = g.chunk_doubles * 8;
-    g.nstages = (int)((200 * 1024 / kCtasPerSm) / chunk_bytes);
+    // Twiddle table: one double per lane per k-step per warp (the A fragments of a whole step), written and read back
+    // by the same lane.  With it the k-loop holds no fp64 instruction but the DMMAs (tools/dmma_lds_bench.cu: 36.3
+    // against 34.9 TFLOP/s for the loop with the 4-DFMA rotation per k-step).  It needs ksteps * 2 KB of shared memory
+    // next to a ring of at least three chunks, which holds up to nx = 128; larger grids rotate in registers.
+    const size_t atab_bytes = (size_t)g.ksteps * 32 * 8 * kConsumerWarps;
+    g.atab = (mtiles == 1 && kCtasPerSm == 1 && atab_bytes + 3 * chunk_bytes <= 216 * 1024) ? 1 : 0;
+    if (const char* e = getenv("SWRT_ATAB")) g.atab = (atoi(e) != 0 && mtiles == 1 && kCtasPerSm == 1 && atab_bytes + 3 * chunk_bytes <= 216 * 1024) ? 1 : 0;
+    const size_t ring_budget = g.atab ? (216 * 1024 - atab_bytes) : (size_t)(200 * 1024 / kCtasPerSm);
+    g.nstages = (int)(ring_budget / chunk_bytes);
     if (g.nstages > 8) g.nstages = 8;
     if (g.nstages < 3) g.nstages = 3;
     // Warps 4..7 (the second warp of every SM sub-partition) start ~1.5 chunks after warps 0..3, so
@@ -284,7 +292,8 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
 }
 
 size_t spectral_smem_bytes(const PackGeom& g) {
-    return (size_t)g.nstages * g.chunk_doubles * 8 + 2 * g.nstages * sizeof(uint64_t) + 128;
+    // ring | full/empty barriers (padded to 128 bytes) | twiddle table
+    return (size_t)g.nstages * g.chunk_doubles * 8 + 128 + (g.atab ? (size_t)g.ksteps * 32 * 8 * kConsumerWarps : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -294,8 +303,9 @@ size_t spectral_smem_bytes(const PackGeom& g) {
 // (integer kx); the six velocity/gradient planes of SpectralScheme.m:18-25 are assembled in stage 2:
 //   u = kap ky Im[T G0], v = kap Re[T G1], ux = kap^2 ky Im[T G1], uy = kap^2 ky^2 Re[T G0],
 //   vx = kap^2 Re[T G2], vy = -ux   (T = e^{i ky ty}),  which halves the DMMA work (6 nx^2 flops).
-template <int NPL, int G, int MT, int MODE, bool PSI>
+template <int NPL, int G, int MT, int MODE, bool PSI, bool ATAB>
 __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(const SpecArgs a) {
+    static_assert(!ATAB || MT == 1, "the twiddle table is laid out for one m-tile per warp");
     constexpr int NT = NPL * G;
     constexpr int NF = PSI ? 6 : NPL;          // planes produced per packet
     static_assert(!PSI || NPL == 3, "psi mode contracts exactly three moment planes");
@@ -312,6 +322,8 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // this lane's column of the warp's twiddle table: sA[s * 32] = A element of k-step s (written and read by this lane only)
+    double* const sA = reinterpret_cast<double*>(smem_raw + (size_t)nstages * chunk_bytes + 128) + (size_t)warp * g.ksteps * 32 + lane;
     const long long ntiles = (a.n + TILE_P - 1) / TILE_P;
     const int nevals = (MODE == SPEC_LEAPFROG) ? a.nsteps : 1;
 
@@ -454,6 +466,16 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                 kyd[mt] = (double)jq;
             }
 
+            if constexpr (ATAB) {
+                // the same two recurrences the in-loop rotation runs, tabulated once per step for all passes
+                double ap = ep0[0], aq = eq0[0], bp = ep1[0], bq = eq1[0];
+                for (int s = 0; s < g.ksteps; s += 2) {
+                    sA[s * 32] = ap; sA[(s + 1) * 32] = bp;
+                    const double nap = fma(ap, xdc[0], fma(aq, xds[0], ap)), naq = fma(aq, xdc[0], fma(-ap, xds[0], aq));
+                    const double nbp = fma(bp, xdc[0], fma(bq, xds[0], bp)), nbq = fma(bq, xdc[0], fma(-bp, xds[0], bq));
+                    ap = nap; aq = naq; bp = nbp; bq = nbq;
+                }
+            }
             // ---- passes over ky blocks -----------------------------------------------------
             for (int pass = 0; pass < kyp_passes; pass++) {
                 double acc[MT][NT][2];
@@ -461,8 +483,10 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                 for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
                     for (int t = 0; t < NT; t++) { acc[mt][t][0] = 0.0; acc[mt][t][1] = 0.0; }
-                    tp_[mt] = ep0[mt]; tq_[mt] = eq0[mt];
-                    tpB[mt] = ep1[mt]; tqB[mt] = eq1[mt];
+                    if constexpr (!ATAB) {
+                        tp_[mt] = ep0[mt]; tq_[mt] = eq0[mt];
+                        tpB[mt] = ep1[mt]; tqB[mt] = eq1[mt];
+                    }
                 }
                 for (int ch = 0; ch < chunks_per_pass; ch++) {
                     SWRT_TRACE_EV(0);
@@ -474,6 +498,7 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                     if (!ready) mbar_wait(&full_bar[stage], phase);
                     SWRT_TRACE_EV(2);
                     const double2* sB = reinterpret_cast<const double2*>(smem_raw + (size_t)stage * chunk_bytes) + lane;
+                    const double* sAc = sA + (size_t)ch * g.kc * 32;
                     int nstage = stage + 1; uint32_t nphase = phase;
                     if (nstage == nstages) { nstage = 0; nphase ^= 1; }
                     for (int s0 = 0; s0 < g.kc; s0 += kKUnroll) {
@@ -483,6 +508,7 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
 #pragma unroll
                         for (int su = 0; su < kKUnroll; su++) {
                             const int s = s0 + su;
+                            if constexpr (ATAB) tp_[0] = sAc[s * 32];
 #pragma unroll
                             for (int tp = 0; tp < HALF_NT; tp++) {
                                 double2 b = sB[(s * HALF_NT + tp) * 32];
@@ -493,7 +519,7 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                                 }
                             }
 #pragma unroll
-                            for (int mt = 0; mt < MT; mt++) {
+                            for (int mt = 0; mt < (ATAB ? 0 : MT); mt++) {
                                 // this chain's next value (two k-steps ahead): E <- E + E*(e^{i 4 tx} - 1); then swap chains
                                 double np = fma(tp_[mt], xdc[mt], fma(tq_[mt], xds[mt], tp_[mt]));
                                 double nq = fma(tq_[mt], xdc[mt], fma(-tp_[mt], xds[mt], tq_[mt]));
@@ -606,11 +632,11 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
     }
 }
 
-template <int NPL, int G, int MT, int MODE, bool PSI>
-static cudaError_t launch_inst(const SpecArgs& a, int num_sms, cudaStream_t st) {
+template <int NPL, int G, int MT, int MODE, bool PSI, bool ATAB>
+static cudaError_t launch_inst2(const SpecArgs& a, int num_sms, cudaStream_t st) {
     constexpr int TILE_P = kConsumerWarps * 8 * MT;
     size_t smem = spectral_smem_bytes(a.g);
-    auto kern = spectral_kernel<NPL, G, MT, MODE, PSI>;
+    auto kern = spectral_kernel<NPL, G, MT, MODE, PSI, ATAB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long ntiles = (a.n + TILE_P - 1) / TILE_P;
@@ -618,6 +644,14 @@ static cudaError_t launch_inst(const SpecArgs& a, int num_sms, cudaStream_t st) 
     if (grid < 1) grid = 1;
     kern<<<grid, kSpecThreads, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int NPL, int G, int MT, int MODE, bool PSI>
+static cudaError_t launch_inst(const SpecArgs& a, int num_sms, cudaStream_t st) {
+    if constexpr (MT == 1) {
+        if (a.g.atab) return launch_inst2<NPL, G, MT, MODE, PSI, true>(a, num_sms, st);
+    }
+    return launch_inst2<NPL, G, MT, MODE, PSI, false>(a, num_sms, st);
 }
 
 template <int NPL, int G, int MT>

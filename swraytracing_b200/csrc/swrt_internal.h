@@ -37,6 +37,8 @@ struct PackGeom {
     int nstages;
     int lag;              // a stage is refilled `lag` chunks after warp 0 released it
     int desync_ns;        // start-up skew of warps 4..7 (0 = none)
+    int atab;             // 1: the x twiddles of a step are tabulated in shared memory (A fragments by LDS.64), else
+                          //    rotated in registers inside the k-loop
     size_t chunk_doubles; // kc * NT * 32
     size_t total_doubles; // npass * ksteps * NT * 32
     int plane_ids[kMaxPlanes];   // which of the 7 source planes each stack plane is

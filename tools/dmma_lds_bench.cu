@@ -7,11 +7,14 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 // 0: DMMA only (B in regs), 1: + LDS.128 per pair, 2: + LDS + 4 DFMA twiddle per k-step,
 // 3: twiddles for 4 k-steps computed in one burst (16 DFMA) every 4 k-steps, 4: Reinsch 2-op recurrence per k-step,
-// 5: Reinsch burst for 4 k-steps
+// 5: Reinsch burst for 4 k-steps, 6: A fragment from a shared-memory table (one LDS.64 per k-step, no DFMA in the loop),
+// 7: own element only, partner's by shuffle (2 DFMA + SHFL per k-step)
 template <int MODE>
 __global__ void __launch_bounds__(256, 1) k(double* out, const double* in, int iters) {
     extern __shared__ double2 sB[];
     for (int i = threadIdx.x; i < 12 * 32 * 8; i += blockDim.x) sB[i] = make_double2(in[i & 63], in[(i + 7) & 63]);
+    double* sA = reinterpret_cast<double*>(sB + 12 * 32 * 8) + (threadIdx.x >> 5) * 32 * 32;     // per-warp twiddle table
+    for (int i = threadIdx.x & 31; i < 32 * 32; i += 32) sA[i] = in[i & 63];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     double acc[24][2];
@@ -47,6 +50,7 @@ __global__ void __launch_bounds__(256, 1) k(double* out, const double* in, int i
 #pragma unroll
             for (int tp = 0; tp < 12; tp++) {
                 double2 b = MODE >= 1 ? sB[(s * 12 + tp) * 32 + lane] : breg;
+                if (MODE == 6 && tp == 0) p = sA[((it & 3) * 8 + s) * 32 + lane];
                 dmma(acc[2 * tp][0], acc[2 * tp][1], p, b.x);
                 dmma(acc[2 * tp + 1][0], acc[2 * tp + 1][1], p, b.y);
             }
@@ -55,6 +59,7 @@ __global__ void __launch_bounds__(256, 1) k(double* out, const double* in, int i
                 p = np; q = nq;
             }
             if (MODE == 4) { dl = fma(dc, p, dl); p = p + dl; }
+            if (MODE == 7) { const double qq = __shfl_xor_sync(0xffffffffu, p, 1); p = fma(p, dc, fma(qq, ds, p)); }
         }
         }
     }
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(256, 1) k(double* out, const double* in, int i
     out[blockIdx.x * blockDim.x + threadIdx.x] = s + p + q + dl + pv[0] + pv[3];
 }
 template <int MODE> void run(const char* name, double* out, const double* in) {
-    int iters = 400, smem = 12 * 32 * 8 * 16;
+    int iters = 400, smem = 12 * 32 * 8 * 16 + 8 * 32 * 32 * 8;
     cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k<MODE><<<148, 256, smem>>>(out, in, 10);
     cudaDeviceSynchronize();
@@ -81,5 +86,6 @@ int main() {
     double *in, *out; cudaMalloc(&in, 4096); cudaMalloc(&out, 148 * 256 * 8);
     double h[128]; for (int i = 0; i < 128; i++) h[i] = 1e-3 * (i % 7) - 2e-3; cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice);
     run<0>("dmma_only_24acc", out, in); run<1>("dmma_lds128", out, in); run<2>("dmma_lds128_twiddle", out, in); run<3>("burst4_rotation", out, in); run<4>("reinsch_per_kstep", out, in); run<5>("burst4_reinsch", out, in);
+    run<6>("a_table_lds64", out, in); run<7>("own_element_shfl", out, in);
     return 0;
 }
