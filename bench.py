@@ -362,7 +362,7 @@ def main():
         achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
         roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
                     "frac": round(achieved / FP64_DGEMM_TFLOPS, 4), "traffic": NCU_TRAFFIC_BYTES.get((w.name, sub)) if w.n_packets == 65536 else None,
-                    "kernel": (f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'}> (fp64 DMMA m8n8k4)"
+                    "kernel": (f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'},{'twiddle-table' if w.nx <= 256 else 'twiddle-rotation'}> (fp64 DMMA m8n8k4)"
                                if w.scheme == "leapfrog" else "swrt::spectral_kernel<*,EVAL> x5 per step + glue (fp64 DMMA m8n8k4)"),
                     "kernel_ms": round(kernel_ms, 4), "contracted_planes": ncontract,
                     "flops_per_packet_step": flops_per_packet_step,

@@ -166,8 +166,51 @@ __device__ __forceinline__ void gather_pair(const double* __restrict__ grid, int
     }
 }
 
+// both frames of interpolate_U.m:5-17 in one sweep over the 36 nodes: the weight product is formed once per node and the
+// two frames' loads are issued together; each frame's plane is still accumulated by one lane in the reference's order
 template <int NPL>
-__global__ void __launch_bounds__(128) lagrange_eval_kernel(const LagArgs a) {
+__device__ __forceinline__ void gather_pair2(const double* __restrict__ grid, const double* __restrict__ grid2, int nx,
+                                             const Stencil& s, int q, double& F0, double& F1, double& G0, double& G1) {
+    F0 = 0.0; F1 = 0.0; G0 = 0.0; G1 = 0.0;
+    const int c0 = 2 * q;
+    const bool on0 = c0 < NPL, on1 = c0 + 1 < NPL;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const size_t rowoff = (size_t)s.ig[i] * nx * NPL;
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            const double w = s.wx[i] * s.wy[j];
+            const size_t off = rowoff + (size_t)s.jg[j] * NPL + c0;
+            double v0 = 0.0, v1 = 0.0, g0 = 0.0, g1 = 0.0;
+            if constexpr (NPL % 2 == 0) {
+                if (on0) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(grid + off));
+                    const double2 g = __ldg(reinterpret_cast<const double2*>(grid2 + off));
+                    v0 = v.x; v1 = v.y; g0 = g.x; g1 = g.y;
+                }
+            } else {
+                if (on0) { v0 = __ldg(grid + off); g0 = __ldg(grid2 + off); }
+                if (on1) { v1 = __ldg(grid + off + 1); g1 = __ldg(grid2 + off + 1); }
+            }
+            F0 = F0 + w * v0;
+            F1 = F1 + w * v1;
+            G0 = G0 + w * g0;
+            G1 = G1 + w * g1;
+        }
+    }
+}
+
+// TWO = a second frame is gathered with the same weights (interpolate_U.m).  The steady instantiation must not carry the
+// second gather: with a run-time branch ptxas hoists both frames' 72 loads and the kernel lands at 252 registers
+// (2 blocks per SM instead of 5; 0.27 -> 0.43 ms at C2).
+#ifndef SWRT_LAG_TWO_MINB
+#define SWRT_LAG_TWO_MINB 4     /* two-frame kernels: 128 registers; 0 / 1 / 3 / 4 give 2.20 / 1.56 / 2.23 / 2.62e9 packet-steps/s at C3 */
+#endif
+#ifndef SWRT_LAG_MINB
+#define SWRT_LAG_MINB 0     /* 0 = unspecified: ptxas then settles at 96 (leapfrog) / 64 (eval) registers */
+#endif
+template <int NPL, bool TWO>
+__global__ void __launch_bounds__(128, TWO ? SWRT_LAG_TWO_MINB : SWRT_LAG_MINB) lagrange_eval_kernel(const LagArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long p = t >> 2;
     const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
@@ -175,12 +218,13 @@ __global__ void __launch_bounds__(128) lagrange_eval_kernel(const LagArgs a) {
     Stencil s;
     make_stencil_quad(a.xin[pc], a.yin[pc], a.dx, a.nx, a.bump, q, qb, s);
     double F0, F1;
-    gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
-    if (a.grid2) {   // interpolate_U.m:19-23: interpolate BOTH frames, then (1 - alpha)*F1 + alpha*F2
+    if constexpr (TWO) {   // interpolate_U.m:19-23: interpolate BOTH frames, then (1 - alpha)*F1 + alpha*F2
         double G0, G1;
-        gather_pair<NPL>(a.grid2, a.nx, s, q, G0, G1);
+        gather_pair2<NPL>(a.grid, a.grid2, a.nx, s, q, F0, F1, G0, G1);
         F0 = (1.0 - a.alpha) * F0 + a.alpha * G0;
         F1 = (1.0 - a.alpha) * F1 + a.alpha * G1;
+    } else {
+        gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
     }
     if (p < a.n) {
         if (2 * q < NPL && a.out[2 * q]) a.out[2 * q][p] = F0;
@@ -189,8 +233,8 @@ __global__ void __launch_bounds__(128) lagrange_eval_kernel(const LagArgs a) {
 }
 
 // ode_symplectic.m:13-21,33-37 with scheme.U / grad_U = six Lagrange interpolations at x1
-template <int NPL>
-__global__ void __launch_bounds__(128) lagrange_leapfrog_kernel(const LagArgs a) {
+template <int NPL, bool TWO>
+__global__ void __launch_bounds__(128, TWO ? SWRT_LAG_TWO_MINB : SWRT_LAG_MINB) lagrange_leapfrog_kernel(const LagArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long p = t >> 2;
     const int lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3;
@@ -204,12 +248,13 @@ __global__ void __launch_bounds__(128) lagrange_leapfrog_kernel(const LagArgs a)
         Stencil s;
         make_stencil_quad(x, y, a.dx, a.nx, a.bump, q, qb, s);
         double F0, F1;
-        gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
-        if (a.grid2) {
+        if constexpr (TWO) {
             double G0, G1;
-            gather_pair<NPL>(a.grid2, a.nx, s, q, G0, G1);
+            gather_pair2<NPL>(a.grid, a.grid2, a.nx, s, q, F0, F1, G0, G1);
             F0 = (1.0 - a.alpha) * F0 + a.alpha * G0;
             F1 = (1.0 - a.alpha) * F1 + a.alpha * G1;
+        } else {
+            gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
         }
         // every lane needs all six planes for the kick: lane 0 holds (u,v), lane 1 (ux,uy), lane 2 (vx,vy)
         double F[6];
@@ -388,16 +433,18 @@ void launch_interleave_grid(const double* const* planes_dev, int npl, int nx, do
 
 cudaError_t launch_lagrange_eval(const LagArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.npl == 6) lagrange_eval_kernel<6><<<blocks_for(4 * a.n, 128), 128, 0, st>>>(a);
-    else if (a.npl == 7) lagrange_eval_kernel<7><<<blocks_for(4 * a.n, 128), 128, 0, st>>>(a);
+    const unsigned nb = blocks_for(4 * a.n, 128);
+    if (a.npl == 6) { if (a.grid2) lagrange_eval_kernel<6, true><<<nb, 128, 0, st>>>(a); else lagrange_eval_kernel<6, false><<<nb, 128, 0, st>>>(a); }
+    else if (a.npl == 7) { if (a.grid2) lagrange_eval_kernel<7, true><<<nb, 128, 0, st>>>(a); else lagrange_eval_kernel<7, false><<<nb, 128, 0, st>>>(a); }
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
 cudaError_t launch_lagrange_leapfrog(const LagArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.npl == 6) lagrange_leapfrog_kernel<6><<<blocks_for(4 * a.n, 128), 128, 0, st>>>(a);
-    else if (a.npl == 7) lagrange_leapfrog_kernel<7><<<blocks_for(4 * a.n, 128), 128, 0, st>>>(a);
+    const unsigned nb = blocks_for(4 * a.n, 128);
+    if (a.npl == 6) { if (a.grid2) lagrange_leapfrog_kernel<6, true><<<nb, 128, 0, st>>>(a); else lagrange_leapfrog_kernel<6, false><<<nb, 128, 0, st>>>(a); }
+    else if (a.npl == 7) { if (a.grid2) lagrange_leapfrog_kernel<7, true><<<nb, 128, 0, st>>>(a); else lagrange_leapfrog_kernel<7, false><<<nb, 128, 0, st>>>(a); }
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

@@ -253,24 +253,41 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     int kyp = 4 * G;
     g.npass = (g.nky + kyp - 1) / kyp;
     // ~48 KB chunks (kc k-steps of NT*256 bytes), kc a multiple of the k-loop unroll
-    int kc = 192 / g.NT;
-    g.kc = kc >= 16 ? 16 : (kc >= 8 ? 8 : 4);
-    if (const char* e = getenv("SWRT_KC")) g.kc = atoi(e);
-    if (g.kc % kKUnroll) g.kc = ((g.kc + kKUnroll - 1) / kKUnroll) * kKUnroll;
-    int ks = (g.kmax + 1 + 1) / 2;
-    g.ksteps = ((ks + g.kc - 1) / g.kc) * g.kc;
-    g.chunks_per_eval = g.npass * (g.ksteps / g.kc);
-    g.chunk_doubles = (size_t)g.kc * g.NT * 32;
-    g.total_doubles = (size_t)g.npass * g.ksteps * g.NT * 32;
-    size_t chunk_bytes = g.chunk_doubles * 8;
+    int kc0 = 192 / g.NT;
+    kc0 = kc0 >= 16 ? 16 : (kc0 >= 8 ? 8 : 4);
+    const int ks = (g.kmax + 1 + 1) / 2;
+    auto layout = [&](int kc) {
+        if (kc % kKUnroll) kc = ((kc + kKUnroll - 1) / kKUnroll) * kKUnroll;
+        g.kc = kc;
+        g.ksteps = ((ks + kc - 1) / kc) * kc;
+        g.chunks_per_eval = g.npass * (g.ksteps / kc);
+        g.chunk_doubles = (size_t)kc * g.NT * 32;
+        g.total_doubles = (size_t)g.npass * g.ksteps * g.NT * 32;
+    };
     // Twiddle table: one double per lane per k-step per warp (the A fragments of a whole step), written and read back
     // by the same lane.  With it the k-loop holds no fp64 instruction but the DMMAs (tools/dmma_lds_bench.cu: 36.3
     // against 34.9 TFLOP/s for the loop with the 4-DFMA rotation per k-step).  It needs ksteps * 2 KB of shared memory
-    // next to a ring of at least three chunks, which holds up to nx = 128; larger grids rotate in registers.
-    const size_t atab_bytes = (size_t)g.ksteps * 32 * 8 * kConsumerWarps;
-    g.atab = (mtiles == 1 && kCtasPerSm == 1 && atab_bytes + 3 * chunk_bytes <= 216 * 1024) ? 1 : 0;
-    if (const char* e = getenv("SWRT_ATAB")) g.atab = (atoi(e) != 0 && mtiles == 1 && kCtasPerSm == 1 && atab_bytes + 3 * chunk_bytes <= 216 * 1024) ? 1 : 0;
-    const size_t ring_budget = g.atab ? (216 * 1024 - atab_bytes) : (size_t)(200 * 1024 / kCtasPerSm);
+    // next to a ring of at least three chunks: 48 KB chunks up to nx = 128, 24 KB chunks at nx = 256 (measured there:
+    // 33.0 TFLOP/s rotating in registers with 48 KB chunks, 32.0 with 24 KB chunks, 33.7 with 24 KB chunks and the table);
+    // larger grids rotate in registers.
+    constexpr size_t kSmemBudget = 216 * 1024;
+    auto atab_fits = [&]() { return (size_t)g.ksteps * 32 * 8 * kConsumerWarps + 3 * g.chunk_doubles * 8 <= kSmemBudget; };
+    bool want_atab = mtiles == 1 && kCtasPerSm == 1;
+    if (const char* e = getenv("SWRT_ATAB")) want_atab = want_atab && atoi(e) != 0;
+    if (const char* e = getenv("SWRT_KC")) {
+        layout(atoi(e));
+        g.atab = want_atab && atab_fits();
+    } else {
+        layout(kc0);
+        g.atab = want_atab && atab_fits();
+        if (want_atab && !g.atab && kc0 > 4) {
+            layout(4);
+            g.atab = atab_fits();
+            if (!g.atab) layout(kc0);
+        }
+    }
+    const size_t chunk_bytes = g.chunk_doubles * 8;
+    const size_t ring_budget = g.atab ? (kSmemBudget - (size_t)g.ksteps * 32 * 8 * kConsumerWarps) : (size_t)(200 * 1024 / kCtasPerSm);
     g.nstages = (int)(ring_budget / chunk_bytes);
     if (g.nstages > 8) g.nstages = 8;
     if (g.nstages < 3) g.nstages = 3;
