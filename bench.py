@@ -125,11 +125,24 @@ def _cpu_setup(w):
     return _CPU_CACHE[id(w)]
 
 
+def _use_all_host_threads(CO):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and is meant to use every host
+    core this process may run on, so the thread count is set explicitly (an OMP_NUM_THREADS the USER chose is kept)."""
+    if os.environ.get("SWRT_CPU_THREADS"):
+        CO.set_threads(int(os.environ["SWRT_CPU_THREADS"]))
+    elif "TORCHELASTIC_RUN_ID" in os.environ or "OMP_NUM_THREADS" not in os.environ:
+        try:
+            CO.set_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            CO.set_threads(os.cpu_count() or 1)
+
+
 def cpu_reference_rate(w, target_s=12.0, nsteps=8):
     """packet-steps/s of the reference's own path -- ode_symplectic leapfrog with 6x6 Lagrange
     interpolation of the six gridded planes (SpectralScheme.m:45-68, interpolate.m) -- restated in C
     (oracle/swrt_oracle.c: orc_leapfrog_lagrange), all host threads.  Bounded sample of ~target_s."""
     from oracle import c_oracle as CO
+    _use_all_host_threads(CO)
     grids = _cpu_setup(w)
     n = min(w.n_packets, 65536)
     x, y, k, l = (a[:n].copy() for a in (w.x, w.y, w.k, w.l))
