@@ -1021,6 +1021,35 @@ def test_nufft_full_size_C4_shard_agrees_with_dense_contraction():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("with_H", [False, True])
+def test_lagrange_two_frame_sweep_equals_the_two_single_frame_gathers_bit_for_bit(with_H):
+    """interpolate_U.m:5-23 in LAGRANGE6 mode: the two-frame kernels gather both frames in one sweep over the 36 nodes;
+    every frame's plane must still be the same doubles as a single-frame gather of that frame (alpha = 0 / alpha = 1), and
+    the blend the un-fused (1 - alpha)*F1 + alpha*F2 -- for six planes and for seven (H, odd record length); a 12-step
+    two-frame leapfrog equals 12 single-step launches"""
+    w = W.make_workload("C5", n_packets=3001, nx=48)
+    planes = W.planes_from_psik(w.psik, w.L, w.u_mean, etak=w.extra["etak"])
+    rs = np.random.RandomState(11)
+    planes2 = [pl * np.exp(1j * rs.uniform(-0.05, 0.05, pl.shape)) for pl in planes]
+    if not with_H:
+        planes, planes2 = planes[:6], planes2[:6]
+    alpha = 0.3
+    with S.Engine(w.nx, w.L, w.f, w.gH, S.MODE_LAGRANGE6) as e:
+        e.set_flow_planes_spectral(planes, 0); e.set_flow_planes_spectral(planes2, 1)
+        f1 = e.eval_at(w.x, w.y, 0.0, with_H=with_H)
+        f2 = e.eval_at(w.x, w.y, 1.0, with_H=with_H)
+        fb = e.eval_at(w.x, w.y, alpha, with_H=with_H)
+        assert np.array_equal(fb, (1.0 - alpha) * f1 + alpha * f2)
+        e.set_packets(w.x, w.y, w.k, w.l)
+        e.step(S.SCHEME_LEAPFROG, w.dt, 12, 1 / 24, 1 / 12)
+        fused = np.stack(e.get_packets())
+        e.set_packets(w.x, w.y, w.k, w.l)
+        for j in range(12):
+            e.step(S.SCHEME_LEAPFROG, w.dt, 1, 1 / 24 + j * (1 / 12), 0.0)      # the doubles swrt_step forms: alpha0 + j*dalpha
+        assert np.array_equal(fused, np.stack(e.get_packets()))
+
+
+@pytest.mark.gpu
 def test_ode23_in_lagrange_mode_is_bit_identical_to_the_restatement():
     """qgsw_raytrace.m:141-150 in LAGRANGE6 mode: interpolate_U (both frames, blended results), odefun and the
     Bogacki-Shampine stages (y + f*hB, the error estimate f*E) are all executed without fused multiply-adds in the
