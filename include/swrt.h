@@ -230,6 +230,12 @@ int     swrt_set_tuning(swrt_handle* h, int mtiles, int flags);
 /* planes the spectral kernel contracts for a six-plane evaluation: 3 when every flow slot was
  * given as psi-hat (moments N0,N1,N2; 6 nx^2 flops), else 6 (12 nx^2 flops); 0 in LAGRANGE6    */
 int     swrt_contracted_planes(const swrt_handle* h);
+/* diagnostic, host-only (no device needed): the launch geometry the dense kernel would use for an
+ * nx^2 grid contracting `nplanes` planes with `mtiles` m-tiles per warp.  out[0..9] = n-tiles per
+ * pass, ky passes, k-steps per pass (padded), k-steps per chunk, ring stages, chunk bytes, twiddle
+ * table on (1) / off (0), twiddle-table bytes, dynamic shared memory bytes per CTA, packed-stack
+ * bytes per flow slot.  Returns SWRT_OK or SWRT_ERR_ARG.                                          */
+int     swrt_spectral_geometry(int nx, int nplanes, int mtiles, int64_t out[10]);
 
 #ifdef __cplusplus
 }

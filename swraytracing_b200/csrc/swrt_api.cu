@@ -1864,4 +1864,18 @@ int swrt_contracted_planes(const swrt_handle* h) {
     return use_psi(h, h->slot_set[1] ? 0.5 : 0.0) ? 3 : 6;
 }
 
+int swrt_spectral_geometry(int nx, int nplanes, int mtiles, int64_t out[10]) {
+    if (!out || nx < 4 || (nx & 1) || nplanes < 1 || nplanes > kMaxPlanes || mtiles < 1 || mtiles > 2)
+        return fail(nullptr, SWRT_ERR_ARG, "swrt_spectral_geometry: bad argument");
+    int ids[kMaxPlanes];
+    for (int i = 0; i < kMaxPlanes; i++) ids[i] = i;
+    const PackGeom g = make_geom(nx, nplanes, ids, mtiles);
+    out[0] = g.NT; out[1] = g.npass; out[2] = g.ksteps; out[3] = g.kc; out[4] = g.nstages;
+    out[5] = (int64_t)(g.chunk_doubles * 8); out[6] = g.atab;
+    out[7] = g.atab ? (int64_t)g.ksteps * 32 * 8 * kConsumerWarps : 0;
+    out[8] = (int64_t)spectral_smem_bytes(g);
+    out[9] = (int64_t)(g.total_doubles * 8);
+    return SWRT_OK;
+}
+
 }  // extern "C"

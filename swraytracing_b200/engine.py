@@ -86,6 +86,7 @@ SIGNATURES = {
     "swrt_synchronize": (C.c_int, [C.c_void_p]),
     "swrt_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "swrt_contracted_planes": (C.c_int, [C.c_void_p]),
+    "swrt_spectral_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "swrt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "swrt_timer_start": (C.c_int, [C.c_void_p]),
     "swrt_timer_stop": (C.c_double, [C.c_void_p]),
@@ -111,6 +112,16 @@ def load_library(path: os.PathLike | None = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def spectral_geometry(nx, nplanes=3, mtiles=1):
+    """launch geometry of the dense kernel (host-only diagnostic, swrt_spectral_geometry)"""
+    out = (C.c_int64 * 10)()
+    rc = load_library().swrt_spectral_geometry(int(nx), int(nplanes), int(mtiles), out)
+    if rc != 0:
+        raise SwrtError(rc, load_library().swrt_last_error(None).decode())
+    keys = ("ntiles", "npass", "ksteps", "kc", "nstages", "chunk_bytes", "twiddle_table", "table_bytes", "smem_bytes", "stack_bytes")
+    return dict(zip(keys, (int(v) for v in out)))
 
 
 def _f64(a):

@@ -92,3 +92,33 @@ def test_mex_gateway_compiles():
     for m in (ROOT / "matlab" / "shims").glob("*.m"):
         cmds |= set(re.findall(r"swrt_mex\('([a-z0-9_]+)'", m.read_text()))
     assert cmds and all(f'"{c}"' in text for c in cmds), cmds
+
+
+def test_spectral_geometry_fits_shared_memory_for_every_size():
+    """host-only: for every even grid size up to 512 and every plane count / m-tile choice the dense kernel's dynamic
+    shared memory (chunk ring + barriers + twiddle table) stays inside the 227 KB a CTA may opt into, the ring has at
+    least three chunks, chunks tile a pass, and the twiddle table (when on) has one double per lane per k-step per warp"""
+    from swraytracing_b200.engine import spectral_geometry
+    seen_on = seen_off = 0
+    for nx in list(range(4, 132, 2)) + [160, 192, 200, 250, 256, 258, 320, 384, 500, 512]:
+        for npl in range(1, 8):
+            for mt in (1, 2):
+                g = spectral_geometry(nx, npl, mt)
+                assert g["smem_bytes"] <= 227 * 1024, (nx, npl, mt, g)
+                assert g["nstages"] >= 3 and g["nstages"] <= 8
+                assert g["ksteps"] % g["kc"] == 0 and g["kc"] % 4 == 0
+                assert 2 * g["ksteps"] >= nx // 2                                  # kx = 0..kmax, two per k-step
+                assert g["chunk_bytes"] == g["kc"] * g["ntiles"] * 256
+                assert g["stack_bytes"] == g["npass"] * g["ksteps"] * g["ntiles"] * 256
+                assert g["smem_bytes"] == g["nstages"] * g["chunk_bytes"] + 128 + g["table_bytes"]
+                if g["twiddle_table"]:
+                    assert mt == 1 and g["table_bytes"] == g["ksteps"] * 32 * 8 * 8
+                    seen_on += 1
+                else:
+                    assert g["table_bytes"] == 0
+                    seen_off += 1
+    assert seen_on and seen_off
+    assert spectral_geometry(128, 3, 1)["twiddle_table"] == 1 and spectral_geometry(256, 3, 1)["twiddle_table"] == 1
+    assert spectral_geometry(512, 3, 1)["twiddle_table"] == 0
+    lib = S.load_library()
+    assert lib.swrt_spectral_geometry(7, 3, 1, (ctypes.c_int64 * 10)()) == -1
