@@ -1,7 +1,8 @@
 // lagrange_kernels.cu -- LAGRANGE6 mode of libswrt: the reference's own field evaluation, the
-// 6x6-point (Iord = 2) periodic Lagrange stencil of ray_trace_sw/interpolate.m:12-49, one thread
-// per packet, fused with the integrators that call it (ode_symplectic.m:33-37,
-// step_packet.m:37-78, step_packet_xka.m:38-91 + cg_sw.m:15-31).
+// 6x6-point (Iord = 2) periodic Lagrange stencil of ray_trace_sw/interpolate.m:12-49 (a quad of lanes
+// per packet in the eval / leapfrog kernels, one thread per packet in the RK4 ones), fused with the
+// integrators that call it (ode_symplectic.m:33-37, step_packet.m:37-78, step_packet_xka.m:38-91 +
+// cg_sw.m:15-31).
 //
 // Data layout: the gridded planes are node-interleaved, grid[(ix*nx + iy)*NPL + c], so the six
 // (seven) values of one stencil node are one contiguous 48 (56) byte record and one stencil row is a
