@@ -365,17 +365,28 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
     // (almost) never a stall.  No deadlock: the issue of chunk j happens before its warp waits on the
     // full barrier of chunk j - D, and only needs chunks < j - D, which were issued earlier.
     const int D = nstages - g.lag;
-    auto producer_issue = [&](long long j) {
-        const int st = (int)(j % nstages);
-        const long long it = j / nstages;
-        if (it > 0) mbar_wait(&empty_bar[st], (uint32_t)((it - 1) & 1));
-        mbar_expect_tx(&full_bar[st], chunk_bytes);
-        bulk_g2s(smem_raw + (size_t)st * chunk_bytes, a.stack + (size_t)(j % g.chunks_per_eval) * g.chunk_doubles,
-                 chunk_bytes, &full_bar[st]);
+    // This warp issues the chunks pj = warp, warp + 8, warp + 16, ...; the ring stage, the ring iteration and the source
+    // chunk of pj are carried incrementally (64-bit divisions by run-time values in the issue path cost the issuing
+    // warp ~700 cycles per turn, i.e. once per step at C2).
+    long long pj = warp;
+    int p_st = warp % nstages, p_src = warp % g.chunks_per_eval;
+    long long p_it = warp / nstages;
+    auto producer_issue = [&]() {          // lane 0 only; issues chunk pj
+        if (p_it > 0) mbar_wait(&empty_bar[p_st], (uint32_t)((p_it - 1) & 1));
+        mbar_expect_tx(&full_bar[p_st], chunk_bytes);
+        bulk_g2s(smem_raw + (size_t)p_st * chunk_bytes, a.stack + (size_t)p_src * g.chunk_doubles, chunk_bytes, &full_bar[p_st]);
     };
-    if (lane == 0) {
-        for (int j = 0; j < D && j < total_chunks; j++)
-            if (j % kConsumerWarps == warp) producer_issue(j);
+    auto producer_advance = [&]() {        // all lanes (uniform): pj += kConsumerWarps
+        pj += kConsumerWarps;
+        p_st += kConsumerWarps;
+        while (p_st >= nstages) { p_st -= nstages; p_it++; }
+        p_src += kConsumerWarps;
+        while (p_src >= g.chunks_per_eval) p_src -= g.chunks_per_eval;
+    };
+    static_assert(kConsumerWarps >= 8, "the prologue assumes at most one chunk per warp (D < kConsumerWarps)");
+    if (pj < D && pj < total_chunks) {
+        if (lane == 0) producer_issue();
+        producer_advance();
     }
 
     if (warp >= kConsumerWarps / 2 && g.desync_ns > 0 && kCtasPerSm == 1) {
@@ -508,8 +519,10 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                 for (int ch = 0; ch < chunks_per_pass; ch++) {
                     SWRT_TRACE_EV(0);
                     {   // producer duty for chunk ci + D (one warp in eight, lane 0 only)
-                        const long long j = ci + D;
-                        if (lane == 0 && j < total_chunks && (int)(j % kConsumerWarps) == warp) producer_issue(j);
+                        if (ci + D == pj && pj < total_chunks) {
+                            if (lane == 0) producer_issue();
+                            producer_advance();
+                        }
                     }
                     SWRT_TRACE_EV(1);
                     if (!ready) mbar_wait(&full_bar[stage], phase);
