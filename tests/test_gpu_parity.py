@@ -1050,6 +1050,35 @@ def test_lagrange_two_frame_sweep_equals_the_two_single_frame_gathers_bit_for_bi
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", [S.MODE_LAGRANGE6, S.MODE_SPECTRAL, S.MODE_NUFFT])
+def test_step_packet_xka_uniform_depth_zero_flow_closed_form_on_device(mode):
+    """the closed form of tests/test_oracle_kat.py (rest state over a uniform depth: straight rays at the group velocity,
+    k unchanged, wave action times the degree-4 Taylor polynomial of exp(-divC dt) per step) through swrt_step(RK4_XKA) in
+    every mode; the flow planes are zero and H-hat has only its (0,0) coefficient"""
+    nx = 32; L = 2 * np.pi; H0 = 1.3; gH = 0.81; f = 3.0; dt = 0.05; nsteps = 3
+    nkx, nky = nx - 1, nx // 2
+    planes = [np.zeros((nkx, nky), complex) for _ in range(7)]
+    planes[6][nkx // 2, 0] = H0                                       # (kx, ky) = (0, 0)
+    rs = np.random.RandomState(5)
+    n = 777
+    x = rs.uniform(-L / 2, L / 2, n); y = rs.uniform(-L / 2, L / 2, n)
+    k = rs.uniform(-3, 3, n); l = rs.uniform(-3, 3, n); a0 = rs.uniform(0.5, 2.0, n)
+    with S.Engine(nx, L, f, gH, mode) as e:
+        e.set_flow_planes_spectral(planes)
+        e.set_packets(x, y, k, l, a0)
+        e.step(S.SCHEME_RK4_XKA, dt, nsteps)
+        xo, yo, ko, lo, ao = e.get_packets(with_a=True)
+    g = gH * H0
+    om = np.sqrt(f ** 2 + g * (k ** 2 + l ** 2))
+    Cx, Cy = g * k / om, g * l / om
+    z = (Cx ** 2 + Cy ** 2) / om * dt
+    tol = 1e-12
+    assert np.abs(xo - (x + nsteps * dt * Cx)).max() < tol and np.abs(yo - (y + nsteps * dt * Cy)).max() < tol
+    assert np.abs(ko - k).max() < tol and np.abs(lo - l).max() < tol
+    assert np.abs(ao / a0 - (1 + z + z ** 2 / 2 + z ** 3 / 6 + z ** 4 / 24) ** nsteps).max() < tol
+
+
+@pytest.mark.gpu
 def test_ode23_in_lagrange_mode_is_bit_identical_to_the_restatement():
     """qgsw_raytrace.m:141-150 in LAGRANGE6 mode: interpolate_U (both frames, blended results), odefun and the
     Bogacki-Shampine stages (y + f*hB, the error estimate f*E) are all executed without fused multiply-adds in the

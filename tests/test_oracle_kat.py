@@ -281,3 +281,29 @@ def test_interpolate_is_degree5_tensor_lagrange_interpolation_independent_check(
     w = O._lagrange_weights(np.array([0.3]), 0.0)[:, 0]
     basis = np.array([lagrange(nodes, np.eye(6)[i])(0.3) for i in range(6)])
     assert np.allclose(w, -basis, atol=1e-14) and abs(w.sum() + 1.0) < 1e-14
+
+
+def test_step_packet_xka_uniform_depth_zero_flow_closed_form():
+    """step_packet_xka.m:38-91 + cg_sw.m:15-31 at rest over a uniform depth H0: the group velocity C = C0^2 H0 k/omega is
+    constant, so RK4 in x is exact (x += dt*C), grad(omega) = 0 leaves k unchanged, and div C = -(Cx^2 + Cy^2)/omega is a
+    constant z/dt, so the RK4 of da/dt = -a divC multiplies a by the degree-4 Taylor polynomial of exp(-divC dt)"""
+    nx = 16; L = 2 * np.pi; dx = L / nx
+    zero = np.zeros((nx, nx)); H0 = 1.3
+    U = {"u": zero, "v": zero}; G = {"u_x": zero, "u_y": zero, "v_x": zero, "v_y": zero}
+    H = np.full((nx, nx), H0)
+    C0, f, dt = 0.9, 3.0, 0.07
+    P = {"x": 0.4, "y": -2.0, "k": 2.5, "l": -1.25, "a": 0.8}
+    out = O.step_packet_xka(P, U, G, H, C0, f, dx, dx, dt)
+    gH = C0 ** 2 * H0
+    om = np.sqrt(f ** 2 + gH * (P["k"] ** 2 + P["l"] ** 2))
+    Cx, Cy = gH * P["k"] / om, gH * P["l"] / om
+    z = (Cx ** 2 + Cy ** 2) / om * dt                       # -divC*dt
+    assert abs(out["x"] - (P["x"] + dt * Cx)) < 1e-13 and abs(out["y"] - (P["y"] + dt * Cy)) < 1e-13
+    assert out["k"] == P["k"] and out["l"] == P["l"]
+    assert abs(out["a"] - P["a"] * (1 + z + z ** 2 / 2 + z ** 3 / 6 + z ** 4 / 24)) < 1e-14
+    # and the batch restatement the GPU tests use agrees
+    arr = lambda v: np.array([v])
+    fields = {"u": zero, "v": zero, "u_x": zero, "u_y": zero, "v_x": zero, "v_y": zero, "H": H}
+    bat = O.rk4_step_batch(arr(P["x"]), arr(P["y"]), arr(P["k"]), arr(P["l"]), arr(P["a"]), dt, C0, f, fields, dx, True)
+    for i, name in enumerate(["x", "y", "k", "l", "a"]):
+        assert abs(out[name] - bat[i][0]) < 1e-14
