@@ -177,3 +177,31 @@ def test_cg_sw_mirror_matches_restatement():
     assert np.array_equal(divC, d0) and np.array_equal(grad["x"], gx) and np.array_equal(grad["y"], gy)
     C, om, _, divC, grad = R.cg_sw(1.5, -2.0, 1.2, 3.0)
     assert divC is None and grad is None and om == np.sqrt(9 + 1.44 * 6.25)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference (the CPU arm the driver times beside the GPU arm): exactly one JSON line on stdout with
+    the contract's keys, zero GPU launches, the oracle port as `kind`, every host core as `cores` -- also when
+    OMP_NUM_THREADS=1 is exported the way torchrun does for its ranks (TORCHELASTIC_RUN_ID present)"""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1", TORCHELASTIC_RUN_ID="test", SWRT_BENCH_TARGET_S="0.3")
+    env.pop("RANK", None)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--packets", "2048"], capture_output=True, text=True, env=env, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "scaling", "dtype", "data",
+                "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    ncores = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == ncores
+    # other ranks of a torchrun launch print nothing and exit 0
+    out2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, env=dict(env, RANK="1"), timeout=120, cwd=root)
+    assert out2.returncode == 0 and out2.stdout.strip() == ""
