@@ -100,6 +100,16 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
+        note = None
+        if not self.rows:
+            # the timed regions were shorter than nvidia-smi's start-up + sampling period: one sample right after them
+            try:
+                one = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+                self.rows = [[c.strip() for c in one[0].split(",")]] if one else []
+                note = "timed regions shorter than the sampling period: one sample taken right after them"
+            except Exception:
+                pass
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
@@ -108,7 +118,10 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -487,9 +500,10 @@ def main():
 
     cpu = cpu_spec = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and w.scheme == "leapfrog":
-        v, cores, sample = cpu_reference_rate(w)
+        hook = os.environ.get("SWRT_BENCH_TARGET_S")             # test hook: a shorter CPU sample
+        v, cores, sample = cpu_reference_rate(w, **({"target_s": float(hook)} if hook else {}))
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        v2, cores2, sample2 = cpu_spectral_rate(w)
+        v2, cores2, sample2 = cpu_spectral_rate(w, **({"target_s": float(hook)} if hook else {}))
         cpu_spec = {"value": v2, "unit": UNIT, "cores": cores2, "kind": "port", "sample": sample2}
 
     if rank == 0:

@@ -1217,3 +1217,33 @@ def test_randomised_schemes_two_frames_awkward_sizes():
         for _ in range(2):
             st_ = O.rk4_step_batch(*st_, dt, 1.0, F0, fields, dx, True)
         assert np.abs(got - np.stack(st_)).max() < TOL_TRAJ, (nx, n)
+
+
+@pytest.mark.gpu
+def test_bench_gpu_arm_prints_one_contract_line():
+    """python bench.py (the GPU arm, N = 1) on a small ensemble: exactly one JSON line on stdout carrying the contract's
+    keys -- value / e2e with host<->device bytes, gpu_launches > 0, roofline of the dominant kernel (tensor bound, fraction
+    in (0, 1]), cpu_baseline measured beside it, sampled clocks -- and the side legs of the other two modes"""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SWRT_BENCH_TARGET_S="0.3")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--packets", "9472"],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "f64" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["gpu_launches"] >= 3 * 3
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 4 * 8 * 9472 == d["e2e"]["d2h_bytes_per_step"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0.0 < r["frac"] <= 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    assert d["clocks"]["sm_max_mhz"] > 0
+    assert d["lagrange6"]["value"] > 0 and d["nufft"]["value"] > 0
+    assert d["histogram_total"] <= 9472
