@@ -12,8 +12,13 @@
  *     non-interleaved);
  *   - every function returns 0 on success, <0 on error; swrt_last_error() gives the message;
  *     nothing throws or longjmps; no caller pointer is kept after return;
- *   - one host thread drives a handle; a handle owns one CUDA device and the device-resident
- *     SoA packet state (x,y,k,l,a) plus the flow-coefficient stacks;
+ *   - one host thread drives a handle; a handle owns swrt_params.ngpu CUDA devices (default 1) and the
+ *     device-resident SoA packet state (x,y,k,l,a) plus the flow-coefficient stacks.  With ngpu > 1 the
+ *     packets are sharded in contiguous index ranges over the devices device .. device+ngpu-1, the flow
+ *     is replicated on each, every call below keeps its meaning for the WHOLE ensemble, and the only
+ *     exchanges are NCCL all-reduces (single-process ncclCommInitAll communicator) of the u64 histogram
+ *     counts, the diagnostic scalars and the ode23 error norm.  The caller is one MATLAB / Octave /
+ *     Python process (qgsw_raytrace.m:121-150 runs the whole loop in one interpreter);
  *   - there is NO CPU fallback: without a CUDA device every call fails with SWRT_ERR_CUDA.
  */
 #ifndef SWRT_H
@@ -25,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SWRT_VERSION 100
+#define SWRT_VERSION 200
 
 /* error codes */
 #define SWRT_OK            0
@@ -70,6 +75,8 @@ typedef struct swrt_params {
     double  f;         /* Coriolis parameter                                                    */
     double  gH;        /* Cg^2 = C0^2 (ode_symplectic.m:10-11)                                  */
     double  bump;      /* Lagrange "bump": 1e-13 (interpolate.m:13) or 1e-10 (interpolate_par)  */
+    int32_t ngpu;      /* devices device .. device+ngpu-1 share the packets (0 or 1 = one device)  */
+    int32_t reserved;  /* must be 0                                                             */
 } swrt_params;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
@@ -101,6 +108,9 @@ int swrt_set_packets(swrt_handle* h, int64_t n, const double* x, const double* y
 int swrt_get_packets(swrt_handle* h, double* x, double* y, double* k, double* l,
                      double* a /* may be NULL */);
 int64_t swrt_num_packets(const swrt_handle* h);
+/* devices behind the handle, and shard i's device ordinal and packet range [lo, lo+n) (any pointer may be NULL) */
+int swrt_num_devices(const swrt_handle* h);
+int swrt_shard_info(const swrt_handle* h, int i, int* device, int64_t* lo, int64_t* n);
 /* device-resident SoA buffers (for callers that already live on the GPU, e.g. torch) */
 int swrt_packets_alloc_dev(swrt_handle* h, int64_t n);
 int swrt_packets_dev(swrt_handle* h, double** x, double** y, double** k, double** l, double** a);
@@ -126,6 +136,16 @@ int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, 
 /* the same launches without the host wait (swrt_step returns when the kernels are done; this returns when they are
  * queued): host work of the previous diagnostic interval overlaps the kernel.  swrt_synchronize completes it.   */
 int swrt_step_async(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha);
+/* The reference's integrators take HOST arrays and return HOST arrays (ode_symplectic.m:1-4: x0,k0 in, x,k out;
+ * step_packet.m:1 / step_packet_xka.m:1: P in, Pout out).  swrt_step_host is that call shape in one entry point:
+ * swrt_set_packets(n, x,y,k,l,a) + swrt_step(scheme, dt, nsteps, alpha0, dalpha) + swrt_get_packets(xo,yo,ko,lo,ao),
+ * with identical results, but pipelined over packet chunks: the buffers may be ordinary pageable memory, they are
+ * staged through an internal pinned ring by helper threads, and chunk i computes while chunk i+1 uploads and chunk
+ * i-1 downloads.  Output pointers may alias the inputs; a / ao may be NULL (a = 1).  The device keeps the final
+ * packets, as after swrt_set_packets + swrt_step.                                                            */
+int swrt_step_host(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha, int64_t n,
+                   const double* x, const double* y, const double* k, const double* l, const double* a,
+                   double* xo, double* yo, double* ko, double* lo, double* ao);
 
 /* ---- ode23 (Bogacki-Shampine 3(2), MATLAB builtin called by qgsw_raytrace.m:149 and
  * qg2layersw_raytrace.m:195 on y = [x;y;k;l]) -- device building blocks.  The HOST owns the step-size

@@ -88,6 +88,22 @@ def leapfrog_lagrange(x, y, k, l, grids, dx, f, gH, dt, nsteps, bump=1e-13):
     return x, y, k, l
 
 
+def leapfrog_lagrange2(x, y, k, l, grids1, grids2, dx, f, gH, dt, nsteps, alpha0, dalpha, bump=1e-13, prepared=None):
+    """two-frame leapfrog (interpolate_U.m blend per plane, alpha_j = alpha0 + j*dalpha); ``prepared`` = the
+    column-major copies a previous call returned (so a timing loop does not re-copy 12 planes per call)"""
+    x, y, k, l = (_f(a).copy() for a in (x, y, k, l))
+    nx = np.asarray(grids1[0]).shape[0]
+    g1, g2 = prepared if prepared is not None else ([_cm(g) for g in grids1[:6]], [_cm(g) for g in grids2[:6]])
+    lib().orc_leapfrog_lagrange2(_p(x), _p(y), _p(k), _p(l), C.c_int64(x.size), _table(g1), _table(g2), C.c_int(nx), C.c_double(dx),
+                                 C.c_double(bump), C.c_double(f), C.c_double(gH), C.c_double(dt), C.c_int(nsteps),
+                                 C.c_double(alpha0), C.c_double(dalpha))
+    return x, y, k, l
+
+
+def prepare_grids(grids):
+    return [_cm(g) for g in grids[:6]]
+
+
 def _planes(planes_k):
     res = [_cm(np.asarray(p).real) for p in planes_k]
     ims = [_cm(np.asarray(p).imag) for p in planes_k]

@@ -137,6 +137,38 @@ void orc_leapfrog_lagrange(double* x, double* y, double* k, double* l, int64_t n
     }
 }
 
+/* The same leapfrog on a TIME-DEPENDENT flow: two stored frames, every plane interpolated in BOTH and blended
+ * (1-alpha)*F1 + alpha*F2 exactly as qg_flow_ray_trace/interpolate_U.m:5-23 does; sub-step j evaluates at
+ * alpha_j = alpha0 + j*dalpha (the time-centred choice of SURVEY 7.0; the production drivers pass t/tmax, qgsw_raytrace.m:261). */
+void orc_leapfrog_lagrange2(double* x, double* y, double* k, double* l, int64_t n, const double* const* g1,
+                            const double* const* g2, int nx, double dx, double bump, double f, double gH, double dt,
+                            int nsteps, double alpha0, double dalpha) {
+    const double h = dt / 2, f2 = f * f;
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < n; m++) {
+        double px = x[m], py = y[m], pk = k[m], pl = l[m];
+        for (int st = 0; st < nsteps; st++) {
+            const double al = alpha0 + (double)st * dalpha;
+            double om = sqrt(f2 + gH * (pk * pk + pl * pl));
+            px = px + h * (gH * pk / om);
+            py = py + h * (gH * pl / om);
+            stencil_t s;
+            make_stencil(px, py, dx, dx, nx, nx, bump, &s);
+            double F[6];
+            for (int c = 0; c < 6; c++) F[c] = (1.0 - al) * stencil_sum(&s, g1[c], nx) + al * stencil_sum(&s, g2[c], nx);
+            px = px + dt * F[0];
+            py = py + dt * F[1];
+            double k0 = pk, l0 = pl;
+            pk = k0 - dt * (F[2] * k0 + F[4] * l0);
+            pl = l0 - dt * (F[3] * k0 + F[5] * l0);
+            om = sqrt(f2 + gH * (pk * pk + pl * pl));
+            px = px + h * (gH * pk / om);
+            py = py + h * (gH * pl / om);
+        }
+        x[m] = px; y[m] = py; k[m] = pk; l[m] = pl;
+    }
+}
+
 /* ---- exact trig-sum evaluation (SPECTRAL mode oracle; pattern scratch/fourier_interpolate_test.m:125-136)
  *   F = sum_kx Fs(kx,0) e^{i kx tx} + 2 Re sum_{ky>=1} sum_kx F(kx,ky) e^{i(kx tx + ky ty)},
  *   tx = 2 pi mod(x/dx, nx)/nx.  The ky=0 column is conjugate-symmetrised (fulspec.m:16).

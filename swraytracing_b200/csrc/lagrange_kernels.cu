@@ -251,11 +251,12 @@ __global__ void __launch_bounds__(128, TWO ? SWRT_LAG_TWO_MINB : SWRT_LAG_MINB) 
         double F0, F1;
         if constexpr (TWO) {
             double G0, G1;
+            const double al = a.alpha + (double)(a.j0 + st) * a.dalpha;     // the host's alpha0 + j*dalpha, same doubles
             gather_pair2<NPL>(a.grid, a.grid2, a.nx, s, q, F0, F1, G0, G1);
-            F0 = (1.0 - a.alpha) * F0 + a.alpha * G0;
-            F1 = (1.0 - a.alpha) * F1 + a.alpha * G1;
+            F0 = (1.0 - al) * F0 + al * G0;
+            F1 = (1.0 - al) * F1 + al * G1;
         } else {
-            gather_pair<NPL>(a.grid, a.nx, s, q, F0, F1);
+            gather_pair<NPL>(a.grid + (size_t)st * a.gstride, a.nx, s, q, F0, F1);
         }
         // every lane needs all six planes for the kick: lane 0 holds (u,v), lane 1 (ux,uy), lane 2 (vx,vy)
         double F[6];
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(128) lagrange_rk4_kernel(const LagArgs a) {
     double amp = XKA ? a.a[p] : 0.0;
     const double f = a.f, f2 = f * f, C02 = a.C0 * a.C0, dt = a.dt;
     for (int st = 0; st < a.nsteps; st++) {
+        const double* __restrict__ grid = a.grid + (size_t)st * a.gstride;    // fused run on pre-blended frames
         const double K2 = k * k + l * l;
         double Cx = 0.0, Cy = 0.0;
         if (!XKA) {   // cg_sw.m:19-26 with scalar gH
@@ -326,19 +328,19 @@ __global__ void __launch_bounds__(128) lagrange_rk4_kernel(const LagArgs a) {
         double g[4] = {0, 0, 0, 0};
         if (!XKA) {
             double F[NPL];
-            gather_planes<NPL>(a.grid, a.nx, s, F);
+            gather_planes<NPL>(grid, a.nx, s, F);
             g[0] = F[2]; g[1] = F[3]; g[2] = F[4]; g[3] = F[5];
         }
-        velocity_stage<NPL, XKA>(a.grid, a.nx, s, k, l, K2, C02, f2, Cx, Cy, vx, vy);
+        velocity_stage<NPL, XKA>(grid, a.nx, s, k, l, K2, C02, f2, Cx, Cy, vx, vy);
         const double x1 = dt * vx, y1 = dt * vy;
         make_stencil(x + x1 / 2, y + y1 / 2, a.dx, a.dx, a.nx, a.nx, a.bump, s);
-        velocity_stage<NPL, XKA>(a.grid, a.nx, s, k, l, K2, C02, f2, Cx, Cy, vx, vy);
+        velocity_stage<NPL, XKA>(grid, a.nx, s, k, l, K2, C02, f2, Cx, Cy, vx, vy);
         const double x2 = dt * vx, y2 = dt * vy;
         make_stencil(x + x2 / 2, y + y2 / 2, a.dx, a.dx, a.nx, a.nx, a.bump, s);
-        velocity_stage<NPL, XKA>(a.grid, a.nx, s, k, l, K2, C02, f2, Cx, Cy, vx, vy);
+        velocity_stage<NPL, XKA>(grid, a.nx, s, k, l, K2, C02, f2, Cx, Cy, vx, vy);
         const double x3 = dt * vx, y3 = dt * vy;
         make_stencil(x + x3, y + y3, a.dx, a.dx, a.nx, a.nx, a.bump, s);
-        velocity_stage<NPL, XKA>(a.grid, a.nx, s, k, l, K2, C02, f2, Cx, Cy, vx, vy);
+        velocity_stage<NPL, XKA>(grid, a.nx, s, k, l, K2, C02, f2, Cx, Cy, vx, vy);
         const double x4 = dt * vx, y4 = dt * vy;
         const double xn = x + (x1 + 2 * x2 + 2 * x3 + x4) / 6;
         const double yn = y + (y1 + 2 * y2 + 2 * y3 + y4) / 6;
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(128) lagrange_rk4_kernel(const LagArgs a) {
             make_stencil(xn, yn, a.dx, a.dx, a.nx, a.nx, a.bump, s);
 #pragma unroll
             for (int i = 0; i < NW; i++) {
-                const double* row = a.grid + (size_t)s.ig[i] * a.nx * NPL;
+                const double* row = grid + (size_t)s.ig[i] * a.nx * NPL;
 #pragma unroll
                 for (int j = 0; j < NW; j++) {
                     const double w = s.wx[i] * s.wy[j];

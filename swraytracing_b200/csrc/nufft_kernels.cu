@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_MINB) nufft_leapfrog_kernel
         x = x + h * (a.gH * k / om);
         y = y + h * (a.gH * l / om);
         double F[6];
-        nufft_eval6<false>(a.grid, nullptr, a.nf, a.beta, a.dscale, reduced_coord(x, a.dx, a.nxd), reduced_coord(y, a.dx, a.nxd), q, qb, F);
+        nufft_eval6<false>(a.grid + (size_t)st * a.gstride, nullptr, a.nf, a.beta, a.dscale, reduced_coord(x, a.dx, a.nxd), reduced_coord(y, a.dx, a.nxd), q, qb, F);
         x = x + a.dt * F[0];
         y = y + a.dt * F[1];
         const double k0 = k, l0 = l;
@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_RK4_MINB) nufft_rk4_kernel(
     double am = XKA ? a.a[pc] : 0.0;
     const double dt = a.dt;
     for (int st = 0; st < a.nsteps; st++) {
+        const double2* __restrict__ grid = a.grid + (size_t)st * a.gstride;      // fused run on pre-blended frames
+        const double* __restrict__ hgrid = XKA ? a.hgrid + (size_t)st * a.hstride : nullptr;
         const double K2 = k * k + l * l;
         double F[7];
         double gux = 0, guy = 0, gvx = 0, gvy = 0;       // step_packet: gradients at the old position
@@ -210,10 +212,10 @@ __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_RK4_MINB) nufft_rk4_kernel(
         for (int stage = 0; stage < 4; stage++) {
             const double xl = reduced_coord(xs, a.dx, a.nxd), yl = reduced_coord(ys, a.dx, a.nxd);
             if (!XKA && stage == 0) {
-                nufft_eval6<false, true>(a.grid, nullptr, a.nf, a.beta, a.dscale, xl, yl, q, qb, F);
+                nufft_eval6<false, true>(grid, nullptr, a.nf, a.beta, a.dscale, xl, yl, q, qb, F);
                 gux = F[2]; guy = F[3]; gvx = F[4]; gvy = F[5];
             } else {
-                nufft_eval6<XKA, false>(a.grid, a.hgrid, a.nf, a.beta, a.dscale, xl, yl, q, qb, F);
+                nufft_eval6<XKA, false>(grid, hgrid, a.nf, a.beta, a.dscale, xl, yl, q, qb, F);
             }
             const double gH = XKA ? a.C0 * a.C0 * F[6] : a.C0 * a.C0;
             const double om = sqrt(a.f * a.f + gH * K2);
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kBlock, SWRT_NUFFT_RK4_MINB) nufft_rk4_kernel(
         }
         double oxi = 0.0, oyi = 0.0, dci = 0.0;
         if constexpr (XKA) {
-            nufft_eval6<true, true>(a.grid, a.hgrid, a.nf, a.beta, a.dscale, reduced_coord(xs, a.dx, a.nxd),
+            nufft_eval6<true, true>(grid, hgrid, a.nf, a.beta, a.dscale, reduced_coord(xs, a.dx, a.nxd),
                                     reduced_coord(ys, a.dx, a.nxd), q, qb, F);
             gux = F[2]; guy = F[3]; gvx = F[4]; gvy = F[5];
             const double gH = a.C0 * a.C0 * F[6];

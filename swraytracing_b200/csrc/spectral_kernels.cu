@@ -227,11 +227,34 @@ void launch_psi_to_planes(const double2* psik, double2* const* planes, int nkx, 
 
 // out = wa*a + wb*b : the on-device frame blend of interpolate_U.m:19-23 applied to the
 // coefficient stack (linear, so identical to blending the evaluated fields).
+// (the expression is pinned -- one rounded product, one fma -- so that the single blend and the multi-blend kernel below
+// produce the same doubles: a fused run of m time-dependent steps equals m single-step launches bit for bit)
 __global__ void axpby_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b,
                              double wa, double wb, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = wa * a[i] + wb * b[i];
+    for (; i < n; i += stride) out[i] = fma(wa, a[i], __dmul_rn(wb, b[i]));
+}
+// out[j][i] = (1 - al_j)*a[i] + al_j*b[i] for the m steps of a fused run, al_j = alpha0 + (j0 + j)*dalpha (the host's
+// expression for step j0 + j of swrt_step): every operand is read once for all m blends
+__global__ void axpby_multi_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b,
+                                   double alpha0, double dalpha, int j0, int m, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double av = a[i], bv = b[i];
+        for (int j = 0; j < m; j++) {
+            const double al = alpha0 + (double)(j0 + j) * dalpha;
+            out[(size_t)j * n + i] = fma(1.0 - al, av, __dmul_rn(al, bv));
+        }
+    }
+}
+void launch_axpby_multi(double* out, const double* a, const double* b, double alpha0, double dalpha, int j0, int m, size_t n,
+                        cudaStream_t st) {
+    int bs = 256;
+    size_t nb = (n + bs - 1) / bs;
+    if (nb > 148 * 16) nb = 148 * 16;
+    axpby_multi_kernel<<<(unsigned)nb, bs, 0, st>>>(out, a, b, alpha0, dalpha, j0, m, n);
 }
 void launch_axpby(double* out, const double* a, const double* b, double wa, double wb, size_t n, cudaStream_t st) {
     int bs = 256;
@@ -368,8 +391,11 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
     // This warp issues the chunks pj = warp, warp + 8, warp + 16, ...; the ring stage, the ring iteration and the source
     // chunk of pj are carried incrementally (64-bit divisions by run-time values in the issue path cost the issuing
     // warp ~700 cycles per turn, i.e. once per step at C2).
+    // a fused run on a time-dependent flow reads one pre-blended stack per step: the nstack stacks are contiguous, so the
+    // source chunk index simply wraps after chunks_per_eval * nstack (every tile walks its evaluations 0..nevals-1 in order)
+    const int src_period = g.chunks_per_eval * ((MODE == SPEC_LEAPFROG && a.nstack > 1) ? a.nstack : 1);
     long long pj = warp;
-    int p_st = warp % nstages, p_src = warp % g.chunks_per_eval;
+    int p_st = warp % nstages, p_src = warp % src_period;
     long long p_it = warp / nstages;
     auto producer_issue = [&]() {          // lane 0 only; issues chunk pj
         if (p_it > 0) mbar_wait(&empty_bar[p_st], (uint32_t)((p_it - 1) & 1));
@@ -381,7 +407,7 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
         p_st += kConsumerWarps;
         while (p_st >= nstages) { p_st -= nstages; p_it++; }
         p_src += kConsumerWarps;
-        while (p_src >= g.chunks_per_eval) p_src -= g.chunks_per_eval;
+        while (p_src >= src_period) p_src -= src_period;
     };
     static_assert(kConsumerWarps >= 8, "the prologue assumes at most one chunk per warp (D < kConsumerWarps)");
     if (pj < D && pj < total_chunks) {
@@ -608,7 +634,10 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                 }
                 if constexpr (PSI) {
                     const double kap = a.kappa, kap2 = a.kappa * a.kappa;
-                    F[mt][0] = fma(kap, F[mt][0], a.u_mean);
+                    // mean shear of the blended frame (grid_U.m:11; interpolate_U.m:19-23), every rounding pinned
+                    const double al = __dadd_rn(a.alpha0, __dmul_rn((double)(a.j0 + ev), a.dalpha));
+                    const double um = __dadd_rn(__dmul_rn(__dsub_rn(1.0, al), a.u_mean0), __dmul_rn(al, a.u_mean1));
+                    F[mt][0] = fma(kap, F[mt][0], um);
                     F[mt][1] = kap * F[mt][1];
                     F[mt][2] = kap2 * F[mt][2];
                     F[mt][3] = kap2 * F[mt][3];

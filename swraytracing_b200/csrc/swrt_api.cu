@@ -4,11 +4,18 @@
 #include "swrt_internal.h"
 
 #include <cufft.h>
+#include <nccl.h>          // types only: the library itself is dlopen()ed when a multi-device handle is created
+#include <dlfcn.h>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace swrt;
@@ -86,6 +93,18 @@ struct swrt_handle {
     bool timing_valid = false;
     int last_nlaunch = 0;
     int mtiles = 0;
+    // fused runs on a time-dependent flow: the operands (packed stacks / fine grids / Lagrange grids) of up to
+    // kMaxFusedBlend steps, pre-blended at alpha_j and stored back to back
+    double* arena = nullptr; size_t arena_cap = 0;
+    double* arena_h = nullptr; size_t arena_h_cap = 0;      // NUFFT (u,v,H,0) grids
+    // host staging of swrt_step_host / swrt_set_packets / swrt_get_packets (pinned ring + copy streams)
+    struct Stager* stager = nullptr;
+    // multi-device handle (swrt_params.ngpu > 1): one single-device child per GPU, contiguous packet shards
+    int ngpu = 1;
+    std::vector<swrt_handle*> shard;
+    std::vector<int64_t> off;             // shard i holds packets [off[i], off[i+1])
+    std::vector<ncclComm_t> comms;
+    double* red_dev = nullptr;            // child: 3 x 8 doubles for the diagnostic all-reduces
 };
 
 namespace {
@@ -95,6 +114,39 @@ int fail(swrt_handle* h, int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
     if (h) h->err = buf; else g_create_error = buf;
     return code;
+}
+
+// multi-device handles (ngpu > 1) are served by the grp_* layer at the end of this file
+#define GROUP(h, call) do { if ((h)->ngpu > 1) return call; } while (0)
+int grp_create(const swrt_params* p, swrt_handle** out);
+int grp_destroy(swrt_handle* g);
+int grp_sync(swrt_handle* g);
+int grp_set_packets(swrt_handle* g, int64_t n, const double* x, const double* y, const double* k, const double* l, const double* a);
+int grp_get_packets(swrt_handle* g, double* x, double* y, double* k, double* l, double* a);
+int grp_step_host(swrt_handle* g, int scheme, double dt, int nsteps, double alpha0, double dalpha, int64_t n,
+                  const double* const in[5], double* const out[5]);
+int grp_step(swrt_handle* g, int scheme, double dt, int nsteps, double alpha0, double dalpha, bool sync);
+int grp_hist_omega(swrt_handle* g, int kind, double alpha, const double* edges, int nedges, uint64_t* counts, int accumulate);
+int grp_hist_omega_dev(swrt_handle* g, int kind, double alpha, const double* edges, int nedges, uint64_t** counts_dev, bool wait);
+int grp_diag(swrt_handle* g, double alpha, double out[8]);
+int grp_bs23_begin(swrt_handle* g, double alpha, double threshold, double* rh_norm);
+int grp_bs23_attempt(swrt_handle* g, double hstep, const double alpha[3], double threshold, double* err_norm);
+int grp_ideal_omega_hist(swrt_handle* g, double alpha, int64_t npts, const double* x, const double* y, const double* kvx,
+                         const double* kvy, int nangles, double omega0, const double* edges, int nedges, uint64_t* counts);
+int up(swrt_handle* g, swrt_handle* c, int rc);
+inline double* at(double* p, int64_t lo) { return p ? p + lo : nullptr; }
+void stager_free(swrt_handle* h);
+// calls whose per-packet outputs are host arrays: each shard writes its slice (devices one after another; these are the
+// inspection entry points, not the stepping path)
+template <typename F>
+int grp_each_slice(swrt_handle* g, F f) {
+    for (size_t i = 0; i < g->shard.size(); i++) {
+        swrt_handle* c = g->shard[i];
+        if (g->off[i + 1] == g->off[i]) continue;
+        int rc = f(c, g->off[i]);
+        if (rc != SWRT_OK) return up(g, c, rc);
+    }
+    return SWRT_OK;
 }
 
 #define CU(h, expr)                                                                                   \
@@ -232,7 +284,9 @@ bool use_psi(const swrt_handle* h, double alpha) {
 void fill_psi_args(const swrt_handle* h, double alpha, SpecArgs& a) {
     a.psi = true;
     a.kappa = 2.0 * M_PI / h->p.L;
-    a.u_mean = alpha == 0.0 ? h->u_mean[0] : (1.0 - alpha) * h->u_mean[0] + alpha * h->u_mean[1];
+    // the kernel forms (1-alpha)*u_mean0 + alpha*u_mean1 itself (pinned roundings; alpha = 0 gives u_mean0 exactly)
+    a.u_mean0 = h->u_mean[0]; a.u_mean1 = h->slot_set[1] ? h->u_mean[1] : 0.0;
+    a.alpha0 = alpha; a.dalpha = 0.0; a.j0 = 0;
 }
 
 int active_nufft_grid(swrt_handle* h, double alpha, const double** out, const double** hout);
@@ -516,7 +570,10 @@ int grid_from_planes(swrt_handle* h, int slot) {
         if (rc) return rc;
         h->launches += 3;
     }
-    if (h->grid_npl != npl) { dfree(h->grid[0]); dfree(h->grid[1]); dfree(h->grid_blend); h->grid_npl = npl; }
+    if (h->grid_npl != npl) {      // the plane count changed: the other slot's grid no longer matches and must be set again
+        dfree(h->grid[0]); dfree(h->grid[1]); dfree(h->grid_blend); h->grid_npl = npl;
+        h->slot_set[1 - slot] = false;
+    }
     if (!h->grid[slot]) CU(h, cudaMalloc(&h->grid[slot], n * npl * sizeof(double)));
     launch_interleave_grid(tmp.data(), npl, nx, h->grid[slot], h->stream);
     h->launches++;
@@ -548,6 +605,8 @@ int swrt_create(const swrt_params* p, swrt_handle** out) {
     if (!(p->L > 0)) return fail(nullptr, SWRT_ERR_ARG, "swrt_create: L must be positive");
     if (p->mode != SWRT_MODE_SPECTRAL && p->mode != SWRT_MODE_LAGRANGE6 && p->mode != SWRT_MODE_NUFFT)
         return fail(nullptr, SWRT_ERR_ARG, "swrt_create: unknown mode %d", p->mode);
+    if (p->ngpu < 0 || p->ngpu > 64) return fail(nullptr, SWRT_ERR_ARG, "swrt_create: ngpu = %d out of range", p->ngpu);
+    if (p->ngpu > 1) return grp_create(p, out);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -562,7 +621,11 @@ int swrt_create(const swrt_params* p, swrt_handle** out) {
     h->p = *p;
     if (!(h->p.bump > 0)) h->p.bump = 1e-13;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: cudaGetDeviceProperties failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    h->num_sms = prop.multiProcessorCount;
     if (prop.major < 10) {
         delete h;
         return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: device is sm_%d%d; libswrt is built for sm_100a only", prop.major, prop.minor);
@@ -581,8 +644,11 @@ int swrt_create(const swrt_params* p, swrt_handle** out) {
 
 int swrt_destroy(swrt_handle* h) {
     if (!h) return SWRT_OK;
+    if (h->ngpu > 1) return grp_destroy(h);
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    stager_free(h);
+    dfree(h->arena); dfree(h->arena_h); dfree(h->red_dev);
     dfree(h->x); dfree(h->y); dfree(h->k); dfree(h->l); dfree(h->a);
     for (int s = 0; s < 2; s++) {
         for (auto& p : h->planes[s]) dfree(p);
@@ -648,9 +714,36 @@ static int set_flow_spectral_dev(swrt_handle* h, int slot, const double2* psi, d
     return rc;
 }
 
+// multi-device handle, psi-hat already on the first device (the QG producers): the first shard takes it in place, the
+// others receive a peer copy (a frame is <= 2 MB: setup traffic, once per flow step)
+static int grp_flow_from_psi_dev(swrt_handle* g, int slot, const double2* psi_dev0, double u_mean) {
+    const size_t n = (size_t)(g->p.nx - 1) * (g->p.nx / 2);
+    for (size_t i = 0; i < g->shard.size(); i++) {
+        swrt_handle* c = g->shard[i];
+        CU(g, cudaSetDevice(c->p.device));
+        int rc;
+        if (i == 0) rc = set_flow_spectral_dev(c, slot, psi_dev0, u_mean);
+        else {
+            DevTmp<double2> tmp;
+            CU(g, tmp.alloc(n));
+            CU(g, cudaMemcpyPeer(tmp.p, c->p.device, psi_dev0, g->shard[0]->p.device, n * sizeof(double2)));
+            rc = set_flow_spectral_dev(c, slot, tmp.p, u_mean);
+            cudaStreamSynchronize(c->stream);
+        }
+        if (rc) return up(g, c, rc);
+    }
+    g->slot_set[slot] = true;
+    return SWRT_OK;
+}
+
 int swrt_set_flow_spectral(swrt_handle* h, int slot, const double* psik_re, const double* psik_im, int nkx, int nky,
                            double u_mean) {
     if (!h) return SWRT_ERR_ARG;
+    if (h->ngpu > 1) {
+        for (swrt_handle* c : h->shard) { int rc = swrt_set_flow_spectral(c, slot, psik_re, psik_im, nkx, nky, u_mean); if (rc) return up(h, c, rc); }
+        h->slot_set[slot] = true;
+        return SWRT_OK;
+    }
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
     REQUIRE(h, psik_re && psik_im, SWRT_ERR_ARG, "null psi-hat pointer");
@@ -669,6 +762,11 @@ int swrt_set_flow_spectral(swrt_handle* h, int slot, const double* psik_re, cons
 int swrt_set_flow_planes_spectral(swrt_handle* h, int slot, const double* const* planes_re,
                                   const double* const* planes_im, int nplanes, int nkx, int nky) {
     if (!h) return SWRT_ERR_ARG;
+    if (h->ngpu > 1) {
+        for (swrt_handle* c : h->shard) { int rc = swrt_set_flow_planes_spectral(c, slot, planes_re, planes_im, nplanes, nkx, nky); if (rc) return up(h, c, rc); }
+        h->slot_set[slot] = true;
+        return SWRT_OK;
+    }
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
     REQUIRE(h, nplanes == 6 || nplanes == 7, SWRT_ERR_ARG, "nplanes must be 6 or 7");
@@ -691,6 +789,11 @@ int swrt_set_flow_planes_spectral(swrt_handle* h, int slot, const double* const*
 int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* v, const double* ux, const double* uy,
                        const double* vx, const double* vy, const double* H, int nx) {
     if (!h) return SWRT_ERR_ARG;
+    if (h->ngpu > 1) {
+        for (swrt_handle* c : h->shard) { int rc = swrt_set_flow_grid(c, slot, u, v, ux, uy, vx, vy, H, nx); if (rc) return up(h, c, rc); }
+        h->slot_set[slot] = true;
+        return SWRT_OK;
+    }
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
     REQUIRE(h, nx == h->p.nx, SWRT_ERR_ARG, "grid is %d^2 but the handle was created with nx = %d", nx, h->p.nx);
@@ -707,7 +810,10 @@ int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* 
         CU(h, cudaMemcpyAsync(tmp[c], src[c], n * 8, cudaMemcpyHostToDevice, h->stream));
     }
     if (h->p.mode == SWRT_MODE_LAGRANGE6) {
-        if (h->grid_npl != npl) { dfree(h->grid[0]); dfree(h->grid[1]); dfree(h->grid_blend); h->grid_npl = npl; }
+        if (h->grid_npl != npl) {
+            dfree(h->grid[0]); dfree(h->grid[1]); dfree(h->grid_blend); h->grid_npl = npl;
+            h->slot_set[1 - slot] = false;
+        }
         if (!h->grid[slot]) CU(h, cudaMalloc(&h->grid[slot], n * npl * 8));
         launch_interleave_grid(tmp.data(), npl, nx, h->grid[slot], h->stream);
         h->launches++;
@@ -736,56 +842,11 @@ int swrt_set_flow_grid(swrt_handle* h, int slot, const double* u, const double* 
     return rc;
 }
 
-// ---- packets ----------------------------------------------------------------------------------
-int swrt_packets_alloc_dev(swrt_handle* h, int64_t n) {
-    if (!h) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
-    REQUIRE(h, n >= 0, SWRT_ERR_ARG, "negative packet count");
-    int rc = ensure_packets(h, n);
-    if (rc) return rc;
-    launch_fill(h->a, 1.0, n, h->stream);
-    return SWRT_OK;
-}
-
-int swrt_packets_dev(swrt_handle* h, double** x, double** y, double** k, double** l, double** a) {
-    if (!h) return SWRT_ERR_ARG;
-    if (x) *x = h->x; if (y) *y = h->y; if (k) *k = h->k; if (l) *l = h->l; if (a) *a = h->a;
-    return SWRT_OK;
-}
-
-int swrt_set_packets(swrt_handle* h, int64_t n, const double* x, const double* y, const double* k, const double* l,
-                     const double* a) {
-    if (!h) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
-    REQUIRE(h, n >= 0, SWRT_ERR_ARG, "negative packet count");
-    REQUIRE(h, n == 0 || (x && y && k && l), SWRT_ERR_ARG, "null packet array");
-    int rc = ensure_packets(h, n);
-    if (rc) return rc;
-    h->bs_ready = false;
-    if ((rc = h2d(h, h->x, x, n)) || (rc = h2d(h, h->y, y, n)) || (rc = h2d(h, h->k, k, n)) || (rc = h2d(h, h->l, l, n)))
-        return rc;
-    if (a) { if ((rc = h2d(h, h->a, a, n))) return rc; }
-    else { launch_fill(h->a, 1.0, n, h->stream); h->launches++; }
-    CU(h, cudaStreamSynchronize(h->stream));
-    return SWRT_OK;
-}
-
-int swrt_get_packets(swrt_handle* h, double* x, double* y, double* k, double* l, double* a) {
-    if (!h) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
-    int rc;
-    if ((rc = d2h(h, x, h->x, h->n)) || (rc = d2h(h, y, h->y, h->n)) || (rc = d2h(h, k, h->k, h->n)) ||
-        (rc = d2h(h, l, h->l, h->n)) || (rc = d2h(h, a, h->a, h->n)))
-        return rc;
-    CU(h, cudaStreamSynchronize(h->stream));
-    return SWRT_OK;
-}
-
-int64_t swrt_num_packets(const swrt_handle* h) { return h ? h->n : 0; }
-
 // ---- evaluation -------------------------------------------------------------------------------
 int swrt_eval(swrt_handle* h, double alpha, double* U, double* V, double* Ux, double* Uy, double* Vx, double* Vy) {
     if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_each_slice(h, [&](swrt_handle* c, int64_t lo) {
+        return swrt_eval(c, alpha, at(U, lo), at(V, lo), at(Ux, lo), at(Uy, lo), at(Vx, lo), at(Vy, lo)); }));
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
     int rc = ensure_scratch(h, h->n);
@@ -804,6 +865,10 @@ int swrt_eval(swrt_handle* h, double alpha, double* U, double* V, double* Ux, do
 int swrt_eval_at(swrt_handle* h, double alpha, int64_t n, const double* x, const double* y, double* U, double* V,
                  double* Ux, double* Uy, double* Vx, double* Vy, double* H) {
     if (!h) return SWRT_ERR_ARG;
+    if (h->ngpu > 1) {   // caller-given points, independent of the packet state: the first device serves them
+        int rc = swrt_eval_at(h->shard[0], alpha, n, x, y, U, V, Ux, Uy, Vx, Vy, H);
+        return up(h, h->shard[0], rc);
+    }
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, n >= 0 && (n == 0 || (x && y)), SWRT_ERR_ARG, "bad positions");
     REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
@@ -826,6 +891,8 @@ static inline double rhs_cgfac(const swrt_handle* h) { return (h->p.flags & SWRT
 
 int swrt_rhs(swrt_handle* h, double alpha, double* dxdt, double* dydt, double* dkdt, double* dldt) {
     if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_each_slice(h, [&](swrt_handle* c, int64_t lo) {
+        return swrt_rhs(c, alpha, at(dxdt, lo), at(dydt, lo), at(dkdt, lo), at(dldt, lo)); }));
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
     int rc = ensure_scratch(h, h->n);
@@ -861,125 +928,138 @@ int swrt_interpolate(int device, const double* x, const double* y, int64_t n, co
     return rc;
 }
 
+}  // extern "C"
+
 // ---- stepping ---------------------------------------------------------------------------------
-static int step_leapfrog(swrt_handle* h, double dt, int nsteps, double alpha0, double dalpha) {
-    const bool steady = (dalpha == 0.0);
-    const int outer = steady ? 1 : nsteps;
-    const int inner = steady ? nsteps : 1;
-    int rc;
-    h->last_nlaunch = 0;
-    for (int j = 0; j < outer; j++) {
-        const double alpha = alpha0 + j * dalpha;
-        if (h->p.mode == SWRT_MODE_SPECTRAL) {
-            int mt = pick_mtiles(h, h->n);
-            SpecArgs a{};
-            const bool psi = use_psi(h, alpha);
-            if ((rc = active_stack(h, psi ? SUB_PSI3 : SUB_SIX, alpha, mt, &a.stack, &a.g))) return rc;
-            if (psi) fill_psi_args(h, alpha, a);
-            a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l;
-            a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
-        a.inv_nx = (h->p.nx & (h->p.nx - 1)) == 0 ? 1.0 / h->p.nx : 0.0;
-            a.f2 = h->p.f * h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = inner;
-#ifdef SWRT_TRACE
-            static unsigned long long* tr = nullptr;
-            if (!tr) { cudaMalloc(&tr, 8 * 640 * 8); }
-            cudaMemset(tr, 0, 8 * 640 * 8);
-            a.trace = tr;
-#endif
-            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
-            CU(h, launch_spectral(a, SPEC_LEAPFROG, mt, h->num_sms, h->stream));
-#ifdef SWRT_TRACE
-            {
-                std::vector<unsigned long long> hb(8 * 640);
-                cudaStreamSynchronize(h->stream);
-                cudaMemcpy(hb.data(), tr, hb.size() * 8, cudaMemcpyDeviceToHost);
-                FILE* fp = fopen("gpurun_out/trace.txt", "w");
-                if (fp) {
-                    for (int w = 0; w < 8; w++) { for (int i = 0; i < 640; i++) fprintf(fp, "%llu ", hb[w * 640 + i]); fprintf(fp, "\n"); }
-                    fclose(fp);
-                }
-            }
-#endif
-        } else if (h->p.mode == SWRT_MODE_NUFFT) {
-            const double* g = nullptr;
-            if ((rc = active_nufft_grid(h, alpha, &g, nullptr))) return rc;
-            NufftArgs a{};
-            fill_nufft_args(h, g, a);
-            a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.dt = dt; a.nsteps = inner;
-            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
-            CU(h, launch_nufft_leapfrog(a, h->stream));
-        } else {
-            LagArgs a{};
-            if ((rc = lag_frames(h, alpha, true, a))) return rc;
-            a.nx = h->p.nx; a.npl = h->grid_npl; a.n = h->n;
-            a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
-            a.dx = h->p.L / h->p.nx; a.bump = h->p.bump; a.f = h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = inner;
-            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
-            CU(h, launch_lagrange_leapfrog(a, h->stream));
-        }
-        h->launches++; h->last_nlaunch++;
-    }
-    CU(h, cudaEventRecord(h->ev1, h->stream));
-    h->timing_valid = true;
+// A "run" is up to m consecutive steps of one scheme executed by ONE launch per packet range with the packet in
+// registers.  Steady flow: the whole call is one run.  Time-dependent flow (dalpha != 0): the operands of every step of the
+// run -- packed stacks (SPECTRAL), fine grids (NUFFT), gridded frames (LAGRANGE6 RK4 / pre-blend tuning) -- are blended on
+// the device at al_j = alpha0 + j*dalpha by ONE multi-blend launch and stored back to back in the handle's arena; the
+// kernels read operand j in step j.  LAGRANGE6 leapfrog keeps interpolate_U.m's exact semantics instead (both frames
+// gathered, results blended with al_j inside the kernel).
+constexpr int kMaxFusedBlend = 32;
+
+struct RunOps {
+    int scheme = 0, m = 0;
+    bool xka = false, composed = false;
+    double dt = 0, alpha0 = 0, dalpha = 0;
+    int j0 = 0, mt = 1;
+    SpecArgs sa{};
+    NufftArgs na{};
+    LagArgs la{};
+};
+
+static int ensure_arena(swrt_handle* h, double*& p, size_t& cap, size_t doubles) {
+    if (doubles <= cap) return SWRT_OK;
+    dfree(p); cap = 0;
+    CU(h, cudaMalloc(&p, doubles * sizeof(double)));
+    cap = doubles;
     return SWRT_OK;
 }
 
-static int step_rk4(swrt_handle* h, bool xka, double dt, int nsteps, double alpha0, double dalpha) {
+// operands of steps j0 .. j0+m-1 of swrt_step(scheme, dt, ., alpha0, dalpha); blends are queued on h->stream
+static int prepare_run(swrt_handle* h, int scheme, double dt, double alpha0, double dalpha, int j0, int m, RunOps& r) {
+    int rc;
+    const bool td = (dalpha != 0.0);
+    const double alpha_first = alpha0 + j0 * dalpha;          // = alpha0 when the flow is steady
+    r.scheme = scheme; r.m = m; r.xka = (scheme == SWRT_SCHEME_RK4_XKA);
+    r.dt = dt; r.alpha0 = alpha0; r.dalpha = dalpha; r.j0 = j0;
+    const double C0 = sqrt(h->p.gH);
+    const int mode = h->p.mode;
+    if (td) REQUIRE(h, h->slot_set[1], SWRT_ERR_STATE, "dalpha = %g but flow slot 1 has not been set", dalpha);
+    if (mode == SWRT_MODE_SPECTRAL && scheme == SWRT_SCHEME_LEAPFROG) {
+        SpecArgs& a = r.sa;
+        r.mt = pick_mtiles(h, h->n);
+        const bool psi = use_psi(h, td ? 0.5 : alpha_first);
+        const int sub = psi ? SUB_PSI3 : SUB_SIX;
+        if (!td) {
+            if ((rc = active_stack(h, sub, alpha_first, r.mt, &a.stack, &a.g))) return rc;
+            a.nstack = 1;
+        } else {
+            if ((rc = ensure_stack(h, sub, 0, r.mt)) || (rc = ensure_stack(h, sub, 1, r.mt))) return rc;
+            Stack& s = h->stacks[sub];
+            a.g = s.g;
+            if ((rc = ensure_arena(h, h->arena, h->arena_cap, (size_t)m * s.g.total_doubles))) return rc;
+            launch_axpby_multi(h->arena, s.slot[0], s.slot[1], alpha0, dalpha, j0, m, s.g.total_doubles, h->stream);
+            h->launches++;
+            a.stack = h->arena; a.nstack = m;
+        }
+        if (psi) { a.psi = true; a.kappa = 2.0 * M_PI / h->p.L; a.u_mean0 = h->u_mean[0]; a.u_mean1 = h->slot_set[1] ? h->u_mean[1] : 0.0; }
+        a.alpha0 = alpha0; a.dalpha = dalpha; a.j0 = j0;
+        a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l;
+        a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
+        a.inv_nx = (h->p.nx & (h->p.nx - 1)) == 0 ? 1.0 / h->p.nx : 0.0;
+        a.f2 = h->p.f * h->p.f; a.gH = h->p.gH; a.dt = dt; a.nsteps = m;
+        return SWRT_OK;
+    }
+    if (mode == SWRT_MODE_NUFFT && (scheme == SWRT_SCHEME_LEAPFROG || !h->unfused_rk4)) {
+        NufftArgs& a = r.na;
+        const double *g = nullptr, *gh = nullptr;
+        const size_t nd = (size_t)2 * (size_t)(kNufftSigma * h->p.nx) * (size_t)(kNufftSigma * h->p.nx);   // doubles per (u,v) grid
+        if (!td) {
+            if ((rc = active_nufft_grid(h, alpha_first, &g, r.xka ? &gh : nullptr))) return rc;
+        } else {
+            REQUIRE(h, h->nufft_grid[0] && h->nufft_grid[1], SWRT_ERR_STATE, "both flow slots must be set");
+            if ((rc = ensure_arena(h, h->arena, h->arena_cap, (size_t)m * nd))) return rc;
+            launch_axpby_multi(h->arena, h->nufft_grid[0], h->nufft_grid[1], alpha0, dalpha, j0, m, nd, h->stream);
+            h->launches++;
+            g = h->arena;
+            if (r.xka && h->nufft_h[0] && h->nufft_h[1]) {
+                if ((rc = ensure_arena(h, h->arena_h, h->arena_h_cap, (size_t)m * 2 * nd))) return rc;
+                launch_axpby_multi(h->arena_h, h->nufft_h[0], h->nufft_h[1], alpha0, dalpha, j0, m, 2 * nd, h->stream);
+                h->launches++;
+                gh = h->arena_h;
+            }
+        }
+        REQUIRE(h, !r.xka || gh, SWRT_ERR_STATE, "flow has no H plane (needed by this scheme)");
+        fill_nufft_args(h, g, a);
+        a.hgrid = gh;
+        a.gstride = td ? nd / 2 : 0; a.hstride = td ? 2 * nd : 0;
+        a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
+        a.f = h->p.f; a.C0 = C0; a.dt = dt; a.nsteps = m;
+        return SWRT_OK;
+    }
+    if (mode == SWRT_MODE_LAGRANGE6) {
+        LagArgs& a = r.la;
+        REQUIRE(h, !r.xka || h->grid_npl == 7, SWRT_ERR_STATE, "step_packet_xka needs the H grid");
+        const bool exact_two = (scheme == SWRT_SCHEME_LEAPFROG) && !h->preblend_grid;
+        if (!td) {
+            if ((rc = lag_frames(h, alpha_first, exact_two, a))) return rc;
+        } else if (exact_two) {
+            REQUIRE(h, h->grid[0] && h->grid[1], SWRT_ERR_STATE, "both flow slots must be set");
+            a.grid = h->grid[0]; a.grid2 = h->grid[1]; a.alpha = alpha0; a.dalpha = dalpha; a.j0 = j0;
+        } else {
+            REQUIRE(h, h->grid[0] && h->grid[1], SWRT_ERR_STATE, "both flow slots must be set");
+            const size_t nd = (size_t)h->p.nx * h->p.nx * h->grid_npl;
+            if ((rc = ensure_arena(h, h->arena, h->arena_cap, (size_t)m * nd))) return rc;
+            launch_axpby_multi(h->arena, h->grid[0], h->grid[1], alpha0, dalpha, j0, m, nd, h->stream);
+            h->launches++;
+            a.grid = h->arena; a.grid2 = nullptr; a.gstride = nd;
+        }
+        a.nx = h->p.nx; a.npl = h->grid_npl;
+        a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
+        a.dx = h->p.L / h->p.nx; a.bump = h->p.bump; a.f = h->p.f; a.gH = h->p.gH; a.C0 = C0; a.dt = dt; a.nsteps = m;
+        return SWRT_OK;
+    }
+    // SPECTRAL RK4 by the composed route (tuning flag 4), and NUFFT with that flag: evaluation + glue launches per step
+    r.composed = true;
+    return ensure_scratch(h, h->n);
+}
+
+// step_packet / step_packet_xka composed point-wise from separate evaluation and stage launches (whole ensemble)
+static int run_composed_rk4(swrt_handle* h, const RunOps& r) {
     int rc;
     const double C0 = sqrt(h->p.gH);
-    h->last_nlaunch = 0;
-    if (h->p.mode == SWRT_MODE_LAGRANGE6) {
-        REQUIRE(h, !xka || h->grid_npl == 7, SWRT_ERR_STATE, "step_packet_xka needs the H grid");
-        const bool steady = (dalpha == 0.0);
-        const int outer = steady ? 1 : nsteps, inner = steady ? nsteps : 1;
-        for (int j = 0; j < outer; j++) {
-            LagArgs a{};
-            if ((rc = lag_frames(h, alpha0 + j * dalpha, false, a))) return rc;      // the RK4 kernels take one (blended) grid
-            a.nx = h->p.nx; a.npl = h->grid_npl; a.n = h->n;
-            a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
-            a.dx = h->p.L / h->p.nx; a.bump = h->p.bump; a.f = h->p.f; a.gH = h->p.gH; a.C0 = C0; a.dt = dt; a.nsteps = inner;
-            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
-            CU(h, launch_lagrange_rk4(a, xka, h->stream));
-            h->launches++; h->last_nlaunch++;
-        }
-        CU(h, cudaEventRecord(h->ev1, h->stream));
-        h->timing_valid = true;
-        return SWRT_OK;
-    }
-    if (h->p.mode == SWRT_MODE_NUFFT && !h->unfused_rk4) {
-        // one launch per run of steps on one flow (steady: all of them): stages, evaluations and the k / a update fused
-        const bool steady = (dalpha == 0.0);
-        const int outer = steady ? 1 : nsteps, inner = steady ? nsteps : 1;
-        for (int j = 0; j < outer; j++) {
-            const double *g = nullptr, *gh = nullptr;
-            if ((rc = active_nufft_grid(h, alpha0 + j * dalpha, &g, xka ? &gh : nullptr))) return rc;
-            REQUIRE(h, !xka || gh, SWRT_ERR_STATE, "flow has no H plane (needed by this scheme)");
-            NufftArgs a{};
-            fill_nufft_args(h, g, a);
-            a.hgrid = gh;
-            a.n = h->n; a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
-            a.f = h->p.f; a.C0 = C0; a.dt = dt; a.nsteps = inner;
-            if (j == 0) CU(h, cudaEventRecord(h->ev0, h->stream));
-            CU(h, launch_nufft_rk4(a, xka, h->stream));
-            h->launches++; h->last_nlaunch++;
-        }
-        CU(h, cudaEventRecord(h->ev1, h->stream));
-        h->timing_valid = true;
-        return SWRT_OK;
-    }
-    // SPECTRAL (and NUFFT with the un-fused tuning flag): continuous ray equations composed point-wise; 5 evaluations per step
-    if ((rc = ensure_scratch(h, h->n))) return rc;
-    CU(h, cudaEventRecord(h->ev0, h->stream));
-    for (int j = 0; j < nsteps; j++) {
-        const double alpha = alpha0 + j * dalpha;
-        Rk4Args r{};
-        r.n = h->n; r.x = h->x; r.y = h->y; r.k = h->k; r.l = h->l; r.a = h->a;
-        r.xs = h->xs; r.ys = h->ys; r.ax = h->ax; r.ay = h->ay;
-        r.dt = dt; r.f = h->p.f; r.C0 = C0; r.xka = xka;
+    for (int j = 0; j < r.m; j++) {
+        const double alpha = r.alpha0 + (r.j0 + j) * r.dalpha;
+        Rk4Args q{};
+        q.n = h->n; q.x = h->x; q.y = h->y; q.k = h->k; q.l = h->l; q.a = h->a;
+        q.xs = h->xs; q.ys = h->ys; q.ax = h->ax; q.ay = h->ay;
+        q.dt = r.dt; q.f = h->p.f; q.C0 = C0; q.xka = r.xka;
         for (int stage = 0; stage < 4; stage++) {
             const double* px = stage == 0 ? h->x : h->xs;
             const double* py = stage == 0 ? h->y : h->ys;
-            if (xka) {
+            if (r.xka) {
                 double* outs[3] = {h->e[0], h->e[1], h->e[6]};
                 if ((rc = eval_dev(h, SUB_UVH, alpha, h->n, px, py, outs))) return rc;
             } else if (stage == 0) {
@@ -991,49 +1071,476 @@ static int step_rk4(swrt_handle* h, bool xka, double dt, int nsteps, double alph
                 if ((rc = eval_dev(h, SUB_UV, alpha, h->n, px, py, outs))) return rc;
             }
             h->last_nlaunch++;
-            r.stage = stage; r.u = h->e[0]; r.v = h->e[1]; r.H = h->e[6];
-            launch_rk4_stage(r, h->stream);
+            q.stage = stage; q.u = h->e[0]; q.v = h->e[1]; q.H = h->e[6];
+            launch_rk4_stage(q, h->stream);
             h->launches++;
         }
-        if (xka) {
+        if (r.xka) {
             if ((rc = eval_dev(h, SUB_SEVEN, alpha, h->n, h->xs, h->ys, h->e))) return rc;
             h->last_nlaunch++;
         }
-        r.u = h->e[0]; r.v = h->e[1]; r.H = h->e[6];
-        r.ux = h->e[2]; r.uy = h->e[3]; r.vx = h->e[4]; r.vy = h->e[5];
-        launch_rk4_final(r, h->stream);
+        q.u = h->e[0]; q.v = h->e[1]; q.H = h->e[6];
+        q.ux = h->e[2]; q.uy = h->e[3]; q.vx = h->e[4]; q.vy = h->e[5];
+        launch_rk4_final(q, h->stream);
         h->launches++;
     }
-    CU(h, cudaEventRecord(h->ev1, h->stream));
-    h->timing_valid = true;
+    return SWRT_OK;
+}
+
+// the run's kernel over packets [lo, lo+cnt) on the handle's stream
+static int launch_run(swrt_handle* h, const RunOps& r, int64_t lo, int64_t cnt) {
+    if (cnt <= 0) return SWRT_OK;
+    if (r.composed) {
+        REQUIRE(h, lo == 0 && cnt == h->n, SWRT_ERR_STATE, "the composed RK4 route runs on the whole ensemble");
+        return run_composed_rk4(h, r);
+    }
+    const int mode = h->p.mode;
+    if (mode == SWRT_MODE_SPECTRAL) {
+        SpecArgs a = r.sa;
+        a.n = cnt; a.x += lo; a.y += lo; a.k += lo; a.l += lo;
+#ifdef SWRT_TRACE
+        static unsigned long long* tr = nullptr;
+        if (!tr) { cudaMalloc(&tr, 8 * 640 * 8); }
+        cudaMemset(tr, 0, 8 * 640 * 8);
+        a.trace = tr;
+#endif
+        CU(h, launch_spectral(a, SPEC_LEAPFROG, r.mt, h->num_sms, h->stream));
+#ifdef SWRT_TRACE
+        {
+            std::vector<unsigned long long> hb(8 * 640);
+            cudaStreamSynchronize(h->stream);
+            cudaMemcpy(hb.data(), tr, hb.size() * 8, cudaMemcpyDeviceToHost);
+            FILE* fp = fopen("gpurun_out/trace.txt", "w");
+            if (fp) {
+                for (int w = 0; w < 8; w++) { for (int i = 0; i < 640; i++) fprintf(fp, "%llu ", hb[w * 640 + i]); fprintf(fp, "\n"); }
+                fclose(fp);
+            }
+        }
+#endif
+    } else if (mode == SWRT_MODE_NUFFT) {
+        NufftArgs a = r.na;
+        a.n = cnt; a.x += lo; a.y += lo; a.k += lo; a.l += lo; a.a += lo;
+        if (r.scheme == SWRT_SCHEME_LEAPFROG) CU(h, launch_nufft_leapfrog(a, h->stream));
+        else CU(h, launch_nufft_rk4(a, r.xka, h->stream));
+    } else {
+        LagArgs a = r.la;
+        a.n = cnt; a.x += lo; a.y += lo; a.k += lo; a.l += lo; a.a += lo;
+        if (r.scheme == SWRT_SCHEME_LEAPFROG) CU(h, launch_lagrange_leapfrog(a, h->stream));
+        else CU(h, launch_lagrange_rk4(a, r.xka, h->stream));
+    }
+    h->launches++; h->last_nlaunch++;
+    return SWRT_OK;
+}
+
+static int check_step_args(swrt_handle* h, int scheme, double dt, int nsteps) {
+    REQUIRE(h, nsteps >= 0, SWRT_ERR_ARG, "negative step count");
+    REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
+    REQUIRE(h, std::isfinite(dt), SWRT_ERR_ARG, "dt is not finite");
+    REQUIRE(h, scheme == SWRT_SCHEME_LEAPFROG || scheme == SWRT_SCHEME_RK4_PACKET || scheme == SWRT_SCHEME_RK4_XKA, SWRT_ERR_ARG,
+            "unknown scheme %d", scheme);
     return SWRT_OK;
 }
 
 static int step_impl(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha, bool sync) {
     if (!h) return SWRT_ERR_ARG;
     CU(h, cudaSetDevice(h->p.device));
-    REQUIRE(h, nsteps >= 0, SWRT_ERR_ARG, "negative step count");
-    REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
-    REQUIRE(h, std::isfinite(dt), SWRT_ERR_ARG, "dt is not finite");
-    if (nsteps == 0 || h->n == 0) return SWRT_OK;
-    int rc;
-    switch (scheme) {
-        case SWRT_SCHEME_LEAPFROG: rc = step_leapfrog(h, dt, nsteps, alpha0, dalpha); break;
-        case SWRT_SCHEME_RK4_PACKET: rc = step_rk4(h, false, dt, nsteps, alpha0, dalpha); break;
-        case SWRT_SCHEME_RK4_XKA: rc = step_rk4(h, true, dt, nsteps, alpha0, dalpha); break;
-        default: return fail(h, SWRT_ERR_ARG, "unknown scheme %d", scheme);
-    }
+    int rc = check_step_args(h, scheme, dt, nsteps);
     if (rc) return rc;
+    if (nsteps == 0 || h->n == 0) return SWRT_OK;
+    h->last_nlaunch = 0;
+    const bool td = (dalpha != 0.0);
+    for (int j0 = 0; j0 < nsteps;) {
+        const int m = td ? (nsteps - j0 < kMaxFusedBlend ? nsteps - j0 : kMaxFusedBlend) : nsteps - j0;
+        RunOps r;
+        if ((rc = prepare_run(h, scheme, dt, alpha0, dalpha, j0, m, r))) return rc;
+        if (j0 == 0) CU(h, cudaEventRecord(h->ev0, h->stream));        // after the blends: ev0..ev1 brackets the packet kernels
+        if ((rc = launch_run(h, r, 0, h->n))) return rc;
+        j0 += m;
+    }
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timing_valid = true;
     if (sync) CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
 }
+
+// ---- host staging: pinned ring + helper threads -------------------------------------------------
+// Callers (MATLAB / Octave mxArrays, numpy arrays) hand ordinary pageable memory.  cudaMemcpyAsync on pageable
+// memory is a synchronous, single-threaded staged copy; instead the packet range is cut into chunks, helper threads copy
+// chunk c between the caller's arrays and a pinned ring while the DMA engines move chunk c-1 and (swrt_step_host) the
+// SMs advance chunk c-1: upload, compute and download overlap chunk by chunk.
+namespace {
+
+class CopyPool {          // process-wide helper threads for the staging copies
+public:
+    static CopyPool& get() { static CopyPool p; return p; }
+    // dst <- src (bytes), asynchronously; *pending is decremented when done
+    void submit(void* dst, const void* src, size_t bytes, std::atomic<int>* pending) {
+        pending->fetch_add(1, std::memory_order_relaxed);
+        if (threads_.empty()) { memcpy(dst, src, bytes); pending->fetch_sub(1, std::memory_order_release); return; }
+        { std::lock_guard<std::mutex> lk(mu_); q_.push_back({dst, src, bytes, pending}); }
+        cv_.notify_one();
+    }
+    // the calling thread helps until *pending reaches zero
+    void wait(std::atomic<int>* pending) {
+        while (pending->load(std::memory_order_acquire) > 0) {
+            Job j;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (q_.empty()) { j.bytes = 0; j.pending = nullptr; }
+                else { j = q_.front(); q_.pop_front(); }
+            }
+            if (j.pending) { memcpy(j.dst, j.src, j.bytes); j.pending->fetch_sub(1, std::memory_order_release); }
+            else std::this_thread::yield();
+        }
+    }
+    int helpers() const { return (int)threads_.size(); }
+private:
+    struct Job { void* dst; const void* src; size_t bytes; std::atomic<int>* pending; };
+    CopyPool() {
+        int n = 3;                                              // + the calling thread = 4 copy lanes
+        if (const char* e = getenv("SWRT_COPY_THREADS")) n = atoi(e);
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && n > hw - 1) n = hw - 1;
+        if (n < 0) n = 0;
+        for (int i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void loop() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = q_.front(); q_.pop_front();
+            }
+            memcpy(j.dst, j.src, j.bytes);
+            j.pending->fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Job> q_;
+    bool stop_ = false;
+};
+
+constexpr int kRing = 3;       // ring slots per direction
+
+}  // namespace
+
+struct Stager {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    double* pin_in = nullptr; double* pin_out = nullptr;   // kRing slots x 5 arrays x chunk_cap doubles
+    int64_t chunk_cap = 0;
+    cudaEvent_t ev_h2d[kRing] = {}, ev_k[kRing] = {}, ev_d2h[kRing] = {}, ev_all = nullptr;
+    std::atomic<int> out_pending[kRing];
+    std::atomic<int> in_pending;
+    Stager() { for (auto& a : out_pending) a.store(0); in_pending.store(0); }
+};
+
+namespace {
+
+void stager_free(swrt_handle* h) {
+    Stager* s = h->stager;
+    if (!s) return;
+    for (int i = 0; i < kRing; i++) CopyPool::get().wait(&s->out_pending[i]);
+    if (s->pin_in) cudaFreeHost(s->pin_in);
+    if (s->pin_out) cudaFreeHost(s->pin_out);
+    for (int i = 0; i < kRing; i++) {
+        if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
+        if (s->ev_k[i]) cudaEventDestroy(s->ev_k[i]);
+        if (s->ev_d2h[i]) cudaEventDestroy(s->ev_d2h[i]);
+    }
+    if (s->ev_all) cudaEventDestroy(s->ev_all);
+    if (s->s_in) cudaStreamDestroy(s->s_in);
+    if (s->s_out) cudaStreamDestroy(s->s_out);
+    delete s;
+    h->stager = nullptr;
+}
+
+int stager_init(swrt_handle* h, int64_t chunk) {
+    if (!h->stager) {
+        Stager* s = new (std::nothrow) Stager();
+        REQUIRE(h, s, SWRT_ERR_ALLOC, "out of host memory");
+        h->stager = s;
+        CU(h, cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < kRing; i++) {
+            CU(h, cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&s->ev_k[i], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&s->ev_d2h[i], cudaEventDisableTiming));
+        }
+        CU(h, cudaEventCreateWithFlags(&s->ev_all, cudaEventDisableTiming));
+    }
+    Stager* s = h->stager;
+    if (chunk > s->chunk_cap) {
+        for (int i = 0; i < kRing; i++) CopyPool::get().wait(&s->out_pending[i]);
+        if (s->pin_in) { cudaFreeHost(s->pin_in); s->pin_in = nullptr; }
+        if (s->pin_out) { cudaFreeHost(s->pin_out); s->pin_out = nullptr; }
+        s->chunk_cap = 0;
+        const size_t bytes = (size_t)kRing * 5 * (size_t)chunk * sizeof(double);
+        if (cudaHostAlloc(&s->pin_in, bytes, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&s->pin_out, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, SWRT_ERR_ALLOC, "cudaHostAlloc of the %zu-byte staging ring failed", 2 * bytes);
+        }
+        s->chunk_cap = chunk;
+    }
+    return SWRT_OK;
+}
+
+// one pipelined pass over the packet range: upload (in != null), run (r != null), download (out != null)
+struct HostPipe {
+    swrt_handle* h = nullptr;
+    const RunOps* run = nullptr;                      // a prepared run: computed chunk by chunk behind its upload
+    bool whole = false;                               // or: the whole plan after the last upload (SPECTRAL, multi-run plans)
+    int scheme = 0, nsteps = 0; double dt = 0, alpha0 = 0, dalpha = 0;
+    int64_t n = 0, chunk = 0; int nchunk = 0;
+    const double* in[5] = {}; double* out[5] = {};
+    bool have_in = false, have_out = false, chunked_compute = false;
+    int next_drain = 0;
+
+    static int64_t pick_chunk(int64_t n) {
+        int64_t c = (n + 7) / 8;
+        c = (c + 4095) / 4096 * 4096;
+        if (c < 16384) c = 16384;
+        if (c > 262144) c = 262144;
+        return c < n ? c : (n > 0 ? n : 1);
+    }
+    int begin() {
+        chunk = pick_chunk(n);
+        nchunk = (int)((n + chunk - 1) / chunk);
+        chunked_compute = run != nullptr;
+        next_drain = 0;
+        return stager_init(h, chunk);
+    }
+    double* dev(int c) const { double* d[5] = {h->x, h->y, h->k, h->l, h->a}; return d[c]; }
+    int enqueue_out(int c) {
+        Stager* s = h->stager;
+        const int slot = c % kRing;
+        const int64_t lo = (int64_t)c * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
+        CopyPool::get().wait(&s->out_pending[slot]);                 // the ring slot's previous contents reached the caller
+        CU(h, cudaStreamWaitEvent(s->s_out, chunked_compute ? s->ev_k[slot] : s->ev_all, 0));
+        for (int a = 0; a < 5; a++)
+            if (out[a])
+                CU(h, cudaMemcpyAsync(s->pin_out + ((size_t)slot * 5 + a) * s->chunk_cap, dev(a) + lo, (size_t)cnt * 8,
+                                      cudaMemcpyDeviceToHost, s->s_out));
+        CU(h, cudaEventRecord(s->ev_d2h[slot], s->s_out));
+        return SWRT_OK;
+    }
+    int drain(int c) {           // pinned ring -> caller's arrays (helper threads; completion is checked at slot reuse / end)
+        Stager* s = h->stager;
+        const int slot = c % kRing;
+        const int64_t lo = (int64_t)c * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
+        CU(h, cudaEventSynchronize(s->ev_d2h[slot]));
+        for (int a = 0; a < 5; a++)
+            if (out[a]) CopyPool::get().submit(out[a] + lo, s->pin_out + ((size_t)slot * 5 + a) * s->chunk_cap, (size_t)cnt * 8, &s->out_pending[slot]);
+        return SWRT_OK;
+    }
+    // chunk c: stage in, upload, (compute, download), drain an older chunk
+    int step(int c) {
+        Stager* s = h->stager;
+        int rc;
+        const int slot = c % kRing;
+        const int64_t lo = (int64_t)c * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
+        if (have_in) {
+            if (c >= kRing) CU(h, cudaEventSynchronize(s->ev_h2d[slot]));       // the DMA out of this ring slot has finished
+            for (int a = 0; a < 5; a++)
+                if (in[a]) CopyPool::get().submit(s->pin_in + ((size_t)slot * 5 + a) * s->chunk_cap, in[a] + lo, (size_t)cnt * 8, &s->in_pending);
+            CopyPool::get().wait(&s->in_pending);
+            for (int a = 0; a < 5; a++)
+                if (in[a])
+                    CU(h, cudaMemcpyAsync(dev(a) + lo, s->pin_in + ((size_t)slot * 5 + a) * s->chunk_cap, (size_t)cnt * 8,
+                                          cudaMemcpyHostToDevice, s->s_in));
+            if (!in[4]) { launch_fill(h->a + lo, 1.0, cnt, s->s_in); h->launches++; }
+            CU(h, cudaEventRecord(s->ev_h2d[slot], s->s_in));
+        }
+        if (chunked_compute) {
+            if (have_in) CU(h, cudaStreamWaitEvent(h->stream, s->ev_h2d[slot], 0));
+            if ((rc = launch_run(h, *run, lo, cnt))) return rc;
+            CU(h, cudaEventRecord(s->ev_k[slot], h->stream));
+        }
+        if (have_out && !whole) {
+            if (!run) { CU(h, cudaEventRecord(s->ev_all, h->stream)); }        // download only: behind the work already queued
+            if ((rc = enqueue_out(c))) return rc;
+            if (c - next_drain >= kRing - 1) { if ((rc = drain(next_drain))) return rc; next_drain++; }
+        }
+        return SWRT_OK;
+    }
+    // after the last chunk: whole-ensemble compute plans (SPECTRAL, composed or multi-run) queue their kernels ...
+    bool compute_done = false;
+    int finish_compute() {
+        Stager* s = h->stager;
+        int rc;
+        compute_done = true;
+        if (whole) {
+            if (have_in) { CU(h, cudaEventRecord(s->ev_all, s->s_in)); CU(h, cudaStreamWaitEvent(h->stream, s->ev_all, 0)); }
+            if ((rc = step_impl(h, scheme, dt, nsteps, alpha0, dalpha, false))) return rc;
+            CU(h, cudaEventRecord(s->ev_all, h->stream));
+        }
+        return SWRT_OK;
+    }
+    // ... and the remaining downloads are collected
+    int finish() {
+        Stager* s = h->stager;
+        int rc;
+        if (!compute_done && (rc = finish_compute())) return rc;
+        if (whole && have_out)
+            for (int c = 0; c < nchunk; c++) {
+                if ((rc = enqueue_out(c))) return rc;
+                if (c - next_drain >= kRing - 1) { if ((rc = drain(next_drain))) return rc; next_drain++; }
+            }
+        if (have_out) {
+            for (; next_drain < nchunk; next_drain++)
+                if ((rc = drain(next_drain))) return rc;
+            for (int i = 0; i < kRing; i++) CopyPool::get().wait(&s->out_pending[i]);
+        }
+        if (have_in && !have_out) CU(h, cudaStreamSynchronize(s->s_in));
+        if (!have_out && (run || whole)) CU(h, cudaStreamSynchronize(h->stream));
+        return SWRT_OK;
+    }
+};
+
+// set up a pipe over n packets of `h`: upload from in[] (when `up`), the plan (when nsteps > 0), download to out[]
+int pipe_setup(swrt_handle* h, HostPipe& p, RunOps& r, int64_t n, bool up, const double* const in[5], double* const out[5],
+               int scheme, double dt, int nsteps, double alpha0, double dalpha) {
+    int rc;
+    p = HostPipe{};
+    p.h = h; p.n = n;
+    if (up) {
+        if ((rc = ensure_packets(h, n))) return rc;
+        h->bs_ready = false;
+        p.have_in = true;
+        for (int a = 0; a < 5; a++) p.in[a] = in[a];
+    }
+    if (out) for (int a = 0; a < 5; a++) { p.out[a] = out[a]; p.have_out = p.have_out || out[a]; }
+    if (nsteps > 0) {
+        const bool td = (dalpha != 0.0);
+        const bool single = !td || nsteps <= kMaxFusedBlend;
+        const bool fused_kernel = h->p.mode == SWRT_MODE_LAGRANGE6 ||
+                                  (h->p.mode == SWRT_MODE_NUFFT && (scheme == SWRT_SCHEME_LEAPFROG || !h->unfused_rk4));
+        if (single && fused_kernel) {
+            if ((rc = prepare_run(h, scheme, dt, alpha0, dalpha, 0, nsteps, r))) return rc;
+            p.run = &r;
+        } else {
+            p.whole = true; p.scheme = scheme; p.dt = dt; p.nsteps = nsteps; p.alpha0 = alpha0; p.dalpha = dalpha;
+        }
+    }
+    return p.begin();
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- packets ----------------------------------------------------------------------------------
+int swrt_packets_alloc_dev(swrt_handle* h, int64_t n) {
+    if (!h) return SWRT_ERR_ARG;
+    REQUIRE(h, n >= 0, SWRT_ERR_ARG, "negative packet count");
+    if (h->ngpu > 1) {
+        const int64_t G = h->ngpu;
+        for (int64_t i = 0; i <= G; i++) h->off[i] = (i * n) / G;
+        h->n = n;
+        for (int64_t i = 0; i < G; i++) { int rc = swrt_packets_alloc_dev(h->shard[i], h->off[i + 1] - h->off[i]); if (rc) return up(h, h->shard[i], rc); }
+        return SWRT_OK;
+    }
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = ensure_packets(h, n);
+    if (rc) return rc;
+    launch_fill(h->a, 1.0, n, h->stream);
+    return SWRT_OK;
+}
+
+int swrt_packets_dev(swrt_handle* h, double** x, double** y, double** k, double** l, double** a) {
+    if (!h) return SWRT_ERR_ARG;
+    REQUIRE(h, h->ngpu <= 1, SWRT_ERR_STATE, "a multi-device handle has one set of buffers per shard (swrt_shard_info)");
+    if (x) *x = h->x; if (y) *y = h->y; if (k) *k = h->k; if (l) *l = h->l; if (a) *a = h->a;
+    return SWRT_OK;
+}
+
+int swrt_set_packets(swrt_handle* h, int64_t n, const double* x, const double* y, const double* k, const double* l,
+                     const double* a) {
+    if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_set_packets(h, n, x, y, k, l, a));
+    CU(h, cudaSetDevice(h->p.device));
+    REQUIRE(h, n >= 0, SWRT_ERR_ARG, "negative packet count");
+    REQUIRE(h, n == 0 || (x && y && k && l), SWRT_ERR_ARG, "null packet array");
+    if (n == 0) { h->n = 0; h->bs_ready = false; return SWRT_OK; }
+    CU(h, cudaStreamSynchronize(h->stream));          // earlier work on the packet buffers has finished
+    const double* in[5] = {x, y, k, l, a};
+    HostPipe p; RunOps r;
+    int rc = pipe_setup(h, p, r, n, true, in, nullptr, 0, 0.0, 0, 0.0, 0.0);
+    for (int c = 0; rc == SWRT_OK && c < p.nchunk; c++) rc = p.step(c);
+    if (rc == SWRT_OK) rc = p.finish();
+    return rc;
+}
+
+int swrt_get_packets(swrt_handle* h, double* x, double* y, double* k, double* l, double* a) {
+    if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_get_packets(h, x, y, k, l, a));
+    CU(h, cudaSetDevice(h->p.device));
+    if (h->n == 0) return SWRT_OK;
+    double* out[5] = {x, y, k, l, a};
+    HostPipe p; RunOps r;
+    int rc = pipe_setup(h, p, r, h->n, false, nullptr, out, 0, 0.0, 0, 0.0, 0.0);
+    for (int c = 0; rc == SWRT_OK && c < p.nchunk; c++) rc = p.step(c);
+    if (rc == SWRT_OK) rc = p.finish();
+    return rc;
+}
+
+int64_t swrt_num_packets(const swrt_handle* h) { return h ? h->n : 0; }
+
+int swrt_num_devices(const swrt_handle* h) { return h ? h->ngpu : 0; }
+
+int swrt_shard_info(const swrt_handle* h, int i, int* device, int64_t* lo, int64_t* n) {
+    if (!h || i < 0 || i >= h->ngpu) return SWRT_ERR_ARG;
+    if (device) *device = h->p.device + i;
+    if (lo) *lo = h->ngpu > 1 ? h->off[i] : 0;
+    if (n) *n = h->ngpu > 1 ? h->off[i + 1] - h->off[i] : h->n;
+    return SWRT_OK;
+}
+
 int swrt_step(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha) {
+    if (h && h->ngpu > 1) return grp_step(h, scheme, dt, nsteps, alpha0, dalpha, true);
     return step_impl(h, scheme, dt, nsteps, alpha0, dalpha, true);
 }
 // same launches, no host wait: the caller overlaps host work (diagnostics of the previous interval, the next
 // frame's upload) with the kernel; swrt_synchronize / any blocking call completes it
 int swrt_step_async(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha) {
+    if (h && h->ngpu > 1) return grp_step(h, scheme, dt, nsteps, alpha0, dalpha, false);
     return step_impl(h, scheme, dt, nsteps, alpha0, dalpha, false);
+}
+
+// host arrays in -> nsteps -> host arrays out (the call shape of ode_symplectic.m:1-4 / step_packet.m:1), pipelined over
+// packet chunks: see HostPipe
+int swrt_step_host(swrt_handle* h, int scheme, double dt, int nsteps, double alpha0, double dalpha, int64_t n, const double* x,
+                   const double* y, const double* k, const double* l, const double* a, double* xo, double* yo, double* ko,
+                   double* lo, double* ao) {
+    if (!h) return SWRT_ERR_ARG;
+    REQUIRE(h, n >= 0, SWRT_ERR_ARG, "negative packet count");
+    REQUIRE(h, n == 0 || (x && y && k && l), SWRT_ERR_ARG, "null packet array");
+    const double* in[5] = {x, y, k, l, a};
+    double* out[5] = {xo, yo, ko, lo, ao};
+    if (h->ngpu > 1) {
+        for (swrt_handle* c : h->shard) { int rc = check_step_args(c, scheme, dt, nsteps); if (rc) return up(h, c, rc); }
+        return grp_step_host(h, scheme, dt, nsteps, alpha0, dalpha, n, in, out);
+    }
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = check_step_args(h, scheme, dt, nsteps);
+    if (rc) return rc;
+    if (n == 0) { h->n = 0; h->bs_ready = false; return SWRT_OK; }
+    CU(h, cudaStreamSynchronize(h->stream));
+    HostPipe p; RunOps r;
+    rc = pipe_setup(h, p, r, n, true, in, out, scheme, dt, nsteps, alpha0, dalpha);
+    for (int c = 0; rc == SWRT_OK && c < p.nchunk; c++) rc = p.step(c);
+    if (rc == SWRT_OK) rc = p.finish();
+    h->timing_valid = false;
+    return rc;
 }
 
 // ---- diagnostics ------------------------------------------------------------------------------
@@ -1054,6 +1561,7 @@ static int compute_omega(swrt_handle* h, double alpha, bool need_abs) {
 
 int swrt_omega(swrt_handle* h, double alpha, double* omega, double* Omega_abs) {
     if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_each_slice(h, [&](swrt_handle* c, int64_t lo) { return swrt_omega(c, alpha, at(omega, lo), at(Omega_abs, lo)); }));
     CU(h, cudaSetDevice(h->p.device));
     int rc = compute_omega(h, alpha, Omega_abs != nullptr);
     if (rc) return rc;
@@ -1084,6 +1592,7 @@ static int hist_to_device(swrt_handle* h, int kind, double alpha, const double* 
 int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges, int nedges, uint64_t* counts,
                     int accumulate) {
     if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_hist_omega(h, kind, alpha, edges, nedges, counts, accumulate));
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, counts, SWRT_ERR_ARG, "null counts");
     int rc = hist_to_device(h, kind, alpha, edges, nedges);
@@ -1098,6 +1607,7 @@ int swrt_hist_omega(swrt_handle* h, int kind, double alpha, const double* edges,
 
 int swrt_hist_omega_dev(swrt_handle* h, int kind, double alpha, const double* edges, int nedges, uint64_t** counts_dev) {
     if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_hist_omega_dev(h, kind, alpha, edges, nedges, counts_dev, true));
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, counts_dev, SWRT_ERR_ARG, "null counts_dev");
     int rc = hist_to_device(h, kind, alpha, edges, nedges);
@@ -1111,6 +1621,7 @@ int swrt_hist_omega_dev(swrt_handle* h, int kind, double alpha, const double* ed
 // recorded after it; swrt_hist_omega_wait blocks on that event only (not on work queued afterwards)
 int swrt_hist_omega_launch(swrt_handle* h, int kind, double alpha, const double* edges, int nedges, uint64_t** counts_dev) {
     if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_hist_omega_dev(h, kind, alpha, edges, nedges, counts_dev, false));    // histograms + all-reduce queued, no host wait
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, counts_dev, SWRT_ERR_ARG, "null counts_dev");
     int rc = hist_to_device(h, kind, alpha, edges, nedges);
@@ -1122,6 +1633,7 @@ int swrt_hist_omega_launch(swrt_handle* h, int kind, double alpha, const double*
 }
 int swrt_hist_omega_wait(swrt_handle* h) {
     if (!h) return SWRT_ERR_ARG;
+    if (h->ngpu > 1) { int rc = swrt_hist_omega_wait(h->shard[0]); return up(h, h->shard[0], rc); }
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, h->hist_ev, SWRT_ERR_STATE, "swrt_hist_omega_launch has not been called");
     CU(h, cudaEventSynchronize(h->hist_ev));
@@ -1131,9 +1643,13 @@ int swrt_hist_omega_wait(swrt_handle* h) {
 int swrt_ideal_omega_hist(swrt_handle* h, double alpha, int64_t npts, const double* x, const double* y, const double* kvx,
                           const double* kvy, int nangles, double omega0, const double* edges, int nedges, uint64_t* counts) {
     if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_ideal_omega_hist(h, alpha, npts, x, y, kvx, kvy, nangles, omega0, edges, nedges, counts));
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, npts >= 0 && x && y && kvx && kvy && edges && counts, SWRT_ERR_ARG, "null argument");
     REQUIRE(h, nangles >= 1 && nangles <= 1024 && nedges >= 2 && nedges <= 4096, SWRT_ERR_ARG, "bad nangles / nedges");
+    // the kernel keeps the edges, the bin counters and the wavevectors in (default-limit) dynamic shared memory
+    REQUIRE(h, (size_t)nedges * 12 + (size_t)nangles * 16 <= 48 * 1024, SWRT_ERR_ARG,
+            "nedges*12 + nangles*16 = %zu bytes exceeds the 48 KB shared-memory budget of the kernel", (size_t)nedges * 12 + (size_t)nangles * 16);
     REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
     for (int i = 1; i < nedges; i++) REQUIRE(h, edges[i] >= edges[i - 1], SWRT_ERR_ARG, "edges must be non-decreasing");
     int rc = ensure_scratch(h, npts > h->n ? npts : h->n);
@@ -1161,13 +1677,21 @@ int swrt_ideal_omega_hist(swrt_handle* h, double alpha, int64_t npts, const doub
     return SWRT_OK;
 }
 
-int swrt_diag(swrt_handle* h, double alpha, double out[8]) {
-    if (!h || !out) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
+// the eight diagnostics of this handle's packets into h->diag_dev (queued, no host wait)
+static int diag_launch(swrt_handle* h, double alpha) {
     int rc = compute_omega(h, alpha, h->slot_set[0]);
     if (rc) return rc;
     launch_diag(h->n, h->x, h->y, h->k, h->l, h->a, h->om, h->slot_set[0] ? h->Om : h->om, h->diag_dev, h->stream);
     h->launches += 2;
+    return SWRT_OK;
+}
+
+int swrt_diag(swrt_handle* h, double alpha, double out[8]) {
+    if (!h || !out) return SWRT_ERR_ARG;
+    GROUP(h, grp_diag(h, alpha, out));
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = diag_launch(h, alpha);
+    if (rc) return rc;
     CU(h, cudaMemcpyAsync(out, h->diag_dev, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
@@ -1209,9 +1733,8 @@ static int bs23_read_norm(swrt_handle* h, double* out) {
     return SWRT_OK;
 }
 
-int swrt_bs23_begin(swrt_handle* h, double alpha, double threshold, double* rh_norm) {
-    if (!h || !rh_norm) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
+// f1 and the scale norm of this handle's packets into bs_norm_dev (queued, no host wait)
+static int bs23_begin_launch(swrt_handle* h, double alpha, double threshold) {
     REQUIRE(h, h->slot_set[0], SWRT_ERR_STATE, "no flow has been set");
     Bs23Args a{};
     int rc = bs23_setup(h, a);
@@ -1221,12 +1744,19 @@ int swrt_bs23_begin(swrt_handle* h, double alpha, double threshold, double* rh_n
     launch_bs23_norm(a, 1, threshold, h->bs_norm_dev, h->stream);
     h->launches++;
     h->bs_ready = true;
+    return SWRT_OK;
+}
+
+int swrt_bs23_begin(swrt_handle* h, double alpha, double threshold, double* rh_norm) {
+    if (!h || !rh_norm) return SWRT_ERR_ARG;
+    GROUP(h, grp_bs23_begin(h, alpha, threshold, rh_norm));
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = bs23_begin_launch(h, alpha, threshold);
+    if (rc) return rc;
     return bs23_read_norm(h, rh_norm);
 }
 
-int swrt_bs23_attempt(swrt_handle* h, double hstep, const double alpha[3], double threshold, double* err_norm) {
-    if (!h || !alpha || !err_norm) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
+static int bs23_attempt_launch(swrt_handle* h, double hstep, const double alpha[3], double threshold) {
     REQUIRE(h, h->bs_ready && h->bs_cap >= h->n, SWRT_ERR_STATE, "swrt_bs23_begin has not been called");
     Bs23Args a{};
     int rc = bs23_setup(h, a);
@@ -1243,11 +1773,24 @@ int swrt_bs23_attempt(swrt_handle* h, double hstep, const double alpha[3], doubl
     if ((rc = bs23_rhs(h, alpha[2], a.yt, f4))) return rc;
     launch_bs23_norm(a, 0, threshold, h->bs_norm_dev, h->stream);
     h->launches += 4;
+    return SWRT_OK;
+}
+
+int swrt_bs23_attempt(swrt_handle* h, double hstep, const double alpha[3], double threshold, double* err_norm) {
+    if (!h || !alpha || !err_norm) return SWRT_ERR_ARG;
+    GROUP(h, grp_bs23_attempt(h, hstep, alpha, threshold, err_norm));
+    CU(h, cudaSetDevice(h->p.device));
+    int rc = bs23_attempt_launch(h, hstep, alpha, threshold);
+    if (rc) return rc;
     return bs23_read_norm(h, err_norm);
 }
 
 int swrt_bs23_accept(swrt_handle* h) {
     if (!h) return SWRT_ERR_ARG;
+    if (h->ngpu > 1) {
+        for (swrt_handle* c : h->shard) { int rc = swrt_bs23_accept(c); if (rc) return up(h, c, rc); }
+        return SWRT_OK;
+    }
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, h->bs_ready, SWRT_ERR_STATE, "swrt_bs23_begin has not been called");
     Bs23Args a{};
@@ -1261,6 +1804,7 @@ int swrt_bs23_accept(swrt_handle* h) {
 
 int swrt_bs23_interp(swrt_handle* h, double hstep, double s, double* x, double* y, double* k, double* l) {
     if (!h || !x || !y || !k || !l) return SWRT_ERR_ARG;
+    GROUP(h, grp_each_slice(h, [&](swrt_handle* c, int64_t lo) { return swrt_bs23_interp(c, hstep, s, x + lo, y + lo, k + lo, l + lo); }));
     CU(h, cudaSetDevice(h->p.device));
     REQUIRE(h, h->bs_ready && h->bs_cap >= h->n, SWRT_ERR_STATE, "swrt_bs23_attempt has not been called");
     Bs23Args a{};
@@ -1495,8 +2039,10 @@ int swrt_set_flow_from_qg(swrt_handle* h, int slot, swrt_qg* q, double u_mean) {
     REQUIRE(h, q->nx == h->p.nx && q->device == h->p.device && q->L == h->p.L, SWRT_ERR_ARG, "QG state and handle differ in nx / L / device");
     const int nkx = q->nx - 1, nky = q->nx / 2, nh = nkx * nky;
     CU(h, cudaStreamSynchronize(q->stream));
-    qg_psi_kernel<<<(nh + 255) / 256, 256, 0, h->stream>>>(q->qk, nkx, nky, 2.0 * M_PI / q->L, q->K_d2, q->psi);
-    h->launches++;
+    swrt_handle* h0 = h->ngpu > 1 ? h->shard[0] : h;
+    qg_psi_kernel<<<(nh + 255) / 256, 256, 0, h0->stream>>>(q->qk, nkx, nky, 2.0 * M_PI / q->L, q->K_d2, q->psi);
+    h0->launches++;
+    if (h->ngpu > 1) { CU(h, cudaStreamSynchronize(h0->stream)); return grp_flow_from_psi_dev(h, slot, q->psi, u_mean); }
     return set_flow_spectral_dev(h, slot, q->psi, u_mean);
 }
 
@@ -1776,8 +2322,10 @@ int swrt_set_flow_from_qg2(swrt_handle* h, int slot, swrt_qg2* q) {
     REQUIRE(h, q->nx == h->p.nx && q->device == h->p.device && q->L == h->p.L, SWRT_ERR_ARG, "QG state and handle differ in nx / L / device");
     const int nkx = q->nx - 1, nky = q->nx / 2, nh = nkx * nky;
     CU(h, cudaStreamSynchronize(q->stream));
-    qg_psi_kernel<<<(nh + 255) / 256, 256, 0, h->stream>>>(q->q[0], nkx, nky, 2.0 * M_PI / q->L, q->par.K_d2, q->psi);
-    h->launches++;
+    swrt_handle* h0 = h->ngpu > 1 ? h->shard[0] : h;
+    qg_psi_kernel<<<(nh + 255) / 256, 256, 0, h0->stream>>>(q->q[0], nkx, nky, 2.0 * M_PI / q->L, q->par.K_d2, q->psi);
+    h0->launches++;
+    if (h->ngpu > 1) { CU(h, cudaStreamSynchronize(h0->stream)); return grp_flow_from_psi_dev(h, slot, q->psi, q->par.shear); }
     return set_flow_spectral_dev(h, slot, q->psi, q->par.shear);
 }
 
@@ -1788,13 +2336,25 @@ extern "C" {
 // ---- instrumentation --------------------------------------------------------------------------
 int64_t swrt_launch_count(swrt_handle* h, int reset) {
     if (!h) return 0;
+    if (h->ngpu > 1) { int64_t v = 0; for (swrt_handle* c : h->shard) v += swrt_launch_count(c, reset); return v; }
     int64_t v = h->launches;
     if (reset) h->launches = 0;
     return v;
 }
 
 double swrt_last_kernel_ms(swrt_handle* h, int* nlaunch) {
-    if (!h || !h->timing_valid) return -1.0;
+    if (!h) return -1.0;
+    if (h->ngpu > 1) {      // the slowest device's kernel time
+        double worst = -1.0;
+        for (swrt_handle* c : h->shard) {
+            if (c->n == 0) continue;
+            const double ms = swrt_last_kernel_ms(c, nlaunch);
+            if (ms < 0) return -1.0;
+            if (ms > worst) worst = ms;
+        }
+        return worst;
+    }
+    if (!h->timing_valid) return -1.0;
     cudaSetDevice(h->p.device);
     if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
     float ms = 0.f;
@@ -1805,6 +2365,7 @@ double swrt_last_kernel_ms(swrt_handle* h, int* nlaunch) {
 
 double swrt_work_per_eval(const swrt_handle* h, int nplanes) {
     if (!h) return 0.0;
+    if (h->ngpu > 1) return swrt_work_per_eval(h->shard[0], nplanes);
     if (h->p.mode == SWRT_MODE_SPECTRAL) {
         // executed DMMA flops per packet per evaluation: (kx>=0 count) * (ky count) * planes * 8
         // flops per folded complex MAC ... = 2 * nplanes * nx^2 for the unpadded problem
@@ -1817,6 +2378,7 @@ double swrt_work_per_eval(const swrt_handle* h, int nplanes) {
 
 int swrt_synchronize(swrt_handle* h) {
     if (!h) return SWRT_ERR_ARG;
+    GROUP(h, grp_sync(h));
     CU(h, cudaSetDevice(h->p.device));
     CU(h, cudaStreamSynchronize(h->stream));
     return SWRT_OK;
@@ -1824,6 +2386,7 @@ int swrt_synchronize(swrt_handle* h) {
 
 int swrt_set_stream(swrt_handle* h, void* cuda_stream) {
     if (!h) return SWRT_ERR_ARG;
+    REQUIRE(h, h->ngpu <= 1, SWRT_ERR_STATE, "a multi-device handle runs one stream per device; a caller stream belongs to one");
     CU(h, cudaSetDevice(h->p.device));
     CU(h, cudaStreamSynchronize(h->stream));
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
@@ -1832,6 +2395,10 @@ int swrt_set_stream(swrt_handle* h, void* cuda_stream) {
 
 int swrt_timer_start(swrt_handle* h) {
     if (!h) return SWRT_ERR_ARG;
+    if (h->ngpu > 1) {
+        for (swrt_handle* c : h->shard) { int rc = swrt_timer_start(c); if (rc) return up(h, c, rc); }
+        return SWRT_OK;
+    }
     CU(h, cudaSetDevice(h->p.device));
     CU(h, cudaEventRecord(h->tm0, h->stream));
     return SWRT_OK;
@@ -1839,6 +2406,11 @@ int swrt_timer_start(swrt_handle* h) {
 
 double swrt_timer_stop(swrt_handle* h) {
     if (!h) return -1.0;
+    if (h->ngpu > 1) {      // device time of the slowest device
+        double worst = -1.0;
+        for (swrt_handle* c : h->shard) { const double ms = swrt_timer_stop(c); if (ms < 0) return -1.0; if (ms > worst) worst = ms; }
+        return worst;
+    }
     cudaSetDevice(h->p.device);
     float ms = 0.f;
     if (cudaEventRecord(h->tm1, h->stream) != cudaSuccess || cudaEventSynchronize(h->tm1) != cudaSuccess ||
@@ -1852,6 +2424,7 @@ double swrt_timer_stop(swrt_handle* h) {
 int swrt_set_tuning(swrt_handle* h, int mtiles, int flags) {
     if (!h) return SWRT_ERR_ARG;
     REQUIRE(h, mtiles >= 0 && mtiles <= 2, SWRT_ERR_ARG, "mtiles must be 0, 1 or 2");
+    for (swrt_handle* c : h->shard) swrt_set_tuning(c, mtiles, flags);
     h->mtiles = mtiles;
     h->disable_psi = (flags & 1) != 0;
     h->preblend_grid = (flags & 2) != 0;
@@ -1861,6 +2434,7 @@ int swrt_set_tuning(swrt_handle* h, int mtiles, int flags) {
 
 int swrt_contracted_planes(const swrt_handle* h) {
     if (!h || h->p.mode != SWRT_MODE_SPECTRAL) return 0;
+    if (h->ngpu > 1) return swrt_contracted_planes(h->shard[0]);
     return use_psi(h, h->slot_set[1] ? 0.5 : 0.0) ? 3 : 6;
 }
 
@@ -1879,3 +2453,278 @@ int swrt_spectral_geometry(int nx, int nplanes, int mtiles, int64_t out[10]) {
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// Multi-device handles (swrt_params.ngpu > 1): SURVEY 8e.  One host thread, one single-device child handle (own
+// stream) per GPU, contiguous packet shards, flow replicated, and a single-process NCCL communicator
+// (ncclCommInitAll) whose only traffic is the all-reduce of the u64 histogram counts, the diagnostic scalars and the
+// ode23 error norm.  Every public entry point dispatches here when the handle is a group.
+// ================================================================================================
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+// NCCL is loaded on first use so that single-device callers carry no dependency on it (and so that a process which
+// already holds an NCCL -- e.g. the one bundled with torch -- shares that copy instead of mapping a second one)
+NcclApi* nccl_api(std::string& err) {
+    static NcclApi api;
+    static bool tried = false;
+    if (api.lib) return &api;
+    if (tried) { err = "NCCL could not be loaded earlier in this process"; return nullptr; }
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) if ((lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?"); return nullptr; }
+#define SWRT_NCCL_SYM(field, name)                                                   \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(lib, name));             \
+    if (!api.field) { err = std::string("NCCL symbol missing: ") + name; dlclose(lib); return nullptr; }
+    SWRT_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+    SWRT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    SWRT_NCCL_SYM(AllReduce, "ncclAllReduce")
+    SWRT_NCCL_SYM(GroupStart, "ncclGroupStart")
+    SWRT_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    SWRT_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef SWRT_NCCL_SYM
+    api.lib = lib;
+    return &api;
+}
+
+// propagate a child's failure to the group handle
+int up(swrt_handle* g, swrt_handle* c, int rc) {
+    if (rc != SWRT_OK) g->err = "device " + std::to_string(c->p.device) + ": " + c->err;
+    return rc;
+}
+#define EACH(g, c) for (swrt_handle* c : (g)->shard)
+#define CHILD(g, c, expr) do { int rc__ = (expr); if (rc__ != SWRT_OK) return up(g, c, rc__); } while (0)
+
+int grp_sync(swrt_handle* g) {
+    EACH(g, c) {
+        if (cudaSetDevice(c->p.device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+            return fail(g, SWRT_ERR_CUDA, "device %d: synchronize failed: %s", c->p.device, cudaGetErrorString(cudaGetLastError()));
+    }
+    return SWRT_OK;
+}
+
+// in-place all-reduce of `count` elements at buf(child) on every child's stream (stream-ordered, no host wait)
+template <typename F>
+int grp_allreduce(swrt_handle* g, F buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) {
+    std::string err;
+    NcclApi* api = nccl_api(err);
+    REQUIRE(g, api, SWRT_ERR_NCCL, "%s", err.c_str());
+    ncclResult_t r = api->GroupStart();
+    for (size_t i = 0; r == ncclSuccess && i < g->shard.size(); i++) {
+        swrt_handle* c = g->shard[i];
+        cudaSetDevice(c->p.device);
+        void* p = buf(c);
+        r = api->AllReduce(p, p, count, dt, op, g->comms[i], c->stream);
+    }
+    ncclResult_t r2 = api->GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) return fail(g, SWRT_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString(r));
+    return SWRT_OK;
+}
+
+int grp_create(const swrt_params* p, swrt_handle** out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: no CUDA device; libswrt has no CPU path");
+    }
+    if (p->device < 0 || p->device + p->ngpu > ndev)
+        return fail(nullptr, SWRT_ERR_ARG, "swrt_create: devices %d..%d requested but %d present", p->device, p->device + p->ngpu - 1, ndev);
+    std::string err;
+    NcclApi* api = nccl_api(err);
+    if (!api) return fail(nullptr, SWRT_ERR_NCCL, "swrt_create: ngpu = %d needs NCCL: %s", p->ngpu, err.c_str());
+    swrt_handle* g = new (std::nothrow) swrt_handle();
+    if (!g) return fail(nullptr, SWRT_ERR_ALLOC, "out of host memory");
+    g->p = *p; g->ngpu = p->ngpu;
+    g->off.assign(p->ngpu + 1, 0);
+    std::vector<int> devs;
+    for (int i = 0; i < p->ngpu; i++) {
+        swrt_params cp = *p;
+        cp.ngpu = 1; cp.device = p->device + i;
+        swrt_handle* c = nullptr;
+        int rc = swrt_create(&cp, &c);
+        if (rc == SWRT_OK && cudaMalloc(&c->red_dev, 24 * sizeof(double)) != cudaSuccess) { swrt_destroy(c); rc = fail(nullptr, SWRT_ERR_ALLOC, "cudaMalloc failed"); }
+        if (rc != SWRT_OK) { swrt_destroy(g); return rc; }      // g_create_error holds the child's message
+        g->shard.push_back(c);
+        devs.push_back(cp.device);
+    }
+    g->comms.assign(p->ngpu, nullptr);
+    ncclResult_t r = api->CommInitAll(g->comms.data(), p->ngpu, devs.data());
+    if (r != ncclSuccess) {
+        g->comms.clear();
+        swrt_destroy(g);
+        return fail(nullptr, SWRT_ERR_NCCL, "ncclCommInitAll(%d devices) failed: %s", p->ngpu, api->GetErrorString(r));
+    }
+    *out = g;
+    return SWRT_OK;
+}
+
+int grp_destroy(swrt_handle* g) {
+    std::string err;
+    NcclApi* api = nccl_api(err);
+    grp_sync(g);
+    if (api) for (ncclComm_t c : g->comms) if (c) api->CommDestroy(c);
+    EACH(g, c) swrt_destroy(c);
+    delete g;
+    return SWRT_OK;
+}
+
+void grp_split(swrt_handle* g, int64_t n) {
+    const int64_t G = g->ngpu;
+    for (int64_t i = 0; i <= G; i++) g->off[i] = (i * n) / G;      // the sharding of swraytracing_b200.distributed.shard_range
+    g->n = n;
+}
+
+// run one HostPipe per child, chunk by chunk round-robin, so that every device's DMA and SMs are busy at once
+int grp_pipes(swrt_handle* g, bool up_, const double* const in[5], double* const out[5], int scheme, double dt, int nsteps,
+              double alpha0, double dalpha) {
+    const size_t G = g->shard.size();
+    std::vector<HostPipe> pipes(G);
+    std::vector<RunOps> runs(G);
+    int maxchunks = 0;
+    for (size_t i = 0; i < G; i++) {
+        swrt_handle* c = g->shard[i];
+        const int64_t lo = g->off[i], cnt = g->off[i + 1] - lo;
+        if (cnt == 0) { if (up_) { c->n = 0; c->bs_ready = false; } continue; }
+        CU(g, cudaSetDevice(c->p.device));
+        const double* cin[5]; double* cout[5];
+        for (int a = 0; a < 5; a++) { cin[a] = (in && in[a]) ? in[a] + lo : nullptr; cout[a] = (out && out[a]) ? out[a] + lo : nullptr; }
+        if (up_) CU(g, cudaStreamSynchronize(c->stream));
+        CHILD(g, c, pipe_setup(c, pipes[i], runs[i], cnt, up_, up_ ? cin : nullptr, out ? cout : nullptr, scheme, dt, nsteps, alpha0, dalpha));
+        if (pipes[i].nchunk > maxchunks) maxchunks = pipes[i].nchunk;
+    }
+    for (int ch = 0; ch < maxchunks; ch++)
+        for (size_t i = 0; i < G; i++)
+            if (pipes[i].h && ch < pipes[i].nchunk) {
+                CU(g, cudaSetDevice(g->shard[i]->p.device));
+                CHILD(g, g->shard[i], pipes[i].step(ch));
+            }
+    // whole-ensemble compute plans: queue every device's kernels first, then collect the downloads
+    for (size_t i = 0; i < G; i++)
+        if (pipes[i].h) { CU(g, cudaSetDevice(g->shard[i]->p.device)); CHILD(g, g->shard[i], pipes[i].finish_compute()); }
+    for (size_t i = 0; i < G; i++)
+        if (pipes[i].h) { CU(g, cudaSetDevice(g->shard[i]->p.device)); CHILD(g, g->shard[i], pipes[i].finish()); }
+    return SWRT_OK;
+}
+
+int grp_set_packets(swrt_handle* g, int64_t n, const double* x, const double* y, const double* k, const double* l, const double* a) {
+    REQUIRE(g, n >= 0, SWRT_ERR_ARG, "negative packet count");
+    REQUIRE(g, n == 0 || (x && y && k && l), SWRT_ERR_ARG, "null packet array");
+    grp_split(g, n);
+    const double* in[5] = {x, y, k, l, a};
+    return grp_pipes(g, true, in, nullptr, 0, 0.0, 0, 0.0, 0.0);
+}
+int grp_get_packets(swrt_handle* g, double* x, double* y, double* k, double* l, double* a) {
+    double* out[5] = {x, y, k, l, a};
+    return grp_pipes(g, false, nullptr, out, 0, 0.0, 0, 0.0, 0.0);
+}
+int grp_step_host(swrt_handle* g, int scheme, double dt, int nsteps, double alpha0, double dalpha, int64_t n,
+                  const double* const in[5], double* const out[5]) {
+    grp_split(g, n);
+    return grp_pipes(g, true, in, out, scheme, dt, nsteps, alpha0, dalpha);
+}
+
+int grp_step(swrt_handle* g, int scheme, double dt, int nsteps, double alpha0, double dalpha, bool sync) {
+    EACH(g, c) CHILD(g, c, step_impl(c, scheme, dt, nsteps, alpha0, dalpha, false));      // all devices queued ...
+    return sync ? grp_sync(g) : SWRT_OK;                                                  // ... before the host waits
+}
+
+// histogram of every shard, counts all-reduced in place on the devices; returns with the reduce queued on the streams
+int grp_hist_queue(swrt_handle* g, int kind, double alpha, const double* edges, int nedges) {
+    EACH(g, c) { CU(g, cudaSetDevice(c->p.device)); CHILD(g, c, hist_to_device(c, kind, alpha, edges, nedges)); }
+    return grp_allreduce(g, [](swrt_handle* c) { return (void*)c->counts_dev; }, (size_t)(nedges - 1), ncclUint64, ncclSum);
+}
+int grp_hist_omega(swrt_handle* g, int kind, double alpha, const double* edges, int nedges, uint64_t* counts, int accumulate) {
+    REQUIRE(g, counts, SWRT_ERR_ARG, "null counts");
+    int rc = grp_hist_queue(g, kind, alpha, edges, nedges);
+    if (rc) return rc;
+    swrt_handle* c0 = g->shard[0];
+    std::vector<uint64_t> tmp(nedges - 1);
+    CU(g, cudaSetDevice(c0->p.device));
+    CU(g, cudaMemcpyAsync(tmp.data(), c0->counts_dev, (size_t)(nedges - 1) * 8, cudaMemcpyDeviceToHost, c0->stream));
+    if ((rc = grp_sync(g))) return rc;
+    for (int i = 0; i < nedges - 1; i++) counts[i] = accumulate ? counts[i] + tmp[i] : tmp[i];
+    return SWRT_OK;
+}
+int grp_hist_omega_dev(swrt_handle* g, int kind, double alpha, const double* edges, int nedges, uint64_t** counts_dev, bool wait) {
+    REQUIRE(g, counts_dev, SWRT_ERR_ARG, "null counts_dev");
+    int rc = grp_hist_queue(g, kind, alpha, edges, nedges);
+    if (rc) return rc;
+    swrt_handle* c0 = g->shard[0];
+    CU(g, cudaSetDevice(c0->p.device));
+    if (!c0->hist_ev) CU(g, cudaEventCreateWithFlags(&c0->hist_ev, cudaEventDisableTiming));
+    CU(g, cudaEventRecord(c0->hist_ev, c0->stream));
+    *counts_dev = reinterpret_cast<uint64_t*>(c0->counts_dev);          // the reduced counts, on the first device
+    return wait ? grp_sync(g) : SWRT_OK;
+}
+
+int grp_diag(swrt_handle* g, double alpha, double out[8]) {
+    // per-shard diagnostics, then SUM / MAX / MIN all-reduces of the eight scalars (three copies of them per device)
+    EACH(g, c) {
+        CU(g, cudaSetDevice(c->p.device));
+        CHILD(g, c, diag_launch(c, alpha));
+        for (int r = 0; r < 3; r++)
+            CU(g, cudaMemcpyAsync(c->red_dev + 8 * r, c->diag_dev, 8 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    int rc;
+    if ((rc = grp_allreduce(g, [](swrt_handle* c) { return (void*)c->red_dev; }, 8, ncclFloat64, ncclSum))) return rc;
+    if ((rc = grp_allreduce(g, [](swrt_handle* c) { return (void*)(c->red_dev + 8); }, 8, ncclFloat64, ncclMax))) return rc;
+    if ((rc = grp_allreduce(g, [](swrt_handle* c) { return (void*)(c->red_dev + 16); }, 8, ncclFloat64, ncclMin))) return rc;
+    swrt_handle* c0 = g->shard[0];
+    double r[24];
+    CU(g, cudaSetDevice(c0->p.device));
+    CU(g, cudaMemcpyAsync(r, c0->red_dev, sizeof r, cudaMemcpyDeviceToHost, c0->stream));
+    if ((rc = grp_sync(g))) return rc;
+    for (int i = 0; i < 8; i++) out[i] = r[i];       // sums: omega, Omega, non-finite count, a, n, omega*a
+    out[2] = r[8 + 2];                               // max omega
+    out[3] = r[16 + 3];                              // min omega
+    return SWRT_OK;
+}
+
+// ode23: the error norm couples ALL packets (qgsw_raytrace.m:149), so the per-shard inf-norms are MAX-all-reduced (as the
+// bit patterns of non-negative doubles, which order like unsigned integers) before the host controller sees them
+int grp_bs23_norm(swrt_handle* g, double* out) {
+    int rc = grp_allreduce(g, [](swrt_handle* c) { return (void*)c->bs_norm_dev; }, 1, ncclUint64, ncclMax);
+    if (rc) return rc;
+    swrt_handle* c0 = g->shard[0];
+    CU(g, cudaSetDevice(c0->p.device));
+    CHILD(g, c0, bs23_read_norm(c0, out));
+    return grp_sync(g);
+}
+int grp_bs23_begin(swrt_handle* g, double alpha, double threshold, double* rh_norm) {
+    EACH(g, c) { CU(g, cudaSetDevice(c->p.device)); CHILD(g, c, bs23_begin_launch(c, alpha, threshold)); }
+    return grp_bs23_norm(g, rh_norm);
+}
+int grp_bs23_attempt(swrt_handle* g, double hstep, const double alpha[3], double threshold, double* err_norm) {
+    EACH(g, c) { CU(g, cudaSetDevice(c->p.device)); CHILD(g, c, bs23_attempt_launch(c, hstep, alpha, threshold)); }
+    return grp_bs23_norm(g, err_norm);
+}
+
+int grp_ideal_omega_hist(swrt_handle* g, double alpha, int64_t npts, const double* x, const double* y, const double* kvx,
+                         const double* kvy, int nangles, double omega0, const double* edges, int nedges, uint64_t* counts) {
+    REQUIRE(g, npts >= 0 && x && y && counts && nedges >= 2, SWRT_ERR_ARG, "null argument");
+    // the caller's grid points are sharded like packets; integer counts add exactly
+    std::vector<uint64_t> part(nedges - 1);
+    for (int i = 0; i < nedges - 1; i++) counts[i] = 0;
+    const int64_t G = g->ngpu;
+    for (int64_t i = 0; i < G; i++) {
+        const int64_t lo = (i * npts) / G, hi = ((i + 1) * npts) / G;
+        swrt_handle* c = g->shard[i];
+        CHILD(g, c, swrt_ideal_omega_hist(c, alpha, hi - lo, x + lo, y + lo, kvx, kvy, nangles, omega0, edges, nedges, part.data()));
+        for (int b = 0; b < nedges - 1; b++) counts[b] += part[b];
+    }
+    return SWRT_OK;
+}
+
+}  // namespace

@@ -54,6 +54,9 @@ void launch_psi_to_planes(const double2* psik, double2* const* planes /*host arr
                           int nkx, int nky, double kappa, double u_mean, cudaStream_t st);
 void launch_axpby(double* out, const double* a, const double* b, double wa, double wb, size_t n,
                   cudaStream_t st);
+// m blends in one launch: out[j*n + i] = (1 - al_j)*a[i] + al_j*b[i], al_j = alpha0 + (j0 + j)*dalpha, j < m
+void launch_axpby_multi(double* out, const double* a, const double* b, double alpha0, double dalpha, int j0, int m, size_t n,
+                        cudaStream_t st);
 
 struct SpecArgs {
     const double* stack;
@@ -67,7 +70,12 @@ struct SpecArgs {
     double f2, gH, dt;
     int nsteps;
     bool psi;               // stack = psi-hat moment planes; assemble the six planes in stage 2
-    double kappa, u_mean;   // psi mode: 2*pi/L and the mean shear added to u
+    double kappa;           // psi mode: 2*pi/L
+    double u_mean0, u_mean1;   // psi mode: mean shear of the two flow slots; evaluation j adds (1-al_j)*u_mean0 + al_j*u_mean1
+    double alpha0, dalpha;  //   with al_j = alpha0 + (j0 + j)*dalpha (EVAL: j = 0)
+    int j0;
+    int nstack;             // LEAPFROG: `stack` holds nstack (= nsteps) consecutive stacks, one per fused step (a
+                            //   time-dependent flow pre-blended at al_j for every step of the launch); 0/1 = one stack
     unsigned long long* trace;   // developer timeline buffer (only read when built with -DSWRT_TRACE)
 };
 
@@ -83,7 +91,9 @@ size_t spectral_smem_bytes(const PackGeom& g);
 struct LagArgs {
     const double* grid;     // [nx][nx][npl] doubles
     const double* grid2;    // second frame for the exact two-frame blend (eval / leapfrog kernels), else null
-    double alpha;           // blend weight of grid2
+    double alpha;           // blend weight of grid2 (step j of a fused run: alpha + (j0 + j)*dalpha)
+    double dalpha; int j0;
+    size_t gstride;         // fused runs on pre-blended grids: step j reads grid + j*gstride (doubles); 0 = one grid
     int nx, npl;            // npl = 6 or 7 (7th = H)
     long long n;
     const double* xin; const double* yin;
@@ -136,6 +146,8 @@ constexpr double kNufftBeta = 2.30 * kNufftW;
 struct NufftArgs {
     const double2* grid;    // (u,v) fine grid, [iy*nf + ix]
     const double* hgrid;    // optional (u,v,H,0) fine grid, 4 doubles per node, same indexing (flows that carry H)
+    size_t gstride, hstride;   // fused runs on pre-blended fine grids: step j reads grid + j*gstride (double2) /
+                               // hgrid + j*hstride (doubles); 0 = one grid for every step
     int nf;
     long long n;
     const double* xin; const double* yin;

@@ -30,7 +30,8 @@ class SwrtError(RuntimeError):
 
 class _Params(C.Structure):
     _fields_ = [("nx", C.c_int32), ("mode", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32),
-                ("L", C.c_double), ("f", C.c_double), ("gH", C.c_double), ("bump", C.c_double)]
+                ("L", C.c_double), ("f", C.c_double), ("gH", C.c_double), ("bump", C.c_double),
+                ("ngpu", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/swrt.h declares
@@ -46,6 +47,8 @@ SIGNATURES = {
     "swrt_set_packets": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
     "swrt_get_packets": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp]),
     "swrt_num_packets": (C.c_int64, [C.c_void_p]),
+    "swrt_num_devices": (C.c_int, [C.c_void_p]),
+    "swrt_shard_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "swrt_packets_alloc_dev": (C.c_int, [C.c_void_p, C.c_int64]),
     "swrt_packets_dev": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5),
     "swrt_eval": (C.c_int, [C.c_void_p, C.c_double] + [_dp] * 6),
@@ -54,6 +57,7 @@ SIGNATURES = {
     "swrt_interpolate": (C.c_int, [C.c_int, _dp, _dp, C.c_int64, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp]),
     "swrt_step": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
     "swrt_step_async": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]),
+    "swrt_step_host": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int64] + [_dp] * 10),
     "swrt_hist_omega": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.POINTER(C.c_uint64), C.c_int]),
     "swrt_bs23_begin": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _dp]),
     "swrt_bs23_attempt": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, _dp]),
@@ -138,13 +142,16 @@ def _colmajor(a):
 
 
 class Engine:
-    """One handle = one CUDA device + device-resident packets + flow stacks."""
+    """One handle = ``ngpu`` CUDA devices (default one) + device-resident packets + flow stacks.  With ``ngpu > 1`` the
+    packets are sharded over the devices ``device .. device+ngpu-1`` inside libswrt (one host thread, in-library NCCL
+    all-reduce of histograms / diagnostics / the ode23 norm); every method keeps its meaning for the whole ensemble."""
 
-    def __init__(self, nx, L, f, gH, mode=MODE_SPECTRAL, device=0, bump=1e-13, flags=0):
+    def __init__(self, nx, L, f, gH, mode=MODE_SPECTRAL, device=0, bump=1e-13, flags=0, ngpu=1):
         self.lib = load_library()
         self.nx, self.L, self.f, self.gH, self.mode, self.device = int(nx), float(L), float(f), float(gH), int(mode), int(device)
+        self.ngpu = int(ngpu)
         self._h = C.c_void_p()
-        prm = _Params(self.nx, self.mode, self.device, int(flags), self.L, self.f, self.gH, float(bump))
+        prm = _Params(self.nx, self.mode, self.device, int(flags), self.L, self.f, self.gH, float(bump), self.ngpu, 0)
         rc = self.lib.swrt_create(C.byref(prm), C.byref(self._h))
         if rc != 0:
             raise SwrtError(rc, (self.lib.swrt_last_error(None) or b"").decode())
@@ -242,6 +249,25 @@ class Engine:
 
     def step(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
         self._check(self.lib.swrt_step(self._h, int(scheme), float(dt), int(nsteps), float(alpha0), float(dalpha)))
+
+    def step_host(self, scheme, dt, nsteps, x, y, k, l, a=None, alpha0=0.0, dalpha=0.0, out=None):
+        """host arrays in -> ``nsteps`` steps -> host arrays out in ONE C call (swrt_step_host: upload, compute and
+        download pipelined over packet chunks).  ``out``: optional (x, y, k, l[, a]) arrays to receive the result."""
+        x, y, k, l = map(_f64, (x, y, k, l))
+        a = _f64(a) if a is not None else None
+        self.n = x.size
+        if out is None:
+            out = [np.empty(self.n) for _ in range(5 if a is not None else 4)]
+        ptrs = [_ptr(o) for o in out] + [None] * (5 - len(out))
+        self._check(self.lib.swrt_step_host(self._h, int(scheme), float(dt), int(nsteps), float(alpha0), float(dalpha), self.n,
+                                            _ptr(x), _ptr(y), _ptr(k), _ptr(l), _ptr(a), *ptrs))
+        return tuple(out)
+
+    def shard_info(self, i):
+        """(device, lo, n) of shard ``i`` of a multi-device handle"""
+        d, lo, n = C.c_int(0), C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.swrt_shard_info(self._h, int(i), C.byref(d), C.byref(lo), C.byref(n)))
+        return d.value, lo.value, n.value
 
     def step_async(self, scheme, dt, nsteps, alpha0=0.0, dalpha=0.0):
         """queue the step's kernels and return at once (``synchronize()`` or any blocking call completes them)"""

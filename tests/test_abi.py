@@ -31,8 +31,8 @@ def test_ctypes_table_matches_header():
 
 def test_version_and_struct_layout():
     lib = S.load_library()
-    assert lib.swrt_version() == 100
-    assert ctypes.sizeof(engine._Params) == 48      # 4 x int32 + 4 x double, as swrt_params
+    assert lib.swrt_version() == 200
+    assert ctypes.sizeof(engine._Params) == 56      # 4 x int32 + 4 x double + 2 x int32 (ngpu, reserved), as swrt_params
 
 
 def test_no_cpu_fallback_without_device():
@@ -56,6 +56,9 @@ def test_create_argument_validation():
     bad = engine._Params(32, 5, 0, 0, 6.28, 3.0, 1.0, 1e-13)     # unknown mode
     assert lib.swrt_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     assert lib.swrt_create(None, ctypes.byref(h)) == -1
+    bad = engine._Params(32, 0, 0, 0, 6.28, 3.0, 1.0, 1e-13, -2, 0)     # negative device count
+    assert lib.swrt_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+    assert b"ngpu" in lib.swrt_last_error(None)
     assert lib.swrt_destroy(None) == 0
 
 

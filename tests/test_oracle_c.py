@@ -97,3 +97,30 @@ def test_linearity_of_time_blend(small_flow, packets):
     a = (1 - al) * CO.spectral_eval(x, y, p1, dx, nx) + al * CO.spectral_eval(x, y, p2, dx, nx)
     b = CO.spectral_eval(x, y, [(1 - al) * u + al * v for u, v in zip(p1, p2)], dx, nx)
     assert np.abs(a - b).max() < 1e-15
+
+
+def test_two_frame_leapfrog_c_port_equals_numpy_restatement(small_flow, packets):
+    """orc_leapfrog_lagrange2 (the CPU arm of the C3 / C4 bench lines) == interpolate_U.m + ode_symplectic.m restated in
+    numpy, bit for bit: both frames interpolated, blended (1-alpha)*F1 + alpha*F2, alpha_j = alpha0 + j*dalpha"""
+    dx = small_flow["dx"]
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    g1 = small_flow["grids"]
+    rs = np.random.RandomState(2)
+    g2 = [g + 0.05 * rs.standard_normal(g.shape) for g in g1]
+    bf1, bf2 = dict(zip(names, g1)), dict(zip(names, g2))
+    x, y, k, l = (packets[c].copy() for c in "xykl")
+    f, gH, dt, m = 3.0, 1.0, 0.01, 5
+    a0, da = 0.5 / m, 1.0 / m
+    for j in range(m):
+        al = a0 + j * da
+
+        def eval6(xx, yy):
+            U, nab = O.interpolate_U(bf1, bf2, al, np.stack([xx, yy], axis=1), dx)
+            return U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]
+        x, y, k, l = O.leapfrog_step(x, y, k, l, dt, f, gH, eval6)
+    got = CO.leapfrog_lagrange2(packets["x"], packets["y"], packets["k"], packets["l"], g1, g2, dx, f, gH, dt, m, a0, da)
+    assert np.array_equal(np.stack(got), np.stack([x, y, k, l]))
+    # dalpha = 0, alpha0 = 0 reduces to the steady port
+    st = CO.leapfrog_lagrange(packets["x"], packets["y"], packets["k"], packets["l"], g1, dx, f, gH, dt, m)
+    st2 = CO.leapfrog_lagrange2(packets["x"], packets["y"], packets["k"], packets["l"], g1, g2, dx, f, gH, dt, m, 0.0, 0.0)
+    assert np.allclose(np.stack(st), np.stack(st2), rtol=0, atol=1e-14)
