@@ -2,7 +2,9 @@
 NVCC      ?= nvcc
 CC        := gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
+# EXTRA=-DSWRT_DEV_TUNING enables the developer environment overrides of the dense kernel's geometry (tools/sweep.sh)
+EXTRA     ?=
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall $(EXTRA)
 CSRC      := swraytracing_b200/csrc
 OBJ       := build
 LIB       := swraytracing_b200/libswrt.so
@@ -20,7 +22,7 @@ $(OBJ)/lagrange_kernels.o: $(CSRC)/lagrange_kernels.cu $(CSRC)/swrt_internal.h i
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 
 $(LIB): $(OBJ)/spectral_kernels.o $(OBJ)/lagrange_kernels.o $(OBJ)/nufft_kernels.o $(OBJ)/misc_kernels.o $(OBJ)/swrt_api.o
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcufft -ldl -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
 
 $(ORACLE): oracle/swrt_oracle.c
 	@mkdir -p oracle/build

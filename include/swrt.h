@@ -256,6 +256,10 @@ int     swrt_contracted_planes(const swrt_handle* h);
  * table on (1) / off (0), twiddle-table bytes, dynamic shared memory bytes per CTA, packed-stack
  * bytes per flow slot.  Returns SWRT_OK or SWRT_ERR_ARG.                                          */
 int     swrt_spectral_geometry(int nx, int nplanes, int mtiles, int64_t out[10]);
+/* roofline probe for the gather-bound modes (LAGRANGE6, NUFFT): the rate (GB/s of useful bytes) at which the device serves
+ * scattered 64-byte segments of an L2-resident table of `table_bytes` (power of two, e.g. 16 MiB = the 512^2 NUFFT fine
+ * grid) to quads of lanes, eight loads in flight per lane; best of `reps`.  Returns SWRT_OK or an error code.      */
+int     swrt_gather_probe(int device, int64_t table_bytes, int reps, double* gbytes_per_s);
 
 #ifdef __cplusplus
 }

@@ -773,7 +773,9 @@ def ode23(odefun, tspan, y0, rtol=1e-3, atol=1e-6):
     f1 = odefun(t, y)
     nfevals = 1
     hmin = 16 * np.spacing(abs(t))
-    absh = min(hmax, abs(tfinal - t0))
+    # MATLAB (odearguments / ode23): htspan = |tspan(2) - tspan(1)|, absh = min(hmax, htspan) -- for a dense tspan the FIRST
+    # output interval, not the whole span, bounds the initial step
+    absh = min(hmax, abs(float(tspan[1]) - float(tspan[0])))
     rh = np.max(np.abs(f1) / np.maximum(np.abs(y), threshold)) / (0.8 * rtol ** pw)
     if absh * rh > 1:
         absh = 1 / rh

@@ -335,4 +335,58 @@ void launch_diag(long long n, const double* x, const double* y, const double* k,
     diag_final_kernel<<<1, 32, 0, st>>>(kDiagBlocks, part, n, out8_dev);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Gather-rate probe (the roofline denominator of the LAGRANGE6 / NUFFT modes).  Those kernels are bound by scattered
+// reads of an L2-resident table through L1TEX, not by HBM: this kernel measures the rate the chip sustains for that access
+// shape with nothing else in the way -- a quad of lanes reads one 64-byte segment (four 16-byte nodes) at a
+// pseudo-random table offset, eight independent loads in flight per lane, table far larger than L1 and smaller than L2.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) gather_probe_kernel(const double2* __restrict__ table, unsigned nseg_mask, int iters, double* __restrict__ sink) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned quad = t >> 2, q = t & 3;
+    unsigned state = quad * 2654435761u + 12345u;
+    double acc = 0.0;
+    for (int it = 0; it < iters; it++) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            state = state * 1664525u + 1013904223u;                 // one segment per quad per load: all four lanes agree
+            const unsigned seg = (state >> 7) & nseg_mask;
+            v[u] = __ldg(table + (size_t)seg * 4 + q);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += v[u].x + v[u].y;
+    }
+    if (acc == 123.456) sink[0] = acc;                              // keeps the loads alive
+}
+}  // namespace
+
+// useful bytes gathered per second (GB/s) from a table of `table_bytes` (power of two); <0 on error
+double gather_probe(size_t table_bytes, int iters, int reps, cudaStream_t st) {
+    double2* table = nullptr; double* sink = nullptr;
+    if (cudaMalloc(&table, table_bytes) != cudaSuccess || cudaMalloc(&sink, 8) != cudaSuccess) { cudaFree(table); return -1.0; }
+    cudaMemsetAsync(table, 0, table_bytes, st);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const unsigned nseg = (unsigned)(table_bytes / 64);
+    const int blocks = 148 * 8;
+    gather_probe_kernel<<<blocks, 256, 0, st>>>(table, nseg - 1, iters, sink);      // warm-up (table into L2)
+    double best = -1.0;
+    for (int r = 0; r < reps; r++) {
+        cudaEventRecord(e0, st);
+        gather_probe_kernel<<<blocks, 256, 0, st>>>(table, nseg - 1, iters, sink);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double gbs = (double)blocks * 256 * iters * 8 * 16 / (ms * 1e-3) * 1e-9;
+        if (gbs > best) best = gbs;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(table); cudaFree(sink);
+    return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}
+
 }  // namespace swrt

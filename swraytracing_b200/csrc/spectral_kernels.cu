@@ -244,8 +244,8 @@ __global__ void axpby_multi_kernel(double* __restrict__ out, const double* __res
     for (; i < n; i += stride) {
         const double av = a[i], bv = b[i];
         for (int j = 0; j < m; j++) {
-            const double al = alpha0 + (double)(j0 + j) * dalpha;
-            out[(size_t)j * n + i] = fma(1.0 - al, av, __dmul_rn(al, bv));
+            const double al = __dadd_rn(alpha0, __dmul_rn((double)(j0 + j), dalpha));      // un-fused: the host's alpha0 + j*dalpha
+            out[(size_t)j * n + i] = fma(__dsub_rn(1.0, al), av, __dmul_rn(al, bv));
         }
     }
 }
@@ -296,9 +296,13 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     constexpr size_t kSmemBudget = 216 * 1024;
     auto atab_fits = [&]() { return (size_t)g.ksteps * 32 * 8 * kConsumerWarps + 3 * g.chunk_doubles * 8 <= kSmemBudget; };
     bool want_atab = mtiles == 1 && kCtasPerSm == 1;
+    int kc_forced = 0;
+#ifdef SWRT_DEV_TUNING      // developer experiments only: the shipped library reads no environment variables
     if (const char* e = getenv("SWRT_ATAB")) want_atab = want_atab && atoi(e) != 0;
-    if (const char* e = getenv("SWRT_KC")) {
-        layout(atoi(e));
+    if (const char* e = getenv("SWRT_KC")) { kc_forced = atoi(e); if (kc_forced < kKUnroll) kc_forced = kKUnroll; }
+#endif
+    if (kc_forced) {
+        layout(kc_forced);
         g.atab = want_atab && atab_fits();
     } else {
         layout(kc0);
@@ -321,10 +325,11 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     g.lag = g.nstages - 1;
     if (g.lag > 4) g.lag = 4;
     g.desync_ns = (int)((g.lag >= 3 ? 1.5 : 0.6) * g.kc * g.NT * 16 / 1.9);
-    // developer tuning overrides (experiments only; defaults above are the shipped configuration)
+#ifdef SWRT_DEV_TUNING
     if (const char* e = getenv("SWRT_LAG")) g.lag = atoi(e);
     if (const char* e = getenv("SWRT_DESYNC_NS")) g.desync_ns = atoi(e);
-    if (const char* e = getenv("SWRT_NSTAGES")) g.nstages = atoi(e);
+    if (const char* e = getenv("SWRT_NSTAGES")) { g.nstages = atoi(e); if (g.nstages < 2) g.nstages = 2; }
+#endif
     if (g.lag >= g.nstages) g.lag = g.nstages - 1;
     if (g.lag < 1) g.lag = 1;
     for (int i = 0; i < kMaxPlanes; i++) g.plane_ids[i] = i < npl ? plane_ids[i] : 0;

@@ -208,12 +208,16 @@ int ensure_packets(swrt_handle* h, int64_t n) {
 // ---- spectral stacks ---------------------------------------------------------------------------
 int ensure_stack(swrt_handle* h, int sub, int slot, int mtiles) {
     Stack& s = h->stacks[sub];
-    if (!s.geom_ready || (s.g.G != make_geom(h->p.nx, kSubsetN[sub], kSubsetIds[sub], mtiles).G)) {
-        s.g = make_geom(h->p.nx, kSubsetN[sub], kSubsetIds[sub], mtiles);
+    const PackGeom want = make_geom(h->p.nx, kSubsetN[sub], kSubsetIds[sub], mtiles);
+    // a packed stack is only valid for the exact geometry it was packed with (tile grouping, chunking, padding)
+    if (!s.geom_ready || s.g.G != want.G || s.g.kc != want.kc || s.g.ksteps != want.ksteps || s.g.npass != want.npass ||
+        s.g.total_doubles != want.total_doubles) {
+        s.g = want;
         s.geom_ready = true;
         for (int i = 0; i < 2; i++) { dfree(s.slot[i]); s.slot_valid[i] = false; }
         dfree(s.blend);
     }
+    s.g = want;
     if (s.slot_valid[slot]) return SWRT_OK;
     REQUIRE(h, h->slot_set[slot], SWRT_ERR_STATE, "flow slot %d has not been set", slot);
     REQUIRE(h, h->slot_npl[slot] >= (sub == SUB_SEVEN || sub == SUB_UVH ? 7 : 6), SWRT_ERR_STATE,
@@ -910,22 +914,25 @@ int swrt_rhs(swrt_handle* h, double alpha, double* dxdt, double* dydt, double* d
 int swrt_interpolate(int device, const double* x, const double* y, int64_t n, const double* F, int nx, int ny,
                      double dx, double dy, double bump, double* FI) {
     if (!x || !y || !F || !FI || n < 0 || nx < 1 || ny < 1) return fail(nullptr, SWRT_ERR_ARG, "swrt_interpolate: bad argument");
+    // interpolate.m:45-46 wraps BOTH stencil indices with nx, so F(ig,jg) reads columns up to nx: for an nx x ny array with
+    // ny < nx MATLAB raises "index exceeds array bounds"; here that is an argument error, never an out-of-bounds read
+    if (ny < nx) return fail(nullptr, SWRT_ERR_ARG, "swrt_interpolate: F is %d x %d but the stencil wraps both indices with nx (interpolate.m:45-46): "
+                                                    "ny >= nx is required", nx, ny);
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_interpolate: no CUDA device"); }
     if (n == 0) return SWRT_OK;
-    double *dF = nullptr, *dx_ = nullptr, *dy_ = nullptr, *dout = nullptr;
-    int rc = SWRT_OK;
-    size_t nb = (size_t)n * 8, gb = (size_t)nx * ny * 8;
-    if (cudaMalloc(&dF, gb) || cudaMalloc(&dx_, nb) || cudaMalloc(&dy_, nb) || cudaMalloc(&dout, nb)) rc = fail(nullptr, SWRT_ERR_ALLOC, "swrt_interpolate: cudaMalloc failed");
-    if (!rc) {
-        cudaMemcpy(dF, F, gb, cudaMemcpyHostToDevice);
-        cudaMemcpy(dx_, x, nb, cudaMemcpyHostToDevice);
-        cudaMemcpy(dy_, y, nb, cudaMemcpyHostToDevice);
-        cudaError_t e = launch_interpolate_single(dF, nx, ny, dx_, dy_, n, dx, dy, bump > 0 ? bump : 1e-13, dout, 0);
-        if (e == cudaSuccess) e = cudaMemcpy(FI, dout, nb, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = fail(nullptr, SWRT_ERR_CUDA, "swrt_interpolate: %s", cudaGetErrorString(e));
+    DevTmp<double> dF, dx_, dy_, dout;
+    const size_t nb = (size_t)n * 8, gb = (size_t)nx * ny * 8;
+    if (dF.alloc((size_t)nx * ny) || dx_.alloc(n) || dy_.alloc(n) || dout.alloc(n)) {
+        cudaGetLastError();
+        return fail(nullptr, SWRT_ERR_ALLOC, "swrt_interpolate: cudaMalloc failed");
     }
-    cudaFree(dF); cudaFree(dx_); cudaFree(dy_); cudaFree(dout);
-    return rc;
+    cudaError_t e = cudaMemcpy(dF.p, F, gb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dx_.p, x, nb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dy_.p, y, nb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_interpolate_single(dF.p, nx, ny, dx_.p, dy_.p, n, dx, dy, bump > 0 ? bump : 1e-13, dout.p, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(FI, dout.p, nb, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(nullptr, SWRT_ERR_CUDA, "swrt_interpolate: %s", cudaGetErrorString(e));
+    return SWRT_OK;
 }
 
 }  // extern "C"
@@ -1197,9 +1204,13 @@ public:
 private:
     struct Job { void* dst; const void* src; size_t bytes; std::atomic<int>* pending; };
     CopyPool() {
-        int n = 3;                                              // + the calling thread = 4 copy lanes
-        if (const char* e = getenv("SWRT_COPY_THREADS")) n = atoi(e);
+        // helpers + the calling thread = copy lanes: half the hardware threads, at most eight lanes (one lane moves
+        // ~6-10 GB/s; a PCIe 5 x16 link wants ~50 GB/s in each direction).  SWRT_COPY_THREADS overrides the helper count.
         const int hw = (int)std::thread::hardware_concurrency();
+        int n = hw / 2 - 1;
+        if (n > 7) n = 7;
+        if (n < 1) n = 1;
+        if (const char* e = getenv("SWRT_COPY_THREADS")) n = atoi(e);
         if (hw > 0 && n > hw - 1) n = hw - 1;
         if (n < 0) n = 0;
         for (int i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
@@ -1278,7 +1289,7 @@ int stager_init(swrt_handle* h, int64_t chunk) {
         CU(h, cudaEventCreateWithFlags(&s->ev_all, cudaEventDisableTiming));
     }
     Stager* s = h->stager;
-    if (chunk > s->chunk_cap) {
+    if (chunk > s->chunk_cap) {      // (chunk = 0: the caller's arrays are page-locked, no ring needed)
         for (int i = 0; i < kRing; i++) CopyPool::get().wait(&s->out_pending[i]);
         if (s->pin_in) { cudaFreeHost(s->pin_in); s->pin_in = nullptr; }
         if (s->pin_out) { cudaFreeHost(s->pin_out); s->pin_out = nullptr; }
@@ -1303,7 +1314,16 @@ struct HostPipe {
     int64_t n = 0, chunk = 0; int nchunk = 0;
     const double* in[5] = {}; double* out[5] = {};
     bool have_in = false, have_out = false, chunked_compute = false;
+    bool direct_in = false, direct_out = false;       // the caller's arrays are page-locked: DMA straight from / to them
     int next_drain = 0;
+
+    // page-locked (cudaHostAlloc / cudaHostRegister) memory needs no staging
+    static bool pinned(const double* p, int64_t cnt) {
+        if (!p || cnt <= 0) return true;
+        cudaPointerAttributes a0{}, a1{};
+        if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, p + cnt - 1) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+    }
 
     static int64_t pick_chunk(int64_t n) {
         int64_t c = (n + 7) / 8;
@@ -1317,7 +1337,9 @@ struct HostPipe {
         nchunk = (int)((n + chunk - 1) / chunk);
         chunked_compute = run != nullptr;
         next_drain = 0;
-        return stager_init(h, chunk);
+        direct_in = have_in; direct_out = have_out;
+        for (int a = 0; a < 5; a++) { direct_in = direct_in && pinned(in[a], n); direct_out = direct_out && pinned(out[a], n); }
+        return stager_init(h, ((have_in && !direct_in) || (have_out && !direct_out)) ? chunk : 0);
     }
     double* dev(int c) const { double* d[5] = {h->x, h->y, h->k, h->l, h->a}; return d[c]; }
     int enqueue_out(int c) {
@@ -1328,7 +1350,7 @@ struct HostPipe {
         CU(h, cudaStreamWaitEvent(s->s_out, chunked_compute ? s->ev_k[slot] : s->ev_all, 0));
         for (int a = 0; a < 5; a++)
             if (out[a])
-                CU(h, cudaMemcpyAsync(s->pin_out + ((size_t)slot * 5 + a) * s->chunk_cap, dev(a) + lo, (size_t)cnt * 8,
+                CU(h, cudaMemcpyAsync(direct_out ? out[a] + lo : s->pin_out + ((size_t)slot * 5 + a) * s->chunk_cap, dev(a) + lo, (size_t)cnt * 8,
                                       cudaMemcpyDeviceToHost, s->s_out));
         CU(h, cudaEventRecord(s->ev_d2h[slot], s->s_out));
         return SWRT_OK;
@@ -1338,6 +1360,7 @@ struct HostPipe {
         const int slot = c % kRing;
         const int64_t lo = (int64_t)c * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
         CU(h, cudaEventSynchronize(s->ev_d2h[slot]));
+        if (direct_out) return SWRT_OK;
         for (int a = 0; a < 5; a++)
             if (out[a]) CopyPool::get().submit(out[a] + lo, s->pin_out + ((size_t)slot * 5 + a) * s->chunk_cap, (size_t)cnt * 8, &s->out_pending[slot]);
         return SWRT_OK;
@@ -1349,13 +1372,15 @@ struct HostPipe {
         const int slot = c % kRing;
         const int64_t lo = (int64_t)c * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
         if (have_in) {
-            if (c >= kRing) CU(h, cudaEventSynchronize(s->ev_h2d[slot]));       // the DMA out of this ring slot has finished
-            for (int a = 0; a < 5; a++)
-                if (in[a]) CopyPool::get().submit(s->pin_in + ((size_t)slot * 5 + a) * s->chunk_cap, in[a] + lo, (size_t)cnt * 8, &s->in_pending);
-            CopyPool::get().wait(&s->in_pending);
+            if (!direct_in) {
+                if (c >= kRing) CU(h, cudaEventSynchronize(s->ev_h2d[slot]));   // the DMA out of this ring slot has finished
+                for (int a = 0; a < 5; a++)
+                    if (in[a]) CopyPool::get().submit(s->pin_in + ((size_t)slot * 5 + a) * s->chunk_cap, in[a] + lo, (size_t)cnt * 8, &s->in_pending);
+                CopyPool::get().wait(&s->in_pending);
+            }
             for (int a = 0; a < 5; a++)
                 if (in[a])
-                    CU(h, cudaMemcpyAsync(dev(a) + lo, s->pin_in + ((size_t)slot * 5 + a) * s->chunk_cap, (size_t)cnt * 8,
+                    CU(h, cudaMemcpyAsync(dev(a) + lo, direct_in ? in[a] + lo : s->pin_in + ((size_t)slot * 5 + a) * s->chunk_cap, (size_t)cnt * 8,
                                           cudaMemcpyHostToDevice, s->s_in));
             if (!in[4]) { launch_fill(h->a + lo, 1.0, cnt, s->s_in); h->launches++; }
             CU(h, cudaEventRecord(s->ev_h2d[slot], s->s_in));
@@ -2436,6 +2461,16 @@ int swrt_contracted_planes(const swrt_handle* h) {
     if (!h || h->p.mode != SWRT_MODE_SPECTRAL) return 0;
     if (h->ngpu > 1) return swrt_contracted_planes(h->shard[0]);
     return use_psi(h, h->slot_set[1] ? 0.5 : 0.0) ? 3 : 6;
+}
+
+int swrt_gather_probe(int device, int64_t table_bytes, int reps, double* gbytes_per_s) {
+    if (!gbytes_per_s || table_bytes < (1 << 16) || (table_bytes & (table_bytes - 1)) || table_bytes > ((int64_t)1 << 31) || reps < 1)
+        return fail(nullptr, SWRT_ERR_ARG, "swrt_gather_probe: bad argument (table_bytes must be a power of two in [64 KiB, 2 GiB])");
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_gather_probe: no CUDA device"); }
+    const double v = gather_probe((size_t)table_bytes, 64, reps, 0);
+    if (v < 0) return fail(nullptr, SWRT_ERR_CUDA, "swrt_gather_probe: %s", cudaGetErrorString(cudaGetLastError()));
+    *gbytes_per_s = v;
+    return SWRT_OK;
 }
 
 int swrt_spectral_geometry(int nx, int nplanes, int mtiles, int64_t out[10]) {

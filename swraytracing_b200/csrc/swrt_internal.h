@@ -136,6 +136,7 @@ void launch_ideal_hist(long long npts, const double* u, const double* v, const d
 void launch_diag(long long n, const double* x, const double* y, const double* k, const double* l, const double* a,
                  const double* omega, const double* Omega_abs, double* out8_dev, cudaStream_t st);
 void launch_fill(double* p, double v, long long n, cudaStream_t st);
+double gather_probe(size_t table_bytes, int iters, int reps, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // NUFFT mode (type-2 non-uniform FFT evaluation of the same Fourier series; nufft_kernels.cu)

@@ -92,6 +92,7 @@ SIGNATURES = {
     "swrt_contracted_planes": (C.c_int, [C.c_void_p]),
     "swrt_spectral_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "swrt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "swrt_gather_probe": (C.c_int, [C.c_int, C.c_int64, C.c_int, _dp]),
     "swrt_timer_start": (C.c_int, [C.c_void_p]),
     "swrt_timer_stop": (C.c_double, [C.c_void_p]),
 }
@@ -126,6 +127,15 @@ def spectral_geometry(nx, nplanes=3, mtiles=1):
         raise SwrtError(rc, load_library().swrt_last_error(None).decode())
     keys = ("ntiles", "npass", "ksteps", "kc", "nstages", "chunk_bytes", "twiddle_table", "table_bytes", "smem_bytes", "stack_bytes")
     return dict(zip(keys, (int(v) for v in out)))
+
+
+def gather_probe(table_bytes=1 << 24, reps=5, device=0):
+    """measured scattered-gather rate (GB/s) from an L2-resident table: the roofline denominator of the gather modes"""
+    out = C.c_double(0.0)
+    rc = load_library().swrt_gather_probe(int(device), int(table_bytes), int(reps), C.byref(out))
+    if rc != 0:
+        raise SwrtError(rc, load_library().swrt_last_error(None).decode())
+    return out.value
 
 
 def _f64(a):

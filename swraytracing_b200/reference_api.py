@@ -289,7 +289,11 @@ def ode23(target, tspan, tmax, rtol=1e-3, atol=1e-6, reduce_max=None):
 
     A ``tspan`` with more than two entries (SW_zero_background_raytracing.m:73-78) additionally returns
     ``Y`` (len(tspan), 4, Np): the state at every requested time from the device-side cubic dense output
-    (MATLAB ``ntrp23``, swrt_bs23_interp) -- the steps themselves are chosen exactly as without it."""
+    (MATLAB ``ntrp23``, swrt_bs23_interp).  The step sequence follows MATLAB's controller, including the initial step
+    ``min(hmax, |tspan(2)-tspan(1)|, 1/rh)``, which for a dense ``tspan`` is bounded by the first output interval.
+
+    One deliberate deviation: a non-finite error estimate (a packet that blew up) REJECTS the step here and, at ``hmin``,
+    raises; MATLAB's ``if err > rtol`` is false for NaN, so it would accept the step and carry NaNs on silently."""
     red = reduce_max if reduce_max is not None else (lambda v: v)
     al = (lambda tt: tt / tmax) if tmax else (lambda tt: 0.0)       # tmax=None: steady flow, slot 0 only
     tspan = np.asarray(tspan, dtype=np.float64)
@@ -304,7 +308,9 @@ def ode23(target, tspan, tmax, rtol=1e-3, atol=1e-6, reduce_max=None):
     rh = red(target.bs23_begin(al(t), threshold)) / (0.8 * rtol ** pw)
     nfevals = 1
     hmin = 16 * np.spacing(abs(t))            # 16*eps(t)
-    absh = min(hmax, abs(tfinal - t0))
+    # MATLAB (odearguments / ode23): htspan = |tspan(2) - tspan(1)|, absh = min(hmax, htspan) -- for a dense tspan the FIRST
+    # output interval, not the whole span, bounds the initial step
+    absh = min(hmax, abs(float(tspan[1]) - float(tspan[0])))
     if absh * rh > 1:
         absh = 1 / rh
     absh = max(absh, hmin)

@@ -1221,29 +1221,38 @@ def test_randomised_schemes_two_frames_awkward_sizes():
 
 @pytest.mark.gpu
 def test_bench_gpu_arm_prints_one_contract_line():
-    """python bench.py (the GPU arm, N = 1) on a small ensemble: exactly one JSON line on stdout carrying the contract's
-    keys -- value / e2e with host<->device bytes, gpu_launches > 0, roofline of the dominant kernel (tensor bound, fraction
-    in (0, 1]), cpu_baseline measured beside it, sampled clocks -- and the side legs of the other two modes"""
+    """python bench.py (the GPU arm, N = 1) on small ensembles: exactly one JSON line on stdout carrying the contract's
+    keys -- value / e2e with host<->device bytes (pinned and pageable), gpu_launches > 0, roofline of the dominant kernel
+    (tensor bound against the fp64 peak measured in the run, fraction in (0, 1]), cpu_baseline measured beside it, sampled
+    clocks -- a side config under "configs" and the side legs of the other two modes (gather bound, "l2")"""
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, SWRT_BENCH_TARGET_S="0.3")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--packets", "9472"],
-                         capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--packets", "9472",
+                          "--configs", "C2", "--side-steps", "3"],
+                         capture_output=True, text=True, env=env, timeout=900, cwd=root)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout[-2000:]
     d = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "configs", "peaks_measured"):
         assert key in d, key
-    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "f64" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "f64" and d["higher_is_better"] is True and d["scaling"] == "strong"
+    assert d["config"]["name"] == "C4" and d["config"]["nx"] == 512 and d["config"]["packets_total"] == 9472
     assert d["value"] > 0 and d["gpu_launches"] >= 3 * 3
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 4 * 8 * 9472 == d["e2e"]["d2h_bytes_per_step"]
+    assert d["e2e"]["pageable"]["value"] > 0
     r = d["roofline"]
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0.0 < r["frac"] <= 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert r["kernel_launches_per_step"] == 1                   # the two sub-steps of the two-frame flow run in ONE packet kernel
+    assert 25.0 < d["peaks_measured"]["fp64_matmul_tflops"] < 45.0 and r["peak"] == d["peaks_measured"]["fp64_matmul_tflops"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     assert d["clocks"]["sm_max_mhz"] > 0
-    assert d["lagrange6"]["value"] > 0 and d["nufft"]["value"] > 0
+    c2 = d["configs"]["C2"]
+    assert c2["value"] > 0 and c2["e2e"]["value"] > 0 and c2["roofline"]["bound"] == "tensor" and c2["config"]["packets_total"] == 65536
+    for m in ("lagrange6", "nufft"):
+        assert d[m]["value"] > 0 and d[m]["roofline"]["bound"] == "l2" and d[m]["roofline"]["peak"] == d["peaks_measured"]["gather_probe_gbs"] > 0
     assert d["histogram_total"] <= 9472

@@ -27,10 +27,10 @@ def _ndev():
 def _engine(w, mode, ngpu=1, with_h=False):
     eng = S.Engine(w.nx, w.L, w.f, w.gH, mode, device=0, ngpu=ngpu)
     if with_h:
-        etak = (w.f / w.gH) * w.psik
-        eng.set_flow_planes_spectral(W.planes_from_psik(w.psik, w.L, w.u_mean, etak=etak), slot=0)
+        sc = 0.3 / np.abs(W._fulspec_ifft(w.psik)).max()            # |eta| <= 0.3, so that H = 1 + eta stays positive
+        eng.set_flow_planes_spectral(W.planes_from_psik(w.psik, w.L, w.u_mean, etak=sc * w.psik), slot=0)
         if w.psik2 is not None:
-            eng.set_flow_planes_spectral(W.planes_from_psik(w.psik2, w.L, w.u_mean, etak=(w.f / w.gH) * w.psik2), slot=1)
+            eng.set_flow_planes_spectral(W.planes_from_psik(w.psik2, w.L, w.u_mean, etak=sc * w.psik2), slot=1)
     else:
         eng.set_flow_spectral(w.psik, slot=0, u_mean=w.u_mean)
         if w.psik2 is not None:
@@ -58,6 +58,7 @@ def test_fused_time_dependent_run_equals_single_steps(mode, scheme):
                 eng.step(sch, w.dt / m, 1, a0 + j * da, 0.0)
         res.append(np.stack(eng.get_packets(with_a=True)))
         eng.close()
+    assert np.isfinite(res[0]).all()
     assert np.array_equal(res[0], res[1])
     assert np.abs(res[0][:4] - np.stack([w.x, w.y, w.k, w.l])).max() > 1e-6      # the packets did move
 

@@ -307,3 +307,23 @@ def test_step_packet_xka_uniform_depth_zero_flow_closed_form():
     bat = O.rk4_step_batch(arr(P["x"]), arr(P["y"]), arr(P["k"]), arr(P["l"]), arr(P["a"]), dt, C0, f, fields, dx, True)
     for i, name in enumerate(["x", "y", "k", "l", "a"]):
         assert abs(out[name] - bat[i][0]) < 1e-14
+
+
+def test_ode23_initial_step_is_bounded_by_the_first_output_interval():
+    """MATLAB's ode23 starts from absh = min(hmax, htspan, 1/rh) with htspan = |tspan(2) - tspan(1)| (odearguments): with the
+    dense ``tspan = dt*(0:Nsteps)`` of SW_zero_background_raytracing.m:73-78 the first step is the first output interval
+    whenever that is shorter than 1/rh.  y' = -y, y0 = 1: rh = 1/(0.8*rtol^(1/3)) -> 1/rh = 0.08 at RelTol 1e-3."""
+    calls = []
+
+    def f(t, y):
+        calls.append(t)
+        return -y
+    y0 = np.array([1.0])
+    O.ode23(f, [0.0, 1.0], y0)
+    assert abs(calls[1] - 0.5 * 0.08) < 1e-15                 # two-point span: 1/rh decides (hmax = 0.1, span = 1)
+    calls.clear()
+    out = O.ode23(f, np.arange(0.0, 1.0 + 1e-12, 0.01), y0)
+    assert abs(calls[1] - 0.5 * 0.01) < 1e-15                 # dense span: the first interval (0.01) decides
+    Y = out[0] if isinstance(out, tuple) else out
+    Y = np.asarray(Y["Y"] if isinstance(Y, dict) else Y)
+    assert np.abs(Y[:, 0] - np.exp(-np.arange(0.0, 1.0 + 1e-12, 0.01))).max() < 1e-3

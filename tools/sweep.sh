@@ -1,4 +1,5 @@
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+# needs a library built with the developer overrides: make clean && make EXTRA=-DSWRT_DEV_TUNING
 for cfg in "-1 -1 -1 -1" "0 3 4 8" "0 2 4 8" "0 4 8 4" "4000 4 8 4"; do
 set -- $cfg
 echo "desync=$1 lag=$2 nstages=$3 kc=$4"
