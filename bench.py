@@ -370,9 +370,10 @@ def measure(ctx, name, total_packets, sub, steps, warmup, mode_name, peaks, head
     from swraytracing_b200 import workloads as W
     from swraytracing_b200.distributed import ShardedEnsemble, shard_range
     torch, args = ctx.torch, ctx.args
-    w = W.make_workload(name, n_packets=total_packets or None)
+    weak = (name == "C2" and not total_packets)                 # C2 is BASELINE's one-GPU case: 65,536 packets PER GPU when N > 1
+    w = W.make_workload(name, n_packets=(65536 * ctx.n_gpus if weak else total_packets) or None)
     n_total = w.n_packets
-    lo, hi = shard_range(n_total, ctx.rank, ctx.world)          # strong scaling: this rank's contiguous shard
+    lo, hi = shard_range(n_total, ctx.rank, ctx.world)          # this rank's contiguous shard of the job's packets
     n = hi - lo
     xs, ys, ks, ls = (np.ascontiguousarray(a[lo:hi]) for a in (w.x, w.y, w.k, w.l))
     mode = {"spectral": S.MODE_SPECTRAL, "nufft": S.MODE_NUFFT, "lagrange6": S.MODE_LAGRANGE6}[mode_name]
@@ -521,7 +522,7 @@ def measure(ctx, name, total_packets, sub, steps, warmup, mode_name, peaks, head
                                    "quad of lanes per segment, 8 loads in flight per lane)",
                     "hbm_bytes_per_packet_step": 64.0 / sub}
 
-    res = {"value": value, "unit": UNIT, "ms_per_step": total_ms / steps, "steps": steps, "scaling": "strong",
+    res = {"value": value, "unit": UNIT, "ms_per_step": total_ms / steps, "steps": steps, "scaling": "weak" if weak else "strong",
            "config": dict(config_for(name, ctx.n_gpus, sub), packets_total=n_total, packets_per_gpu=-(-n_total // ctx.n_gpus), nx=w.nx,
                           mode=mode_name.upper(), scheme=w.scheme, l2="flushed between timed steps (256 MiB write per device)"),
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n, "ms_per_step": e2e_ms,

@@ -2515,9 +2515,10 @@ NcclApi* nccl_api(std::string& err) {
     if (api.lib) return &api;
     if (tried) { err = "NCCL could not be loaded earlier in this process"; return nullptr; }
     tried = true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    // SWRT_NCCL_LIB names a specific library file (installs whose NCCL is not on the loader path)
+    const char* names[] = {getenv("SWRT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     void* lib = nullptr;
-    for (const char* nm : names) if ((lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+    for (const char* nm : names) if (nm && *nm && (lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
     if (!lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?"); return nullptr; }
 #define SWRT_NCCL_SYM(field, name)                                                   \
     api.field = reinterpret_cast<decltype(api.field)>(dlsym(lib, name));             \

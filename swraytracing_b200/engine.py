@@ -119,6 +119,30 @@ def load_library(path: os.PathLike | None = None):
     return lib
 
 
+_nccl_preloaded = False
+
+
+def _preload_nccl():
+    """A multi-device handle makes libswrt dlopen("libnccl.so.2").  The dynamic loader keeps ONE library per soname in a
+    process, so whichever NCCL is mapped first also serves everybody else -- e.g. a later ``import torch``, whose
+    libtorch_cuda.so needs the symbols of the NCCL release it was built against.  When a pip-installed NCCL (the one torch
+    bundles: site-packages/nvidia/nccl/lib) is present, map that one first; otherwise the system library is used."""
+    global _nccl_preloaded
+    if _nccl_preloaded or os.environ.get("SWRT_NCCL_LIB"):
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = Path(root) / "lib" / "libnccl.so.2"
+            if cand.exists():
+                C.CDLL(str(cand), mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def spectral_geometry(nx, nplanes=3, mtiles=1):
     """launch geometry of the dense kernel (host-only diagnostic, swrt_spectral_geometry)"""
     out = (C.c_int64 * 10)()
@@ -160,6 +184,8 @@ class Engine:
         self.lib = load_library()
         self.nx, self.L, self.f, self.gH, self.mode, self.device = int(nx), float(L), float(f), float(gH), int(mode), int(device)
         self.ngpu = int(ngpu)
+        if self.ngpu > 1:
+            _preload_nccl()
         self._h = C.c_void_p()
         prm = _Params(self.nx, self.mode, self.device, int(flags), self.L, self.f, self.gH, float(bump), self.ngpu, 0)
         rc = self.lib.swrt_create(C.byref(prm), C.byref(self._h))

@@ -1,0 +1,214 @@
+"""Hot-path parity against the REFERENCE ITSELF, when its outputs are available.
+
+``tests/golden/make_octave_goldens.m`` runs the unmodified reference functions (interpolate, interpolate_U, SpectralScheme.U /
+grad_U / grad_U_times_k, ode_symplectic x 100 steps, cg_sw, step_packet, step_packet_xka) under MATLAB / GNU Octave on the
+seeded inputs of ``tests/golden/hotpath_nx32.npz`` and writes raw fp64 files with the reference's own ``write_field.m`` into
+``tests/golden/octave_out/``.  Neither MATLAB nor Octave exists in the development image, so until someone runs that
+script and commits its output these tests XFAIL with "parity unpinned"; once the files exist, the CPU oracle (numpy and C)
+and -- in the ``gpu`` tests -- the CUDA path through the C ABI are held to them: fields / RHS 1e-12 of max|plane|,
+trajectories (<= 100 steps) 1e-9.
+
+``test_golden_file_pipeline_self_check`` proves the plumbing (file format, array orientation, every comparison) on stand-in
+files written by the oracle into a temporary directory.  That is a self-check of this test module, NOT a pin."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import swrt_oracle as O
+from oracle import c_oracle as CO
+
+HERE = Path(__file__).resolve().parent
+GOLD = np.load(HERE / "golden" / "hotpath_nx32.npz")
+OUT = HERE / "golden" / "octave_out"
+TOL_FIELD, TOL_TRAJ = 1e-12, 1e-9
+NAMES = ("u", "v", "ux", "uy", "vx", "vy")
+EXPECTED = ("eval_lagrange", "interpU_lagrange", "rhs_lagrange", "scheme_eval", "scheme_gradU_times_k", "scheme_fields",
+            "leapfrog100_scheme", "leapfrog20_scheme", "leapfrog_t", "cg_sw_fields", "rk4x3_packet_lagrange", "rk4x3_xka_lagrange")
+
+
+def read_bin(d, name, *shape):
+    """one frame written by write_field.m: native-endian real*8, column-major"""
+    a = np.fromfile(Path(d) / f"{name}.bin", dtype=np.float64)
+    assert a.size == int(np.prod(shape)), (name, a.size, shape)
+    return a.reshape(shape, order="F")
+
+
+def have_goldens(d=OUT):
+    return all((Path(d) / f"{n}.bin").exists() for n in EXPECTED)
+
+
+def need_goldens():
+    if not have_goldens():
+        pytest.xfail("parity unpinned: tests/golden/octave_out/ is absent -- run tests/golden/make_octave_goldens.m under MATLAB / "
+                     "GNU Octave against the reference checkout and commit its output")
+
+
+def inputs():
+    nx = int(GOLD["nx"]); L = float(GOLD["L"])
+    kx_, ky_ = O.wavenumbers(nx)
+    g1 = list(GOLD["grids"])
+    g2 = [O.k2g(p) for p in O.velocity_planes_k(GOLD["psik2"], kx_, ky_)]
+    return dict(nx=nx, L=L, dx=L / nx, f=float(GOLD["f"]), gH=float(GOLD["gH"]), alpha=float(GOLD["alpha"]), dt=float(GOLD["dt"]),
+                x=GOLD["x"], y=GOLD["y"], k=GOLD["k"], l=GOLD["l"], g1=g1, g2=g2, H=GOLD["H"], psi=O.k2g(GOLD["psik"]), n=GOLD["x"].size)
+
+
+def scaled(got, ref):
+    ref = np.asarray(ref); got = np.asarray(got)
+    sc = np.abs(ref).reshape(ref.shape[0], -1).max(axis=1)
+    sc = np.where(sc > 0, sc, 1.0)
+    return float((np.abs(got - ref).reshape(ref.shape[0], -1).max(axis=1) / sc).max())
+
+
+def oracle_outputs(I):
+    """everything make_octave_goldens.m writes, computed by the numpy oracle (same names, same shapes)"""
+    x, y, k, l, dx = I["x"], I["y"], I["k"], I["l"], I["dx"]
+    out = {}
+    out["eval_lagrange"] = np.stack([O.interpolate(x, y, g, dx, dx) for g in I["g1"]])
+    bf1, bf2 = dict(zip(NAMES, I["g1"])), dict(zip(NAMES, I["g2"]))
+    U, nab = O.interpolate_U(bf1, bf2, I["alpha"], np.stack([x, y], axis=1), dx)
+    out["interpU_lagrange"] = np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])
+    out["rhs_lagrange"] = np.stack(O.odefun_rhs(x, y, k, l, I["alpha"], bf1, bf2, I["f"], 1.0, dx))
+    kx_, ky_ = O.wavenumbers(I["nx"])
+    planes = O.velocity_planes_k(O.g2k(I["psi"]), kx_, ky_)                     # SpectralScheme.m:16-25
+    fields = [O.k2g(p) for p in planes]                                         # :28-35
+    out["scheme_fields"] = np.stack(fields, axis=2)
+    ev = np.stack([O.interpolate(x, y, g, dx, dx) for g in fields])
+    out["scheme_eval"] = ev
+    out["scheme_gradU_times_k"] = np.stack([ev[2] * k + ev[4] * l, ev[3] * k + ev[5] * l])          # RaytracingScheme.m:9-16
+    st = (x, y, k, l)
+    for j in range(100):
+        st = O.leapfrog_step(*st, I["dt"], I["f"], I["gH"], lambda xx, yy: np.stack([O.interpolate(xx, yy, g, dx, dx) for g in fields]))
+        if j == 19:
+            out["leapfrog20_scheme"] = np.stack(st)
+    out["leapfrog100_scheme"] = np.stack(st)
+    out["leapfrog_t"] = np.arange(101) * I["dt"]
+    Uf = {"u": I["g1"][0], "v": I["g1"][1]}
+    Cx, Cy, om, divC, gx, gy = O.cg_sw(k[0], l[0], 1.0, I["f"], Uf, I["H"])
+    out["cg_sw_fields"] = np.stack([Cx, Cy, om, divC, gx, gy], axis=2)
+    flds = dict(zip(("u", "v", "u_x", "u_y", "v_x", "v_y"), I["g1"])); flds["H"] = I["H"]
+    for xka, name in ((False, "rk4x3_packet_lagrange"), (True, "rk4x3_xka_lagrange")):
+        s5 = (x, y, k, l, np.ones(I["n"]))
+        for _ in range(3):
+            s5 = O.rk4_step_batch(*s5, I["dt"], 1.0, I["f"], flds, dx, xka)
+        out[name] = np.stack(s5 if xka else s5[:4])
+    return out
+
+
+def shapes(I):
+    n, nx = I["n"], I["nx"]
+    return {"eval_lagrange": (6, n), "interpU_lagrange": (6, n), "rhs_lagrange": (4, n), "scheme_eval": (6, n), "scheme_gradU_times_k": (2, n),
+            "scheme_fields": (nx, nx, 6), "leapfrog100_scheme": (4, n), "leapfrog20_scheme": (4, n), "leapfrog_t": (101,),
+            "cg_sw_fields": (nx, nx, 6), "rk4x3_packet_lagrange": (4, n), "rk4x3_xka_lagrange": (5, n)}
+
+
+def check_oracle_against(d):
+    I = inputs()
+    mine = oracle_outputs(I)
+    shp = shapes(I)
+    worst = {}
+    for name in EXPECTED:
+        ref = read_bin(d, name, *shp[name])
+        got = mine[name]
+        if name in ("scheme_fields", "cg_sw_fields"):
+            got = np.moveaxis(got, 2, 0); ref = np.moveaxis(ref, 2, 0)
+        if name == "leapfrog_t":
+            got = got[None]; ref = ref[None]
+        tol = TOL_TRAJ if name.startswith(("leapfrog1", "leapfrog2", "rk4")) else TOL_FIELD
+        err = float(np.abs(got - ref).max()) if tol == TOL_TRAJ else scaled(got, ref)
+        worst[name] = err
+        assert err <= tol, (name, err)
+    return worst
+
+
+# ------------------------------------------------------------------------------------------------
+def test_oracle_against_reference_outputs():
+    """numpy oracle == the reference's own outputs (interpolate ... step_packet_xka)"""
+    need_goldens()
+    check_oracle_against(OUT)
+
+
+def test_c_port_against_reference_outputs():
+    """the C port that bench.py times as the CPU arm == the reference's own outputs"""
+    need_goldens()
+    I = inputs(); shp = shapes(I)
+    assert scaled(CO.interpolate6(I["x"], I["y"], I["g1"], I["dx"]), read_bin(OUT, "eval_lagrange", *shp["eval_lagrange"])) <= TOL_FIELD
+    fields = list(np.moveaxis(read_bin(OUT, "scheme_fields", *shp["scheme_fields"]), 2, 0))
+    st = CO.leapfrog_lagrange(I["x"], I["y"], I["k"], I["l"], fields, I["dx"], I["f"], I["gH"], I["dt"], 100)
+    assert np.abs(np.stack(st) - read_bin(OUT, "leapfrog100_scheme", 4, I["n"])).max() <= TOL_TRAJ
+    for xka, name in ((False, "rk4x3_packet_lagrange"), (True, "rk4x3_xka_lagrange")):
+        got = CO.rk4_lagrange(I["x"], I["y"], I["k"], I["l"], np.ones(I["n"]), I["g1"] + [I["H"]], I["dx"], I["f"], 1.0, I["dt"], 3, xka)
+        ref = read_bin(OUT, name, *shp[name])
+        assert np.abs(np.stack(got)[: ref.shape[0]] - ref).max() <= TOL_TRAJ
+
+
+@pytest.mark.gpu
+def test_gpu_path_against_reference_outputs():
+    """the CUDA path through the C ABI == the reference's own outputs: LAGRANGE6 mode everywhere (the reference's
+    arithmetic), SPECTRAL / NUFFT modes at the RHS level against SpectralScheme's evaluation under the degree-5
+    interpolation bound"""
+    need_goldens()
+    import swraytracing_b200 as S
+    from swraytracing_b200 import reference_api as R
+    I = inputs(); shp = shapes(I)
+    n = I["n"]
+    eng = S.Engine(I["nx"], I["L"], I["f"], I["gH"], S.MODE_LAGRANGE6)
+    eng.set_flow_grid(*I["g1"], H=I["H"], slot=0)
+    eng.set_packets(I["x"], I["y"], I["k"], I["l"])
+    assert scaled(eng.eval(0.0), read_bin(OUT, "eval_lagrange", 6, n)) <= TOL_FIELD
+    for xka, name, sch in ((False, "rk4x3_packet_lagrange", S.SCHEME_RK4_PACKET), (True, "rk4x3_xka_lagrange", S.SCHEME_RK4_XKA)):
+        eng.set_packets(I["x"], I["y"], I["k"], I["l"])
+        eng.step(sch, I["dt"], 3)
+        ref = read_bin(OUT, name, *shp[name])
+        assert np.abs(np.stack(eng.get_packets(with_a=True))[: ref.shape[0]] - ref).max() <= TOL_TRAJ
+    eng.set_flow_grid(*I["g2"], H=I["H"], slot=1)
+    eng.set_packets(I["x"], I["y"], I["k"], I["l"])
+    assert scaled(eng.eval(I["alpha"]), read_bin(OUT, "interpU_lagrange", 6, n)) <= TOL_FIELD
+    assert scaled(np.stack(eng.rhs(I["alpha"])), read_bin(OUT, "rhs_lagrange", 4, n)) <= TOL_FIELD
+    eng.close()
+    # ode_symplectic through the reference-named API on the scheme's own fields
+    fields = list(np.moveaxis(read_bin(OUT, "scheme_fields", *shp["scheme_fields"]), 2, 0))
+    eng = S.Engine(I["nx"], I["L"], I["f"], I["gH"], S.MODE_LAGRANGE6)
+    eng.set_flow_grid(*fields)
+    eng.set_packets(I["x"], I["y"], I["k"], I["l"])
+    assert scaled(eng.eval(0.0), read_bin(OUT, "scheme_eval", 6, n)) <= TOL_FIELD
+    eng.step(S.SCHEME_LEAPFROG, I["dt"], 20)
+    assert np.abs(np.stack(eng.get_packets()) - read_bin(OUT, "leapfrog20_scheme", 4, n)).max() <= TOL_TRAJ
+    eng.step(S.SCHEME_LEAPFROG, I["dt"], 80)
+    assert np.abs(np.stack(eng.get_packets()) - read_bin(OUT, "leapfrog100_scheme", 4, n)).max() <= TOL_TRAJ
+    eng.close()
+    # the exact Fourier-series modes evaluate the same fields: at grid nodes they equal the reference's interpolation
+    for mode in (S.MODE_SPECTRAL, S.MODE_NUFFT):
+        eng = S.Engine(I["nx"], I["L"], I["f"], I["gH"], mode)
+        eng.set_flow_spectral(O.g2k(I["psi"]))
+        ii = (np.arange(n) * 7) % I["nx"]; jj = (np.arange(n) * 3) % I["nx"]
+        got = eng.eval_at(ii * I["dx"], jj * I["dx"])
+        ref = np.stack([f[ii, jj] for f in fields])
+        assert scaled(got, ref) <= TOL_FIELD
+        eng.close()
+
+
+def test_golden_file_pipeline_self_check(tmp_path):
+    """NOT a pin: stand-in files written by the oracle in write_field.m's format go through the same reader and the same
+    comparisons, so that a maintainer who drops real reference outputs into tests/golden/octave_out/ gets a meaningful
+    verdict (and a transposed or mis-sized file is caught)"""
+    I = inputs()
+    mine = oracle_outputs(I)
+    for name, arr in mine.items():
+        (tmp_path / f"{name}.bin").write_bytes(np.asfortranarray(np.asarray(arr, dtype=np.float64)).ravel(order="F").tobytes())
+    assert have_goldens(tmp_path)
+    worst = check_oracle_against(tmp_path)
+    assert max(worst.values()) == 0.0
+    # a transposed file must fail
+    bad = np.asarray(mine["eval_lagrange"]).T.copy()
+    (tmp_path / "eval_lagrange.bin").write_bytes(np.asfortranarray(bad).ravel(order="F").tobytes())
+    with pytest.raises(AssertionError):
+        check_oracle_against(tmp_path)
+    # and the inputs the .m script reads are the fixture's: x, grids round-trip through the exported files
+    ind = HERE / "golden" / "octave_in"
+    assert np.array_equal(read_bin(ind, "x", I["n"]), I["x"])
+    assert np.array_equal(read_bin(ind, "bf1_ux", I["nx"], I["nx"]), I["g1"][2])
+    assert np.array_equal(read_bin(ind, "bf2_v", I["nx"], I["nx"]), I["g2"][1])
+    assert np.array_equal(read_bin(ind, "psi", I["nx"], I["nx"]), I["psi"])
+    p = read_bin(ind, "params", 8)
+    assert p[0] == I["nx"] and p[4] == I["alpha"] and p[5] == I["dt"] and p[7] == I["n"]
