@@ -12,7 +12,7 @@ ORACLE    := oracle/build/liboracle.so
 
 all: $(LIB) $(ORACLE)
 
-$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/swrt_internal.h include/swrt.h
+$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/swrt_internal.h $(CSRC)/spectral_common.cuh include/swrt.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
@@ -21,7 +21,7 @@ $(OBJ)/lagrange_kernels.o: $(CSRC)/lagrange_kernels.cu $(CSRC)/swrt_internal.h i
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 
-$(LIB): $(OBJ)/spectral_kernels.o $(OBJ)/lagrange_kernels.o $(OBJ)/nufft_kernels.o $(OBJ)/misc_kernels.o $(OBJ)/swrt_api.o
+$(LIB): $(OBJ)/spectral_kernels.o $(OBJ)/spectral_rk4_kernels.o $(OBJ)/lagrange_kernels.o $(OBJ)/nufft_kernels.o $(OBJ)/misc_kernels.o $(OBJ)/swrt_api.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcufft -ldl -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
 
 $(ORACLE): oracle/swrt_oracle.c

@@ -244,8 +244,9 @@ double  swrt_timer_stop(swrt_handle* h);
  * not use the psi-hat moment contraction (always contract the six planes); flags bit 1 (LAGRANGE6) =
  * blend two flow frames on the grid before the gather (half the gathers) instead of interpolating both
  * frames and blending the results as interpolate_U.m:19-23 does (the default, bit-faithful); flags
- * bit 2 (NUFFT) = run step_packet / step_packet_xka as separate evaluation + stage launches (the
- * dense mode's route) instead of the fused kernel                                                 */
+ * bit 2 (SPECTRAL, NUFFT) = run step_packet / step_packet_xka as separate evaluation + stage launches (the
+ * composed route: 4-5 evaluation kernels + 5 point-wise kernels per step, state and planes through
+ * HBM) instead of the fused kernel (one launch per run of steps, packet in registers)            */
 int     swrt_set_tuning(swrt_handle* h, int mtiles, int flags);
 /* planes the spectral kernel contracts for a six-plane evaluation: 3 when every flow slot was
  * given as psi-hat (moments N0,N1,N2; 6 nx^2 flops), else 6 (12 nx^2 flops); 0 in LAGRANGE6    */

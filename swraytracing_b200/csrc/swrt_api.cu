@@ -952,6 +952,7 @@ struct RunOps {
     double dt = 0, alpha0 = 0, dalpha = 0;
     int j0 = 0, mt = 1;
     SpecArgs sa{};
+    SpecRk4Args ra{};
     NufftArgs na{};
     LagArgs la{};
 };
@@ -1048,7 +1049,39 @@ static int prepare_run(swrt_handle* h, int scheme, double dt, double alpha0, dou
         a.dx = h->p.L / h->p.nx; a.bump = h->p.bump; a.f = h->p.f; a.gH = h->p.gH; a.C0 = C0; a.dt = dt; a.nsteps = m;
         return SWRT_OK;
     }
-    // SPECTRAL RK4 by the composed route (tuning flag 4), and NUFFT with that flag: evaluation + glue launches per step
+    if (mode == SWRT_MODE_SPECTRAL && !h->unfused_rk4) {
+        // fused step_packet / step_packet_xka: stage stack A = (u,v[,H]), big stack B = six / psi-moment / seven planes
+        SpecRk4Args& a = r.ra;
+        r.mt = 1;
+        const bool psi = !r.xka && use_psi(h, td ? 0.5 : alpha_first);
+        const int subA = r.xka ? SUB_UVH : SUB_UV, subB = r.xka ? SUB_SEVEN : (psi ? SUB_PSI3 : SUB_SIX);
+        if (!td) {
+            if ((rc = active_stack(h, subA, alpha_first, 1, &a.stackA, &a.gA)) || (rc = active_stack(h, subB, alpha_first, 1, &a.stackB, &a.gB))) return rc;
+            a.nstack = 1;
+        } else {
+            for (int sub : {subA, subB})
+                for (int slot = 0; slot < 2; slot++)
+                    if ((rc = ensure_stack(h, sub, slot, 1))) return rc;
+            Stack& sa_ = h->stacks[subA];
+            Stack& sb_ = h->stacks[subB];
+            a.gA = sa_.g; a.gB = sb_.g;
+            if ((rc = ensure_arena(h, h->arena, h->arena_cap, (size_t)m * sa_.g.total_doubles)) ||
+                (rc = ensure_arena(h, h->arena_h, h->arena_h_cap, (size_t)m * sb_.g.total_doubles))) return rc;
+            launch_axpby_multi(h->arena, sa_.slot[0], sa_.slot[1], alpha0, dalpha, j0, m, sa_.g.total_doubles, h->stream);
+            launch_axpby_multi(h->arena_h, sb_.slot[0], sb_.slot[1], alpha0, dalpha, j0, m, sb_.g.total_doubles, h->stream);
+            h->launches += 2;
+            a.stackA = h->arena; a.stackB = h->arena_h; a.nstack = m;
+        }
+        a.psiB = psi;
+        a.kappa = 2.0 * M_PI / h->p.L; a.u_mean0 = h->u_mean[0]; a.u_mean1 = h->slot_set[1] ? h->u_mean[1] : 0.0;
+        a.alpha0 = alpha0; a.dalpha = dalpha; a.j0 = j0;
+        a.x = h->x; a.y = h->y; a.k = h->k; a.l = h->l; a.a = h->a;
+        a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
+        a.inv_nx = (h->p.nx & (h->p.nx - 1)) == 0 ? 1.0 / h->p.nx : 0.0;
+        a.f = h->p.f; a.C0 = C0; a.dt = dt; a.nsteps = m;
+        return SWRT_OK;
+    }
+    // the composed route (tuning flag 4, SPECTRAL and NUFFT): evaluation + glue launches per step
     r.composed = true;
     return ensure_scratch(h, h->n);
 }
@@ -1102,7 +1135,11 @@ static int launch_run(swrt_handle* h, const RunOps& r, int64_t lo, int64_t cnt) 
         return run_composed_rk4(h, r);
     }
     const int mode = h->p.mode;
-    if (mode == SWRT_MODE_SPECTRAL) {
+    if (mode == SWRT_MODE_SPECTRAL && r.scheme != SWRT_SCHEME_LEAPFROG) {
+        SpecRk4Args a = r.ra;
+        a.n = cnt; a.x += lo; a.y += lo; a.k += lo; a.l += lo; a.a += lo;
+        CU(h, launch_spectral_rk4(a, r.xka, h->num_sms, h->stream));
+    } else if (mode == SWRT_MODE_SPECTRAL) {
         SpecArgs a = r.sa;
         a.n = cnt; a.x += lo; a.y += lo; a.k += lo; a.l += lo;
 #ifdef SWRT_TRACE

@@ -81,6 +81,26 @@ struct SpecArgs {
 
 enum SpecMode { SPEC_EVAL = 0, SPEC_LEAPFROG = 1 };
 
+// fused step_packet / step_packet_xka in SPECTRAL mode (spectral_rk4_kernels.cu): two packed stacks share one chunk ring
+struct SpecRk4Args {
+    const double* stackA;   // stage evaluations: (u,v) or (u,v,H)
+    const double* stackB;   // the big evaluation: six planes / the psi-hat moment planes (old position) or seven planes (new position)
+    PackGeom gA, gB;
+    int nstages, lag, atab, tab_ksteps;      // joint ring geometry (filled by spectral_rk4_geometry)
+    uint32_t stage_bytes;
+    long long n;
+    double *x, *y, *k, *l, *a;
+    double dx, nxd, inv_nx;
+    double f, C0, dt;
+    int nsteps;
+    int nstack;             // > 1: one pre-blended pair of stacks per step (time-dependent flow), stored back to back
+    bool psiB;              // stackB = psi-hat moment planes
+    double kappa, u_mean0, u_mean1, alpha0, dalpha;
+    int j0;
+};
+bool spectral_rk4_geometry(SpecRk4Args& a, size_t* smem_bytes);
+cudaError_t launch_spectral_rk4(const SpecRk4Args& a, bool xka, int num_sms, cudaStream_t st);
+
 // returns cudaError; grid is sized to the SM count (persistent CTAs)
 cudaError_t launch_spectral(const SpecArgs& a, int mode, int mtiles, int num_sms, cudaStream_t st);
 size_t spectral_smem_bytes(const PackGeom& g);

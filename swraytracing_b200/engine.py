@@ -405,7 +405,7 @@ class Engine:
     def set_tuning(self, mtiles=0, use_psi_moments=True, preblend_grid=False, unfused_rk4=False):
         """``preblend_grid`` (LAGRANGE6): blend two frames on the grid before the gather (faster) instead of
         interpolating both frames and blending the results as interpolate_U.m does (default, bit-faithful);
-        ``unfused_rk4`` (NUFFT): step_packet* as evaluation + stage launches instead of the fused kernel"""
+        ``unfused_rk4`` (SPECTRAL, NUFFT): step_packet* as evaluation + stage launches instead of the fused kernel"""
         self._check(self.lib.swrt_set_tuning(self._h, int(mtiles), (0 if use_psi_moments else 1) | (2 if preblend_grid else 0)
                                              | (4 if unfused_rk4 else 0)))
 

@@ -240,3 +240,41 @@ def test_multi_device_handle_qg_frame_producer():
         res.append(eng.eval())
         eng.close(); qg.close()
     assert np.array_equal(res[0], res[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# fused SPECTRAL RK4 steppers (one launch per run of steps) against the composed route
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx", [32, 64, 128])
+@pytest.mark.parametrize("scheme", ["rk4_packet", "rk4_xka"])
+@pytest.mark.parametrize("flow", ["psi", "planes", "two-frame"])
+def test_spectral_fused_rk4_equals_the_composed_launches(nx, scheme, flow):
+    """step_packet / step_packet_xka in SPECTRAL mode: the fused kernel (five contractions + the RK4 update with the packet
+    in registers, ONE launch) against the composed route of round 1 (five EVAL launches + five glue kernels per step,
+    swrt_set_tuning flag 4).  Same contraction order, so the evaluations agree to the last bits; the stage arithmetic is
+    compiled in two places, hence 1e-13 rather than bit equality."""
+    xka = scheme == "rk4_xka"
+    if xka and flow == "psi":
+        pytest.skip("step_packet_xka needs the H plane (planes upload)")
+    w = W.make_workload("C4" if flow == "two-frame" else "C5", n_packets=1203, nx=nx)
+    sch = S.SCHEME_RK4_XKA if xka else S.SCHEME_RK4_PACKET
+    m = 3
+    a0, da = (0.5 / m, 1.0 / m) if flow == "two-frame" else (0.0, 0.0)
+    res, launches = [], []
+    for fused in (True, False):
+        eng = _engine(w, S.MODE_SPECTRAL, with_h=(xka or flow == "planes"))
+        eng.set_tuning(unfused_rk4=not fused)
+        eng.set_packets(w.x, w.y, w.k, w.l, np.linspace(0.5, 2.0, w.n_packets))
+        eng.step(sch, w.dt, 1, a0, 0.0)                       # warm: stacks packed
+        n0 = eng.launch_count(reset=True)
+        eng.step(sch, w.dt, m, a0, da)
+        launches.append(eng.launch_count())
+        res.append(np.stack(eng.get_packets(with_a=True)))
+        eng.close()
+    assert np.isfinite(res[0]).all()
+    scale = np.abs(res[1]).max(axis=1, keepdims=True)
+    assert (np.abs(res[0] - res[1]) / scale).max() < 1e-13
+    assert launches[0] == (3 if flow == "two-frame" else 1)     # one packet kernel (+ the two multi-blends of a two-frame run)
+    assert launches[1] >= 9 * m                                  # 4-5 evaluations + 4 stage kernels + the final update, per step
+    if xka:
+        assert np.abs(res[0][4] - np.linspace(0.5, 2.0, w.n_packets)).max() > 0
