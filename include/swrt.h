@@ -240,7 +240,9 @@ int     swrt_set_stream(swrt_handle* h, void* cuda_stream);
  * waits for it and returns the elapsed milliseconds (<0 on error)                               */
 int     swrt_timer_start(swrt_handle* h);
 double  swrt_timer_stop(swrt_handle* h);
-/* tuning knobs: 1 or 2 m-tiles per warp in the spectral kernel (0 = automatic); flags bit 0 = do
+/* tuning knobs: 1 or 2 m-tiles per warp in the spectral kernel (0 = automatic); flags bits 3-4 = where the dense
+ * kernel keeps the x twiddles of a step (0 automatic, 1 rotate in registers, 2 global / L2 table, 3 shared-memory
+ * table with shrunk chunks else global); flags bit 0 = do
  * not use the psi-hat moment contraction (always contract the six planes); flags bit 1 (LAGRANGE6) =
  * blend two flow frames on the grid before the gather (half the gathers) instead of interpolating both
  * frames and blending the results as interpolate_U.m:19-23 does (the default, bit-faithful); flags
@@ -253,9 +255,10 @@ int     swrt_set_tuning(swrt_handle* h, int mtiles, int flags);
 int     swrt_contracted_planes(const swrt_handle* h);
 /* diagnostic, host-only (no device needed): the launch geometry the dense kernel would use for an
  * nx^2 grid contracting `nplanes` planes with `mtiles` m-tiles per warp.  out[0..9] = n-tiles per
- * pass, ky passes, k-steps per pass (padded), k-steps per chunk, ring stages, chunk bytes, twiddle
- * table on (1) / off (0), twiddle-table bytes, dynamic shared memory bytes per CTA, packed-stack
- * bytes per flow slot.  Returns SWRT_OK or SWRT_ERR_ARG.                                          */
+ * pass, ky passes, k-steps per pass (padded), k-steps per chunk, ring stages, chunk bytes, x twiddles
+ * (0 = rotated in registers, 1 = per-step table in shared memory, 2 = per-step table in a per-CTA
+ * global / L2 scratch), shared-memory twiddle-table bytes, dynamic shared memory bytes per CTA,
+ * packed-stack bytes per flow slot.  Returns SWRT_OK or SWRT_ERR_ARG.                             */
 int     swrt_spectral_geometry(int nx, int nplanes, int mtiles, int64_t out[10]);
 /* roofline probe for the gather-bound modes (LAGRANGE6, NUFFT): the rate (GB/s of useful bytes) at which the device serves
  * scattered 64-byte segments of an L2-resident table of `table_bytes` (power of two, e.g. 16 MiB = the 512^2 NUFFT fine

@@ -166,7 +166,7 @@ void launch_axpby(double* out, const double* a, const double* b, double wa, doub
     axpby_kernel<<<(unsigned)nb, bs, 0, st>>>(out, a, b, wa, wb, n);
 }
 
-PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
+PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles, int twiddle_pref) {
     PackGeom g{};
     g.nx = nx; g.nkx = nx - 1; g.nky = nx / 2; g.kmax = nx / 2 - 1;
     g.npl = npl;
@@ -198,7 +198,13 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     // larger grids rotate in registers.
     constexpr size_t kSmemBudget = 216 * 1024;
     auto atab_fits = [&]() { return (size_t)g.ksteps * 32 * 8 * kConsumerWarps + 3 * g.chunk_doubles * 8 <= kSmemBudget; };
-    bool want_atab = mtiles == 1 && kCtasPerSm == 1;
+    // twiddle_pref: 0 = automatic (shared-memory table when it fits beside a ring of full-size chunks, else the global / L2
+    // table), 1 = rotate in registers, 2 = global table wherever a table is possible, 3 = shared-memory table even with
+    // shrunk chunks (the round-1 layout at 256^2), else the global one.  Measured (profiles/README.md, TFLOP/s, rotation /
+    // shared / global): 128^2 31.1 / 32.2 / 31.6; 256^2 32.9 / 33.9 (24 KB chunks) / 34.2; 512^2 33.4 / does not fit / 34.8.
+    bool want_atab = mtiles == 1 && kCtasPerSm == 1 && twiddle_pref != 1 && twiddle_pref != 2;
+    const bool want_global = mtiles == 1 && kCtasPerSm == 1 && twiddle_pref != 1;
+    const bool shrink_for_table = twiddle_pref == 3;
     int kc_forced = 0;
 #ifdef SWRT_DEV_TUNING      // developer experiments only: the shipped library reads no environment variables
     if (const char* e = getenv("SWRT_ATAB")) want_atab = want_atab && atoi(e) != 0;
@@ -210,14 +216,15 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
     } else {
         layout(kc0);
         g.atab = want_atab && atab_fits();
-        if (want_atab && !g.atab && kc0 > 4) {
+        if (want_atab && !g.atab && kc0 > 4 && shrink_for_table) {
             layout(4);
             g.atab = atab_fits();
             if (!g.atab) layout(kc0);
         }
     }
+    if (!g.atab && want_global) g.atab = 2;       // table in the per-CTA global scratch: full-size chunks, full-size ring
     const size_t chunk_bytes = g.chunk_doubles * 8;
-    const size_t ring_budget = g.atab ? (kSmemBudget - (size_t)g.ksteps * 32 * 8 * kConsumerWarps) : (size_t)(200 * 1024 / kCtasPerSm);
+    const size_t ring_budget = g.atab == 1 ? (kSmemBudget - (size_t)g.ksteps * 32 * 8 * kConsumerWarps) : (size_t)(200 * 1024 / kCtasPerSm);
     g.nstages = (int)(ring_budget / chunk_bytes);
     if (g.nstages > 8) g.nstages = 8;
     if (g.nstages < 3) g.nstages = 3;
@@ -241,7 +248,7 @@ PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles) {
 
 size_t spectral_smem_bytes(const PackGeom& g) {
     // ring | full/empty barriers (padded to 128 bytes) | twiddle table
-    return (size_t)g.nstages * g.chunk_doubles * 8 + 128 + (g.atab ? (size_t)g.ksteps * 32 * 8 * kConsumerWarps : 0);
+    return (size_t)g.nstages * g.chunk_doubles * 8 + 128 + (g.atab == 1 ? (size_t)g.ksteps * 32 * 8 * kConsumerWarps : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -251,7 +258,10 @@ size_t spectral_smem_bytes(const PackGeom& g) {
 // (integer kx); the six velocity/gradient planes of SpectralScheme.m:18-25 are assembled in stage 2:
 //   u = kap ky Im[T G0], v = kap Re[T G1], ux = kap^2 ky Im[T G1], uy = kap^2 ky^2 Re[T G0],
 //   vx = kap^2 Re[T G2], vy = -ux   (T = e^{i ky ty}),  which halves the DMMA work (6 nx^2 flops).
-template <int NPL, int G, int MT, int MODE, bool PSI, bool ATAB>
+// ATAB: 0 = x twiddles rotated in registers inside the k-loop; 1 = tabulated once per step in shared memory; 2 = tabulated
+// once per step in a per-CTA global scratch (L2-resident; grids whose table does not fit in shared memory), read back
+// with plain loads one unrolled body ahead -- in both table forms the k-loop holds no fp64 instruction but the DMMAs.
+template <int NPL, int G, int MT, int MODE, bool PSI, int ATAB>
 __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(const SpecArgs a) {
     static_assert(!ATAB || MT == 1, "the twiddle table is laid out for one m-tile per warp");
     constexpr int NT = NPL * G;
@@ -271,7 +281,9 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // this lane's column of the warp's twiddle table: sA[s * 32] = A element of k-step s (written and read by this lane only)
-    double* const sA = reinterpret_cast<double*>(smem_raw + (size_t)nstages * chunk_bytes + 128) + (size_t)warp * g.ksteps * 32 + lane;
+    double* sA;
+    if constexpr (ATAB == 2) sA = a.twid + ((size_t)blockIdx.x * kConsumerWarps + warp) * g.ksteps * 32 + lane;
+    else sA = reinterpret_cast<double*>(smem_raw + (size_t)nstages * chunk_bytes + 128) + (size_t)warp * g.ksteps * 32 + lane;
     const long long ntiles = (a.n + TILE_P - 1) / TILE_P;
     const int nevals = (MODE == SPEC_LEAPFROG) ? a.nsteps : 1;
 
@@ -438,6 +450,11 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                     ap = nap; aq = naq; bp = nbp; bq = nbq;
                 }
             }
+            double apf[kKUnroll];                  // ATAB 2: the A elements of the next unrolled body, in flight from L2
+            if constexpr (ATAB == 2) {
+#pragma unroll
+                for (int su = 0; su < kKUnroll; su++) apf[su] = sA[su * 32];
+            }
             // ---- passes over ky blocks -----------------------------------------------------
             for (int pass = 0; pass < kyp_passes; pass++) {
                 double acc[MT][NT][2];
@@ -469,10 +486,18 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
                         // probe the NEXT chunk's full barrier while this chunk's last k-steps run, so the
                         // hand-over at the chunk boundary does not wait on the barrier round trip
                         if (s0 + kKUnroll >= g.kc) ready = mbar_test(&full_bar[nstage], nphase);
+                        double acur[kKUnroll];
+                        if constexpr (ATAB == 2) {
+                            int nb = ch * g.kc + s0 + kKUnroll;          // next body of this pass; the table serves every pass
+                            if (nb >= g.ksteps) nb = 0;
+#pragma unroll
+                            for (int su = 0; su < kKUnroll; su++) { acur[su] = apf[su]; apf[su] = sA[(nb + su) * 32]; }
+                        }
 #pragma unroll
                         for (int su = 0; su < kKUnroll; su++) {
                             const int s = s0 + su;
-                            if constexpr (ATAB) tp_[0] = sAc[s * 32];
+                            if constexpr (ATAB == 1) tp_[0] = sAc[s * 32];
+                            if constexpr (ATAB == 2) tp_[0] = acur[su];
 #pragma unroll
                             for (int tp = 0; tp < HALF_NT; tp++) {
                                 double2 b = sB[(s * HALF_NT + tp) * 32];
@@ -599,7 +624,7 @@ __global__ void __launch_bounds__(kSpecThreads, kCtasPerSm) spectral_kernel(cons
     }
 }
 
-template <int NPL, int G, int MT, int MODE, bool PSI, bool ATAB>
+template <int NPL, int G, int MT, int MODE, bool PSI, int ATAB>
 static cudaError_t launch_inst2(const SpecArgs& a, int num_sms, cudaStream_t st) {
     constexpr int TILE_P = kConsumerWarps * 8 * MT;
     size_t smem = spectral_smem_bytes(a.g);
@@ -616,9 +641,10 @@ static cudaError_t launch_inst2(const SpecArgs& a, int num_sms, cudaStream_t st)
 template <int NPL, int G, int MT, int MODE, bool PSI>
 static cudaError_t launch_inst(const SpecArgs& a, int num_sms, cudaStream_t st) {
     if constexpr (MT == 1) {
-        if (a.g.atab) return launch_inst2<NPL, G, MT, MODE, PSI, true>(a, num_sms, st);
+        if (a.g.atab == 1) return launch_inst2<NPL, G, MT, MODE, PSI, 1>(a, num_sms, st);
+        if (a.g.atab == 2 && a.twid) return launch_inst2<NPL, G, MT, MODE, PSI, 2>(a, num_sms, st);
     }
-    return launch_inst2<NPL, G, MT, MODE, PSI, false>(a, num_sms, st);
+    return launch_inst2<NPL, G, MT, MODE, PSI, 0>(a, num_sms, st);
 }
 
 template <int NPL, int G, int MT>

@@ -68,7 +68,7 @@ __device__ __forceinline__ void ring_advance(Ring& r) {              // all lane
 // One evaluation of NPL stack planes at (px, py) for this lane's packet row: F[0..NF) on every lane of the quad.
 // PSI: the stack holds the psi-hat moment planes and the six velocity / gradient planes are assembled (see
 // spectral_kernels.cu); um = mean shear added to u.
-template <int NPL, int G, bool PSI, bool ATAB>
+template <int NPL, int G, bool PSI, int ATAB>
 __device__ __forceinline__ void contract(Ring& r, const PackGeom& g, double px, double py, double dx, double nxd, double inv_nx,
                                          int lane, double kappa, double um, double* F) {
     constexpr int NT = NPL * G;
@@ -116,6 +116,11 @@ __device__ __forceinline__ void contract(Ring& r, const PackGeom& g, double px, 
             ap = nap; aq = naq; bp = nbp; bq = nbq;
         }
     }
+    double apf[kKUnroll];                          // ATAB 2: the A elements of the next unrolled body, in flight from L2
+    if constexpr (ATAB == 2) {
+#pragma unroll
+        for (int su = 0; su < kKUnroll; su++) apf[su] = r.sA[su * 32];
+    }
     const int chunks_per_pass = g.ksteps / g.kc;
     for (int pass = 0; pass < g.npass; pass++) {
         double acc[NT][2];
@@ -134,10 +139,18 @@ __device__ __forceinline__ void contract(Ring& r, const PackGeom& g, double px, 
             if (nstage == r.nstages) { nstage = 0; nphase ^= 1; }
             for (int s0 = 0; s0 < g.kc; s0 += kKUnroll) {
                 if (s0 + kKUnroll >= g.kc) r.ready = mbar_test(&r.full_bar[nstage], nphase);
+                double acur[kKUnroll];
+                if constexpr (ATAB == 2) {
+                    int nb = ch * g.kc + s0 + kKUnroll;
+                    if (nb >= g.ksteps) nb = 0;
+#pragma unroll
+                    for (int su = 0; su < kKUnroll; su++) { acur[su] = apf[su]; apf[su] = r.sA[(nb + su) * 32]; }
+                }
 #pragma unroll
                 for (int su = 0; su < kKUnroll; su++) {
                     const int s = s0 + su;
-                    if constexpr (ATAB) tp = sAc[s * 32];
+                    if constexpr (ATAB == 1) tp = sAc[s * 32];
+                    if constexpr (ATAB == 2) tp = acur[su];
 #pragma unroll
                     for (int t2 = 0; t2 < HALF_NT; t2++) {
                         const double2 b = sB[(s * HALF_NT + t2) * 32];
@@ -203,7 +216,7 @@ __device__ __forceinline__ void contract(Ring& r, const PackGeom& g, double px, 
 
 // XKA: step_packet_xka (A = u,v,H; B = seven planes at the new position); else step_packet (B first, at the old position;
 // PSIB: B = the three psi-hat moment planes).
-template <bool XKA, bool PSIB, bool ATAB>
+template <bool XKA, bool PSIB, int ATAB>
 __global__ void __launch_bounds__(kSpecThreads, 1) spectral_rk4_kernel(const SpecRk4Args a) {
     constexpr int NPL_A = XKA ? 3 : 2, G_A = XKA ? 8 : 12;
     constexpr int NPL_B = XKA ? 7 : (PSIB ? 3 : 6), G_B = XKA ? 4 : (PSIB ? 8 : 4);
@@ -218,7 +231,8 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_rk4_kernel(const Spe
     r.stage_bytes = a.stage_bytes;
     r.full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)a.nstages * a.stage_bytes);
     r.empty_bar = r.full_bar + a.nstages;
-    r.sA = reinterpret_cast<double*>(smem_raw + (size_t)a.nstages * a.stage_bytes + 128) + (size_t)warp * a.tab_ksteps * 32 + lane;
+    if constexpr (ATAB == 2) r.sA = a.twid + ((size_t)blockIdx.x * kConsumerWarps + warp) * a.tab_ksteps * 32 + lane;
+    else r.sA = reinterpret_cast<double*>(smem_raw + (size_t)a.nstages * a.stage_bytes + 128) + (size_t)warp * a.tab_ksteps * 32 + lane;
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nstages; s++) { mbar_init(&r.full_bar[s], 1); mbar_init(&r.empty_bar[s], kConsumerWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -328,7 +342,7 @@ __global__ void __launch_bounds__(kSpecThreads, 1) spectral_rk4_kernel(const Spe
     }
 }
 
-template <bool XKA, bool PSIB, bool ATAB>
+template <bool XKA, bool PSIB, int ATAB>
 cudaError_t launch_rk4_inst(const SpecRk4Args& a, size_t smem, int num_sms, cudaStream_t st) {
     auto kern = spectral_rk4_kernel<XKA, PSIB, ATAB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -351,15 +365,15 @@ bool spectral_rk4_geometry(SpecRk4Args& a, size_t* smem_bytes) {
     a.stage_bytes = (uint32_t)cb;
     a.tab_ksteps = a.gA.ksteps > a.gB.ksteps ? a.gA.ksteps : a.gB.ksteps;
     const size_t table = (size_t)a.tab_ksteps * 32 * 8 * kConsumerWarps;
-    a.atab = (a.gA.atab && a.gB.atab && table + 3 * cb <= kSmemBudget) ? 1 : 0;
-    const size_t ring_budget = a.atab ? kSmemBudget - table : (size_t)200 * 1024;
+    a.atab = (a.gA.atab == 1 && a.gB.atab == 1 && table + 3 * cb <= kSmemBudget) ? 1 : ((a.gA.atab && a.gB.atab) ? 2 : 0);
+    const size_t ring_budget = a.atab == 1 ? kSmemBudget - table : (size_t)200 * 1024;
     int ns = (int)(ring_budget / cb);
     if (ns > 8) ns = 8;
     if (ns < 3) ns = 3;
     a.nstages = ns;
     a.lag = ns - 1 > 4 ? 4 : ns - 1;
     if (a.lag < 1) a.lag = 1;
-    *smem_bytes = (size_t)ns * cb + 128 + (a.atab ? table : 0);
+    *smem_bytes = (size_t)ns * cb + 128 + (a.atab == 1 ? table : 0);
     return *smem_bytes <= 227 * 1024;
 }
 
@@ -372,9 +386,17 @@ cudaError_t launch_spectral_rk4(const SpecRk4Args& a_in, bool xka, int num_sms, 
     const bool ok = xka ? (a.gA.npl == 3 && a.gA.G == 8 && a.gB.npl == 7 && a.gB.G == 4 && !a.psiB)
                         : (a.gA.npl == 2 && a.gA.G == 12 && (a.psiB ? (a.gB.npl == 3 && a.gB.G == 8) : (a.gB.npl == 6 && a.gB.G == 4)));
     if (!ok) return cudaErrorInvalidValue;
-    if (xka) return a.atab ? launch_rk4_inst<true, false, true>(a, smem, num_sms, st) : launch_rk4_inst<true, false, false>(a, smem, num_sms, st);
-    if (a.psiB) return a.atab ? launch_rk4_inst<false, true, true>(a, smem, num_sms, st) : launch_rk4_inst<false, true, false>(a, smem, num_sms, st);
-    return a.atab ? launch_rk4_inst<false, false, true>(a, smem, num_sms, st) : launch_rk4_inst<false, false, false>(a, smem, num_sms, st);
+    if (a.atab == 2 && !a.twid) a.atab = 0;
+#define SWRT_RK4_DISPATCH(XKA_, PSI_)                                                                  \
+    switch (a.atab) {                                                                                 \
+        case 1: return launch_rk4_inst<XKA_, PSI_, 1>(a, smem, num_sms, st);                          \
+        case 2: return launch_rk4_inst<XKA_, PSI_, 2>(a, smem, num_sms, st);                          \
+        default: return launch_rk4_inst<XKA_, PSI_, 0>(a, smem, num_sms, st);                         \
+    }
+    if (xka) { SWRT_RK4_DISPATCH(true, false) }
+    if (a.psiB) { SWRT_RK4_DISPATCH(false, true) }
+    SWRT_RK4_DISPATCH(false, false)
+#undef SWRT_RK4_DISPATCH
 }
 
 }  // namespace swrt

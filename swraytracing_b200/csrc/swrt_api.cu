@@ -96,6 +96,8 @@ struct swrt_handle {
     // fused runs on a time-dependent flow: the operands (packed stacks / fine grids / Lagrange grids) of up to
     // kMaxFusedBlend steps, pre-blended at alpha_j and stored back to back
     double* arena = nullptr; size_t arena_cap = 0;
+    double* twid = nullptr; size_t twid_cap = 0;          // global twiddle-table scratch of the dense kernel (atab == 2)
+    int twiddle_pref = 0;                                 // swrt_set_tuning bits 3-4
     double* arena_h = nullptr; size_t arena_h_cap = 0;      // NUFFT (u,v,H,0) grids
     // host staging of swrt_step_host / swrt_set_packets / swrt_get_packets (pinned ring + copy streams)
     struct Stager* stager = nullptr;
@@ -173,6 +175,20 @@ struct DevTmp {
     cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
 };
 
+// per-CTA global scratch of the dense kernel's twiddle table (PackGeom.atab == 2): one double per lane per k-step per warp
+int ensure_twid(swrt_handle* h, const PackGeom& g, double** out) {
+    *out = nullptr;
+    if (g.atab != 2) return SWRT_OK;
+    const size_t need = (size_t)h->num_sms * kCtasPerSm * kConsumerWarps * g.ksteps * 32;
+    if (need > h->twid_cap) {
+        dfree(h->twid); h->twid_cap = 0;
+        CU(h, cudaMalloc(&h->twid, need * sizeof(double)));
+        h->twid_cap = need;
+    }
+    *out = h->twid;
+    return SWRT_OK;
+}
+
 int pick_mtiles(const swrt_handle* h, int64_t n) {
     if (h->mtiles == 1 || h->mtiles == 2) return h->mtiles;
     (void)n;
@@ -208,10 +224,10 @@ int ensure_packets(swrt_handle* h, int64_t n) {
 // ---- spectral stacks ---------------------------------------------------------------------------
 int ensure_stack(swrt_handle* h, int sub, int slot, int mtiles) {
     Stack& s = h->stacks[sub];
-    const PackGeom want = make_geom(h->p.nx, kSubsetN[sub], kSubsetIds[sub], mtiles);
+    const PackGeom want = make_geom(h->p.nx, kSubsetN[sub], kSubsetIds[sub], mtiles, h->twiddle_pref);
     // a packed stack is only valid for the exact geometry it was packed with (tile grouping, chunking, padding)
     if (!s.geom_ready || s.g.G != want.G || s.g.kc != want.kc || s.g.ksteps != want.ksteps || s.g.npass != want.npass ||
-        s.g.total_doubles != want.total_doubles) {
+        s.g.total_doubles != want.total_doubles || s.g.atab != want.atab) {
         s.g = want;
         s.geom_ready = true;
         for (int i = 0; i < 2; i++) { dfree(s.slot[i]); s.slot_valid[i] = false; }
@@ -311,6 +327,7 @@ int eval_dev(swrt_handle* h, int sub, double alpha, int64_t n, const double* xd,
         for (int c = 0; c < kSubsetN[sub]; c++) a.out[c] = out[c];
         a.dx = h->p.L / h->p.nx; a.nxd = (double)h->p.nx;
         a.inv_nx = (h->p.nx & (h->p.nx - 1)) == 0 ? 1.0 / h->p.nx : 0.0;
+        if ((rc = ensure_twid(h, a.g, &a.twid))) return rc;
         CU(h, launch_spectral(a, SPEC_EVAL, mt, h->num_sms, h->stream));
         h->launches++;
         return SWRT_OK;
@@ -652,7 +669,7 @@ int swrt_destroy(swrt_handle* h) {
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     stager_free(h);
-    dfree(h->arena); dfree(h->arena_h); dfree(h->red_dev);
+    dfree(h->arena); dfree(h->arena_h); dfree(h->red_dev); dfree(h->twid);
     dfree(h->x); dfree(h->y); dfree(h->k); dfree(h->l); dfree(h->a);
     for (int s = 0; s < 2; s++) {
         for (auto& p : h->planes[s]) dfree(p);
@@ -1138,6 +1155,15 @@ static int launch_run(swrt_handle* h, const RunOps& r, int64_t lo, int64_t cnt) 
     if (mode == SWRT_MODE_SPECTRAL && r.scheme != SWRT_SCHEME_LEAPFROG) {
         SpecRk4Args a = r.ra;
         a.n = cnt; a.x += lo; a.y += lo; a.k += lo; a.l += lo; a.a += lo;
+        {   // joint geometry decides where the twiddle table lives; the global form needs the handle's scratch
+            SpecRk4Args probe = a; size_t smem = 0;
+            spectral_rk4_geometry(probe, &smem);
+            if (probe.atab == 2) {
+                PackGeom tg = a.gA; tg.atab = 2; tg.ksteps = probe.tab_ksteps;
+                int rc2 = ensure_twid(h, tg, &a.twid);
+                if (rc2) return rc2;
+            }
+        }
         CU(h, launch_spectral_rk4(a, r.xka, h->num_sms, h->stream));
     } else if (mode == SWRT_MODE_SPECTRAL) {
         SpecArgs a = r.sa;
@@ -1148,6 +1174,7 @@ static int launch_run(swrt_handle* h, const RunOps& r, int64_t lo, int64_t cnt) 
         cudaMemset(tr, 0, 8 * 640 * 8);
         a.trace = tr;
 #endif
+        { int rc2 = ensure_twid(h, a.g, &a.twid); if (rc2) return rc2; }
         CU(h, launch_spectral(a, SPEC_LEAPFROG, r.mt, h->num_sms, h->stream));
 #ifdef SWRT_TRACE
         {
@@ -2491,6 +2518,7 @@ int swrt_set_tuning(swrt_handle* h, int mtiles, int flags) {
     h->disable_psi = (flags & 1) != 0;
     h->preblend_grid = (flags & 2) != 0;
     h->unfused_rk4 = (flags & 4) != 0;
+    h->twiddle_pref = (flags >> 3) & 3;
     return SWRT_OK;
 }
 
@@ -2518,7 +2546,7 @@ int swrt_spectral_geometry(int nx, int nplanes, int mtiles, int64_t out[10]) {
     const PackGeom g = make_geom(nx, nplanes, ids, mtiles);
     out[0] = g.NT; out[1] = g.npass; out[2] = g.ksteps; out[3] = g.kc; out[4] = g.nstages;
     out[5] = (int64_t)(g.chunk_doubles * 8); out[6] = g.atab;
-    out[7] = g.atab ? (int64_t)g.ksteps * 32 * 8 * kConsumerWarps : 0;
+    out[7] = g.atab == 1 ? (int64_t)g.ksteps * 32 * 8 * kConsumerWarps : 0;
     out[8] = (int64_t)spectral_smem_bytes(g);
     out[9] = (int64_t)(g.total_doubles * 8);
     return SWRT_OK;

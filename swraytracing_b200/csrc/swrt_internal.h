@@ -37,14 +37,14 @@ struct PackGeom {
     int nstages;
     int lag;              // a stage is refilled `lag` chunks after warp 0 released it
     int desync_ns;        // start-up skew of warps 4..7 (0 = none)
-    int atab;             // 1: the x twiddles of a step are tabulated in shared memory (A fragments by LDS.64), else
-                          //    rotated in registers inside the k-loop
+    int atab;             // x twiddles of a step: 0 = rotated in registers inside the k-loop, 1 = tabulated in shared memory
+                          //    (A fragments by LDS.64), 2 = tabulated in a per-CTA global scratch (L2), prefetched by LDG
     size_t chunk_doubles; // kc * NT * 32
     size_t total_doubles; // npass * ksteps * NT * 32
     int plane_ids[kMaxPlanes];   // which of the 7 source planes each stack plane is
 };
 
-PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles);
+PackGeom make_geom(int nx, int npl, const int* plane_ids, int mtiles, int twiddle_pref = 0);
 
 // one source slot: complex planes on the device, [plane][ky][kx+kmax] as double2 (kx fastest)
 void launch_pack(const PackGeom& g, const double2* const* planes_dev /*[kNumSrcPlanes] device ptrs (host array)*/,
@@ -76,6 +76,7 @@ struct SpecArgs {
     int j0;
     int nstack;             // LEAPFROG: `stack` holds nstack (= nsteps) consecutive stacks, one per fused step (a
                             //   time-dependent flow pre-blended at al_j for every step of the launch); 0/1 = one stack
+    double* twid;           // atab == 2: per-CTA twiddle scratch, gridDim.x * 8 warps * ksteps * 32 doubles
     unsigned long long* trace;   // developer timeline buffer (only read when built with -DSWRT_TRACE)
 };
 
@@ -95,6 +96,7 @@ struct SpecRk4Args {
     int nsteps;
     int nstack;             // > 1: one pre-blended pair of stacks per step (time-dependent flow), stored back to back
     bool psiB;              // stackB = psi-hat moment planes
+    double* twid;           // per-CTA global twiddle scratch (atab == 2): gridDim.x * 8 warps * tab_ksteps * 32 doubles
     double kappa, u_mean0, u_mean1, alpha0, dalpha;
     int j0;
 };

@@ -402,12 +402,13 @@ class Engine:
             raise SwrtError(-3, "timer failed")
         return ms
 
-    def set_tuning(self, mtiles=0, use_psi_moments=True, preblend_grid=False, unfused_rk4=False):
+    def set_tuning(self, mtiles=0, use_psi_moments=True, preblend_grid=False, unfused_rk4=False, twiddles=0):
         """``preblend_grid`` (LAGRANGE6): blend two frames on the grid before the gather (faster) instead of
         interpolating both frames and blending the results as interpolate_U.m does (default, bit-faithful);
-        ``unfused_rk4`` (SPECTRAL, NUFFT): step_packet* as evaluation + stage launches instead of the fused kernel"""
+        ``unfused_rk4`` (SPECTRAL, NUFFT): step_packet* as evaluation + stage launches instead of the fused kernel;
+        ``twiddles`` (SPECTRAL): 0 automatic, 1 rotate in registers, 2 global (L2) table, 3 shared-memory table else global"""
         self._check(self.lib.swrt_set_tuning(self._h, int(mtiles), (0 if use_psi_moments else 1) | (2 if preblend_grid else 0)
-                                             | (4 if unfused_rk4 else 0)))
+                                             | (4 if unfused_rk4 else 0) | ((int(twiddles) & 3) << 3)))
 
     def contracted_planes(self):
         return int(self.lib.swrt_contracted_planes(self._h))

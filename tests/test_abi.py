@@ -114,14 +114,15 @@ def test_spectral_geometry_fits_shared_memory_for_every_size():
                 assert g["chunk_bytes"] == g["kc"] * g["ntiles"] * 256
                 assert g["stack_bytes"] == g["npass"] * g["ksteps"] * g["ntiles"] * 256
                 assert g["smem_bytes"] == g["nstages"] * g["chunk_bytes"] + 128 + g["table_bytes"]
-                if g["twiddle_table"]:
+                if g["twiddle_table"] == 1:                 # table in shared memory, beside the ring
                     assert mt == 1 and g["table_bytes"] == g["ksteps"] * 32 * 8 * 8
                     seen_on += 1
-                else:
-                    assert g["table_bytes"] == 0
+                else:                                       # 2: table in the global / L2 scratch; 0 (two m-tiles): rotation
+                    assert g["table_bytes"] == 0 and g["twiddle_table"] == (2 if mt == 1 else 0)
                     seen_off += 1
     assert seen_on and seen_off
-    assert spectral_geometry(128, 3, 1)["twiddle_table"] == 1 and spectral_geometry(256, 3, 1)["twiddle_table"] == 1
-    assert spectral_geometry(512, 3, 1)["twiddle_table"] == 0
+    assert spectral_geometry(128, 3, 1)["twiddle_table"] == 1
+    assert spectral_geometry(256, 3, 1)["twiddle_table"] == 2 and spectral_geometry(256, 3, 1)["chunk_bytes"] == 48 * 1024
+    assert spectral_geometry(512, 3, 1)["twiddle_table"] == 2
     lib = S.load_library()
     assert lib.swrt_spectral_geometry(7, 3, 1, (ctypes.c_int64 * 10)()) == -1

@@ -18,12 +18,13 @@ ap.add_argument("--packets", type=int, default=0)
 ap.add_argument("--substeps", type=int, default=2)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--unfused", action="store_true")
+ap.add_argument("--twiddles", type=int, default=0)
 a = ap.parse_args()
 
 w = W.make_workload(a.workload, n_packets=a.packets or None)
 mode = {"spectral": S.MODE_SPECTRAL, "lagrange6": S.MODE_LAGRANGE6, "nufft": S.MODE_NUFFT}[a.mode]
 eng = S.Engine(w.nx, w.L, w.f, w.gH, mode)
-eng.set_tuning(unfused_rk4=a.unfused)
+eng.set_tuning(unfused_rk4=a.unfused, twiddles=a.twiddles)
 if w.scheme == "rk4_xka":
     eng.set_flow_planes_spectral(W.planes_from_psik(w.psik, w.L, w.u_mean, etak=w.extra["etak"]))
 else:
@@ -38,6 +39,10 @@ eng.set_packets(w.x, w.y, w.k, w.l)
 for _ in range(a.reps):
     eng.step(scheme, dt, a.substeps, a0, da)
     ms, nl = eng.last_kernel_ms()
-    print(f"{a.workload} {a.mode}: {w.n_packets} packets x {a.substeps} steps: {ms:.3f} ms in {nl} launch(es) = "
-          f"{w.n_packets * a.substeps / ms * 1e3:.4g} packet-steps/s", flush=True)
+    tf = ""
+    if a.mode == "spectral":
+        pe = {"leapfrog": eng.contracted_planes(), "rk4_packet": eng.contracted_planes() + 6, "rk4_xka": 19}[w.scheme]
+        tf = f" = {eng.work_per_eval(pe) * w.n_packets * a.substeps / ms * 1e-9:.2f} TFLOP/s"
+    print(f"{a.workload} {a.mode} tw={a.twiddles}: {w.n_packets} packets x {a.substeps} steps: {ms:.3f} ms in {nl} launch(es) = "
+          f"{w.n_packets * a.substeps / ms * 1e3:.4g} packet-steps/s{tf}", flush=True)
 eng.close()
