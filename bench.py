@@ -491,10 +491,10 @@ def measure(ctx, name, total_packets, sub, steps, warmup, mode_name, peaks, head
         flops_per_launch = flops_per_packet_step * n_dev * sub
         achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
         peak = peaks["fp64_tflops"]
-        inst = (f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'},"
-                f"{'twiddle-table' if w.nx <= 256 else 'twiddle-rotation'}>" if w.scheme == "leapfrog" else
+        tw = {0: "twiddle-rotation", 1: "twiddle-table(smem)", 2: "twiddle-table(L2)"}[S.engine.spectral_geometry(w.nx, ncontract, 1)["twiddle_table"]]
+        inst = (f"swrt::spectral_kernel<{ncontract},{24 // ncontract},1,LEAPFROG,{'psi' if ncontract == 3 else 'planes'},{tw}>" if w.scheme == "leapfrog" else
                 f"swrt::spectral_rk4_kernel<{'xka' if w.scheme == 'rk4_xka' else 'packet'},{'psi' if (ncontract == 3 and w.scheme != 'rk4_xka') else 'planes'},"
-                f"{'twiddle-table' if w.nx <= 256 else 'twiddle-rotation'}> (fused: 5 contractions + RK4 update per step)")
+                f"{'twiddle-table(smem)' if w.nx <= 128 else 'twiddle-table(L2)'}> (fused: 5 contractions + RK4 update per step)")
         roofline = {"bound": "tensor", "achieved": round(achieved, 3), "peak": round(peak, 3), "unit": "TFLOP/s",
                     "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES.get((name, sub, n)),
                     "kernel": inst + " (fp64 DMMA m8n8k4)", "kernel_ms": round(kernel_ms, 4), "kernel_launches_per_step": nl,
