@@ -182,3 +182,43 @@ def test_device_k2g_matches_matlab_workspace(case):
     name, fk, rows = case
     got = R.k2g(fk)[::int(RSW["row_stride"])]
     assert np.abs(got - rows).max() <= 1e-15, name
+
+
+# ------------------------------------------------------------------------------------------------
+# the PRODUCT's initial condition against the reference's logs, with no oracle in the loop
+# ------------------------------------------------------------------------------------------------
+def test_product_initial_q_reproduces_logged_U0_without_the_oracle():
+    """swraytracing_b200.drivers.initial_q is checked against the reference's printed ``Background velocity`` directly:
+    the spectral kit between q and U0 (g2k.m:5-9, grid_U.m:2-4, k2g.m:5-6 / fulspec.m:10-19) is spelled out here in plain
+    numpy FFT calls, so neither the oracle (whose initial_q has the same text as the product's) nor the device is involved.
+    A wrong phase fill order, seed, mode set (the always-true comparison of qgsw_raytrace.m:202) or normalisation in the
+    product changes the sixth decimal of U0."""
+    from swraytracing_b200 import drivers
+    nx, K_d2 = 256, 3.0
+    kmax = nx // 2 - 1
+    xg = np.linspace(-L / 2, L / 2, nx)
+    X, Y = np.meshgrid(xg, xg)
+    q = drivers.initial_q(X, Y, 1.0, K_d2, np.random.RandomState(146))
+    # g2k.m: fk = fftshift(fft2(fg))/nx^2, rows 2:end (kx = -kmax..kmax), columns kmax+2:end (ky = 0..kmax)
+    qk = (np.fft.fftshift(np.fft.fft2(q)) / nx ** 2)[1:, kmax + 1:]
+    kx = np.arange(-kmax, kmax + 1, dtype=np.float64)[:, None]
+    ky = np.arange(0, kmax + 1, dtype=np.float64)[None, :]
+    psik = -qk / (K_d2 + kx ** 2 + ky ** 2)                       # grid_U.m:2
+
+    def k2g(fk):                                                   # fulspec.m:10-19 + k2g.m:5-6
+        full = np.zeros((nx, nx), dtype=np.complex128)
+        up = fk.copy()
+        up[:kmax, 0] = np.conj(up[:kmax:-1, 0])                    # conjugate-symmetrise the ky = 0 column from its kx > 0 half
+        up[kmax, 0] = up[kmax, 0].real
+        full[1:, kmax + 1:] = up
+        full[1:, 1:kmax + 1] = np.conj(up[::-1, :0:-1])            # the ky < 0 half-plane
+        return (nx ** 2 * np.fft.ifft2(np.fft.ifftshift(full))).real
+
+    u, v = k2g(-1j * ky * psik), k2g(1j * kx * psik)               # grid_U.m:3-4
+    U0 = float(np.sqrt((u * u + v * v).max()))
+    assert _fmt(U0) == 1.013140
+    for row in LOGS:
+        assert _fmt(U0 * row["U_g"]) == row["U0"], row["source"]
+    # and the product's mode set really is the full square: the intended annulus prints a different number
+    q_ring = drivers.initial_q(X, Y, 1.0, K_d2, np.random.RandomState(146), ring=True)
+    assert np.abs(q_ring - q).max() > 1e-3
