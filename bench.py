@@ -75,9 +75,16 @@ def parse():
     return ap.parse_args()
 
 
-def config_for(name, n_gpus, sub):
-    """the `config` object BOTH arms print (so that the driver compares like with like)"""
-    return {"workload": DESCR.get(name, name), "name": name, "substeps_per_step": sub, "n_gpus": n_gpus,
+TOTALS = {"C2": 65536, "C3": 1048576, "C4": 16777216, "C5": 4194304}
+GRID = {"C1": 64, "C2": 128, "C3": 256, "C4": 512, "C5": 256}
+SCHEME = {"C5": "rk4_xka"}
+
+
+def config_for(name, n_gpus, sub, packets_total=0):
+    """the `config` object BOTH arms print, key for key (the driver compares them); what is specific to an arm -- evaluation
+    mode, sharding, L2 policy -- goes under "arm" """
+    return {"workload": DESCR.get(name, name), "name": name, "nx": GRID.get(name), "packets_total": packets_total or TOTALS.get(name),
+            "scheme": SCHEME.get(name, "leapfrog"), "substeps_per_step": sub, "n_gpus": n_gpus,
             "field": "full-spectrum random-phase QG streamfunction (every (kx,ky) non-zero)", "histogram_bins": 299}
 
 
@@ -246,7 +253,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": config_for(args.workload, args.gpus, sub),
+            "config": config_for(args.workload, args.gpus, sub, args.packets),
+            "arm": {"impl": "C port of the reference's own path (oracle/swrt_oracle.c), OpenMP", "sample_packets": w.n_packets},
             "note": "the reference's own CPU path (gridded planes + 6x6 Lagrange interpolate, both frames blended) restated in C with OpenMP; "
                     "the MATLAB original cannot run here (it sustains ~1e3 packet-steps/s, SURVEY.md 6).  Host-side throughput is "
                     "independent of the GPU count.",
@@ -524,8 +532,9 @@ def measure(ctx, name, total_packets, sub, steps, warmup, mode_name, peaks, head
                     "hbm_bytes_per_packet_step": 64.0 / sub}
 
     res = {"value": value, "unit": UNIT, "ms_per_step": total_ms / steps, "steps": steps, "scaling": "weak" if weak else "strong",
-           "config": dict(config_for(name, ctx.n_gpus, sub), packets_total=n_total, packets_per_gpu=-(-n_total // ctx.n_gpus), nx=w.nx,
-                          mode=mode_name.upper(), scheme=w.scheme, l2="flushed between timed steps (256 MiB write per device)"),
+           "config": config_for(name, ctx.n_gpus, sub, 0 if weak else n_total),
+           "arm": {"mode": mode_name.upper(), "packets_this_run": n_total, "packets_per_gpu": -(-n_total // ctx.n_gpus),
+                   "l2": "flushed between timed steps (256 MiB write per device)"},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n, "ms_per_step": e2e_ms,
                    "host_buffers": "pinned", "call": "swrt_step_host (one C-ABI call: upload, steps, download)",
                    "pageable": {"value": e2e_page_value, "unit": UNIT, "ms_per_step": e2e_page_ms,
@@ -604,8 +613,9 @@ def main():
         line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": dict(head["config"], parallelism=(f"one process, multi-device handle (ngpu = {ctx.n_gpus}), in-library NCCL" if ctx.single
-                                                            else f"one process per GPU (torchrun), packets sharded x{ctx.n_gpus}, flow replicated")),
+                "config": head["config"],
+                "arm": dict(head["arm"], parallelism=(f"one process, multi-device handle (ngpu = {ctx.n_gpus}), in-library NCCL" if ctx.single
+                                                      else f"one process per GPU (torchrun), packets sharded x{ctx.n_gpus}, flow replicated")),
                 "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "clocks": head.get("clocks"),
                 "wall_s_timed_region": head["wall_s_timed_region"], "histogram_total": head["histogram_total"],
                 "peaks_measured": {"fp64_matmul_tflops": round(peaks["fp64_tflops"], 3), "gather_probe_gbs": round(peaks["gather_gbs"], 1),

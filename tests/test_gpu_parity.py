@@ -1242,6 +1242,7 @@ def test_bench_gpu_arm_prints_one_contract_line():
         assert key in d, key
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "f64" and d["higher_is_better"] is True and d["scaling"] == "strong"
     assert d["config"]["name"] == "C4" and d["config"]["nx"] == 512 and d["config"]["packets_total"] == 9472
+    assert d["arm"]["mode"] == "SPECTRAL" and d["arm"]["packets_per_gpu"] == 9472
     assert d["value"] > 0 and d["gpu_launches"] >= 3 * 3
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 4 * 8 * 9472 == d["e2e"]["d2h_bytes_per_step"]
     assert d["e2e"]["pageable"]["value"] > 0
