@@ -12,7 +12,7 @@ ORACLE    := oracle/build/liboracle.so
 
 all: $(LIB) $(ORACLE)
 
-$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/swrt_internal.h $(CSRC)/spectral_common.cuh include/swrt.h
+$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/swrt_internal.h $(CSRC)/spectral_common.cuh $(wildcard $(CSRC)/*.inc) include/swrt.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

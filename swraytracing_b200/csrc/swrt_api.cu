@@ -1234,296 +1234,7 @@ static int step_impl(swrt_handle* h, int scheme, double dt, int nsteps, double a
     return SWRT_OK;
 }
 
-// ---- host staging: pinned ring + helper threads -------------------------------------------------
-// Callers (MATLAB / Octave mxArrays, numpy arrays) hand ordinary pageable memory.  cudaMemcpyAsync on pageable
-// memory is a synchronous, single-threaded staged copy; instead the packet range is cut into chunks, helper threads copy
-// chunk c between the caller's arrays and a pinned ring while the DMA engines move chunk c-1 and (swrt_step_host) the
-// SMs advance chunk c-1: upload, compute and download overlap chunk by chunk.
-namespace {
-
-class CopyPool {          // process-wide helper threads for the staging copies
-public:
-    static CopyPool& get() { static CopyPool p; return p; }
-    // dst <- src (bytes), asynchronously; *pending is decremented when done
-    void submit(void* dst, const void* src, size_t bytes, std::atomic<int>* pending) {
-        pending->fetch_add(1, std::memory_order_relaxed);
-        if (threads_.empty()) { memcpy(dst, src, bytes); pending->fetch_sub(1, std::memory_order_release); return; }
-        { std::lock_guard<std::mutex> lk(mu_); q_.push_back({dst, src, bytes, pending}); }
-        cv_.notify_one();
-    }
-    // the calling thread helps until *pending reaches zero
-    void wait(std::atomic<int>* pending) {
-        while (pending->load(std::memory_order_acquire) > 0) {
-            Job j;
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (q_.empty()) { j.bytes = 0; j.pending = nullptr; }
-                else { j = q_.front(); q_.pop_front(); }
-            }
-            if (j.pending) { memcpy(j.dst, j.src, j.bytes); j.pending->fetch_sub(1, std::memory_order_release); }
-            else std::this_thread::yield();
-        }
-    }
-    int helpers() const { return (int)threads_.size(); }
-private:
-    struct Job { void* dst; const void* src; size_t bytes; std::atomic<int>* pending; };
-    CopyPool() {
-        // helpers + the calling thread = copy lanes: half the hardware threads, at most eight lanes (one lane moves
-        // ~6-10 GB/s; a PCIe 5 x16 link wants ~50 GB/s in each direction).  SWRT_COPY_THREADS overrides the helper count.
-        const int hw = (int)std::thread::hardware_concurrency();
-        int n = hw / 2 - 1;
-        if (n > 7) n = 7;
-        if (n < 1) n = 1;
-        if (const char* e = getenv("SWRT_COPY_THREADS")) n = atoi(e);
-        if (hw > 0 && n > hw - 1) n = hw - 1;
-        if (n < 0) n = 0;
-        for (int i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
-    }
-    ~CopyPool() {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
-        cv_.notify_all();
-        for (auto& t : threads_) t.join();
-    }
-    void loop() {
-        for (;;) {
-            Job j;
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
-                if (q_.empty()) return;
-                j = q_.front(); q_.pop_front();
-            }
-            memcpy(j.dst, j.src, j.bytes);
-            j.pending->fetch_sub(1, std::memory_order_release);
-        }
-    }
-    std::vector<std::thread> threads_;
-    std::mutex mu_;
-    std::condition_variable cv_;
-    std::deque<Job> q_;
-    bool stop_ = false;
-};
-
-constexpr int kRing = 3;       // ring slots per direction
-
-}  // namespace
-
-struct Stager {
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    double* pin_in = nullptr; double* pin_out = nullptr;   // kRing slots x 5 arrays x chunk_cap doubles
-    int64_t chunk_cap = 0;
-    cudaEvent_t ev_h2d[kRing] = {}, ev_k[kRing] = {}, ev_d2h[kRing] = {}, ev_all = nullptr;
-    std::atomic<int> out_pending[kRing];
-    std::atomic<int> in_pending;
-    Stager() { for (auto& a : out_pending) a.store(0); in_pending.store(0); }
-};
-
-namespace {
-
-void stager_free(swrt_handle* h) {
-    Stager* s = h->stager;
-    if (!s) return;
-    for (int i = 0; i < kRing; i++) CopyPool::get().wait(&s->out_pending[i]);
-    if (s->pin_in) cudaFreeHost(s->pin_in);
-    if (s->pin_out) cudaFreeHost(s->pin_out);
-    for (int i = 0; i < kRing; i++) {
-        if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
-        if (s->ev_k[i]) cudaEventDestroy(s->ev_k[i]);
-        if (s->ev_d2h[i]) cudaEventDestroy(s->ev_d2h[i]);
-    }
-    if (s->ev_all) cudaEventDestroy(s->ev_all);
-    if (s->s_in) cudaStreamDestroy(s->s_in);
-    if (s->s_out) cudaStreamDestroy(s->s_out);
-    delete s;
-    h->stager = nullptr;
-}
-
-int stager_init(swrt_handle* h, int64_t chunk) {
-    if (!h->stager) {
-        Stager* s = new (std::nothrow) Stager();
-        REQUIRE(h, s, SWRT_ERR_ALLOC, "out of host memory");
-        h->stager = s;
-        CU(h, cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
-        CU(h, cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < kRing; i++) {
-            CU(h, cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming));
-            CU(h, cudaEventCreateWithFlags(&s->ev_k[i], cudaEventDisableTiming));
-            CU(h, cudaEventCreateWithFlags(&s->ev_d2h[i], cudaEventDisableTiming));
-        }
-        CU(h, cudaEventCreateWithFlags(&s->ev_all, cudaEventDisableTiming));
-    }
-    Stager* s = h->stager;
-    if (chunk > s->chunk_cap) {      // (chunk = 0: the caller's arrays are page-locked, no ring needed)
-        for (int i = 0; i < kRing; i++) CopyPool::get().wait(&s->out_pending[i]);
-        if (s->pin_in) { cudaFreeHost(s->pin_in); s->pin_in = nullptr; }
-        if (s->pin_out) { cudaFreeHost(s->pin_out); s->pin_out = nullptr; }
-        s->chunk_cap = 0;
-        const size_t bytes = (size_t)kRing * 5 * (size_t)chunk * sizeof(double);
-        if (cudaHostAlloc(&s->pin_in, bytes, cudaHostAllocDefault) != cudaSuccess ||
-            cudaHostAlloc(&s->pin_out, bytes, cudaHostAllocDefault) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(h, SWRT_ERR_ALLOC, "cudaHostAlloc of the %zu-byte staging ring failed", 2 * bytes);
-        }
-        s->chunk_cap = chunk;
-    }
-    return SWRT_OK;
-}
-
-// one pipelined pass over the packet range: upload (in != null), run (r != null), download (out != null)
-struct HostPipe {
-    swrt_handle* h = nullptr;
-    const RunOps* run = nullptr;                      // a prepared run: computed chunk by chunk behind its upload
-    bool whole = false;                               // or: the whole plan after the last upload (SPECTRAL, multi-run plans)
-    int scheme = 0, nsteps = 0; double dt = 0, alpha0 = 0, dalpha = 0;
-    int64_t n = 0, chunk = 0; int nchunk = 0;
-    const double* in[5] = {}; double* out[5] = {};
-    bool have_in = false, have_out = false, chunked_compute = false;
-    bool direct_in = false, direct_out = false;       // the caller's arrays are page-locked: DMA straight from / to them
-    int next_drain = 0;
-
-    // page-locked (cudaHostAlloc / cudaHostRegister) memory needs no staging
-    static bool pinned(const double* p, int64_t cnt) {
-        if (!p || cnt <= 0) return true;
-        cudaPointerAttributes a0{}, a1{};
-        if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, p + cnt - 1) != cudaSuccess) { cudaGetLastError(); return false; }
-        return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
-    }
-
-    static int64_t pick_chunk(int64_t n) {
-        int64_t c = (n + 7) / 8;
-        c = (c + 4095) / 4096 * 4096;
-        if (c < 16384) c = 16384;
-        if (c > 262144) c = 262144;
-        return c < n ? c : (n > 0 ? n : 1);
-    }
-    int begin() {
-        chunk = pick_chunk(n);
-        nchunk = (int)((n + chunk - 1) / chunk);
-        chunked_compute = run != nullptr;
-        next_drain = 0;
-        direct_in = have_in; direct_out = have_out;
-        for (int a = 0; a < 5; a++) { direct_in = direct_in && pinned(in[a], n); direct_out = direct_out && pinned(out[a], n); }
-        return stager_init(h, ((have_in && !direct_in) || (have_out && !direct_out)) ? chunk : 0);
-    }
-    double* dev(int c) const { double* d[5] = {h->x, h->y, h->k, h->l, h->a}; return d[c]; }
-    int enqueue_out(int c) {
-        Stager* s = h->stager;
-        const int slot = c % kRing;
-        const int64_t lo = (int64_t)c * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
-        CopyPool::get().wait(&s->out_pending[slot]);                 // the ring slot's previous contents reached the caller
-        CU(h, cudaStreamWaitEvent(s->s_out, chunked_compute ? s->ev_k[slot] : s->ev_all, 0));
-        for (int a = 0; a < 5; a++)
-            if (out[a])
-                CU(h, cudaMemcpyAsync(direct_out ? out[a] + lo : s->pin_out + ((size_t)slot * 5 + a) * s->chunk_cap, dev(a) + lo, (size_t)cnt * 8,
-                                      cudaMemcpyDeviceToHost, s->s_out));
-        CU(h, cudaEventRecord(s->ev_d2h[slot], s->s_out));
-        return SWRT_OK;
-    }
-    int drain(int c) {           // pinned ring -> caller's arrays (helper threads; completion is checked at slot reuse / end)
-        Stager* s = h->stager;
-        const int slot = c % kRing;
-        const int64_t lo = (int64_t)c * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
-        CU(h, cudaEventSynchronize(s->ev_d2h[slot]));
-        if (direct_out) return SWRT_OK;
-        for (int a = 0; a < 5; a++)
-            if (out[a]) CopyPool::get().submit(out[a] + lo, s->pin_out + ((size_t)slot * 5 + a) * s->chunk_cap, (size_t)cnt * 8, &s->out_pending[slot]);
-        return SWRT_OK;
-    }
-    // chunk c: stage in, upload, (compute, download), drain an older chunk
-    int step(int c) {
-        Stager* s = h->stager;
-        int rc;
-        const int slot = c % kRing;
-        const int64_t lo = (int64_t)c * chunk, cnt = (lo + chunk <= n ? chunk : n - lo);
-        if (have_in) {
-            if (!direct_in) {
-                if (c >= kRing) CU(h, cudaEventSynchronize(s->ev_h2d[slot]));   // the DMA out of this ring slot has finished
-                for (int a = 0; a < 5; a++)
-                    if (in[a]) CopyPool::get().submit(s->pin_in + ((size_t)slot * 5 + a) * s->chunk_cap, in[a] + lo, (size_t)cnt * 8, &s->in_pending);
-                CopyPool::get().wait(&s->in_pending);
-            }
-            for (int a = 0; a < 5; a++)
-                if (in[a])
-                    CU(h, cudaMemcpyAsync(dev(a) + lo, direct_in ? in[a] + lo : s->pin_in + ((size_t)slot * 5 + a) * s->chunk_cap, (size_t)cnt * 8,
-                                          cudaMemcpyHostToDevice, s->s_in));
-            if (!in[4]) { launch_fill(h->a + lo, 1.0, cnt, s->s_in); h->launches++; }
-            CU(h, cudaEventRecord(s->ev_h2d[slot], s->s_in));
-        }
-        if (chunked_compute) {
-            if (have_in) CU(h, cudaStreamWaitEvent(h->stream, s->ev_h2d[slot], 0));
-            if ((rc = launch_run(h, *run, lo, cnt))) return rc;
-            CU(h, cudaEventRecord(s->ev_k[slot], h->stream));
-        }
-        if (have_out && !whole) {
-            if (!run) { CU(h, cudaEventRecord(s->ev_all, h->stream)); }        // download only: behind the work already queued
-            if ((rc = enqueue_out(c))) return rc;
-            if (c - next_drain >= kRing - 1) { if ((rc = drain(next_drain))) return rc; next_drain++; }
-        }
-        return SWRT_OK;
-    }
-    // after the last chunk: whole-ensemble compute plans (SPECTRAL, composed or multi-run) queue their kernels ...
-    bool compute_done = false;
-    int finish_compute() {
-        Stager* s = h->stager;
-        int rc;
-        compute_done = true;
-        if (whole) {
-            if (have_in) { CU(h, cudaEventRecord(s->ev_all, s->s_in)); CU(h, cudaStreamWaitEvent(h->stream, s->ev_all, 0)); }
-            if ((rc = step_impl(h, scheme, dt, nsteps, alpha0, dalpha, false))) return rc;
-            CU(h, cudaEventRecord(s->ev_all, h->stream));
-        }
-        return SWRT_OK;
-    }
-    // ... and the remaining downloads are collected
-    int finish() {
-        Stager* s = h->stager;
-        int rc;
-        if (!compute_done && (rc = finish_compute())) return rc;
-        if (whole && have_out)
-            for (int c = 0; c < nchunk; c++) {
-                if ((rc = enqueue_out(c))) return rc;
-                if (c - next_drain >= kRing - 1) { if ((rc = drain(next_drain))) return rc; next_drain++; }
-            }
-        if (have_out) {
-            for (; next_drain < nchunk; next_drain++)
-                if ((rc = drain(next_drain))) return rc;
-            for (int i = 0; i < kRing; i++) CopyPool::get().wait(&s->out_pending[i]);
-        }
-        if (have_in && !have_out) CU(h, cudaStreamSynchronize(s->s_in));
-        if (!have_out && (run || whole)) CU(h, cudaStreamSynchronize(h->stream));
-        return SWRT_OK;
-    }
-};
-
-// set up a pipe over n packets of `h`: upload from in[] (when `up`), the plan (when nsteps > 0), download to out[]
-int pipe_setup(swrt_handle* h, HostPipe& p, RunOps& r, int64_t n, bool up, const double* const in[5], double* const out[5],
-               int scheme, double dt, int nsteps, double alpha0, double dalpha) {
-    int rc;
-    p = HostPipe{};
-    p.h = h; p.n = n;
-    if (up) {
-        if ((rc = ensure_packets(h, n))) return rc;
-        h->bs_ready = false;
-        p.have_in = true;
-        for (int a = 0; a < 5; a++) p.in[a] = in[a];
-    }
-    if (out) for (int a = 0; a < 5; a++) { p.out[a] = out[a]; p.have_out = p.have_out || out[a]; }
-    if (nsteps > 0) {
-        const bool td = (dalpha != 0.0);
-        const bool single = !td || nsteps <= kMaxFusedBlend;
-        const bool fused_kernel = h->p.mode == SWRT_MODE_LAGRANGE6 ||
-                                  (h->p.mode == SWRT_MODE_NUFFT && (scheme == SWRT_SCHEME_LEAPFROG || !h->unfused_rk4));
-        if (single && fused_kernel) {
-            if ((rc = prepare_run(h, scheme, dt, alpha0, dalpha, 0, nsteps, r))) return rc;
-            p.run = &r;
-        } else {
-            p.whole = true; p.scheme = scheme; p.dt = dt; p.nsteps = nsteps; p.alpha0 = alpha0; p.dalpha = dalpha;
-        }
-    }
-    return p.begin();
-}
-
-}  // namespace
+#include "swrt_staging.inc"   // host staging: pinned ring + helper threads (HostPipe)
 
 extern "C" {
 
@@ -1961,464 +1672,7 @@ int swrt_k2g(int device, const double* fk_re, const double* fk_im, int nx, doubl
 
 }  // extern "C"
 
-// ================================================================================================
-// On-device one-layer QG frame producer ("next" row f3): qgsw_raytrace.m:111-137 (AB3 time loop),
-// :222-230 (exponential cutoff filter), :216-220 (inertial-ring forcing), :270-286 (update()).
-// Setup for the hot path, not the hot path: it exists so that time-evolving runs never leave the GPU.
-// ================================================================================================
-namespace {
-__global__ void qg_spec_kernel(const double2* __restrict__ qk, int nkx, int nky, double kappa, double K_d2,
-                               double2* psikx, double2* psiky, double2* qkx, double2* qky) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nkx * nky) return;
-    const int kmax = (nkx - 1) / 2;
-    const double kx = kappa * (double)(idx % nkx - kmax), ky = kappa * (double)(idx / nkx);
-    const double2 q = qk[idx];
-    const double d = K_d2 + (kx * kx + ky * ky);
-    const double2 psi = make_double2(-q.x / d, -q.y / d);                 // psik = -qk./(K_d2 + K2)
-    psikx[idx] = make_double2(-kx * psi.y, kx * psi.x);                   // 1i*kx_.*psik
-    psiky[idx] = make_double2(-ky * psi.y, ky * psi.x);
-    qkx[idx] = make_double2(-kx * q.y, kx * q.x);
-    qky[idx] = make_double2(-ky * q.y, ky * q.x);
-}
-__global__ void qg_jacobian_kernel(const double* psix, const double* psiy, const double* qx, const double* qy, double* J, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) J[i] = psix[i] * qy[i] - psiy[i] * qx[i];                  // J = psix.*qy - psiy.*qx
-}
-// Qn = g2k(J) - beta*psikx + r_drag*K2 + surface_forces  (as written in update(), qgsw_raytrace.m:285)
-__global__ void qg_rhs_kernel(const double2* __restrict__ Jk, const double2* __restrict__ psikx, int nkx, int nky, double kappa,
-                              double beta, double r_drag, double force, double f, double Cg, double2* Qn) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nkx * nky) return;
-    const int kmax = (nkx - 1) / 2;
-    const double kx = kappa * (double)(idx % nkx - kmax), ky = kappa * (double)(idx / nkx);
-    const double K2 = kx * kx + ky * ky;
-    const double om = sqrt(f * f + Cg * Cg * K2);
-    const double frc = (0.9 * f < om && om < 1.1 * f) ? force : 0.0;      // inertial_ring, :216-220
-    Qn[idx] = make_double2(Jk[idx].x - beta * psikx[idx].x + r_drag * K2 + frc, Jk[idx].y - beta * psikx[idx].y);
-}
-// AB1/AB2/AB3 increment (qgsw_raytrace.m:123-132), history rotation (:134-135), filter (:137)
-__global__ void qg_ab_kernel(double2* qk, const double2* Qn, double2* Qm1, double2* Qm2, int order, double dt, int nkx, int nky,
-                             double kappa, double dx) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nkx * nky) return;
-    const int kmax = (nkx - 1) / 2;
-    const double kx = kappa * (double)(idx % nkx - kmax), ky = kappa * (double)(idx / nkx);
-    const double2 a = Qn[idx], b = Qm1[idx], c = Qm2[idx];
-    double2 dq;
-    if (order == 1) dq = make_double2(dt * a.x, dt * a.y);
-    else if (order == 2) dq = make_double2(dt / 2 * (3 * a.x - b.x), dt / 2 * (3 * a.y - b.y));
-    else dq = make_double2(dt / 12 * (23 * a.x - 16 * b.x + 5 * c.x), dt / 12 * (23 * a.y - 16 * b.y + 5 * c.y));
-    Qm2[idx] = b; Qm1[idx] = a;
-    // Ef: exponential cutoff above kstar = 0.75*pi (:222-230)
-    const double kstar = sqrt((kx * dx) * (kx * dx) + (ky * dx) * (ky * dx));
-    const double kc = 0.75 * M_PI;
-    double Ef = 1.0;
-    if (kstar >= kc) { const double cst = log(1e-15) / pow(0.25 * M_PI, 4.0); Ef = exp(cst * pow(kstar - kc, 4.0)); }
-    qk[idx] = make_double2(Ef * (qk[idx].x + dq.x), Ef * (qk[idx].y + dq.y));
-}
-__global__ void qg_psi_kernel(const double2* __restrict__ qk, int nkx, int nky, double kappa, double K_d2, double2* psi) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nkx * nky) return;
-    const int kmax = (nkx - 1) / 2;
-    const double kx = kappa * (double)(idx % nkx - kmax), ky = kappa * (double)(idx / nkx);
-    const double d = K_d2 + (kx * kx + ky * ky);
-    psi[idx] = make_double2(-qk[idx].x / d, -qk[idx].y / d);
-}
-}  // namespace
-
-struct swrt_qg {
-    int device = 0, nx = 0;
-    double L = 0, K_d2 = 0, beta = 0, r_drag = 0, force = 0, f = 0, Cg = 0, dt = 0;
-    long long step = 0;
-    cudaStream_t stream = nullptr;
-    FftWork fft;
-    double2 *qk = nullptr, *Qn = nullptr, *Qm1 = nullptr, *Qm2 = nullptr, *s[4] = {}, *Jk = nullptr, *psi = nullptr;
-    double* g[5] = {};
-    std::string err;
-};
-
-extern "C" {
-
-int swrt_qg_create(int device, int nx, double L, double K_d2, double beta, double r_drag, double force_strength, double f,
-                   double Cg, double dt, const double* qk_re, const double* qk_im, swrt_qg** out) {
-    if (!out || !qk_re || !qk_im || nx < 8 || (nx & 1) || !(L > 0) || !(dt > 0)) return fail(nullptr, SWRT_ERR_ARG, "swrt_qg_create: bad argument");
-    *out = nullptr;
-    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_qg_create: no CUDA device; libswrt has no CPU path"); }
-    swrt_qg* q = new (std::nothrow) swrt_qg();
-    if (!q) return fail(nullptr, SWRT_ERR_ALLOC, "out of host memory");
-    q->device = device; q->nx = nx; q->L = L; q->K_d2 = K_d2; q->beta = beta; q->r_drag = r_drag; q->force = force_strength;
-    q->f = f; q->Cg = Cg; q->dt = dt;
-    const size_t nh = (size_t)(nx - 1) * (nx / 2), ng = (size_t)nx * nx;
-    bool ok = cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) == cudaSuccess && q->fft.init(nx, q->stream, q->err) == SWRT_OK;
-    double2** cplx[] = {&q->qk, &q->Qn, &q->Qm1, &q->Qm2, &q->s[0], &q->s[1], &q->s[2], &q->s[3], &q->Jk, &q->psi};
-    for (auto p : cplx) ok = ok && cudaMalloc(p, nh * sizeof(double2)) == cudaSuccess;
-    for (auto& p : q->g) ok = ok && cudaMalloc(&p, ng * sizeof(double)) == cudaSuccess;
-    if (!ok) { swrt_qg_destroy(q); return fail(nullptr, SWRT_ERR_ALLOC, "swrt_qg_create: allocation failed"); }
-    std::vector<double2> hq(nh);
-    for (size_t i = 0; i < nh; i++) hq[i] = make_double2(qk_re[i], qk_im[i]);
-    cudaMemcpy(q->qk, hq.data(), nh * sizeof(double2), cudaMemcpyHostToDevice);
-    cudaMemset(q->Qm1, 0, nh * sizeof(double2)); cudaMemset(q->Qm2, 0, nh * sizeof(double2));
-    *out = q;
-    return SWRT_OK;
-}
-
-int swrt_qg_destroy(swrt_qg* q) {
-    if (!q) return SWRT_OK;
-    cudaSetDevice(q->device);
-    if (q->stream) cudaStreamSynchronize(q->stream);
-    double2* cplx[] = {q->qk, q->Qn, q->Qm1, q->Qm2, q->s[0], q->s[1], q->s[2], q->s[3], q->Jk, q->psi};
-    for (auto p : cplx) if (p) cudaFree(p);
-    for (auto p : q->g) if (p) cudaFree(p);
-    if (q->stream) cudaStreamDestroy(q->stream);
-    delete q;
-    return SWRT_OK;
-}
-
-int swrt_qg_step(swrt_qg* q, int nsteps) {
-    if (!q || nsteps < 0) return SWRT_ERR_ARG;
-    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
-    const int nkx = q->nx - 1, nky = q->nx / 2, nh = nkx * nky;
-    const size_t ng = (size_t)q->nx * q->nx;
-    const double kappa = 2.0 * M_PI / q->L, dx = q->L / q->nx;
-    const int bs = 256, gb = (nh + bs - 1) / bs;
-    for (int it = 0; it < nsteps; it++) {
-        qg_spec_kernel<<<gb, bs, 0, q->stream>>>(q->qk, nkx, nky, kappa, q->K_d2, q->s[0], q->s[1], q->s[2], q->s[3]);
-        for (int c = 0; c < 4; c++)
-            if (k2g_dev(q->fft, q->s[c], q->g[c], q->stream, q->err)) return SWRT_ERR_CUDA;
-        qg_jacobian_kernel<<<(unsigned)((ng + bs - 1) / bs), bs, 0, q->stream>>>(q->g[0], q->g[1], q->g[2], q->g[3], q->g[4], ng);
-        if (g2k_dev(q->fft, q->g[4], q->Jk, q->stream, q->err)) return SWRT_ERR_CUDA;
-        qg_rhs_kernel<<<gb, bs, 0, q->stream>>>(q->Jk, q->s[0], nkx, nky, kappa, q->beta, q->r_drag, q->force, q->f, q->Cg, q->Qn);
-        const int order = q->step == 0 ? 1 : (q->step == 1 ? 2 : 3);
-        qg_ab_kernel<<<gb, bs, 0, q->stream>>>(q->qk, q->Qn, q->Qm1, q->Qm2, order, q->dt, nkx, nky, kappa, dx);
-        q->step++;
-    }
-    cudaError_t e = cudaStreamSynchronize(q->stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { q->err = cudaGetErrorString(e); return SWRT_ERR_CUDA; }
-    return SWRT_OK;
-}
-
-int swrt_qg_get(swrt_qg* q, double* qk_re, double* qk_im) {
-    if (!q || !qk_re || !qk_im) return SWRT_ERR_ARG;
-    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
-    const size_t nh = (size_t)(q->nx - 1) * (q->nx / 2);
-    std::vector<double2> hq(nh);
-    if (cudaMemcpy(hq.data(), q->qk, nh * sizeof(double2), cudaMemcpyDeviceToHost) != cudaSuccess) return SWRT_ERR_CUDA;
-    for (size_t i = 0; i < nh; i++) { qk_re[i] = hq[i].x; qk_im[i] = hq[i].y; }
-    return SWRT_OK;
-}
-
-// q = k2g(qk) on the device with the solver's own FFT plan (the PV frame qgsw_raytrace.m:165-170 writes every 50 steps)
-int swrt_qg_get_grid(swrt_qg* q, double* qgrid) {
-    if (!q || !qgrid) return SWRT_ERR_ARG;
-    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
-    const size_t ng = (size_t)q->nx * q->nx;
-    if (k2g_dev(q->fft, q->qk, q->g[4], q->stream, q->err)) return SWRT_ERR_CUDA;
-    if (cudaMemcpyAsync(qgrid, q->g[4], ng * sizeof(double), cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
-        cudaStreamSynchronize(q->stream) != cudaSuccess) return SWRT_ERR_CUDA;
-    return SWRT_OK;
-}
-
-// flow slot <- psi = -q/(K_d2 + K2) of the QG state, entirely on the device (grid_U.m:2 without the host)
-int swrt_set_flow_from_qg(swrt_handle* h, int slot, swrt_qg* q, double u_mean) {
-    if (!h || !q) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
-    REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
-    REQUIRE(h, q->nx == h->p.nx && q->device == h->p.device && q->L == h->p.L, SWRT_ERR_ARG, "QG state and handle differ in nx / L / device");
-    const int nkx = q->nx - 1, nky = q->nx / 2, nh = nkx * nky;
-    CU(h, cudaStreamSynchronize(q->stream));
-    swrt_handle* h0 = h->ngpu > 1 ? h->shard[0] : h;
-    qg_psi_kernel<<<(nh + 255) / 256, 256, 0, h0->stream>>>(q->qk, nkx, nky, 2.0 * M_PI / q->L, q->K_d2, q->psi);
-    h0->launches++;
-    if (h->ngpu > 1) { CU(h, cudaStreamSynchronize(h0->stream)); return grp_flow_from_psi_dev(h, slot, q->psi, u_mean); }
-    return set_flow_spectral_dev(h, slot, q->psi, u_mean);
-}
-
-}  // extern "C"
-
-// ================================================================================================
-// On-device TWO-layer QG frame producer: qg2layersw_raytrace.m:120-181 (inversion matrix B, linear
-// operator factor_L and its exponentials, AB3 with integrating factor) and :309-323 (update()).
-// MATLAB builds exp(L dt) as V exp(D dt) V^-1 from pageeig (:147-150); the 2x2 matrix exponential is
-// evaluated here in closed form (the same matrix; pageeig is a proprietary builtin -> parity unpinned).
-// ================================================================================================
-namespace {
-struct c2 { double x, y; };
-__device__ __forceinline__ c2 cmul(c2 a, c2 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-__device__ __forceinline__ c2 cadd(c2 a, c2 b) { return {a.x + b.x, a.y + b.y}; }
-__device__ __forceinline__ c2 csub(c2 a, c2 b) { return {a.x - b.x, a.y - b.y}; }
-__device__ __forceinline__ c2 cscale(c2 a, double r) { return {a.x * r, a.y * r}; }
-__device__ __forceinline__ c2 csqrt2(c2 z) {
-    const double m = hypot(z.x, z.y);
-    if (m == 0.0) return {0.0, 0.0};
-    double re = sqrt(0.5 * (m + fabs(z.x)));
-    double im = 0.5 * z.y / re;
-    if (z.x < 0.0) { const double t = re; re = fabs(im); im = copysign(t, z.y); }
-    return {re, im};
-}
-__device__ __forceinline__ c2 cexp2(c2 z) { const double e = exp(z.x); double s, c; sincos(z.y, &s, &c); return {e * c, e * s}; }
-// exp(t*M) for the 2x2 complex M = [a b; c d]:  e^{ts} [cosh(t D) I + sinh(t D)/D (M - s I)],  s = (a+d)/2, D^2 = ((a-d)/2)^2 + bc
-__device__ void expm2(c2 a, c2 b, c2 c, c2 d, double t, c2 out[4]) {
-    const c2 s = cscale(cadd(a, d), 0.5), p = cscale(csub(a, d), 0.5);
-    const c2 D2 = cadd(cmul(p, p), cmul(b, c));
-    const c2 D = csqrt2(D2);
-    const c2 tD = cscale(D, t);
-    c2 ch, shc;                                  // cosh(tD), sinh(tD)/D
-    if (hypot(tD.x, tD.y) < 1e-4) {              // series: cosh z = 1 + z^2/2 + z^4/24, sinh z / z = 1 + z^2/6 + z^4/120
-        const c2 z2 = cmul(tD, tD), z4 = cmul(z2, z2);
-        ch = cadd(cadd({1.0, 0.0}, cscale(z2, 0.5)), cscale(z4, 1.0 / 24.0));
-        shc = cscale(cadd(cadd({1.0, 0.0}, cscale(z2, 1.0 / 6.0)), cscale(z4, 1.0 / 120.0)), t);
-    } else {
-        const c2 ep = cexp2(tD), em = cexp2({-tD.x, -tD.y});
-        ch = cscale(cadd(ep, em), 0.5);
-        const c2 sh = cscale(csub(ep, em), 0.5);
-        const double n2 = D.x * D.x + D.y * D.y;
-        shc = cmul(sh, {D.x / n2, -D.y / n2});
-    }
-    const c2 es = cexp2(cscale(s, t));
-    out[0] = cmul(es, cadd(ch, cmul(shc, p)));
-    out[1] = cmul(es, cmul(shc, b));
-    out[2] = cmul(es, cmul(shc, c));
-    out[3] = cmul(es, csub(ch, cmul(shc, p)));
-}
-struct Qg2Par { int nkx, nky; double kappa, K_d2, beta, shear, r, nu, alpha; };
-__device__ __forceinline__ void qg2_B(const Qg2Par& P, double K2, double& B11, double& B12) {
-    // B = [-F-K2, -F; -F, -F-K2] ./ detB, detB = K2.*(K2+2F), detB(K2==0) = Inf  (:137-143)
-    const double F = 0.5 * P.K_d2;
-    if (K2 == 0.0) { B11 = 0.0; B12 = 0.0; return; }
-    const double det = K2 * (K2 + 2.0 * F);
-    B11 = (-F - K2) / det; B12 = -F / det;
-}
-// expLdt = expm(factor_L*dt), expL2dt = expm(factor_L*2dt); factor_L = mean_flow_terms + diffusion_terms (:146-153)
-__global__ void qg2_expl_kernel(Qg2Par P, double dt, double2* E1, double2* E2) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nh = P.nkx * P.nky;
-    if (idx >= nh) return;
-    const int kmax = (P.nkx - 1) / 2;
-    const double kx = P.kappa * (double)(idx % P.nkx - kmax), ky = P.kappa * (double)(idx / P.nkx);
-    const double K2 = kx * kx + ky * ky, F = 0.5 * P.K_d2;
-    double B11, B12; qg2_B(P, K2, B11, B12);
-    const c2 dfac = {(P.nu * pow(K2, P.alpha) + P.r) * K2, -kx * P.beta};       // (nu K2^alpha + r) K2 - i kx beta
-    const c2 sh = {0.0, kx * P.shear};                                              // i kx shear
-    // [-1 0; 0 1] * (I + 2F B) = [-(1+2F B11), -2F B12; 2F B12, 1+2F B11]
-    const double m11 = -(1.0 + 2.0 * F * B11), m12 = -2.0 * F * B12, m21 = 2.0 * F * B12, m22 = 1.0 + 2.0 * F * B11;
-    const c2 a = cadd(cscale(sh, m11), cscale(dfac, B11)), b = cadd(cscale(sh, m12), cscale(dfac, B12));
-    const c2 c = cadd(cscale(sh, m21), cscale(dfac, B12)), d = cadd(cscale(sh, m22), cscale(dfac, B11));
-    c2 o[4];
-    expm2(a, b, c, d, dt, o);
-    for (int j = 0; j < 4; j++) E1[(size_t)j * nh + idx] = make_double2(o[j].x, o[j].y);
-    expm2(a, b, c, d, 2.0 * dt, o);
-    for (int j = 0; j < 4; j++) E2[(size_t)j * nh + idx] = make_double2(o[j].x, o[j].y);
-}
-// update(), spectral half (:310-314): psik = mmult3(B, qk); i kx/i ky multiples of psik and qk for BOTH layers
-__global__ void qg2_spec_kernel(Qg2Par P, const double2* __restrict__ q1, const double2* __restrict__ q2, double2* const* s) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P.nkx * P.nky) return;
-    const int kmax = (P.nkx - 1) / 2;
-    const double kx = P.kappa * (double)(idx % P.nkx - kmax), ky = P.kappa * (double)(idx / P.nkx);
-    double B11, B12; qg2_B(P, kx * kx + ky * ky, B11, B12);
-    const double2 a = q1[idx], b = q2[idx];
-    const double2 p1 = make_double2(B11 * a.x + B12 * b.x, B11 * a.y + B12 * b.y);
-    const double2 p2 = make_double2(B12 * a.x + B11 * b.x, B12 * a.y + B11 * b.y);
-    const double2 ps[2] = {p1, p2}, qs[2] = {a, b};
-    for (int l = 0; l < 2; l++) {
-        s[4 * l + 0][idx] = make_double2(-kx * ps[l].y, kx * ps[l].x);
-        s[4 * l + 1][idx] = make_double2(-ky * ps[l].y, ky * ps[l].x);
-        s[4 * l + 2][idx] = make_double2(-kx * qs[l].y, kx * qs[l].x);
-        s[4 * l + 3][idx] = make_double2(-ky * qs[l].y, ky * qs[l].x);
-    }
-}
-__device__ __forceinline__ double2 mm(const double2* E, size_t nh, int row, int idx, double2 x1, double2 x2) {
-    const double2 e1 = E[(size_t)(2 * row) * nh + idx], e2 = E[(size_t)(2 * row + 1) * nh + idx];      // mmult3 (:333-338)
-    return make_double2(e1.x * x1.x - e1.y * x1.y + e2.x * x2.x - e2.y * x2.y, e1.x * x1.y + e1.y * x1.x + e2.x * x2.y + e2.y * x2.x);
-}
-// AB1/AB2/AB3 with integrating factor (:167-181): dq, history rotation, qk = expLdt*(qk + dq)
-__global__ void qg2_ab_kernel(int nh, int order, double dt, const double2* __restrict__ E1, const double2* __restrict__ E2,
-                              double2* q1, double2* q2, const double2* Qn1, const double2* Qn2, double2* A1, double2* A2,
-                              double2* C1, double2* C2) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nh) return;
-    const double2 n1 = Qn1[idx], n2 = Qn2[idx], a1 = A1[idx], a2 = A2[idx], c1 = C1[idx], c2v = C2[idx];
-    double2 d1, d2;
-    if (order == 1) { d1 = make_double2(dt * n1.x, dt * n1.y); d2 = make_double2(dt * n2.x, dt * n2.y); }
-    else {
-        const double2 ea1 = mm(E1, nh, 0, idx, a1, a2), ea2 = mm(E1, nh, 1, idx, a1, a2);
-        if (order == 2) {
-            d1 = make_double2(dt / 2 * (3 * n1.x - ea1.x), dt / 2 * (3 * n1.y - ea1.y));
-            d2 = make_double2(dt / 2 * (3 * n2.x - ea2.x), dt / 2 * (3 * n2.y - ea2.y));
-        } else {
-            const double2 ec1 = mm(E2, nh, 0, idx, c1, c2v), ec2 = mm(E2, nh, 1, idx, c1, c2v);
-            d1 = make_double2(dt / 12 * (23 * n1.x - 16 * ea1.x + 5 * ec1.x), dt / 12 * (23 * n1.y - 16 * ea1.y + 5 * ec1.y));
-            d2 = make_double2(dt / 12 * (23 * n2.x - 16 * ea2.x + 5 * ec2.x), dt / 12 * (23 * n2.y - 16 * ea2.y + 5 * ec2.y));
-        }
-    }
-    C1[idx] = a1; C2[idx] = a2; A1[idx] = n1; A2[idx] = n2;
-    const double2 y1 = make_double2(q1[idx].x + d1.x, q1[idx].y + d1.y), y2 = make_double2(q2[idx].x + d2.x, q2[idx].y + d2.y);
-    q1[idx] = mm(E1, nh, 0, idx, y1, y2);
-    q2[idx] = mm(E1, nh, 1, idx, y1, y2);
-}
-// grid_U.m:2-4 for one layer: uk = -i ky psik, vk = i kx psik with psik = -qk./(K_d2 + K2)  (the ONE-layer inversion,
-// which is what qg2layersw_raytrace.m:155,187-188 applies to each layer)
-__global__ void qg2_uv_kernel(Qg2Par P, const double2* __restrict__ q, double2* uk, double2* vk) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P.nkx * P.nky) return;
-    const int kmax = (P.nkx - 1) / 2;
-    const double kx = P.kappa * (double)(idx % P.nkx - kmax), ky = P.kappa * (double)(idx / P.nkx);
-    const double d = P.K_d2 + (kx * kx + ky * ky);
-    const double2 psi = make_double2(-q[idx].x / d, -q[idx].y / d);
-    uk[idx] = make_double2(ky * psi.y, -ky * psi.x);
-    vk[idx] = make_double2(-kx * psi.y, kx * psi.x);
-}
-__global__ void qg2_speed_kernel(const double* u, const double* v, double shear, size_t n, unsigned long long* out) {
-    double m = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const double uu = u[i] + shear, s2 = uu * uu + v[i] * v[i];
-        m = (s2 > m || s2 != s2) ? s2 : m;
-    }
-    __shared__ double sh[256];
-    sh[threadIdx.x] = m; __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) { double o = sh[threadIdx.x + s], w = sh[threadIdx.x]; sh[threadIdx.x] = (o > w || o != o) ? o : w; } __syncthreads(); }
-    if (threadIdx.x == 0) { double w = sh[0]; if (w != w) w = __longlong_as_double(0x7ff0000000000000LL); atomicMax(out, (unsigned long long)__double_as_longlong(w)); }
-}
-}  // namespace
-
-struct swrt_qg2 {
-    int device = 0, nx = 0;
-    double L = 0;
-    Qg2Par par{};
-    double dt_cached = -1.0;
-    long long step = 0;
-    cudaStream_t stream = nullptr;
-    FftWork fft;
-    double2 *q[2] = {}, *Qn[2] = {}, *Qm1[2] = {}, *Qm2[2] = {}, *s[8] = {}, *E1 = nullptr, *E2 = nullptr, *psi = nullptr;
-    double2** s_dev = nullptr;
-    double* g[5] = {};
-    unsigned long long* red = nullptr;
-    std::string err;
-};
-
-extern "C" {
-
-int swrt_qg2_create(int device, int nx, double L, double K_d2, double beta, double shear_strength, double r, double nu, double alpha,
-                    const double* q1_re, const double* q1_im, const double* q2_re, const double* q2_im, swrt_qg2** out) {
-    if (!out || !q1_re || !q1_im || !q2_re || !q2_im || nx < 8 || (nx & 1) || !(L > 0)) return fail(nullptr, SWRT_ERR_ARG, "swrt_qg2_create: bad argument");
-    *out = nullptr;
-    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SWRT_ERR_CUDA, "swrt_qg2_create: no CUDA device; libswrt has no CPU path"); }
-    swrt_qg2* q = new (std::nothrow) swrt_qg2();
-    if (!q) return fail(nullptr, SWRT_ERR_ALLOC, "out of host memory");
-    q->device = device; q->nx = nx; q->L = L;
-    q->par = Qg2Par{nx - 1, nx / 2, 2.0 * M_PI / L, K_d2, beta, shear_strength, r, nu, alpha};
-    const size_t nh = (size_t)(nx - 1) * (nx / 2), ng = (size_t)nx * nx;
-    bool ok = cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) == cudaSuccess && q->fft.init(nx, q->stream, q->err) == SWRT_OK;
-    std::vector<double2**> cplx;
-    for (int l = 0; l < 2; l++) { cplx.push_back(&q->q[l]); cplx.push_back(&q->Qn[l]); cplx.push_back(&q->Qm1[l]); cplx.push_back(&q->Qm2[l]); }
-    for (auto& p : q->s) cplx.push_back(&p);
-    cplx.push_back(&q->psi);
-    for (auto p : cplx) ok = ok && cudaMalloc(p, nh * sizeof(double2)) == cudaSuccess;
-    ok = ok && cudaMalloc(&q->E1, 4 * nh * sizeof(double2)) == cudaSuccess && cudaMalloc(&q->E2, 4 * nh * sizeof(double2)) == cudaSuccess;
-    ok = ok && cudaMalloc(&q->s_dev, 8 * sizeof(double2*)) == cudaSuccess && cudaMalloc(&q->red, sizeof(unsigned long long)) == cudaSuccess;
-    for (auto& p : q->g) ok = ok && cudaMalloc(&p, ng * sizeof(double)) == cudaSuccess;
-    if (!ok) { swrt_qg2_destroy(q); return fail(nullptr, SWRT_ERR_ALLOC, "swrt_qg2_create: allocation failed"); }
-    cudaMemcpy(q->s_dev, q->s, 8 * sizeof(double2*), cudaMemcpyHostToDevice);
-    std::vector<double2> hq(nh);
-    const double* re[2] = {q1_re, q2_re}; const double* im[2] = {q1_im, q2_im};
-    for (int l = 0; l < 2; l++) {
-        for (size_t i = 0; i < nh; i++) hq[i] = make_double2(re[l][i], im[l][i]);
-        cudaMemcpy(q->q[l], hq.data(), nh * sizeof(double2), cudaMemcpyHostToDevice);
-        cudaMemset(q->Qm1[l], 0, nh * sizeof(double2)); cudaMemset(q->Qm2[l], 0, nh * sizeof(double2));
-    }
-    *out = q;
-    return SWRT_OK;
-}
-
-int swrt_qg2_destroy(swrt_qg2* q) {
-    if (!q) return SWRT_OK;
-    cudaSetDevice(q->device);
-    if (q->stream) cudaStreamSynchronize(q->stream);
-    for (int l = 0; l < 2; l++) { cudaFree(q->q[l]); cudaFree(q->Qn[l]); cudaFree(q->Qm1[l]); cudaFree(q->Qm2[l]); }
-    for (auto p : q->s) cudaFree(p);
-    cudaFree(q->psi); cudaFree(q->E1); cudaFree(q->E2); cudaFree(q->s_dev); cudaFree(q->red);
-    for (auto p : q->g) cudaFree(p);
-    if (q->stream) cudaStreamDestroy(q->stream);
-    delete q;
-    return SWRT_OK;
-}
-
-// U0 = sqrt(max(flow.u.^2 + flow.v.^2)) over BOTH layers of grid_U(qk, ..., shear) (qg2layersw_raytrace.m:69-71,155-157)
-int swrt_qg2_max_speed(swrt_qg2* q, double* U0) {
-    if (!q || !U0) return SWRT_ERR_ARG;
-    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
-    const int nh = q->par.nkx * q->par.nky;
-    const size_t ng = (size_t)q->nx * q->nx;
-    cudaMemsetAsync(q->red, 0, sizeof(unsigned long long), q->stream);
-    for (int l = 0; l < 2; l++) {
-        qg2_uv_kernel<<<(nh + 255) / 256, 256, 0, q->stream>>>(q->par, q->q[l], q->s[0], q->s[1]);
-        if (k2g_dev(q->fft, q->s[0], q->g[0], q->stream, q->err) || k2g_dev(q->fft, q->s[1], q->g[1], q->stream, q->err)) return SWRT_ERR_CUDA;
-        qg2_speed_kernel<<<296, 256, 0, q->stream>>>(q->g[0], q->g[1], q->par.shear, ng, q->red);
-    }
-    unsigned long long bits = 0;
-    if (cudaMemcpyAsync(&bits, q->red, sizeof bits, cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
-        cudaStreamSynchronize(q->stream) != cudaSuccess) { q->err = "swrt_qg2_max_speed: CUDA failure"; return SWRT_ERR_CUDA; }
-    double s2; memcpy(&s2, &bits, sizeof s2);
-    *U0 = sqrt(s2);
-    return SWRT_OK;
-}
-
-// one step of the while-loop body (:166-181) with the caller's dt (the CFL logic of :156-165 is host control flow)
-int swrt_qg2_step(swrt_qg2* q, double dt) {
-    if (!q || !(dt > 0)) return SWRT_ERR_ARG;
-    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
-    const int nh = q->par.nkx * q->par.nky;
-    const size_t ng = (size_t)q->nx * q->nx;
-    const int bs = 256, gb = (nh + bs - 1) / bs;
-    if (dt != q->dt_cached) {
-        qg2_expl_kernel<<<gb, bs, 0, q->stream>>>(q->par, dt, q->E1, q->E2);
-        q->dt_cached = dt;
-    }
-    qg2_spec_kernel<<<gb, bs, 0, q->stream>>>(q->par, q->q[0], q->q[1], q->s_dev);
-    for (int l = 0; l < 2; l++) {
-        for (int c = 0; c < 4; c++)
-            if (k2g_dev(q->fft, q->s[4 * l + c], q->g[c], q->stream, q->err)) return SWRT_ERR_CUDA;
-        qg_jacobian_kernel<<<(unsigned)((ng + bs - 1) / bs), bs, 0, q->stream>>>(q->g[0], q->g[1], q->g[2], q->g[3], q->g[4], ng);
-        if (g2k_dev(q->fft, q->g[4], q->Qn[l], q->stream, q->err)) return SWRT_ERR_CUDA;
-    }
-    const int order = q->step == 0 ? 1 : (q->step == 1 ? 2 : 3);
-    qg2_ab_kernel<<<gb, bs, 0, q->stream>>>(nh, order, dt, q->E1, q->E2, q->q[0], q->q[1], q->Qn[0], q->Qn[1], q->Qm1[0], q->Qm1[1],
-                                           q->Qm2[0], q->Qm2[1]);
-    q->step++;
-    cudaError_t e = cudaStreamSynchronize(q->stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { q->err = cudaGetErrorString(e); return SWRT_ERR_CUDA; }
-    return SWRT_OK;
-}
-
-int swrt_qg2_get(swrt_qg2* q, int layer, double* qk_re, double* qk_im) {
-    if (!q || !qk_re || !qk_im || layer < 0 || layer > 1) return SWRT_ERR_ARG;
-    if (cudaSetDevice(q->device) != cudaSuccess) return SWRT_ERR_CUDA;
-    const size_t nh = (size_t)(q->nx - 1) * (q->nx / 2);
-    std::vector<double2> hq(nh);
-    if (cudaMemcpy(hq.data(), q->q[layer], nh * sizeof(double2), cudaMemcpyDeviceToHost) != cudaSuccess) return SWRT_ERR_CUDA;
-    for (size_t i = 0; i < nh; i++) { qk_re[i] = hq[i].x; qk_im[i] = hq[i].y; }
-    return SWRT_OK;
-}
-
-// flow slot <- grid_U(qk(:,:,1), K_d2, K2, kx_, ky_, shear) of the TOP layer (:187-188), entirely on the device
-int swrt_set_flow_from_qg2(swrt_handle* h, int slot, swrt_qg2* q) {
-    if (!h || !q) return SWRT_ERR_ARG;
-    CU(h, cudaSetDevice(h->p.device));
-    REQUIRE(h, slot == 0 || slot == 1, SWRT_ERR_ARG, "slot must be 0 or 1");
-    REQUIRE(h, q->nx == h->p.nx && q->device == h->p.device && q->L == h->p.L, SWRT_ERR_ARG, "QG state and handle differ in nx / L / device");
-    const int nkx = q->nx - 1, nky = q->nx / 2, nh = nkx * nky;
-    CU(h, cudaStreamSynchronize(q->stream));
-    swrt_handle* h0 = h->ngpu > 1 ? h->shard[0] : h;
-    qg_psi_kernel<<<(nh + 255) / 256, 256, 0, h0->stream>>>(q->q[0], nkx, nky, 2.0 * M_PI / q->L, q->par.K_d2, q->psi);
-    h0->launches++;
-    if (h->ngpu > 1) { CU(h, cudaStreamSynchronize(h0->stream)); return grp_flow_from_psi_dev(h, slot, q->psi, q->par.shear); }
-    return set_flow_spectral_dev(h, slot, q->psi, q->par.shear);
-}
-
-}  // extern "C"
+#include "swrt_qg.inc"        // one- and two-layer QG frame producers
 
 extern "C" {
 
@@ -2554,278 +1808,4 @@ int swrt_spectral_geometry(int nx, int nplanes, int mtiles, int64_t out[10]) {
 
 }  // extern "C"
 
-// ================================================================================================
-// Multi-device handles (swrt_params.ngpu > 1): SURVEY 8e.  One host thread, one single-device child handle (own
-// stream) per GPU, contiguous packet shards, flow replicated, and a single-process NCCL communicator
-// (ncclCommInitAll) whose only traffic is the all-reduce of the u64 histogram counts, the diagnostic scalars and the
-// ode23 error norm.  Every public entry point dispatches here when the handle is a group.
-// ================================================================================================
-namespace {
-
-struct NcclApi {
-    void* lib = nullptr;
-    decltype(&ncclCommInitAll) CommInitAll = nullptr;
-    decltype(&ncclCommDestroy) CommDestroy = nullptr;
-    decltype(&ncclAllReduce) AllReduce = nullptr;
-    decltype(&ncclGroupStart) GroupStart = nullptr;
-    decltype(&ncclGroupEnd) GroupEnd = nullptr;
-    decltype(&ncclGetErrorString) GetErrorString = nullptr;
-};
-
-// NCCL is loaded on first use so that single-device callers carry no dependency on it (and so that a process which
-// already holds an NCCL -- e.g. the one bundled with torch -- shares that copy instead of mapping a second one)
-NcclApi* nccl_api(std::string& err) {
-    static NcclApi api;
-    static bool tried = false;
-    if (api.lib) return &api;
-    if (tried) { err = "NCCL could not be loaded earlier in this process"; return nullptr; }
-    tried = true;
-    // SWRT_NCCL_LIB names a specific library file (installs whose NCCL is not on the loader path)
-    const char* names[] = {getenv("SWRT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
-    void* lib = nullptr;
-    for (const char* nm : names) if (nm && *nm && (lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
-    if (!lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?"); return nullptr; }
-#define SWRT_NCCL_SYM(field, name)                                                   \
-    api.field = reinterpret_cast<decltype(api.field)>(dlsym(lib, name));             \
-    if (!api.field) { err = std::string("NCCL symbol missing: ") + name; dlclose(lib); return nullptr; }
-    SWRT_NCCL_SYM(CommInitAll, "ncclCommInitAll")
-    SWRT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
-    SWRT_NCCL_SYM(AllReduce, "ncclAllReduce")
-    SWRT_NCCL_SYM(GroupStart, "ncclGroupStart")
-    SWRT_NCCL_SYM(GroupEnd, "ncclGroupEnd")
-    SWRT_NCCL_SYM(GetErrorString, "ncclGetErrorString")
-#undef SWRT_NCCL_SYM
-    api.lib = lib;
-    return &api;
-}
-
-// propagate a child's failure to the group handle
-int up(swrt_handle* g, swrt_handle* c, int rc) {
-    if (rc != SWRT_OK) g->err = "device " + std::to_string(c->p.device) + ": " + c->err;
-    return rc;
-}
-#define EACH(g, c) for (swrt_handle* c : (g)->shard)
-#define CHILD(g, c, expr) do { int rc__ = (expr); if (rc__ != SWRT_OK) return up(g, c, rc__); } while (0)
-
-int grp_sync(swrt_handle* g) {
-    EACH(g, c) {
-        if (cudaSetDevice(c->p.device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
-            return fail(g, SWRT_ERR_CUDA, "device %d: synchronize failed: %s", c->p.device, cudaGetErrorString(cudaGetLastError()));
-    }
-    return SWRT_OK;
-}
-
-// in-place all-reduce of `count` elements at buf(child) on every child's stream (stream-ordered, no host wait)
-template <typename F>
-int grp_allreduce(swrt_handle* g, F buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) {
-    std::string err;
-    NcclApi* api = nccl_api(err);
-    REQUIRE(g, api, SWRT_ERR_NCCL, "%s", err.c_str());
-    ncclResult_t r = api->GroupStart();
-    for (size_t i = 0; r == ncclSuccess && i < g->shard.size(); i++) {
-        swrt_handle* c = g->shard[i];
-        cudaSetDevice(c->p.device);
-        void* p = buf(c);
-        r = api->AllReduce(p, p, count, dt, op, g->comms[i], c->stream);
-    }
-    ncclResult_t r2 = api->GroupEnd();
-    if (r == ncclSuccess) r = r2;
-    if (r != ncclSuccess) return fail(g, SWRT_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString(r));
-    return SWRT_OK;
-}
-
-int grp_create(const swrt_params* p, swrt_handle** out) {
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(nullptr, SWRT_ERR_CUDA, "swrt_create: no CUDA device; libswrt has no CPU path");
-    }
-    if (p->device < 0 || p->device + p->ngpu > ndev)
-        return fail(nullptr, SWRT_ERR_ARG, "swrt_create: devices %d..%d requested but %d present", p->device, p->device + p->ngpu - 1, ndev);
-    std::string err;
-    NcclApi* api = nccl_api(err);
-    if (!api) return fail(nullptr, SWRT_ERR_NCCL, "swrt_create: ngpu = %d needs NCCL: %s", p->ngpu, err.c_str());
-    swrt_handle* g = new (std::nothrow) swrt_handle();
-    if (!g) return fail(nullptr, SWRT_ERR_ALLOC, "out of host memory");
-    g->p = *p; g->ngpu = p->ngpu;
-    g->off.assign(p->ngpu + 1, 0);
-    std::vector<int> devs;
-    for (int i = 0; i < p->ngpu; i++) {
-        swrt_params cp = *p;
-        cp.ngpu = 1; cp.device = p->device + i;
-        swrt_handle* c = nullptr;
-        int rc = swrt_create(&cp, &c);
-        if (rc == SWRT_OK && cudaMalloc(&c->red_dev, 24 * sizeof(double)) != cudaSuccess) { swrt_destroy(c); rc = fail(nullptr, SWRT_ERR_ALLOC, "cudaMalloc failed"); }
-        if (rc != SWRT_OK) { swrt_destroy(g); return rc; }      // g_create_error holds the child's message
-        g->shard.push_back(c);
-        devs.push_back(cp.device);
-    }
-    g->comms.assign(p->ngpu, nullptr);
-    ncclResult_t r = api->CommInitAll(g->comms.data(), p->ngpu, devs.data());
-    if (r != ncclSuccess) {
-        g->comms.clear();
-        swrt_destroy(g);
-        return fail(nullptr, SWRT_ERR_NCCL, "ncclCommInitAll(%d devices) failed: %s", p->ngpu, api->GetErrorString(r));
-    }
-    *out = g;
-    return SWRT_OK;
-}
-
-int grp_destroy(swrt_handle* g) {
-    std::string err;
-    NcclApi* api = nccl_api(err);
-    grp_sync(g);
-    if (api) for (ncclComm_t c : g->comms) if (c) api->CommDestroy(c);
-    EACH(g, c) swrt_destroy(c);
-    delete g;
-    return SWRT_OK;
-}
-
-void grp_split(swrt_handle* g, int64_t n) {
-    const int64_t G = g->ngpu;
-    for (int64_t i = 0; i <= G; i++) g->off[i] = (i * n) / G;      // the sharding of swraytracing_b200.distributed.shard_range
-    g->n = n;
-}
-
-// run one HostPipe per child, chunk by chunk round-robin, so that every device's DMA and SMs are busy at once
-int grp_pipes(swrt_handle* g, bool up_, const double* const in[5], double* const out[5], int scheme, double dt, int nsteps,
-              double alpha0, double dalpha) {
-    const size_t G = g->shard.size();
-    std::vector<HostPipe> pipes(G);
-    std::vector<RunOps> runs(G);
-    int maxchunks = 0;
-    for (size_t i = 0; i < G; i++) {
-        swrt_handle* c = g->shard[i];
-        const int64_t lo = g->off[i], cnt = g->off[i + 1] - lo;
-        if (cnt == 0) { if (up_) { c->n = 0; c->bs_ready = false; } continue; }
-        CU(g, cudaSetDevice(c->p.device));
-        const double* cin[5]; double* cout[5];
-        for (int a = 0; a < 5; a++) { cin[a] = (in && in[a]) ? in[a] + lo : nullptr; cout[a] = (out && out[a]) ? out[a] + lo : nullptr; }
-        if (up_) CU(g, cudaStreamSynchronize(c->stream));
-        CHILD(g, c, pipe_setup(c, pipes[i], runs[i], cnt, up_, up_ ? cin : nullptr, out ? cout : nullptr, scheme, dt, nsteps, alpha0, dalpha));
-        if (pipes[i].nchunk > maxchunks) maxchunks = pipes[i].nchunk;
-    }
-    for (int ch = 0; ch < maxchunks; ch++)
-        for (size_t i = 0; i < G; i++)
-            if (pipes[i].h && ch < pipes[i].nchunk) {
-                CU(g, cudaSetDevice(g->shard[i]->p.device));
-                CHILD(g, g->shard[i], pipes[i].step(ch));
-            }
-    // whole-ensemble compute plans: queue every device's kernels first, then collect the downloads
-    for (size_t i = 0; i < G; i++)
-        if (pipes[i].h) { CU(g, cudaSetDevice(g->shard[i]->p.device)); CHILD(g, g->shard[i], pipes[i].finish_compute()); }
-    for (size_t i = 0; i < G; i++)
-        if (pipes[i].h) { CU(g, cudaSetDevice(g->shard[i]->p.device)); CHILD(g, g->shard[i], pipes[i].finish()); }
-    return SWRT_OK;
-}
-
-int grp_set_packets(swrt_handle* g, int64_t n, const double* x, const double* y, const double* k, const double* l, const double* a) {
-    REQUIRE(g, n >= 0, SWRT_ERR_ARG, "negative packet count");
-    REQUIRE(g, n == 0 || (x && y && k && l), SWRT_ERR_ARG, "null packet array");
-    grp_split(g, n);
-    const double* in[5] = {x, y, k, l, a};
-    return grp_pipes(g, true, in, nullptr, 0, 0.0, 0, 0.0, 0.0);
-}
-int grp_get_packets(swrt_handle* g, double* x, double* y, double* k, double* l, double* a) {
-    double* out[5] = {x, y, k, l, a};
-    return grp_pipes(g, false, nullptr, out, 0, 0.0, 0, 0.0, 0.0);
-}
-int grp_step_host(swrt_handle* g, int scheme, double dt, int nsteps, double alpha0, double dalpha, int64_t n,
-                  const double* const in[5], double* const out[5]) {
-    grp_split(g, n);
-    return grp_pipes(g, true, in, out, scheme, dt, nsteps, alpha0, dalpha);
-}
-
-int grp_step(swrt_handle* g, int scheme, double dt, int nsteps, double alpha0, double dalpha, bool sync) {
-    EACH(g, c) CHILD(g, c, step_impl(c, scheme, dt, nsteps, alpha0, dalpha, false));      // all devices queued ...
-    return sync ? grp_sync(g) : SWRT_OK;                                                  // ... before the host waits
-}
-
-// histogram of every shard, counts all-reduced in place on the devices; returns with the reduce queued on the streams
-int grp_hist_queue(swrt_handle* g, int kind, double alpha, const double* edges, int nedges) {
-    EACH(g, c) { CU(g, cudaSetDevice(c->p.device)); CHILD(g, c, hist_to_device(c, kind, alpha, edges, nedges)); }
-    return grp_allreduce(g, [](swrt_handle* c) { return (void*)c->counts_dev; }, (size_t)(nedges - 1), ncclUint64, ncclSum);
-}
-int grp_hist_omega(swrt_handle* g, int kind, double alpha, const double* edges, int nedges, uint64_t* counts, int accumulate) {
-    REQUIRE(g, counts, SWRT_ERR_ARG, "null counts");
-    int rc = grp_hist_queue(g, kind, alpha, edges, nedges);
-    if (rc) return rc;
-    swrt_handle* c0 = g->shard[0];
-    std::vector<uint64_t> tmp(nedges - 1);
-    CU(g, cudaSetDevice(c0->p.device));
-    CU(g, cudaMemcpyAsync(tmp.data(), c0->counts_dev, (size_t)(nedges - 1) * 8, cudaMemcpyDeviceToHost, c0->stream));
-    if ((rc = grp_sync(g))) return rc;
-    for (int i = 0; i < nedges - 1; i++) counts[i] = accumulate ? counts[i] + tmp[i] : tmp[i];
-    return SWRT_OK;
-}
-int grp_hist_omega_dev(swrt_handle* g, int kind, double alpha, const double* edges, int nedges, uint64_t** counts_dev, bool wait) {
-    REQUIRE(g, counts_dev, SWRT_ERR_ARG, "null counts_dev");
-    int rc = grp_hist_queue(g, kind, alpha, edges, nedges);
-    if (rc) return rc;
-    swrt_handle* c0 = g->shard[0];
-    CU(g, cudaSetDevice(c0->p.device));
-    if (!c0->hist_ev) CU(g, cudaEventCreateWithFlags(&c0->hist_ev, cudaEventDisableTiming));
-    CU(g, cudaEventRecord(c0->hist_ev, c0->stream));
-    *counts_dev = reinterpret_cast<uint64_t*>(c0->counts_dev);          // the reduced counts, on the first device
-    return wait ? grp_sync(g) : SWRT_OK;
-}
-
-int grp_diag(swrt_handle* g, double alpha, double out[8]) {
-    // per-shard diagnostics, then SUM / MAX / MIN all-reduces of the eight scalars (three copies of them per device)
-    EACH(g, c) {
-        CU(g, cudaSetDevice(c->p.device));
-        CHILD(g, c, diag_launch(c, alpha));
-        for (int r = 0; r < 3; r++)
-            CU(g, cudaMemcpyAsync(c->red_dev + 8 * r, c->diag_dev, 8 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    }
-    int rc;
-    if ((rc = grp_allreduce(g, [](swrt_handle* c) { return (void*)c->red_dev; }, 8, ncclFloat64, ncclSum))) return rc;
-    if ((rc = grp_allreduce(g, [](swrt_handle* c) { return (void*)(c->red_dev + 8); }, 8, ncclFloat64, ncclMax))) return rc;
-    if ((rc = grp_allreduce(g, [](swrt_handle* c) { return (void*)(c->red_dev + 16); }, 8, ncclFloat64, ncclMin))) return rc;
-    swrt_handle* c0 = g->shard[0];
-    double r[24];
-    CU(g, cudaSetDevice(c0->p.device));
-    CU(g, cudaMemcpyAsync(r, c0->red_dev, sizeof r, cudaMemcpyDeviceToHost, c0->stream));
-    if ((rc = grp_sync(g))) return rc;
-    for (int i = 0; i < 8; i++) out[i] = r[i];       // sums: omega, Omega, non-finite count, a, n, omega*a
-    out[2] = r[8 + 2];                               // max omega
-    out[3] = r[16 + 3];                              // min omega
-    return SWRT_OK;
-}
-
-// ode23: the error norm couples ALL packets (qgsw_raytrace.m:149), so the per-shard inf-norms are MAX-all-reduced (as the
-// bit patterns of non-negative doubles, which order like unsigned integers) before the host controller sees them
-int grp_bs23_norm(swrt_handle* g, double* out) {
-    int rc = grp_allreduce(g, [](swrt_handle* c) { return (void*)c->bs_norm_dev; }, 1, ncclUint64, ncclMax);
-    if (rc) return rc;
-    swrt_handle* c0 = g->shard[0];
-    CU(g, cudaSetDevice(c0->p.device));
-    CHILD(g, c0, bs23_read_norm(c0, out));
-    return grp_sync(g);
-}
-int grp_bs23_begin(swrt_handle* g, double alpha, double threshold, double* rh_norm) {
-    EACH(g, c) { CU(g, cudaSetDevice(c->p.device)); CHILD(g, c, bs23_begin_launch(c, alpha, threshold)); }
-    return grp_bs23_norm(g, rh_norm);
-}
-int grp_bs23_attempt(swrt_handle* g, double hstep, const double alpha[3], double threshold, double* err_norm) {
-    EACH(g, c) { CU(g, cudaSetDevice(c->p.device)); CHILD(g, c, bs23_attempt_launch(c, hstep, alpha, threshold)); }
-    return grp_bs23_norm(g, err_norm);
-}
-
-int grp_ideal_omega_hist(swrt_handle* g, double alpha, int64_t npts, const double* x, const double* y, const double* kvx,
-                         const double* kvy, int nangles, double omega0, const double* edges, int nedges, uint64_t* counts) {
-    REQUIRE(g, npts >= 0 && x && y && counts && nedges >= 2, SWRT_ERR_ARG, "null argument");
-    // the caller's grid points are sharded like packets; integer counts add exactly
-    std::vector<uint64_t> part(nedges - 1);
-    for (int i = 0; i < nedges - 1; i++) counts[i] = 0;
-    const int64_t G = g->ngpu;
-    for (int64_t i = 0; i < G; i++) {
-        const int64_t lo = (i * npts) / G, hi = ((i + 1) * npts) / G;
-        swrt_handle* c = g->shard[i];
-        CHILD(g, c, swrt_ideal_omega_hist(c, alpha, hi - lo, x + lo, y + lo, kvx, kvy, nangles, omega0, edges, nedges, part.data()));
-        for (int b = 0; b < nedges - 1; b++) counts[b] += part[b];
-    }
-    return SWRT_OK;
-}
-
-}  // namespace
+#include "swrt_group.inc"     // multi-device handles: sharding + in-library NCCL

@@ -278,3 +278,53 @@ def test_spectral_fused_rk4_equals_the_composed_launches(nx, scheme, flow):
     assert launches[1] >= 9 * m                                  # 4-5 evaluations + 4 stage kernels + the final update, per step
     if xka:
         assert np.abs(res[0][4] - np.linspace(0.5, 2.0, w.n_packets)).max() > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# where the x twiddles live: rotation in registers / shared-memory table / global (L2) table
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx", [64, 128, 256])
+def test_twiddle_homes_agree_and_match_the_exact_sum(nx):
+    """swrt_set_tuning bits 3-4 pick where the dense kernel keeps a step's x twiddles.  The three homes run the SAME
+    recurrences (the table forms tabulate them), so the evaluations agree to the last bits (<= 1e-14 of max|plane|), and each
+    is within 1e-12 of the long-double exact-sum oracle; 20 leapfrog steps agree to 1e-12.  256^2 exercises the L2 table
+    that is now the default above 128^2."""
+    from oracle import c_oracle as CO
+    w = W.make_workload("C3", n_packets=389, nx=nx)
+    planes = W.planes_from_psik(w.psik, w.L, w.u_mean)
+    ref = CO.spectral_eval(w.x, w.y, planes, w.dx, nx, precise=True)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    evs, trajs, homes = [], [], []
+    for tw in (0, 1, 2, 3):
+        eng = S.Engine(nx, w.L, w.f, w.gH, S.MODE_SPECTRAL)
+        eng.set_tuning(twiddles=tw)
+        eng.set_flow_spectral(w.psik, 0, w.u_mean)
+        eng.set_packets(w.x, w.y, w.k, w.l)
+        ev = eng.eval()
+        assert (np.abs(ev - ref) / scale).max() < 1e-12, (nx, tw)
+        eng.step(S.SCHEME_LEAPFROG, w.dt, 20)
+        evs.append(ev); trajs.append(np.stack(eng.get_packets()))
+        eng.close()
+    for ev, tr in zip(evs[1:], trajs[1:]):
+        assert (np.abs(ev - evs[0]) / scale).max() < 1e-14
+        assert np.abs(tr - trajs[0]).max() < 1e-12
+    geo = S.engine.spectral_geometry(nx, 3, 1)
+    assert geo["twiddle_table"] == (1 if nx <= 128 else 2)
+
+
+def test_a_blown_up_packet_does_not_poison_its_neighbours():
+    """non-finite packets travel through swrt_step_host (chunked, staged) without touching the others; swrt_diag counts them"""
+    w = W.make_workload("C2", n_packets=40000, nx=32)
+    x = w.x.copy(); k = w.k.copy()
+    bad = [0, 17, 16384, 39999]
+    x[bad[:2]] = np.nan; k[bad[2:]] = np.inf
+    for mode in MODES.values():
+        eng = _engine(w, mode)
+        got = np.stack(eng.step_host(S.SCHEME_LEAPFROG, w.dt, 3, x, w.y, k, w.l))
+        clean = _engine(w, mode)
+        ref = np.stack(clean.step_host(S.SCHEME_LEAPFROG, w.dt, 3, w.x, w.y, w.k, w.l))
+        good = np.ones(w.n_packets, dtype=bool); good[bad] = False
+        assert np.array_equal(got[:, good], ref[:, good])
+        assert not np.isfinite(got[:, bad]).all(axis=0).any()
+        assert eng.diag()[4] == len(bad)
+        eng.close(); clean.close()
