@@ -13,7 +13,7 @@ pw = 1/3; threshold = atol / rtol;
 hmax = min(abs(tfinal - t0), abs(0.1 * (tfinal - t0)));
 t = t0;
 rh = swrt_mex('bs23_begin', eng, t / tmax, threshold) / (0.8 * rtol^pw);
-absh = min(hmax, abs(tfinal - t0));
+absh = min(hmax, abs(tspan(2) - tspan(1)));          % MATLAB's htspan: the FIRST output interval bounds the initial step
 if absh * rh > 1, absh = 1 / rh; end
 absh = max(absh, 16 * eps(t));
 nsteps = 0; nfailed = 0; done = false;
