@@ -522,6 +522,8 @@ def interpolate_dev(x, y, F, dx, dy, bump=1e-13, device=0):
     lib = load_library()
     x = _f64(x); shp = x.shape
     x = x.ravel(); y = _f64(y).ravel()
+    if x.size != y.size:
+        raise ValueError(f"interpolate: x has {x.size} elements, y has {y.size}")
     F = np.asarray(F, dtype=np.float64)
     nx, ny = F.shape
     Ff = _colmajor(F)

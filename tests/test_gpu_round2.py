@@ -328,3 +328,20 @@ def test_a_blown_up_packet_does_not_poison_its_neighbours():
         assert not np.isfinite(got[:, bad]).all(axis=0).any()
         assert eng.diag()[4] == len(bad)
         eng.close(); clean.close()
+
+
+def test_interpolate_rejects_what_matlab_would_reject():
+    """interpolate.m:45-46 wraps BOTH stencil indices with nx, so an nx x ny array with ny < nx makes MATLAB raise
+    "index exceeds array bounds"; swrt_interpolate returns SWRT_ERR_ARG instead of reading out of bounds, and the Python
+    mirror refuses x / y of different lengths"""
+    F = np.arange(8.0 * 6).reshape(8, 6)
+    with pytest.raises(S.SwrtError) as ei:
+        S.interpolate_dev(np.array([1.0]), np.array([1.0]), F, 1.0, 1.0)
+    assert ei.value.code == -1 and "ny >= nx" in str(ei.value)
+    with pytest.raises(ValueError):
+        S.interpolate_dev(np.zeros(3), np.zeros(4), np.zeros((8, 8)), 1.0, 1.0)
+    # ny > nx is legal in the reference (only the first nx columns are ever read) and matches the restatement bit for bit
+    from oracle import swrt_oracle as O
+    G = np.random.RandomState(1).standard_normal((8, 11))
+    x, y = np.random.RandomState(2).uniform(-20, 20, (2, 50))
+    assert np.array_equal(S.interpolate_dev(x, y, G, 0.7, 0.7), O.interpolate(x, y, G, 0.7, 0.7))
