@@ -82,10 +82,11 @@ def test_fused_run_longer_than_the_blend_arena():
 
 
 @pytest.mark.parametrize("mode", list(MODES))
-@pytest.mark.parametrize("n", [1, 1000, 16384, 70001, 300007])
+@pytest.mark.parametrize("n", [1, 1000, 16384, 70001, 300007, 800003])
 def test_step_host_equals_set_step_get(mode, n):
     """swrt_step_host == swrt_set_packets + swrt_step + swrt_get_packets bit for bit; sizes straddle the staging chunks
-    (one chunk, exact chunk, ragged tails, more chunks than ring slots); pageable numpy buffers"""
+    (one chunk, exact chunk, ragged tails, more chunks than ring slots; 800,003 packets also puts the dense kernel on its
+    chunked path: whole waves of 64-packet tiles per chunk); pageable numpy buffers"""
     w = W.make_workload("C3", n_packets=n, nx=32)
     eng = _engine(w, MODES[mode])
     m = 3
