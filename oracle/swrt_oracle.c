@@ -3,11 +3,14 @@
  * TEST INFRASTRUCTURE ONLY: this is the CPU checker/baseline.  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may load it; the product (libswrt.so) never
  * links or calls it.  Parity status: the packet arithmetic restated here (interpolate, leapfrog,
- * step_packet*, histcounts) is "parity unpinned" against MATLAB -- the reference stores no packet
- * outputs and cannot run here (no MATLAB/Octave); this file is pinned against oracle/swrt_oracle.py
- * and the known-answer tests derived from the reference's scripts (tests/test_oracle_kat.py).  The
- * spectral kit / initial-condition chain of the numpy oracle IS pinned against the reference's
- * stored run logs and pv_time stream (tests/test_reference_goldens.py).
+ * step_packet*) is PINNED to the outputs of the unmodified reference .m files, executed from
+ * /root/reference by oracle/minimat (the MATLAB-subset interpreter of this repository; no MATLAB /
+ * Octave in the image): tests/golden/octave_out/*.bin, held to 1e-12 / 1e-9 by
+ * tests/test_octave_goldens.py::test_c_port_against_reference_outputs, and this file is bit-identical
+ * to oracle/swrt_oracle.py.  histcounts is a MATLAB builtin (nothing of the reference's to execute):
+ * pinned by known-answer tests (tests/test_oracle_kat.py).  The spectral kit / initial-condition
+ * chain of the numpy oracle is pinned against the reference's stored run logs and pv_time stream
+ * (tests/test_reference_goldens.py).
  *
  * Every function cites the reference file:line it follows (relative to /root/reference).
  * Arrays are MATLAB column-major: F[ix + nx*iy]; spectral planes fk[(kx+kmax) + nkx*ky].

@@ -16,11 +16,25 @@ Parity status -- what is pinned and what is not:
   ten U_g -- reproduced digit for digit -- and the stored ``pv_time`` frame stream (2,682 frames of
   ``t = t + dt``) is reproduced bit for bit but for three frames at 1-2 ulps, which fixes U0 to a
   few ulps of what MATLAB computed.
-* **parity unpinned** for the packet arithmetic itself (``interpolate``, ``interpolate_U``,
-  ``ode_symplectic``, ``step_packet*``) and at the MATLAB-builtin boundary ``ode23``: the reference
-  stores no packet outputs (``packet_*.bin`` are git-ignored), has no tests, and neither MATLAB nor
-  GNU Octave exists in this image.  Those functions are pinned by the known-answer tests derived
-  from the reference's own scripts (``tests/test_oracle_kat.py``):
+* **Pinned against the reference itself, executed here** for the packet arithmetic (``interpolate``,
+  ``interpolate_U``, the ``odefun`` right-hand side, ``SpectralScheme`` constructor / ``U`` / ``grad_U`` /
+  ``grad_U_times_k``, ``ode_symplectic`` x 100 steps, ``cg_sw``, ``step_packet`` and ``step_packet_xka`` x 3
+  steps): ``tests/golden/octave_out/*.bin`` are the outputs of the UNMODIFIED reference ``.m`` files, run from
+  where they lie under /root/reference by ``oracle/minimat`` (the MATLAB-subset interpreter of this repository --
+  neither MATLAB nor GNU Octave exists in the image) through the recipe ``tests/golden/make_octave_goldens.m`` on
+  203 seeded packets; generator ``tests/golden/run_reference_recipe.py``, provenance (sha256 of every executed
+  reference file) in ``octave_out/PROVENANCE.json``.  ``tests/test_octave_goldens.py`` holds this module, the C port
+  and -- under ``-m gpu`` -- the CUDA path to them at 1e-12 (fields, RHS) / 1e-9 (trajectories); measured: this
+  module equals them BIT FOR BIT on all twelve outputs.  The interpreter is generic MATLAB semantics, not a
+  restatement of the path, and is itself pinned to numbers real MATLAB produced (``tests/test_minimat.py``: the
+  unmodified ``qgsw_raytrace.m`` run under it prints MATLAB R2020b's log header character for character and lands
+  within 2 ulps of the stored ``pv_time`` stream; the unmodified ``rsw/k2g.m`` reproduces ``rsw/matlab.mat``).
+  The same recipe runs unchanged under real MATLAB / Octave (``tests/golden/make_octave_goldens.m``'s header) for
+  anyone who wants the cross-check; its output would replace the committed files one for one.
+* **parity unpinned** only at the MATLAB-builtin boundary ``ode23``: it is MathWorks code, not the reference's,
+  so there is nothing of the reference's to execute; the restated controller is checked against scipy's RK23
+  tableau, closed forms and MATLAB's documented step-size rules (``tests/test_oracle_kat.py``).  The known-answer
+  tests derived from the reference's own scripts stay as a second net:
   grid-node identity of ``interpolate``, the closed-form Childress-Soward flow of
   ``ray_trace_sw/raytrace.m:31-37``, the zero-flow analytic trajectory, the direct trig-sum pattern
   of ``scratch/fourier_interpolate_test.m:92-136``, the ``g2k(k2g(.))`` round trip, and the

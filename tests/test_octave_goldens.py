@@ -1,12 +1,17 @@
-"""Hot-path parity against the REFERENCE ITSELF, when its outputs are available.
+"""Hot-path parity against the REFERENCE ITSELF.
 
-``tests/golden/make_octave_goldens.m`` runs the unmodified reference functions (interpolate, interpolate_U, SpectralScheme.U /
-grad_U / grad_U_times_k, ode_symplectic x 100 steps, cg_sw, step_packet, step_packet_xka) under MATLAB / GNU Octave on the
-seeded inputs of ``tests/golden/hotpath_nx32.npz`` and writes raw fp64 files with the reference's own ``write_field.m`` into
-``tests/golden/octave_out/``.  Neither MATLAB nor Octave exists in the development image, so until someone runs that
-script and commits its output these tests XFAIL with "parity unpinned"; once the files exist, the CPU oracle (numpy and C)
-and -- in the ``gpu`` tests -- the CUDA path through the C ABI are held to them: fields / RHS 1e-12 of max|plane|,
-trajectories (<= 100 steps) 1e-9.
+``tests/golden/octave_out/*.bin`` are the outputs of the UNMODIFIED reference functions (interpolate, interpolate_U,
+SpectralScheme constructor / U / grad_U / grad_U_times_k, ode_symplectic x 100 steps, cg_sw, step_packet, step_packet_xka) on the
+seeded inputs of ``tests/golden/hotpath_nx32.npz`` (203 packets, 32^2 grid, two flow frames, H), written by the reference's own
+``write_field.m``.  The recipe is ``tests/golden/make_octave_goldens.m``; it runs unchanged under MATLAB / GNU Octave, and --
+because neither exists in the development image -- was executed by ``oracle/minimat``, this repository's MATLAB-subset
+interpreter, straight from the ``.m`` files under /root/reference (``tests/golden/run_reference_recipe.py``;
+``octave_out/PROVENANCE.json`` records the sha256 of every reference file that ran).  ``tests/test_minimat.py`` pins the
+interpreter itself to numbers real MATLAB produced and re-runs a slice of the recipe against the committed files.
+
+Here the CPU oracle (numpy and C) and -- in the ``gpu`` tests -- the CUDA path through the C ABI are held to those files:
+fields / RHS 1e-12 of max|plane|, trajectories (<= 100 steps) 1e-9.  Should the files be missing the tests XFAIL with
+"parity unpinned" rather than pass.
 
 ``test_golden_file_pipeline_self_check`` proves the plumbing (file format, array orientation, every comparison) on stand-in
 files written by the oracle into a temporary directory.  That is a self-check of this test module, NOT a pin."""
@@ -40,8 +45,8 @@ def have_goldens(d=OUT):
 
 def need_goldens():
     if not have_goldens():
-        pytest.xfail("parity unpinned: tests/golden/octave_out/ is absent -- run tests/golden/make_octave_goldens.m under MATLAB / "
-                     "GNU Octave against the reference checkout and commit its output")
+        pytest.xfail("parity unpinned: tests/golden/octave_out/ is absent -- run tests/golden/run_reference_recipe.py (or "
+                     "make_octave_goldens.m under MATLAB / GNU Octave) against the reference checkout and commit its output")
 
 
 def inputs():
@@ -126,6 +131,17 @@ def test_oracle_against_reference_outputs():
     """numpy oracle == the reference's own outputs (interpolate ... step_packet_xka)"""
     need_goldens()
     check_oracle_against(OUT)
+
+
+def test_oracle_is_bit_identical_to_the_reference_as_executed():
+    """stronger than the tolerance: on all twelve outputs the numpy restatement and the unmodified reference (as executed by
+    oracle/minimat) agree to the last bit -- two independent implementations of the same operation order.  (Files regenerated
+    under real MATLAB / Octave would keep the per-packet arithmetic bit-identical but could move the FFT-derived
+    ``scheme_*`` outputs by an ulp, FFTW vs pocketfft; relax those names to TOL_FIELD then.)"""
+    need_goldens()
+    I = inputs(); mine = oracle_outputs(I); shp = shapes(I)
+    for name in EXPECTED:
+        assert np.array_equal(np.asarray(mine[name]), read_bin(OUT, name, *shp[name])), name
 
 
 def test_c_port_against_reference_outputs():
