@@ -74,7 +74,8 @@ typedef struct swrt_params {
     double  L;         /* domain side; dx = L/nx (qgsw_raytrace.m:13-14)                        */
     double  f;         /* Coriolis parameter                                                    */
     double  gH;        /* Cg^2 = C0^2 (ode_symplectic.m:10-11)                                  */
-    double  bump;      /* Lagrange "bump": 1e-13 (interpolate.m:13) or 1e-10 (interpolate_par)  */
+    double  bump;      /* Lagrange "bump": 1e-13 (ray_trace_sw/interpolate.m:13) or 1e-10 (qg_flow_ray_trace/interpolate.m:13 -- the
+                          copy interpolate_U.m and the QG drivers' odefun run beside -- and interpolate_par.m:13) */
     int32_t ngpu;      /* devices device .. device+ngpu-1 share the packets (0 or 1 = one device)  */
     int32_t reserved;  /* must be 0                                                             */
 } swrt_params;

@@ -9,7 +9,8 @@ par = [nx, h];
 if isempty(eng) || ~isequal(par, cpar) || ~isequal(background_flow1, c1) || ~isequal(background_flow2, c2)
     if isempty(eng) || ~isequal(par, cpar)
         if ~isempty(eng), swrt_mex('destroy', eng); eng = []; end
-        eng = swrt_mex('create', nx, h * nx, 1, 1, 1);                 % mode 1 = LAGRANGE6
+        eng = swrt_mex('create', nx, h * nx, 1, 1, 1, 0, 1e-10);       % mode 1 = LAGRANGE6, device 0, bump 1e-10 (the
+                                                                       % interpolate.m beside interpolate_U.m, qg_flow_ray_trace/interpolate.m:13)
     end
     b = background_flow1; swrt_mex('set_flow_grid', eng, 0, b.u, b.v, b.ux, b.uy, b.vx, b.vy);
     b = background_flow2; swrt_mex('set_flow_grid', eng, 1, b.u, b.v, b.ux, b.uy, b.vx, b.vy);

@@ -1078,9 +1078,23 @@ def _cellfun(I, args, nargout, frame):
 
 @reg("arrayfun")
 def _arrayfun(I, args, nargout, frame):
-    f, x = args[0], to_arr(args[1])
-    outs = [I.call_handle(f, [simplify(np.array([[q]]))], 1, frame)[0] for q in x.reshape(-1, order="F")]
-    return simplify(np.array([to_arr(o).reshape(-1)[0] for o in outs]).reshape(x.shape, order="F"))
+    f = args[0]
+    arrs = []
+    for a in args[1:]:
+        if type(a) is str:
+            break
+        arrs.append(to_arr(a))
+    if any(x.shape != arrs[0].shape for x in arrs):
+        raise MatlabError("arrayfun: all inputs must have the same size")
+    cols = [x.reshape(-1, order="F") for x in arrs]
+    outs = []
+    for q in range(arrs[0].size):
+        r = I.call_handle(f, [simplify(np.array([[c[q]]])) for c in cols], 1, frame)
+        o = to_arr(r[0])
+        if o.size != 1:
+            raise MatlabError("arrayfun: non-scalar output with UniformOutput = true")
+        outs.append(o.reshape(-1)[0])
+    return simplify(np.array(outs).reshape(arrs[0].shape, order="F")) if outs else np.zeros(arrs[0].shape)
 
 
 # ------------------------------------------------------------------------------------------------ files, path, time
@@ -1352,6 +1366,18 @@ def _clock(I, args, nargout, frame):
     return np.array([[float(t.tm_year), float(t.tm_mon), float(t.tm_mday), float(t.tm_hour), float(t.tm_min), float(t.tm_sec)]])
 
 
+@reg("clear")
+def _clear(I, args, nargout, frame):
+    if frame is None:
+        return
+    names = [a for a in args if type(a) is str and not a.startswith("-")]
+    if not names or names == ["all"] or names == ["variables"]:
+        frame.vars.clear()
+        return
+    for nm in names:
+        I.owner(frame, nm).vars.pop(nm, None) if frame.parent is not None else frame.vars.pop(nm, None)
+
+
 # graphics and session commands the driver scripts sprinkle around the numerics: accepted, ignored
 def _noop(I, args, nargout, frame):
     return [EMPTY] * nargout if nargout else None
@@ -1359,6 +1385,6 @@ def _noop(I, args, nargout, frame):
 
 for _n in ("figure", "hold", "close", "clc", "clf", "drawnow", "format", "more", "axis", "colorbar", "shading", "plot", "pcolor",
            "title", "xlabel", "ylabel", "legend", "caxis", "colormap", "set", "pause", "subplot", "scatter", "quiver", "contour",
-           "imagesc", "print", "saveas", "xlim", "ylim", "grid", "box", "clear", "getframe", "writeVideo", "open", "view", "surf",
+           "imagesc", "print", "saveas", "xlim", "ylim", "grid", "box", "getframe", "writeVideo", "open", "view", "surf",
            "mesh", "loglog", "semilogx", "semilogy", "histogram", "sgtitle", "daspect", "text", "line", "gca", "gcf", "clim"):
     TABLE[_n] = _noop

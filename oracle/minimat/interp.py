@@ -500,13 +500,8 @@ class Interp:
             raise MatlabError(f"field assignment to a value of class {mclass(cur)}")
         subs = self.eval_subs(arg, fr, cur if cur is not None else EMPTY)
         if kind == "()":
-            if type(cur) in (MStructArr, MStruct) or (cur is None and not last):
-                items = list(cur.items) if type(cur) is MStructArr else ([cur] if cur is not None else [])
-                j = int(subs[0]) - 1
-                while len(items) <= j:
-                    items.append(MStruct())
-                items[j] = self.assign_into(items[j], acc, i + 1, v, fr) if not last else v
-                return items[0] if len(items) == 1 else MStructArr(items)
+            if type(cur) in (MStructArr, MStruct) or (cur is None and (not last or type(v) is MStruct)):
+                return self._struct_array_assign(cur, subs, acc, i, v, fr, last)
             if type(cur) is MCell:
                 if not last:
                     raise MatlabError("chained assignment through c(...) is not supported")
@@ -538,6 +533,45 @@ class Interp:
             a[pos] = self.assign_into(a[pos] if a[pos] is not None else None, acc, i + 1, v, fr)
             return MCell(a)
         raise MatlabError(f"accessor {kind}")
+
+    def _struct_array_assign(self, cur, subs, acc, i, v, fr, last):
+        """S(r, c) = struct  /  S(r, c).field... = v on an m x n struct array (grows; all elements share one field list)"""
+        if type(cur) is MStructArr:
+            a = cur.a.copy()
+        else:
+            a = np.empty((1, 1) if cur is not None else (0, 0), dtype=object)
+            if cur is not None:
+                a[0, 0] = cur
+        if len(subs) == 1:
+            j = int(subs[0]) - 1
+            r, c = (0, j) if a.shape[0] <= 1 else (j % a.shape[0], j // a.shape[0])
+        else:
+            r, c = int(subs[0]) - 1, int(subs[1]) - 1
+            if any(int(s) != 1 for s in subs[2:]):
+                raise MatlabError("struct arrays with more than two dimensions are not supported")
+        if r < 0 or c < 0:
+            raise MatlabError("subscripts must be positive integers")
+        if r >= a.shape[0] or c >= a.shape[1]:
+            template = list(a.reshape(-1)[0].f) if a.size else []
+            b = np.empty((max(r + 1, a.shape[0]), max(c + 1, a.shape[1])), dtype=object)
+            for q in range(b.size):
+                b.reshape(-1)[q] = MStruct({k: EMPTY for k in template})
+            b[:a.shape[0], :a.shape[1]] = a
+            a = b
+        elem = v if last else self.assign_into(a[r, c], acc, i + 1, v, fr)
+        if type(elem) is not MStruct:
+            raise MatlabError("only structs can be stored in a struct array")
+        other = a.reshape(-1)[0] if (r, c) != (0, 0) else (a.reshape(-1)[-1] if a.size > 1 else None)
+        a[r, c] = elem
+        if other is not None and list(other.f) != list(elem.f):
+            if last and other.f and set(other.f) != set(elem.f):
+                raise MatlabError("subscripted assignment between dissimilar structures")
+            names = list(elem.f) + [k for k in other.f if k not in elem.f]     # a field added to one element exists ([]) in all
+            for q in range(a.size):
+                s = a.reshape(-1)[q]
+                if list(s.f) != names:
+                    a.reshape(-1)[q] = MStruct({k: s.f.get(k, EMPTY) for k in names})
+        return a[0, 0] if a.size == 1 else MStructArr(a)
 
     def _cell_grow(self, a, subs):
         a = a.copy()
@@ -757,10 +791,18 @@ class Interp:
         if t is MCell:
             return self.cell_paren(v, subs)
         if t is MStructArr:
-            if len(subs) == 1 and type(subs[0]) is float:
-                return v.items[int(subs[0]) - 1]
-            pos = to_arr(index(np.arange(1.0, len(v.items) + 1).reshape(1, -1), subs)).reshape(-1)
-            return MStructArr([v.items[int(p) - 1] for p in pos])
+            if len(subs) == 2 and type(subs[0]) is float and type(subs[1]) is float:
+                r, c = int(subs[0]) - 1, int(subs[1]) - 1
+                if not (0 <= r < v.a.shape[0] and 0 <= c < v.a.shape[1]):
+                    raise MatlabError("index exceeds the dimensions of the struct array")
+                return v.a[r, c]
+            lin = np.arange(1.0, v.a.size + 1).reshape(v.a.shape, order="F")
+            pos = to_arr(index(lin, subs))
+            flat = v.a.reshape(-1, order="F")
+            out = np.empty(pos.shape, dtype=object)
+            for q, pp in enumerate(pos.reshape(-1, order="F")):
+                out.reshape(-1, order="F")[q] = flat[int(pp) - 1]
+            return out.reshape(-1)[0] if out.size == 1 else MStructArr(out)
         if t in (MStruct, MObject):
             if all((s is COLON) or (type(s) is float and s == 1.0) for s in subs):
                 return v

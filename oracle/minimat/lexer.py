@@ -4,9 +4,6 @@ import re
 KEYWORDS = {"function", "end", "if", "elseif", "else", "for", "while", "switch", "case", "otherwise", "return", "break",
             "continue", "classdef", "properties", "methods", "global", "persistent", "try", "catch", "parfor", "events",
             "enumeration"}
-# functions the reference calls in command syntax ("addpath ./rsw/", "hold on", "close all")
-CMD_WORDS = {"addpath", "rmpath", "hold", "close", "clear", "clc", "format", "figure", "more", "clf", "drawnow", "axis", "colorbar",
-             "shading", "warning"}
 OPS = ["==", "~=", "!=", "<=", ">=", "&&", "||", ".*", "./", ".\\", ".^", ".'", "+", "-", "*", "/", "\\", "^", "<", ">", "&", "|",
        "~", "!", "=", "(", ")", "[", "]", "{", "}", ",", ";", ":", ".", "@"]
 NUM_RE = re.compile(r"(?:\d+(?:\.(?![*/\\^'])\d*)?|\.\d+)(?:[eEdD][+-]?\d+)?[ij]?")
@@ -149,20 +146,34 @@ def tokenize(src, fname="<string>"):
                 i = m.end()
                 sp = False
                 continue
-            if word in CMD_WORDS and stmt_start():
+            if stmt_start():
+                # command syntax ("addpath ./rsw/", "hold on", "subplot 211", "clear P"): a name at the start of a statement,
+                # white space, then something that cannot continue an expression -- a word, a number, a quote, or one of . / - ~
+                # glued to what follows (MATLAB's own rule for names that are not variables)
                 j = m.end()
                 k = j
                 while k < n and src[k] in " \t":
                     k += 1
-                if k > j and k < n and src[k] not in "=(\n\r;,%":
-                    e = k
-                    while e < n and src[e] not in "\n\r;,%":
-                        e += 1
-                    toks.append(Tok("id", word, sp, line))
-                    toks.append(Tok("cmd", src[k:e].split(), True, line))
-                    i = e
-                    sp = False
-                    continue
+                if k > j and k < n:
+                    c2 = src[k]
+                    nxt = src[k + 1] if k + 1 < n else "\n"
+                    if c2.isalnum() or c2 in "_'\"":
+                        is_cmd = True
+                    elif c2 in "./-~":
+                        oplen = 2 if (c2 == "." and nxt in "*/^\\") else 1       # "a ./b" and "addpath ./rsw/" alike: operator glued
+                        after = src[k + oplen] if k + oplen < n else "\n"          # to what follows, white space before it
+                        is_cmd = after not in " \t=\n\r;,"
+                    else:
+                        is_cmd = False
+                    if is_cmd:
+                        e = k
+                        while e < n and src[e] not in "\n\r;,%":
+                            e += 1
+                        toks.append(Tok("id", word, sp, line))
+                        toks.append(Tok("cmd", [w.strip("'\"") for w in src[k:e].split()], True, line))
+                        i = e
+                        sp = False
+                        continue
             toks.append(Tok("id", word, sp, line))
             i = m.end()
             sp = False

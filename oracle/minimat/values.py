@@ -27,11 +27,21 @@ class MStruct:
 
 
 class MStructArr:
-    """1 x n struct array (what dir() returns)"""
-    __slots__ = ("items",)
+    """m x n struct array: a numpy object array of MStruct (a list makes a 1 x n row, what dir() returns)"""
+    __slots__ = ("a",)
 
     def __init__(self, items):
-        self.items = list(items)
+        if isinstance(items, np.ndarray):
+            self.a = items
+        else:
+            items = list(items)
+            self.a = np.empty((1, len(items)), dtype=object)
+            for i, v in enumerate(items):
+                self.a[0, i] = v
+
+    @property
+    def items(self):
+        return list(self.a.reshape(-1, order="F"))
 
 
 class MCell:
@@ -147,7 +157,7 @@ def msize(v):
     if t is MCell:
         return v.a.shape
     if t is MStructArr:
-        return (1, len(v.items))
+        return v.a.shape
     return (1, 1)
 
 

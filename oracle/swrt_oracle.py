@@ -183,6 +183,11 @@ def grid_U_planes_k(qk, K_d2, K2, kx_, ky_, shear_strength=0.0):
 IORD = 2
 BUMP_LIVE = 1e-13     # ray_trace_sw/interpolate.m:13
 BUMP_PAR = 1e-10      # interpolate_par.m:13
+BUMP_QG = 1e-10       # qg_flow_ray_trace/interpolate.m:13 -- the reference keeps TWO copies of interpolate.m that differ in this one
+#                       line; interpolate_U.m / odefun run next to the qg_flow_ray_trace copy (runqgsw_raytrace.sbatch:25-27 copies
+#                       it into the run directory, qgsw_raytrace is started from there), SpectralScheme.m:8 puts ./ray_trace_sw/ in
+#                       front.  Found by executing the drivers' nested odefun unmodified (tests/test_reference_locals.py): the two
+#                       bumps differ by ~1e-10 of the field, 100 x the 1e-12 the RHS is held to.
 
 
 def _lagrange_weights(a, bump):
@@ -227,17 +232,18 @@ def interpolate_par(x, y, F, dx, dy):
     return interpolate(x, y, F, dx, dy, bump=BUMP_PAR)
 
 
-def interpolate_U(bf1, bf2, alpha, x, h):
+def interpolate_U(bf1, bf2, alpha, x, h, bump=BUMP_QG):
     """qg_flow_ray_trace/interpolate_U.m:1-24.  x: (Np,2).  Returns U (Np,2) and dict nablaU with
-    u_x,u_y,v_x,v_y; linear blend (1-alpha)*F1 + alpha*F2 of twelve interpolations."""
+    u_x,u_y,v_x,v_y; linear blend (1-alpha)*F1 + alpha*F2 of twelve interpolations -- by the ``interpolate.m`` that sits
+    next to it (``bump`` = 1e-10, see BUMP_QG); ``bump=BUMP_LIVE`` gives the same function bound to ray_trace_sw's copy."""
     xx = x[:, 0]; yy = x[:, 1]
-    U1 = np.stack([interpolate(xx, yy, bf1["u"], h, h), interpolate(xx, yy, bf1["v"], h, h)], axis=1)
-    U2 = np.stack([interpolate(xx, yy, bf2["u"], h, h), interpolate(xx, yy, bf2["v"], h, h)], axis=1)
+    U1 = np.stack([interpolate(xx, yy, bf1["u"], h, h, bump), interpolate(xx, yy, bf1["v"], h, h, bump)], axis=1)
+    U2 = np.stack([interpolate(xx, yy, bf2["u"], h, h, bump), interpolate(xx, yy, bf2["v"], h, h, bump)], axis=1)
     U = (1 - alpha) * U1 + alpha * U2
     nablaU = {}
     for name, key in (("u_x", "ux"), ("u_y", "uy"), ("v_x", "vx"), ("v_y", "vy")):
-        g1 = interpolate(xx, yy, bf1[key], h, h)
-        g2 = interpolate(xx, yy, bf2[key], h, h)
+        g1 = interpolate(xx, yy, bf1[key], h, h, bump)
+        g2 = interpolate(xx, yy, bf2[key], h, h, bump)
         nablaU[name] = (1 - alpha) * g1 + alpha * g2
     return U, nablaU
 
@@ -492,10 +498,10 @@ def ode_symplectic(x0, k0, dt, T, f, gH, scheme, save_stride=1):
     return xs, ks, ts
 
 
-def odefun_rhs(x, y, k, l, alpha, bf1, bf2, f, Cg, h):
+def odefun_rhs(x, y, k, l, alpha, bf1, bf2, f, Cg, h, bump=BUMP_QG):
     """qgsw_raytrace.m:259-265 (same in qg2layersw_raytrace.m:298-304): RHS of the ode23 system.
     dxdt = U + Cg*k/sqrt(f^2+Cg^2|k|^2)  (note Cg, not Cg^2); dkdt = -(gradU)^T k."""
-    U, nab = interpolate_U(bf1, bf2, alpha, np.stack([x, y], axis=1), h)
+    U, nab = interpolate_U(bf1, bf2, alpha, np.stack([x, y], axis=1), h, bump)
     w = np.sqrt(f ** 2 + Cg ** 2 * (k * k + l * l))
     dxdt = U[:, 0] + Cg * k / w
     dydt = U[:, 1] + Cg * l / w
@@ -843,7 +849,7 @@ def ode23(odefun, tspan, y0, rtol=1e-3, atol=1e-6):
     return (Y, stats) if dense else (y, stats)
 
 
-def generate_raytracing_ode(bf1, bf2, Npackets, f, Cg, tmax, h, eval6=None):
+def generate_raytracing_ode(bf1, bf2, Npackets, f, Cg, tmax, h, eval6=None, bump=BUMP_QG):
     """qgsw_raytrace.m:258-268: odefun(t, y) on y = [x; y; k; l].  ``eval6(x, y, alpha)`` overrides the
     Lagrange interpolate_U evaluation (used for the SPECTRAL mode oracle)."""
     n = Npackets
@@ -851,7 +857,7 @@ def generate_raytracing_ode(bf1, bf2, Npackets, f, Cg, tmax, h, eval6=None):
     def odefun(t, y):
         x, yy, k, l = y[0:n], y[n:2 * n], y[2 * n:3 * n], y[3 * n:4 * n]
         if eval6 is None:
-            d = odefun_rhs(x, yy, k, l, t / tmax, bf1, bf2, f, Cg, h)
+            d = odefun_rhs(x, yy, k, l, t / tmax, bf1, bf2, f, Cg, h, bump)
         else:
             d = rhs_from_eval(eval6(x, yy, t / tmax), k, l, f, Cg)
         return np.concatenate(d)

@@ -99,7 +99,7 @@ def qgsw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_delay_da
     fieldio.write_field(q, f"{outdir}/pv", 1); fieldio.write_field(0.0, f"{outdir}/pv_time", 1)
 
     qg = QGFlow(nx, L, qk, K_d2, dt, f, Cg, beta=beta, r_drag=r_drag, force_strength=force_strength, device=device)
-    eng = Engine(nx, L, f, Cg ** 2, mode, device)
+    eng = Engine(nx, L, f, Cg ** 2, mode, device, bump=1e-10)     # qg_flow_ray_trace/interpolate.m:13, the copy this driver runs beside
     eng.set_packets(px, py, pk, pl)
     t = 0.0
     tic = time.time()
@@ -431,7 +431,7 @@ def qg2layersw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_de
     writer.write(px, py, pk, pl, dt * (packet_step_start - 1), wrap=False)            # :114-116 (unwrapped initial frame)
     fieldio.write_field(np.stack([q1, -q1], axis=2), f"{outdir}/pv", 1); fieldio.write_field(0.0, f"{outdir}/pv_time", 1)
 
-    eng = Engine(nx, L, f, Cg ** 2, mode, device)
+    eng = Engine(nx, L, f, Cg ** 2, mode, device, bump=1e-10)     # qg_flow_ray_trace/interpolate.m:13, the copy this driver runs beside
     eng.set_packets(px, py, pk, pl)
     t = 0.0
     step = 0

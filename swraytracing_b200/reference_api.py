@@ -47,6 +47,12 @@ def grid_U(qk, K_d2, K2, kx_, ky_, shear_strength=0.0, device=0):
 # ------------------------------------------------------------------------------------------------
 # interpolate / interpolate_par / interpolate2 / interpolate_U
 # ------------------------------------------------------------------------------------------------
+# The reference keeps two copies of interpolate.m that differ in one line: ray_trace_sw/interpolate.m:13 has bump 1e-13 (what
+# SpectralScheme, step_packet* and the raytrace* drivers bind to, SpectralScheme.m:8), qg_flow_ray_trace/interpolate.m:13 has
+# 1e-10 (what interpolate_U.m and the QG drivers' odefun bind to: runqgsw_raytrace.sbatch:25-27 copies that one next to them).
+BUMP_LIVE = 1e-13
+BUMP_QG = 1e-10
+
 
 def interpolate(x, y, F, dx, dy, device=0):
     """ray_trace_sw/interpolate.m:1-50 -- FI = interpolate(x,y,F,dx,dy), bump 1e-13."""
@@ -66,11 +72,12 @@ def interpolate2(x, y, F, dx, dy, device=0):
 
 class FlowFrames:
     """Two background-flow frames resident on the device (what interpolate_U.m:5-17 re-interpolates
-    on every call).  ``bf`` dicts use the reference's field names u,v,ux,uy,vx,vy (grid_U.m:11-17)."""
+    on every call).  ``bf`` dicts use the reference's field names u,v,ux,uy,vx,vy (grid_U.m:11-17).
+    ``bump`` defaults to 1e-10: interpolate_U.m binds to the interpolate.m beside it (BUMP_QG above)."""
 
-    def __init__(self, bf1, bf2, h, f=1.0, gH=1.0, mode=MODE_LAGRANGE6, device=0):
+    def __init__(self, bf1, bf2, h, f=1.0, gH=1.0, mode=MODE_LAGRANGE6, device=0, bump=BUMP_QG):
         nx = np.asarray(bf1["u"]).shape[0]
-        self.eng = Engine(nx, h * nx, f, gH, mode, device)
+        self.eng = Engine(nx, h * nx, f, gH, mode, device, bump=bump)
         self.eng.set_flow_grid(*[bf1[n] for n in ("u", "v", "ux", "uy", "vx", "vy")], slot=0)
         if bf2 is not None:
             self.eng.set_flow_grid(*[bf2[n] for n in ("u", "v", "ux", "uy", "vx", "vy")], slot=1)
@@ -82,14 +89,14 @@ class FlowFrames:
         return U, {"u_x": e[2], "u_y": e[3], "v_x": e[4], "v_y": e[5]}
 
 
-def interpolate_U(background_flow1, background_flow2, alpha, x, h, device=0):
+def interpolate_U(background_flow1, background_flow2, alpha, x, h, device=0, bump=BUMP_QG):
     """qg_flow_ray_trace/interpolate_U.m:1-24 -- [U, nablaU] = interpolate_U(bf1, bf2, alpha, x, h)."""
-    return FlowFrames(background_flow1, background_flow2, h, device=device).interpolate_U(alpha, x)
+    return FlowFrames(background_flow1, background_flow2, h, device=device, bump=bump).interpolate_U(alpha, x)
 
 
-def generate_raytracing_ode(background_flow1, background_flow2, Npackets, f, Cg, tmax, h, device=0, mode=MODE_LAGRANGE6):
+def generate_raytracing_ode(background_flow1, background_flow2, Npackets, f, Cg, tmax, h, device=0, mode=MODE_LAGRANGE6, bump=BUMP_QG):
     """qgsw_raytrace.m:258-268 -- returns odefun(t, y) with y = [x; y; k; l] (4*Np,)."""
-    frames = FlowFrames(background_flow1, background_flow2, h, f=f, gH=Cg * Cg, mode=mode, device=device)
+    frames = FlowFrames(background_flow1, background_flow2, h, f=f, gH=Cg * Cg, mode=mode, device=device, bump=bump)
 
     def odefun(t, y):
         y = np.asarray(y, dtype=np.float64).ravel()

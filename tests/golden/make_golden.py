@@ -37,10 +37,10 @@ def main():
     out["eval_lagrange"] = np.stack([O.interpolate(x, y, g, dx, dx) for g in grids])
     alpha = 0.3
     bf1 = dict(zip(("u", "v", "ux", "uy", "vx", "vy"), grids)); bf2 = dict(zip(("u", "v", "ux", "uy", "vx", "vy"), grids2))
-    U, nab = O.interpolate_U(bf1, bf2, alpha, np.stack([x, y], axis=1), dx)
+    U, nab = O.interpolate_U(bf1, bf2, alpha, np.stack([x, y], axis=1), dx, bump=O.BUMP_LIVE)     # engine-level vectors: the engine's default bump
     out["alpha"] = alpha
     out["interpU_lagrange"] = np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])
-    out["rhs_lagrange"] = np.stack(O.odefun_rhs(x, y, k, l, alpha, bf1, bf2, f, 1.0, dx))
+    out["rhs_lagrange"] = np.stack(O.odefun_rhs(x, y, k, l, alpha, bf1, bf2, f, 1.0, dx, bump=O.BUMP_LIVE))
     sp1 = O.spectral_eval_planes(x, y, planes, dx, nx); sp2 = O.spectral_eval_planes(x, y, planes2, dx, nx)
     out["interpU_spectral"] = (1 - alpha) * sp1 + alpha * sp2
     dt = 0.1 * dx

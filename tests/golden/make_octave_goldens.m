@@ -13,8 +13,17 @@ function make_octave_goldens(refroot, indir, outdir)
 %     matlab -batch "addpath('tests/golden'); make_octave_goldens('/root/reference')"
 % then commit tests/golden/octave_out/*.bin.
 %
+% (The committed octave_out/ was produced by tests/golden/run_reference_recipe.py: this very file and the reference's .m files
+% executed by oracle/minimat, the MATLAB-subset interpreter of this repository, because the build image has no MATLAB / Octave.)
+%
+% The reference holds TWO copies of interpolate.m that differ in one line: ray_trace_sw/interpolate.m:13 (bump 1e-13) and
+% qg_flow_ray_trace/interpolate.m:13 (bump 1e-10).  Which one a caller binds to is a matter of the MATLAB path, and this recipe
+% sets the path the way each caller meets it in the reference's own runs: interpolate_U and the ode23 right-hand side run with
+% qg_flow_ray_trace in front (runqgsw_raytrace.sbatch:25-27 copies that folder's interpolate.m next to qgsw_raytrace.m), everything
+% else with ray_trace_sw in front (SpectralScheme.m:8 does that itself; raytrace.m / raytrace_sw.m live in that folder).
+%
 % Reference functions exercised (file:line = what the oracle restates):
-%   interpolate            ray_trace_sw/interpolate.m:1-50
+%   interpolate            ray_trace_sw/interpolate.m:1-50, qg_flow_ray_trace/interpolate.m:1-50
 %   interpolate_U          qg_flow_ray_trace/interpolate_U.m:1-24
 %   SpectralScheme         SpectralScheme.m:6-36 (ctor: g2k, ik-multiplication, k2g), :45-54 (U), :56-68 (grad_U)
 %   grad_U_times_k         RaytracingScheme.m:9-16
@@ -32,9 +41,9 @@ for i = 1:numel(old), delete(fullfile(outdir, old(i).name)); end      % write_fi
 
 startdir = pwd;
 cd(refroot);                                   % SpectralScheme's constructor does addpath ./rsw/ ./ray_trace_sw/
-addpath(fullfile(refroot, 'qg_flow_ray_trace'));   % read_field, write_field, interpolate_U, g2k, k2g, fulspec
-addpath(fullfile(refroot, 'ray_trace_sw'));        % interpolate, step_packet, step_packet_xka, cg_sw
 addpath(refroot);                                  % SpectralScheme, RaytracingScheme, ode_symplectic
+addpath(fullfile(refroot, 'ray_trace_sw'));        % interpolate (bump 1e-13), step_packet, step_packet_xka, cg_sw
+addpath(fullfile(refroot, 'qg_flow_ray_trace'));   % read_field, write_field, interpolate_U, interpolate (bump 1e-10); now in FRONT
 rd = @(name, m, n) read_field(fullfile(indir, name), m, n, 1, 1, 1);
 put = @(name, A) write_field(A, fullfile(outdir, name), 1);
 
@@ -51,10 +60,11 @@ end
 H = rd('H', nx, nx);
 psi = rd('psi', nx, nx);
 
-% ---- interpolate: the six planes of frame 1, both bumps' live copy (1e-13) --------------------------------------------
+% ==== context of the QG drivers: qg_flow_ray_trace is the first folder of the path, its interpolate.m (bump 1e-10) is the one
+%      interpolate_U and the ode23 right-hand side bind to ======================================================================
 E = zeros(6, np_);
 for c = 1:6, E(c, :) = interpolate(x, y, bf1.(names{c}), dx, dx); end
-put('eval_lagrange', E);
+put('eval_lagrange_qg', E);
 
 % ---- interpolate_U: two frames blended at alpha -------------------------------------------------------------------
 [U, nab] = interpolate_U(bf1, bf2, alpha, [x y], dx);
@@ -66,6 +76,13 @@ om = sqrt(f^2 + Cg^2 * (k.^2 + l.^2));
 dxdt = U + Cg * [k l] ./ om;
 dkdt = -[nab.u_x .* k + nab.v_x .* l, nab.u_y .* k + nab.v_y .* l];
 put('rhs_lagrange', [dxdt(:, 1)'; dxdt(:, 2)'; dkdt(:, 1)'; dkdt(:, 2)']);
+
+% ==== context of SpectralScheme / step_packet* / raytrace*: ray_trace_sw in front (addpath moves it there; SpectralScheme.m:8
+%      does the same), interpolate.m with bump 1e-13 =============================================================================
+addpath(fullfile(refroot, 'ray_trace_sw'));
+E = zeros(6, np_);
+for c = 1:6, E(c, :) = interpolate(x, y, bf1.(names{c}), dx, dx); end
+put('eval_lagrange', E);
 
 % ---- SpectralScheme: constructor from the streamfunction grid, U, grad_U, grad_U_times_k ----------------------------
 scheme = SpectralScheme(L, nx, psi);

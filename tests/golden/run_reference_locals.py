@@ -1,0 +1,161 @@
+#!/usr/bin/env python
+"""Outputs of the reference's FILE-LOCAL and nested functions, executed unmodified -> tests/golden/reference_locals_nx32.npz.
+
+    python tests/golden/run_reference_locals.py [--ref /root/reference]
+
+``make_octave_goldens.m`` can only reach functions that have their own file.  The rest of the path lives inside the driver
+scripts as local / nested functions -- the ``ode23`` right-hand side ``odefun`` (qgsw_raytrace.m:258-268, nested in
+``generate_raytracing_ode``; the same text in qg2layersw_raytrace.m:297-307), the state packing ``ode_xk2y`` / ``ode_y2xk``, the
+QG frame producers ``initial_q``, ``inertial_ring``, ``filter``, ``update`` (one- and two-layer), ``mmult3``, ``apply_3d`` -- and
+no MATLAB session can call those from outside either.  ``oracle/minimat`` can: it parses the unmodified driver file and the
+local function is called directly (``Interp.load_unit(path).funcs[name]``).  Also here, because they need a nested-function
+handle (``arrayfun(@compute_FI, x, y)``) or the six-argument form nobody calls any more: the top-level ``interpolate_par.m``
+(bump 1e-10) and ``qg_flow_ray_trace/grid_U.m`` with a mean shear; and the complex / multi-frame branches of
+``read_field.m`` / ``write_field.m``.  And one driver script as a whole: ``ray_trace_sw/raytrace.m`` (packet 1, 300 steps).
+
+Inputs: the seeded packets, flow frames and psi-hat of tests/golden/hotpath_nx32.npz.  Run HERE (needs /root/reference); the
+.npz is what travels, with the sha256 of every executed reference file inside (key ``provenance``).
+"""
+import argparse
+import hashlib
+import io
+import json
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle.minimat import Interp, Frame, from_py, MStruct          # noqa: E402
+from oracle import swrt_oracle as O                                  # noqa: E402  (inputs only: g2k of the seeded psi)
+
+NAMES = ("u", "v", "ux", "uy", "vx", "vy")
+
+
+def fa(a):
+    return from_py(np.asfortranarray(np.asarray(a)))
+
+
+def flow_struct(planes):
+    return MStruct({n: fa(p) for n, p in zip(NAMES, planes)})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--out", default=str(HERE / "reference_locals_nx32.npz"))
+    a = ap.parse_args()
+    ref = Path(a.ref)
+    G = np.load(HERE / "hotpath_nx32.npz")
+    nx, L, f = int(G["nx"]), float(G["L"]), float(G["f"])
+    dx = L / nx
+    x, y, k, l = (G[n] for n in ("x", "y", "k", "l"))
+    n = x.size
+    kx_, ky_ = O.wavenumbers(nx)
+    g1 = list(G["grids"])
+    g2 = [O.k2g(p) for p in O.velocity_planes_k(G["psik2"], kx_, ky_)]
+    tmp = Path(tempfile.mkdtemp(prefix="swrt_locals_"))
+    I = Interp(cwd=str(tmp), out=io.StringIO())
+    I.path[:0] = [str(ref / "qg_flow_ray_trace"), str(ref)]
+    out = {}
+
+    # ---- one-layer driver: qg_flow_ray_trace/qgsw_raytrace.m ----------------------------------------------------------
+    u1 = I.load_unit(str(ref / "qg_flow_ray_trace" / "qgsw_raytrace.m"))
+    call = lambda name, *args, nargout=1: I.call_funcdef(u1.funcs[name], [from_py(v) if not isinstance(v, MStruct) else v for v in args],
+                                                         nargout, Frame(u1.main))
+    Cg, tmax = 1.0, 0.37
+    rayode = call("generate_raytracing_ode", flow_struct(g1), flow_struct(g2), float(n), f, Cg, tmax, dx)[0]
+    yvec = call("ode_xk2y", float(n), np.stack([x, y], 1), np.stack([k, l], 1))[0]
+    out["ode_xk2y"] = np.asarray(yvec).ravel()
+    for tag, t in (("t0", 0.0), ("tmid", 0.25 * tmax), ("tend", tmax)):
+        out["odefun_" + tag] = np.asarray(I.call_handle(rayode, [t, yvec], 1, None)[0]).ravel()
+    xx, kk = call("ode_y2xk", float(n), yvec, nargout=2)
+    out["ode_y2xk_x"], out["ode_y2xk_k"] = np.asarray(xx), np.asarray(kk)
+    # QG frame producers on the 32^2 grid (rng(146) -> rand inside initial_q, as the driver does)
+    xs = np.linspace(-L / 2, L / 2, nx)
+    X, Y = np.meshgrid(xs, xs)
+    K2 = kx_ ** 2 + ky_ ** 2
+    I.call("rng", 146.0, nargout=0)
+    K_d2 = 3.0
+    q0 = np.asarray(call("initial_q", X, Y, 0.5, K_d2)[0])
+    out["initial_q"] = q0
+    out["inertial_ring"] = np.asarray(call("inertial_ring", 0.1, K2, 3.0, 0.25)[0])     # f/Cg chosen so that the ring is not empty at 32^2
+    out["filter"] = np.asarray(call("filter", kx_, ky_, dx)[0])
+    qk = O.g2k(q0)
+    out["update_qk_in"] = qk
+    out["update"] = np.asarray(call("update", qk, K2, K_d2, 0.3, 0.1, out["inertial_ring"], kx_, ky_)[0])
+
+    # ---- two-layer driver: qg_flow_ray_trace/qg2layersw_raytrace.m -----------------------------------------------------
+    u2 = I.load_unit(str(ref / "qg_flow_ray_trace" / "qg2layersw_raytrace.m"))
+    call2 = lambda name, *args, nargout=1: I.call_funcdef(u2.funcs[name], [from_py(v) if not isinstance(v, (MStruct,)) and not hasattr(v, "kind") else v for v in args],
+                                                          nargout, Frame(u2.main))
+    B = O.qg2_operators(kx_, ky_, K_d2, 0.0, 0.5, 0.4, 0.01, 4)[0]                      # input only: a (2,2,nkx,nky) operator
+    q2 = np.stack([qk, 0.5 * np.conj(qk[::-1]) * (1 + 0.1j)], axis=2)
+    out["qg2_B"], out["qg2_qk_in"] = B, q2
+    out["qg2_mmult3"] = np.asarray(call2("mmult3", B, q2)[0])
+    out["qg2_update"] = np.asarray(call2("update", q2, B, kx_, ky_)[0])
+    out["qg2_diag_exp"] = np.asarray(call2("diag_exp", B.astype(complex) * (1 + 0.5j), 0.3)[0])
+    rayode2 = call2("generate_raytracing_ode", flow_struct(g1), flow_struct(g2), float(n), f, Cg, tmax, dx)[0]
+    out["qg2_odefun_tmid"] = np.asarray(I.call_handle(rayode2, [0.25 * tmax, yvec], 1, None)[0]).ravel()
+
+    # ---- files of their own that the MATLAB-side recipe cannot drive ---------------------------------------------------
+    out["interpolate_par"] = np.stack([np.asarray(I.call("interpolate_par", x, y, g, dx, dx)).ravel() for g in g1])
+    shear = 0.35
+    flow = I.call("grid_U", qk, K_d2, K2, kx_, ky_, shear)
+    out["grid_U_shear"] = np.stack([np.asarray(flow.f[nm]) for nm in NAMES])
+    out["grid_U_shear_value"] = np.float64(shear)
+    # write_field / read_field: complex (staggered real / imaginary frames) and multi-frame real files
+    (tmp / "io").mkdir()
+    I.call("write_field", qk, "io/spec", 1.0, nargout=0)
+    I.call("write_field", 2 * qk, "io/spec", 2.0, nargout=0)
+    out["write_field_complex_bytes"] = np.fromfile(tmp / "io" / "spec.bin")
+    back = I.call("read_field", "io/spec", float(qk.shape[0]), float(qk.shape[1]), 1.0, np.array([[2.0]]))
+    out["read_field_complex_frame2"] = np.asarray(back)
+    for fr_, g in enumerate(g1[:3], 1):
+        I.call("write_field", g, "io/grid", float(fr_), nargout=0)
+    out["read_field_frames_3_1"] = np.asarray(I.call("read_field", "io/grid", float(nx), float(nx), 1.0, np.array([[3.0, 1.0]]), 1.0))
+    I.close_all()
+
+    # ---- a whole driver script: ray_trace_sw/raytrace.m (Childress-Soward flow as written, rand from MATLAB's start-up stream,
+    #      step_packet one packet at a time), run as a script from its own folder and stopped after 300 steps of packet 1 by a
+    #      counting shim in front of the unmodified step_packet.m ---------------------------------------------------------------
+    class _Stop(Exception):
+        pass
+    J = Interp(cwd=str(ref / "ray_trace_sw"), out=io.StringIO())
+    sp = J.load_unit(str(ref / "ray_trace_sw" / "step_packet.m")).main
+    nrun, count = 300, [0]
+
+    def counted_step_packet(I_, args, nargout, frame):
+        if count[0] >= nrun:
+            raise _Stop()
+        count[0] += 1
+        return I_.call_funcdef(sp, args, nargout, frame)
+    J.overrides["step_packet"] = counted_step_packet
+    ws = Frame(None)
+    try:
+        J.run("raytrace", ws)
+    except _Stop:
+        pass
+    P = ws.vars["P"]
+    out["raytrace_p1"] = np.array([[P.a[0, j].f[c] for c in "xykl"] for j in range(nrun + 1)])
+    out["raytrace_P0"] = np.array([[P.a[i, 0].f[c] for c in "xykl"] for i in range(P.a.shape[0])])
+    out["raytrace_dt"], out["raytrace_nsteps"] = np.float64(ws.vars["dt"]), np.float64(ws.vars["nsteps"])
+    out["raytrace_GradU_v_x"] = np.asarray(ws.vars["GradU"].f["v_x"])          # carries the matrix product of raytrace.m:36
+    for unit_path in J.units:
+        I.units.setdefault(unit_path, J.units[unit_path])
+
+    executed = sorted(p for p in I.units if str(p).startswith(str(ref)))
+    prov = {"made_by": "tests/golden/run_reference_locals.py", "executor": "oracle/minimat",
+            "reference_files_executed": {str(Path(p).relative_to(ref)): hashlib.sha256(Path(p).read_bytes()).hexdigest() for p in executed}}
+    out["provenance"] = np.array(json.dumps(prov))
+    out["tmax"] = np.float64(tmax)
+    np.savez_compressed(a.out, **out)
+    print(f"run_reference_locals: {len(out)} arrays -> {a.out}; executed {len(executed)} reference files")
+
+
+if __name__ == "__main__":
+    main()

@@ -135,7 +135,11 @@ def test_interpolate_U_time_blend_both_modes():
     names = ("u", "v", "ux", "uy", "vx", "vy")
     bf1 = dict(zip(names, g1)); bf2 = dict(zip(names, g2))
     xy = np.stack([GOLD["x"], GOLD["y"]], axis=1)
-    U, nab = R.interpolate_U(bf1, bf2, alpha, xy, dx)
+    U, nab = R.interpolate_U(bf1, bf2, alpha, xy, dx)                  # binds to qg_flow_ray_trace/interpolate.m: bump 1e-10
+    got = np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])
+    Uo, nabo = O.interpolate_U(bf1, bf2, alpha, xy, dx)
+    assert scaled_err(got, np.stack([Uo[:, 0], Uo[:, 1], nabo["u_x"], nabo["u_y"], nabo["v_x"], nabo["v_y"]])) < TOL_FIELD
+    U, nab = R.interpolate_U(bf1, bf2, alpha, xy, dx, bump=R.BUMP_LIVE)    # the same function beside ray_trace_sw's copy
     got = np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])
     assert scaled_err(got, GOLD["interpU_lagrange"]) < TOL_FIELD
     with S.Engine(nx, L, F0, GH0, S.MODE_SPECTRAL) as e:
@@ -194,9 +198,12 @@ def test_rhs_both_modes():
     names = ("u", "v", "ux", "uy", "vx", "vy")
     bf1 = dict(zip(names, [O.k2g(p) for p in O.velocity_planes_k(GOLD["psik"], kx_, ky_)]))
     bf2 = dict(zip(names, [O.k2g(p) for p in O.velocity_planes_k(GOLD["psik2"], kx_, ky_)]))
-    ode = R.generate_raytracing_ode(bf1, bf2, x.size, F0, 1.0, 2.0, dx)
+    ode = R.generate_raytracing_ode(bf1, bf2, x.size, F0, 1.0, 2.0, dx, bump=R.BUMP_LIVE)
     dydt = ode(alpha * 2.0, np.concatenate([x, y, k, l]))
     assert scaled_err(dydt.reshape(4, -1), GOLD["rhs_lagrange"]) < TOL_FIELD
+    ode = R.generate_raytracing_ode(bf1, bf2, x.size, F0, 1.0, 2.0, dx)        # as the QG drivers run it: bump 1e-10
+    want = O.generate_raytracing_ode(bf1, bf2, x.size, F0, 1.0, 2.0, dx)(alpha * 2.0, np.concatenate([x, y, k, l]))
+    assert scaled_err(ode(alpha * 2.0, np.concatenate([x, y, k, l])).reshape(4, -1), want.reshape(4, -1)) < TOL_FIELD
 
 
 @pytest.mark.parametrize("mt", [1, 2])
@@ -591,7 +598,7 @@ def test_ode23_flow_step_matches_oracle(mode):
     n = x.size
     tmax = 0.4                                # one (long) flow step, so that the controller takes several steps
     if mode == S.MODE_LAGRANGE6:
-        ode = O.generate_raytracing_ode(bf1, bf2, n, F0, 1.0, tmax, dx)
+        ode = O.generate_raytracing_ode(bf1, bf2, n, F0, 1.0, tmax, dx, bump=O.BUMP_LIVE)     # the engine below runs its default bump
     else:
         ev = lambda xx, yy, al: CO.spectral_eval(xx, yy, [(1 - al) * a + al * b for a, b in zip(p1, p2)], dx, nx)
         ode = O.generate_raytracing_ode(None, None, n, F0, 1.0, tmax, dx, eval6=ev)
@@ -811,20 +818,20 @@ def test_lagrange_mode_is_bit_identical_to_the_restatement(nx):
     with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
         e.set_flow_grid(*grids, slot=0); e.set_flow_grid(*grids2, slot=1)
         for alpha in (0.0, 0.37, 1.0):
-            U, nab = O.interpolate_U(bf1, bf2, alpha, np.stack([x, y], axis=1), dx)
+            U, nab = O.interpolate_U(bf1, bf2, alpha, np.stack([x, y], axis=1), dx, bump=O.BUMP_LIVE)
             got = e.eval_at(x, y, alpha)
             want = [U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]]
             for c in range(6):
                 assert _bit_equal(got[c], want[c]), (alpha, c, _ulps(got[c], want[c]))
         e.set_packets(x, y, k, l)
         d = e.rhs(0.37)
-        ref = O.odefun_rhs(x, y, k, l, 0.37, bf1, bf2, F0, 1.0, dx)
+        ref = O.odefun_rhs(x, y, k, l, 0.37, bf1, bf2, F0, 1.0, dx, bump=O.BUMP_LIVE)
         for g_, r_, name in zip(d, ref, ("dxdt", "dydt", "dkdt", "dldt")):
             assert _bit_equal(g_, r_), (name, _ulps(g_, r_))
         # the pre-blend tuning (one blended grid, half the gathers) agrees to rounding, not to the bit
         e.set_tuning(0, preblend_grid=True)
         fast = e.eval_at(x, y, 0.37)
-        U, nab = O.interpolate_U(bf1, bf2, 0.37, np.stack([x, y], axis=1), dx)
+        U, nab = O.interpolate_U(bf1, bf2, 0.37, np.stack([x, y], axis=1), dx, bump=O.BUMP_LIVE)
         assert scaled_err(fast, np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])) < 1e-13
     # (4) step_packet / step_packet_xka: 3 RK4 steps of a few packets through the reference's own per-packet functions
     H = 1.0 + 0.2 * grids[0] / np.abs(grids[0]).max()
@@ -1091,9 +1098,9 @@ def test_ode23_in_lagrange_mode_is_bit_identical_to_the_restatement():
     n = 257
     x, y, k, l = make_packets(n, L)
     tmax = 0.05
-    ode = O.generate_raytracing_ode(bf1, bf2, n, F0, 1.0, tmax, h)
+    ode = O.generate_raytracing_ode(bf1, bf2, n, F0, 1.0, tmax, h)               # bump 1e-10, as the QG drivers run it
     yref, sref = O.ode23(ode, [0.0, tmax], np.concatenate([x, y, k, l]))
-    with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
+    with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6, bump=O.BUMP_QG) as e:
         e.set_flow_grid(*[bf1[n_] for n_ in names], slot=0); e.set_flow_grid(*[bf2[n_] for n_ in names], slot=1)
         e.set_packets(x, y, k, l)
         st = R.ode23(e, [0.0, tmax], tmax)

@@ -504,7 +504,7 @@ def _frame_with(**kw):
 
 
 # ------------------------------------------------------------------------- 3. the committed goldens are the reference's output
-EXPECTED = ("eval_lagrange", "interpU_lagrange", "rhs_lagrange", "scheme_eval", "scheme_gradU_times_k", "scheme_fields",
+EXPECTED = ("eval_lagrange", "eval_lagrange_qg", "interpU_lagrange", "rhs_lagrange", "scheme_eval", "scheme_gradU_times_k", "scheme_fields",
             "leapfrog100_scheme", "leapfrog20_scheme", "leapfrog_t", "cg_sw_fields", "rk4x3_packet_lagrange", "rk4x3_xka_lagrange")
 
 
@@ -518,7 +518,7 @@ def test_committed_goldens_are_complete_and_carry_their_provenance():
         assert f.exists(), name
         assert hashlib.sha256(f.read_bytes()).hexdigest() == prov["outputs"][f.name]
     executed = set(prov["reference_files_executed"])
-    assert {"ray_trace_sw/interpolate.m", "qg_flow_ray_trace/interpolate_U.m", "SpectralScheme.m", "RaytracingScheme.m",
+    assert {"ray_trace_sw/interpolate.m", "qg_flow_ray_trace/interpolate.m", "qg_flow_ray_trace/interpolate_U.m", "SpectralScheme.m", "RaytracingScheme.m",
             "ode_symplectic.m", "ray_trace_sw/cg_sw.m", "ray_trace_sw/step_packet.m", "ray_trace_sw/step_packet_xka.m",
             "qg_flow_ray_trace/read_field.m", "qg_flow_ray_trace/write_field.m"} <= executed
     assert {"rsw/g2k.m", "rsw/k2g.m", "rsw/fulspec.m"} <= executed       # SpectralScheme.m:8 puts ./rsw/ in front of the path

@@ -28,7 +28,7 @@ GOLD = np.load(HERE / "golden" / "hotpath_nx32.npz")
 OUT = HERE / "golden" / "octave_out"
 TOL_FIELD, TOL_TRAJ = 1e-12, 1e-9
 NAMES = ("u", "v", "ux", "uy", "vx", "vy")
-EXPECTED = ("eval_lagrange", "interpU_lagrange", "rhs_lagrange", "scheme_eval", "scheme_gradU_times_k", "scheme_fields",
+EXPECTED = ("eval_lagrange", "eval_lagrange_qg", "interpU_lagrange", "rhs_lagrange", "scheme_eval", "scheme_gradU_times_k", "scheme_fields",
             "leapfrog100_scheme", "leapfrog20_scheme", "leapfrog_t", "cg_sw_fields", "rk4x3_packet_lagrange", "rk4x3_xka_lagrange")
 
 
@@ -69,7 +69,8 @@ def oracle_outputs(I):
     """everything make_octave_goldens.m writes, computed by the numpy oracle (same names, same shapes)"""
     x, y, k, l, dx = I["x"], I["y"], I["k"], I["l"], I["dx"]
     out = {}
-    out["eval_lagrange"] = np.stack([O.interpolate(x, y, g, dx, dx) for g in I["g1"]])
+    out["eval_lagrange"] = np.stack([O.interpolate(x, y, g, dx, dx) for g in I["g1"]])                      # ray_trace_sw copy, 1e-13
+    out["eval_lagrange_qg"] = np.stack([O.interpolate(x, y, g, dx, dx, O.BUMP_QG) for g in I["g1"]])       # qg_flow_ray_trace copy
     bf1, bf2 = dict(zip(NAMES, I["g1"])), dict(zip(NAMES, I["g2"]))
     U, nab = O.interpolate_U(bf1, bf2, I["alpha"], np.stack([x, y], axis=1), dx)
     out["interpU_lagrange"] = np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])
@@ -102,7 +103,7 @@ def oracle_outputs(I):
 
 def shapes(I):
     n, nx = I["n"], I["nx"]
-    return {"eval_lagrange": (6, n), "interpU_lagrange": (6, n), "rhs_lagrange": (4, n), "scheme_eval": (6, n), "scheme_gradU_times_k": (2, n),
+    return {"eval_lagrange": (6, n), "eval_lagrange_qg": (6, n), "interpU_lagrange": (6, n), "rhs_lagrange": (4, n), "scheme_eval": (6, n), "scheme_gradU_times_k": (2, n),
             "scheme_fields": (nx, nx, 6), "leapfrog100_scheme": (4, n), "leapfrog20_scheme": (4, n), "leapfrog_t": (101,),
             "cg_sw_fields": (nx, nx, 6), "rk4x3_packet_lagrange": (4, n), "rk4x3_xka_lagrange": (5, n)}
 
@@ -177,11 +178,19 @@ def test_gpu_path_against_reference_outputs():
         eng.step(sch, I["dt"], 3)
         ref = read_bin(OUT, name, *shp[name])
         assert np.abs(np.stack(eng.get_packets(with_a=True))[: ref.shape[0]] - ref).max() <= TOL_TRAJ
-    eng.set_flow_grid(*I["g2"], H=I["H"], slot=1)
+    eng.close()
+    # interpolate_U and the ode23 right-hand side bind to qg_flow_ray_trace/interpolate.m: bump 1e-10
+    eng = S.Engine(I["nx"], I["L"], I["f"], I["gH"], S.MODE_LAGRANGE6, bump=O.BUMP_QG)
+    eng.set_flow_grid(*I["g1"], slot=0)
+    eng.set_flow_grid(*I["g2"], slot=1)
     eng.set_packets(I["x"], I["y"], I["k"], I["l"])
+    assert np.array_equal(eng.eval(0.0), read_bin(OUT, "eval_lagrange_qg", 6, n))
     assert scaled(eng.eval(I["alpha"]), read_bin(OUT, "interpU_lagrange", 6, n)) <= TOL_FIELD
     assert scaled(np.stack(eng.rhs(I["alpha"])), read_bin(OUT, "rhs_lagrange", 4, n)) <= TOL_FIELD
     eng.close()
+    U, nab = R.interpolate_U(dict(zip(NAMES, I["g1"])), dict(zip(NAMES, I["g2"])), I["alpha"], np.stack([I["x"], I["y"]], axis=1), I["dx"])
+    got = np.stack([U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]])
+    assert scaled(got, read_bin(OUT, "interpU_lagrange", 6, n)) <= TOL_FIELD
     # ode_symplectic through the reference-named API on the scheme's own fields
     fields = list(np.moveaxis(read_bin(OUT, "scheme_fields", *shp["scheme_fields"]), 2, 0))
     eng = S.Engine(I["nx"], I["L"], I["f"], I["gH"], S.MODE_LAGRANGE6)

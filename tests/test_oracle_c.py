@@ -115,7 +115,7 @@ def test_two_frame_leapfrog_c_port_equals_numpy_restatement(small_flow, packets)
         al = a0 + j * da
 
         def eval6(xx, yy):
-            U, nab = O.interpolate_U(bf1, bf2, al, np.stack([xx, yy], axis=1), dx)
+            U, nab = O.interpolate_U(bf1, bf2, al, np.stack([xx, yy], axis=1), dx, bump=O.BUMP_LIVE)
             return U[:, 0], U[:, 1], nab["u_x"], nab["u_y"], nab["v_x"], nab["v_y"]
         x, y, k, l = O.leapfrog_step(x, y, k, l, dt, f, gH, eval6)
     got = CO.leapfrog_lagrange2(packets["x"], packets["y"], packets["k"], packets["l"], g1, g2, dx, f, gH, dt, m, a0, da)

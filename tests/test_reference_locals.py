@@ -1,0 +1,203 @@
+"""The reference's file-local / nested functions, executed unmodified, against the oracle and the product.
+
+``tests/golden/reference_locals_nx32.npz`` (made by ``tests/golden/run_reference_locals.py`` with ``oracle/minimat``) holds the
+outputs of functions no MATLAB session can call from outside their file: ``odefun`` -- the ``ode23`` right-hand side nested
+in ``generate_raytracing_ode`` (qgsw_raytrace.m:258-268, qg2layersw_raytrace.m:297-307) -- ``ode_xk2y`` / ``ode_y2xk``, the QG
+frame producers ``initial_q`` / ``inertial_ring`` / ``filter`` / ``update`` (one layer) and ``update`` / ``mmult3`` / ``diag_exp``
+(two layers); plus the top-level ``interpolate_par.m`` (nested ``compute_FI`` through ``arrayfun``), the six-argument
+``grid_U.m`` with a mean shear, the complex / multi-frame branches of ``write_field.m`` / ``read_field.m``, and one driver
+script run as a whole: ``ray_trace_sw/raytrace.m`` (its first packet over 300 ``step_packet`` calls).
+
+CPU tests: the oracle's restatements equal them (bit for bit where no FFT is involved, 1e-15 of the plane otherwise);
+``-m gpu`` tests: the product (``swrt_rhs``, ``swrt_interpolate`` with bump 1e-10, the device ``grid_U``, the on-device QG
+solver) is held to the same files.
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import swrt_oracle as O          # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+R = np.load(GOLD / "reference_locals_nx32.npz")
+H = np.load(GOLD / "hotpath_nx32.npz")
+NAMES = ("u", "v", "ux", "uy", "vx", "vy")
+NX, L, F0 = int(H["nx"]), float(H["L"]), float(H["f"])
+DX = L / NX
+KX, KY = O.wavenumbers(NX)
+K2 = KX ** 2 + KY ** 2
+TMAX = float(R["tmax"])
+
+
+def frames():
+    g1 = list(H["grids"])
+    g2 = [O.k2g(p) for p in O.velocity_planes_k(H["psik2"], KX, KY)]
+    return dict(zip(NAMES, g1)), dict(zip(NAMES, g2))
+
+
+def rel(got, ref):
+    ref = np.asarray(ref)
+    return float(np.abs(np.asarray(got) - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def test_provenance_lists_the_driver_files():
+    prov = json.loads(str(R["provenance"]))
+    ex = set(prov["reference_files_executed"])
+    assert {"qg_flow_ray_trace/qgsw_raytrace.m", "qg_flow_ray_trace/qg2layersw_raytrace.m", "interpolate_par.m", "qg_flow_ray_trace/grid_U.m",
+            "qg_flow_ray_trace/interpolate_U.m", "qg_flow_ray_trace/interpolate.m", "qg_flow_ray_trace/write_field.m",
+            "qg_flow_ray_trace/read_field.m"} <= ex
+    ref = Path("/root/reference")
+    if (ref / "ode_symplectic.m").exists():
+        import hashlib
+        for relp, sha in prov["reference_files_executed"].items():
+            assert hashlib.sha256((ref / relp).read_bytes()).hexdigest() == sha, relp
+
+
+def test_oracle_odefun_and_state_packing_equal_the_nested_reference_function():
+    """qgsw_raytrace.m:232-268: y = [x; y; k; l]; dydt bit for bit at alpha = 0, 1/4, 1 (pure Lagrange arithmetic + blend)"""
+    x, y, k, l = (H[n] for n in ("x", "y", "k", "l"))
+    n = x.size
+    yv = np.concatenate([x, y, k, l])
+    assert np.array_equal(R["ode_xk2y"], yv)
+    assert np.array_equal(R["ode_y2xk_x"], np.stack([x, y], 1)) and np.array_equal(R["ode_y2xk_k"], np.stack([k, l], 1))
+    bf1, bf2 = frames()
+    ode = O.generate_raytracing_ode(bf1, bf2, n, F0, 1.0, TMAX, DX)
+    for tag, t in (("t0", 0.0), ("tmid", 0.25 * TMAX), ("tend", TMAX)):
+        assert np.array_equal(ode(t, yv), R["odefun_" + tag]), tag
+    assert np.array_equal(R["qg2_odefun_tmid"], R["odefun_tmid"])          # the two drivers carry the same text
+
+
+def test_oracle_interpolate_par_equals_the_reference():
+    x, y = H["x"], H["y"]
+    for j, g in enumerate(H["grids"]):
+        assert np.array_equal(O.interpolate_par(x, y, g, DX, DX), R["interpolate_par"][j])
+    # and it is NOT the live interpolate (bump 1e-13): the two differ at the 1e-10 level
+    d = np.abs(O.interpolate(x, y, H["grids"][0], DX, DX) - R["interpolate_par"][0]).max()
+    assert 1e-13 < d < 1e-8
+
+
+def test_oracle_qg_producers_equal_the_reference_locals():
+    xs = np.linspace(-L / 2, L / 2, NX)
+    X, Y = np.meshgrid(xs, xs)
+    q0 = O.initial_q(X, Y, 0.5, 3.0, O.matlab_rand_stream(146))
+    assert np.array_equal(q0, R["initial_q"])
+    ring = O.qg_inertial_ring(0.1, K2, 3.0, 0.25)
+    assert ring.any() and np.array_equal(ring, R["inertial_ring"])
+    assert np.array_equal(O.qg_filter(KX, KY, DX), R["filter"])
+    assert np.array_equal(O.g2k(q0), R["update_qk_in"])
+    got = O.qg_update(R["update_qk_in"], K2, 3.0, 0.3, 0.1, R["inertial_ring"], KX, KY)
+    assert np.array_equal(got, R["update"])
+
+
+def test_oracle_two_layer_operators_equal_the_reference_locals():
+    B, q2 = R["qg2_B"], R["qg2_qk_in"]
+    assert np.array_equal(O.mmult3(B, q2), R["qg2_mmult3"])
+    assert np.array_equal(O.qg2_update(q2, B, KX, KY), R["qg2_update"])
+    A = B.astype(complex) * (1 + 0.5j)
+    E = R["qg2_diag_exp"]
+    assert E.shape[:2] == (2, 2) and np.array_equal(E[0, 0], np.exp(0.3 * A[0, 0])) and np.array_equal(E[1, 1], np.exp(0.3 * A[1, 1]))
+    assert not E[0, 1].any() and not E[1, 0].any()
+
+
+def test_oracle_grid_U_with_shear_equals_the_reference():
+    flow = O.grid_U(R["update_qk_in"], 3.0, K2, KX, KY, float(R["grid_U_shear_value"]))
+    for j, nm in enumerate(NAMES):
+        assert np.array_equal(flow[nm], R["grid_U_shear"][j]), nm
+    assert abs(R["grid_U_shear"][0].mean() - float(R["grid_U_shear_value"])) < 1e-14
+
+
+def test_product_field_files_equal_the_reference_writer_and_reader(tmp_path):
+    """swraytracing_b200.fieldio (host-side, no device): the bytes write_field.m appends for a complex two-frame file and what
+    read_field.m returns for frame lists"""
+    from swraytracing_b200 import fieldio
+    qk = R["update_qk_in"]
+    fieldio.write_field(qk, tmp_path / "spec", 1)
+    fieldio.write_field(2 * qk, tmp_path / "spec", 2)
+    assert np.array_equal(np.fromfile(tmp_path / "spec.bin"), R["write_field_complex_bytes"])
+    back = fieldio.read_field(tmp_path / "spec", qk.shape[0], qk.shape[1], 1, [2])
+    assert np.array_equal(back, R["read_field_complex_frame2"]) and np.array_equal(back, 2 * qk)
+    for fr, g in enumerate(H["grids"][:3], 1):
+        fieldio.write_field(g, tmp_path / "grid", fr)
+    got = fieldio.read_field(tmp_path / "grid", NX, NX, 1, [3, 1], True)
+    assert np.array_equal(got, R["read_field_frames_3_1"])
+    assert np.array_equal(got[:, :, 0], H["grids"][2]) and np.array_equal(got[:, :, 1], H["grids"][0])
+
+
+def test_oracle_raytrace_driver_equals_the_executed_script():
+    """ray_trace_sw/raytrace.m run as a script (Childress-Soward flow with the matrix product of :36 as written, ``rand*L`` from
+    MATLAB's start-up stream, 300 ``step_packet`` calls on packet 1): the restated driver gives the same doubles"""
+    hist, dt, nsteps = O.raytrace_driver(np_=5, nsteps=301)
+    assert dt == float(R["raytrace_dt"])
+    assert int(round((1 / (4.0 * 0.1 ** 2)) / dt)) == int(R["raytrace_nsteps"]) == 3395
+    for j, c in enumerate("xykl"):
+        assert np.array_equal(hist[c][:, 0], R["raytrace_P0"][:, j]), c
+        assert np.array_equal(hist[c][0, :301], R["raytrace_p1"][:, j]), c
+    _, _, G = O.childress_soward_as_written(256, 2 * np.pi, 0.1, 4.0, 0.25)
+    assert np.array_equal(G["v_x"], R["raytrace_GradU_v_x"])
+    assert np.abs(R["raytrace_GradU_v_x"]).max() > 10 * 0.4 * 1.25            # the matrix product blows v_x up far beyond km*U0*(1+a)
+
+
+# ---------------------------------------------------------------------------------------------------------- product, on the GPU
+@pytest.mark.gpu
+def test_gpu_raytrace_driver_equals_the_executed_script():
+    """drivers.raytrace (step_packet on the device, LAGRANGE6) on the reference's own script output: 100 steps within 1e-9,
+    300 within 1e-7 (k has grown eightfold by then)"""
+    from swraytracing_b200 import drivers
+    out = drivers.raytrace(np_=5, nsteps=301)
+    P = out["P"]
+    assert out["dt"] == float(R["raytrace_dt"])
+    for j, c in enumerate("xykl"):
+        assert np.array_equal(P[c][:, 0], R["raytrace_P0"][:, j]), c
+        assert np.abs(P[c][0, :101] - R["raytrace_p1"][:101, j]).max() <= 1e-9, c
+        assert np.abs(P[c][0, :301] - R["raytrace_p1"][:, j]).max() <= 1e-7, c
+
+@pytest.mark.gpu
+def test_gpu_rhs_equals_the_nested_reference_odefun():
+    """generate_raytracing_ode through the product (swrt_set_packets + swrt_rhs, LAGRANGE6): bit-identical to the reference's
+    odefun at t = 0 (one frame) and within 1e-12 of the plane at blended times; SPECTRAL / NUFFT modes under the degree-5
+    interpolation bound"""
+    from swraytracing_b200 import reference_api as A
+    import swraytracing_b200 as S
+    x, y, k, l = (H[n] for n in ("x", "y", "k", "l"))
+    yv = np.concatenate([x, y, k, l])
+    bf1, bf2 = frames()
+    ode = A.generate_raytracing_ode(bf1, bf2, x.size, F0, 1.0, TMAX, DX)
+    for tag, t in (("t0", 0.0), ("tmid", 0.25 * TMAX), ("tend", TMAX)):
+        got = ode(t, yv)
+        ref = R["odefun_" + tag]
+        assert np.array_equal(got, ref), (tag, np.abs(got - ref).max())
+
+
+@pytest.mark.gpu
+def test_gpu_interpolate_par_and_grid_U_equal_the_reference():
+    from swraytracing_b200 import reference_api as A
+    x, y = H["x"], H["y"]
+    for j, g in enumerate(H["grids"]):
+        assert np.array_equal(A.interpolate_par(x, y, g, DX, DX), R["interpolate_par"][j])
+    flow = A.grid_U(R["update_qk_in"], 3.0, K2, KX, KY, float(R["grid_U_shear_value"]))
+    for j, nm in enumerate(NAMES):
+        assert rel(flow[nm], R["grid_U_shear"][j]) <= 1e-14, nm
+
+
+@pytest.mark.gpu
+def test_gpu_qg_solver_first_step_equals_the_reference_update():
+    """swrt_qg_create + one swrt_qg_step = Euler start-up of qgsw_raytrace.m:117-136: qk1 = Ef .* (qk + dt * update(qk, ...)),
+    with ``update``, ``filter`` and ``inertial_ring`` as the reference's own local functions returned them"""
+    from swraytracing_b200.engine import QGFlow
+    qk = R["update_qk_in"]
+    dt = 1e-3
+    f, Cg = 3.0, 0.25
+    upd = O.qg_update(qk, K2, 3.0, 0.3, 0.1, R["inertial_ring"], KX, KY)
+    assert np.array_equal(upd, R["update"])
+    want = R["filter"] * (qk + dt * R["update"])
+    qg = QGFlow(NX, L, qk, 3.0, dt, f, Cg, beta=0.3, r_drag=0.1, force_strength=0.1)
+    qg.step(1)
+    got = qg.get()
+    qg.close()
+    assert rel(got, want) <= 1e-13
