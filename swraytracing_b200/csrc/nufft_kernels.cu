@@ -34,7 +34,12 @@ __device__ __forceinline__ double reduced_coord(double x, double dx, double nxd)
 // phi and dphi/dz of the ES kernel at z in [-1, 1]
 __device__ __forceinline__ void es_kernel(double z, double beta, double& p0, double& p1) {
     const double s2 = fma(-z, z, 1.0);
-    if (s2 <= 0.0) { p0 = 0.0; p1 = 0.0; return; }      // |z| = 1: phi = e^-beta ~ 1e-16 of the peak, dropped
+    // The end of the support: phi = e^-beta ~ 1e-18 of the peak there, but phi' = -phi beta z / sqrt(1 - z^2) has an
+    // (integrable) singularity at |z| = 1.  A packet that sits on a fine-grid node -- or within rounding of one, which is
+    // what x = i*dx gives -- puts a stencil node at |z| = 1 - O(1e-16), where the formula returns ~1e-18 * beta / 1e-8:
+    // a spurious 2e-10 of the gradient (found by the node test of tests/test_octave_goldens.py).  The node is dropped while
+    // sqrt(1 - z^2) < 1e-3: what is dropped is below e^-beta * beta / 1e-3 = 4e-14 of the peak in phi' and 1e-18 in phi.
+    if (s2 <= 1e-6) { p0 = 0.0; p1 = 0.0; return; }
     const double s = sqrt(s2);
     const double e = exp(beta * (s - 1.0));
     p0 = e;

@@ -1110,7 +1110,7 @@ def test_ode23_in_lagrange_mode_is_bit_identical_to_the_restatement():
     # dense output (SW_zero_background_raytracing.m:73-78) through the same stages
     ts = tmax * np.linspace(0.0, 1.0, 7)
     Yref, _ = O.ode23(ode, ts, np.concatenate([x, y, k, l]))
-    with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6) as e:
+    with S.Engine(nx, L, F0, 1.0, S.MODE_LAGRANGE6, bump=O.BUMP_QG) as e:
         e.set_flow_grid(*[bf1[n_] for n_ in names], slot=0); e.set_flow_grid(*[bf2[n_] for n_ in names], slot=1)
         e.set_packets(x, y, k, l)
         Y = R.ode23(e, ts, tmax)["Y"].reshape(len(ts), 4 * n)
@@ -1264,3 +1264,25 @@ def test_bench_gpu_arm_prints_one_contract_line():
     for m in ("lagrange6", "nufft"):
         assert d[m]["value"] > 0 and d[m]["roofline"]["bound"] == "l2" and d[m]["roofline"]["peak"] == d["peaks_measured"]["gather_probe_gbs"] > 0
     assert d["histogram_total"] <= 9472
+
+
+def test_nufft_gradients_at_and_next_to_grid_nodes():
+    """A packet on a grid node (or within rounding of one: x = i*dx) puts a stencil node at the very end of the NUFFT kernel's
+    support, where the analytic derivative phi' = -phi beta z / sqrt(1 - z^2) is singular; before the end node was dropped
+    (nufft_kernels.cu:es_kernel) such packets got a spurious 2e-10 of the gradient.  All six planes within 1e-12 of the exact
+    sum on nodes, one ulp either side, and at offsets down to 1e-12 of a cell, in SPECTRAL and NUFFT modes."""
+    nx = 32; L = 2 * np.pi; dx = L / nx
+    psik, planes = make_flow(nx, seed=11)
+    ii = np.arange(nx * 3) % nx; jj = (np.arange(nx * 3) * 5 + 3) % nx
+    xs, ys = [], []
+    for off in (0.0, 1e-12, -1e-12, 1e-9, -1e-9, 3e-7, -3e-7, 1e-4):
+        xs.append((ii + off) * dx); ys.append((jj - off) * dx)
+        xs.append((ii * 0.5 + off) * dx); ys.append((jj * 0.5 + 0.25 - off) * dx)          # fine-grid nodes between coarse ones
+    xs.append(np.nextafter(ii * dx, np.inf)); ys.append(np.nextafter(jj * dx, -np.inf))
+    xs.append(np.nextafter(ii * dx, -np.inf)); ys.append(np.nextafter(jj * dx, np.inf))
+    x = np.concatenate(xs); y = np.concatenate(ys)
+    ref = CO.spectral_eval(x, y, planes, dx, nx)
+    for mode in (S.MODE_SPECTRAL, S.MODE_NUFFT):
+        with S.Engine(nx, L, F0, GH0, mode) as e:
+            e.set_flow_planes_spectral(planes)
+            assert scaled_err(e.eval_at(x, y), ref) < TOL_FIELD, mode
