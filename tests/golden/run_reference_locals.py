@@ -44,6 +44,16 @@ def flow_struct(planes):
     return MStruct({n: fa(p) for n, p in zip(NAMES, planes)})
 
 
+def edge_positions(nx, dx, L):
+    i = np.array([0.0, 1.0, 7.0, nx - 1.0, nx / 2.0])
+    xs = [i * dx, np.nextafter(i * dx, np.inf), np.nextafter(i * dx, -np.inf), (i + 1e-13) * dx, (i - 1e-13) * dx, (i + 1e-10) * dx,
+          (i + 0.5) * dx, (i + 1 - 1e-12) * dx, i * dx + L, i * dx - L, i * dx + 1e6 * L, i * dx - 12345 * L,
+          np.array([-1e-17, -1e-300, 0.0, -0.0, L, np.nextafter(L, 0), -L, nx * dx, 2.5 * dx - 3 * L])]
+    x = np.concatenate(xs)
+    y = np.concatenate([x[3:], x[:3]])[::-1].copy()
+    return x, y
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -108,6 +118,14 @@ def main():
     flow = I.call("grid_U", qk, K_d2, K2, kx_, ky_, shear)
     out["grid_U_shear"] = np.stack([np.asarray(flow.f[nm]) for nm in NAMES])
     out["grid_U_shear_value"] = np.float64(shear)
+    # interpolate.m (both copies) at the awkward places: on nodes, one ulp either side, the bump's own scale, the domain ends,
+    # mod(-tiny, nx) = nx (i0 = nx + 1 wraps through the second mod), many periods away
+    ex, ey = edge_positions(nx, dx, L)
+    out["edge_x"], out["edge_y"] = ex, ey
+    I.path.insert(0, str(ref / "ray_trace_sw"))
+    out["edge_interpolate_live"] = np.stack([np.asarray(I.call("interpolate", ex, ey, g, dx, dx)).ravel() for g in g1[:2]])
+    I.path.pop(0)
+    out["edge_interpolate_qg"] = np.stack([np.asarray(I.call("interpolate", ex, ey, g, dx, dx)).ravel() for g in g1[:2]])
     # write_field / read_field: complex (staggered real / imaginary frames) and multi-frame real files
     (tmp / "io").mkdir()
     I.call("write_field", qk, "io/spec", 1.0, nargout=0)

@@ -82,6 +82,18 @@ def test_oracle_interpolate_par_equals_the_reference():
     assert 1e-13 < d < 1e-8
 
 
+def test_oracle_interpolate_at_the_awkward_places_equals_both_reference_copies():
+    """on nodes, one ulp either side, at the bump's own scale, at the domain ends, mod(-tiny, nx) = nx, a million periods away"""
+    ex, ey = R["edge_x"], R["edge_y"]
+    assert ex.size >= 60 and (ex == 0).any() and (ex < 0).any() and (np.abs(ex) > 1e6).any()
+    for j in range(2):
+        g = H["grids"][j]
+        assert np.array_equal(O.interpolate(ex, ey, g, DX, DX), R["edge_interpolate_live"][j])
+        assert np.array_equal(O.interpolate(ex, ey, g, DX, DX, O.BUMP_QG), R["edge_interpolate_qg"][j])
+        on = np.abs(ex / DX - np.round(ex / DX)) < 1e-9
+        assert on.sum() > 20 and np.abs(R["edge_interpolate_live"][j] - R["edge_interpolate_qg"][j])[~on].max() > 1e-12
+
+
 def test_oracle_qg_producers_equal_the_reference_locals():
     xs = np.linspace(-L / 2, L / 2, NX)
     X, Y = np.meshgrid(xs, xs)
@@ -172,6 +184,17 @@ def test_gpu_rhs_equals_the_nested_reference_odefun():
         got = ode(t, yv)
         ref = R["odefun_" + tag]
         assert np.array_equal(got, ref), (tag, np.abs(got - ref).max())
+
+
+@pytest.mark.gpu
+def test_gpu_interpolate_at_the_awkward_places_equals_both_reference_copies():
+    from swraytracing_b200 import reference_api as A
+    from swraytracing_b200.engine import interpolate_dev
+    ex, ey = R["edge_x"], R["edge_y"]
+    for j in range(2):
+        g = H["grids"][j]
+        assert np.array_equal(A.interpolate(ex, ey, g, DX, DX), R["edge_interpolate_live"][j])
+        assert np.array_equal(interpolate_dev(ex, ey, g, DX, DX, 1e-10), R["edge_interpolate_qg"][j])
 
 
 @pytest.mark.gpu
