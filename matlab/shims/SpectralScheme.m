@@ -4,6 +4,7 @@ classdef SpectralScheme < handle
     % mode 1 = the reference's gridded 6x6 Lagrange evaluation.
     properties
         L, nx, mode, psik, eng
+        U_field, GradU_field, psi_field          % the gridded planes the reference's class exposes (SpectralScheme.m:3,28-35)
     end
     methods
         function obj = SpectralScheme(L, nx, psi_field, mode)
@@ -12,6 +13,19 @@ classdef SpectralScheme < handle
             obj.psik = swrt_mex('g2k', psi_field);
             obj.eng = swrt_mex('create', nx, L, 1, 1, mode);
             swrt_mex('set_flow_spectral', obj.eng, 0, obj.psik);
+            % the public gridded fields of the reference's class (SpectralScheme.m:16-35), transformed on the device; wavenumbers
+            % in units of 2*pi/L, which is what the engine evaluates (the reference writes integer wavenumbers, i.e. L = 2*pi)
+            kmax = nx/2 - 1;
+            [kx_, ky_] = ndgrid(-kmax:kmax, 0:kmax);
+            kap = 2*pi/L;
+            ugk = -1i*kap*ky_.*obj.psik;  vgk = 1i*kap*kx_.*obj.psik;
+            obj.psi_field = swrt_mex('k2g', obj.psik);
+            obj.U_field.u = swrt_mex('k2g', ugk);
+            obj.U_field.v = swrt_mex('k2g', vgk);
+            obj.GradU_field.u_x = swrt_mex('k2g', 1i*kap*kx_.*ugk);
+            obj.GradU_field.u_y = swrt_mex('k2g', 1i*kap*ky_.*ugk);
+            obj.GradU_field.v_x = swrt_mex('k2g', 1i*kap*kx_.*vgk);
+            obj.GradU_field.v_y = swrt_mex('k2g', 1i*kap*ky_.*vgk);
         end
         function delete(obj)
             if ~isempty(obj.eng), swrt_mex('destroy', obj.eng); end

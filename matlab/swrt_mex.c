@@ -52,6 +52,15 @@ static mxArray* new_id(uint64_t id) {
     return o;
 }
 static double* vec(mxArray** out, size_t n) { *out = mxCreateDoubleMatrix(n, 1, mxREAL); return mxGetPr(*out); }
+/* Output i of a multi-output command.  plhs[] has room for max(nlhs, 1) pointers only: a caller that asks for fewer outputs
+   than the command can give ("[px, py, pk, pl] = swrt_mex('get_packets', eng)" in shims/ode_symplectic.m) must not have the
+   rest written past the end of plhs -- those go to scratch memory that MATLAB / Octave release when mexFunction returns.
+   (Found by executing the shims: tests/test_shims_executed.py.) */
+static int g_nlhs = 0;
+static double* outv(mxArray* plhs[], int i, size_t n) {
+    if (i == 0 || i < g_nlhs) return vec(&plhs[i], n);
+    return (double*)mxCalloc(n ? n : 1, sizeof(double));
+}
 static double* opt(const mxArray* prhs[], int nrhs, int i) { return (i < nrhs && !mxIsEmpty(prhs[i])) ? mxGetPr(prhs[i]) : NULL; }
 static double sc(const mxArray* prhs[], int nrhs, int i, double dflt) { return i < nrhs ? mxGetScalar(prhs[i]) : dflt; }
 
@@ -97,6 +106,7 @@ static int free_slot(void** table) {
 }
 
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    g_nlhs = nlhs;
     char cmd[48];
     if (nrhs < 1 || !mxIsChar(prhs[0]) || mxGetString(prhs[0], cmd, sizeof cmd)) mexErrMsgIdAndTxt("swrt:usage", "swrt_mex('command', ...)");
     if (!g_locked) { mexLock(); mexAtExit(destroy_all); g_locked = 1; }
@@ -247,18 +257,18 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         for (int i = 3; i < 6; i++) if (mxGetNumberOfElements(prhs[i]) != m) mexErrMsgIdAndTxt("swrt:usage", "set_packets: arrays differ in size");
         if (swrt_set_packets(h, (int64_t)m, mxGetPr(prhs[2]), mxGetPr(prhs[3]), mxGetPr(prhs[4]), mxGetPr(prhs[5]), opt(prhs, nrhs, 6))) fail(h, cmd);
     } else if (!strcmp(cmd, "get_packets")) {         /* [x, y, k, l, a] = ... */
-        double* o[5]; for (int i = 0; i < 5; i++) o[i] = vec(&plhs[i], n);
+        double* o[5]; for (int i = 0; i < 5; i++) o[i] = outv(plhs, i, n);
         if (swrt_get_packets(h, o[0], o[1], o[2], o[3], o[4])) fail(h, cmd);
     } else if (!strcmp(cmd, "eval")) {                /* [U, V, Ux, Uy, Vx, Vy] = (h, alpha) */
-        double* o[6]; for (int i = 0; i < 6; i++) o[i] = vec(&plhs[i], n);
+        double* o[6]; for (int i = 0; i < 6; i++) o[i] = outv(plhs, i, n);
         if (swrt_eval(h, sc(prhs, nrhs, 2, 0.0), o[0], o[1], o[2], o[3], o[4], o[5])) fail(h, cmd);
     } else if (!strcmp(cmd, "eval_at")) {             /* [U, V, Ux, Uy, Vx, Vy] = (h, alpha, x, y) */
         need(nrhs, 5, "'eval_at', h, alpha, x, y");
-        size_t m = mxGetNumberOfElements(prhs[3]); double* o[6]; for (int i = 0; i < 6; i++) o[i] = vec(&plhs[i], m);
+        size_t m = mxGetNumberOfElements(prhs[3]); double* o[6]; for (int i = 0; i < 6; i++) o[i] = outv(plhs, i, m);
         if (mxGetNumberOfElements(prhs[4]) != m) mexErrMsgIdAndTxt("swrt:usage", "eval_at: x and y differ in size");
         if (swrt_eval_at(h, mxGetScalar(prhs[2]), (int64_t)m, mxGetPr(prhs[3]), mxGetPr(prhs[4]), o[0], o[1], o[2], o[3], o[4], o[5], NULL)) fail(h, cmd);
     } else if (!strcmp(cmd, "rhs")) {                 /* [dxdt, dydt, dkdt, dldt] = (h, alpha) */
-        double* o[4]; for (int i = 0; i < 4; i++) o[i] = vec(&plhs[i], n);
+        double* o[4]; for (int i = 0; i < 4; i++) o[i] = outv(plhs, i, n);
         if (swrt_rhs(h, sc(prhs, nrhs, 2, 0.0), o[0], o[1], o[2], o[3])) fail(h, cmd);
     } else if (!strcmp(cmd, "step")) {                /* (h, scheme, dt, nsteps [, alpha0, dalpha]) */
         need(nrhs, 5, "'step', h, scheme, dt, nsteps [, alpha0, dalpha]");
@@ -267,7 +277,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         need(nrhs, 9, "'step_host', h, scheme, dt, nsteps, x, y, k, l [, a, alpha0, dalpha]");
         size_t m = mxGetNumberOfElements(prhs[5]);
         for (int i = 6; i < 9; i++) if (mxGetNumberOfElements(prhs[i]) != m) mexErrMsgIdAndTxt("swrt:usage", "step_host: arrays differ in size");
-        double* o[5]; for (int i = 0; i < 5; i++) o[i] = vec(&plhs[i], m);
+        double* o[5]; for (int i = 0; i < 5; i++) o[i] = outv(plhs, i, m);
         if (swrt_step_host(h, (int)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), (int)mxGetScalar(prhs[4]), sc(prhs, nrhs, 10, 0.0), sc(prhs, nrhs, 11, 0.0),
                            (int64_t)m, mxGetPr(prhs[5]), mxGetPr(prhs[6]), mxGetPr(prhs[7]), mxGetPr(prhs[8]), opt(prhs, nrhs, 9), o[0], o[1], o[2], o[3], o[4]))
             fail(h, cmd);
@@ -284,7 +294,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (swrt_bs23_accept(h)) fail(h, cmd);
     } else if (!strcmp(cmd, "bs23_interp")) {         /* [x, y, k, l] = (h, hstep, s)        -- ntrp23 */
         need(nrhs, 4, "'bs23_interp', h, hstep, s");
-        double* o[4]; for (int i = 0; i < 4; i++) o[i] = vec(&plhs[i], n);
+        double* o[4]; for (int i = 0; i < 4; i++) o[i] = outv(plhs, i, n);
         if (swrt_bs23_interp(h, mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), o[0], o[1], o[2], o[3])) fail(h, cmd);
     } else if (!strcmp(cmd, "hist_omega")) {          /* counts = (h, kind, alpha, edges) */
         need(nrhs, 5, "'hist_omega', h, kind, alpha, edges");
@@ -303,7 +313,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     } else if (!strcmp(cmd, "diag")) {                /* d = (h, alpha) */
         if (swrt_diag(h, sc(prhs, nrhs, 2, 0.0), vec(&plhs[0], 8))) fail(h, cmd);
     } else if (!strcmp(cmd, "omega")) {               /* [omega, Omega] = (h, alpha) */
-        double* a = vec(&plhs[0], n); double* b = vec(&plhs[1], n);
+        double* a = outv(plhs, 0, n); double* b = outv(plhs, 1, n);
         if (swrt_omega(h, sc(prhs, nrhs, 2, 0.0), a, b)) fail(h, cmd);
     } else if (!strcmp(cmd, "set_tuning")) {          /* (h, mtiles, flags) */
         need(nrhs, 4, "'set_tuning', h, mtiles, flags");

@@ -335,7 +335,9 @@ def _class(I, args, nargout, frame):
 @reg("isfield")
 def _isfield(I, args, nargout, frame):
     s, n = args
-    return type(s) is MStruct and type(n) is str and n in s.f
+    if type(s) is MStructArr:
+        return s.a.size > 0 and type(n) is str and n in s.a.reshape(-1)[0].f
+    return type(s) in (MStruct, MObject) and type(n) is str and n in s.f
 
 
 @reg("fieldnames")
@@ -356,18 +358,28 @@ def _struct(I, args, nargout, frame):
     return s
 
 
+def _equal(a, b):
+    ta, tb = type(a), type(b)
+    if ta in (MStruct, MObject) or tb in (MStruct, MObject):
+        return ta is tb and set(a.f) == set(b.f) and all(_equal(a.f[k], b.f[k]) for k in a.f)
+    if ta is MStructArr or tb is MStructArr:
+        return ta is tb and a.a.shape == b.a.shape and all(_equal(x, y) for x, y in zip(a.a.reshape(-1), b.a.reshape(-1)))
+    if ta is MCell or tb is MCell:
+        return ta is tb and a.a.shape == b.a.shape and all(_equal(x, y) for x, y in zip(a.a.reshape(-1), b.a.reshape(-1)))
+    if ta is FuncHandle or tb is FuncHandle:
+        return a is b
+    try:
+        x, y = to_arr(a), to_arr(b)
+    except MatlabError:
+        return a is b or a == b
+    if x.size == 0 and y.size == 0:
+        return x.shape == y.shape or (x.size == 0 and y.size == 0 and len(x.shape) == len(y.shape) == 2 and x.shape == y.shape)
+    return msize(a) == msize(b) and bool(np.array_equal(x, y))
+
+
 @reg("isequal")
 def _isequal(I, args, nargout, frame):
-    a = args[0]
-    for b in args[1:]:
-        if type(a) is str or type(b) is str:
-            if not (type(a) is str and type(b) is str and a == b) and not (
-                    type(a) is not MStruct and type(b) is not MStruct and msize(a) == msize(b) and np.array_equal(to_arr(a), to_arr(b))):
-                return False
-            continue
-        if msize(a) != msize(b) or not np.array_equal(to_arr(a), to_arr(b)):
-            return False
-    return True
+    return all(_equal(args[0], b) for b in args[1:])
 
 
 # ------------------------------------------------------------------------------------------------ arithmetic helpers

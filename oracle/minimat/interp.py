@@ -142,7 +142,7 @@ class Interp:
 
     def getvar(self, frame, name):
         if frame.globals and name in frame.globals:
-            return self.globals.get(name, EMPTY)
+            return self.globals.get(frame.globals[name], EMPTY)
         f = frame
         while True:
             v = f.vars.get(name)
@@ -155,7 +155,7 @@ class Interp:
 
     def setvar(self, frame, name, val):
         if frame.globals and name in frame.globals:
-            self.globals[name] = val
+            self.globals[frame.globals[name]] = val
             return
         if frame.parent is None:
             frame.vars[name] = val
@@ -334,12 +334,19 @@ class Interp:
             raise _Return()
         elif k == "global":
             if fr.globals is None:
-                fr.globals = set()
+                fr.globals = {}                   # local name -> key in the interpreter-wide store
             for n in st[1]:
-                fr.globals.add(n)
+                fr.globals[n] = n
                 self.globals.setdefault(n, EMPTY)
         elif k == "persistent":
-            raise MatlabError("persistent variables are not supported")
+            if fr.func is None:
+                raise MatlabError("persistent outside a function")
+            if fr.globals is None:
+                fr.globals = {}
+            for n in st[1]:
+                key = ("persistent", id(fr.func), n)         # one value per function definition, [] until first assigned
+                fr.globals[n] = key
+                self.globals.setdefault(key, EMPTY)
         elif k == "try":
             try:
                 self.exec_block(st[1], fr)
@@ -734,8 +741,8 @@ class Interp:
                         seen.add(n)
                 f = f.parent
             if fr.globals:
-                for n in fr.globals:
-                    captured[n] = self.globals.get(n, EMPTY)
+                for n, key in fr.globals.items():
+                    captured[n] = self.globals.get(key, EMPTY)
             return [FuncHandle("anon", func=fr.func, frame=fr, params=e[1], body=e[2], captured=captured)]
         if k == "fhandle":
             name = e[1]

@@ -90,16 +90,19 @@ class Mex:
         lib = self.lib
         rhs = [self._to_mx(cmd)] + [self._to_mx(a) for a in args]
         prhs = (C.c_void_p * len(rhs))(*rhs)
-        plhs = (C.c_void_p * max(nlhs, 1))()
-        rc = lib.hx_call(nlhs, plhs, len(rhs), prhs)
+        nout = max(nlhs, 1)
+        plhs = (C.c_void_p * (nout + 8))()                 # MATLAB gives mexFunction room for max(nlhs, 1) outputs; the 8 guard
+        rc = lib.hx_call(nlhs, plhs, len(rhs), prhs)       # slots behind them must come back untouched
         try:
+            overrun = [i for i in range(nout, nout + 8) if plhs[i]]
+            assert not overrun, f"swrt_mex('{cmd}', ...) wrote plhs{overrun} with nlhs = {nlhs}"
             if rc != 0:
                 raise MexError(lib.hx_error_id().decode(), lib.hx_error_msg().decode())
             outs = [self._from_mx(plhs[i]) for i in range(nlhs) if plhs[i]]
         finally:
             for r in rhs:
                 lib.hx_free(r)
-            for i in range(max(nlhs, 1)):
+            for i in range(nout + 8):
                 if plhs[i]:
                     lib.hx_free(plhs[i])
         if nlhs <= 1:
@@ -175,6 +178,11 @@ def test_gateway_leapfrog_session_equals_ctypes_path(mex):
     assert mex("num_packets", h) == w.n_packets and mex("num_devices", h) == 1
     mex("step", h, 0.0, w.dt / 4, 4.0, 0.125, 0.25, nlhs=0)
     got = np.stack(mex("get_packets", h, nlhs=5))
+    # fewer outputs than the command can give (shims/ode_symplectic.m asks for four): nothing may be written past plhs[nlhs-1]
+    # -- the driver checks guard slots behind plhs on every call
+    part = mex("get_packets", h, nlhs=2)
+    assert len(part) == 2 and np.array_equal(part[0], got[0]) and np.array_equal(part[1], got[1])
+    assert np.array_equal(mex("get_packets", h, nlhs=1), got[0]) and np.array_equal(mex("omega", h, 0.5), mex("omega", h, 0.5, nlhs=2)[0])
     counts = mex("hist_omega", h, 0.0, 0.0, edges)
     d = mex("diag", h, 0.5)
     ev = np.stack(mex("eval", h, 0.5, nlhs=6))
