@@ -52,7 +52,12 @@ DESCR = {
     "C5": "C5: step_packet_xka (wave action, refraction by H) on a synthetic geostrophic 256^2 state, 4,194,304 packets (raytrace_sw.m)",
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch from the committed ncu --set full captures
-NCU_TRAFFIC_BYTES = {("C2", 16, 65536): 2.53e6}      # profiles/r01c_spectral_leapfrog_ncu_summary.json
+# (tools/r02h_traffic.sh at the bench's own launch shapes: profiles/r02h_spec512_c4_fullsize_ncu_summary.json, r02h_traffic.csv);
+# key = (workload, fused sub-steps, packets of this process); other shapes report null
+NCU_TRAFFIC_BYTES = {("C4", 2, 16777216): 596984832 + 561957888,     # 1.16 GB = 1.08 x (64 B of packet state per packet + stacks)
+                     ("C3", 16, 1048576): 60381696 + 13184256,
+                     ("C5", 2, 4194304): 186920448 + 154308352,
+                     ("C2", 16, 65536): 2526464}
 
 
 def parse():
