@@ -19,7 +19,7 @@ import numpy as np
 from . import fieldio
 from .engine import (Engine, QGFlow, QG2Flow, MODE_SPECTRAL, SCHEME_LEAPFROG, SCHEME_RK4_PACKET, SCHEME_RK4_XKA, k2g_dev,
                      g2k_dev)
-from .reference_api import ode23
+from .reference_api import ode23, matlab_linspace
 
 
 def wavenumber_grids(nx):
@@ -54,7 +54,7 @@ def qgsw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_delay_da
     symplectic stepper with time-centred frame blending).  ``max_steps`` truncates the run (tests)."""
     L = 2 * np.pi
     dx = L / nx
-    xg = np.linspace(-L / 2, L / 2, nx)
+    xg = matlab_linspace(-L / 2, L / 2, nx)
     X, Y = np.meshgrid(xg, xg)
     kx_, ky_ = wavenumber_grids(nx)
     K2 = kx_ ** 2 + ky_ ** 2
@@ -170,7 +170,7 @@ def _frozen_flow_setup(q, nx, f, Cg, Nparticles, grid_lo, mode, device, seed, ri
     kx_, ky_ = wavenumber_grids(nx)
     K2 = kx_ ** 2 + ky_ ** 2
     rs = np.random.RandomState(seed)                                   # rng(123)
-    X = np.linspace(grid_lo, grid_lo + L, nx)                          # linspace(0,L,nx) / linspace(-L/2,L/2,nx)
+    X = matlab_linspace(grid_lo, grid_lo + L, nx)                       # linspace(0,L,nx) / linspace(-L/2,L/2,nx)
     XX, YY = np.meshgrid(X, X)
     gH = Cg ** 2
     scheme = SpectralScheme(L, nx, k2g(-g2k(q, device) / (K_d2 + K2), device), mode=mode, f=f, gH=gH, device=device)
@@ -387,7 +387,7 @@ def qg2layersw_raytrace(nx, Npackets, near_inertial_factor, T_Fr_days, packet_de
     and ``max_steps`` exist for tests."""
     L = 20.0
     dx = L / nx
-    xg = np.linspace(-L / 2, L / 2, nx)
+    xg = matlab_linspace(-L / 2, L / 2, nx)
     X, Y = np.meshgrid(xg, xg, indexing="ij")                          # ndgrid (:16)
     rs = np.random.RandomState(seed)                                   # rng(5)
     beta = 0.0
@@ -482,7 +482,7 @@ def load_data(directory, *, times=None, offset=500, bins=300, device=0):
     t, x_save, k_save = fieldio.load_packet_frames(d, Npackets)
     nfr = t.size
     omega = np.sqrt(f ** 2 + Cg ** 2 * (k_save ** 2).sum(axis=1))                   # (Np, frames)
-    edges = np.linspace(0.0, omega.max(), bins)
+    edges = matlab_linspace(0.0, omega.max(), bins)
     center = (edges[1:] + edges[:-1]) / 2
     if times is None:
         times = [tt for tt in (1000, 30000, nfr - offset) if offset < tt <= nfr - offset] or [max(1, nfr // 2)]

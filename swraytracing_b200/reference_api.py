@@ -44,6 +44,21 @@ def grid_U(qk, K_d2, K2, kx_, ky_, shear_strength=0.0, device=0):
     return out
 
 
+def matlab_linspace(d1, d2, n=100):
+    """MATLAB's ``linspace``: ``d1 + (0:n-1).*(d2 - d1)./(n-1)`` -- multiply, THEN divide -- with both ends forced.
+    ``numpy.linspace`` multiplies by a pre-divided step instead, which differs in the last bit for most points; the grids and
+    wavevector fans of the reference's scripts (symplectic_full_fourier.m:14, qgsw_raytrace.m:14, ideal_omega_distribution.m:3,
+    analysis/load_data.m:39) are reproduced with MATLAB's formula.  (Found by executing ideal_omega_distribution.m.)"""
+    d1 = float(d1); d2 = float(d2); n = int(n)
+    if n <= 0:
+        return np.zeros(0)
+    if n == 1:
+        return np.array([d2])
+    y = d1 + np.arange(n, dtype=np.float64) * (d2 - d1) / (n - 1)
+    y[0], y[-1] = d1, d2
+    return y
+
+
 # ------------------------------------------------------------------------------------------------
 # interpolate / interpolate_par / interpolate2 / interpolate_U
 # ------------------------------------------------------------------------------------------------
@@ -370,9 +385,9 @@ def ideal_omega_distribution(scheme, f, Cg, k_0, edges, nangles=100):
     grid ``X = linspace(0, L, nx); [XX,YY] = meshgrid(X)`` (symplectic_full_fourier.m:14-15) and
     ``t = linspace(0, 2*pi)`` wavevector directions.  MATLAB's ``histogram`` picks its own bins; here the
     caller passes ``edges`` (histcounts rule).  Returns (counts, pdf) with pdf = counts/(N*binwidth)."""
-    X = np.linspace(0.0, scheme.L, scheme.nx)
+    X = matlab_linspace(0.0, scheme.L, scheme.nx)
     XX, YY = np.meshgrid(X, X)
-    t = np.linspace(0.0, 2 * np.pi, nangles)
+    t = matlab_linspace(0.0, 2 * np.pi, nangles)
     kvx, kvy = k_0 * np.cos(t), k_0 * np.sin(t)
     omega_0 = math.sqrt(f ** 2 + Cg ** 2 * k_0 ** 2)
     edges = np.asarray(edges, dtype=np.float64)

@@ -86,7 +86,7 @@ def main():
     xx, kk = call("ode_y2xk", float(n), yvec, nargout=2)
     out["ode_y2xk_x"], out["ode_y2xk_k"] = np.asarray(xx), np.asarray(kk)
     # QG frame producers on the 32^2 grid (rng(146) -> rand inside initial_q, as the driver does)
-    xs = np.linspace(-L / 2, L / 2, nx)
+    xs = O.matlab_linspace(-L / 2, L / 2, nx)                 # qgsw_raytrace.m:14 (multiply-then-divide, unlike numpy.linspace)
     X, Y = np.meshgrid(xs, xs)
     K2 = kx_ ** 2 + ky_ ** 2
     I.call("rng", 146.0, nargout=0)
@@ -137,6 +137,23 @@ def main():
         I.call("write_field", g, "io/grid", float(fr_), nargout=0)
     out["read_field_frames_3_1"] = np.asarray(I.call("read_field", "io/grid", float(nx), float(nx), 1.0, np.array([[3.0, 1.0]]), 1.0))
     I.close_all()
+
+    # ---- the theoretical omega pdf: ideal_omega_distribution.m is a SCRIPT over the caller's workspace (U = scheme.U on the
+    #      grid of symplectic_full_fourier.m:14-15,31; f, Cg; w); run as one, with histogram() replaced by a recorder -------------
+    K = Interp(cwd=str(ref), out=io.StringIO())
+    seen = []
+    K.overrides["histogram"] = lambda I_, args, nargout, frame: seen.append(np.asarray(args[0]).copy())
+    ws2 = Frame(None)
+    ws2.vars.update({"L": L, "nx": float(nx), "psi": fa(O.k2g(G["psik"])), "f": f, "Cg": 1.0, "w": fa(np.ones((4, 3)))})
+    K.run("X = linspace(0, L, nx); [XX, YY] = meshgrid(X); scheme = SpectralScheme(L, nx, psi); U = scheme.U([XX(:), YY(:)]);", ws2)
+    K.run("ideal_omega_distribution", ws2)
+    out["ideal_U"] = np.asarray(ws2.vars["U"])
+    out["ideal_omega_abs"] = seen[0].ravel(order="F")[::16].copy()           # every 16th value (N * 100 in all)
+    out["ideal_edges"] = np.linspace(2.0, 6.0, 41)
+    out["ideal_counts"] = O.histcounts(seen[0].ravel(order="F"), out["ideal_edges"])
+    out["ideal_total"] = np.float64(seen[0].size)
+    for unit_path in K.units:
+        I.units.setdefault(unit_path, K.units[unit_path])
 
     # ---- a whole driver script: ray_trace_sw/raytrace.m (Childress-Soward flow as written, rand from MATLAB's start-up stream,
     #      step_packet one packet at a time), run as a script from its own folder and stopped after 300 steps of packet 1 by a

@@ -647,9 +647,9 @@ def test_ideal_omega_distribution_theoretical_pdf():
     psi = O.k2g(psik)
     for mode in (S.MODE_SPECTRAL, S.MODE_LAGRANGE6):
         sch = R.SpectralScheme(L, nx, psi, mode=mode)
-        X = np.linspace(0.0, L, nx); XX, YY = np.meshgrid(X, X)
+        X = O.matlab_linspace(0.0, L, nx); XX, YY = np.meshgrid(X, X)
         U = sch.U(np.stack([XX.ravel(order="F"), YY.ravel(order="F")], axis=1))
-        t = np.linspace(0, 2 * np.pi, 100)
+        t = O.matlab_linspace(0, 2 * np.pi, 100)
         om0 = np.sqrt(f * f + Cg * Cg * k0 * k0)
         om_abs = om0 + (np.outer(U[:, 0], k0 * np.cos(t)) + np.outer(U[:, 1], k0 * np.sin(t)))
         edges = O.matlab_linspace(om_abs.min(), om_abs.max(), 61)
@@ -665,7 +665,7 @@ def test_device_qg_frame_producer_and_time_evolving_run():
     # "next" row f3: the one-layer QG solver of qgsw_raytrace.m:111-137,270-286 on the device, feeding the two
     # flow slots without a host copy; packets advanced per flow step with frame blending (config C3's shape)
     nx = 64; L = 2 * np.pi; f, Cg = 3.0, 1.0; K_d2 = f / Cg
-    xg = np.linspace(-L / 2, L / 2, nx)
+    xg = O.matlab_linspace(-L / 2, L / 2, nx)
     X, Y = np.meshgrid(xg, xg)
     q0 = O.initial_q(X, Y, 0.5, K_d2, O.matlab_rand_stream(146))
     qk0 = O.g2k(q0)
@@ -711,7 +711,7 @@ def test_qgsw_raytrace_driver_on_device(tmp_path):
     out = drivers.qgsw_raytrace(nx, Np, nif, 6000, 0, U_g, f, Cg, outdir=str(tmp_path), max_steps=nst, r_drag=0.01, log=lambda s: None)
     # --- oracle-side restatement of the same loop
     L = 2 * np.pi; K_d2 = f / Cg
-    xg = np.linspace(-L / 2, L / 2, nx); X, Y = np.meshgrid(xg, xg)
+    xg = O.matlab_linspace(-L / 2, L / 2, nx); X, Y = np.meshgrid(xg, xg)
     rs = O.matlab_rand_stream(146)
     qk0 = O.g2k(O.initial_q(X, Y, U_g, K_d2, rs))
     x, y, k, l = O.init_packets(Np, L, np.sqrt((nif ** 2 - 1) * f ** 2 / Cg ** 2), rs)

@@ -182,7 +182,7 @@ def test_ode_symplectic_shapes_and_row_convention(small_flow):
 def test_initial_q_always_true_bug_and_packet_init():
     # qgsw_raytrace.m:202 sums every |k|,|l| <= k_max mode; ring=True is the intended annulus
     nx = 32; L = 2 * np.pi
-    xg = np.linspace(-L / 2, L / 2, nx)
+    xg = O.matlab_linspace(-L / 2, L / 2, nx)
     X, Y = np.meshgrid(xg, xg)
     q_all = O.initial_q(X, Y, 0.5, 3.0, O.matlab_rand_stream(146), k_min=2, k_max=3)
     q_ring = O.initial_q(X, Y, 0.5, 3.0, O.matlab_rand_stream(146), k_min=2, k_max=3, ring=True)

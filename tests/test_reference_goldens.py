@@ -126,7 +126,7 @@ def test_device_driver_prints_the_reference_log_header(U_g, tmp_path):
 def test_device_spectral_kit_reproduces_logged_U0():
     """g2k / grid_U / k2g through the C ABI (cuFFT) on the reference's own initial PV."""
     from swraytracing_b200 import drivers, reference_api as R
-    xg = np.linspace(-L / 2, L / 2, 256)
+    xg = R.matlab_linspace(-L / 2, L / 2, 256)
     X, Y = np.meshgrid(xg, xg)
     kx_, ky_ = drivers.wavenumber_grids(256)
     q = drivers.initial_q(X, Y, 1.0, 3.0, np.random.RandomState(146))
@@ -196,7 +196,7 @@ def test_product_initial_q_reproduces_logged_U0_without_the_oracle():
     from swraytracing_b200 import drivers
     nx, K_d2 = 256, 3.0
     kmax = nx // 2 - 1
-    xg = np.linspace(-L / 2, L / 2, nx)
+    xg = drivers.matlab_linspace(-L / 2, L / 2, nx)
     X, Y = np.meshgrid(xg, xg)
     q = drivers.initial_q(X, Y, 1.0, K_d2, np.random.RandomState(146))
     # g2k.m: fk = fftshift(fft2(fg))/nx^2, rows 2:end (kx = -kmax..kmax), columns kmax+2:end (ky = 0..kmax)

@@ -95,7 +95,7 @@ def test_oracle_interpolate_at_the_awkward_places_equals_both_reference_copies()
 
 
 def test_oracle_qg_producers_equal_the_reference_locals():
-    xs = np.linspace(-L / 2, L / 2, NX)
+    xs = O.matlab_linspace(-L / 2, L / 2, NX)
     X, Y = np.meshgrid(xs, xs)
     q0 = O.initial_q(X, Y, 0.5, 3.0, O.matlab_rand_stream(146))
     assert np.array_equal(q0, R["initial_q"])
@@ -141,6 +141,24 @@ def test_product_field_files_equal_the_reference_writer_and_reader(tmp_path):
     assert np.array_equal(got[:, :, 0], H["grids"][2]) and np.array_equal(got[:, :, 1], H["grids"][0])
 
 
+def test_theoretical_omega_pdf_of_the_executed_script():
+    """ideal_omega_distribution.m run as a script on U = scheme.U(grid): omega_abs = omega_0 + U.k over (grid point, angle) --
+    restated here in three numpy lines from the stored U, and binned (histcounts rule) into the stored counts"""
+    U = R["ideal_U"]
+    t = O.matlab_linspace(0.0, 2 * np.pi, 100)             # multiply-then-divide: numpy.linspace differs in the last bit
+    kv = 3.0 * np.stack([np.cos(t), np.sin(t)], axis=1)
+    om = np.sqrt(F0 ** 2 + 1.0 * 9.0) + (np.outer(U[:, 0], kv[:, 0]) + np.outer(U[:, 1], kv[:, 1]))
+    assert om.size == int(R["ideal_total"]) == NX * NX * 100
+    assert np.array_equal(om.ravel(order="F")[::16], R["ideal_omega_abs"])
+    assert np.array_equal(O.histcounts(om.ravel(order="F"), R["ideal_edges"]), R["ideal_counts"]) and R["ideal_counts"].sum() > 0.9 * om.size
+    # U itself: the reference's SpectralScheme on the grid of symplectic_full_fourier.m:14-15 (linspace(0, L, nx): the last node
+    # wraps onto the first)
+    X = O.matlab_linspace(0.0, L, NX); XX, YY = np.meshgrid(X, X)
+    planes = O.velocity_planes_k(O.g2k(O.k2g(H["psik"])), KX, KY)
+    for j in range(2):
+        assert np.array_equal(O.interpolate(XX.ravel(order="F"), YY.ravel(order="F"), O.k2g(planes[j]), DX, DX), U[:, j])
+
+
 def test_oracle_raytrace_driver_equals_the_executed_script():
     """ray_trace_sw/raytrace.m run as a script (Childress-Soward flow with the matrix product of :36 as written, ``rand*L`` from
     MATLAB's start-up stream, 300 ``step_packet`` calls on packet 1): the restated driver gives the same doubles"""
@@ -156,6 +174,18 @@ def test_oracle_raytrace_driver_equals_the_executed_script():
 
 
 # ---------------------------------------------------------------------------------------------------------- product, on the GPU
+@pytest.mark.gpu
+def test_gpu_theoretical_omega_pdf_equals_the_executed_script():
+    """reference_api.ideal_omega_distribution (swrt_ideal_omega_hist: evaluation + binning on the device) on the same scheme:
+    the counts of the executed ideal_omega_distribution.m, bin for bin"""
+    from swraytracing_b200 import reference_api as A
+    import swraytracing_b200 as S
+    sch = A.SpectralScheme(L, NX, O.k2g(H["psik"]), mode=S.MODE_LAGRANGE6, f=F0, gH=1.0)
+    counts, pdf = A.ideal_omega_distribution(sch, F0, 1.0, 3.0, R["ideal_edges"])
+    assert np.array_equal(np.asarray(counts, dtype=np.uint64), R["ideal_counts"].astype(np.uint64))
+    assert abs(float((pdf * np.diff(R["ideal_edges"])).sum()) - R["ideal_counts"].sum() / float(R["ideal_total"])) < 1e-12
+
+
 @pytest.mark.gpu
 def test_gpu_raytrace_driver_equals_the_executed_script():
     """drivers.raytrace (step_packet on the device, LAGRANGE6) on the reference's own script output: 100 steps within 1e-9,
