@@ -126,6 +126,35 @@ def main():
     out["edge_interpolate_live"] = np.stack([np.asarray(I.call("interpolate", ex, ey, g, dx, dx)).ravel() for g in g1[:2]])
     I.path.pop(0)
     out["edge_interpolate_qg"] = np.stack([np.asarray(I.call("interpolate", ex, ey, g, dx, dx)).ravel() for g in g1[:2]])
+    # a second geometry: 24 x 24 grid (not a power of two), L = 20 (the two-layer driver's domain), plain random planes
+    # (interpolate / step_packet_xka do not care where the planes come from), 40 packets spread over +-3 domains
+    rs = np.random.RandomState(2024)
+    n2, L2, m2 = 24, 20.0, 40
+    h2 = L2 / n2
+    A1 = [rs.standard_normal((n2, n2)) for _ in range(6)]
+    A2 = [a_ + 0.1 * rs.standard_normal((n2, n2)) for a_ in A1]
+    Hh = 1.0 + 0.2 * rs.uniform(-1, 1, (n2, n2))
+    px, py = rs.uniform(-3 * L2, 3 * L2, m2), rs.uniform(-3 * L2, 3 * L2, m2)
+    pk, pl = 2.5 * np.cos(0.7 * np.arange(m2)), 2.5 * np.sin(0.7 * np.arange(m2))
+    out.update({"g24_planes1": np.stack(A1), "g24_planes2": np.stack(A2), "g24_H": Hh, "g24_x": px, "g24_y": py, "g24_k": pk, "g24_l": pl,
+                "g24_L": np.float64(L2), "g24_dt": np.float64(0.05), "g24_f": np.float64(1.3), "g24_C0": np.float64(0.8)})
+    ode24 = call("generate_raytracing_ode", flow_struct(A1), flow_struct(A2), float(m2), 1.3, 0.8, 0.2, h2)[0]
+    y24 = np.concatenate([px, py, pk, pl]).reshape(-1, 1)
+    out["g24_odefun"] = np.asarray(I.call_handle(ode24, [0.06, from_py(y24)], 1, None)[0]).ravel()      # alpha = 0.3, bump 1e-10
+    I.path.insert(0, str(ref / "ray_trace_sw"))                                        # step_packet*, cg_sw, interpolate (1e-13)
+    Us = MStruct({"u": fa(A1[0]), "v": fa(A1[1])})
+    Gs = MStruct({"u_x": fa(A1[2]), "u_y": fa(A1[3]), "v_x": fa(A1[4]), "v_y": fa(A1[5])})
+    res = np.zeros((5, m2)); res4 = np.zeros((4, m2))
+    for m in range(m2):
+        P = MStruct({"x": float(px[m]), "y": float(py[m]), "k": float(pk[m]), "l": float(pl[m]), "a": 1.0})
+        Q = MStruct({"x": float(px[m]), "y": float(py[m]), "k": float(pk[m]), "l": float(pl[m])})
+        for _ in range(2):
+            P = I.call("step_packet_xka", P, Us, Gs, fa(Hh), 0.8, 1.3, h2, h2, 0.05)
+            Q = I.call("step_packet", Q, Us, Gs, 0.8, 1.3, h2, h2, 0.05)
+        res[:, m] = [P.f[c] for c in "xykla"]
+        res4[:, m] = [Q.f[c] for c in "xykl"]
+    I.path.pop(0)
+    out["g24_rk4x2_xka"], out["g24_rk4x2_packet"] = res, res4
     # write_field / read_field: complex (staggered real / imaginary frames) and multi-frame real files
     (tmp / "io").mkdir()
     I.call("write_field", qk, "io/spec", 1.0, nargout=0)

@@ -94,6 +94,27 @@ def test_oracle_interpolate_at_the_awkward_places_equals_both_reference_copies()
         assert on.sum() > 20 and np.abs(R["edge_interpolate_live"][j] - R["edge_interpolate_qg"][j])[~on].max() > 1e-12
 
 
+def _g24():
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    bf1 = dict(zip(names, R["g24_planes1"])); bf2 = dict(zip(names, R["g24_planes2"]))
+    return bf1, bf2, float(R["g24_L"]) / 24, tuple(R["g24_" + c] for c in "xykl")
+
+
+def test_oracle_on_a_24x24_grid_with_L_20_equals_the_reference():
+    """a grid that is not a power of two, a domain that is not 2*pi: odefun (bump 1e-10) and two RK4 steps of step_packet /
+    step_packet_xka (bump 1e-13) per packet, bit for bit"""
+    bf1, bf2, h, (x, y, k, l) = _g24()
+    ode = O.generate_raytracing_ode(bf1, bf2, x.size, float(R["g24_f"]), float(R["g24_C0"]), 0.2, h)
+    assert np.array_equal(ode(0.06, np.concatenate([x, y, k, l])), R["g24_odefun"])
+    fields = dict(zip(("u", "v", "u_x", "u_y", "v_x", "v_y"), R["g24_planes1"]))
+    fields["H"] = R["g24_H"]
+    for xka, key in ((True, "g24_rk4x2_xka"), (False, "g24_rk4x2_packet")):
+        st = (x, y, k, l, np.ones(x.size))
+        for _ in range(2):
+            st = O.rk4_step_batch(*st, float(R["g24_dt"]), float(R["g24_C0"]), float(R["g24_f"]), fields, h, xka)
+        assert np.array_equal(np.stack(st)[: R[key].shape[0]], R[key]), key
+
+
 def test_oracle_qg_producers_equal_the_reference_locals():
     xs = O.matlab_linspace(-L / 2, L / 2, NX)
     X, Y = np.meshgrid(xs, xs)
@@ -174,6 +195,25 @@ def test_oracle_raytrace_driver_equals_the_executed_script():
 
 
 # ---------------------------------------------------------------------------------------------------------- product, on the GPU
+@pytest.mark.gpu
+def test_gpu_on_a_24x24_grid_with_L_20_equals_the_reference():
+    import swraytracing_b200 as S
+    bf1, bf2, h, (x, y, k, l) = _g24()
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    f, C0, dt, L24 = float(R["g24_f"]), float(R["g24_C0"]), float(R["g24_dt"]), float(R["g24_L"])
+    with S.Engine(24, L24, f, C0 * C0, S.MODE_LAGRANGE6, bump=1e-10) as e:
+        e.set_flow_grid(*[bf1[n] for n in names], slot=0); e.set_flow_grid(*[bf2[n] for n in names], slot=1)
+        e.set_packets(x, y, k, l)
+        assert np.array_equal(np.concatenate(e.rhs(0.3)), R["g24_odefun"])
+    for xka, key, sch in ((True, "g24_rk4x2_xka", S.SCHEME_RK4_XKA), (False, "g24_rk4x2_packet", S.SCHEME_RK4_PACKET)):
+        with S.Engine(24, L24, f, C0 * C0, S.MODE_LAGRANGE6) as e:
+            e.set_flow_grid(*[bf1[n] for n in names], H=R["g24_H"] if xka else None, slot=0)
+            e.set_packets(x, y, k, l)
+            e.step(sch, dt, 2)
+            got = np.stack(e.get_packets(with_a=True))
+            assert np.array_equal(got[: R[key].shape[0]], R[key]), key
+
+
 @pytest.mark.gpu
 def test_gpu_theoretical_omega_pdf_equals_the_executed_script():
     """reference_api.ideal_omega_distribution (swrt_ideal_omega_hist: evaluation + binning on the device) on the same scheme:
