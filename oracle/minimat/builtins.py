@@ -555,7 +555,16 @@ def _minmax(fn, argfn):
             return simplify(np.where(pick, x, y))
         if x.size == 0:
             return (EMPTY, EMPTY)[:max(nargout, 1)]
-        d = _int(args[2]) - 1 if len(args) > 2 else _reduce_dim(x, [])
+        if len(args) > 2 and type(args[2]) is str and args[2] == "all":
+            x = x.reshape(-1, 1, order="F")
+            d = 0
+        elif len(args) > 2 and numel(args[2]) > 1:                   # vecdim: reduce over several dimensions, one after another
+            dims = sorted(int(q) - 1 for q in to_arr(args[2]).reshape(-1))
+            for dd in dims:
+                x = to_arr(f(I, [x, EMPTY, float(dd + 1)], 1, frame))
+            return simplify(x)
+        else:
+            d = _int(args[2]) - 1 if len(args) > 2 else _reduce_dim(x, [])
         x = _along(x, d)
         key = np.abs(x) if x.dtype.kind == "c" else x
         with np.errstate(all="ignore"):
@@ -777,6 +786,75 @@ def _colon(I, args, nargout, frame):
     if len(args) == 2:
         return make_range(args[0], 1.0, args[1])
     return make_range(args[0], args[1], args[2])
+
+
+# ------------------------------------------------------------------------------------------------ page-wise linear algebra
+def _pages_first(x):
+    """m x k x p1 x p2 ... -> (p..., m, k) for numpy's stacked linear algebra"""
+    if x.ndim == 2:
+        return x
+    return np.moveaxis(x, (0, 1), (-2, -1))
+
+
+def _pages_last(x):
+    if x.ndim == 2:
+        return x
+    return np.asfortranarray(np.moveaxis(x, (-2, -1), (0, 1)))
+
+
+@reg("pagemtimes")
+def _pagemtimes(I, args, nargout, frame):
+    a, b = _f(args[0]), _f(args[1])
+    # numpy stacks pages in front; MATLAB keeps them behind: pages are reversed into numpy order and back
+    A = np.transpose(_pages_first(a), tuple(range(a.ndim - 2))[::-1] + (a.ndim - 2, a.ndim - 1)) if a.ndim > 2 else a
+    B = np.transpose(_pages_first(b), tuple(range(b.ndim - 2))[::-1] + (b.ndim - 2, b.ndim - 1)) if b.ndim > 2 else b
+    C = np.matmul(A, B)
+    if C.ndim > 2:
+        C = np.transpose(C, tuple(range(C.ndim - 2))[::-1] + (C.ndim - 2, C.ndim - 1))
+    return simplify(_pages_last(C))
+
+
+@reg("pageinv")
+def _pageinv(I, args, nargout, frame):
+    a = _f(args[0])
+    return simplify(_pages_last(np.linalg.inv(_pages_first(a))))
+
+
+@reg("pageeig")
+def _pageeig(I, args, nargout, frame):
+    """[V, D] = pageeig(A): eigenvectors (unit 2-norm, as LAPACK returns them) and the diagonal eigenvalue matrix of every page.
+    Order and phase of the eigenvectors are LAPACK's in MATLAB and in numpy alike, and arbitrary in both; callers may only rely
+    on V*D*inv(V)."""
+    a = _f(args[0])
+    w, v = np.linalg.eig(_pages_first(a))
+    if nargout < 2:
+        return simplify(_pages_last(w[..., :, None]))
+    d = np.zeros(v.shape, dtype=w.dtype)
+    idx = np.arange(w.shape[-1])
+    d[..., idx, idx] = w
+    return [simplify(_pages_last(v)), simplify(_pages_last(d))]
+
+
+@reg("eig")
+def _eig(I, args, nargout, frame):
+    a = _f(args[0])
+    w, v = np.linalg.eig(a)
+    if nargout < 2:
+        return simplify(w.reshape(-1, 1))
+    return [simplify(np.asfortranarray(v)), simplify(np.asfortranarray(np.diag(w)))]
+
+
+@reg("inv")
+def _inv(I, args, nargout, frame):
+    return simplify(np.asfortranarray(np.linalg.inv(_f(args[0]))))
+
+
+@reg("diag")
+def _diag(I, args, nargout, frame):
+    a = _f(args[0])
+    if 1 in a.shape:
+        return simplify(np.asfortranarray(np.diag(a.reshape(-1))))
+    return simplify(np.diag(a).reshape(-1, 1))
 
 
 # ------------------------------------------------------------------------------------------------ FFT kit
@@ -1388,6 +1466,14 @@ def _clear(I, args, nargout, frame):
         return
     for nm in names:
         I.owner(frame, nm).vars.pop(nm, None) if frame.parent is not None else frame.vars.pop(nm, None)
+
+
+@reg("get")
+def _get(I, args, nargout, frame):
+    # graphics property query; only the default colormap size is ever looked at (qg_flow_ray_trace/redblue.m:18)
+    if len(args) > 1 and type(args[1]) is str and args[1].lower() == "colormap":
+        return np.zeros((256, 3), order="F")
+    return EMPTY
 
 
 # graphics and session commands the driver scripts sprinkle around the numerics: accepted, ignored

@@ -167,6 +167,36 @@ def main():
     out["read_field_frames_3_1"] = np.asarray(I.call("read_field", "io/grid", float(nx), float(nx), 1.0, np.array([[3.0, 1.0]]), 1.0))
     I.close_all()
 
+    # ---- the two-layer driver as a whole: qg2layersw_raytrace(32, 0, 2, 600, 100, 0.3, 3, 1) -- rng(5), initial_q, the B /
+    #      factor_L operators, pageeig / pageinv / pagemtimes, the CFL logic, Euler / AB2 / AB3 with the integrating factor, the
+    #      plotting calls swallowed -- stopped at its 7th call of update(); qk at the start of steps 1, 2, 4, 7 and the log header
+    tmp2 = Path(tempfile.mkdtemp(prefix="swrt_qg2_")); (tmp2 / "data").mkdir()
+    buf2 = io.StringIO()
+    Q2 = Interp(cwd=str(tmp2), out=buf2)
+    Q2.path.insert(0, str(ref / "qg_flow_ray_trace"))
+    uq = Q2.load_unit(str(ref / "qg_flow_ray_trace" / "qg2layersw_raytrace.m"))
+    ref_update, states = uq.funcs["update"], []
+
+    class _Stop2(Exception):
+        pass
+
+    def recording_update(I_, args, nargout, frame):
+        states.append(np.asarray(args[0]).copy())                # qk at the start of this step
+        if len(states) >= 7:
+            raise _Stop2()
+        return I_.call_funcdef(ref_update, args, nargout, frame)
+    uq.funcs["update"] = recording_update                        # a recorder in front of the unmodified local function
+    try:
+        Q2.call("qg2layersw_raytrace", 32, 0, 2, 600, 100, 0.3, 3, 1, nargout=0)
+    except _Stop2:
+        pass
+    uq.funcs["update"] = ref_update
+    Q2.close_all()
+    out["qg2_driver_states"] = np.stack([states[j] for j in (0, 1, 3, 6)])
+    out["qg2_driver_log"] = np.array(buf2.getvalue().split("Simulation progress")[0])
+    for unit_path in Q2.units:
+        I.units.setdefault(unit_path, Q2.units[unit_path])
+
     # ---- the theoretical omega pdf: ideal_omega_distribution.m is a SCRIPT over the caller's workspace (U = scheme.U on the
     #      grid of symplectic_full_fourier.m:14-15,31; f, Cg; w); run as one, with histogram() replaced by a recorder -------------
     K = Interp(cwd=str(ref), out=io.StringIO())

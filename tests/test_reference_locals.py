@@ -162,6 +162,20 @@ def test_product_field_files_equal_the_reference_writer_and_reader(tmp_path):
     assert np.array_equal(got[:, :, 0], H["grids"][2]) and np.array_equal(got[:, :, 1], H["grids"][0])
 
 
+def test_oracle_two_layer_driver_equals_the_executed_driver():
+    """qg2layersw_raytrace(32, 0, 2, 600, 100, 0.3, 3, 1) executed as the reference wrote it (rng(5), B / factor_L, pageeig,
+    integrating-factor AB3, CFL logic): the restated driver has the same PV spectra at the start of steps 1, 2, 4, 7 --
+    bit-identical before the first step, to round-off after (V exp(D t) V^-1 is evaluated by einsum here, pagemtimes there) --
+    and prints the same header"""
+    log = str(R["qg2_driver_log"])
+    for steps, ref in zip((0, 1, 3, 6), R["qg2_driver_states"]):
+        r = O.qg2layersw_driver(32, 0, 2, 600, 100, 0.3, 3.0, 1.0, max_steps=steps)
+        err = np.abs(r["qk"] - ref).max() / np.abs(ref).max()
+        assert (err == 0.0) if steps == 0 else (err < 1e-13), (steps, err)
+    assert "Initial time step: %f" % r["dt"] in log and "Froude Number: %f" % r["Fr"] in log
+    assert "Background velocity (parameter,computed): (0.300000,%f)" % (r["Fr"] * 1.0) in log and "Simulation time: %f" % r["T"] in log
+
+
 def test_theoretical_omega_pdf_of_the_executed_script():
     """ideal_omega_distribution.m run as a script on U = scheme.U(grid): omega_abs = omega_0 + U.k over (grid point, angle) --
     restated here in three numpy lines from the stored U, and binned (histcounts rule) into the stored counts"""
@@ -212,6 +226,27 @@ def test_gpu_on_a_24x24_grid_with_L_20_equals_the_reference():
             e.step(sch, dt, 2)
             got = np.stack(e.get_packets(with_a=True))
             assert np.array_equal(got[: R[key].shape[0]], R[key]), key
+
+
+@pytest.mark.gpu
+def test_gpu_two_layer_solver_equals_the_executed_driver():
+    """the on-device two-layer QG solver (swrt_qg2_*: B, expm(factor_L dt) and the AB3 history on the GPU) from the executed
+    driver's initial spectra: its states at the start of steps 2, 4, 7"""
+    import swraytracing_b200 as S
+    nx, Lq = 32, 20.0
+    st = R["qg2_driver_states"]
+    dt = float(str(R["qg2_driver_log"]).split("Initial time step: ")[1].split()[0])
+    r = O.qg2layersw_driver(nx, 0, 2, 600, 100, 0.3, 3.0, 1.0, max_steps=0)
+    assert abs(r["dt"] - dt) < 1e-6
+    g2 = S.QG2Flow(nx, Lq, st[0][:, :, 0], st[0][:, :, 1], 3.0, 0.0, 0.5, 0.4, 0.1 * (Lq / nx) ** 8, 4)
+    assert abs(g2.max_speed() - r["U0"]) < 1e-12 * r["U0"]
+    done = 0
+    for steps, ref in zip((1, 3, 6), st[1:]):
+        while done < steps:
+            g2.step(r["dt"]); done += 1
+        got = np.stack([g2.get(0), g2.get(1)], axis=2)
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-12, steps
+    g2.close()
 
 
 @pytest.mark.gpu
