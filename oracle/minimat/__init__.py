@@ -23,6 +23,9 @@ to numbers that REAL MATLAB produced and the reference still holds (``tests/test
   depends on arithmetic (``rng(146)`` -> ``rand`` -> ``initial_q`` with its always-true chained comparison -> ``g2k`` ->
   ``grid_U`` -> 6 x ``k2g`` -> ``U0``, ``Fr``, ``dt``; 'Simulation time' is skipped, the logged runs defined T differently) --
   and the ``pv_time`` frames its solver loop writes land within 2 ulps of the stream the reference's own run stored;
+* running the unmodified ``rsw/swk.m`` -- a 359-line pseudo-spectral rotating-shallow-water solver -- from the initial condition
+  that ``rsw/matlab.mat`` (MATLAB's own workspace dump at step 300 of that run) still holds, for the same 300 steps, reproduces
+  the clock, time step, viscosity and counters MATLAB held EXACTLY, the spectral state to 1e-15 and the energy series to 1e-13;
 * running the unmodified ``rsw/k2g.m`` / ``fulspec.m`` on the spectral state of ``rsw/matlab.mat`` reproduces the grid fields
   MATLAB stored in the same workspace to 1e-15.
 

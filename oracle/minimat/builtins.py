@@ -732,6 +732,12 @@ def _fliplr(I, args, nargout, frame):
     return simplify(np.asfortranarray(to_arr(args[0])[:, ::-1]))
 
 
+@reg("rot90")
+def _rot90(I, args, nargout, frame):
+    k = _int(args[1]) if len(args) > 1 else 1
+    return simplify(np.asfortranarray(np.rot90(to_arr(args[0]), k)))           # counter-clockwise, like MATLAB
+
+
 @reg("circshift")
 def _circshift(I, args, nargout, frame):
     x = to_arr(args[0])

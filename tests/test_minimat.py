@@ -5,8 +5,9 @@
    parent workspace, closures, classdef with inheritance and method dispatch, command syntax, ``fread`` / ``fwrite``).
 2. Against numbers REAL MATLAB produced and the reference still holds (needs ``/root/reference``; skipped on the GPU box):
    the unmodified ``qg_flow_ray_trace/qgsw_raytrace.m`` run under minimat prints the header lines MATLAB R2020b printed into
-   the shipped SLURM logs, its ``pv_time`` stream lands within 2 ulps of the stored one, and the unmodified ``rsw/k2g.m`` /
-   ``fulspec.m`` reproduce the grid fields stored in ``rsw/matlab.mat``.
+   the shipped SLURM logs, its ``pv_time`` stream lands within 2 ulps of the stored one, the unmodified ``rsw/k2g.m`` /
+   ``fulspec.m`` reproduce the grid fields stored in ``rsw/matlab.mat``, and the unmodified solver ``rsw/swk.m`` run for 300
+   steps from the initial condition in that file reproduces the whole workspace MATLAB dumped at step 300.
 3. The committed hot-path goldens (``tests/golden/octave_out``) are what running the unmodified reference gives: a slice of
    the recipe is re-run here and compared bit for bit, and the sha256 of every executed reference file is checked.
 """
@@ -493,6 +494,45 @@ def test_unmodified_k2g_reproduces_the_fields_in_matlabs_workspace_dump(tmp_path
         rows = R[name + "_rows"]
         assert np.abs(rows).max() > 1e-2
         assert np.abs(fr.vars[name][::stride] - rows).max() <= 1e-15, name
+
+
+@needs_ref
+def test_unmodified_swk_run_for_300_steps_reproduces_matlabs_workspace(tmp_path):
+    """The strongest pin of the interpreter.  ``rsw/matlab.mat`` is the workspace MATLAB dumped (the bare ``save`` of
+    rsw/swk.m:178) at step n = 300 of ``swk(Sin, f, Cg, 10000, 100)`` -- and it still holds the inputs.  The unmodified
+    ``rsw/swk.m`` (a 359-line pseudo-spectral rotating-shallow-water solver: globals, eight local functions closed by ``return``,
+    Orszag-dealiased products through half-cell-shifted grids, AB3 with trapezoidal hyperviscosity, adaptive dt) is run by
+    minimat from the same ``Sin`` for the same 300 steps and stopped at the same ``save``: the clock, time step, viscosity, Umax
+    and counters MATLAB held are reproduced EXACTLY, the spectral state to 1e-15, the three saved right-hand sides to 1e-14 and
+    the energy series to 1e-13 (the residue is FFTW vs pocketfft round-off through 300 nonlinear steps)."""
+    sio = pytest.importorskip("scipy.io")
+    names = ["Sin", "f", "Cg", "numsteps", "savestep", "n", "frame", "t", "dt", "nu", "Umax", "Sk", "Rk", "Rkm1", "Rkm2", "time", "ke", "pe"]
+    M = sio.loadmat(str(REF / "rsw" / "matlab.mat"), variable_names=names)
+    sc = lambda k: float(M[k][0, 0])
+    assert sc("n") == 300 and sc("frame") == 4 and sc("savestep") == 100
+    I = Interp(cwd=str(tmp_path), out=io.StringIO())
+    I.path.insert(0, str(REF / "rsw"))
+    snap = {}
+
+    def save(I_, args, nargout, frame):                      # the bare ``save``: snapshot the workspace at n = 300 and stop there
+        if I_.getvar(frame, "n") == sc("n"):
+            for k in ("Sk", "Rk", "Rkm1", "Rkm2", "time", "ke", "pe", "dt", "nu", "Umax", "t", "frame", "n"):
+                snap[k] = I_.getvar(frame, k)
+            raise _Stop()
+    I.overrides["save"] = save
+    with pytest.raises(_Stop):
+        I.call("swk", M["Sin"], sc("f"), sc("Cg"), sc("numsteps"), sc("savestep"), nargout=4)
+    for k in ("t", "dt", "nu", "Umax", "frame", "n"):
+        assert snap[k] == sc(k), (k, snap[k], sc(k))
+    rel = lambda a, b: float(np.abs(np.asarray(a) - b).max() / np.abs(b).max())
+    assert rel(snap["Sk"], M["Sk"]) < 1e-15
+    for k in ("Rk", "Rkm1", "Rkm2"):
+        assert rel(snap[k], M[k]) < 1e-14, k
+    fr = int(sc("frame"))
+    assert np.array_equal(np.asarray(snap["time"]).ravel()[:fr], M["time"].ravel()[:fr])
+    for k in ("ke", "pe"):
+        assert rel(np.asarray(snap[k]).ravel()[:fr], M[k].ravel()[:fr]) < 1e-13, k
+    assert "Wrote frame >4 out of >100" in I.out.getvalue()
 
 
 def _frame_with(**kw):
