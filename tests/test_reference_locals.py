@@ -208,6 +208,22 @@ def test_oracle_raytrace_driver_equals_the_executed_script():
     assert np.abs(R["raytrace_GradU_v_x"]).max() > 10 * 0.4 * 1.25            # the matrix product blows v_x up far beyond km*U0*(1+a)
 
 
+def test_oracle_raytrace_sw_driver_equals_the_executed_script():
+    """ray_trace_sw/raytrace_sw.m run as a script on a seeded [u,v,eta] state served to its ``load``: geostrophic projection,
+    gradients and H (rsw/g2k.m, k2g.m), U0 / dt / nsteps, ring of packets from the start-up random stream, 150 step_packet_xka
+    calls on packet 1 with wave action -- the restated driver gives the same doubles"""
+    hist, info = O.raytrace_sw_driver(R["rsw_S"], 3.0, 1.0, np_=10, nsteps=151)
+    assert info["dt"] == float(R["rsw_dt"]) and info["U0"] == float(R["rsw_U0"])
+    assert int(round(20 / (3.0 * info["Fr"] ** 2) / info["dt"])) == int(R["rsw_nsteps"])
+    got = [info["U"]["u"], info["U"]["v"]] + [info["GradU"][c] for c in ("u_x", "u_y", "v_x", "v_y")] + [info["H"]]
+    for j, g in enumerate(got):
+        assert np.array_equal(g, R["rsw_fields"][j]), j
+    for j, c in enumerate("xykla"):
+        assert np.array_equal(hist[c][:, 0], R["rsw_P0"][:, j]), c
+        assert np.array_equal(hist[c][0, :151], R["rsw_p1"][:, j]), c
+    assert abs(R["rsw_p1"][-1, 4] - 1.0) > 1e-3                     # the wave action has moved
+
+
 # ---------------------------------------------------------------------------------------------------------- product, on the GPU
 @pytest.mark.gpu
 def test_gpu_on_a_24x24_grid_with_L_20_equals_the_reference():
@@ -329,3 +345,20 @@ def test_gpu_qg_solver_first_step_equals_the_reference_update():
     got = qg.get()
     qg.close()
     assert rel(got, want) <= 1e-13
+
+
+@pytest.mark.gpu
+def test_gpu_raytrace_sw_driver_equals_the_executed_script():
+    """drivers.raytrace_sw (BASELINE config 5's caller: device k2g for the projection, step_packet_xka on the device) on the
+    executed script's output: fields to 1e-14 of each plane, 100 steps of packet 1 within 1e-9, 150 within 1e-8"""
+    from swraytracing_b200 import drivers
+    out = drivers.raytrace_sw(R["rsw_S"], 3.0, 1.0, np_=10, nsteps=151)
+    assert abs(out["dt"] - float(R["rsw_dt"])) < 1e-15 and abs(out["U0"] - float(R["rsw_U0"])) < 1e-13
+    got = [out["U"]["u"], out["U"]["v"]] + [out["GradU"][c] for c in ("u_x", "u_y", "v_x", "v_y")] + [out["H"]]
+    for j, g in enumerate(got):
+        assert rel(g, R["rsw_fields"][j]) <= 1e-14, j
+    P = out["P"]
+    for j, c in enumerate("xykla"):
+        assert np.array_equal(P[c][:, 0], R["rsw_P0"][:, j]), c
+        assert np.abs(P[c][0, :101] - R["rsw_p1"][:101, j]).max() <= 1e-9, c
+        assert np.abs(P[c][0, :151] - R["rsw_p1"][:, j]).max() <= 1e-8, c
