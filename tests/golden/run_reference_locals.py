@@ -54,16 +54,20 @@ def edge_positions(nx, dx, L):
     return x, y
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=str(HERE / "reference_locals_nx32.npz"))
-    a = ap.parse_args()
+    ap.add_argument("--quick", action="store_true", help="shorter script runs (40 / 30 packet steps instead of 300 / 150): what "
+                    "tests/test_reference_locals.py re-runs against the committed file")
+    a = ap.parse_args(argv)
     ref = Path(a.ref)
     G = np.load(HERE / "hotpath_nx32.npz")
     nx, L, f = int(G["nx"]), float(G["L"]), float(G["f"])
     dx = L / nx
     x, y, k, l = (G[n] for n in ("x", "y", "k", "l"))
+    if a.quick:                                          # the per-packet outputs of the first 24 packets only
+        x, y, k, l = x[:24], y[:24], k[:24], l[:24]
     n = x.size
     kx_, ky_ = O.wavenumbers(nx)
     g1 = list(G["grids"])
@@ -221,7 +225,7 @@ def main():
         pass
     J = Interp(cwd=str(ref / "ray_trace_sw"), out=io.StringIO())
     sp = J.load_unit(str(ref / "ray_trace_sw" / "step_packet.m")).main
-    nrun, count = 300, [0]
+    nrun, count = (40 if a.quick else 300), [0]
 
     def counted_step_packet(I_, args, nargout, frame):
         if count[0] >= nrun:
@@ -258,7 +262,7 @@ def main():
         frame.vars.update({"S": fa(S5), "nx": float(nx5), "f": 3.0, "Cg": 1.0})
     W5.overrides["load"] = load_state
     spx = W5.load_unit(str(ref / "ray_trace_sw" / "step_packet_xka.m")).main
-    nrun5, count5 = 150, [0]
+    nrun5, count5 = (30 if a.quick else 150), [0]
 
     def counted_xka(I_, args, nargout, frame):
         if count5[0] >= nrun5:

@@ -59,6 +59,31 @@ def test_provenance_lists_the_driver_files():
             assert hashlib.sha256((ref / relp).read_bytes()).hexdigest() == sha, relp
 
 
+@pytest.mark.skipif(not Path("/root/reference/ode_symplectic.m").exists(), reason="the reference checkout is not on this machine")
+def test_rerunning_the_generator_reproduces_the_committed_file(tmp_path):
+    """tests/golden/run_reference_locals.py --quick, executed again here from the unmodified reference: every array equals the
+    committed one bit for bit (the two script trajectories are compared on the steps the quick run makes)"""
+    sys.path.insert(0, str(GOLD))
+    import run_reference_locals as G
+    out = tmp_path / "locals.npz"
+    G.main(["--quick", "--out", str(out)])
+    N = np.load(out)
+    assert set(N.files) == set(R.files)
+    for key in R.files:
+        if key == "provenance":
+            assert json.loads(str(N[key]))["reference_files_executed"] == json.loads(str(R[key]))["reference_files_executed"]
+        elif key in ("raytrace_p1", "rsw_p1"):
+            assert np.array_equal(N[key], R[key][: N[key].shape[0]]), key
+        elif key.startswith("odefun_") or key in ("ode_xk2y", "qg2_odefun_tmid"):            # [x; y; k; l] blocks of the first 24 packets
+            assert np.array_equal(N[key].reshape(4, 24), R[key].reshape(4, -1)[:, :24]), key
+        elif key in ("ode_y2xk_x", "ode_y2xk_k"):
+            assert np.array_equal(N[key], R[key][:24]), key
+        elif key == "interpolate_par":
+            assert np.array_equal(N[key], R[key][:, :24]), key
+        else:
+            assert np.array_equal(N[key], R[key]), key
+
+
 def test_oracle_odefun_and_state_packing_equal_the_nested_reference_function():
     """qgsw_raytrace.m:232-268: y = [x; y; k; l]; dydt bit for bit at alpha = 0, 1/4, 1 (pure Lagrange arithmetic + blend)"""
     x, y, k, l = (H[n] for n in ("x", "y", "k", "l"))
