@@ -171,6 +171,26 @@ def main(argv=None):
     out["read_field_frames_3_1"] = np.asarray(I.call("read_field", "io/grid", float(nx), float(nx), 1.0, np.array([[3.0, 1.0]]), 1.0))
     I.close_all()
 
+    # ---- BASELINE config 1 as the reference would run it: 1,000 packets, ZERO background flow, the symplectic stepper
+    #      (SpectralScheme of a zero streamfunction + ode_symplectic.m, five leapfrog steps) -- plumbing + analytic dispersion
+    rs1 = np.random.RandomState(101)
+    n1 = 40 if a.quick else 1000
+    c1 = {"x": rs1.uniform(-3 * L, 3 * L, 1000)[:n1], "y": rs1.uniform(-3 * L, 3 * L, 1000)[:n1],
+          "k": rs1.uniform(-6, 6, 1000)[:n1], "l": rs1.uniform(-6, 6, 1000)[:n1]}
+    C1 = Interp(cwd=str(ref), out=io.StringIO())
+    w1 = Frame(None)
+    x3 = np.zeros((1, 2, n1)); x3[0, 0], x3[0, 1] = c1["x"], c1["y"]
+    k3 = np.zeros((1, 2, n1)); k3[0, 0], k3[0, 1] = c1["k"], c1["l"]
+    w1.vars.update({"L": L, "nx": float(nx), "x3": fa(x3), "k3": fa(k3), "f": 3.0, "gH": 1.0, "dt": 0.01})
+    C1.run("scheme = SpectralScheme(L, nx, zeros(nx)); [xs, ks, ts] = ode_symplectic(x3, k3, dt, 6.5*dt, f, gH, scheme);", w1)
+    xs, ks = np.asarray(w1.vars["xs"]), np.asarray(w1.vars["ks"])
+    assert xs.shape == (6, 2, n1)
+    out["c1_x"], out["c1_y"], out["c1_k"], out["c1_l"] = (rs_ for rs_ in (c1["x"], c1["y"], c1["k"], c1["l"]))
+    out["c1_final"] = np.stack([xs[5, 0], xs[5, 1], ks[5, 0], ks[5, 1]])
+    out["c1_t"] = np.asarray(w1.vars["ts"]).ravel()
+    for unit_path in C1.units:
+        I.units.setdefault(unit_path, C1.units[unit_path])
+
     # ---- the two-layer driver as a whole: qg2layersw_raytrace(32, 0, 2, 600, 100, 0.3, 3, 1) -- rng(5), initial_q, the B /
     #      factor_L operators, pageeig / pageinv / pagemtimes, the CFL logic, Euler / AB2 / AB3 with the integrating factor, the
     #      plotting calls swallowed -- stopped at its 7th call of update(); qk at the start of steps 1, 2, 4, 7 and the log header

@@ -80,6 +80,10 @@ def test_rerunning_the_generator_reproduces_the_committed_file(tmp_path):
             assert np.array_equal(N[key], R[key][:24]), key
         elif key == "interpolate_par":
             assert np.array_equal(N[key], R[key][:, :24]), key
+        elif key in ("c1_x", "c1_y", "c1_k", "c1_l"):
+            assert np.array_equal(N[key], R[key][:40]), key
+        elif key == "c1_final":
+            assert np.array_equal(N[key], R[key][:, :40]), key
         else:
             assert np.array_equal(N[key], R[key]), key
 
@@ -231,6 +235,24 @@ def test_oracle_raytrace_driver_equals_the_executed_script():
     _, _, G = O.childress_soward_as_written(256, 2 * np.pi, 0.1, 4.0, 0.25)
     assert np.array_equal(G["v_x"], R["raytrace_GradU_v_x"])
     assert np.abs(R["raytrace_GradU_v_x"]).max() > 10 * 0.4 * 1.25            # the matrix product blows v_x up far beyond km*U0*(1+a)
+
+
+def test_config_1_zero_background_flow_under_the_executed_reference():
+    """BASELINE config 1 (1,000 packets, zero background flow, symplectic step; plumbing + analytic dispersion): five steps of
+    the reference's own ode_symplectic.m over a SpectralScheme of a zero streamfunction.  The packets move in straight lines at
+    the group velocity, k unchanged -- the analytic answer to 1e-13 -- and the restated stepper gives the same doubles."""
+    x, y, k, l = (R["c1_" + c] for c in "xykl")
+    assert x.size == 1000
+    fin = R["c1_final"]
+    w = np.sqrt(9.0 + (k * k + l * l))
+    assert np.array_equal(fin[2], k) and np.array_equal(fin[3], l)
+    assert np.abs(fin[0] - (x + 5 * 0.01 * k / w)).max() < 1e-13 and np.abs(fin[1] - (y + 5 * 0.01 * l / w)).max() < 1e-13
+    assert np.allclose(R["c1_t"], 0.01 * np.arange(6), rtol=0, atol=1e-17)
+    zero = [np.zeros((NX, NX))] * 6
+    st = (x, y, k, l)
+    for _ in range(5):
+        st = O.leapfrog_step(*st, 0.01, 3.0, 1.0, lambda xx, yy: [O.interpolate(xx, yy, g, DX, DX) for g in zero])
+    assert np.array_equal(np.stack(st), fin)
 
 
 def test_oracle_raytrace_sw_driver_equals_the_executed_script():
@@ -387,3 +409,18 @@ def test_gpu_raytrace_sw_driver_equals_the_executed_script():
         assert np.array_equal(P[c][:, 0], R["rsw_P0"][:, j]), c
         assert np.abs(P[c][0, :101] - R["rsw_p1"][:101, j]).max() <= 1e-9, c
         assert np.abs(P[c][0, :151] - R["rsw_p1"][:, j]).max() <= 1e-8, c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["SPECTRAL", "NUFFT", "LAGRANGE6"])
+def test_gpu_config_1_zero_background_flow_equals_the_executed_reference(mode):
+    """config 1 on the device, all three modes: five fused leapfrog steps over a zero flow == the reference's own run"""
+    import swraytracing_b200 as S
+    x, y, k, l = (R["c1_" + c] for c in "xykl")
+    with S.Engine(NX, L, 3.0, 1.0, getattr(S, "MODE_" + mode)) as e:
+        e.set_flow_spectral(np.zeros((NX - 1, NX // 2), dtype=complex))
+        e.set_packets(x, y, k, l)
+        e.step(S.SCHEME_LEAPFROG, 0.01, 5)
+        got = np.stack(e.get_packets())
+    assert np.array_equal(got[2:], R["c1_final"][2:])
+    assert np.abs(got[:2] - R["c1_final"][:2]).max() <= 1e-13
