@@ -1440,6 +1440,59 @@ def _feof(I, args, nargout, frame):
     return pos >= end
 
 
+@reg("textscan")
+def _textscan(I, args, nargout, frame):
+    """textscan(fid, format [, N] [, 'delimiter', d] [, 'headerlines', h]) -> 1 x nconv cell of columns.  The subset the
+    reference's log parser uses (symplectic_full_fourier.m:68-83): literal text with %f / %d conversions, applied up to N times
+    (as often as it matches when N is absent); white space in the format matches any run of white space, including line
+    breaks; 'headerlines' first skips that many line ends, the remainder of the current line counting as one; the file
+    position is left behind the last character consumed."""
+    fh = I.files[_int(args[0])]
+    fmt = args[1]
+    rest = list(args[2:])
+    nrep = None
+    if rest and type(rest[0]) is not str:
+        nrep = _int(rest.pop(0))
+    opts = {rest[i].lower(): rest[i + 1] for i in range(0, len(rest) - 1, 2)}
+    start = fh.tell()
+    text = fh.read().decode("latin-1")
+    pos = 0
+    for _ in range(int(opts.get("headerlines", 0))):
+        j = text.find("\n", pos)
+        pos = len(text) if j < 0 else j + 1
+    # format -> regex
+    pieces = re.split(r"(%[fd])", fmt.replace("\\n", "\n"))
+    pat, nconv = "", 0
+    for pc in pieces:
+        if pc in ("%f", "%d"):
+            pat += r"\s*([-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?)" if pc == "%f" else r"\s*([-+]?\d+)"
+            nconv += 1
+        else:
+            pat += r"\s*".join(re.escape(w) for w in re.split(r"\s+", pc)) if pc.strip() else (r"\s*" if pc else "")
+    rx = re.compile(r"\s*" + pat)
+    cols = [[] for _ in range(nconv)]
+    while nrep is None or len(cols[0]) < nrep:
+        m = rx.match(text, pos)
+        if not m or m.end() == pos:
+            break
+        for c, g in zip(cols, m.groups()):
+            c.append(float(g))
+        pos = m.end()
+    fh.seek(start + len(text[:pos].encode("latin-1")))
+    return MCell.row([simplify(np.array(c, dtype=np.float64).reshape(-1, 1)) if c else np.zeros((0, 1)) for c in cols])
+
+
+@reg("vecnorm")
+def _vecnorm(I, args, nargout, frame):
+    x = _f(args[0])
+    p = float(args[1]) if len(args) > 1 else 2.0
+    d = _int(args[2]) - 1 if len(args) > 2 else _reduce_dim(x, [])
+    if p != 2.0:
+        raise MatlabError("vecnorm: only the 2-norm is implemented")
+    sq = _sum(I, [np.abs(x) ** 2, float(d + 1)], 1, frame)
+    return simplify(np.sqrt(to_arr(sq)))
+
+
 @reg("tic")
 def _tic(I, args, nargout, frame):
     I.tic_time = time.perf_counter()

@@ -191,7 +191,14 @@ class Interp:
                 return []
             return list(r) if isinstance(r, (tuple, list)) else [r]
         if hasattr(fn, "script"):
-            self.exec_block(fn.script, frame)
+            # a script runs in the caller's workspace; the local functions at the end of its file are visible while it runs
+            prev = frame.func
+            if prev is None or prev.unit is not fn:
+                frame.func = FuncDef("<script>", [], [], fn)
+            try:
+                self.exec_block(fn.script, frame)
+            finally:
+                frame.func = prev
             return []
         raise MatlabError(f"cannot call {fn!r}")
 
