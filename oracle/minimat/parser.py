@@ -574,6 +574,9 @@ class Parser:
                     self.adv()
                     args.append(("colon",))
                     continue
+                if close == ")" and self.tok.kind == "id" and self.peek().kind == "op" and self.peek().val == "=":
+                    args.append(("str", self.adv().val))          # name=value argument (R2021a): f(..., FontSize=14)
+                    self.adv()
                 args.append(self.parse_expr())
         finally:
             self.matrix.pop()

@@ -384,6 +384,19 @@ def test_errors_are_matlabs():
             run(src)
 
 
+@needs_ref
+def test_every_m_file_of_the_reference_parses():
+    """all 97 .m files of the reference -- scripts, functions with and without ``end``, nested functions, classdefs, command
+    syntax, name=value arguments, block comments -- go through the lexer and parser"""
+    from oracle.minimat.parser import parse_source
+    files = sorted(REF.rglob("*.m"))
+    assert len(files) >= 90
+    kinds = {"script": 0, "function": 0, "class": 0}
+    for f in files:
+        kinds[parse_source(f.read_text(errors="replace"), str(f)).kind] += 1
+    assert kinds["class"] >= 3 and kinds["function"] >= 30 and kinds["script"] >= 20
+
+
 # ------------------------------------------------------------------------------------------ 2. against real MATLAB output
 class _Stop(Exception):
     pass
