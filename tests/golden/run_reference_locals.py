@@ -44,6 +44,12 @@ def flow_struct(planes):
     return MStruct({n: fa(p) for n, p in zip(NAMES, planes)})
 
 
+def FuncDefStub(unit):
+    """a frame context whose file-local function table is ``unit``'s (what a local function of that file sees)"""
+    from oracle.minimat.parser import FuncDef
+    return FuncDef("<local>", [], [], unit)
+
+
 def edge_positions(nx, dx, L):
     i = np.array([0.0, 1.0, 7.0, nx - 1.0, nx / 2.0])
     xs = [i * dx, np.nextafter(i * dx, np.inf), np.nextafter(i * dx, -np.inf), (i + 1e-13) * dx, (i - 1e-13) * dx, (i + 1e-10) * dx,
@@ -190,6 +196,24 @@ def main(argv=None):
     out["c1_t"] = np.asarray(w1.vars["ts"]).ravel()
     for unit_path in C1.units:
         I.units.setdefault(unit_path, C1.units[unit_path])
+
+    # ---- config 1's script, SW_zero_background_raytracing.m: its ode23 right-hand side (nested odefun of the local
+    #      initialize_raytracing: dx/dt = U + gH k/omega, dk/dt = -(grad U)^T k on y = [x y k l] columns) over the reference's own
+    #      SpectralScheme object, and its local omega / grad_omega
+    Z = Interp(cwd=str(ref), out=io.StringIO())
+    uz = Z.load_unit(str(ref / "SW_zero_background_raytracing.m"))
+    wz = Frame(None)
+    wz.vars.update({"L": L, "nx": float(nx), "psi": fa(O.k2g(G["psik"]))})
+    Z.run("scheme = SpectralScheme(L, nx, psi);", wz)
+    zcall = lambda name, *args: Z.call_funcdef(uz.funcs[name], list(args), 1, Frame(FuncDefStub(uz)))[0]
+    rayfun = zcall("initialize_raytracing", wz.vars["scheme"], f, 1.7, float(n))
+    yz = np.concatenate([x, y, k, l]).reshape(-1, 1)
+    out["swz_odefun"] = np.asarray(Z.call_handle(rayfun, [0.0, fa(yz)], 1, None)[0]).ravel()
+    kk2 = fa(np.stack([k, l], axis=1))
+    out["swz_omega"] = np.asarray(zcall("omega", kk2, f, 1.7)).ravel()
+    out["swz_grad_omega"] = np.asarray(zcall("grad_omega", kk2, f, 1.7))
+    for unit_path in Z.units:
+        I.units.setdefault(unit_path, Z.units[unit_path])
 
     # ---- the two-layer driver as a whole: qg2layersw_raytrace(32, 0, 2, 600, 100, 0.3, 3, 1) -- rng(5), initial_q, the B /
     #      factor_L operators, pageeig / pageinv / pagemtimes, the CFL logic, Euler / AB2 / AB3 with the integrating factor, the

@@ -80,6 +80,10 @@ def test_rerunning_the_generator_reproduces_the_committed_file(tmp_path):
             assert np.array_equal(N[key], R[key][:24]), key
         elif key == "interpolate_par":
             assert np.array_equal(N[key], R[key][:, :24]), key
+        elif key == "swz_odefun":
+            assert np.array_equal(N[key].reshape(4, 24), R[key].reshape(4, -1)[:, :24]), key
+        elif key in ("swz_omega", "swz_grad_omega"):
+            assert np.array_equal(N[key], R[key][:24]), key
         elif key in ("c1_x", "c1_y", "c1_k", "c1_l"):
             assert np.array_equal(N[key], R[key][:40]), key
         elif key == "c1_final":
@@ -255,6 +259,25 @@ def test_config_1_zero_background_flow_under_the_executed_reference():
     assert np.array_equal(np.stack(st), fin)
 
 
+def _swz_rhs(ev6, k, l, f, gH):
+    """SW_zero_background_raytracing.m:134-145,182-184 from the six evaluated planes"""
+    u, v, ux, uy, vx, vy = ev6
+    w = np.sqrt(f * f + gH * (k * k + l * l))
+    return np.concatenate([u + gH * k / w, v + gH * l / w, -(ux * k + vx * l), -(uy * k + vy * l)])
+
+
+def test_config_1_script_right_hand_side_equals_the_nested_reference_function():
+    """the ode23 right-hand side of SW_zero_background_raytracing.m (gH k/omega, not Cg k/omega as in the QG drivers) over the
+    reference's own SpectralScheme object, and its local omega / grad_omega"""
+    x, y, k, l = (H[c] for c in "xykl")
+    fields = [O.k2g(p) for p in O.velocity_planes_k(O.g2k(O.k2g(H["psik"])), KX, KY)]
+    ev6 = [O.interpolate(x, y, g, DX, DX) for g in fields]
+    assert np.array_equal(_swz_rhs(ev6, k, l, F0, 1.7), R["swz_odefun"])
+    w = np.sqrt(F0 * F0 + 1.7 * (k * k + l * l))
+    assert np.array_equal(w, R["swz_omega"])
+    assert np.array_equal(np.stack([1.7 * k / w, 1.7 * l / w], axis=1), R["swz_grad_omega"])
+
+
 def test_oracle_raytrace_sw_driver_equals_the_executed_script():
     """ray_trace_sw/raytrace_sw.m run as a script on a seeded [u,v,eta] state served to its ``load``: geostrophic projection,
     gradients and H (rsw/g2k.m, k2g.m), U0 / dt / nsteps, ring of packets from the start-up random stream, 150 step_packet_xka
@@ -424,3 +447,16 @@ def test_gpu_config_1_zero_background_flow_equals_the_executed_reference(mode):
         got = np.stack(e.get_packets())
     assert np.array_equal(got[2:], R["c1_final"][2:])
     assert np.abs(got[:2] - R["c1_final"][:2]).max() <= 1e-13
+
+
+@pytest.mark.gpu
+def test_gpu_config_1_script_right_hand_side_equals_the_nested_reference_function():
+    """swrt_rhs with SWRT_FLAG_RHS_GH (dx/dt = U + gH k/omega) in LAGRANGE6 mode on the scheme's own planes"""
+    import swraytracing_b200 as S
+    from swraytracing_b200.engine import FLAG_RHS_GH
+    x, y, k, l = (H[c] for c in "xykl")
+    with S.Engine(NX, L, F0, 1.7, S.MODE_LAGRANGE6, flags=FLAG_RHS_GH) as e:
+        e.set_flow_spectral(O.g2k(O.k2g(H["psik"])))
+        e.set_packets(x, y, k, l)
+        got = np.concatenate(e.rhs(0.0))
+    assert rel(got, R["swz_odefun"]) <= 1e-12
