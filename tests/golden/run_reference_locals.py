@@ -197,6 +197,42 @@ def main(argv=None):
     for unit_path in C1.units:
         I.units.setdefault(unit_path, C1.units[unit_path])
 
+    # ---- config 3's driver WITH packets: qgsw_raytrace(32, 12, 2, 6000, 0, 0.5, 3, 1) -- no spin-up, so the packets move
+    #      from the first flow step: grid_U of both frames, generate_raytracing_ode / odefun, ode_xk2y / ode_y2xk, the wrapped
+    #      packet frames written by write_field -- all the reference's own code.  Two things are supplied from outside: the
+    #      sixth argument of grid_U (see tests/test_minimat.py) and ``ode23`` itself, a MATLAB builtin (MathWorks code, not the
+    #      reference's), served by the restated controller oracle.ode23 -- so this pins everything AROUND ode23, not ode23.
+    tmp3 = Path(tempfile.mkdtemp(prefix="swrt_qgsw_")); (tmp3 / "data").mkdir()
+    Q3 = Interp(cwd=str(tmp3), out=io.StringIO())
+    Q3.path.insert(0, str(ref / "qg_flow_ray_trace"))
+    ref_grid_U = Q3.load_unit(str(ref / "qg_flow_ray_trace" / "grid_U.m")).main
+    Q3.overrides["grid_U"] = lambda I_, args, nargout, frame: I_.call_funcdef(ref_grid_U, list(args) + [0.0], nargout, frame)
+    calls3 = []
+
+    class _Stop3(Exception):
+        pass
+
+    def ode23_builtin(I_, args, nargout, frame):
+        fun, tspan, y0 = args[0], np.asarray(args[1]).ravel(), np.asarray(args[2]).ravel()
+        calls3.append(y0.copy())
+        if len(calls3) > (2 if a.quick else 6):
+            raise _Stop3()
+        yfin, st = O.ode23(lambda t, yv: np.asarray(I_.call_handle(fun, [float(t), fa(np.asarray(yv).reshape(-1, 1))], 1, frame)[0]).ravel(),
+                           tspan, y0)
+        return [fa(tspan.reshape(-1, 1)), fa(np.stack([y0, yfin]))]          # [t, y]: the caller reads solver_y(end, :)
+    Q3.overrides["ode23"] = ode23_builtin
+    try:
+        Q3.call("qgsw_raytrace", 32, 12, 2, 6000, 0, 0.5, 3, 1, nargout=0)
+    except _Stop3:
+        pass
+    Q3.close_all()
+    out["qgsw_packets_y"] = np.stack(calls3)                                 # y = [x; y; k; l] at the start of steps 1..7
+    for nm in ("packet_x", "packet_k", "packet_time", "pv_time"):
+        out["qgsw_file_" + nm] = np.fromfile(tmp3 / "data" / f"{nm}.bin")
+    out["qgsw_log"] = np.array(Q3.out.getvalue().split("Simulation progress")[0])
+    for unit_path in Q3.units:
+        I.units.setdefault(unit_path, Q3.units[unit_path])
+
     # ---- config 1's script, SW_zero_background_raytracing.m: its ode23 right-hand side (nested odefun of the local
     #      initialize_raytracing: dx/dt = U + gH k/omega, dk/dt = -(grad U)^T k on y = [x y k l] columns) over the reference's own
     #      SpectralScheme object, and its local omega / grad_omega

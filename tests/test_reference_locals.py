@@ -80,6 +80,10 @@ def test_rerunning_the_generator_reproduces_the_committed_file(tmp_path):
             assert np.array_equal(N[key], R[key][:24]), key
         elif key == "interpolate_par":
             assert np.array_equal(N[key], R[key][:, :24]), key
+        elif key == "qgsw_packets_y":
+            assert np.array_equal(N[key], R[key][: N[key].shape[0]]), key
+        elif key.startswith("qgsw_file_"):
+            assert np.array_equal(N[key], R[key][: N[key].size]), key
         elif key == "swz_odefun":
             assert np.array_equal(N[key].reshape(4, 24), R[key].reshape(4, -1)[:, :24]), key
         elif key in ("swz_omega", "swz_grad_omega"):
@@ -257,6 +261,38 @@ def test_config_1_zero_background_flow_under_the_executed_reference():
     for _ in range(5):
         st = O.leapfrog_step(*st, 0.01, 3.0, 1.0, lambda xx, yy: [O.interpolate(xx, yy, g, DX, DX) for g in zero])
     assert np.array_equal(np.stack(st), fin)
+
+
+def test_oracle_qgsw_loop_with_packets_equals_the_executed_driver():
+    """qgsw_raytrace(32, 12, 2, 6000, 0, 0.5, 3, 1) executed (packets from the first flow step; ode23 = the restated controller,
+    a MATLAB builtin): the restated pieces chained the way the driver chains them -- qg_run frames, grid_U, odefun with the
+    bump of the copy beside it, ode23 over [0, dt] -- give the same packets at the start of steps 1..7, and the packet files
+    hold the initial frame (time -dt: packet_step_start = 0) and the wrapped frame of step 4"""
+    nx, Np, nif, U_g, f, Cg = 32, 12, 2.0, 0.5, 3.0, 1.0
+    K_d2 = f / Cg
+    xg = O.matlab_linspace(-L / 2, L / 2, nx); X, Y = np.meshgrid(xg, xg)
+    rs = O.matlab_rand_stream(146)
+    qk0 = O.g2k(O.initial_q(X, Y, U_g, K_d2, rs))
+    x, y, k, l = O.init_packets(Np, L, np.sqrt((nif ** 2 - 1) * f ** 2 / Cg ** 2), rs)
+    fl = O.grid_U(qk0, K_d2, K2, KX, KY)
+    U0 = np.sqrt((fl["u"] ** 2 + fl["v"] ** 2).max()); dt = 0.05 * (L / nx) / U0
+    assert "Time step: %f" % dt in str(R["qgsw_log"]) and "(0.500000,%f)" % U0 in str(R["qgsw_log"])
+    yv = np.concatenate([x, y, k, l])
+    ref = R["qgsw_packets_y"]
+    assert np.array_equal(yv, ref[0])
+    names = ("u", "v", "ux", "uy", "vx", "vy")
+    for step in range(1, ref.shape[0]):
+        bf1 = O.grid_U(O.qg_run(qk0, step - 1, dt, nx, L, K_d2, f, Cg), K_d2, K2, KX, KY)
+        bf2 = O.grid_U(O.qg_run(qk0, step, dt, nx, L, K_d2, f, Cg), K_d2, K2, KX, KY)
+        yv, _ = O.ode23(O.generate_raytracing_ode(bf1, bf2, Np, f, Cg, dt, L / nx), [0, dt], yv)
+        assert np.abs(yv - ref[step]).max() <= 1e-12, step            # qg_run vs the driver's in-place AB3: round-off only
+    t = R["qgsw_file_packet_time"]
+    assert t.size == 2 and t[0] == dt * (0 - 1) and abs(t[1] - 4 * dt) < 1e-15
+    px = R["qgsw_file_packet_x"].reshape(2, 2, Np)                     # two frames of an Np x 2 array, column-major
+    assert np.array_equal(px[0, 0], x) and np.array_equal(px[0, 1], y)
+    wrapped = np.mod(ref[4][: 2 * Np] + L / 2, L) - L / 2
+    assert np.array_equal(px[1].ravel(), wrapped)
+    assert np.array_equal(R["qgsw_file_packet_k"].reshape(2, 2, Np)[1].ravel(), ref[4][2 * Np:])
 
 
 def _swz_rhs(ev6, k, l, f, gH):
@@ -460,3 +496,19 @@ def test_gpu_config_1_script_right_hand_side_equals_the_nested_reference_functio
         e.set_packets(x, y, k, l)
         got = np.concatenate(e.rhs(0.0))
     assert rel(got, R["swz_odefun"]) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_qgsw_driver_with_packets_equals_the_executed_driver(tmp_path):
+    """drivers.qgsw_raytrace (device QG solver, both frames resident, ode23 with the stages on the device) in LAGRANGE6 mode:
+    the packets after six flow steps and the packet files it writes, against the executed qgsw_raytrace.m"""
+    import swraytracing_b200 as S
+    from swraytracing_b200 import drivers
+    ref = R["qgsw_packets_y"]
+    out = drivers.qgsw_raytrace(32, 12, 2, 6000, 0, 0.5, 3.0, 1.0, outdir=str(tmp_path), max_steps=6, mode=S.MODE_LAGRANGE6,
+                                log=lambda s: None)
+    assert np.abs(np.concatenate(out["packets"]) - ref[6]).max() <= 1e-9
+    for nm in ("packet_x", "packet_k", "packet_time"):
+        got = np.fromfile(tmp_path / f"{nm}.bin")
+        want = R["qgsw_file_" + nm]
+        assert got.size == want.size and np.abs(got - want).max() <= 1e-9, nm
