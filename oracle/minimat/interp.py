@@ -425,8 +425,12 @@ class Interp:
             seq = iter(it)
         else:
             seq = iter([it])
+        plain = fr.parent is None and fr.globals is None
         for v in seq:
-            self.setvar(fr, var, v)
+            if plain:
+                fr.vars[var] = v
+            else:
+                self.setvar(fr, var, v)
             try:
                 self.exec_block(body, fr)
             except _Break:
@@ -453,10 +457,7 @@ class Interp:
     def exec_assign(self, st, fr):
         lvs, rhs, show = st[1], st[2], st[3]
         if len(lvs) == 1:
-            vals = self.eval_multi(rhs, fr, 1)
-            if not vals:
-                raise MatlabError("the right-hand side of this assignment returns no value")
-            vals = vals[:1]
+            vals = [self.eval(rhs, fr)]
         else:
             vals = self.eval_multi(rhs, fr, len(lvs))
             if len(vals) < len(lvs):
@@ -466,7 +467,10 @@ class Interp:
                 continue
             name, acc = lv[1], lv[2]
             if not acc:
-                self.setvar(fr, name, v)
+                if fr.parent is None and fr.globals is None:
+                    fr.vars[name] = v
+                else:
+                    self.setvar(fr, name, v)
             elif len(acc) == 1 and acc[0][0] == "()" and len(acc[0][1]) == 1 and type(v) is float:
                 cur = self.getvar(fr, name)                # fast path: a(i) = scalar inside the array
                 done = False
@@ -640,6 +644,10 @@ class Interp:
         if k == "num":
             return e[1]
         if k == "id":
+            if fr.globals is None:                         # own variables win anyway: skip the general lookup
+                v = fr.vars.get(e[1])
+                if v is not None:
+                    return v
             v = self.getvar(fr, e[1])
             if v is not None:
                 return v

@@ -421,6 +421,16 @@ def _fold_shape(shape, k):
     return tuple(shape) + (1,) * (k - n)
 
 
+def _scalar(r, kind):
+    if kind == "f":
+        return float(r)
+    if kind == "c":
+        return complex(r)
+    if kind == "b":
+        return bool(r)
+    return simplify(np.array([[r]]))
+
+
 def index(a, subs):
     """a(subs...) for numeric / char / logical arrays"""
     is_str = type(a) is str
@@ -437,7 +447,7 @@ def index(a, subs):
             if j > x.size:
                 raise MatlabError(f"index {s!r} out of bounds (numel {x.size})")
             r = x.reshape(-1, order="F")[j - 1]
-            return chr(int(r)) if is_str else simplify(np.array([[r]]))
+            return chr(int(r)) if is_str else _scalar(r, x.dtype.kind)
         pos, shp = _index_vector(s, x.size)
         if pos.size and pos.max() >= x.size:
             raise MatlabError(f"index {int(pos.max()) + 1} out of bounds (numel {x.size})")
@@ -462,7 +472,7 @@ def index(a, subs):
         if i > shape[0] or j > shape[1]:
             raise MatlabError(f"index ({subs[0]!r},{subs[1]!r}) out of bounds ({shape[0]}x{shape[1]})")
         r = x[i - 1, j - 1]
-        return chr(int(r)) if is_str else simplify(np.array([[r]]))
+        return chr(int(r)) if is_str else _scalar(r, x.dtype.kind)
     xv = x.reshape(shape, order="F") if shape != x.shape else x
     pos = []
     for d, s in enumerate(subs):
