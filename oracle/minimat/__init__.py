@@ -33,6 +33,14 @@ Floating point: every arithmetic operation is IEEE double through numpy / libm, 
 may differ from MATLAB's (FFT, sum order of long vectors, ``pow``) are listed in ``builtins.py``.  The hot-path functions
 use none of them inside the per-packet arithmetic, and the tests hold results to 1e-12 / 1e-9, not to the bit.
 
+What it is not.  A subset, grown until the reference ran: double / complex / logical / char arrays, cells, structs and 2-D struct
+arrays, function handles, value classes (``classdef`` with inheritance; ``handle`` classes run with value semantics, which is all
+the shims need).  No integer or single classes, no sparse matrices, no ``try`` beyond catching the interpreter's own errors, no
+graphics (plotting calls are accepted and ignored), no ODE suite (``ode23`` is a MATLAB builtin, not reference code: where a
+driver needs it the test supplies the restated controller and says so), no ``eval`` / ``evalin`` / ``inputname``.  ``end`` inside
+``x(...)`` of a function CALL is not supported (only inside subscripts of variables), and command syntax follows MATLAB's rule
+for names that are not variables.  Anything outside the subset raises ``MatlabError`` / ``ParseError`` -- it never guesses.
+
 Layout: ``lexer.py`` (tokens, transpose-vs-quote, command syntax), ``parser.py`` (statements, functions with and without
 ``end``, nested functions, classdef), ``values.py`` (array semantics), ``interp.py`` (evaluator), ``builtins.py`` (library).
 """
