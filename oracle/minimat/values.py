@@ -261,6 +261,10 @@ def binop(op, a, b):
                     return a ** b
                 except (ZeroDivisionError, OverflowError):
                     pass
+    if op == "+" and ta is str and tb is str and len(a) != len(b):
+        # "text" + 'more' with a double-quoted (string) operand concatenates in MATLAB; this interpreter keeps both quote styles
+        # as character rows, so only the case that would otherwise be a size error (different lengths) is read that way
+        return a + b
     if op in _CMP:
         x, y = align(_num(a), _num(b))
         if op not in ("==", "~="):

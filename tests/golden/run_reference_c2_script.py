@@ -56,28 +56,89 @@ def pv_frame(nx, seed=2000, k_max=8, amp=1.6):
     return amp * q / np.abs(q).max() * 6.0
 
 
+def scratch_folder(ref, nx, q):
+    """a folder the reference's frozen-flow scripts can be started in: the run log they parse (its Resolution line set to
+    nx), frame 2000 of analysis/pv, links to the folders they addpath"""
+    tmp = Path(tempfile.mkdtemp(prefix="swrt_script_"))
+    for d in ("qg_flow_ray_trace", "rsw", "ray_trace_sw"):
+        os.symlink(ref / d, tmp / d)
+    logdir = tmp / "analysis" / "job-36976465" / "run-4"
+    logdir.mkdir(parents=True)
+    log = (ref / "analysis" / "job-36976465" / "run-4" / "run.log").read_text(errors="replace")
+    lognx, nsub = re.subn(r"Resolution: 256x256", f"Resolution: {nx}x{nx}", log, count=1)
+    assert nsub == 1
+    (logdir / "run.log").write_text(lognx)
+    with open(tmp / "analysis" / "pv.bin", "wb") as fh:           # frame 2000 of a frame-addressed real*8 stream (read_field.m:88)
+        fh.seek(8 * nx * nx * 1999)
+        fh.write(np.asfortranarray(q).tobytes(order="F"))
+    np.array([0.0]).tofile(tmp / "analysis" / "pv_time.bin")       # SW_zero_background_raytracing.m:25 reads it, never uses it
+    return tmp
+
+
+def run_c1_script(ref, out_path, nx=32, amp=2.0):
+    """BASELINE config 1's script, SW_zero_background_raytracing.m, executed unmodified and to the end on a 32^2 frame.  Its
+    integrator is MATLAB's ``ode23`` (``method = @ode23``, RelTol 1e-6 / AbsTol 1e-7 through ``odeset``, output at
+    ``dt*(0:Nsteps)``): a builtin, MathWorks code, not part of the reference -- served here by the restated controller
+    ``oracle.ode23`` (``odeset`` by a name/value struct).  Everything else is the reference's own code: parse_data, read_field,
+    grid_U (its six-argument call fails as in MATLAB: the script's line 26 is therefore given shear 0 through the same shim
+    the qgsw tests use), SpectralScheme, the packet ring, initialize_raytracing / odefun, the Omega series."""
+    from oracle import swrt_oracle as O
+    from oracle.minimat import MStruct, from_py
+    q = pv_frame(nx, amp=amp)
+    tmp = scratch_folder(ref, nx, q)
+    buf = io.StringIO()
+    I = Interp(cwd=str(tmp), out=buf)
+    I.path.insert(0, str(ref))
+    ref_grid_U = I.load_unit(str(ref / "qg_flow_ray_trace" / "grid_U.m")).main
+    I.overrides["grid_U"] = lambda I_, args, nargout, frame: I_.call_funcdef(ref_grid_U, list(args) + [0.0], nargout, frame)
+    I.overrides["odeset"] = lambda I_, args, nargout, frame: MStruct({args[i]: args[i + 1] for i in range(0, len(args), 2)})
+    I.overrides["hist"] = lambda I_, args, nargout, frame: None
+    stats = {}
+
+    def ode23_builtin(I_, args, nargout, frame):
+        fun, tspan, y0 = args[0], np.asarray(args[1]).ravel(), np.asarray(args[2]).ravel()
+        opts = args[3].f if len(args) > 3 else {}
+        Y, st = O.ode23(lambda t, yv: np.asarray(I_.call_handle(fun, [float(t), from_py(np.asarray(yv).reshape(-1, 1))], 1, frame)[0]).ravel(),
+                        tspan, y0, rtol=float(opts.get("RelTol", 1e-3)), atol=float(opts.get("AbsTol", 1e-6)))
+        stats.update(st)
+        return [from_py(tspan.reshape(-1, 1)), from_py(np.asfortranarray(Y))]
+    I.overrides["ode23"] = ode23_builtin
+    ws = Frame(None)
+    t0 = time.time()
+    I.run("SW_zero_background_raytracing", ws)
+    secs = time.time() - t0
+    I.close_all()
+    v = ws.vars
+    out = {"nx": np.float64(v["nx"]), "f": np.float64(v["f"]), "Cg": np.float64(v["Cg"]), "U0": np.float64(v["U0"]), "Fr": np.float64(v["Fr"]),
+           "dt": np.float64(v["dt"]), "Tend": np.float64(v["Tend"]), "Nsteps": np.float64(v["Nsteps"]), "q": q,
+           "x0": np.asarray(v["x"]), "k0": np.asarray(v["k"]), "t_hist": np.asarray(v["t_hist"]).ravel(),
+           "solver_x": np.asarray(v["solver_x"]), "solver_k": np.asarray(v["solver_k"]), "solver_error": np.asarray(v["solver_error"]),
+           "w": np.asarray(v["w"]), "ode23_nsteps": np.float64(stats["nsteps"]), "ode23_nfailed": np.float64(stats["nfailed"]),
+           "stdout": np.array(buf.getvalue())}
+    executed = sorted(p for p in I.units if str(Path(p).resolve()).startswith(str(ref)))
+    prov = {"made_by": "tests/golden/run_reference_c2_script.py --c1", "executor": "oracle/minimat", "seconds": round(secs, 1),
+            "ode23": "MATLAB builtin, served by oracle.ode23 (restated controller)",
+            "reference_files_executed": {str(Path(p).resolve().relative_to(ref)): hashlib.sha256(Path(p).read_bytes()).hexdigest() for p in executed}}
+    out["provenance"] = np.array(json.dumps(prov))
+    np.savez_compressed(out_path, **out)
+    print(f"run_c1_script: Nsteps = {int(v['Nsteps'])}, ode23 steps = {stats['nsteps']} (+{stats['nfailed']} failed), U0 = {float(v['U0']):.6f} in {secs:.0f} s -> {out_path}")
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=str(HERE / "reference_c2_script.npz"))
     ap.add_argument("--nx", type=int, default=NX, help="grid size written into the log (a small one makes a quick dry run)")
     ap.add_argument("--amp", type=float, default=0.67, help="PV amplitude (sets U0, hence Tend / dt)")
+    ap.add_argument("--c1", action="store_true", help="run config 1's script (SW_zero_background_raytracing.m, 32^2, half a minute) "
+                    "into reference_c1_script.npz instead")
     a = ap.parse_args(argv)
     nx = a.nx
     ref = Path(a.ref)
-    tmp = Path(tempfile.mkdtemp(prefix="swrt_c2_"))
-    for d in ("qg_flow_ray_trace", "rsw", "ray_trace_sw"):
-        os.symlink(ref / d, tmp / d)
-    logdir = tmp / "analysis" / "job-36976465" / "run-4"
-    logdir.mkdir(parents=True)
-    log = (ref / "analysis" / "job-36976465" / "run-4" / "run.log").read_text(errors="replace")
-    log128, nsub = re.subn(r"Resolution: 256x256", f"Resolution: {nx}x{nx}", log, count=1)
-    assert nsub == 1
-    (logdir / "run.log").write_text(log128)
+    if a.c1:
+        return run_c1_script(ref, a.out if a.out != str(HERE / "reference_c2_script.npz") else str(HERE / "reference_c1_script.npz"))
     q = pv_frame(nx, amp=a.amp)
-    with open(tmp / "analysis" / "pv.bin", "wb") as fh:           # frame 2000 of a frame-addressed real*8 stream (read_field.m:88)
-        fh.seek(8 * nx * nx * 1999)
-        fh.write(np.asfortranarray(q).tobytes(order="F"))
+    tmp = scratch_folder(ref, nx, q)
     buf = io.StringIO()
     I = Interp(cwd=str(tmp), out=buf)
     I.path.insert(0, str(ref))                                     # symplectic_full_fourier.m, SpectralScheme.m, ode_symplectic.m

@@ -94,3 +94,49 @@ def test_gpu_driver_follows_the_executed_script():
     ref = np.abs(D["solver_error"])
     assert 0.5 * ref.max() < e2.max() < 2.0 * ref.max()
     assert np.abs(e2[:200] - ref[:200]).max() < 1e-4                     # and early on the two still agree closely
+
+
+# ------------------------------------------------------------------------------------------------------------------ config 1
+# SW_zero_background_raytracing.m executed to the end on a 32^2 frame (tests/golden/run_reference_c2_script.py --c1 ->
+# reference_c1_script.npz).  Its integrator is MATLAB's ode23 (a builtin, not reference code: served by the restated controller,
+# with the script's own RelTol 1e-6 / AbsTol 1e-7 and dense output at dt*(0:Nsteps)); everything else -- parse_data, read_field,
+# SpectralScheme, the packet ring, initialize_raytracing / odefun, the Omega series -- is the reference's own code.
+C1 = np.load(GOLD / "reference_c1_script.npz")
+
+
+def test_config_1_script_ran_to_its_end():
+    prov = json.loads(str(C1["provenance"]))
+    assert {"SW_zero_background_raytracing.m", "SpectralScheme.m", "RaytracingScheme.m", "ray_trace_sw/interpolate.m",
+            "qg_flow_ray_trace/read_field.m", "qg_flow_ray_trace/grid_U.m"} <= set(prov["reference_files_executed"])
+    assert "ode23 with 1e-5 tol:" in str(C1["stdout"]) and "Nsteps =" in str(C1["stdout"])          # the script's own printing
+    n = int(C1["Nsteps"])
+    assert n == int(np.floor(float(C1["Tend"]) / float(C1["dt"]))) and float(C1["Tend"]) == 1 / (3.0 * float(C1["Fr"]) ** 2)
+    assert C1["solver_x"].shape == (n + 1, 2, 10) and C1["solver_error"].shape == (10, n + 1) and C1["w"].shape == (n + 1, 10)
+    assert int(C1["ode23_nsteps"]) > n                                    # RelTol 1e-6 takes several steps per output interval
+    if (REF / "ode_symplectic.m").exists():
+        import hashlib
+        for rel, sha in prov["reference_files_executed"].items():
+            assert hashlib.sha256((REF / rel).read_bytes()).hexdigest() == sha, rel
+
+
+def test_oracle_config_1_driver_gives_the_same_doubles_as_the_executed_script():
+    r = O.sw_zero_background_driver(C1["q"], 32, float(C1["f"]), float(C1["Cg"]))
+    assert (r["U0"], r["dt"], r["Nsteps"]) == (float(C1["U0"]), float(C1["dt"]), int(C1["Nsteps"]))
+    assert (r["stats"]["nsteps"], r["stats"]["nfailed"]) == (int(C1["ode23_nsteps"]), int(C1["ode23_nfailed"]))
+    assert np.array_equal(r["t_hist"], C1["t_hist"])
+    assert np.array_equal(r["solver_x"], C1["solver_x"]) and np.array_equal(r["solver_k"], C1["solver_k"])
+    assert np.array_equal(np.squeeze(r["solver_error"]), C1["solver_error"].T)
+
+
+@pytest.mark.gpu
+def test_gpu_config_1_driver_follows_the_executed_script():
+    """drivers.SW_zero_background_raytracing: ode23 with its stages, error norm and dense output on the device (LAGRANGE6 mode,
+    SWRT_FLAG_RHS_GH): the same accept / reject decisions as the executed script's run and its history within 1e-9"""
+    import swraytracing_b200 as S
+    from swraytracing_b200 import drivers
+    r = drivers.SW_zero_background_raytracing(C1["q"], nx=32, f=float(C1["f"]), Cg=float(C1["Cg"]), mode=S.MODE_LAGRANGE6)
+    assert r["Nsteps"] == int(C1["Nsteps"]) and abs(r["dt"] - float(C1["dt"])) < 1e-15
+    assert (r["stats"]["nsteps"], r["stats"]["nfailed"]) == (int(C1["ode23_nsteps"]), int(C1["ode23_nfailed"]))
+    assert np.abs(np.asarray(r["solver_x"]) - C1["solver_x"]).max() <= 1e-9
+    assert np.abs(np.asarray(r["solver_k"]) - C1["solver_k"]).max() <= 1e-9
+    assert np.abs(np.squeeze(np.asarray(r["solver_error"])) - C1["solver_error"].T).max() <= 1e-9
